@@ -1,0 +1,141 @@
+// Extractor core: owns the plan, the device workspace and the stream; enqueues the kernel sequence
+//   level0/resize x (L-1)  ->  FAST cells  ->  octree  ->  [blur on a 2nd stream]  ->  orient+describe  ->  grid
+// for a batch of equally sized images.  No host round trip inside the sequence.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include "fbe_internal.cuh"
+
+namespace fbe {
+
+static thread_local std::string t_err;
+void set_error(const std::string& s) { t_err = s; }
+const char* last_error() { return t_err.c_str(); }
+std::atomic<unsigned long long> g_launches{0};
+
+int ExtractorCore::init(const fbe_extractor_cfg& c) {
+    cfg = c;
+    if (cfg.nlevels < 1 || cfg.nlevels > FBE_MAX_LEVELS || cfg.nfeatures < 1 || !(cfg.scale_factor > 1.0f) ||
+        cfg.ini_th_fast < 0 || cfg.min_th_fast < 0 || cfg.ini_th_fast > 254 || cfg.min_th_fast > 254) {
+        set_error("invalid extractor configuration");
+        return FBE_E_INVALID;
+    }
+    if (cfg.max_batch < 1) cfg.max_batch = 1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        set_error("no CUDA device: this library has no CPU path");
+        return FBE_E_CUDA;
+    }
+    FBE_CUDA(cudaSetDevice(cfg.device));
+    compute_extractor_tables(cfg.nfeatures, cfg.scale_factor, cfg.nlevels, scale, inv_scale, sigma2, inv_sigma2, per_level, umax);
+    FBE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    FBE_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+    FBE_CUDA(cudaEventCreateWithFlags(&ev_pyr, cudaEventDisableTiming));
+    FBE_CUDA(cudaEventCreateWithFlags(&ev_blur, cudaEventDisableTiming));
+    std::memset(&ws, 0, sizeof(ws));
+    return FBE_OK;
+}
+
+int ExtractorCore::free_ws() {
+    cudaFree(ws.pyr); cudaFree(ws.blur); cudaFree(ws.cell_count); cudaFree(ws.slots); cudaFree(ws.keys);
+    cudaFree(ws.key_node); cudaFree(ws.oct_scratch); cudaFree(ws.sel); cudaFree(ws.level_n); cudaFree(ws.out_kps);
+    cudaFree(ws.out_desc); cudaFree(ws.out_n); cudaFree(ws.out_cell); cudaFree(ws.grid_start); cudaFree(ws.grid_items);
+    cudaFree(ws.status); cudaFree(dplan); cudaFree(dtab);
+    std::memset(&ws, 0, sizeof(ws));
+    dplan = nullptr; dtab = nullptr; have_ws = false;
+    return FBE_OK;
+}
+
+void ExtractorCore::destroy() {
+    cudaSetDevice(cfg.device);
+    if (stream) cudaStreamSynchronize(stream);
+    if (stream2) cudaStreamSynchronize(stream2);
+    free_ws();
+    cudaFree(d_in); d_in = nullptr;
+    if (h_pin) cudaFreeHost(h_pin);
+    h_pin = nullptr;
+    if (ev_pyr) cudaEventDestroy(ev_pyr);
+    if (ev_blur) cudaEventDestroy(ev_blur);
+    if (stream) cudaStreamDestroy(stream);
+    if (stream2) cudaStreamDestroy(stream2);
+    stream = stream2 = nullptr;
+}
+
+int ExtractorCore::set_grid(float min_x, float min_y, float inv_w, float inv_h, int gcols, int grows) {
+    if (gcols * grows > kMaxGridCells * 4) { set_error("grid too large"); return FBE_E_UNSUPPORTED; }
+    const bool realloc_grid = have_ws && gcols * grows != g_cols * g_rows;
+    g_min_x = min_x; g_min_y = min_y; g_inv_w = inv_w; g_inv_h = inv_h; g_cols = gcols; g_rows = grows;
+    if (have_ws) {
+        hplan.grid_min_x = min_x; hplan.grid_min_y = min_y; hplan.grid_inv_w = inv_w; hplan.grid_inv_h = inv_h;
+        hplan.grid_cols = gcols; hplan.grid_rows = grows;
+        FBE_CUDA(cudaMemcpyAsync(dplan, &hplan, sizeof(Plan), cudaMemcpyHostToDevice, stream));
+        FBE_CUDA(cudaStreamSynchronize(stream));
+        if (realloc_grid) {
+            cudaFree(ws.grid_start);
+            FBE_CUDA(cudaMalloc(&ws.grid_start, (size_t)cfg.max_batch * (gcols * grows + 1) * sizeof(int)));
+        }
+    }
+    return FBE_OK;
+}
+
+int ExtractorCore::ensure_plan(int rows, int cols) {
+    if (have_ws && rows == plan_rows && cols == plan_cols) return FBE_OK;
+    FBE_CUDA(cudaSetDevice(cfg.device));
+    if (have_ws) { FBE_CUDA(cudaStreamSynchronize(stream)); FBE_CUDA(cudaStreamSynchronize(stream2)); free_ws(); }
+    std::vector<ResizeTab> tabs;
+    int rc = build_plan(cfg, scale, inv_scale, per_level, umax, rows, cols, hplan, tabs);
+    if (rc != FBE_OK) return rc;
+    hplan.grid_min_x = g_min_x; hplan.grid_min_y = g_min_y; hplan.grid_inv_w = g_inv_w; hplan.grid_inv_h = g_inv_h;
+    hplan.grid_cols = g_cols; hplan.grid_rows = g_rows;
+    const size_t B = (size_t)cfg.max_batch;
+    FBE_CUDA(cudaMalloc(&dplan, sizeof(Plan)));
+    FBE_CUDA(cudaMemcpy(dplan, &hplan, sizeof(Plan), cudaMemcpyHostToDevice));
+    FBE_CUDA(cudaMalloc(&dtab, std::max<size_t>(tabs.size(), 1) * sizeof(ResizeTab)));
+    if (!tabs.empty()) FBE_CUDA(cudaMemcpy(dtab, tabs.data(), tabs.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
+    FBE_CUDA(cudaMalloc(&ws.pyr, B * hplan.pyr_bytes));
+    FBE_CUDA(cudaMalloc(&ws.blur, B * hplan.pyr_bytes));
+    FBE_CUDA(cudaMemset(ws.blur, 0, B * hplan.pyr_bytes));
+    FBE_CUDA(cudaMalloc(&ws.cell_count, B * hplan.ncells_total * sizeof(int)));
+    FBE_CUDA(cudaMalloc(&ws.slots, B * hplan.slots_total * sizeof(uint32_t)));
+    FBE_CUDA(cudaMalloc(&ws.keys, B * hplan.slots_total * sizeof(uint32_t)));
+    FBE_CUDA(cudaMalloc(&ws.key_node, B * hplan.slots_total * sizeof(uint32_t)));
+    ws.oct_scratch_bytes = (octree_scratch_bytes(hplan) + 255) & ~(size_t)255;
+    FBE_CUDA(cudaMalloc(&ws.oct_scratch, B * ws.oct_scratch_bytes));
+    FBE_CUDA(cudaMalloc(&ws.sel, B * hplan.kp_cap_total * sizeof(uint32_t)));
+    FBE_CUDA(cudaMalloc(&ws.level_n, B * FBE_MAX_LEVELS * sizeof(int)));
+    FBE_CUDA(cudaMemset(ws.level_n, 0, B * FBE_MAX_LEVELS * sizeof(int)));
+    FBE_CUDA(cudaMalloc(&ws.out_kps, B * hplan.kp_cap_total * sizeof(fbe_keypoint)));
+    FBE_CUDA(cudaMalloc(&ws.out_desc, B * hplan.kp_cap_total * 32));
+    FBE_CUDA(cudaMalloc(&ws.out_n, B * sizeof(int)));
+    FBE_CUDA(cudaMalloc(&ws.out_cell, B * hplan.kp_cap_total * sizeof(int)));
+    const int gcells = std::max(g_cols * g_rows, kMaxGridCells);
+    FBE_CUDA(cudaMalloc(&ws.grid_start, B * (gcells + 1) * sizeof(int)));
+    FBE_CUDA(cudaMalloc(&ws.grid_items, B * hplan.kp_cap_total * sizeof(int)));
+    FBE_CUDA(cudaMalloc(&ws.status, B * sizeof(int)));
+    FBE_CUDA(cudaMemset(ws.status, 0, B * sizeof(int)));
+    plan_rows = rows; plan_cols = cols; have_ws = true;
+    return FBE_OK;
+}
+
+int ExtractorCore::run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, int nimg, int rows, int cols) {
+    if (nimg < 1 || nimg > cfg.max_batch) { set_error("batch larger than max_batch"); return FBE_E_INVALID; }
+    FBE_CUDA(cudaSetDevice(cfg.device));
+    int rc = ensure_plan(rows, cols);
+    if (rc != FBE_OK) return rc;
+    ws.in = d_imgs; ws.in_pitch = pitch; ws.in_slot_stride = slot_stride;
+    if ((rc = launch_pyramid(hplan, dplan, ws, dtab, nimg, stream)) != FBE_OK) return rc;
+    // blur depends only on the pyramid: run it on the side stream while FAST + octree proceed
+    FBE_CUDA(cudaEventRecord(ev_pyr, stream));
+    FBE_CUDA(cudaStreamWaitEvent(stream2, ev_pyr, 0));
+    if ((rc = launch_blur(hplan, dplan, ws, nimg, stream2)) != FBE_OK) return rc;
+    FBE_CUDA(cudaEventRecord(ev_blur, stream2));
+    if ((rc = launch_fast_cells(hplan, dplan, ws, nimg, stream)) != FBE_OK) return rc;
+    if ((rc = launch_octree(hplan, dplan, ws, nimg, stream)) != FBE_OK) return rc;
+    FBE_CUDA(cudaStreamWaitEvent(stream, ev_blur, 0));
+    if ((rc = launch_describe(hplan, dplan, ws, nimg, stream)) != FBE_OK) return rc;
+    if ((rc = launch_grid(hplan, dplan, ws, nimg, stream)) != FBE_OK) return rc;
+    last_nimg = nimg;
+    return FBE_OK;
+}
+
+}  // namespace fbe

@@ -1,0 +1,162 @@
+// Internal declarations shared by the sm_100a kernels and the C-ABI glue.  Not installed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <string>
+#include <vector>
+#include "../../include/fbe_cabi.h"
+
+namespace fbe {
+
+constexpr int kEdge = 19;        // EDGE_THRESHOLD (src/ORBextractor.cc:74): frame around every pyramid level
+constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE (:73)
+constexpr int kPatch = 31;       // PATCH_SIZE (:72)
+constexpr int kMaxDim = 4095;    // x,y packed in 12 bits each
+constexpr int kMaxGridCells = 64 * 48;
+
+// packed candidate / key: score[31:24] | y[23:12] | x[11:0], level pixel coordinates
+__host__ __device__ inline uint32_t pack_key(int x, int y, int s) { return ((uint32_t)s << 24) | ((uint32_t)y << 12) | (uint32_t)x; }
+__host__ __device__ inline int key_x(uint32_t k) { return (int)(k & 0xFFFu); }
+__host__ __device__ inline int key_y(uint32_t k) { return (int)((k >> 12) & 0xFFFu); }
+__host__ __device__ inline int key_s(uint32_t k) { return (int)(k >> 24); }
+
+// Geometry of one pyramid level for the current image size.  All offsets are per image slot.
+struct LevelGeom {
+    int w, h;            // level size (ROI)
+    int pitch;           // bytes per padded row, multiple of 16
+    int ph;              // padded rows = h + 38
+    int img_off;         // byte offset of the padded level inside the per-slot pyramid slab (256-aligned)
+    int ncols, nrows;    // FAST cell grid (src/ORBextractor.cc:781-787)
+    int wcell, hcell;
+    int cell_base;       // first cell of this level in the per-slot cell arrays
+    int cell_cap;        // candidate slots per cell = ceil(wcell/2)*ceil(hcell/2) (NMS survivors are never adjacent)
+    int slot_base;       // first slot (u32 units) of this level in the per-slot slot array
+    int key_cap;         // capacity of the compacted key array of this level ( = ncells*cell_cap )
+    int nfeat;           // mnFeaturesPerLevel[level]
+    int nini;            // octree roots
+    float hx;            // root width
+    int node_cap;        // live-node capacity of the octree
+    int node_base;       // first node (in node-scratch units) of this level
+    int kp_cap;          // selected keypoints capacity
+    int kp_base;         // offset of this level in the per-slot selected-key array
+    int tabx_off, taby_off;   // offsets (in entries) into the resize tables (levels >= 1)
+    float scale;         // mvScaleFactor[level]
+    float patch_size;    // (float)(int)(31*scale)
+};
+
+struct Plan {
+    int nlevels;
+    int rows, cols;
+    int ini_th, min_th;
+    int ncells_total;
+    int slots_total;
+    int kp_cap_total;
+    int nodes_total;
+    int pyr_bytes;       // per-slot pyramid slab size
+    int max_cell_w, max_cell_h;
+    int umax[16];
+    // grid-assignment parameters applied to the final (scaled) keypoints
+    float grid_min_x, grid_min_y, grid_inv_w, grid_inv_h;
+    int grid_cols, grid_rows;
+    LevelGeom lv[FBE_MAX_LEVELS];
+};
+
+// Per-call device workspace pointers (all arrays are [max_batch] slabs, slot-major).
+struct Workspace {
+    const uint8_t* in;     // [B][rows][in_pitch] source images
+    int in_pitch, in_slot_stride;
+    uint8_t* pyr;          // [B][pyr_bytes]
+    uint8_t* blur;         // [B][pyr_bytes]  (same geometry as pyr; only the ROI is written)
+    int* cell_count;       // [B][ncells_total]
+    uint32_t* slots;       // [B][slots_total]
+    uint32_t* keys;        // [B][slots_total]   compacted per level, level region = slot_base..
+    uint32_t* key_node;    // [B][slots_total]
+    uint8_t* oct_scratch;  // [B][oct_scratch_bytes]
+    size_t oct_scratch_bytes;   // per slot
+    uint32_t* sel;         // [B][kp_cap_total] selected keys per level in output order
+    int* level_n;          // [B][FBE_MAX_LEVELS] keypoints per level
+    fbe_keypoint* out_kps; // [B][kp_cap_total]
+    uint8_t* out_desc;     // [B][kp_cap_total][32]
+    int* out_n;            // [B]
+    int* out_cell;         // [B][kp_cap_total] grid cell id per keypoint or -1
+    int* grid_start;       // [B][gcells+1]
+    int* grid_items;       // [B][kp_cap_total]
+    int* status;           // [B] error flags raised by kernels (capacity overflow ...)
+};
+
+struct ResizeTab { int ofs; short a0, a1; };   // 8 bytes per padded coordinate
+
+void set_error(const std::string& s);
+const char* last_error();
+extern std::atomic<unsigned long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+#define FBE_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            ::fbe::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
+            return FBE_E_CUDA;                                                                           \
+        }                                                                                                \
+    } while (0)
+
+// ---- kernel launchers (each enqueues on `st`) ---------------------------------------------------
+int launch_pyramid(const Plan& hp, const Plan* dp, const Workspace& ws, const ResizeTab* d_tab, int nimg, cudaStream_t st);
+int launch_fast_cells(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
+int launch_octree(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
+int launch_blur(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
+int launch_describe(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
+int launch_grid(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
+size_t octree_scratch_bytes(const Plan& hp);
+// stand-alone octree on caller candidates (device arrays): keys packed with level coordinates (= relative + 16)
+int launch_octree_debug(const uint32_t* d_keys, uint32_t* d_knode, int nk, int nini, float hx, int H, int nfeat, int cap,
+                        uint8_t* d_scratch, uint32_t* d_sel_idx, int* d_n, cudaStream_t st);
+size_t octree_debug_scratch_bytes(int cap);
+
+// stand-alone grid build on arbitrary keypoint arrays (device pointers), used by the matchers
+int launch_grid_build(const fbe_keypoint* d_kps, const int* d_n, int n_stride, int nframes, float min_x, float min_y,
+                      float inv_w, float inv_h, int gcols, int grows, int* d_cell_of, int* d_start, int* d_items,
+                      cudaStream_t st);
+
+// ---- extractor core: plan + workspace + run ------------------------------------------------------
+struct ExtractorCore {
+    fbe_extractor_cfg cfg;
+    std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+    std::vector<int> per_level;
+    int umax[16];
+    Plan hplan;            // valid when plan_rows/cols set
+    Plan* dplan = nullptr;
+    ResizeTab* dtab = nullptr;
+    int plan_rows = 0, plan_cols = 0;
+    Workspace ws;
+    uint8_t* d_in = nullptr;      // staging for host-API calls
+    size_t d_in_bytes = 0;
+    uint8_t* h_pin = nullptr;     // pinned staging
+    size_t h_pin_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;   // blur runs beside FAST/octree
+    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
+    bool have_ws = false;
+    int last_nimg = 0;
+    // grid parameters (0 cols = grid disabled)
+    float g_min_x = 0, g_min_y = 0, g_inv_w = 0, g_inv_h = 0;
+    int g_cols = 0, g_rows = 0;
+
+    int init(const fbe_extractor_cfg& c);
+    void destroy();
+    int ensure_plan(int rows, int cols);
+    int set_grid(float min_x, float min_y, float inv_w, float inv_h, int gcols, int grows);
+    // images already on the device: [nimg][rows][pitch]
+    int run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, int nimg, int rows, int cols);
+    int free_ws();
+};
+
+void compute_extractor_tables(int nfeatures, float scale_factor, int nlevels, std::vector<float>& scale,
+                              std::vector<float>& inv_scale, std::vector<float>& sigma2, std::vector<float>& inv_sigma2,
+                              std::vector<int>& per_level, int umax[16]);
+int build_plan(const fbe_extractor_cfg& cfg, const std::vector<float>& scale, const std::vector<float>& inv_scale,
+               const std::vector<int>& per_level, const int umax[16], int rows, int cols, Plan& p,
+               std::vector<ResizeTab>& tabs);
+
+}  // namespace fbe

@@ -1,0 +1,386 @@
+// DistributeOctTree (src/ORBextractor.cc:539-763, DivideNode :481-537) as a round-parallel replay.
+//
+// One CTA per (image, level).  The reference walks a std::list and splits nodes one at a time; the selection it
+// produces depends on list order, on the order children are created and on a sort by (size, node address).  Two facts
+// make an exact parallel replay possible:
+//   1. after the roots the only list insertion is push_front, so the list is always "live nodes by creation sequence,
+//      newest first".  We keep the live nodes in an ARRAY in ascending creation order (array index == rank); the list
+//      front is the last array element.
+//   2. within one sweep (or one refinement round) the nodes to split are fixed up front and their splits are mutually
+//      independent; only the ORDER of processing matters (it numbers the children, and in refinement it decides where
+//      the "stop at N" cut falls).  Sweep order = list order = descending array index.  Refinement order = (size,
+//      creation sequence) descending -- the canonical reading of the reference's sort over (size, pointer) pairs with a
+//      monotonic allocator (the oracle's verbatim reference build runs on a bump arena for the same reason).
+// Keys never move: each key carries the array index of its node, child sizes come from shared-memory atomics, and
+// "first key in candidate order with the maximum response" is an atomicMax over (score, -candidate index).
+#include <algorithm>
+#include "fbe_internal.cuh"
+
+namespace fbe {
+
+constexpr int kOctThreads = 512;
+
+struct __align__(16) OctNode { short x0, y0, x1, y1; int cnt; int nomore; };   // bounds relative to (16,16): UL=(x0,y0) BR=(x1,y1)
+
+__device__ __forceinline__ int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+struct BlockScan {
+    int* warp_sums;   // [kOctThreads/32 + 1] shared
+    // exclusive scan of one int per thread; returns exclusive prefix, writes block total to *total
+    __device__ __forceinline__ int exclusive(int v, int& total) {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        __syncthreads();                       // protect warp_sums from the previous use
+        if (lane == 31) warp_sums[wid] = inc;
+        __syncthreads();
+        int before = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kOctThreads / 32; ++w) {
+            int c = warp_sums[w];
+            if (w < wid) before += c;
+            tot += c;
+        }
+        total = tot;
+        return before + inc - v;
+    }
+};
+
+// quadrant of a key inside a node: n1=0 (left,top) n2=1 (right,top) n3=2 (left,bottom) n4=3 (right,bottom).
+// The reference compares float key coordinates with int bounds (:515-525); coordinates are integral here.
+__device__ __forceinline__ int quadrant(uint32_t key, const OctNode& nd) {
+    const int x = key_x(key) - 16, y = key_y(key) - 16;
+    const int mx = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1);   // UL.x + ceil((UR.x-UL.x)/2)
+    const int my = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
+    return (x < mx ? 0 : 1) + (y < my ? 0 : 2);
+}
+
+__device__ __forceinline__ int nonempty4(const int* c4) { return (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0); }
+
+// The replay proper.  keys/knode: nk entries.  Returns the number of live nodes; `cur` points at the final array.
+// All pointers may be shared or global memory.
+__device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode, int nk, int nini, float hx, int H,
+                             int N, int cap, OctNode* nodesA, OctNode* nodesB, int* cnt4, int* newidx, int* splitf,
+                             int* order, unsigned long long* sortbuf, BlockScan& bs, int* s_ctl, OctNode** out_nodes) {
+    const int tid = threadIdx.x;
+    OctNode* cur = nodesA;
+    OctNode* nxt = nodesB;
+
+    // ---- roots (:543-585) -------------------------------------------------------------------------------------
+    for (int r = tid; r < nini; r += kOctThreads) cnt4[r] = 0;
+    __syncthreads();
+    for (int k = tid; k < nk; k += kOctThreads) {
+        const int x = key_x(keys[k]) - 16;
+        int r = (int)__fdiv_rn((float)x, hx);         // vpIniNodes[kp.pt.x/hX]
+        r = min(max(r, 0), nini - 1);
+        knode[k] = (uint32_t)r;
+        atomicAdd(&cnt4[r], 1);
+    }
+    __syncthreads();
+    // array position of root r = number of non-empty roots with a larger index (root 0 is the list front = last)
+    for (int r = tid; r < nini; r += kOctThreads) {
+        int pos = 0;
+        for (int r2 = r + 1; r2 < nini; ++r2) pos += cnt4[r2] > 0;
+        newidx[r] = pos;
+        if (cnt4[r] > 0) {
+            OctNode nd;
+            nd.x0 = (short)(int)__fmul_rn(hx, (float)r);
+            nd.x1 = (short)(int)__fmul_rn(hx, (float)(r + 1));
+            nd.y0 = 0; nd.y1 = (short)H;
+            nd.cnt = cnt4[r];
+            nd.nomore = cnt4[r] == 1;
+            cur[pos] = nd;
+        }
+    }
+    if (tid == 0) {
+        int n = 0;
+        for (int r = 0; r < nini; ++r) n += cnt4[r] > 0;
+        s_ctl[0] = n;
+    }
+    __syncthreads();
+    for (int k = tid; k < nk; k += kOctThreads) knode[k] = (uint32_t)newidx[knode[k]];
+    int n = s_ctl[0];
+    __syncthreads();
+
+    bool refine = false;
+    while (true) {
+        const int prev = n;
+        // ---- child sizes of every splittable node ------------------------------------------------------------
+        for (int i = tid; i < 4 * n; i += kOctThreads) cnt4[i] = 0;
+        __syncthreads();
+        for (int k = tid; k < nk; k += kOctThreads) {
+            const int i = (int)knode[k];
+            const OctNode nd = cur[i];
+            if (!nd.nomore) atomicAdd(&cnt4[4 * i + quadrant(keys[k], nd)], 1);
+        }
+        __syncthreads();
+
+        // ---- processing order of the splittable nodes --------------------------------------------------------
+        int m = 0;   // number of splittable nodes
+        if (!refine) {
+            // sweep: list order = descending array index
+            for (int base = 0; base < n; base += kOctThreads) {
+                const int j = base + tid;            // j-th node from the back
+                const int i = n - 1 - j;
+                const int f = (j < n) && !cur[i].nomore;
+                int tot;
+                const int ex = bs.exclusive(f, tot);
+                if (f) order[m + ex] = i;
+                m += tot;
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += kOctThreads) splitf[i] = !cur[i].nomore;
+        } else {
+            // refinement: (size, creation rank) descending; stop once the live count reaches N (:685-732)
+            for (int base = 0; base < n; base += kOctThreads) {
+                const int i = base + tid;
+                const int f = (i < n) && !cur[i].nomore;
+                int tot;
+                const int ex = bs.exclusive(f, tot);
+                if (f) sortbuf[m + ex] = ((unsigned long long)(unsigned)cur[i].cnt << 32) | (unsigned)i;
+                m += tot;
+            }
+            const int mp = pow2_ceil(max(m, 1));
+            for (int j = m + tid; j < mp; j += kOctThreads) sortbuf[j] = 0ull;
+            __syncthreads();
+            for (int k2 = 2; k2 <= mp; k2 <<= 1) {
+                for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                    for (int t = tid; t < mp; t += kOctThreads) {
+                        const int p = t ^ j2;
+                        if (p > t) {
+                            const unsigned long long a = sortbuf[t], c = sortbuf[p];
+                            const bool desc = (t & k2) == 0;      // descending overall
+                            if (desc ? (a < c) : (a > c)) { sortbuf[t] = c; sortbuf[p] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int i = tid; i < n; i += kOctThreads) splitf[i] = 0;
+            __syncthreads();
+            // running live count after each split in order; everything up to and including the first split that
+            // reaches N is performed
+            int carry = 0;
+            if (tid == 0) s_ctl[1] = m;          // cut position (exclusive end of performed splits)
+            __syncthreads();
+            for (int base = 0; base < m; base += kOctThreads) {
+                const int j = base + tid;
+                int gain = 0, i = 0;
+                if (j < m) { i = (int)(sortbuf[j] & 0xffffffffu); gain = nonempty4(cnt4 + 4 * i) - 1; }
+                int tot;
+                const int ex = bs.exclusive(gain, tot);
+                const int live_before = n + carry + ex;          // live count before this split
+                if (j < m) {
+                    order[j] = i;
+                    if (live_before < N) {
+                        splitf[i] = 1;
+                        if (live_before + gain >= N) atomicMin(&s_ctl[1], j + 1);
+                    }
+                }
+                carry += tot;
+            }
+            __syncthreads();
+            m = s_ctl[1];     // only the first m entries of `order` are split (prefix property of the cut)
+            __syncthreads();
+        }
+
+        // ---- new array = unsplit nodes (ascending) ++ children in creation order ------------------------------
+        int nsurv = 0;
+        for (int base = 0; base < n; base += kOctThreads) {
+            const int i = base + tid;
+            const int f = (i < n) && !splitf[i];
+            int tot;
+            const int ex = bs.exclusive(f, tot);
+            if (f) { newidx[i] = nsurv + ex; nxt[nsurv + ex] = cur[i]; }
+            nsurv += tot;
+        }
+        int nchild = 0, nexp_local = 0;
+        for (int base = 0; base < m; base += kOctThreads) {
+            const int j = base + tid;
+            int i = 0, c = 0;
+            if (j < m) { i = order[j]; c = nonempty4(cnt4 + 4 * i); }
+            int tot;
+            const int ex = bs.exclusive(c, tot);
+            if (j < m) {
+                int pos = nsurv + nchild + ex;
+                newidx[i] = pos;                         // child base of a split node
+                if (pos + c <= cap) {
+                    const OctNode nd = cur[i];
+                    const int mx = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), my = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int cq = cnt4[4 * i + q];
+                        if (cq > 0) {
+                            OctNode ch;
+                            ch.x0 = (q & 1) ? (short)mx : nd.x0;  ch.x1 = (q & 1) ? nd.x1 : (short)mx;
+                            ch.y0 = (q & 2) ? (short)my : nd.y0;  ch.y1 = (q & 2) ? nd.y1 : (short)my;
+                            ch.cnt = cq; ch.nomore = cq == 1;
+                            nxt[pos++] = ch;
+                            nexp_local += cq > 1;
+                        }
+                    }
+                }
+            }
+            nchild += tot;
+        }
+        const int n2 = nsurv + nchild;
+        if (tid == 0) s_ctl[2] = 0;
+        __syncthreads();
+        if (nexp_local) atomicAdd(&s_ctl[2], nexp_local);
+        // ---- re-home the keys ----------------------------------------------------------------------------------
+        if (n2 <= cap) {
+            for (int k = tid; k < nk; k += kOctThreads) {
+                const int i = (int)knode[k];
+                int dst = newidx[i];
+                if (splitf[i]) {
+                    const int q = quadrant(keys[k], cur[i]);
+                    const int* c4 = cnt4 + 4 * i;
+                    dst += (q > 0 && c4[0] > 0) + (q > 1 && c4[1] > 0) + (q > 2 && c4[2] > 0);
+                }
+                knode[k] = (uint32_t)dst;
+            }
+        }
+        __syncthreads();
+        const int nexp = s_ctl[2];
+        __syncthreads();
+        OctNode* t = cur; cur = nxt; nxt = t;
+        if (n2 > cap) { n = -1; break; }          // cannot happen (see DESIGN.md bound); guarded anyway
+        n = n2;
+        if (n >= N || n == prev) break;
+        if (!refine && n + 3 * nexp > N) refine = true;
+    }
+    *out_nodes = cur;
+    return n;
+}
+
+__global__ void __launch_bounds__(kOctThreads) k_octree(const Plan* __restrict__ plan, Workspace ws, int use_smem) {
+    extern __shared__ __align__(16) uint8_t dyn[];
+    __shared__ int s_warp[kOctThreads / 32 + 1];
+    __shared__ int s_ctl[4];
+    const int tid = threadIdx.x;
+    const int l = blockIdx.x, b = blockIdx.y;
+    const LevelGeom g = plan->lv[l];
+    BlockScan bs{s_warp};
+
+    uint32_t* keys = ws.keys + (size_t)b * plan->slots_total + g.slot_base;
+    uint32_t* knode = ws.key_node + (size_t)b * plan->slots_total + g.slot_base;
+    const uint32_t* slots = ws.slots + (size_t)b * plan->slots_total + g.slot_base;
+    const int* ccount = ws.cell_count + (size_t)b * plan->ncells_total + g.cell_base;
+    const int ncells = g.ncols * g.nrows;
+
+    // ---- vToDistributeKeys: concatenate the cells in row-major order ----------------------------------------------
+    int nk = 0;
+    for (int base = 0; base < ncells; base += kOctThreads) {
+        const int c = base + tid;
+        const int cnt = c < ncells ? ccount[c] : 0;
+        int tot;
+        const int ex = bs.exclusive(cnt, tot);
+        const uint32_t* src = slots + (size_t)c * g.cell_cap;
+        for (int i = 0; i < cnt; ++i) keys[nk + ex + i] = src[i];
+        nk += tot;
+    }
+    __syncthreads();
+
+    // ---- scratch carve-up -----------------------------------------------------------------------------------------
+    const int cap = g.node_cap;
+    // global fallback: level l starts at node_base*80 + l*128 (oct_level_bytes(cap) <= 76*cap + 64)
+    uint8_t* base_ptr = use_smem ? dyn : ws.oct_scratch + (size_t)b * ws.oct_scratch_bytes + (size_t)g.node_base * 80 + (size_t)l * 128;
+    OctNode* nodesA = reinterpret_cast<OctNode*>(base_ptr);
+    OctNode* nodesB = nodesA + cap;
+    unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(nodesB + cap);
+    int* cnt4 = reinterpret_cast<int*>(sortbuf + pow2_ceil(cap));
+    int* newidx = cnt4 + 4 * cap;
+    int* splitf = newidx + cap;
+    int* order = splitf + cap;
+
+    const int W = g.w - 2 * kEdge + 6, H = g.h - 2 * kEdge + 6;   // maxBorder - minBorder
+    (void)W;
+    OctNode* fin = nullptr;
+    int n = octree_replay(keys, knode, nk, g.nini, g.hx, H, g.nfeat, cap, nodesA, nodesB, cnt4, newidx, splitf, order,
+                          sortbuf, bs, s_ctl, &fin);
+    int* level_n = ws.level_n + (size_t)b * FBE_MAX_LEVELS + l;
+    if (n < 0) {
+        if (tid == 0) { *level_n = 0; atomicOr(ws.status + b, 1); }
+        return;
+    }
+    // ---- best key of every live node (:742-760): max response, first in candidate order -----------------------------
+    unsigned* best = reinterpret_cast<unsigned*>(cnt4);
+    for (int i = tid; i < n; i += kOctThreads) best[i] = 0u;
+    __syncthreads();
+    for (int k = tid; k < nk; k += kOctThreads)
+        atomicMax(&best[knode[k]], ((unsigned)key_s(keys[k]) << 24) | (0xFFFFFFu - (unsigned)k));
+    __syncthreads();
+    uint32_t* sel = ws.sel + (size_t)b * plan->kp_cap_total + g.kp_base;
+    for (int j = tid; j < n && j < g.kp_cap; j += kOctThreads) {
+        const unsigned v = best[n - 1 - j];                  // list front = last array element
+        sel[j] = keys[0xFFFFFFu - (v & 0xFFFFFFu)];
+    }
+    if (tid == 0) *level_n = min(n, g.kp_cap);
+}
+
+// Stand-alone entry used by fbe_debug_octree (adversarial parity tests): same replay, scratch in global memory,
+// output = selected candidate INDICES in reference output order.
+__global__ void __launch_bounds__(kOctThreads) k_octree_debug(const uint32_t* keys, uint32_t* knode, int nk, int nini, float hx,
+                                                              int H, int N, int cap, uint8_t* scratch, uint32_t* sel_idx, int* n_out) {
+    __shared__ int s_warp[kOctThreads / 32 + 1];
+    __shared__ int s_ctl[4];
+    const int tid = threadIdx.x;
+    BlockScan bs{s_warp};
+    OctNode* nodesA = reinterpret_cast<OctNode*>(scratch);
+    OctNode* nodesB = nodesA + cap;
+    unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(nodesB + cap);
+    int* cnt4 = reinterpret_cast<int*>(sortbuf + pow2_ceil(cap));
+    int* newidx = cnt4 + 4 * cap;
+    int* splitf = newidx + cap;
+    int* order = splitf + cap;
+    OctNode* fin = nullptr;
+    int n = octree_replay(keys, knode, nk, nini, hx, H, N, cap, nodesA, nodesB, cnt4, newidx, splitf, order, sortbuf, bs, s_ctl, &fin);
+    if (n < 0) { if (tid == 0) *n_out = -1; return; }
+    unsigned* best = reinterpret_cast<unsigned*>(cnt4);
+    for (int i = tid; i < n; i += kOctThreads) best[i] = 0u;
+    __syncthreads();
+    for (int k = tid; k < nk; k += kOctThreads)
+        atomicMax(&best[knode[k]], ((unsigned)key_s(keys[k]) << 24) | (0xFFFFFFu - (unsigned)k));
+    __syncthreads();
+    for (int j = tid; j < n; j += kOctThreads) sel_idx[j] = 0xFFFFFFu - (best[n - 1 - j] & 0xFFFFFFu);
+    if (tid == 0) *n_out = n;
+}
+
+static size_t oct_level_bytes(int cap) {
+    int p2 = 1;
+    while (p2 < cap) p2 <<= 1;
+    return (size_t)cap * (16 + 16 + 16 + 4 + 4 + 4) + (size_t)p2 * 8 + 64;
+}
+
+size_t octree_scratch_bytes(const Plan& hp) {
+    return (size_t)hp.nodes_total * 80 + (size_t)hp.nlevels * 128 + 1024;
+}
+
+size_t octree_debug_scratch_bytes(int cap) { return oct_level_bytes(cap); }
+
+int launch_octree_debug(const uint32_t* d_keys, uint32_t* d_knode, int nk, int nini, float hx, int H, int nfeat, int cap,
+                        uint8_t* d_scratch, uint32_t* d_sel_idx, int* d_n, cudaStream_t st) {
+    k_octree_debug<<<1, kOctThreads, 0, st>>>(d_keys, d_knode, nk, nini, hx, H, nfeat, cap, d_scratch, d_sel_idx, d_n);
+    count_launch();
+    FBE_CUDA(cudaGetLastError());
+    return FBE_OK;
+}
+
+int launch_octree(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st) {
+    size_t need = 0;
+    for (int l = 0; l < hp.nlevels; ++l) need = std::max(need, oct_level_bytes(hp.lv[l].node_cap));
+    const int use_smem = need <= 160 * 1024;
+    size_t smem = use_smem ? need : 0;
+    if (smem > 48 * 1024) FBE_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(hp.nlevels, nimg);
+    k_octree<<<grid, kOctThreads, smem, st>>>(dp, ws, use_smem);
+    count_launch();
+    FBE_CUDA(cudaGetLastError());
+    return FBE_OK;
+}
+
+}  // namespace fbe

@@ -1,0 +1,235 @@
+/*
+ * fbe_cabi.h -- C ABI of the B200-native ORB front end (extract + grid + match).
+ *
+ * This is the drop-in boundary: plain C, POD arguments, no torch / OpenCV / C++ types.  Every entry point
+ * replaces one interface of the reference (file:line relative to the FishBirdEyeVisualSLAM checkout) and is what
+ * the drop-in host classes in fishbirdeyevisualslam_b200/host/ (ORBextractor / ORBmatcher with the reference's
+ * signatures) and the Python mirror (fishbirdeyevisualslam_b200/*.py, ctypes) bind.
+ *
+ * Conventions
+ *   - every function returns 0 (FBE_OK) or a negative FBE_E_* code; it never throws and never aborts;
+ *   - there is NO CPU fallback: without a CUDA device (or without the sm_100a image) creation fails with
+ *     FBE_E_CUDA and nothing else is callable;
+ *   - handles are not re-entrant per instance, distinct handles may be used from distinct threads
+ *     (each owns its stream and workspace), mirroring the reference (SURVEY 8b "Threading");
+ *   - "device-resident" functions (*_dev) take/return device pointers and only enqueue work on the handle's
+ *     stream; fbe_*_sync waits for it.
+ */
+#ifndef FBE_CABI_H
+#define FBE_CABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FBE_API __attribute__((visibility("default")))
+#else
+#define FBE_API
+#endif
+
+#define FBE_OK 0
+#define FBE_E_INVALID (-1)     /* bad argument */
+#define FBE_E_CUDA (-2)        /* CUDA runtime error / no device; see fbe_last_error() */
+#define FBE_E_CAPACITY (-3)    /* caller buffer or internal workspace too small */
+#define FBE_E_UNSUPPORTED (-4) /* geometry outside what the kernels support */
+
+#define FBE_MAX_LEVELS 16
+#define FBE_HISTO_LENGTH 30 /* ORBmatcher::HISTO_LENGTH, src/ORBmatcher.cc:40 */
+#define FBE_TH_HIGH 100     /* ORBmatcher::TH_HIGH,      src/ORBmatcher.cc:38 */
+#define FBE_TH_LOW 50       /* ORBmatcher::TH_LOW,       src/ORBmatcher.cc:39 */
+
+/* cv::KeyPoint layout (28 bytes): what ORBextractor::operator() fills, include/ORBextractor.h:59-61 */
+typedef struct fbe_keypoint {
+    float x, y;      /* pt, level-0 pixel coordinates (pt *= scale for octave > 0) */
+    float size;      /* (int)(31 * scale[octave]) */
+    float angle;     /* degrees [0,360), IC_Angle */
+    float response;  /* FAST score */
+    int32_t octave;
+    int32_t class_id; /* always -1 */
+} fbe_keypoint;
+
+/* ORBextractor ctor arguments, src/ORBextractor.cc:410-412 (+ workspace sizing) */
+typedef struct fbe_extractor_cfg {
+    int32_t nfeatures;
+    float scale_factor;
+    int32_t nlevels;
+    int32_t ini_th_fast;
+    int32_t min_th_fast;
+    int32_t max_batch; /* images processed per launch group (>=1); workspace is sized for it */
+    int32_t device;    /* CUDA ordinal */
+} fbe_extractor_cfg;
+
+typedef struct fbe_extractor fbe_extractor;
+
+FBE_API const char* fbe_last_error(void);
+FBE_API int fbe_version(void);
+/* number of kernels this library has launched since load (bench.py's "gpu_launches") */
+FBE_API uint64_t fbe_kernel_launch_count(void);
+
+/* ---- ORBextractor ----------------------------------------------------------------------------- */
+/* ORBextractor::ORBextractor, src/ORBextractor.cc:410-470 */
+FBE_API int fbe_extractor_create(const fbe_extractor_cfg* cfg, fbe_extractor** out);
+FBE_API int fbe_extractor_destroy(fbe_extractor* e);
+/* GetLevels / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares,
+ * include/ORBextractor.h:63-83.  Pointers stay valid for the life of the handle. */
+FBE_API int fbe_extractor_tables(const fbe_extractor* e, int32_t* nlevels, const float** scale, const float** inv_scale,
+                         const float** sigma2, const float** inv_sigma2);
+/* mnFeaturesPerLevel, src/ORBextractor.cc:432-446 */
+FBE_API int fbe_extractor_features_per_level(const fbe_extractor* e, const int32_t** per_level);
+/* upper bound on keypoints one image can produce (octree may overshoot nfeatures) */
+FBE_API int fbe_extractor_max_keypoints(const fbe_extractor* e, int32_t rows, int32_t cols, int32_t* cap);
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors), src/ORBextractor.cc:1043-1105.
+ * Host buffers.  img: rows x cols 8-bit, `step` bytes per row.  kps/desc: `capacity` entries / x32 bytes.
+ * Empty image (img NULL or rows/cols <= 0) -> *n_out = 0 and outputs untouched, like the reference's early return. */
+FBE_API int fbe_extract(fbe_extractor* e, const uint8_t* img, int32_t rows, int32_t cols, size_t step, fbe_keypoint* kps,
+                uint8_t* desc, int32_t capacity, int32_t* n_out);
+/* nimg images of one size; kps is [nimg][capacity], desc [nimg][capacity][32], n_out [nimg]. */
+FBE_API int fbe_extract_batch(fbe_extractor* e, const uint8_t* const* imgs, int32_t nimg, int32_t rows, int32_t cols,
+                      size_t step, fbe_keypoint* kps, uint8_t* desc, int32_t capacity, int32_t* n_out);
+/* public member mvImagePyramid, include/ORBextractor.h:85: level image of batch slot `slot` of the LAST call,
+ * with its 19-px REFLECT_101 frame ((rows+38) x (cols+38) written to dst). dst may be NULL to query the size. */
+FBE_API int fbe_pyramid_level(fbe_extractor* e, int32_t slot, int32_t level, uint8_t* dst_padded, size_t dst_step,
+                      int32_t* rows, int32_t* cols);
+
+/* Stage taps for the parity tests (slot of the LAST call). Not part of the reference interface. */
+/* vToDistributeKeys of one level in reference order: (x, y, score) triples in level coordinates */
+FBE_API int fbe_debug_candidates(fbe_extractor* e, int32_t slot, int32_t level, int32_t* xys, int32_t cap, int32_t* n);
+/* blurred level image (rows x cols, tightly packed) */
+FBE_API int fbe_debug_blurred(fbe_extractor* e, int32_t slot, int32_t level, uint8_t* dst, int32_t* rows, int32_t* cols);
+/* stand-alone DistributeOctTree on caller candidates (relative coords as in src/ORBextractor.cc:539): returns
+ * selected candidate indices in reference output order */
+FBE_API int fbe_debug_octree(const int32_t* xys, int32_t n, int32_t min_x, int32_t max_x, int32_t min_y, int32_t max_y,
+                     int32_t nfeat, int32_t* sel, int32_t cap, int32_t* n_sel);
+
+/* ---- Frame grid -------------------------------------------------------------------------------- */
+/* Frame::AssignFeaturesToGrid / PosInGrid / PosInGridBirdview, src/Frame.cc:381-411,548-570.
+ * cell = (round((x-min_x)*inv_w), round((y-min_y)*inv_h)), dropped when outside gcols x grows.
+ * CSR out: cell_start[gcols*grows+1] indexed [ix*grows+iy] (mGrid[ix][iy]), cell_items[n] in index order. */
+FBE_API int fbe_grid_assign(const fbe_keypoint* kps, int32_t n, float min_x, float min_y, float inv_w, float inv_h,
+                    int32_t gcols, int32_t grows, int32_t* cell_start, int32_t* cell_items, int32_t* n_assigned);
+
+/* ---- ORBmatcher -------------------------------------------------------------------------------- */
+/* ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1951-1967 (host inline; never a device round trip) */
+FBE_API int fbe_hamming256(const uint8_t a[32], const uint8_t b[32]);
+
+/* A frame as the matchers see it: keypoints (mvKeysUn / mvKeysBird), descriptors and the grid geometry.
+ * The CSR grid is rebuilt on the device from the keypoints with the parameters below (same as fbe_grid_assign). */
+typedef struct fbe_frame_view {
+    const fbe_keypoint* kps;
+    const uint8_t* desc; /* n x 32 */
+    int32_t n;
+    float min_x, min_y, inv_w, inv_h; /* mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv */
+    int32_t gcols, grows;             /* 64x48 front (Frame.h:38-39), 32x32 bird (Frame.h:40) */
+} fbe_frame_view;
+
+typedef struct fbe_matcher fbe_matcher;
+/* ORBmatcher::ORBmatcher(nnratio, checkOri), src/ORBmatcher.cc:42 */
+FBE_API int fbe_matcher_create(float nn_ratio, int32_t check_orientation, int32_t device, fbe_matcher** out);
+FBE_API int fbe_matcher_destroy(fbe_matcher* m);
+
+/* ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:406-521.
+ * prev_matched: n1 (x,y) pairs, in/out (vbPrevMatched). matches12: n1 ints out (-1 = none). */
+FBE_API int fbe_search_for_initialization(fbe_matcher* m, const fbe_frame_view* f1, const fbe_frame_view* f2,
+                                  float* prev_matched, int32_t* matches12, int32_t window_size, int32_t* nmatches);
+
+/* ORBmatcher::BirdviewMatch with isProject == 0, src/ORBmatcher.cc:1602-1760.
+ * ref side: keypoints + descriptors of the reference bird frame; cur: current frame (32x32 bird grid).
+ * Output: DMatch triples (queryIdx, trainIdx, distance) appended in index order, only trainIdx > 0 (quirk Q8). */
+FBE_API int fbe_birdview_match(fbe_matcher* m, const fbe_keypoint* ref_kps, const uint8_t* ref_desc, int32_t n_ref,
+                       const fbe_frame_view* cur, int32_t window_size, int32_t* dmatches /* n_ref x 3 */,
+                       int32_t* n_dmatches, int32_t* nmatches);
+
+/* ORBmatcher::BirdMapPointMatch, src/ORBmatcher.cc:1763-1902.
+ * Map points: world xyz (n x 3 floats; NaN x marks a NULL MapPointBird*), descriptors n x 32.
+ * tbw / tcw: row-major 4x4 float (Frame::Tbc*mTcw and mTcw).  cur_cam_xyz: mvKeysBirdCamXYZ, cur->n x 3.
+ * Outputs: matches12 (n ints, -1 none), assigned_mp (cur->n ints: index of the map point written to
+ * mvpMapPointsBird[k], -1 untouched), *inliers = return value of the reference. */
+FBE_API int fbe_bird_map_point_match(fbe_matcher* m, const float* mp_world, const uint8_t* mp_desc, int32_t n_mp,
+                             const fbe_frame_view* cur, const float* cur_cam_xyz, const float* tbw,
+                             const float* tcw, int32_t bird_cols, int32_t bird_rows, int32_t window_size,
+                             float filter_size, int32_t* matches12, int32_t* assigned_mp, int32_t* inliers);
+
+/* ORBmatcher::SearchByProjection(Frame&, const Frame& LastFrame, th, bMono=true), src/ORBmatcher.cc:1329-1471.
+ * last_*: per last-frame keypoint i: has_mp[i] != 0 iff mvpMapPoints[i] && !mvbOutlier[i]; world xyz (n x 3);
+ * descriptor of the map point (n x 32); octave and angle come from last->kps.  tcw: CurrentFrame.mTcw (4x4).
+ * cur_taken[k] != 0 iff CurrentFrame.mvpMapPoints[k] has Observations()>0 on entry.
+ * Output: cur_mp[k] = index i of the last-frame map point assigned to keypoint k, -1 none. */
+FBE_API int fbe_search_by_projection_last(fbe_matcher* m, const fbe_frame_view* cur, const fbe_frame_view* last,
+                                  const uint8_t* last_has_mp, const float* last_world, const uint8_t* last_mp_desc,
+                                  const float* tcw, float fx, float fy, float cx, float cy, float max_x,
+                                  float max_y, const uint8_t* cur_taken, float th, int32_t* cur_mp,
+                                  int32_t* nmatches);
+
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th), src/ORBmatcher.cc:46-130.
+ * Per map point (already filtered by mbTrackInView && !isBad): proj (n x 2), predicted level, view cosine,
+ * descriptor.  scale_factors: F.mvScaleFactors.  cur_taken as above (updated by accepted matches in order). */
+FBE_API int fbe_search_by_projection_map(fbe_matcher* m, const fbe_frame_view* cur, const float* scale_factors,
+                                 int32_t nlevels, const float* mp_proj, const int32_t* mp_level,
+                                 const float* mp_viewcos, const uint8_t* mp_desc, int32_t n_mp,
+                                 const uint8_t* cur_taken, float th, int32_t* cur_mp, int32_t* nmatches);
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, matches), src/ORBmatcher.cc:160-289.
+ * Feature vectors as CSR over ascending node ids: node_ids[nn], start[nn+1], items[...].
+ * kf_has_mp[i] != 0 iff the key-frame keypoint has a good map point.  Output: f_mp[k] = key-frame keypoint index
+ * matched to frame keypoint k (-1 none). */
+FBE_API int fbe_search_by_bow(fbe_matcher* m, const fbe_keypoint* kf_kps, const uint8_t* kf_desc, int32_t n_kf,
+                      const uint8_t* kf_has_mp, const int32_t* kf_node_ids, const int32_t* kf_start,
+                      const int32_t* kf_items, int32_t kf_nn, const fbe_keypoint* f_kps, const uint8_t* f_desc,
+                      int32_t n_f, const int32_t* f_node_ids, const int32_t* f_start, const int32_t* f_items,
+                      int32_t f_nn, int32_t* f_mp, int32_t* nmatches);
+
+/* Brute-force Hamming top-2 (stress config C5): for each of nq queries best / second-best over nt targets,
+ * ties -> lowest target index (traversal order). */
+FBE_API int fbe_bruteforce_top2(fbe_matcher* m, const uint8_t* q_desc, int32_t nq, const uint8_t* t_desc, int32_t nt,
+                        int32_t* best_idx, int32_t* best_dist, int32_t* second_dist);
+
+/* ---- Device-resident batch pipeline (bench / offline batches; config C4) ------------------------- */
+typedef struct fbe_pipeline fbe_pipeline;
+typedef struct fbe_pipeline_cfg {
+    fbe_extractor_cfg front; /* e.g. 2000 features */
+    fbe_extractor_cfg bird;  /* e.g. 1000 features */
+    int32_t front_rows, front_cols, bird_rows, bird_cols;
+    int32_t batch; /* frame pairs per step */
+    float nn_ratio;
+    int32_t check_orientation;
+    int32_t front_window; /* SearchForInitialization window (100) */
+    int32_t bird_window;  /* BirdviewMatch window (10) */
+    int32_t device;
+} fbe_pipeline_cfg;
+
+typedef struct fbe_pair_result { /* per frame pair, fixed stride */
+    int32_t n_front, n_bird, front_matches, bird_matches;
+} fbe_pair_result;
+
+FBE_API int fbe_pipeline_create(const fbe_pipeline_cfg* cfg, fbe_pipeline** out);
+FBE_API int fbe_pipeline_destroy(fbe_pipeline* p);
+/* One step = `batch` frame pairs: extract front + bird, build both grids, match pair i against pair i-1
+ * (pair 0 against the last pair of the previous step; the very first pair of a run has no match).
+ * d_front / d_bird: device pointers, [batch][rows][cols] u8 tightly packed.  Asynchronous on the pipeline
+ * streams; results stay on the device until fetched. */
+FBE_API int fbe_pipeline_step_dev(fbe_pipeline* p, const uint8_t* d_front, const uint8_t* d_bird);
+/* Same through HOST (ideally pinned) buffers: H2D copies, step, D2H of the per-pair results + match lists. */
+FBE_API int fbe_pipeline_step_host(fbe_pipeline* p, const uint8_t* h_front, const uint8_t* h_bird, fbe_pair_result* res,
+                           int32_t* front_matches12 /* [batch][front_cap] or NULL */,
+                           int32_t* bird_matches12 /* [batch][bird_cap] or NULL */);
+FBE_API int fbe_pipeline_sync(fbe_pipeline* p);
+FBE_API int fbe_pipeline_caps(const fbe_pipeline* p, int32_t* front_cap, int32_t* bird_cap);
+/* copy back the results of the last step */
+FBE_API int fbe_pipeline_fetch(fbe_pipeline* p, fbe_pair_result* res, int32_t* front_matches12, int32_t* bird_matches12);
+/* full outputs of one pair of the last step (for parity tests at batch sizes) */
+FBE_API int fbe_pipeline_fetch_pair(fbe_pipeline* p, int32_t pair, fbe_keypoint* front_kps, uint8_t* front_desc,
+                            fbe_keypoint* bird_kps, uint8_t* bird_desc);
+/* elapsed GPU milliseconds between the first kernel and the last kernel of the last step (CUDA events) */
+FBE_API int fbe_pipeline_last_step_ms(fbe_pipeline* p, float* ms);
+/* raw stream handle (cudaStream_t) so that a caller can record its own events around steps */
+FBE_API int fbe_pipeline_stream(fbe_pipeline* p, void** stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FBE_CABI_H */
