@@ -1,5 +1,520 @@
-// placeholder: matcher entry points (implemented next)
-#include "fbe_internal.cuh"
-extern "C" {
-int fbe_matcher_create(float, int32_t, int32_t, fbe_matcher**) { return FBE_E_UNSUPPORTED; }
+// 256-bit Hamming searches over grid-windowed candidates (ORBmatcher family) for sm_100a.
+//
+// Shape shared by every search: one WARP per query walks the grid window of
+// Frame::GetFeaturesInArea[Birdview] (src/Frame.cc:493-546, 572-626) -- ix outer, iy inner, in-cell insertion order.
+// Because the CSR grid is stored [ix*grows + iy], the cells (ix, minY..maxY) of one column are ONE contiguous item
+// range, so the walk is a handful of coalesced range scans, lanes = candidates.  Candidates are ranked in traversal
+// order with ballot/popc so that strict-'<' tie-breaking of the reference is reproduced: best = lexicographic
+// min of (distance, rank), second = second element of that order.
+// Order-INDEPENDENT searches (BirdviewMatch, BirdMapPointMatch, brute force) reduce to top-2 in registers.
+// Order-DEPENDENT searches (SearchForInitialization, SearchByProjection x2, SearchByBoW) first store every
+// (candidate, distance) row in traversal order -- all the Hamming work, fully parallel -- and then ONE warp per
+// problem replays the reference's sequential gate / steal / assign rules over those rows.
+#include <algorithm>
+#include <climits>
+#include "match_kernels.cuh"
+
+namespace fbe {
+
+__device__ __forceinline__ int hamming256(const uint32_t (&a)[8], const uint8_t* __restrict__ b) {
+    const uint4 b0 = *reinterpret_cast<const uint4*>(b);
+    const uint4 b1 = *reinterpret_cast<const uint4*>(b + 16);
+    return __popc(a[0] ^ b0.x) + __popc(a[1] ^ b0.y) + __popc(a[2] ^ b0.z) + __popc(a[3] ^ b0.w) +
+           __popc(a[4] ^ b1.x) + __popc(a[5] ^ b1.y) + __popc(a[6] ^ b1.z) + __popc(a[7] ^ b1.w);
 }
+
+__device__ __forceinline__ void load_desc(uint32_t (&a)[8], const uint8_t* __restrict__ p) {
+    const uint4 v0 = *reinterpret_cast<const uint4*>(p);
+    const uint4 v1 = *reinterpret_cast<const uint4*>(p + 16);
+    a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w; a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
+}
+
+// keep the two smallest packed keys
+__device__ __forceinline__ void top2_push(unsigned& k1, unsigned& k2, unsigned k) {
+    if (k < k1) { k2 = k1; k1 = k; }
+    else if (k < k2) k2 = k;
+}
+__device__ __forceinline__ void top2_warp_merge(unsigned& k1, unsigned& k2) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned o1 = __shfl_xor_sync(0xffffffffu, k1, o), o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+        // two smallest of {k1,k2,o1,o2}; keys are distinct (rank is unique) except for kNoKey
+        const unsigned lo = min(k1, o1), hi = max(k1, o1);
+        k2 = min(hi, min(k2, o2));
+        k1 = lo;
+    }
+}
+
+// Warp-collective walk of the window.  fn(idx, pass, rank) is called for every lane of every chunk; `pass` lanes carry
+// a candidate index that cleared the level and window filters, `rank` its position in traversal order.
+template <class Fn>
+__device__ __forceinline__ int window_walk(const fbe_keypoint* __restrict__ kps, const int* __restrict__ start,
+                                           const int* __restrict__ items, float min_x, float min_y, float inv_w, float inv_h,
+                                           int gcols, int grows, float x, float y, float r, int minL, int maxL,
+                                           bool incl, Fn&& fn) {
+    const int lane = threadIdx.x & 31;
+    const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, min_x), r), inv_w)));
+    if (cx0 >= gcols) return 0;
+    const int cx1 = min(gcols - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, min_x), r), inv_w)));
+    if (cx1 < 0) return 0;
+    const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, min_y), r), inv_h)));
+    if (cy0 >= grows) return 0;
+    const int cy1 = min(grows - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, min_y), r), inv_h)));
+    if (cy1 < 0) return 0;
+    const bool check = (minL > 0) || (maxL >= 0);
+    const int xe = incl ? cx1 + 1 : cx1, ye = incl ? cy1 + 1 : cy1;     // exclusive ends (bird: quirk Q2)
+    int rank = 0;
+    if (ye <= cy0) return 0;
+    for (int ix = cx0; ix < xe; ++ix) {
+        const int beg = start[ix * grows + cy0], end = start[ix * grows + ye];
+        for (int base = beg; base < end; base += 32) {
+            const int p = base + lane;
+            int idx = -1;
+            bool pass = false;
+            if (p < end) {
+                idx = items[p];
+                const fbe_keypoint* kp = kps + idx;
+                const int oct = kp->octave;
+                bool ok = true;
+                if (check) {
+                    if (oct < minL) ok = false;
+                    if (maxL >= 0 && oct > maxL) ok = false;
+                }
+                if (ok) {
+                    const float dx = __fsub_rn(kp->x, x), dy = __fsub_rn(kp->y, y);
+                    pass = fabsf(dx) < r && fabsf(dy) < r;
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            fn(idx, pass, rank + __popc(bal & ((1u << lane) - 1u)));
+            rank += __popc(bal);
+        }
+    }
+    return rank;
+}
+
+// ---- query construction ------------------------------------------------------------------------------------------
+// SearchForInitialization / BirdviewMatch(isProject=0): one query per octave-0 keypoint of the reference frame,
+// centred on vbPrevMatched[i] (pos != NULL) or on the keypoint itself; levels (0,0); others are marked r < 0.
+__global__ void k_queries_from_kps(const fbe_keypoint* __restrict__ kps, const float2* __restrict__ pos, const int* __restrict__ n,
+                                   int stride, float window, float4* __restrict__ q, int2* __restrict__ lv) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n[b]) return;
+    const fbe_keypoint kp = kps[(size_t)b * stride + i];
+    float x = kp.x, y = kp.y;
+    if (pos) { const float2 p = pos[(size_t)b * stride + i]; x = p.x; y = p.y; }
+    q[(size_t)b * stride + i] = make_float4(x, y, kp.octave > 0 ? -1.f : window, 0.f);
+    lv[(size_t)b * stride + i] = make_int2(kp.octave, kp.octave);
+}
+
+// ---- parallel stage: rows of (candidate, distance) in traversal order -----------------------------------------------
+__global__ void __launch_bounds__(256) k_window_rows(FrameDev f, QueryDev qs, bool incl, int C, unsigned* __restrict__ rows,
+                                                     int* __restrict__ cnt, int* __restrict__ overflow) {
+    const int b = blockIdx.y;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= qs.nq[b]) return;
+    const size_t qoff = (size_t)b * qs.stride + qi;
+    const float4 q = qs.q[qoff];
+    int total = 0;
+    if (q.z >= 0.f) {
+        const int2 lv = qs.lv[qoff];
+        uint32_t qd[8];
+        load_desc(qd, qs.desc + qoff * 32);
+        const uint8_t* tdesc = f.desc + (size_t)b * f.kp_stride * 32;
+        unsigned* row = rows + qoff * C;
+        total = window_walk(f.kps + (size_t)b * f.kp_stride, f.start + (size_t)b * (f.gcols * f.grows + 1),
+                            f.items + (size_t)b * f.kp_stride, f.min_x, f.min_y, f.inv_w, f.inv_h, f.gcols, f.grows, q.x, q.y,
+                            q.z, lv.x, lv.y, incl, [&](int idx, bool pass, int rank) {
+                                if (pass && rank < C) {
+                                    const int d = hamming256(qd, tdesc + (size_t)idx * 32);
+                                    row[rank] = ((unsigned)idx << kRowDistBits) | (unsigned)d;
+                                }
+                            });
+    }
+    if ((threadIdx.x & 31) == 0) {
+        cnt[qoff] = min(total, C);
+        if (total > C) atomicExch(overflow, 1);
+    }
+}
+
+// ---- parallel stage, order-independent searches: top-2 directly ------------------------------------------------------
+__global__ void __launch_bounds__(256) k_window_top2(FrameDev f, QueryDev qs, bool incl, int* __restrict__ best_idx,
+                                                     int* __restrict__ best_dist, int* __restrict__ second_dist) {
+    const int b = blockIdx.y;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= qs.nq[b]) return;
+    const size_t qoff = (size_t)b * qs.stride + qi;
+    const float4 q = qs.q[qoff];
+    unsigned k1 = kNoKey, k2 = kNoKey;
+    int my_idx = -1;       // candidate index behind this lane's k1
+    if (q.z >= 0.f) {
+        const int2 lv = qs.lv[qoff];
+        uint32_t qd[8];
+        load_desc(qd, qs.desc + qoff * 32);
+        const uint8_t* tdesc = f.desc + (size_t)b * f.kp_stride * 32;
+        window_walk(f.kps + (size_t)b * f.kp_stride, f.start + (size_t)b * (f.gcols * f.grows + 1),
+                    f.items + (size_t)b * f.kp_stride, f.min_x, f.min_y, f.inv_w, f.inv_h, f.gcols, f.grows, q.x, q.y, q.z, lv.x,
+                    lv.y, incl, [&](int idx, bool pass, int rank) {
+                        if (pass) {
+                            const unsigned k = ((unsigned)hamming256(qd, tdesc + (size_t)idx * 32) << 20) | (unsigned)min(rank, 0xFFFFF);
+                            if (k < k1) my_idx = idx;
+                            top2_push(k1, k2, k);
+                        }
+                    });
+    }
+    const unsigned mine = k1;
+    top2_warp_merge(k1, k2);
+    // the lane that owns the winning key publishes its index
+    const unsigned owner = __ballot_sync(0xffffffffu, mine == k1 && k1 != kNoKey);
+    const int widx = __shfl_sync(0xffffffffu, my_idx, owner ? (__ffs(owner) - 1) : 0);
+    if ((threadIdx.x & 31) == 0) {
+        best_idx[qoff] = k1 == kNoKey ? -1 : widx;
+        best_dist[qoff] = k1 == kNoKey ? INT_MAX : (int)(k1 >> 20);
+        second_dist[qoff] = k2 == kNoKey ? INT_MAX : (int)(k2 >> 20);
+    }
+}
+
+// ---- rotation histogram helpers ------------------------------------------------------------------------------------
+__device__ __forceinline__ int rot_bin(float a1, float a2) {
+    float rot = __fsub_rn(a1, a2);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, 1.0f / FBE_HISTO_LENGTH));
+    if (bin == FBE_HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+// ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:1905-1946)
+__device__ inline void three_maxima(const int* histo, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    ind1 = ind2 = ind3 = -1;
+    for (int i = 0; i < FBE_HISTO_LENGTH; ++i) {
+        const int s = histo[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+// ---- sequential stage: one warp per problem replays the reference's loop over the stored rows ---------------------
+__global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
+    __shared__ int s_hist[FBE_HISTO_LENGTH];
+    __shared__ int s_ind[3];
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int nq = a.nq[b], nt = a.nt[b];
+    const size_t qb = (size_t)b * a.q_stride, tb = (size_t)b * a.t_stride;
+    const bool init = a.mode == kResolveInit;
+    int nm = 0;
+    // state reset
+    if (init) {
+        for (int i = lane; i < nt; i += 32) { a.matched_dist[tb + i] = INT_MAX; a.match21[tb + i] = -1; }
+        for (int i = lane; i < nq; i += 32) a.matches12[qb + i] = -1;
+    } else {
+        for (int i = lane; i < nt; i += 32) a.cur_mp[tb + i] = -1;
+    }
+    for (int i = lane; i < nq; i += 32) a.q_bin[qb + i] = -1;
+    if (lane < FBE_HISTO_LENGTH) s_hist[lane] = 0;
+    __syncwarp();
+    const int sentinel = init ? INT_MAX : 256;
+    for (int qi = 0; qi < nq; ++qi) {
+        const int c = a.cnt[qb + qi];
+        if (c == 0) continue;
+        const unsigned* row = a.rows + (qb + qi) * a.C;
+        unsigned k1 = kNoKey, k2 = kNoKey;
+        for (int j = lane; j < c; j += 32) {
+            const unsigned e = row[j];
+            const int idx = (int)(e >> kRowDistBits), dist = (int)(e & ((1u << kRowDistBits) - 1u));
+            bool skip;
+            if (init) skip = a.matched_dist[tb + idx] <= dist;          // :445-446
+            else skip = a.taken[tb + idx] != 0 || dist >= 256;          // :88-90, :1404-1406, :210-211
+            if (!skip) top2_push(k1, k2, ((unsigned)dist << 20) | (unsigned)j);
+        }
+        top2_warp_merge(k1, k2);
+        if (k1 == kNoKey) continue;
+        const int bestDist = (int)(k1 >> 20);
+        const int bestDist2 = k2 == kNoKey ? sentinel : (int)(k2 >> 20);
+        const int bestIdx = (int)(row[k1 & 0xFFFFFu] >> kRowDistBits);
+        bool accept = false;
+        switch (a.mode) {
+            case kResolveInit: accept = bestDist <= FBE_TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, a.nn_ratio); break;
+            case kResolveLast: accept = bestDist <= FBE_TH_HIGH; break;
+            case kResolveMap: {
+                accept = bestDist <= FBE_TH_HIGH;
+                if (accept) {
+                    const int lvl1 = a.t_kps[tb + bestIdx].octave;
+                    const int lvl2 = k2 == kNoKey ? -1 : a.t_kps[tb + (int)(row[k2 & 0xFFFFFu] >> kRowDistBits)].octave;
+                    if (lvl1 == lvl2 && (float)bestDist > __fmul_rn(a.nn_ratio, (float)bestDist2)) accept = false;
+                }
+            } break;
+            default: accept = bestDist <= FBE_TH_LOW && (float)bestDist < __fmul_rn(a.nn_ratio, (float)bestDist2); break;
+        }
+        if (!accept) continue;
+        if (lane == 0) {
+            const int src = a.q_src ? a.q_src[qb + qi] : qi;
+            if (init) {
+                const int old = a.match21[tb + bestIdx];
+                if (old >= 0) { a.matches12[qb + old] = -1; --nm; }          // steal (:464-468)
+                a.matches12[qb + qi] = bestIdx;
+                a.match21[tb + bestIdx] = qi;
+                a.matched_dist[tb + bestIdx] = bestDist;
+            } else {
+                a.cur_mp[tb + bestIdx] = src;
+                if (!a.q_has_obs || a.q_has_obs[qb + qi]) a.taken[tb + bestIdx] = 1;
+            }
+            ++nm;
+            if (a.check_ori && a.mode != kResolveMap) {
+                const int bin = rot_bin(a.q_kps[qb + src].angle, a.t_kps[tb + bestIdx].angle);
+                a.q_bin[qb + qi] = bin;
+                a.q_hit[qb + qi] = bestIdx;
+                s_hist[bin] += 1;
+            }
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    if (a.check_ori && a.mode != kResolveMap) {
+        if (lane == 0) { int i1, i2, i3; three_maxima(s_hist, i1, i2, i3); s_ind[0] = i1; s_ind[1] = i2; s_ind[2] = i3; }
+        __syncwarp();
+        const int i1 = s_ind[0], i2 = s_ind[1], i3 = s_ind[2];
+        int dec = 0;
+        for (int qi = lane; qi < nq; qi += 32) {
+            const int bin = a.q_bin[qb + qi];
+            if (bin < 0 || bin == i1 || bin == i2 || bin == i3) continue;
+            if (init) {
+                if (a.matches12[qb + qi] >= 0) { a.matches12[qb + qi] = -1; ++dec; }
+            } else {
+                a.cur_mp[tb + a.q_hit[qb + qi]] = -1;
+                ++dec;
+            }
+        }
+        dec = __reduce_add_sync(0xffffffffu, dec);
+        nm -= dec;     // only lane 0's nm is meaningful; dec is warp-uniform
+    }
+    __syncwarp();
+    if (init && a.prev_matched) {
+        for (int qi = lane; qi < nq; qi += 32) {
+            const int m = a.matches12[qb + qi];
+            if (m >= 0) a.prev_matched[qb + qi] = make_float2(a.t_kps[tb + m].x, a.t_kps[tb + m].y);
+        }
+    }
+    if (lane == 0) a.nmatches[b] = nm;
+}
+
+// ---- BirdviewMatch epilogue (src/ORBmatcher.cc:1700-1759): ratio test, orientation histogram, DMatch list -----------
+__global__ void __launch_bounds__(256) k_bird_finish(BirdFinishArgs a) {
+    __shared__ int s_hist[FBE_HISTO_LENGTH];
+    __shared__ int s_ind[3];
+    __shared__ int s_warp[8];
+    __shared__ int s_nm, s_carry;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int nq = a.nq[b];
+    const size_t qb = (size_t)b * a.q_stride, tb = (size_t)b * a.t_stride;
+    if (tid < FBE_HISTO_LENGTH) s_hist[tid] = 0;
+    if (tid == 0) { s_nm = 0; s_carry = 0; }
+    __syncthreads();
+    int nm = 0;
+    for (int i = tid; i < nq; i += 256) {
+        const int bi = a.best_idx[qb + i], d1 = a.best_dist[qb + i], d2 = a.second_dist[qb + i];
+        int m = -1, bin = -1;
+        if (bi >= 0 && d1 <= FBE_TH_LOW) {
+            if ((float)d1 < __fmul_rn((float)d2, a.nn_ratio)) { m = bi; ++nm; }
+            if (a.check_ori) { bin = rot_bin(a.q_kps[qb + i].angle, a.t_kps[tb + bi].angle); atomicAdd(&s_hist[bin], 1); }   // Q7
+        }
+        a.matches12[qb + i] = m;
+        a.q_bin[qb + i] = bin;
+    }
+    __syncthreads();
+    if (a.check_ori) {
+        if (tid == 0) { int i1, i2, i3; three_maxima(s_hist, i1, i2, i3); s_ind[0] = i1; s_ind[1] = i2; s_ind[2] = i3; }
+        __syncthreads();
+        const int i1 = s_ind[0], i2 = s_ind[1], i3 = s_ind[2];
+        for (int i = tid; i < nq; i += 256) {
+            const int bin = a.q_bin[qb + i];
+            if (bin < 0 || bin == i1 || bin == i2 || bin == i3) continue;
+            if (a.matches12[qb + i] >= 0) { a.matches12[qb + i] = -1; --nm; }
+        }
+    }
+    if (nm) atomicAdd(&s_nm, nm);
+    __syncthreads();
+    // DMatch(i, matches12[i], best_dist[i]) for matches12[i] > 0, in index order (Q8)
+    if (a.dmatches) {
+        const int lane = tid & 31, wid = tid >> 5;
+        for (int base = 0; base < nq; base += 256) {
+            const int i = base + tid;
+            const int m = i < nq ? a.matches12[qb + i] : -1;
+            const bool f = m > 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, f);
+            if (lane == 0) s_warp[wid] = __popc(bal);
+            __syncthreads();
+            int before = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { const int c = s_warp[w]; if (w < wid) before += c; tot += c; }
+            const int carry = s_carry;
+            if (f) {
+                int* o = a.dmatches + (qb + carry + before + __popc(bal & ((1u << lane) - 1u))) * 3;
+                o[0] = i; o[1] = m; o[2] = a.best_dist[qb + i];
+            }
+            __syncthreads();
+            if (tid == 0) s_carry = carry + tot;
+            __syncthreads();
+        }
+        if (tid == 0) a.n_dmatches[b] = s_carry;
+    }
+    if (tid == 0) a.nmatches[b] = s_nm;
+}
+
+// ---- BirdMapPointMatch first-pass epilogue (src/ORBmatcher.cc:1852-1862) --------------------------------------------
+__global__ void k_map_finish(const int* __restrict__ best_idx, const int* __restrict__ best_dist, const int* __restrict__ second_dist,
+                             int n, float nn_ratio, int th_dist, int* __restrict__ matches12, int* __restrict__ nmatches) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int ok = 0;
+    if (i < n) {
+        const int bi = best_idx[i], d1 = best_dist[i], d2 = second_dist[i];
+        ok = bi >= 0 && d1 <= th_dist && (float)d1 < __fmul_rn((float)d2, nn_ratio);
+        matches12[i] = ok ? bi : -1;
+    }
+    const int c = __reduce_add_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(nmatches, c);
+}
+
+// ---- SearchByBoW rows: query = key-frame feature, candidates = the frame's features under the same vocabulary node ----
+__global__ void __launch_bounds__(256) k_bow_rows(const uint8_t* __restrict__ kf_desc, const uint8_t* __restrict__ f_desc,
+                                                  const int* __restrict__ q_src, const int* __restrict__ q_beg,
+                                                  const int* __restrict__ q_end, const int* __restrict__ f_items, int nq, int C,
+                                                  unsigned* __restrict__ rows, int* __restrict__ cnt) {
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t qd[8];
+    load_desc(qd, kf_desc + (size_t)q_src[qi] * 32);
+    const int beg = q_beg[qi], end = q_end[qi];
+    for (int p = beg + lane; p < end; p += 32) {
+        const int idx = f_items[p];
+        rows[(size_t)qi * C + (p - beg)] = ((unsigned)idx << kRowDistBits) | (unsigned)hamming256(qd, f_desc + (size_t)idx * 32);
+    }
+    if (lane == 0) cnt[qi] = end - beg;
+}
+
+// ---- brute force top-2 (stress config C5): POPC-pipe bound --------------------------------------------------------------
+// 128 queries per CTA, one per thread with its descriptor in registers; targets stream through shared memory in tiles
+// (every lane reads the same target word -> broadcast, no bank conflicts).  blockIdx.y splits the target set so that
+// the grid covers the 148 SMs; a merge kernel folds the partial top-2 keys.
+constexpr int kBfThreads = 128, kBfTile = 256;
+__global__ void __launch_bounds__(kBfThreads) k_bruteforce(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t, int nt,
+                                                           int chunk, unsigned* __restrict__ partial) {
+    __shared__ __align__(16) uint4 s_t[kBfTile * 2];
+    const int qi = blockIdx.x * kBfThreads + threadIdx.x;
+    uint32_t qd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (qi < nq) load_desc(qd, q + (size_t)qi * 32);
+    const int t0 = blockIdx.y * chunk, t1 = min(nt, t0 + chunk);
+    unsigned k1 = kNoKey, k2 = kNoKey;
+    for (int base = t0; base < t1; base += kBfTile) {
+        const int m = min(kBfTile, t1 - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < m * 2; i += kBfThreads) s_t[i] = reinterpret_cast<const uint4*>(t + (size_t)base * 32)[i];
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < m; ++j) {
+            const uint4 b0 = s_t[2 * j], b1 = s_t[2 * j + 1];
+            const int d = __popc(qd[0] ^ b0.x) + __popc(qd[1] ^ b0.y) + __popc(qd[2] ^ b0.z) + __popc(qd[3] ^ b0.w) +
+                          __popc(qd[4] ^ b1.x) + __popc(qd[5] ^ b1.y) + __popc(qd[6] ^ b1.z) + __popc(qd[7] ^ b1.w);
+            top2_push(k1, k2, ((unsigned)d << 20) | (unsigned)(base + j));
+        }
+    }
+    if (qi < nq) {
+        partial[((size_t)blockIdx.y * nq + qi) * 2] = k1;
+        partial[((size_t)blockIdx.y * nq + qi) * 2 + 1] = k2;
+    }
+}
+__global__ void k_bruteforce_merge(const unsigned* __restrict__ partial, int nq, int nchunks, int* __restrict__ best_idx,
+                                   int* __restrict__ best_dist, int* __restrict__ second_dist) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    unsigned k1 = kNoKey, k2 = kNoKey;
+    for (int c = 0; c < nchunks; ++c) {
+        top2_push(k1, k2, partial[((size_t)c * nq + qi) * 2]);
+        top2_push(k1, k2, partial[((size_t)c * nq + qi) * 2 + 1]);
+    }
+    best_idx[qi] = k1 == kNoKey ? -1 : (int)(k1 & 0xFFFFFu);
+    best_dist[qi] = k1 == kNoKey ? 257 : (int)(k1 >> 20);
+    second_dist[qi] = k2 == kNoKey ? 257 : (int)(k2 >> 20);
+}
+
+// ---- launch wrappers -------------------------------------------------------------------------------------------------
+int launch_queries_from_kps(const fbe_keypoint* kps, const float2* pos, const uint8_t*, const int* n, int stride, int nb,
+                            float window, float4* q, int2* lv, cudaStream_t st) {
+    dim3 grid((stride + 255) / 256, nb);
+    k_queries_from_kps<<<grid, 256, 0, st>>>(kps, pos, n, stride, window, q, lv);
+    count_launch();
+    FBE_CUDA(cudaGetLastError());
+    return FBE_OK;
+}
+
+int launch_window_rows(const FrameDev& f, const QueryDev& qs, int nb, int max_nq, bool incl, int C, unsigned* rows, int* cnt,
+                       int* overflow, cudaStream_t st) {
+    if (max_nq <= 0) return FBE_OK;
+    dim3 grid((max_nq + 7) / 8, nb);
+    k_window_rows<<<grid, 256, 0, st>>>(f, qs, incl, C, rows, cnt, overflow);
+    count_launch();
+    FBE_CUDA(cudaGetLastError());
+    return FBE_OK;
+}
+
+int launch_window_top2(const FrameDev& f, const QueryDev& qs, int nb, int max_nq, bool incl, int* best_idx, int* best_dist,
+                       int* second_dist, cudaStream_t st) {
+    if (max_nq <= 0) return FBE_OK;
+    dim3 grid((max_nq + 7) / 8, nb);
+    k_window_top2<<<grid, 256, 0, st>>>(f, qs, incl, best_idx, best_dist, second_dist);
+    count_launch();
+    FBE_CUDA(cudaGetLastError());
+    return FBE_OK;
+}
+
+int launch_resolve(const ResolveArgs& a, int nb, cudaStream_t st) {
+    k_resolve<<<nb, 32, 0, st>>>(a);
+    count_launch();
+    FBE_CUDA(cudaGetLastError());
+    return FBE_OK;
+}
+
+int launch_bird_finish(const BirdFinishArgs& a, int nb, cudaStream_t st) {
+    k_bird_finish<<<nb, 256, 0, st>>>(a);
+    count_launch();
+    FBE_CUDA(cudaGetLastError());
+    return FBE_OK;
+}
+
+int launch_map_finish(const int* best_idx, const int* best_dist, const int* second_dist, int n, float nn_ratio, int th_dist,
+                      int* matches12, int* nmatches, cudaStream_t st) {
+    if (n <= 0) return FBE_OK;
+    k_map_finish<<<(n + 255) / 256, 256, 0, st>>>(best_idx, best_dist, second_dist, n, nn_ratio, th_dist, matches12, nmatches);
+    count_launch();
+    FBE_CUDA(cudaGetLastError());
+    return FBE_OK;
+}
+
+int launch_bow_rows(const uint8_t* kf_desc, const uint8_t* f_desc, const int* q_src, const int* q_beg, const int* q_end,
+                    const int* f_items, int nq, int C, unsigned* rows, int* cnt, cudaStream_t st) {
+    if (nq <= 0) return FBE_OK;
+    k_bow_rows<<<(nq + 7) / 8, 256, 0, st>>>(kf_desc, f_desc, q_src, q_beg, q_end, f_items, nq, C, rows, cnt);
+    count_launch();
+    FBE_CUDA(cudaGetLastError());
+    return FBE_OK;
+}
+
+int launch_bruteforce(const uint8_t* q, int nq, const uint8_t* t, int nt, unsigned* partial, int nchunks, int* best_idx,
+                      int* best_dist, int* second_dist, cudaStream_t st) {
+    if (nq <= 0) return FBE_OK;
+    const int chunk = (((nt + nchunks - 1) / nchunks) + kBfTile - 1) / kBfTile * kBfTile;
+    dim3 grid((nq + kBfThreads - 1) / kBfThreads, nchunks);
+    k_bruteforce<<<grid, kBfThreads, 0, st>>>(q, nq, t, nt, std::max(chunk, kBfTile), partial);
+    k_bruteforce_merge<<<(nq + 255) / 256, 256, 0, st>>>(partial, nq, nchunks, best_idx, best_dist, second_dist);
+    count_launch(2);
+    FBE_CUDA(cudaGetLastError());
+    return FBE_OK;
+}
+
+}  // namespace fbe

@@ -1,0 +1,406 @@
+// C-ABI of the matcher family (include/fbe_cabi.h): host buffers in/out, all searches on the device.
+// The host side only marshals: it flattens frames to arrays, builds the per-query (centre, radius, level range)
+// records with the reference's fp32 arithmetic, and copies results back.  No Hamming distance is computed on the host.
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "match_kernels.cuh"
+
+using namespace fbe;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return FBE_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        FBE_CUDA(cudaMalloc(&p, want));
+        cap = want;
+        return FBE_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct FrameBufs {
+    DevBuf kps, desc, n, cell, start, items;
+};
+
+}  // namespace
+
+struct fbe_matcher {
+    float nn_ratio;
+    int check_ori;
+    int device;
+    cudaStream_t stream = nullptr;
+    int row_cap = 128;
+    FrameBufs fa, fb;                          // target frame / auxiliary source frame
+    DevBuf q, lv, qdesc, nq, rows, cnt, misc, i0, i1, i2, i3, i4, u0, u1, f0, partial;
+};
+
+namespace {
+
+#define FBE_TRY(expr) do { int _rc = (expr); if (_rc != FBE_OK) return _rc; } while (0)
+
+int upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t st) {
+    FBE_TRY(b.ensure(std::max<size_t>(bytes, 16)));
+    if (bytes) FBE_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+    return FBE_OK;
+}
+
+// uploads keypoints + descriptors of a frame and builds its CSR grid on the device
+int upload_frame(fbe_matcher* m, FrameBufs& fb, const fbe_frame_view* v, bool with_grid, FrameDev& out) {
+    if (!v || v->n < 0 || (v->n > 0 && (!v->kps || !v->desc))) return FBE_E_INVALID;
+    const int n = v->n, stride = std::max(n, 1);
+    FBE_TRY(upload(fb.kps, v->kps, (size_t)n * sizeof(fbe_keypoint), m->stream));
+    FBE_TRY(upload(fb.desc, v->desc, (size_t)n * 32, m->stream));
+    FBE_TRY(upload(fb.n, &v->n, sizeof(int), m->stream));
+    out = FrameDev();
+    out.kps = fb.kps.as<fbe_keypoint>(); out.desc = fb.desc.as<uint8_t>(); out.n = fb.n.as<int>();
+    out.kp_stride = stride;
+    out.min_x = v->min_x; out.min_y = v->min_y; out.inv_w = v->inv_w; out.inv_h = v->inv_h;
+    out.gcols = v->gcols; out.grows = v->grows;
+    if (with_grid) {
+        if (v->gcols <= 0 || v->grows <= 0) return FBE_E_INVALID;
+        FBE_TRY(fb.cell.ensure((size_t)stride * 4));
+        FBE_TRY(fb.start.ensure((size_t)(v->gcols * v->grows + 1) * 4));
+        FBE_TRY(fb.items.ensure((size_t)stride * 4));
+        FBE_TRY(launch_grid_build(out.kps, out.n, stride, 1, v->min_x, v->min_y, v->inv_w, v->inv_h, v->gcols, v->grows,
+                                  fb.cell.as<int>(), fb.start.as<int>(), fb.items.as<int>(), m->stream));
+        out.start = fb.start.as<int>(); out.items = fb.items.as<int>();
+    }
+    return FBE_OK;
+}
+
+int upload_queries(fbe_matcher* m, const std::vector<float4>& q, const std::vector<int2>& lv, const uint8_t* desc, int nq,
+                   QueryDev& out) {
+    const int stride = std::max(nq, 1);
+    FBE_TRY(upload(m->q, q.data(), (size_t)nq * sizeof(float4), m->stream));
+    FBE_TRY(upload(m->lv, lv.data(), (size_t)nq * sizeof(int2), m->stream));
+    FBE_TRY(upload(m->qdesc, desc, (size_t)nq * 32, m->stream));
+    FBE_TRY(upload(m->nq, &nq, sizeof(int), m->stream));
+    out.q = m->q.as<float4>(); out.lv = m->lv.as<int2>(); out.desc = m->qdesc.as<uint8_t>(); out.nq = m->nq.as<int>();
+    out.stride = stride;
+    return FBE_OK;
+}
+
+// rows + sequential resolve with automatic growth of the per-query row capacity
+template <class Setup>
+int rows_and_resolve(fbe_matcher* m, const FrameDev& tf, const QueryDev& qs, int nq, int nt, bool incl, ResolveArgs a, Setup&& before_resolve) {
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        const int C = m->row_cap;
+        FBE_TRY(m->rows.ensure((size_t)std::max(nq, 1) * C * 4));
+        FBE_TRY(m->cnt.ensure((size_t)std::max(nq, 1) * 4));
+        FBE_TRY(m->misc.ensure(64));
+        FBE_CUDA(cudaMemsetAsync(m->misc.p, 0, 64, m->stream));
+        FBE_TRY(launch_window_rows(tf, qs, 1, nq, incl, C, m->rows.as<unsigned>(), m->cnt.as<int>(), m->misc.as<int>(), m->stream));
+        FBE_TRY(before_resolve());
+        a.C = C; a.rows = m->rows.as<unsigned>(); a.cnt = m->cnt.as<int>();
+        a.nq = qs.nq; a.q_stride = qs.stride; a.t_stride = tf.kp_stride; a.nt = tf.n; a.t_kps = tf.kps;
+        a.nmatches = m->misc.as<int>() + 1;
+        (void)nt;
+        FBE_TRY(launch_resolve(a, 1, m->stream));
+        int h[2] = {0, 0};
+        FBE_CUDA(cudaMemcpyAsync(h, m->misc.p, 8, cudaMemcpyDeviceToHost, m->stream));
+        FBE_CUDA(cudaStreamSynchronize(m->stream));
+        if (!h[0]) return h[1];           // >= 0 : nmatches
+        m->row_cap *= 2;                  // a window held more candidates than the row capacity: redo, larger
+    }
+    set_error("candidate rows overflow");
+    return FBE_E_CAPACITY;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fbe_matcher_create(float nn_ratio, int32_t check_orientation, int32_t device, fbe_matcher** out) {
+    if (!out) return FBE_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_error("no CUDA device: this library has no CPU path"); return FBE_E_CUDA; }
+    FBE_CUDA(cudaSetDevice(device));
+    fbe_matcher* m = new (std::nothrow) fbe_matcher();
+    if (!m) return FBE_E_INVALID;
+    m->nn_ratio = nn_ratio; m->check_ori = check_orientation != 0; m->device = device;
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) { delete m; set_error("stream"); return FBE_E_CUDA; }
+    *out = m;
+    return FBE_OK;
+}
+
+int fbe_matcher_destroy(fbe_matcher* m) {
+    if (!m) return FBE_E_INVALID;
+    cudaSetDevice(m->device);
+    cudaStreamSynchronize(m->stream);
+    for (FrameBufs* f : {&m->fa, &m->fb}) { f->kps.release(); f->desc.release(); f->n.release(); f->cell.release(); f->start.release(); f->items.release(); }
+    for (DevBuf* b : {&m->q, &m->lv, &m->qdesc, &m->nq, &m->rows, &m->cnt, &m->misc, &m->i0, &m->i1, &m->i2, &m->i3, &m->i4, &m->u0, &m->u1, &m->f0, &m->partial}) b->release();
+    cudaStreamDestroy(m->stream);
+    delete m;
+    return FBE_OK;
+}
+
+int fbe_search_for_initialization(fbe_matcher* m, const fbe_frame_view* f1, const fbe_frame_view* f2, float* prev_matched,
+                                  int32_t* matches12, int32_t window_size, int32_t* nmatches) {
+    if (!m || !f1 || !f2 || !nmatches || (f1->n > 0 && (!prev_matched || !matches12))) return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(m->device));
+    *nmatches = 0;
+    const int n1 = f1->n, n2 = f2->n;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    if (n1 == 0 || n2 == 0) return FBE_OK;
+    FrameDev F1, F2;
+    FBE_TRY(upload_frame(m, m->fb, f1, false, F1));
+    FBE_TRY(upload_frame(m, m->fa, f2, true, F2));
+    FBE_TRY(upload(m->f0, prev_matched, (size_t)n1 * 8, m->stream));
+    FBE_TRY(m->q.ensure((size_t)n1 * sizeof(float4)));
+    FBE_TRY(m->lv.ensure((size_t)n1 * sizeof(int2)));
+    FBE_TRY(launch_queries_from_kps(F1.kps, m->f0.as<float2>(), nullptr, F1.n, n1, 1, (float)window_size, m->q.as<float4>(),
+                                    m->lv.as<int2>(), m->stream));
+    QueryDev qs{m->q.as<float4>(), m->lv.as<int2>(), F1.desc, F1.n, n1};
+    FBE_TRY(m->i0.ensure((size_t)n2 * 4)); FBE_TRY(m->i1.ensure((size_t)n2 * 4));
+    FBE_TRY(m->i2.ensure((size_t)n1 * 4)); FBE_TRY(m->i3.ensure((size_t)n1 * 4)); FBE_TRY(m->i4.ensure((size_t)n1 * 4));
+    ResolveArgs a{};
+    a.mode = kResolveInit; a.q_kps = F1.kps; a.q_src = nullptr; a.q_has_obs = nullptr;
+    a.nn_ratio = m->nn_ratio; a.check_ori = m->check_ori;
+    a.matched_dist = m->i0.as<int>(); a.match21 = m->i1.as<int>(); a.matches12 = m->i2.as<int>();
+    a.prev_matched = m->f0.as<float2>(); a.q_bin = m->i3.as<int>(); a.q_hit = m->i4.as<int>();
+    // a retry after a row overflow must start from the caller's vbPrevMatched again
+    int rc = rows_and_resolve(m, F2, qs, n1, n2, true, a, [&]() {
+        return upload(m->f0, prev_matched, (size_t)n1 * 8, m->stream);
+    });
+    if (rc < 0) return rc;
+    *nmatches = rc;
+    FBE_CUDA(cudaMemcpyAsync(matches12, m->i2.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, m->stream));
+    FBE_CUDA(cudaMemcpyAsync(prev_matched, m->f0.p, (size_t)n1 * 8, cudaMemcpyDeviceToHost, m->stream));
+    FBE_CUDA(cudaStreamSynchronize(m->stream));
+    return FBE_OK;
+}
+
+int fbe_birdview_match(fbe_matcher* m, const fbe_keypoint* ref_kps, const uint8_t* ref_desc, int32_t n_ref,
+                       const fbe_frame_view* cur, int32_t window_size, int32_t* dmatches, int32_t* n_dmatches, int32_t* nmatches) {
+    if (!m || !cur || !nmatches || !n_dmatches || n_ref < 0 || (n_ref > 0 && (!ref_kps || !ref_desc || !dmatches))) return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(m->device));
+    *nmatches = 0; *n_dmatches = 0;
+    if (n_ref == 0 || cur->n == 0) return FBE_OK;
+    fbe_frame_view rv = *cur;
+    rv.kps = ref_kps; rv.desc = ref_desc; rv.n = n_ref;
+    FrameDev R, Cf;
+    FBE_TRY(upload_frame(m, m->fb, &rv, false, R));
+    FBE_TRY(upload_frame(m, m->fa, cur, true, Cf));
+    FBE_TRY(m->q.ensure((size_t)n_ref * sizeof(float4)));
+    FBE_TRY(m->lv.ensure((size_t)n_ref * sizeof(int2)));
+    FBE_TRY(launch_queries_from_kps(R.kps, nullptr, nullptr, R.n, n_ref, 1, (float)window_size, m->q.as<float4>(), m->lv.as<int2>(), m->stream));
+    QueryDev qs{m->q.as<float4>(), m->lv.as<int2>(), R.desc, R.n, n_ref};
+    FBE_TRY(m->i0.ensure((size_t)n_ref * 4)); FBE_TRY(m->i1.ensure((size_t)n_ref * 4)); FBE_TRY(m->i2.ensure((size_t)n_ref * 4));
+    FBE_TRY(m->i3.ensure((size_t)n_ref * 4)); FBE_TRY(m->i4.ensure((size_t)n_ref * 12)); FBE_TRY(m->misc.ensure(64));
+    FBE_TRY(launch_window_top2(Cf, qs, 1, n_ref, false, m->i0.as<int>(), m->i1.as<int>(), m->i2.as<int>(), m->stream));
+    BirdFinishArgs a{};
+    a.best_idx = m->i0.as<int>(); a.best_dist = m->i1.as<int>(); a.second_dist = m->i2.as<int>();
+    a.nq = R.n; a.q_stride = n_ref; a.q_kps = R.kps; a.t_kps = Cf.kps; a.t_stride = Cf.kp_stride;
+    a.nn_ratio = m->nn_ratio; a.check_ori = m->check_ori;
+    a.matches12 = m->i3.as<int>(); a.dmatches = m->i4.as<int>(); a.n_dmatches = m->misc.as<int>(); a.nmatches = m->misc.as<int>() + 1;
+    FBE_TRY(m->partial.ensure((size_t)n_ref * 4));
+    a.q_bin = m->partial.as<int>();
+    FBE_TRY(launch_bird_finish(a, 1, m->stream));
+    int h[2];
+    FBE_CUDA(cudaMemcpyAsync(h, m->misc.p, 8, cudaMemcpyDeviceToHost, m->stream));
+    FBE_CUDA(cudaStreamSynchronize(m->stream));
+    *n_dmatches = h[0]; *nmatches = h[1];
+    if (h[0] > 0) FBE_CUDA(cudaMemcpy(dmatches, m->i4.p, (size_t)h[0] * 12, cudaMemcpyDeviceToHost));
+    return FBE_OK;
+}
+
+int fbe_bird_map_point_match(fbe_matcher* m, const float* mp_pix, const uint8_t* mp_desc, int32_t n_mp, const fbe_frame_view* cur,
+                             int32_t window_size, int32_t* matches12, int32_t* nmatches) {
+    if (!m || !cur || !nmatches || n_mp < 0 || (n_mp > 0 && (!mp_pix || !mp_desc || !matches12))) return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(m->device));
+    *nmatches = 0;
+    for (int i = 0; i < n_mp; ++i) matches12[i] = -1;
+    if (n_mp == 0 || cur->n == 0) return FBE_OK;
+    std::vector<float4> q(n_mp);
+    std::vector<int2> lv(n_mp, make_int2(-1, -1));
+    for (int i = 0; i < n_mp; ++i) {
+        const bool skip = std::isnan(mp_pix[2 * i]);
+        q[i] = make_float4(skip ? 0.f : mp_pix[2 * i], skip ? 0.f : mp_pix[2 * i + 1], skip ? -1.f : (float)window_size, 0.f);
+    }
+    FrameDev Cf;
+    QueryDev qs;
+    FBE_TRY(upload_frame(m, m->fa, cur, true, Cf));
+    FBE_TRY(upload_queries(m, q, lv, mp_desc, n_mp, qs));
+    FBE_TRY(m->i0.ensure((size_t)n_mp * 4)); FBE_TRY(m->i1.ensure((size_t)n_mp * 4)); FBE_TRY(m->i2.ensure((size_t)n_mp * 4));
+    FBE_TRY(m->i3.ensure((size_t)n_mp * 4)); FBE_TRY(m->misc.ensure(64));
+    FBE_CUDA(cudaMemsetAsync(m->misc.p, 0, 64, m->stream));
+    FBE_TRY(launch_window_top2(Cf, qs, 1, n_mp, false, m->i0.as<int>(), m->i1.as<int>(), m->i2.as<int>(), m->stream));
+    FBE_TRY(launch_map_finish(m->i0.as<int>(), m->i1.as<int>(), m->i2.as<int>(), n_mp, m->nn_ratio, FBE_TH_LOW, m->i3.as<int>(),
+                              m->misc.as<int>(), m->stream));
+    FBE_CUDA(cudaMemcpyAsync(matches12, m->i3.p, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, m->stream));
+    FBE_CUDA(cudaMemcpyAsync(nmatches, m->misc.p, 4, cudaMemcpyDeviceToHost, m->stream));
+    FBE_CUDA(cudaStreamSynchronize(m->stream));
+    return FBE_OK;
+}
+
+static int projection_search(fbe_matcher* m, int mode, const fbe_frame_view* cur, const std::vector<float4>& q,
+                             const std::vector<int2>& lv, const uint8_t* qdesc, const fbe_keypoint* q_kps, int nq,
+                             const uint8_t* cur_taken, const uint8_t* q_has_obs, const int* q_src, int check_ori,
+                             int32_t* cur_mp, int32_t* nmatches) {
+    const int nt = cur->n;
+    FrameDev Cf;
+    QueryDev qs;
+    FBE_TRY(upload_frame(m, m->fa, cur, true, Cf));
+    FBE_TRY(upload_queries(m, q, lv, qdesc, nq, qs));
+    std::vector<uint8_t> taken(nt, 0);
+    if (cur_taken) std::memcpy(taken.data(), cur_taken, nt);
+    std::vector<uint8_t> obs(std::max(nq, 1), 1);
+    if (q_has_obs) std::memcpy(obs.data(), q_has_obs, nq);
+    FBE_TRY(upload(m->u1, obs.data(), (size_t)nq, m->stream));
+    FBE_TRY(m->i0.ensure((size_t)nt * 4)); FBE_TRY(m->i3.ensure((size_t)std::max(nq, 1) * 4)); FBE_TRY(m->i4.ensure((size_t)std::max(nq, 1) * 4));
+    if (q_kps) FBE_TRY(upload(m->fb.kps, q_kps, (size_t)nq * sizeof(fbe_keypoint), m->stream));
+    if (q_src) FBE_TRY(upload(m->i1, q_src, (size_t)nq * 4, m->stream));
+    ResolveArgs a{};
+    a.mode = mode; a.q_kps = q_kps ? m->fb.kps.as<fbe_keypoint>() : nullptr; a.q_src = q_src ? m->i1.as<int>() : nullptr;
+    a.q_has_obs = m->u1.as<uint8_t>(); a.nn_ratio = m->nn_ratio; a.check_ori = check_ori;
+    a.cur_mp = m->i0.as<int>(); a.q_bin = m->i3.as<int>(); a.q_hit = m->i4.as<int>();
+    FBE_TRY(m->u0.ensure((size_t)nt));
+    a.taken = m->u0.as<uint8_t>();
+    int rc = rows_and_resolve(m, Cf, qs, nq, nt, true, a, [&]() {
+        return upload(m->u0, taken.data(), (size_t)nt, m->stream);      // fresh `taken` state on every attempt
+    });
+    if (rc < 0) return rc;
+    *nmatches = rc;
+    FBE_CUDA(cudaMemcpy(cur_mp, m->i0.p, (size_t)nt * 4, cudaMemcpyDeviceToHost));
+    return FBE_OK;
+}
+
+int fbe_search_by_projection_last(fbe_matcher* m, const fbe_frame_view* cur, const fbe_keypoint* last_kps, const float* last_proj,
+                                  const uint8_t* last_mp_desc, int32_t n_last, const float* scale_factors, int32_t nlevels,
+                                  const uint8_t* cur_taken, const uint8_t* last_has_obs, float th, int32_t* cur_mp, int32_t* nmatches) {
+    if (!m || !cur || !nmatches || n_last < 0 || !scale_factors || (cur->n > 0 && !cur_mp) ||
+        (n_last > 0 && (!last_kps || !last_proj || !last_mp_desc))) return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(m->device));
+    *nmatches = 0;
+    for (int k = 0; k < cur->n; ++k) cur_mp[k] = -1;
+    if (n_last == 0 || cur->n == 0) return FBE_OK;
+    std::vector<float4> q(n_last);
+    std::vector<int2> lv(n_last);
+    for (int i = 0; i < n_last; ++i) {
+        const int o = last_kps[i].octave;
+        if (o < 0 || o >= nlevels) return FBE_E_INVALID;
+        const bool skip = std::isnan(last_proj[2 * i]);
+        const float radius = th * scale_factors[o];          // :1382
+        q[i] = make_float4(skip ? 0.f : last_proj[2 * i], skip ? 0.f : last_proj[2 * i + 1], skip ? -1.f : radius, 0.f);
+        lv[i] = make_int2(o - 1, o + 1);                    // mono branch :1391
+    }
+    return projection_search(m, kResolveLast, cur, q, lv, last_mp_desc, last_kps, n_last, cur_taken, last_has_obs, nullptr,
+                             m->check_ori, cur_mp, nmatches);
+}
+
+int fbe_search_by_projection_map(fbe_matcher* m, const fbe_frame_view* cur, const float* scale_factors, int32_t nlevels,
+                                 const float* mp_proj, const int32_t* mp_level, const float* mp_viewcos, const uint8_t* mp_desc,
+                                 int32_t n_mp, const uint8_t* cur_taken, const uint8_t* mp_has_obs, float th, int32_t* cur_mp,
+                                 int32_t* nmatches) {
+    if (!m || !cur || !nmatches || n_mp < 0 || !scale_factors || (cur->n > 0 && !cur_mp) ||
+        (n_mp > 0 && (!mp_proj || !mp_level || !mp_viewcos || !mp_desc))) return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(m->device));
+    *nmatches = 0;
+    for (int k = 0; k < cur->n; ++k) cur_mp[k] = -1;
+    if (n_mp == 0 || cur->n == 0) return FBE_OK;
+    const bool bFactor = th != 1.0;
+    std::vector<float4> q(n_mp);
+    std::vector<int2> lv(n_mp);
+    for (int i = 0; i < n_mp; ++i) {
+        const int l = mp_level[i];
+        if (l < 0 || l >= nlevels) return FBE_E_INVALID;
+        float r = mp_viewcos[i] > 0.998 ? 2.5f : 4.0f;       // RadiusByViewingCos :132-138
+        if (bFactor) r *= th;
+        q[i] = make_float4(mp_proj[2 * i], mp_proj[2 * i + 1], r * scale_factors[l], 0.f);
+        lv[i] = make_int2(l - 1, l);
+    }
+    return projection_search(m, kResolveMap, cur, q, lv, mp_desc, nullptr, n_mp, cur_taken, mp_has_obs, nullptr, 0, cur_mp, nmatches);
+}
+
+int fbe_search_by_bow(fbe_matcher* m, const fbe_keypoint* kf_kps, const uint8_t* kf_desc, int32_t n_kf, const uint8_t* kf_has_mp,
+                      const int32_t* kf_node_ids, const int32_t* kf_start, const int32_t* kf_items, int32_t kf_nn,
+                      const fbe_keypoint* f_kps, const uint8_t* f_desc, int32_t n_f, const int32_t* f_node_ids,
+                      const int32_t* f_start, const int32_t* f_items, int32_t f_nn, int32_t* f_mp, int32_t* nmatches) {
+    if (!m || !nmatches || n_kf < 0 || n_f < 0 || kf_nn < 0 || f_nn < 0 || (n_f > 0 && !f_mp)) return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(m->device));
+    *nmatches = 0;
+    for (int k = 0; k < n_f; ++k) f_mp[k] = -1;
+    if (n_kf == 0 || n_f == 0 || kf_nn == 0 || f_nn == 0) return FBE_OK;
+    if (!kf_kps || !kf_desc || !kf_has_mp || !kf_node_ids || !kf_start || !kf_items || !f_kps || !f_desc || !f_node_ids || !f_start || !f_items)
+        return FBE_E_INVALID;
+    // merge-walk of the two feature vectors (:184-262): the ordered query list
+    std::vector<int> q_src, q_beg, q_end;
+    int a = 0, b = 0, C = 1;
+    while (a < kf_nn && b < f_nn) {
+        if (kf_node_ids[a] == f_node_ids[b]) {
+            for (int p = kf_start[a]; p < kf_start[a + 1]; ++p) {
+                const int i = kf_items[p];
+                if (i < 0 || i >= n_kf) return FBE_E_INVALID;
+                if (!kf_has_mp[i]) continue;
+                q_src.push_back(i); q_beg.push_back(f_start[b]); q_end.push_back(f_start[b + 1]);
+            }
+            C = std::max(C, f_start[b + 1] - f_start[b]);
+            ++a; ++b;
+        } else if (kf_node_ids[a] < f_node_ids[b]) ++a;
+        else ++b;
+    }
+    const int nq = (int)q_src.size();
+    if (nq == 0) return FBE_OK;
+    const int n_items = f_start[f_nn];
+    FBE_TRY(upload(m->fb.kps, kf_kps, (size_t)n_kf * sizeof(fbe_keypoint), m->stream));
+    FBE_TRY(upload(m->fb.desc, kf_desc, (size_t)n_kf * 32, m->stream));
+    FBE_TRY(upload(m->fa.kps, f_kps, (size_t)n_f * sizeof(fbe_keypoint), m->stream));
+    FBE_TRY(upload(m->fa.desc, f_desc, (size_t)n_f * 32, m->stream));
+    FBE_TRY(upload(m->i1, q_src.data(), (size_t)nq * 4, m->stream));
+    FBE_TRY(upload(m->i2, q_beg.data(), (size_t)nq * 4, m->stream));
+    FBE_TRY(upload(m->partial, q_end.data(), (size_t)nq * 4, m->stream));
+    FBE_TRY(upload(m->fa.items, f_items, (size_t)n_items * 4, m->stream));
+    FBE_TRY(upload(m->nq, &nq, 4, m->stream));
+    FBE_TRY(upload(m->fa.n, &n_f, 4, m->stream));
+    FBE_TRY(m->rows.ensure((size_t)nq * C * 4)); FBE_TRY(m->cnt.ensure((size_t)nq * 4));
+    FBE_TRY(m->i0.ensure((size_t)n_f * 4)); FBE_TRY(m->i3.ensure((size_t)nq * 4)); FBE_TRY(m->i4.ensure((size_t)nq * 4));
+    FBE_TRY(m->u0.ensure((size_t)n_f)); FBE_TRY(m->misc.ensure(64));
+    FBE_CUDA(cudaMemsetAsync(m->u0.p, 0, (size_t)n_f, m->stream));
+    FBE_TRY(launch_bow_rows(m->fb.desc.as<uint8_t>(), m->fa.desc.as<uint8_t>(), m->i1.as<int>(), m->i2.as<int>(), m->partial.as<int>(),
+                            m->fa.items.as<int>(), nq, C, m->rows.as<unsigned>(), m->cnt.as<int>(), m->stream));
+    ResolveArgs r{};
+    r.mode = kResolveBow; r.C = C; r.rows = m->rows.as<unsigned>(); r.cnt = m->cnt.as<int>(); r.nq = m->nq.as<int>();
+    r.q_stride = nq; r.t_stride = n_f; r.nt = m->fa.n.as<int>(); r.q_kps = m->fb.kps.as<fbe_keypoint>(); r.q_src = m->i1.as<int>();
+    r.t_kps = m->fa.kps.as<fbe_keypoint>(); r.q_has_obs = nullptr; r.nn_ratio = m->nn_ratio; r.check_ori = m->check_ori;
+    r.taken = m->u0.as<uint8_t>(); r.cur_mp = m->i0.as<int>(); r.q_bin = m->i3.as<int>(); r.q_hit = m->i4.as<int>();
+    r.nmatches = m->misc.as<int>();
+    // q_kps is indexed by the key-frame keypoint index: give the resolve kernel a q_stride-independent view
+    FBE_TRY(launch_resolve(r, 1, m->stream));
+    FBE_CUDA(cudaMemcpyAsync(f_mp, m->i0.p, (size_t)n_f * 4, cudaMemcpyDeviceToHost, m->stream));
+    FBE_CUDA(cudaMemcpyAsync(nmatches, m->misc.p, 4, cudaMemcpyDeviceToHost, m->stream));
+    FBE_CUDA(cudaStreamSynchronize(m->stream));
+    return FBE_OK;
+}
+
+int fbe_bruteforce_top2(fbe_matcher* m, const uint8_t* q_desc, int32_t nq, const uint8_t* t_desc, int32_t nt, int32_t* best_idx,
+                        int32_t* best_dist, int32_t* second_dist) {
+    if (!m || nq < 0 || nt < 0 || (nq > 0 && (!q_desc || !best_idx || !best_dist || !second_dist)) || (nt > 0 && !t_desc)) return FBE_E_INVALID;
+    if (nt >= (1 << 20)) { set_error("more than 2^20 targets"); return FBE_E_UNSUPPORTED; }
+    FBE_CUDA(cudaSetDevice(m->device));
+    if (nq == 0) return FBE_OK;
+    const int qblocks = (nq + 127) / 128;
+    int nchunks = std::max(1, std::min((2 * 148 + qblocks - 1) / qblocks, (nt + 255) / 256));
+    FBE_TRY(upload(m->qdesc, q_desc, (size_t)nq * 32, m->stream));
+    FBE_TRY(upload(m->fa.desc, t_desc, (size_t)nt * 32, m->stream));
+    FBE_TRY(m->partial.ensure((size_t)nchunks * nq * 8));
+    FBE_TRY(m->i0.ensure((size_t)nq * 4)); FBE_TRY(m->i1.ensure((size_t)nq * 4)); FBE_TRY(m->i2.ensure((size_t)nq * 4));
+    FBE_TRY(launch_bruteforce(m->qdesc.as<uint8_t>(), nq, m->fa.desc.as<uint8_t>(), nt, m->partial.as<unsigned>(), nchunks,
+                              m->i0.as<int>(), m->i1.as<int>(), m->i2.as<int>(), m->stream));
+    FBE_CUDA(cudaMemcpyAsync(best_idx, m->i0.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, m->stream));
+    FBE_CUDA(cudaMemcpyAsync(best_dist, m->i1.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, m->stream));
+    FBE_CUDA(cudaMemcpyAsync(second_dist, m->i2.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, m->stream));
+    FBE_CUDA(cudaStreamSynchronize(m->stream));
+    return FBE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+"""Python mirror of the reference's ORBmatcher (include/ORBmatcher.h:36-108) and of the slice of Frame it reads,
+over the C-ABI.  Method names, argument meaning and return values follow the reference; pointer-valued arguments
+(MapPoint*, KeyFrame*) are replaced by the flat arrays the C++ drop-in shim extracts from them.
+All searches run in the CUDA library; this module only marshals and performs the reference's host-side cv::Mat
+arithmetic (projections, bird pixel conversion, the BirdMapPointMatch distance filter).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import KP_DTYPE, FrameView, check, ptr
+
+FRAME_GRID_ROWS, FRAME_GRID_COLS, FRAME_GRID_BIRD = 48, 64, 32          # include/Frame.h:38-40
+METER2PIXEL, PIXEL2METER, REAR_AXLE_TO_CENTER = 25.1, 0.03984, 1.393     # src/Frame.cc:39-44
+
+
+@dataclass
+class Frame:
+    """The fields of ORB_SLAM2::Frame the matchers read (src/Frame.cc): keypoints, descriptors, grid geometry."""
+    kps: np.ndarray                      # KP_DTYPE[n]   (mvKeysUn / mvKeysBird)
+    desc: np.ndarray                     # u8[n,32]      (mDescriptors / mDescriptorsBird)
+    min_x: float = 0.0                   # mnMinX
+    min_y: float = 0.0                   # mnMinY
+    inv_w: float = 0.0                   # mfGridElementWidthInv
+    inv_h: float = 0.0                   # mfGridElementHeightInv
+    gcols: int = FRAME_GRID_COLS
+    grows: int = FRAME_GRID_ROWS
+    scale_factors: np.ndarray = field(default_factory=lambda: np.ones(8, np.float32))   # mvScaleFactors
+
+    @staticmethod
+    def front(kps, desc, cols, rows, scale_factors=None):
+        """k1 == 0 image bounds (src/Frame.cc:741-795): mnMinX = 0, mnMaxX = cols, ..."""
+        f = Frame(np.ascontiguousarray(kps), np.ascontiguousarray(desc), 0.0, 0.0,
+                  float(np.float32(FRAME_GRID_COLS) / np.float32(cols)), float(np.float32(FRAME_GRID_ROWS) / np.float32(rows)),
+                  FRAME_GRID_COLS, FRAME_GRID_ROWS)
+        if scale_factors is not None:
+            f.scale_factors = np.ascontiguousarray(scale_factors, np.float32)
+        return f
+
+    @staticmethod
+    def bird(kps, desc, bird_cols, bird_rows):
+        return Frame(np.ascontiguousarray(kps), np.ascontiguousarray(desc), 0.0, 0.0,
+                     float(np.float32(FRAME_GRID_BIRD) / np.float32(bird_cols)),
+                     float(np.float32(FRAME_GRID_BIRD) / np.float32(bird_rows)), FRAME_GRID_BIRD, FRAME_GRID_BIRD)
+
+    @property
+    def N(self):
+        return len(self.kps)
+
+    def view(self) -> FrameView:
+        return FrameView(self.kps.ctypes.data if len(self.kps) else None, self.desc.ctypes.data if len(self.kps) else None,
+                         len(self.kps), self.min_x, self.min_y, self.inv_w, self.inv_h, self.gcols, self.grows)
+
+    def AssignFeaturesToGrid(self):
+        """Frame::AssignFeaturesToGrid (src/Frame.cc:381-411) -> CSR (cell_start[gcols*grows+1], cell_items)."""
+        return grid_assign(self.kps, self.min_x, self.min_y, self.inv_w, self.inv_h, self.gcols, self.grows)
+
+
+def grid_assign(kps, min_x, min_y, inv_w, inv_h, gcols, grows):
+    L = _lib.load()
+    kps = np.ascontiguousarray(kps)
+    start = np.zeros(gcols * grows + 1, np.int32)
+    items = np.zeros(max(len(kps), 1), np.int32)
+    n = C.c_int32()
+    check(L.fbe_grid_assign(ptr(kps) if len(kps) else None, len(kps), min_x, min_y, inv_w, inv_h, gcols, grows,
+                            ptr(start), ptr(items), C.byref(n)))
+    return start, items[:n.value].copy()
+
+
+def BaseXY2BirdPixel(local_xyz: np.ndarray, bird_cols: int, bird_rows: int) -> np.ndarray:
+    """Converter::BaseXY2BirdPixel (src/Converter.cc:304-310), fp32, integer cols/2 (quirk Q12)."""
+    x = np.float32(bird_cols // 2) - local_xyz[:, 1].astype(np.float32) * np.float32(METER2PIXEL)
+    y = np.float32(bird_rows // 2) - (local_xyz[:, 0].astype(np.float32) - np.float32(REAR_AXLE_TO_CENTER)) * np.float32(METER2PIXEL)
+    return np.stack([x, y], axis=1).astype(np.float32)
+
+
+def transform_points(T: np.ndarray, pts: np.ndarray) -> np.ndarray:
+    """R*x + t with a row-major 4x4; fp32 products accumulated in fp64 then rounded (cv::gemm on CV_32F)."""
+    R = T[:3, :3].astype(np.float64)
+    t = T[:3, 3].astype(np.float32)
+    return ((pts.astype(np.float64) @ R.T).astype(np.float32) + t).astype(np.float32)
+
+
+class ORBmatcher:
+    TH_LOW = 50
+    TH_HIGH = 100
+    HISTO_LENGTH = 30
+
+    def __init__(self, nnratio: float = 0.6, checkOri: bool = True, device: int = 0):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        check(self._L.fbe_matcher_create(C.c_float(nnratio), int(bool(checkOri)), device, C.byref(self._h)))
+        self.mfNNratio, self.mbCheckOrientation = nnratio, checkOri
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.fbe_matcher_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    @staticmethod
+    def DescriptorDistance(a: np.ndarray, b: np.ndarray) -> int:
+        """ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1951-1967): host inline, never a device round trip."""
+        a = np.ascontiguousarray(a, np.uint8)
+        b = np.ascontiguousarray(b, np.uint8)
+        return int(_lib.load().fbe_hamming256(ptr(a), ptr(b)))
+
+    def SearchForInitialization(self, F1: Frame, F2: Frame, vbPrevMatched: np.ndarray, windowSize: int = 10):
+        """-> (nmatches, vnMatches12[int32 N1]); vbPrevMatched (float32 [N1,2]) is updated in place."""
+        assert vbPrevMatched.dtype == np.float32 and vbPrevMatched.flags.c_contiguous
+        m12 = np.full(F1.N, -1, np.int32)
+        n = C.c_int32()
+        v1, v2 = F1.view(), F2.view()
+        check(self._L.fbe_search_for_initialization(self._h, C.byref(v1), C.byref(v2), ptr(vbPrevMatched), ptr(m12),
+                                                    int(windowSize), C.byref(n)))
+        return n.value, m12
+
+    def BirdviewMatch(self, CurF: Frame, vRefKeysBird: np.ndarray, DescriptorsBird: np.ndarray, windowSize: int = 10):
+        """isProject == 0 path. -> (nmatches, DMatch array int32 [k,3] = (queryIdx, trainIdx, distance))."""
+        ref_k = np.ascontiguousarray(vRefKeysBird)
+        ref_d = np.ascontiguousarray(DescriptorsBird)
+        dm = np.zeros((max(len(ref_k), 1), 3), np.int32)
+        nd, n = C.c_int32(), C.c_int32()
+        v = CurF.view()
+        check(self._L.fbe_birdview_match(self._h, ptr(ref_k) if len(ref_k) else None, ptr(ref_d) if len(ref_k) else None,
+                                         len(ref_k), C.byref(v), int(windowSize), ptr(dm), C.byref(nd), C.byref(n)))
+        return n.value, dm[:nd.value].copy()
+
+    def BirdMapPointMatch(self, CurF: Frame, mp_world: np.ndarray, mp_desc: np.ndarray, Tbw: np.ndarray, Tcw: np.ndarray,
+                          cur_cam_xyz: np.ndarray, bird_cols: int, bird_rows: int, windowSize: int = 10, filterSize: float = 0.05):
+        """mp_world: float32 [n,3] (NaN row = NULL MapPointBird*).  -> (InlierMatches, vnMatches12, assigned[cur.N])."""
+        n_mp = len(mp_world)
+        local = transform_points(Tbw, np.nan_to_num(mp_world))
+        pix = BaseXY2BirdPixel(local, bird_cols, bird_rows)
+        skip = np.isnan(mp_world[:, 0]) | (np.abs(local[:, 2]) > 0.2) | (pix[:, 0] < 0) | (pix[:, 0] >= bird_cols) | \
+            (pix[:, 1] < 0) | (pix[:, 1] >= bird_rows)
+        pix[skip, 0] = np.nan
+        pix = np.ascontiguousarray(pix, np.float32)
+        mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+        m12 = np.full(n_mp, -1, np.int32)
+        n = C.c_int32()
+        v = CurF.view()
+        check(self._L.fbe_bird_map_point_match(self._h, ptr(pix), ptr(mp_desc), n_mp, C.byref(v), int(windowSize), ptr(m12), C.byref(n)))
+        return (*bird_map_second_pass(m12, mp_world, Tcw, cur_cam_xyz, CurF.N, filterSize), m12)
+
+    def SearchByProjectionLast(self, CurrentFrame: Frame, last_kps: np.ndarray, last_proj: np.ndarray, last_mp_desc: np.ndarray,
+                               th: float, cur_taken=None, last_has_obs=None):
+        """SearchByProjection(CurrentFrame, LastFrame, th, bMono=true) with host-projected (u,v) (NaN u = skipped).
+        -> (nmatches, cur_mp[int32 N] = last-frame index assigned to each keypoint or -1)."""
+        last_kps = np.ascontiguousarray(last_kps)
+        last_proj = np.ascontiguousarray(last_proj, np.float32)
+        last_mp_desc = np.ascontiguousarray(last_mp_desc, np.uint8)
+        cur_mp = np.full(max(CurrentFrame.N, 1), -1, np.int32)
+        n = C.c_int32()
+        v = CurrentFrame.view()
+        sf = np.ascontiguousarray(CurrentFrame.scale_factors, np.float32)
+        tk = None if cur_taken is None else np.ascontiguousarray(cur_taken, np.uint8)
+        ho = None if last_has_obs is None else np.ascontiguousarray(last_has_obs, np.uint8)
+        check(self._L.fbe_search_by_projection_last(self._h, C.byref(v), ptr(last_kps), ptr(last_proj), ptr(last_mp_desc), len(last_kps),
+                                                    ptr(sf), len(sf), None if tk is None else ptr(tk), None if ho is None else ptr(ho),
+                                                    C.c_float(th), ptr(cur_mp), C.byref(n)))
+        return n.value, cur_mp[:CurrentFrame.N]
+
+    def SearchByProjectionMap(self, F: Frame, mp_proj, mp_level, mp_viewcos, mp_desc, th: float = 1.0, cur_taken=None, mp_has_obs=None):
+        """SearchByProjection(F, vpMapPoints, th) on the fields Frame::isInFrustum fills."""
+        mp_proj = np.ascontiguousarray(mp_proj, np.float32)
+        mp_level = np.ascontiguousarray(mp_level, np.int32)
+        mp_viewcos = np.ascontiguousarray(mp_viewcos, np.float32)
+        mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+        cur_mp = np.full(max(F.N, 1), -1, np.int32)
+        n = C.c_int32()
+        v = F.view()
+        sf = np.ascontiguousarray(F.scale_factors, np.float32)
+        tk = None if cur_taken is None else np.ascontiguousarray(cur_taken, np.uint8)
+        ho = None if mp_has_obs is None else np.ascontiguousarray(mp_has_obs, np.uint8)
+        check(self._L.fbe_search_by_projection_map(self._h, C.byref(v), ptr(sf), len(sf), ptr(mp_proj), ptr(mp_level), ptr(mp_viewcos),
+                                                   ptr(mp_desc), len(mp_level), None if tk is None else ptr(tk),
+                                                   None if ho is None else ptr(ho), C.c_float(th), ptr(cur_mp), C.byref(n)))
+        return n.value, cur_mp[:F.N]
+
+    def SearchByBoW(self, kf_kps, kf_desc, kf_has_mp, kf_featvec, F: Frame, f_featvec):
+        """SearchByBoW(KeyFrame*, Frame&, matches).  Feature vectors: (node_ids[nn], start[nn+1], items).
+        -> (nmatches, f_mp[int32 N] = key-frame keypoint index per frame keypoint or -1)."""
+        kf_kps = np.ascontiguousarray(kf_kps)
+        kf_desc = np.ascontiguousarray(kf_desc, np.uint8)
+        kf_has_mp = np.ascontiguousarray(kf_has_mp, np.uint8)
+        ka, kb, kc = (np.ascontiguousarray(a, np.int32) for a in kf_featvec)
+        fa, fb, fc = (np.ascontiguousarray(a, np.int32) for a in f_featvec)
+        f_mp = np.full(max(F.N, 1), -1, np.int32)
+        n = C.c_int32()
+        check(self._L.fbe_search_by_bow(self._h, ptr(kf_kps), ptr(kf_desc), len(kf_kps), ptr(kf_has_mp), ptr(ka), ptr(kb), ptr(kc), len(ka),
+                                        ptr(F.kps), ptr(F.desc), F.N, ptr(fa), ptr(fb), ptr(fc), len(fa), ptr(f_mp), C.byref(n)))
+        return n.value, f_mp[:F.N]
+
+    def BruteForceTop2(self, q_desc, t_desc):
+        q_desc = np.ascontiguousarray(q_desc, np.uint8)
+        t_desc = np.ascontiguousarray(t_desc, np.uint8)
+        nq = len(q_desc)
+        bi, bd, sd = (np.zeros(max(nq, 1), np.int32) for _ in range(3))
+        check(self._L.fbe_bruteforce_top2(self._h, ptr(q_desc), nq, ptr(t_desc), len(t_desc), ptr(bi), ptr(bd), ptr(sd)))
+        return bi[:nq], bd[:nq], sd[:nq]
+
+
+def bird_map_second_pass(m12, mp_world, Tcw, cur_cam_xyz, n_cur, filter_size):
+    """BirdMapPointMatch second pass (src/ORBmatcher.cc:1865-1895): host arithmetic, as in the reference.
+    -> (InlierMatches, assigned[n_cur] = map point index written to mvpMapPointsBird[k] or -1)."""
+    assigned = np.full(n_cur, -1, np.int32)
+    inliers = 0
+    idx = np.nonzero(m12 > 0)[0]                      # `> 0`: a match to keypoint 0 is dropped (quirk Q8)
+    if len(idx):
+        pc = transform_points(Tcw, mp_world[idx])
+        d = np.linalg.norm((pc - cur_cam_xyz[m12[idx]].astype(np.float32)).astype(np.float64), axis=1)
+        for i1, dis in zip(idx, d):
+            if dis < filter_size:
+                assigned[m12[i1]] = i1                # last writer in i1 order wins
+                inliers += 1
+    return inliers, assigned

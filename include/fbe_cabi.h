@@ -144,34 +144,35 @@ FBE_API int fbe_birdview_match(fbe_matcher* m, const fbe_keypoint* ref_kps, cons
                        const fbe_frame_view* cur, int32_t window_size, int32_t* dmatches /* n_ref x 3 */,
                        int32_t* n_dmatches, int32_t* nmatches);
 
-/* ORBmatcher::BirdMapPointMatch, src/ORBmatcher.cc:1763-1902.
- * Map points: world xyz (n x 3 floats; NaN x marks a NULL MapPointBird*), descriptors n x 32.
- * tbw / tcw: row-major 4x4 float (Frame::Tbc*mTcw and mTcw).  cur_cam_xyz: mvKeysBirdCamXYZ, cur->n x 3.
- * Outputs: matches12 (n ints, -1 none), assigned_mp (cur->n ints: index of the map point written to
- * mvpMapPointsBird[k], -1 untouched), *inliers = return value of the reference. */
-FBE_API int fbe_bird_map_point_match(fbe_matcher* m, const float* mp_world, const uint8_t* mp_desc, int32_t n_mp,
-                             const fbe_frame_view* cur, const float* cur_cam_xyz, const float* tbw,
-                             const float* tcw, int32_t bird_cols, int32_t bird_rows, int32_t window_size,
-                             float filter_size, int32_t* matches12, int32_t* assigned_mp, int32_t* inliers);
+/* ORBmatcher::BirdMapPointMatch, first pass, src/ORBmatcher.cc:1763-1863 (the window search + ratio test).
+ * The reference's cv::Mat arithmetic stays on the host: the drop-in shim computes, exactly as :1797-1808 do,
+ * local = Tbw*world, the |z| > 0.2 rejection, Converter::BaseXY2BirdPixel and the image-bounds test, and passes the
+ * resulting bird pixel per map point (mp_pix: n x 2 floats; NaN x = skipped).  It also runs the second pass
+ * (:1865-1895, distance filter + mvpMapPointsBird assignment) on the returned matches12.
+ * Output: matches12[n_mp] = bird keypoint index or -1. */
+FBE_API int fbe_bird_map_point_match(fbe_matcher* m, const float* mp_pix, const uint8_t* mp_desc, int32_t n_mp,
+                                     const fbe_frame_view* cur, int32_t window_size, int32_t* matches12,
+                                     int32_t* nmatches);
 
 /* ORBmatcher::SearchByProjection(Frame&, const Frame& LastFrame, th, bMono=true), src/ORBmatcher.cc:1329-1471.
- * last_*: per last-frame keypoint i: has_mp[i] != 0 iff mvpMapPoints[i] && !mvbOutlier[i]; world xyz (n x 3);
- * descriptor of the map point (n x 32); octave and angle come from last->kps.  tcw: CurrentFrame.mTcw (4x4).
- * cur_taken[k] != 0 iff CurrentFrame.mvpMapPoints[k] has Observations()>0 on entry.
+ * The projection (:1359-1376, cv::Mat fp32) stays in the host shim: last_proj is n_last x 2 (u,v), NaN u = skipped
+ * (no map point, outlier, invzc < 0, outside the image bounds).  last_kps supplies octave and angle.
+ * cur_taken[k] != 0 iff CurrentFrame.mvpMapPoints[k] has Observations()>0 on entry (NULL = none);
+ * last_has_obs[i] != 0 iff that map point has Observations()>0, i.e. blocks its keypoint once assigned (NULL = all).
  * Output: cur_mp[k] = index i of the last-frame map point assigned to keypoint k, -1 none. */
-FBE_API int fbe_search_by_projection_last(fbe_matcher* m, const fbe_frame_view* cur, const fbe_frame_view* last,
-                                  const uint8_t* last_has_mp, const float* last_world, const uint8_t* last_mp_desc,
-                                  const float* tcw, float fx, float fy, float cx, float cy, float max_x,
-                                  float max_y, const uint8_t* cur_taken, float th, int32_t* cur_mp,
-                                  int32_t* nmatches);
+FBE_API int fbe_search_by_projection_last(fbe_matcher* m, const fbe_frame_view* cur, const fbe_keypoint* last_kps,
+                                          const float* last_proj, const uint8_t* last_mp_desc, int32_t n_last,
+                                          const float* scale_factors, int32_t nlevels, const uint8_t* cur_taken,
+                                          const uint8_t* last_has_obs, float th, int32_t* cur_mp, int32_t* nmatches);
 
 /* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th), src/ORBmatcher.cc:46-130.
  * Per map point (already filtered by mbTrackInView && !isBad): proj (n x 2), predicted level, view cosine,
- * descriptor.  scale_factors: F.mvScaleFactors.  cur_taken as above (updated by accepted matches in order). */
+ * descriptor -- the fields Frame::isInFrustum fills.  scale_factors: F.mvScaleFactors.  Monocular (mvuRight < 0). */
 FBE_API int fbe_search_by_projection_map(fbe_matcher* m, const fbe_frame_view* cur, const float* scale_factors,
-                                 int32_t nlevels, const float* mp_proj, const int32_t* mp_level,
-                                 const float* mp_viewcos, const uint8_t* mp_desc, int32_t n_mp,
-                                 const uint8_t* cur_taken, float th, int32_t* cur_mp, int32_t* nmatches);
+                                         int32_t nlevels, const float* mp_proj, const int32_t* mp_level,
+                                         const float* mp_viewcos, const uint8_t* mp_desc, int32_t n_mp,
+                                         const uint8_t* cur_taken, const uint8_t* mp_has_obs, float th,
+                                         int32_t* cur_mp, int32_t* nmatches);
 
 /* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, matches), src/ORBmatcher.cc:160-289.
  * Feature vectors as CSR over ascending node ids: node_ids[nn], start[nn+1], items[...].

@@ -1,1 +1,433 @@
-// placeholder, filled in below
+// ORACLE (test infrastructure, never shipped, never on the product path).
+//
+// CPU restatement, on plain arrays, of the reference's keypoint grid and of the named ORBmatcher searches.
+// The reference translation units (src/Frame.cc, src/ORBmatcher.cc) drag in Eigen/g2o/DBoW2/OpenCV and cannot be
+// compiled in this image, so these functions follow the reference line by line instead (file:line below, relative
+// to /root/reference).  "parity unpinned" for this file: the reference ships no tests or golden vectors for these
+// paths; it is pinned only by review against the cited lines and by hand-built cases in
+// tests/test_oracle_match.py that exercise each documented quirk.
+//   Frame::AssignFeaturesToGrid / PosInGrid / PosInGridBirdview   src/Frame.cc:381-411, 548-570
+//   Frame::GetFeaturesInArea / GetFeaturesInAreaBirdview           src/Frame.cc:493-546, 572-626
+//   ORBmatcher::DescriptorDistance                                 src/ORBmatcher.cc:1951-1967
+//   ORBmatcher::ComputeThreeMaxima                                 src/ORBmatcher.cc:1905-1946
+//   ORBmatcher::SearchForInitialization                            src/ORBmatcher.cc:406-521
+//   ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) src/ORBmatcher.cc:46-130
+//   ORBmatcher::SearchByProjection(Frame&, const Frame&, th, mono) src/ORBmatcher.cc:1329-1471
+//   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...)                src/ORBmatcher.cc:160-289
+//   ORBmatcher::BirdviewMatch (isProject == 0)                     src/ORBmatcher.cc:1602-1760
+//   ORBmatcher::BirdMapPointMatch (first pass)                     src/ORBmatcher.cc:1763-1863
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+namespace {
+
+const int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;
+
+struct Kp { float x, y, size, angle, response; int32_t octave, class_id; };
+
+struct FrameView {
+    const Kp* kps;
+    const uint8_t* desc;
+    int32_t n;
+    float min_x, min_y, inv_w, inv_h;
+    int32_t gcols, grows;
+};
+
+struct Grid {
+    int gcols, grows;
+    std::vector<std::vector<int> > cell;   // [ix*grows + iy], push_back order
+};
+
+Grid build_grid(const FrameView& f) {
+    Grid g;
+    g.gcols = f.gcols; g.grows = f.grows;
+    g.cell.assign((size_t)f.gcols * f.grows, std::vector<int>());
+    for (int i = 0; i < f.n; ++i) {
+        int px = (int)std::round((f.kps[i].x - f.min_x) * f.inv_w);
+        int py = (int)std::round((f.kps[i].y - f.min_y) * f.inv_h);
+        if (px < 0 || px >= f.gcols || py < 0 || py >= f.grows) continue;
+        g.cell[(size_t)px * f.grows + py].push_back(i);
+    }
+    return g;
+}
+
+// upper_inclusive = true : Frame::GetFeaturesInArea        (ix <= nMaxCellX)
+// upper_inclusive = false: Frame::GetFeaturesInAreaBirdview (ix <  nMaxCellX)   -- quirk Q2
+std::vector<int> features_in_area(const FrameView& f, const Grid& g, float x, float y, float r, int minLevel,
+                                  int maxLevel, bool upper_inclusive) {
+    std::vector<int> out;
+    const int nMinCellX = std::max(0, (int)std::floor((x - f.min_x - r) * f.inv_w));
+    if (nMinCellX >= g.gcols) return out;
+    const int nMaxCellX = std::min(g.gcols - 1, (int)std::ceil((x - f.min_x + r) * f.inv_w));
+    if (nMaxCellX < 0) return out;
+    const int nMinCellY = std::max(0, (int)std::floor((y - f.min_y - r) * f.inv_h));
+    if (nMinCellY >= g.grows) return out;
+    const int nMaxCellY = std::min(g.grows - 1, (int)std::ceil((y - f.min_y + r) * f.inv_h));
+    if (nMaxCellY < 0) return out;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    const int ex = upper_inclusive ? 1 : 0;
+    for (int ix = nMinCellX; ix < nMaxCellX + ex; ++ix)
+        for (int iy = nMinCellY; iy < nMaxCellY + ex; ++iy) {
+            const std::vector<int>& c = g.cell[(size_t)ix * g.grows + iy];
+            for (size_t j = 0; j < c.size(); ++j) {
+                const Kp& kp = f.kps[c[j]];
+                if (bCheckLevels) {
+                    if (kp.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                }
+                const float dx = kp.x - x, dy = kp.y - y;
+                if (std::fabs(dx) < r && std::fabs(dy) < r) out.push_back(c[j]);
+            }
+        }
+    return out;
+}
+
+int hamming(const uint8_t* a, const uint8_t* b) {
+    int dist = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint32_t pa, pb;
+        std::memcpy(&pa, a + 4 * i, 4);
+        std::memcpy(&pb, b + 4 * i, 4);
+        unsigned v = pa ^ pb;
+        v = v - ((v >> 1) & 0x55555555);
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+        dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+    }
+    return dist;
+}
+
+void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; ++i) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+int rot_bin(float a1, float a2) {
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)std::round(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orc_hamming256(const uint8_t* a, const uint8_t* b) { return hamming(a, b); }
+
+int orc_grid_assign(const Kp* kps, int n, float min_x, float min_y, float inv_w, float inv_h, int gcols, int grows,
+                    int32_t* cell_start, int32_t* cell_items) {
+    FrameView f{kps, nullptr, n, min_x, min_y, inv_w, inv_h, gcols, grows};
+    Grid g = build_grid(f);
+    int off = 0;
+    for (int c = 0; c < gcols * grows; ++c) {
+        cell_start[c] = off;
+        for (size_t j = 0; j < g.cell[c].size(); ++j) cell_items[off++] = g.cell[c][j];
+    }
+    cell_start[gcols * grows] = off;
+    return off;
+}
+
+// candidate list of one query, for direct tests of the area queries
+int orc_features_in_area(const FrameView* f, float x, float y, float r, int minLevel, int maxLevel, int upper_inclusive,
+                         int32_t* out, int cap) {
+    Grid g = build_grid(*f);
+    std::vector<int> v = features_in_area(*f, g, x, y, r, minLevel, maxLevel, upper_inclusive != 0);
+    for (size_t i = 0; i < v.size() && (int)i < cap; ++i) out[i] = v[i];
+    return (int)v.size();
+}
+
+int orc_search_for_initialization(const FrameView* F1, const FrameView* F2, float* prev_matched, int32_t* matches12,
+                                  int window, float nn_ratio, int check_ori) {
+    int nmatches = 0;
+    for (int i = 0; i < F1->n; ++i) matches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    std::vector<int> vMatchedDistance(F2->n, INT_MAX), vnMatches21(F2->n, -1);
+    Grid g2 = build_grid(*F2);
+    for (int i1 = 0; i1 < F1->n; ++i1) {
+        const Kp& kp1 = F1->kps[i1];
+        const int level1 = kp1.octave;
+        if (level1 > 0) continue;
+        std::vector<int> cand = features_in_area(*F2, g2, prev_matched[2 * i1], prev_matched[2 * i1 + 1], (float)window,
+                                                 level1, level1, true);
+        if (cand.empty()) continue;
+        const uint8_t* d1 = F1->desc + (size_t)i1 * 32;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (size_t k = 0; k < cand.size(); ++k) {
+            const int i2 = cand[k];
+            const int dist = hamming(d1, F2->desc + (size_t)i2 * 32);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nn_ratio) {
+                if (vnMatches21[bestIdx2] >= 0) { matches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                matches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (check_ori) rotHist[rot_bin(F1->kps[i1].angle, F2->kps[bestIdx2].angle)].push_back(i1);
+            }
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); ++j) {
+                const int idx1 = rotHist[i][j];
+                if (matches12[idx1] >= 0) { matches12[idx1] = -1; nmatches--; }
+            }
+        }
+    }
+    for (int i1 = 0; i1 < F1->n; ++i1)
+        if (matches12[i1] >= 0) {
+            prev_matched[2 * i1] = F2->kps[matches12[i1]].x;
+            prev_matched[2 * i1 + 1] = F2->kps[matches12[i1]].y;
+        }
+    return nmatches;
+}
+
+// BirdviewMatch, isProject == 0.  dmatches: up to n_ref triples (queryIdx, trainIdx, distance).
+int orc_birdview_match(const Kp* ref_kps, const uint8_t* ref_desc, int n_ref, const FrameView* cur, int window,
+                       float nn_ratio, int check_ori, int32_t* dmatches, int32_t* n_dmatches) {
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    std::vector<int> vnMatches21(cur->n, -1), vnMatches12(n_ref, -1), vMatchedDistance(n_ref, INT_MAX);
+    Grid g = build_grid(*cur);
+    for (int i1 = 0; i1 < n_ref; ++i1) {
+        const Kp& kp1 = ref_kps[i1];
+        const int level1 = kp1.octave;
+        if (level1 > 0) continue;
+        std::vector<int> cand = features_in_area(*cur, g, kp1.x, kp1.y, (float)window, level1, level1, false);
+        if (cand.empty()) continue;
+        const uint8_t* d1 = ref_desc + (size_t)i1 * 32;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx = -1;
+        for (size_t k = 0; k < cand.size(); ++k) {
+            const int i2 = cand[k];
+            if (i2 >= cur->n) continue;
+            const int dist = hamming(d1, cur->desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nn_ratio) {
+                vnMatches21[bestIdx] = i1;
+                vnMatches12[i1] = bestIdx;
+                vMatchedDistance[i1] = bestDist;
+                nmatches++;
+            }
+            if (check_ori) rotHist[rot_bin(kp1.angle, cur->kps[bestIdx].angle)].push_back(i1);   // even if the ratio test failed (Q7)
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); ++j) {
+                const int idx1 = rotHist[i][j];
+                if (vnMatches12[idx1] >= 0) { vnMatches21[vnMatches12[idx1]] = -1; vnMatches12[idx1] = -1; nmatches--; }
+            }
+        }
+    }
+    int nd = 0;
+    for (int i = 0; i < n_ref; ++i)
+        if (vnMatches12[i] > 0) {   // index 0 is dropped (Q8)
+            dmatches[3 * nd] = i; dmatches[3 * nd + 1] = vnMatches12[i]; dmatches[3 * nd + 2] = vMatchedDistance[i];
+            ++nd;
+        }
+    *n_dmatches = nd;
+    return nmatches;
+}
+
+// BirdMapPointMatch, first pass (:1763-1863).  mp_pix: n x 2 projected bird pixels, NaN x = map point skipped
+// (NULL pointer, |z| > 0.2 or outside the image -- decided by the caller with the reference's host arithmetic).
+int orc_bird_map_point_match(const float* mp_pix, const uint8_t* mp_desc, int n_mp, const FrameView* cur, int window,
+                             float nn_ratio, int32_t* matches12) {
+    int nmatches = 0;
+    Grid g = build_grid(*cur);
+    for (int i1 = 0; i1 < n_mp; ++i1) {
+        matches12[i1] = -1;
+        const float px = mp_pix[2 * i1], py = mp_pix[2 * i1 + 1];
+        if (std::isnan(px)) continue;
+        std::vector<int> cand = features_in_area(*cur, g, px, py, (float)window, -1, -1, false);
+        if (cand.empty()) continue;
+        const uint8_t* d1 = mp_desc + (size_t)i1 * 32;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx = -1;
+        for (size_t k = 0; k < cand.size(); ++k) {
+            const int i2 = cand[k];
+            if (i2 >= cur->n) continue;
+            const int dist = hamming(d1, cur->desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW && bestDist < (float)bestDist2 * nn_ratio) { matches12[i1] = bestIdx; nmatches++; }
+    }
+    return nmatches;
+}
+
+// SearchByProjection(CurrentFrame, LastFrame, th, bMono = true).  last_proj: n_last x 2 projected (u,v), NaN u =
+// skipped (no map point, outlier, behind the camera or outside the image bounds -- caller's host arithmetic).
+// cur_taken: 1 where CurrentFrame.mvpMapPoints[k] has Observations() > 0 on entry.  last_has_obs: 1 where the
+// last-frame map point has Observations() > 0 (so that, once assigned, it blocks its keypoint); NULL = all.
+int orc_search_by_projection_last(const FrameView* cur, const Kp* last_kps, const float* last_proj,
+                                  const uint8_t* last_mp_desc, int n_last, const float* scale_factors,
+                                  const uint8_t* cur_taken, const uint8_t* last_has_obs, float th, int check_ori,
+                                  int32_t* cur_mp) {
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    Grid g = build_grid(*cur);
+    std::vector<uint8_t> taken(cur->n, 0);
+    for (int k = 0; k < cur->n; ++k) { cur_mp[k] = -1; taken[k] = cur_taken ? cur_taken[k] : 0; }
+    for (int i = 0; i < n_last; ++i) {
+        const float u = last_proj[2 * i], v = last_proj[2 * i + 1];
+        if (std::isnan(u)) continue;
+        const int nLastOctave = last_kps[i].octave;
+        const float radius = th * scale_factors[nLastOctave];
+        std::vector<int> cand = features_in_area(*cur, g, u, v, radius, nLastOctave - 1, nLastOctave + 1, true);
+        if (cand.empty()) continue;
+        const uint8_t* dMP = last_mp_desc + (size_t)i * 32;
+        int bestDist = 256, bestIdx2 = -1;
+        for (size_t k = 0; k < cand.size(); ++k) {
+            const int i2 = cand[k];
+            if (taken[i2]) continue;
+            const int dist = hamming(dMP, cur->desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            cur_mp[bestIdx2] = i;
+            if (!last_has_obs || last_has_obs[i]) taken[bestIdx2] = 1;
+            nmatches++;
+            if (check_ori) rotHist[rot_bin(last_kps[i].angle, cur->kps[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); ++j) { cur_mp[rotHist[i][j]] = -1; nmatches--; }
+    }
+    return nmatches;
+}
+
+// SearchByProjection(F, vpMapPoints, th).  Map points already filtered by mbTrackInView && !isBad().
+int orc_search_by_projection_map(const FrameView* cur, const float* scale_factors, const float* mp_proj,
+                                 const int32_t* mp_level, const float* mp_viewcos, const uint8_t* mp_desc, int n_mp,
+                                 const uint8_t* cur_taken, const uint8_t* mp_has_obs, float th, float nn_ratio,
+                                 int32_t* cur_mp) {
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    Grid g = build_grid(*cur);
+    std::vector<uint8_t> taken(cur->n, 0);
+    for (int k = 0; k < cur->n; ++k) { cur_mp[k] = -1; taken[k] = cur_taken ? cur_taken[k] : 0; }
+    for (int iMP = 0; iMP < n_mp; ++iMP) {
+        const int nPredictedLevel = mp_level[iMP];
+        float r = mp_viewcos[iMP] > 0.998 ? 2.5f : 4.0f;
+        if (bFactor) r *= th;
+        std::vector<int> cand = features_in_area(*cur, g, mp_proj[2 * iMP], mp_proj[2 * iMP + 1],
+                                                 r * scale_factors[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel, true);
+        if (cand.empty()) continue;
+        const uint8_t* d = mp_desc + (size_t)iMP * 32;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (size_t k = 0; k < cand.size(); ++k) {
+            const int idx = cand[k];
+            if (taken[idx]) continue;
+            const int dist = hamming(d, cur->desc + (size_t)idx * 32);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = cur->kps[idx].octave; bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = cur->kps[idx].octave; bestDist2 = dist;
+            }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > nn_ratio * bestDist2) continue;
+            cur_mp[bestIdx] = iMP;
+            if (!mp_has_obs || mp_has_obs[iMP]) taken[bestIdx] = 1;
+            nmatches++;
+        }
+    }
+    return nmatches;
+}
+
+// SearchByBoW(KeyFrame*, Frame&, matches).  Feature vectors as CSR over ascending node ids.
+int orc_search_by_bow(const Kp* kf_kps, const uint8_t* kf_desc, int n_kf, const uint8_t* kf_has_mp,
+                      const int32_t* kf_node_ids, const int32_t* kf_start, const int32_t* kf_items, int kf_nn,
+                      const Kp* f_kps, const uint8_t* f_desc, int n_f, const int32_t* f_node_ids,
+                      const int32_t* f_start, const int32_t* f_items, int f_nn, float nn_ratio, int check_ori,
+                      int32_t* f_mp) {
+    (void)n_kf;
+    for (int k = 0; k < n_f; ++k) f_mp[k] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int a = 0, b = 0;
+    while (a < kf_nn && b < f_nn) {
+        if (kf_node_ids[a] == f_node_ids[b]) {
+            for (int p = kf_start[a]; p < kf_start[a + 1]; ++p) {
+                const int realIdxKF = kf_items[p];
+                if (!kf_has_mp[realIdxKF]) continue;
+                const uint8_t* dKF = kf_desc + (size_t)realIdxKF * 32;
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                for (int q = f_start[b]; q < f_start[b + 1]; ++q) {
+                    const int realIdxF = f_items[q];
+                    if (f_mp[realIdxF] >= 0) continue;
+                    const int dist = hamming(dKF, f_desc + (size_t)realIdxF * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 <= TH_LOW) {
+                    if ((float)bestDist1 < nn_ratio * (float)bestDist2) {
+                        f_mp[bestIdxF] = realIdxKF;
+                        if (check_ori) rotHist[rot_bin(kf_kps[realIdxKF].angle, f_kps[bestIdxF].angle)].push_back(bestIdxF);
+                        nmatches++;
+                    }
+                }
+            }
+            ++a; ++b;
+        } else if (kf_node_ids[a] < f_node_ids[b]) {
+            while (a < kf_nn && kf_node_ids[a] < f_node_ids[b]) ++a;      // lower_bound
+        } else {
+            while (b < f_nn && f_node_ids[b] < kf_node_ids[a]) ++b;
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); ++j) { f_mp[rotHist[i][j]] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+// brute-force top-2 (stress config C5): ties -> lowest target index, second counts duplicates
+void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* best_idx, int32_t* best_dist,
+                         int32_t* second_dist) {
+    for (int i = 0; i < nq; ++i) {
+        int b1 = 256 + 1, b2 = 256 + 1, bi = -1;
+        for (int j = 0; j < nt; ++j) {
+            const int d = hamming(q + (size_t)i * 32, t + (size_t)j * 32);
+            if (d < b1) { b2 = b1; b1 = d; bi = j; }
+            else if (d < b2) b2 = d;
+        }
+        best_idx[i] = bi; best_dist[i] = b1; second_dist[i] = b2;
+    }
+}
+
+}  // extern "C"

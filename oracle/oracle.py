@@ -161,3 +161,105 @@ class RefExtractor:
         out = np.zeros((r.value + 38, c.value + 38), np.uint8)
         self.R.ref_pyramid_level(self.h, _p(img), img.shape[0], img.shape[1], img.strides[0], level, _p(out), out.strides[0], C.byref(r), C.byref(c))
         return out
+
+
+class OFrameView(C.Structure):
+    _fields_ = [("kps", C.c_void_p), ("desc", C.c_void_p), ("n", C.c_int32),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("inv_w", C.c_float), ("inv_h", C.c_float),
+                ("gcols", C.c_int32), ("grows", C.c_int32)]
+
+
+def _view(f):
+    """f: any object with kps, desc, min_x, min_y, inv_w, inv_h, gcols, grows (e.g. the package's matcher.Frame)."""
+    return OFrameView(f.kps.ctypes.data if len(f.kps) else None, f.desc.ctypes.data if len(f.kps) else None, len(f.kps),
+                      f.min_x, f.min_y, f.inv_w, f.inv_h, f.gcols, f.grows)
+
+
+def _fp(x):
+    return C.c_float(float(x))
+
+
+def hamming256(a, b):
+    return lib().orc_hamming256(_p(np.ascontiguousarray(a, np.uint8)), _p(np.ascontiguousarray(b, np.uint8)))
+
+
+def grid_assign(kps, min_x, min_y, inv_w, inv_h, gcols, grows):
+    kps = np.ascontiguousarray(kps)
+    start = np.zeros(gcols * grows + 1, np.int32)
+    items = np.zeros(max(len(kps), 1), np.int32)
+    n = lib().orc_grid_assign(_p(kps), len(kps), _fp(min_x), _fp(min_y), _fp(inv_w), _fp(inv_h), gcols, grows, _p(start), _p(items))
+    return start, items[:n].copy()
+
+
+def features_in_area(f, x, y, r, min_level=-1, max_level=-1, upper_inclusive=True):
+    v = _view(f)
+    out = np.zeros(max(len(f.kps), 1), np.int32)
+    n = lib().orc_features_in_area(C.byref(v), _fp(x), _fp(y), _fp(r), min_level, max_level, int(upper_inclusive), _p(out), len(out))
+    return out[:n].copy()
+
+
+def search_for_initialization(f1, f2, prev_matched, window, nn_ratio, check_ori):
+    v1, v2 = _view(f1), _view(f2)
+    m12 = np.full(len(f1.kps), -1, np.int32)
+    n = lib().orc_search_for_initialization(C.byref(v1), C.byref(v2), _p(prev_matched), _p(m12), int(window), _fp(nn_ratio), int(check_ori))
+    return n, m12
+
+
+def birdview_match(ref_kps, ref_desc, cur, window, nn_ratio, check_ori):
+    v = _view(cur)
+    ref_kps = np.ascontiguousarray(ref_kps); ref_desc = np.ascontiguousarray(ref_desc)
+    dm = np.zeros((max(len(ref_kps), 1), 3), np.int32)
+    nd = C.c_int32()
+    n = lib().orc_birdview_match(_p(ref_kps), _p(ref_desc), len(ref_kps), C.byref(v), int(window), _fp(nn_ratio), int(check_ori), _p(dm), C.byref(nd))
+    return n, dm[:nd.value].copy()
+
+
+def bird_map_point_match(mp_pix, mp_desc, cur, window, nn_ratio):
+    v = _view(cur)
+    mp_pix = np.ascontiguousarray(mp_pix, np.float32); mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+    m12 = np.full(len(mp_pix), -1, np.int32)
+    n = lib().orc_bird_map_point_match(_p(mp_pix), _p(mp_desc), len(mp_pix), C.byref(v), int(window), _fp(nn_ratio), _p(m12))
+    return n, m12
+
+
+def search_by_projection_last(cur, last_kps, last_proj, last_mp_desc, scale_factors, th, check_ori, cur_taken=None, last_has_obs=None):
+    v = _view(cur)
+    last_kps = np.ascontiguousarray(last_kps); last_proj = np.ascontiguousarray(last_proj, np.float32)
+    last_mp_desc = np.ascontiguousarray(last_mp_desc, np.uint8); sf = np.ascontiguousarray(scale_factors, np.float32)
+    cur_mp = np.full(max(len(cur.kps), 1), -1, np.int32)
+    tk = None if cur_taken is None else np.ascontiguousarray(cur_taken, np.uint8)
+    ho = None if last_has_obs is None else np.ascontiguousarray(last_has_obs, np.uint8)
+    n = lib().orc_search_by_projection_last(C.byref(v), _p(last_kps), _p(last_proj), _p(last_mp_desc), len(last_kps), _p(sf),
+                                            None if tk is None else _p(tk), None if ho is None else _p(ho), _fp(th), int(check_ori), _p(cur_mp))
+    return n, cur_mp[:len(cur.kps)]
+
+
+def search_by_projection_map(cur, scale_factors, mp_proj, mp_level, mp_viewcos, mp_desc, th, nn_ratio, cur_taken=None, mp_has_obs=None):
+    v = _view(cur)
+    sf = np.ascontiguousarray(scale_factors, np.float32); mp_proj = np.ascontiguousarray(mp_proj, np.float32)
+    mp_level = np.ascontiguousarray(mp_level, np.int32); mp_viewcos = np.ascontiguousarray(mp_viewcos, np.float32)
+    mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+    cur_mp = np.full(max(len(cur.kps), 1), -1, np.int32)
+    tk = None if cur_taken is None else np.ascontiguousarray(cur_taken, np.uint8)
+    ho = None if mp_has_obs is None else np.ascontiguousarray(mp_has_obs, np.uint8)
+    n = lib().orc_search_by_projection_map(C.byref(v), _p(sf), _p(mp_proj), _p(mp_level), _p(mp_viewcos), _p(mp_desc), len(mp_level),
+                                           None if tk is None else _p(tk), None if ho is None else _p(ho), _fp(th), _fp(nn_ratio), _p(cur_mp))
+    return n, cur_mp[:len(cur.kps)]
+
+
+def search_by_bow(kf_kps, kf_desc, kf_has_mp, kf_fv, f_kps, f_desc, f_fv, nn_ratio, check_ori):
+    kf_kps = np.ascontiguousarray(kf_kps); kf_desc = np.ascontiguousarray(kf_desc, np.uint8); kf_has_mp = np.ascontiguousarray(kf_has_mp, np.uint8)
+    f_kps = np.ascontiguousarray(f_kps); f_desc = np.ascontiguousarray(f_desc, np.uint8)
+    ka, kb, kc = (np.ascontiguousarray(a, np.int32) for a in kf_fv)
+    fa, fb, fc = (np.ascontiguousarray(a, np.int32) for a in f_fv)
+    f_mp = np.full(max(len(f_kps), 1), -1, np.int32)
+    n = lib().orc_search_by_bow(_p(kf_kps), _p(kf_desc), len(kf_kps), _p(kf_has_mp), _p(ka), _p(kb), _p(kc), len(ka),
+                                _p(f_kps), _p(f_desc), len(f_kps), _p(fa), _p(fb), _p(fc), len(fa), _fp(nn_ratio), int(check_ori), _p(f_mp))
+    return n, f_mp[:len(f_kps)]
+
+
+def bruteforce_top2(q, t):
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    bi, bd, sd = (np.zeros(max(len(q), 1), np.int32) for _ in range(3))
+    lib().orc_bruteforce_top2(_p(q), len(q), _p(t), len(t), _p(bi), _p(bd), _p(sd))
+    return bi[:len(q)], bd[:len(q)], sd[:len(q)]
