@@ -61,6 +61,29 @@ int fbe_extractor_max_keypoints(const fbe_extractor* e, int32_t rows, int32_t co
     return FBE_OK;
 }
 
+int fbe_plan_query(const fbe_extractor_cfg* cfg, int32_t rows, int32_t cols, int32_t* out, float* scale, float* inv_scale,
+                   float* sigma2, float* inv_sigma2) {
+    if (!cfg || !out || cfg->nlevels < 1 || cfg->nlevels > FBE_MAX_LEVELS || cfg->nfeatures < 1 || !(cfg->scale_factor > 1.0f)) return FBE_E_INVALID;
+    std::vector<float> sc, isc, s2, is2;
+    std::vector<int> per;
+    int umax[16];
+    compute_extractor_tables(cfg->nfeatures, cfg->scale_factor, cfg->nlevels, sc, isc, s2, is2, per, umax);
+    Plan p;
+    std::vector<ResizeTab> tabs;
+    int rc = build_plan(*cfg, sc, isc, per, umax, rows, cols, p, tabs);
+    if (rc != FBE_OK) return rc;
+    for (int l = 0; l < cfg->nlevels; ++l) {
+        const LevelGeom& g = p.lv[l];
+        int32_t* o = out + 8 * l;
+        o[0] = g.w; o[1] = g.h; o[2] = g.ncols; o[3] = g.nrows; o[4] = g.wcell; o[5] = g.hcell; o[6] = g.nfeat; o[7] = g.nini;
+        if (scale) scale[l] = sc[l];
+        if (inv_scale) inv_scale[l] = isc[l];
+        if (sigma2) sigma2[l] = s2[l];
+        if (inv_sigma2) inv_sigma2[l] = is2[l];
+    }
+    return FBE_OK;
+}
+
 int fbe_extract_batch(fbe_extractor* e, const uint8_t* const* imgs, int32_t nimg, int32_t rows, int32_t cols, size_t step,
                       fbe_keypoint* kps, uint8_t* desc, int32_t capacity, int32_t* n_out) {
     if (!e || !n_out) return FBE_E_INVALID;

@@ -54,6 +54,8 @@ void ExtractorCore::destroy() {
     cudaFree(d_in); d_in = nullptr;
     if (h_pin) cudaFreeHost(h_pin);
     h_pin = nullptr;
+    for (auto& e : tev) cudaEventDestroy(e);
+    tev.clear();
     if (ev_pyr) cudaEventDestroy(ev_pyr);
     if (ev_blur) cudaEventDestroy(ev_blur);
     if (stream) cudaStreamDestroy(stream);
@@ -117,24 +119,84 @@ int ExtractorCore::ensure_plan(int rows, int cols) {
     return FBE_OK;
 }
 
-int ExtractorCore::run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, int nimg, int rows, int cols) {
-    if (nimg < 1 || nimg > cfg.max_batch) { set_error("batch larger than max_batch"); return FBE_E_INVALID; }
+Workspace ExtractorCore::slot_view(int slot0) const {
+    Workspace v = ws;
+    const size_t s = (size_t)slot0;
+    const int gcells = hplan.grid_cols * hplan.grid_rows;
+    v.pyr += s * hplan.pyr_bytes; v.blur += s * hplan.pyr_bytes;
+    v.cell_count += s * hplan.ncells_total;
+    v.slots += s * hplan.slots_total; v.keys += s * hplan.slots_total; v.key_node += s * hplan.slots_total;
+    v.oct_scratch += s * ws.oct_scratch_bytes;
+    v.sel += s * hplan.kp_cap_total; v.level_n += s * FBE_MAX_LEVELS;
+    v.out_kps += s * hplan.kp_cap_total; v.out_desc += s * hplan.kp_cap_total * 32; v.out_n += s;
+    v.out_cell += s * hplan.kp_cap_total; v.grid_start += s * (gcells + 1); v.grid_items += s * hplan.kp_cap_total;
+    v.status += s;
+    return v;
+}
+
+int ExtractorCore::run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, int nimg, int rows, int cols, int slot0) {
+    if (nimg < 1 || slot0 < 0 || slot0 + nimg > cfg.max_batch) { set_error("batch larger than max_batch"); return FBE_E_INVALID; }
     FBE_CUDA(cudaSetDevice(cfg.device));
     int rc = ensure_plan(rows, cols);
     if (rc != FBE_OK) return rc;
-    ws.in = d_imgs; ws.in_pitch = pitch; ws.in_slot_stride = slot_stride;
-    if ((rc = launch_pyramid(hplan, dplan, ws, dtab, nimg, stream)) != FBE_OK) return rc;
+    Workspace v = slot_view(slot0);
+    v.in = d_imgs; v.in_pitch = pitch; v.in_slot_stride = slot_stride;
+    cudaEvent_t* te = nullptr;
+    if (timing) {
+        te = tev.data() + (size_t)tpos * (kStages + 3);
+        tpos = (tpos + 1) % kTimingRing;
+        tcount = std::min(tcount + 1, kTimingRing);
+    }
+#define FBE_MARK(i, st) do { if (te) FBE_CUDA(cudaEventRecord(te[i], st)); } while (0)
+    FBE_MARK(0, stream);
+    if ((rc = launch_pyramid(hplan, dplan, v, dtab, nimg, stream)) != FBE_OK) return rc;
+    FBE_MARK(1, stream);
     // blur depends only on the pyramid: run it on the side stream while FAST + octree proceed
     FBE_CUDA(cudaEventRecord(ev_pyr, stream));
     FBE_CUDA(cudaStreamWaitEvent(stream2, ev_pyr, 0));
-    if ((rc = launch_blur(hplan, dplan, ws, nimg, stream2)) != FBE_OK) return rc;
+    FBE_MARK(6, stream2);
+    if ((rc = launch_blur(hplan, dplan, v, nimg, stream2)) != FBE_OK) return rc;
+    FBE_MARK(7, stream2);
     FBE_CUDA(cudaEventRecord(ev_blur, stream2));
-    if ((rc = launch_fast_cells(hplan, dplan, ws, nimg, stream)) != FBE_OK) return rc;
-    if ((rc = launch_octree(hplan, dplan, ws, nimg, stream)) != FBE_OK) return rc;
+    if ((rc = launch_fast_cells(hplan, dplan, v, nimg, stream)) != FBE_OK) return rc;
+    FBE_MARK(2, stream);
+    if ((rc = launch_octree(hplan, dplan, v, nimg, stream)) != FBE_OK) return rc;
+    FBE_MARK(3, stream);
     FBE_CUDA(cudaStreamWaitEvent(stream, ev_blur, 0));
-    if ((rc = launch_describe(hplan, dplan, ws, nimg, stream)) != FBE_OK) return rc;
-    if ((rc = launch_grid(hplan, dplan, ws, nimg, stream)) != FBE_OK) return rc;
+    FBE_MARK(8, stream);
+    if ((rc = launch_describe(hplan, dplan, v, nimg, stream)) != FBE_OK) return rc;
+    FBE_MARK(4, stream);
+    if ((rc = launch_grid(hplan, dplan, v, nimg, stream)) != FBE_OK) return rc;
+    FBE_MARK(5, stream);
+#undef FBE_MARK
     last_nimg = nimg;
+    return FBE_OK;
+}
+
+int ExtractorCore::enable_timing(bool on) {
+    FBE_CUDA(cudaSetDevice(cfg.device));
+    if (on && tev.empty()) {
+        tev.resize((size_t)kTimingRing * (kStages + 3));
+        for (auto& e : tev) FBE_CUDA(cudaEventCreate(&e));
+    }
+    timing = on; tpos = 0; tcount = 0;
+    return FBE_OK;
+}
+
+// Sums, over the recorded steps, the device time of: [0] pyramid, [1] FAST cells, [2] octree, [3] orient+describe,
+// [4] grid, [5] blur (side stream).  Call after synchronising the stream.
+int ExtractorCore::collect_timing(double* ms_sum, int* nsteps) {
+    for (int i = 0; i < kStages; ++i) ms_sum[i] = 0.0;
+    *nsteps = tcount;
+    for (int k = 0; k < tcount; ++k) {
+        cudaEvent_t* te = tev.data() + (size_t)k * (kStages + 3);
+        float ms;
+        const int a[kStages] = {0, 1, 2, 8, 4, 6}, b[kStages] = {1, 2, 3, 4, 5, 7};
+        for (int i = 0; i < kStages; ++i) {
+            FBE_CUDA(cudaEventElapsedTime(&ms, te[a[i]], te[b[i]]));
+            ms_sum[i] += ms;
+        }
+    }
     return FBE_OK;
 }
 

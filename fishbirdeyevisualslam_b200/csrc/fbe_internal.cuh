@@ -143,12 +143,22 @@ struct ExtractorCore {
     float g_min_x = 0, g_min_y = 0, g_inv_w = 0, g_inv_h = 0;
     int g_cols = 0, g_rows = 0;
 
+    // optional per-stage CUDA-event timing (bench.py's live roofline): ring of event sets, read back on demand
+    static constexpr int kStages = 6;          // pyramid, fast, octree, describe, grid | blur (side stream)
+    static constexpr int kTimingRing = 64;
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;              // [ring][kStages + 3]
+    int tpos = 0, tcount = 0;
+    int enable_timing(bool on);
+    int collect_timing(double* ms_sum /*[kStages]*/, int* nsteps);
+
     int init(const fbe_extractor_cfg& c);
     void destroy();
     int ensure_plan(int rows, int cols);
     int set_grid(float min_x, float min_y, float inv_w, float inv_h, int gcols, int grows);
-    // images already on the device: [nimg][rows][pitch]
-    int run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, int nimg, int rows, int cols);
+    // images already on the device: [nimg][rows][pitch]; results go to workspace slots slot0 .. slot0+nimg-1
+    int run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, int nimg, int rows, int cols, int slot0 = 0);
+    Workspace slot_view(int slot0) const;
     int free_ws();
 };
 

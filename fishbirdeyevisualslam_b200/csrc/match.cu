@@ -219,9 +219,15 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
     if (lane < FBE_HISTO_LENGTH) s_hist[lane] = 0;
     __syncwarp();
     const int sentinel = init ? INT_MAX : 256;
-    for (int qi = 0; qi < nq; ++qi) {
-        const int c = a.cnt[qb + qi];
-        if (c == 0) continue;
+    // queries without candidates are skipped 32 at a time (most keypoints are not octave-0 queries)
+    for (int qbase = 0; qbase < nq; qbase += 32) {
+      const int c_lane = (qbase + lane < nq) ? a.cnt[qb + qbase + lane] : 0;
+      unsigned todo = __ballot_sync(0xffffffffu, c_lane > 0);
+      while (todo) {
+        const int jq = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int qi = qbase + jq;
+        const int c = __shfl_sync(0xffffffffu, c_lane, jq);
         const unsigned* row = a.rows + (qb + qi) * a.C;
         unsigned k1 = kNoKey, k2 = kNoKey;
         for (int j = lane; j < c; j += 32) {
@@ -273,6 +279,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
             }
         }
         __syncwarp();
+      }
     }
     __syncwarp();
     if (a.check_ori && a.mode != kResolveMap) {

@@ -1,0 +1,285 @@
+// Device-resident batch pipeline (config C2/C4): per step `batch` front+bird frame pairs are extracted, bucketed and
+// matched against the previous pair without any host round trip.
+//   front : ORBextractor -> 64x48 grid -> SearchForInitialization-style window search (vbPrevMatched = previous keypoints)
+//   bird  : ORBextractor -> 32x32 grid -> BirdviewMatch (isProject == 0)
+// Frame slots: each extractor workspace holds batch+1 frames; slot 0 carries the last frame of the previous step, slots
+// 1..batch receive this step's frames, so "pair p vs pair p-1" is the uniform-stride problem (query slot p, target
+// slot p+1) for p = 0..batch-1.  The bird extractor runs on its own stream beside the front extractor.
+#include <cstring>
+#include <new>
+#include "match_kernels.cuh"
+
+using namespace fbe;
+
+struct fbe_pipeline {
+    fbe_pipeline_cfg cfg;
+    ExtractorCore front, bird;
+    int B = 0, fcap = 0, bcap = 0, row_cap = 256;
+    bool have_prev = false;
+    cudaEvent_t ev_bird = nullptr, ev_match = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    // front matching workspace
+    float4* fq = nullptr; int2* flv = nullptr; unsigned* frows = nullptr; int* fcnt = nullptr;
+    int *f_mdist = nullptr, *f_m21 = nullptr, *f_m12 = nullptr, *f_bin = nullptr, *f_hit = nullptr, *f_nm = nullptr;
+    // bird matching workspace
+    float4* bq = nullptr; int2* blv = nullptr;
+    int *b_bi = nullptr, *b_bd = nullptr, *b_sd = nullptr, *b_m12 = nullptr, *b_bin = nullptr, *b_nm = nullptr;
+    int* flags = nullptr;                // [0] row overflow
+    fbe_pair_result* d_res = nullptr;
+    uint8_t *d_front_in = nullptr, *d_bird_in = nullptr;   // staging for the host-buffer step
+    fbe_pair_result* h_res = nullptr;    // pinned
+};
+
+namespace {
+
+#define FBE_TRY(expr) do { int _rc = (expr); if (_rc != FBE_OK) return _rc; } while (0)
+
+__global__ void k_pair_results(const int* __restrict__ nf, const int* __restrict__ nb, const int* __restrict__ fm,
+                               const int* __restrict__ bm, int B, fbe_pair_result* __restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    fbe_pair_result r;
+    r.n_front = nf[p + 1]; r.n_bird = nb[p + 1]; r.front_matches = fm[p]; r.bird_matches = bm[p];
+    out[p] = r;
+}
+
+FrameDev frame_dev(const ExtractorCore& e, int slot0) {
+    Workspace v = e.slot_view(slot0);
+    FrameDev f;
+    f.kps = v.out_kps; f.desc = v.out_desc; f.n = v.out_n; f.start = v.grid_start; f.items = v.grid_items;
+    f.kp_stride = e.hplan.kp_cap_total;
+    f.min_x = e.hplan.grid_min_x; f.min_y = e.hplan.grid_min_y; f.inv_w = e.hplan.grid_inv_w; f.inv_h = e.hplan.grid_inv_h;
+    f.gcols = e.hplan.grid_cols; f.grows = e.hplan.grid_rows;
+    return f;
+}
+
+int carry_last(ExtractorCore& e, int B, cudaStream_t st) {
+    Workspace s = e.slot_view(B), d = e.slot_view(0);
+    const int cap = e.hplan.kp_cap_total, gcells = e.hplan.grid_cols * e.hplan.grid_rows;
+    FBE_CUDA(cudaMemcpyAsync(d.out_kps, s.out_kps, (size_t)cap * sizeof(fbe_keypoint), cudaMemcpyDeviceToDevice, st));
+    FBE_CUDA(cudaMemcpyAsync(d.out_desc, s.out_desc, (size_t)cap * 32, cudaMemcpyDeviceToDevice, st));
+    FBE_CUDA(cudaMemcpyAsync(d.out_n, s.out_n, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    FBE_CUDA(cudaMemcpyAsync(d.grid_start, s.grid_start, (size_t)(gcells + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    FBE_CUDA(cudaMemcpyAsync(d.grid_items, s.grid_items, (size_t)cap * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return FBE_OK;
+}
+
+void free_all(fbe_pipeline* p) {
+    cudaSetDevice(p->cfg.device);
+    if (p->front.stream) cudaStreamSynchronize(p->front.stream);
+    if (p->bird.stream) cudaStreamSynchronize(p->bird.stream);
+    void* ptrs[] = {p->fq, p->flv, p->frows, p->fcnt, p->f_mdist, p->f_m21, p->f_m12, p->f_bin, p->f_hit, p->f_nm, p->bq, p->blv,
+                    p->b_bi, p->b_bd, p->b_sd, p->b_m12, p->b_bin, p->b_nm, p->flags, p->d_res, p->d_front_in, p->d_bird_in};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    if (p->h_res) cudaFreeHost(p->h_res);
+    for (cudaEvent_t e : {p->ev_bird, p->ev_match, p->ev_t0, p->ev_t1}) if (e) cudaEventDestroy(e);
+    p->front.destroy();
+    p->bird.destroy();
+}
+
+}  // namespace
+
+extern "C" {
+
+int fbe_pipeline_create(const fbe_pipeline_cfg* cfg, fbe_pipeline** out) {
+    if (!cfg || !out || cfg->batch < 1) return FBE_E_INVALID;
+    *out = nullptr;
+    fbe_pipeline* p = new (std::nothrow) fbe_pipeline();
+    if (!p) return FBE_E_INVALID;
+    p->cfg = *cfg;
+    p->B = cfg->batch;
+    fbe_extractor_cfg fc = cfg->front, bc = cfg->bird;
+    fc.max_batch = bc.max_batch = cfg->batch + 1;
+    fc.device = bc.device = cfg->device;
+    int rc = p->front.init(fc);
+    if (rc == FBE_OK) rc = p->bird.init(bc);
+    auto fail = [&](int code) { free_all(p); delete p; return code; };
+    if (rc != FBE_OK) return fail(rc);
+    // k1 == 0 image bounds: mnMinX = 0, mnMaxX = cols (src/Frame.cc:741-795); grid constants of src/Frame.cc:276-283
+    if ((rc = p->front.set_grid(0.f, 0.f, 64.f / (float)cfg->front_cols, 48.f / (float)cfg->front_rows, 64, 48)) != FBE_OK) return fail(rc);
+    if ((rc = p->bird.set_grid(0.f, 0.f, 32.f / (float)cfg->bird_cols, 32.f / (float)cfg->bird_rows, 32, 32)) != FBE_OK) return fail(rc);
+    if ((rc = p->front.ensure_plan(cfg->front_rows, cfg->front_cols)) != FBE_OK) return fail(rc);
+    if ((rc = p->bird.ensure_plan(cfg->bird_rows, cfg->bird_cols)) != FBE_OK) return fail(rc);
+    p->fcap = p->front.hplan.kp_cap_total;
+    p->bcap = p->bird.hplan.kp_cap_total;
+    const size_t B = (size_t)p->B, fc_ = (size_t)p->fcap, bc_ = (size_t)p->bcap;
+    bool ok = true;
+    auto A = [&](auto** ptr, size_t bytes) { if (ok && cudaMalloc((void**)ptr, bytes) != cudaSuccess) ok = false; };
+    A(&p->fq, (B + 1) * fc_ * sizeof(float4)); A(&p->flv, (B + 1) * fc_ * sizeof(int2));
+    A(&p->frows, (B + 1) * fc_ * p->row_cap * 4); A(&p->fcnt, (B + 1) * fc_ * 4);
+    A(&p->f_mdist, (B + 1) * fc_ * 4); A(&p->f_m21, (B + 1) * fc_ * 4); A(&p->f_m12, (B + 1) * fc_ * 4);
+    A(&p->f_bin, (B + 1) * fc_ * 4); A(&p->f_hit, (B + 1) * fc_ * 4); A(&p->f_nm, (B + 1) * 4);
+    A(&p->bq, (B + 1) * bc_ * sizeof(float4)); A(&p->blv, (B + 1) * bc_ * sizeof(int2));
+    A(&p->b_bi, (B + 1) * bc_ * 4); A(&p->b_bd, (B + 1) * bc_ * 4); A(&p->b_sd, (B + 1) * bc_ * 4);
+    A(&p->b_m12, (B + 1) * bc_ * 4); A(&p->b_bin, (B + 1) * bc_ * 4); A(&p->b_nm, (B + 1) * 4);
+    A(&p->flags, 64); A(&p->d_res, B * sizeof(fbe_pair_result));
+    if (!ok) { set_error("pipeline workspace allocation failed"); return fail(FBE_E_CUDA); }
+    if (cudaMallocHost((void**)&p->h_res, B * sizeof(fbe_pair_result)) != cudaSuccess) { set_error("pinned alloc failed"); return fail(FBE_E_CUDA); }
+    cudaMemset(p->flags, 0, 64);
+    cudaMemset(p->front.ws.out_n, 0, (B + 1) * sizeof(int));
+    cudaMemset(p->bird.ws.out_n, 0, (B + 1) * sizeof(int));
+    cudaMemset(p->front.ws.grid_start, 0, (B + 1) * (64 * 48 + 1) * sizeof(int));
+    cudaMemset(p->bird.ws.grid_start, 0, (B + 1) * (32 * 32 + 1) * sizeof(int));
+    for (cudaEvent_t* e : {&p->ev_bird, &p->ev_match}) cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+    cudaEventCreate(&p->ev_t0); cudaEventCreate(&p->ev_t1);
+    cudaDeviceSynchronize();
+    *out = p;
+    return FBE_OK;
+}
+
+int fbe_pipeline_destroy(fbe_pipeline* p) {
+    if (!p) return FBE_E_INVALID;
+    free_all(p);
+    delete p;
+    return FBE_OK;
+}
+
+int fbe_pipeline_caps(const fbe_pipeline* p, int32_t* front_cap, int32_t* bird_cap) {
+    if (!p) return FBE_E_INVALID;
+    if (front_cap) *front_cap = p->fcap;
+    if (bird_cap) *bird_cap = p->bcap;
+    return FBE_OK;
+}
+
+int fbe_pipeline_stream(fbe_pipeline* p, void** stream) {
+    if (!p || !stream) return FBE_E_INVALID;
+    *stream = (void*)p->front.stream;
+    return FBE_OK;
+}
+
+int fbe_pipeline_step_dev(fbe_pipeline* p, const uint8_t* d_front, const uint8_t* d_bird) {
+    if (!p || !d_front || !d_bird) return FBE_E_INVALID;
+    const fbe_pipeline_cfg& c = p->cfg;
+    FBE_CUDA(cudaSetDevice(c.device));
+    cudaStream_t ms = p->front.stream, bs = p->bird.stream;
+    const int B = p->B;
+    FBE_CUDA(cudaEventRecord(p->ev_t0, ms));
+    // the bird extractor must not overwrite slots that the previous step's matching still reads
+    FBE_CUDA(cudaStreamWaitEvent(bs, p->ev_match, 0));
+    FBE_TRY(p->front.run_dev(d_front, c.front_cols, c.front_rows * c.front_cols, B, c.front_rows, c.front_cols, 1));
+    FBE_TRY(p->bird.run_dev(d_bird, c.bird_cols, c.bird_rows * c.bird_cols, B, c.bird_rows, c.bird_cols, 1));
+    FBE_CUDA(cudaEventRecord(p->ev_bird, bs));
+
+    // ---- front: pair p (slot p+1) against pair p-1 (slot p) --------------------------------------------------------
+    const FrameDev fq = frame_dev(p->front, 0), ft = frame_dev(p->front, 1);
+    FBE_TRY(launch_queries_from_kps(fq.kps, nullptr, nullptr, fq.n, p->fcap, B, (float)c.front_window, p->fq, p->flv, ms));
+    QueryDev fqs{p->fq, p->flv, fq.desc, fq.n, p->fcap};
+    FBE_TRY(launch_window_rows(ft, fqs, B, p->fcap, true, p->row_cap, p->frows, p->fcnt, p->flags, ms));
+    ResolveArgs a{};
+    a.mode = kResolveInit; a.C = p->row_cap; a.rows = p->frows; a.cnt = p->fcnt; a.nq = fq.n; a.q_stride = p->fcap;
+    a.t_stride = p->fcap; a.nt = ft.n; a.q_kps = fq.kps; a.t_kps = ft.kps; a.nn_ratio = c.nn_ratio; a.check_ori = c.check_orientation;
+    a.matched_dist = p->f_mdist; a.match21 = p->f_m21; a.matches12 = p->f_m12; a.prev_matched = nullptr;
+    a.q_bin = p->f_bin; a.q_hit = p->f_hit; a.nmatches = p->f_nm;
+    FBE_TRY(launch_resolve(a, B, ms));
+
+    // ---- bird ----------------------------------------------------------------------------------------------------
+    FBE_CUDA(cudaStreamWaitEvent(ms, p->ev_bird, 0));
+    const FrameDev bq = frame_dev(p->bird, 0), bt = frame_dev(p->bird, 1);
+    FBE_TRY(launch_queries_from_kps(bq.kps, nullptr, nullptr, bq.n, p->bcap, B, (float)c.bird_window, p->bq, p->blv, ms));
+    QueryDev bqs{p->bq, p->blv, bq.desc, bq.n, p->bcap};
+    FBE_TRY(launch_window_top2(bt, bqs, B, p->bcap, false, p->b_bi, p->b_bd, p->b_sd, ms));
+    BirdFinishArgs f{};
+    f.best_idx = p->b_bi; f.best_dist = p->b_bd; f.second_dist = p->b_sd; f.nq = bq.n; f.q_stride = p->bcap;
+    f.q_kps = bq.kps; f.t_kps = bt.kps; f.t_stride = p->bcap; f.nn_ratio = c.nn_ratio; f.check_ori = c.check_orientation;
+    f.matches12 = p->b_m12; f.dmatches = nullptr; f.n_dmatches = nullptr; f.nmatches = p->b_nm; f.q_bin = p->b_bin;
+    FBE_TRY(launch_bird_finish(f, B, ms));
+
+    k_pair_results<<<(B + 127) / 128, 128, 0, ms>>>(p->front.ws.out_n, p->bird.ws.out_n, p->f_nm, p->b_nm, B, p->d_res);
+    count_launch();
+    FBE_CUDA(cudaGetLastError());
+    FBE_TRY(carry_last(p->front, B, ms));
+    FBE_TRY(carry_last(p->bird, B, ms));
+    FBE_CUDA(cudaEventRecord(p->ev_match, ms));
+    FBE_CUDA(cudaEventRecord(p->ev_t1, ms));
+    p->have_prev = true;
+    return FBE_OK;
+}
+
+int fbe_pipeline_sync(fbe_pipeline* p) {
+    if (!p) return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(p->cfg.device));
+    FBE_CUDA(cudaStreamSynchronize(p->front.stream));
+    FBE_CUDA(cudaStreamSynchronize(p->bird.stream));
+    return FBE_OK;
+}
+
+int fbe_pipeline_last_step_ms(fbe_pipeline* p, float* ms) {
+    if (!p || !ms) return FBE_E_INVALID;
+    FBE_CUDA(cudaEventSynchronize(p->ev_t1));
+    FBE_CUDA(cudaEventElapsedTime(ms, p->ev_t0, p->ev_t1));
+    return FBE_OK;
+}
+
+int fbe_pipeline_fetch(fbe_pipeline* p, fbe_pair_result* res, int32_t* front_matches12, int32_t* bird_matches12) {
+    if (!p) return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(p->cfg.device));
+    cudaStream_t ms = p->front.stream;
+    const size_t B = (size_t)p->B;
+    int h_flags[2] = {0, 0};
+    FBE_CUDA(cudaMemcpyAsync(p->h_res, p->d_res, B * sizeof(fbe_pair_result), cudaMemcpyDeviceToHost, ms));
+    FBE_CUDA(cudaMemcpyAsync(h_flags, p->flags, 8, cudaMemcpyDeviceToHost, ms));
+    if (front_matches12) FBE_CUDA(cudaMemcpyAsync(front_matches12, p->f_m12, B * p->fcap * 4, cudaMemcpyDeviceToHost, ms));
+    if (bird_matches12) FBE_CUDA(cudaMemcpyAsync(bird_matches12, p->b_m12, B * p->bcap * 4, cudaMemcpyDeviceToHost, ms));
+    FBE_CUDA(cudaStreamSynchronize(ms));
+    if (h_flags[0]) { set_error("candidate rows overflow in pipeline (raise row capacity)"); return FBE_E_CAPACITY; }
+    if (res) std::memcpy(res, p->h_res, B * sizeof(fbe_pair_result));
+    return FBE_OK;
+}
+
+int fbe_pipeline_step_host(fbe_pipeline* p, const uint8_t* h_front, const uint8_t* h_bird, fbe_pair_result* res,
+                           int32_t* front_matches12, int32_t* bird_matches12) {
+    if (!p || !h_front || !h_bird) return FBE_E_INVALID;
+    const fbe_pipeline_cfg& c = p->cfg;
+    FBE_CUDA(cudaSetDevice(c.device));
+    const size_t fbytes = (size_t)p->B * c.front_rows * c.front_cols, bbytes = (size_t)p->B * c.bird_rows * c.bird_cols;
+    if (!p->d_front_in) FBE_CUDA(cudaMalloc(&p->d_front_in, fbytes));
+    if (!p->d_bird_in) FBE_CUDA(cudaMalloc(&p->d_bird_in, bbytes));
+    // the previous step may still be reading the staging buffers
+    FBE_CUDA(cudaStreamWaitEvent(p->bird.stream, p->ev_match, 0));
+    FBE_CUDA(cudaMemcpyAsync(p->d_front_in, h_front, fbytes, cudaMemcpyHostToDevice, p->front.stream));
+    FBE_CUDA(cudaMemcpyAsync(p->d_bird_in, h_bird, bbytes, cudaMemcpyHostToDevice, p->bird.stream));
+    FBE_TRY(fbe_pipeline_step_dev(p, p->d_front_in, p->d_bird_in));
+    return fbe_pipeline_fetch(p, res, front_matches12, bird_matches12);
+}
+
+int fbe_pipeline_fetch_pair(fbe_pipeline* p, int32_t pair, fbe_keypoint* front_kps, uint8_t* front_desc, fbe_keypoint* bird_kps,
+                            uint8_t* bird_desc) {
+    if (!p || pair < 0 || pair >= p->B) return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(p->cfg.device));
+    FBE_TRY(fbe_pipeline_sync(p));
+    Workspace f = p->front.slot_view(pair + 1), b = p->bird.slot_view(pair + 1);
+    if (front_kps) FBE_CUDA(cudaMemcpy(front_kps, f.out_kps, (size_t)p->fcap * sizeof(fbe_keypoint), cudaMemcpyDeviceToHost));
+    if (front_desc) FBE_CUDA(cudaMemcpy(front_desc, f.out_desc, (size_t)p->fcap * 32, cudaMemcpyDeviceToHost));
+    if (bird_kps) FBE_CUDA(cudaMemcpy(bird_kps, b.out_kps, (size_t)p->bcap * sizeof(fbe_keypoint), cudaMemcpyDeviceToHost));
+    if (bird_desc) FBE_CUDA(cudaMemcpy(bird_desc, b.out_desc, (size_t)p->bcap * 32, cudaMemcpyDeviceToHost));
+    return FBE_OK;
+}
+
+// live per-stage device timing of the FRONT and BIRD extractors (CUDA events on their launching streams).
+// ms: 12 doubles = front[pyramid, fast, octree, describe, grid, blur], bird[...]; steps: number of steps summed.
+int fbe_pipeline_stage_timing(fbe_pipeline* p, int32_t enable) {
+    if (!p) return FBE_E_INVALID;
+    FBE_TRY(p->front.enable_timing(enable != 0));
+    return p->bird.enable_timing(enable != 0);
+}
+int fbe_pipeline_stage_ms(fbe_pipeline* p, double* ms, int32_t* steps) {
+    if (!p || !ms || !steps) return FBE_E_INVALID;
+    FBE_TRY(fbe_pipeline_sync(p));
+    int n1 = 0, n2 = 0;
+    FBE_TRY(p->front.collect_timing(ms, &n1));
+    FBE_TRY(p->bird.collect_timing(ms + 6, &n2));
+    *steps = n1;
+    return FBE_OK;
+}
+
+// pinned host memory for callers that have no CUDA runtime of their own (bench.py's host-buffer leg)
+int fbe_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return FBE_E_INVALID;
+    FBE_CUDA(cudaMallocHost(ptr, bytes));
+    return FBE_OK;
+}
+int fbe_host_free(void* ptr) {
+    if (ptr) FBE_CUDA(cudaFreeHost(ptr));
+    return FBE_OK;
+}
+
+}  // extern "C"

@@ -83,6 +83,12 @@ FBE_API int fbe_extractor_features_per_level(const fbe_extractor* e, const int32
 /* upper bound on keypoints one image can produce (octree may overshoot nfeatures) */
 FBE_API int fbe_extractor_max_keypoints(const fbe_extractor* e, int32_t rows, int32_t cols, int32_t* cap);
 
+/* Host-only geometry query (no device needed): per level {w, h, fast_cols, fast_rows, cell_w, cell_h, nfeatures, octree_roots}
+ * for an image of rows x cols -- the arithmetic of src/ORBextractor.cc:1111-1112, 768-787, 543, 432-446.
+ * out: nlevels x 8 int32; scale/inv_scale/sigma2/inv_sigma2 (each nlevels floats) may be NULL. */
+FBE_API int fbe_plan_query(const fbe_extractor_cfg* cfg, int32_t rows, int32_t cols, int32_t* out, float* scale,
+                           float* inv_scale, float* sigma2, float* inv_sigma2);
+
 /* ORBextractor::operator()(image, mask, keypoints, descriptors), src/ORBextractor.cc:1043-1105.
  * Host buffers.  img: rows x cols 8-bit, `step` bytes per row.  kps/desc: `capacity` entries / x32 bytes.
  * Empty image (img NULL or rows/cols <= 0) -> *n_out = 0 and outputs untouched, like the reference's early return. */
@@ -229,6 +235,15 @@ FBE_API int fbe_pipeline_fetch_pair(fbe_pipeline* p, int32_t pair, fbe_keypoint*
 FBE_API int fbe_pipeline_last_step_ms(fbe_pipeline* p, float* ms);
 /* raw stream handle (cudaStream_t) so that a caller can record its own events around steps */
 FBE_API int fbe_pipeline_stream(fbe_pipeline* p, void** stream);
+
+/* live per-stage device timing (CUDA events on the launching streams) for bench.py's roofline block.
+ * ms: 12 doubles summed over `steps` steps = front[pyramid, fast, octree, describe, grid, blur], bird[same]. */
+FBE_API int fbe_pipeline_stage_timing(fbe_pipeline* p, int32_t enable);
+FBE_API int fbe_pipeline_stage_ms(fbe_pipeline* p, double* ms, int32_t* steps);
+
+/* pinned (page-locked) host memory for the host-buffer entry points */
+FBE_API int fbe_host_alloc(void** ptr, size_t bytes);
+FBE_API int fbe_host_free(void* ptr);
 
 #ifdef __cplusplus
 }

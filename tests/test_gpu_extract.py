@@ -1,0 +1,203 @@
+"""Parity of the CUDA extractor (through the C-ABI) with the oracle: every stage bit-exact; angles within 1e-4 rad
+(observed: bit-exact); a differing descriptor is tolerated only on keypoints the oracle flags as sitting on a
+cvRound tie of the rotated sample coordinates (north_star: "traced to an angle-rounding boundary")."""
+import zlib
+
+import numpy as np
+import pytest
+
+from fishbirdeyevisualslam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ANGLE_TOL_DEG = 1e-4 * 180.0 / np.pi
+
+
+def compare(kg, dg, ko, do, boundary):
+    assert len(kg) == len(ko)
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(kg[f], ko[f]), f
+    assert np.max(np.abs(kg["angle"] - ko["angle"]), initial=0) <= ANGLE_TOL_DEG
+    bad = np.nonzero((dg != do).any(axis=1))[0]
+    assert boundary[bad].all(), f"{len(bad)} descriptors differ away from a rounding boundary"
+    return len(bad)
+
+
+CONFIGS = [
+    (480, 640, 1000, 8, 1),      # C1
+    (720, 1280, 2000, 8, 2),     # C2 front
+    (384, 384, 1000, 8, 3),      # C2 bird
+    (400, 950, 2000, 8, 4),      # the reference's real input size
+    (200, 300, 500, 5, 5),
+    (96, 400, 200, 3, 8),        # wide: 4 octree roots
+    (300, 200, 400, 5, 9),       # tall: 1 root
+    (203, 331, 5000, 4, 10),     # more features requested than candidates exist
+    (150, 150, 50, 2, 6),
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_full_operator_and_stages(oracle, cfg):
+    from fishbirdeyevisualslam_b200.extractor import ORBextractor
+    h, w, nf, nl, seed = cfg
+    img = synth.frame(h, w, seed)
+    o = oracle.OracleExtractor(nf, 1.2, nl, 15, 5)
+    ko, do = o(img)
+    g = ORBextractor(nf, 1.2, nl, 15, 5)
+    kg, dg = g(img)
+    for l in range(nl):
+        assert np.array_equal(g.pyramid_level(l), o.level_padded(l)), f"pyramid level {l}"
+        assert np.array_equal(g.debug_candidates(l), o.candidates(l)), f"candidates level {l}"
+        ob = o.level_blurred(l)
+        if ob is not None:
+            assert np.array_equal(g.debug_blurred(l), ob), f"blur level {l}"
+    compare(kg, dg, ko, do, o.boundary)
+    assert np.array_equal(g.GetScaleFactors(), o.tables()["scale"])
+    assert np.array_equal(g.GetInverseScaleSigmaSquares(), o.tables()["inv_sigma2"])
+    assert g.GetLevels() == nl
+
+
+def test_golden_reference_outputs(extract_golden):
+    """CUDA path against outputs of the reference's own ORBextractor.cc (verbatim build), committed as fixtures."""
+    from fishbirdeyevisualslam_b200.extractor import ORBextractor
+    g = extract_golden
+    for i in range(3):
+        h, w, nf, nl, seed = g[f"small{i}_cfg"].tolist()
+        k, d = ORBextractor(nf, 1.2, nl, 15, 5)(synth.frame(h, w, seed))
+        assert k.view(np.uint8).reshape(-1, 28).tobytes() == g[f"small{i}_kps"].tobytes()
+        assert np.array_equal(d, g[f"small{i}_desc"])
+    for h, w, nf, nl, seed, icrc, n, kcrc, dcrc in g["big"].tolist():
+        k, d = ORBextractor(nf, 1.2, nl, 15, 5)(synth.frame(h, w, seed))
+        assert (len(k), zlib.crc32(k.tobytes()) & 0xFFFFFFFF, zlib.crc32(d.tobytes()) & 0xFFFFFFFF) == (n, kcrc, dcrc)
+
+
+@pytest.mark.parametrize("th", [(20, 7), (7, 7), (40, 2), (5, 15)])
+def test_threshold_variants(oracle, th):
+    from fishbirdeyevisualslam_b200.extractor import ORBextractor
+    img = synth.frame(240, 320, 55)
+    o = oracle.OracleExtractor(600, 1.2, 6, th[0], th[1])
+    ko, do = o(img)
+    kg, dg = ORBextractor(600, 1.2, 6, th[0], th[1])(img)
+    compare(kg, dg, ko, do, o.boundary)
+
+
+@pytest.mark.parametrize("scale,nl", [(1.1, 10), (1.5, 4), (2.0, 3), (1.3, 1)])
+def test_scale_factor_variants(oracle, scale, nl):
+    from fishbirdeyevisualslam_b200.extractor import ORBextractor
+    img = synth.frame(360, 480, 56)
+    o = oracle.OracleExtractor(800, scale, nl, 15, 5)
+    ko, do = o(img)
+    g = ORBextractor(800, scale, nl, 15, 5)
+    kg, dg = g(img)
+    compare(kg, dg, ko, do, o.boundary)
+    assert np.array_equal(g.mnFeaturesPerLevel, o.tables()["per_level"])
+
+
+def test_edge_inputs(oracle):
+    from fishbirdeyevisualslam_b200.extractor import ORBextractor
+    g = ORBextractor(300, 1.2, 4, 15, 5)
+    # empty image: silent return, outputs empty (src/ORBextractor.cc:1046-1047)
+    k, d = g(np.zeros((0, 0), np.uint8))
+    assert len(k) == 0 and d.shape == (0, 32)
+    # flat image: zero keypoints -> descriptors released
+    k, d = g(np.full((120, 160), 90, np.uint8))
+    assert len(k) == 0 and d.shape == (0, 32)
+    # single bright rectangle: cells that need the minTh fallback, very few candidates
+    one = np.full((120, 160), 90, np.uint8)
+    one[40:80, 50:110] = 120
+    o = oracle.OracleExtractor(300, 1.2, 4, 15, 5)
+    ko, do = o(one)
+    kg, dg = g(one)
+    compare(kg, dg, ko, do, o.boundary)
+    # saturated noise: maximum candidate density
+    rng = np.random.default_rng(1)
+    noise = rng.integers(0, 2, (120, 160), dtype=np.uint8) * 255
+    ko, do = o(noise)
+    kg, dg = g(noise)
+    compare(kg, dg, ko, do, o.boundary)
+    # non-contiguous rows (step > cols)
+    big = synth.frame(130, 200, 3)
+    view = big[5:125, 20:180]
+    ko, do = o(np.ascontiguousarray(view))
+    kg, dg = g(view)
+    compare(kg, dg, ko, do, o.boundary)
+
+
+def test_same_handle_changes_image_size(oracle):
+    from fishbirdeyevisualslam_b200.extractor import ORBextractor
+    g = ORBextractor(500, 1.2, 5, 15, 5)
+    o = oracle.OracleExtractor(500, 1.2, 5, 15, 5)
+    for (h, w, seed) in [(200, 300, 1), (240, 320, 2), (200, 300, 1)]:
+        img = synth.frame(h, w, seed)
+        ko, do = o(img)
+        kg, dg = g(img)
+        compare(kg, dg, ko, do, o.boundary)
+
+
+def test_batch_equals_single(oracle):
+    from fishbirdeyevisualslam_b200.extractor import ORBextractor
+    imgs = [synth.frame(240, 320, 60 + i) for i in range(7)]
+    gb = ORBextractor(500, 1.2, 6, 15, 5, max_batch=3)       # 7 images through a 3-slot workspace
+    res = gb.extract_batch(imgs)
+    o = oracle.OracleExtractor(500, 1.2, 6, 15, 5)
+    for im, (kg, dg) in zip(imgs, res):
+        ko, do = o(im)
+        compare(kg, dg, ko, do, o.boundary)
+
+
+def test_octree_adversarial(oracle):
+    """Ties everywhere: equal responses inside leaves, equal-size nodes at the N boundary, clustered keys, N edge values."""
+    import ctypes as C
+    from fishbirdeyevisualslam_b200.extractor import debug_octree
+    L = oracle.lib()
+    rng = np.random.default_rng(7)
+
+    def run(xy, W, H, N):
+        xy = np.ascontiguousarray(xy, np.int32)
+        sel = np.zeros(max(len(xy), 1) + 64, np.int32)
+        n = L.orc_octree(xy.ctypes.data_as(C.c_void_p), len(xy), 0, W, 0, H, N, sel.ctypes.data_as(C.c_void_p), len(sel))
+        got = debug_octree(xy, 0, W, 0, H, N)
+        assert got.tolist() == sel[:n].tolist(), (W, H, N, len(xy))
+
+    # regular lattice, all responses equal: every size tie and response tie in the book
+    lat = np.array([[x, y, 30] for y in range(3, 125, 4) for x in range(3, 253, 4)], np.int32)
+    for N in (1, 7, 64, 100, 257, 500, 2000, 5000):
+        run(lat, 256, 128, N)
+    # random points with few distinct responses, various aspect ratios and N
+    for W, H in ((608, 448), (300, 300), (1000, 120), (200, 390)):
+        for npts in (0, 1, 2, 50, 3000):
+            pts = set()
+            while len(pts) < npts:
+                pts.add((int(rng.integers(3, W - 3)), int(rng.integers(3, H - 3))))
+            xy = np.array([[x, y, int(rng.choice([5, 20, 20, 40]))] for x, y in sorted(pts, key=lambda p: (p[1], p[0]))], np.int32).reshape(-1, 3)
+            for N in (30, 217, 1200):
+                run(xy, W, H, N)
+    # tight clusters: chains of single-child splits
+    cl = np.array([[100 + (i % 7), 100 + (i // 7), 10 + (i % 3)] for i in range(49)] + [[500 + (i % 5), 20 + (i // 5), 9] for i in range(25)], np.int32)
+    cl = cl[np.lexsort((cl[:, 0], cl[:, 1]))]
+    for N in (5, 20, 74, 200):
+        run(cl, 640, 448, N)
+
+
+@pytest.mark.slow
+def test_stress_config_c5(oracle):
+    """C5: 3840x2160, 8000 features, 12 levels (octree scratch lives in global memory at this size)."""
+    from fishbirdeyevisualslam_b200.extractor import ORBextractor
+    img = synth.frame(2160, 3840, 5000)
+    o = oracle.OracleExtractor(8000, 1.2, 12, 15, 5)
+    ko, do = o(img)
+    g = ORBextractor(8000, 1.2, 12, 15, 5)
+    kg, dg = g(img)
+    compare(kg, dg, ko, do, o.boundary)
+    for l in (0, 5, 11):
+        assert np.array_equal(g.debug_candidates(l), o.candidates(l))
+
+
+def test_idempotent_and_deterministic():
+    from fishbirdeyevisualslam_b200.extractor import ORBextractor
+    g = ORBextractor(2000, 1.2, 8, 15, 5)
+    img = synth.frame(720, 1280, 2)
+    k1, d1 = g(img)
+    for _ in range(3):
+        k2, d2 = g(img)
+        assert k1.tobytes() == k2.tobytes() and np.array_equal(d1, d2)

@@ -1,0 +1,242 @@
+"""Parity of the CUDA matchers (through the C-ABI) with the oracle: index lists and counts bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import pyref
+from conftest import make_kps
+from fishbirdeyevisualslam_b200 import synth
+from scenes import featvec, flip_bits, frame_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def front_pair():
+    from fishbirdeyevisualslam_b200.extractor import ORBextractor
+    from fishbirdeyevisualslam_b200.matcher import Frame
+    h, w = 480, 640
+    a, b = synth.frame_pair_in_time(h, w, 11)
+    ex = ORBextractor(1000, 1.2, 8, 15, 5)
+    ka, da = ex(a)
+    kb, db = ex(b)
+    sf = ex.GetScaleFactors()
+    return Frame.front(ka, da, w, h, sf), Frame.front(kb, db, w, h, sf)
+
+
+@pytest.fixture(scope="module")
+def bird_pair():
+    from fishbirdeyevisualslam_b200.extractor import ORBextractor
+    from fishbirdeyevisualslam_b200.matcher import Frame
+    a, b = synth.frame_pair_in_time(384, 384, 21)
+    ex = ORBextractor(1000, 1.2, 8, 15, 5)
+    ka, da = ex(a)
+    kb, db = ex(b)
+    return Frame.bird(ka, da, 384, 384), Frame.bird(kb, db, 384, 384)
+
+
+def test_grid_assign(oracle, front_pair, bird_pair):
+    for F in (*front_pair, *bird_pair):
+        s_g, i_g = F.AssignFeaturesToGrid()
+        s_o, i_o = oracle.grid_assign(F.kps, F.min_x, F.min_y, F.inv_w, F.inv_h, F.gcols, F.grows)
+        assert np.array_equal(s_g, s_o) and np.array_equal(i_g, i_o)
+    # quirk Q1 + empty + out-of-grid keypoints
+    from fishbirdeyevisualslam_b200.matcher import grid_assign
+    k = make_kps(np.float32([14.9, 15.0, 635.0, 634.9, -20.0, 3000.0]), np.float32([10, 10, 10, 10, 10, 10]))
+    s_g, i_g = grid_assign(k, 0.0, 0.0, 0.1, 0.1, 64, 48)
+    s_o, i_o = oracle.grid_assign(k, 0.0, 0.0, 0.1, 0.1, 64, 48)
+    assert np.array_equal(s_g, s_o) and np.array_equal(i_g, i_o) and len(i_g) == 3
+    s_g, i_g = grid_assign(k[:0], 0.0, 0.0, 0.1, 0.1, 64, 48)
+    assert s_g.sum() == 0 and len(i_g) == 0
+
+
+@pytest.mark.parametrize("ratio,ori,win", [(0.9, True, 100), (0.9, False, 100), (0.7, True, 30), (0.9, True, 400), (0.6, True, 10)])
+def test_search_for_initialization(oracle, front_pair, ratio, ori, win):
+    from fishbirdeyevisualslam_b200.matcher import ORBmatcher
+    F1, F2 = front_pair
+    m = ORBmatcher(ratio, ori)
+    pm_g = np.ascontiguousarray(np.stack([F1.kps["x"], F1.kps["y"]], 1), np.float32)
+    pm_o = pm_g.copy()
+    for _ in range(2):     # second round starts from the updated vbPrevMatched, as Tracking does
+        n_g, m_g = m.SearchForInitialization(F1, F2, pm_g, win)
+        n_o, m_o = oracle.search_for_initialization(F1, F2, pm_o, win, ratio, ori)
+        assert n_g == n_o and np.array_equal(m_g, m_o) and np.array_equal(pm_g, pm_o)
+    assert n_g > 20 or win <= 10
+
+
+def test_initialization_row_capacity_growth(oracle):
+    """A window that holds more candidates than the initial row capacity (128) forces the grow-and-redo path."""
+    from fishbirdeyevisualslam_b200.matcher import Frame, ORBmatcher
+    rng = np.random.default_rng(3)
+    n = 700
+    k2 = make_kps(rng.uniform(280, 360, n).astype(np.float32), rng.uniform(200, 280, n).astype(np.float32))
+    d2 = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    k1 = make_kps(np.float32([320, 322, 318]), np.float32([240, 241, 239]))
+    d1 = flip_bits(rng, d2[[5, 77, 300]], 10)
+    F1, F2 = Frame.front(k1, d1, 640, 480), Frame.front(k2, d2, 640, 480)
+    pm_g = np.ascontiguousarray(np.stack([k1["x"], k1["y"]], 1), np.float32)
+    pm_o = pm_g.copy()
+    n_g, m_g = ORBmatcher(0.9, True).SearchForInitialization(F1, F2, pm_g, 100)
+    n_o, m_o = oracle.search_for_initialization(F1, F2, pm_o, 100, 0.9, True)
+    assert n_g == n_o == 3 and np.array_equal(m_g, m_o)
+
+
+@pytest.mark.parametrize("ratio,ori,win", [(0.9, True, 10), (0.9, False, 10), (0.8, True, 25)])
+def test_birdview_match(oracle, bird_pair, ratio, ori, win):
+    from fishbirdeyevisualslam_b200.matcher import ORBmatcher
+    F1, F2 = bird_pair
+    n_g, d_g = ORBmatcher(ratio, ori).BirdviewMatch(F2, F1.kps, F1.desc, win)
+    n_o, d_o = oracle.birdview_match(F1.kps, F1.desc, F2, win, ratio, ori)
+    assert n_g == n_o and np.array_equal(d_g, d_o) and n_g > 20
+
+
+def test_bird_map_point_match_c3(oracle, bird_pair):
+    """Config C3: 20 000 projected bird map points against the keypoints of one bird frame."""
+    from fishbirdeyevisualslam_b200.matcher import ORBmatcher, PIXEL2METER, REAR_AXLE_TO_CENTER
+    _, FB = bird_pair
+    rng = np.random.default_rng(5)
+    nmp = 20000
+    src = rng.integers(0, FB.N, nmp)
+    mp_desc = FB.desc[src].copy()
+    nflip = rng.integers(0, 41, nmp)
+    bitpos = rng.integers(0, 256, (nmp, 40))
+    for j in range(40):
+        sel = nflip > j
+        mp_desc[sel, bitpos[sel, j] >> 3] ^= (1 << (bitpos[sel, j] & 7)).astype(np.uint8)
+    # world points: bird pixel -> base XY (Converter::BirdPixel2BaseXY) -> world through Tbw^-1, +-0.1 m jitter
+    px, py = FB.kps["x"][src], FB.kps["y"][src]
+    bx = (192 - py) * PIXEL2METER + REAR_AXLE_TO_CENTER
+    by = (192 - px) * PIXEL2METER
+    base = np.stack([bx, by, np.zeros(nmp)], 1) + rng.uniform(-0.1, 0.1, (nmp, 3)) * [1, 1, 0.5]
+    yaw = np.deg2rad(2.0)
+    Tbw = np.eye(4, dtype=np.float32)
+    Tbw[:3, :3] = [[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]]
+    Tbw[:3, 3] = [0.3, 0.1, 0.0]
+    world = ((base - Tbw[:3, 3]) @ Tbw[:3, :3]).astype(np.float32)           # R^T (p - t)
+    world[rng.random(nmp) < 0.03, 0] = np.nan                                # NULL MapPointBird*
+    Tcw = np.eye(4, dtype=np.float32)
+    cam_xyz = rng.normal(0, 1, (FB.N, 3)).astype(np.float32)
+    m = ORBmatcher(0.9, True)
+    inl, assigned, m12 = m.BirdMapPointMatch(FB, world, mp_desc, Tbw, Tcw, cam_xyz, 384, 384, 10, 0.05)
+    # oracle on the same host-projected pixels
+    from fishbirdeyevisualslam_b200.matcher import BaseXY2BirdPixel, transform_points
+    local = transform_points(Tbw, np.nan_to_num(world))
+    pix = BaseXY2BirdPixel(local, 384, 384)
+    skip = np.isnan(world[:, 0]) | (np.abs(local[:, 2]) > 0.2) | (pix[:, 0] < 0) | (pix[:, 0] >= 384) | (pix[:, 1] < 0) | (pix[:, 1] >= 384)
+    pix[skip, 0] = np.nan
+    n_o, m_o = oracle.bird_map_point_match(pix, mp_desc, FB, 10, 0.9)
+    assert np.array_equal(m12, m_o) and (m12 >= 0).sum() == n_o and n_o > 1000
+
+
+def test_search_by_projection_last(oracle, front_pair):
+    from fishbirdeyevisualslam_b200.matcher import ORBmatcher
+    F1, F2 = front_pair
+    rng = np.random.default_rng(6)
+    proj = np.stack([F1.kps["x"], F1.kps["y"]], 1).astype(np.float32) + rng.normal(0, 3, (F1.N, 2)).astype(np.float32)
+    proj[rng.random(F1.N) < 0.2, 0] = np.nan
+    taken = (rng.random(F2.N) < 0.1).astype(np.uint8)
+    obs = (rng.random(F1.N) < 0.7).astype(np.uint8)
+    for th, ori, ho in [(15, True, None), (30, True, None), (15, False, None), (15, True, obs)]:
+        n_g, c_g = ORBmatcher(0.9, ori).SearchByProjectionLast(F2, F1.kps, proj, F1.desc, th, cur_taken=taken, last_has_obs=ho)
+        n_o, c_o = oracle.search_by_projection_last(F2, F1.kps, proj, F1.desc, F2.scale_factors, th, ori, cur_taken=taken, last_has_obs=ho)
+        assert n_g == n_o and np.array_equal(c_g, c_o) and n_g > 100
+
+
+def test_search_by_projection_map(oracle, front_pair):
+    from fishbirdeyevisualslam_b200.matcher import ORBmatcher
+    _, F2 = front_pair
+    rng = np.random.default_rng(7)
+    nmap = 6000
+    src = rng.integers(0, F2.N, nmap)
+    mdesc = flip_bits(rng, F2.desc[src], 60)
+    mproj = np.stack([F2.kps["x"][src], F2.kps["y"][src]], 1).astype(np.float32) + rng.normal(0, 2, (nmap, 2)).astype(np.float32)
+    mlevel = np.clip(F2.kps["octave"][src] + rng.integers(-1, 2, nmap), 0, 7).astype(np.int32)
+    mcos = rng.uniform(0.99, 1.0, nmap).astype(np.float32)
+    taken = (rng.random(F2.N) < 0.1).astype(np.uint8)
+    for th, ratio in [(1.0, 0.8), (3.0, 0.8), (5.0, 0.6)]:
+        n_g, c_g = ORBmatcher(ratio, True).SearchByProjectionMap(F2, mproj, mlevel, mcos, mdesc, th, cur_taken=taken)
+        n_o, c_o = oracle.search_by_projection_map(F2, F2.scale_factors, mproj, mlevel, mcos, mdesc, th, ratio, cur_taken=taken)
+        assert n_g == n_o and np.array_equal(c_g, c_o) and n_g > 300
+
+
+def test_search_by_bow(oracle, front_pair):
+    from fishbirdeyevisualslam_b200.matcher import ORBmatcher
+    F1, F2 = front_pair
+
+    def nodes(k, shift):
+        return (np.floor((k["x"] - shift[0]) / 80).astype(int) * 16 + np.floor((k["y"] - shift[1]) / 80).astype(int)) * 8 + k["octave"]
+    kfv, ffv = featvec(nodes(F1.kps, (0, 0))), featvec(nodes(F2.kps, (3, 2)))
+    has_mp = (np.random.default_rng(8).random(F1.N) < 0.8).astype(np.uint8)
+    for ratio, ori in [(0.7, True), (0.75, False)]:
+        n_g, f_g = ORBmatcher(ratio, ori).SearchByBoW(F1.kps, F1.desc, has_mp, kfv, F2, ffv)
+        n_o, f_o = oracle.search_by_bow(F1.kps, F1.desc, has_mp, kfv, F2.kps, F2.desc, ffv, ratio, ori)
+        assert n_g == n_o and np.array_equal(f_g, f_o) and n_g > 50
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_random_scenes_all_matchers(oracle, seed):
+    """Synthetic scenes with quantised coordinates (exact cell-boundary and window-boundary hits) and duplicates (ties)."""
+    from fishbirdeyevisualslam_b200.matcher import ORBmatcher
+    rng = np.random.default_rng(100 + seed)
+    F1, F2 = frame_pair(rng, 400)
+    pm_g = np.ascontiguousarray(np.stack([F1.kps["x"], F1.kps["y"]], 1), np.float32)
+    pm_o = pm_g.copy()
+    n_g, m_g = ORBmatcher(0.9, True).SearchForInitialization(F1, F2, pm_g, 100)
+    n_o, m_o = oracle.search_for_initialization(F1, F2, pm_o, 100, 0.9, True)
+    assert n_g == n_o and np.array_equal(m_g, m_o) and np.array_equal(pm_g, pm_o)
+    B1, B2 = frame_pair(rng, 400, 384, 384, bird=True)
+    n_g, d_g = ORBmatcher(0.9, True).BirdviewMatch(B2, B1.kps, B1.desc, 10)
+    n_o, d_o = oracle.birdview_match(B1.kps, B1.desc, B2, 10, 0.9, True)
+    assert n_g == n_o and np.array_equal(d_g, d_o)
+
+
+def test_quirk_cases_on_device(oracle):
+    from fishbirdeyevisualslam_b200.matcher import Frame, ORBmatcher
+    rng = np.random.default_rng(0)
+    # Q8: match to keypoint 0 is counted but not emitted
+    d = rng.integers(0, 256, (3, 32), dtype=np.uint8)
+    cur = Frame.bird(make_kps(np.float32([100, 200, 300]), np.float32([100, 200, 300])), d, 384, 384)
+    ref = make_kps(np.float32([101, 201]), np.float32([101, 201]))
+    n, dm = ORBmatcher(0.9, False).BirdviewMatch(cur, ref, d[:2], 10)
+    assert n == 2 and dm.tolist() == [[1, 1, 0]]
+    # Q2: exclusive upper cell bound of the bird query hides an in-window keypoint
+    k = make_kps(np.float32([3.0, 105.0]), np.float32([3.0, 100.0]))
+    dd = rng.integers(0, 256, (2, 32), dtype=np.uint8)
+    cur = Frame.bird(k, dd, 384, 384)
+    q = make_kps(np.float32([98.0]), np.float32([100.0]))
+    n, dm = ORBmatcher(0.9, False).BirdviewMatch(cur, q, dd[1:2], 10)
+    assert n == 0 and len(dm) == 0
+    # Q10: gate (<=) and steal
+    base = rng.integers(0, 256, 32, dtype=np.uint8)
+    far = base.copy(); far[0] ^= 0xFF
+    near = base.copy(); near[1] ^= 0x01
+    F2 = Frame.front(make_kps(np.float32([100]), np.float32([100])), base[None], 640, 480)
+    F1 = Frame.front(make_kps(np.float32([100, 101, 102]), np.float32([100, 100, 100])), np.stack([far, near, far]), 640, 480)
+    pm = np.ascontiguousarray(np.stack([F1.kps["x"], F1.kps["y"]], 1), np.float32)
+    n, m = ORBmatcher(0.9, False).SearchForInitialization(F1, F2, pm, 50)
+    assert n == 1 and m.tolist() == [-1, 0, -1]
+    # empty frames
+    E = Frame.front(make_kps(np.float32([]), np.float32([])), np.zeros((0, 32), np.uint8), 640, 480)
+    n, m = ORBmatcher(0.9, True).SearchForInitialization(F1, E, pm, 50)
+    assert n == 0 and m.tolist() == [-1, -1, -1]
+    n, m = ORBmatcher(0.9, True).SearchForInitialization(E, F2, np.zeros((0, 2), np.float32), 50)
+    assert n == 0 and len(m) == 0
+
+
+def test_bruteforce_top2_c5_size(oracle):
+    """C5 matching leg: 8000 x 8000 brute-force Hamming, ties -> lowest index, second counts duplicates."""
+    from fishbirdeyevisualslam_b200.matcher import ORBmatcher
+    rng = np.random.default_rng(9)
+    q = rng.integers(0, 256, (8000, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (8000, 32), dtype=np.uint8)
+    t[100] = q[5]; t[4000] = q[5]; t[7999] = q[6]
+    g = ORBmatcher(0.9, True).BruteForceTop2(q, t)
+    # oracle on a slice (the scalar loop needs ~1 s per 1000 queries) + vectorised numpy check of the distances
+    o = oracle.bruteforce_top2(q[:600], t)
+    assert all(np.array_equal(a[:600], b) for a, b in zip(g, o))
+    assert g[0][5] == 100 and g[1][5] == 0 and g[2][5] == 0 and g[0][6] == 7999
+    idx = rng.integers(0, 8000, 300)
+    dist = np.unpackbits(q[idx] ^ t[g[0][idx]], axis=1).sum(1)
+    assert np.array_equal(dist, g[1][idx])
+    assert (g[2] >= g[1]).all()

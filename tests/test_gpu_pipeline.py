@@ -1,0 +1,97 @@
+"""The device-resident batch pipeline (config C2/C4 shape): per-pair outputs equal single-image extraction + oracle
+matching; results do not depend on the batch size (shard equality); repeated steps are deterministic."""
+import numpy as np
+import pytest
+
+from fishbirdeyevisualslam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+FH, FW, BH, BW = 720, 1280, 384, 384
+
+
+def sequence(n, seed):
+    fr = np.stack([synth.frame(FH, FW, seed, (min(3 * i, 8) - 4, min(2 * i, 8) - 4), noise_seed=i) for i in range(n)])
+    bi = np.stack([synth.frame(BH, BW, seed + 1, (min(2 * i, 8) - 4, min(i, 8) - 4), noise_seed=50 + i) for i in range(n)])
+    return fr, bi
+
+
+def run_pipeline(fr, bi, batch):
+    import torch
+    from fishbirdeyevisualslam_b200.pipeline import FrontBirdPipeline
+    pipe = FrontBirdPipeline(batch)
+    dF, dB = torch.from_numpy(fr).cuda(), torch.from_numpy(bi).cuda()
+    out = []
+    for s in range(len(fr) // batch):
+        pipe.step_dev(dF[s * batch:].data_ptr(), dB[s * batch:].data_ptr())
+        res, fm, bm = pipe.fetch()
+        for p in range(batch):
+            fk, fd, bk, bd = pipe.fetch_pair(p)
+            nf, nb = int(res["n_front"][p]), int(res["n_bird"][p])
+            out.append(dict(res=res[p].copy(), fk=fk[:nf].copy(), fd=fd[:nf].copy(), bk=bk[:nb].copy(), bd=bd[:nb].copy(),
+                            fm=fm[p].copy(), bm=bm[p].copy()))
+    pipe.close()
+    return out
+
+
+def test_pipeline_equals_oracle_and_carries_across_steps(oracle):
+    from fishbirdeyevisualslam_b200.matcher import Frame
+    n, B = 8, 4
+    fr, bi = sequence(n, 100)
+    out = run_pipeline(fr, bi, B)
+    of, ob = oracle.OracleExtractor(2000, 1.2, 8, 15, 5), oracle.OracleExtractor(1000, 1.2, 8, 15, 5)
+    prev = None
+    for i, r in enumerate(out):
+        kf, df = of(fr[i])
+        kb, db = ob(bi[i])
+        assert r["fk"].tobytes() == kf.tobytes() and np.array_equal(r["fd"], df)
+        assert r["bk"].tobytes() == kb.tobytes() and np.array_equal(r["bd"], db)
+        F, Bf = Frame.front(kf, df, FW, FH), Frame.bird(kb, db, BW, BH)
+        if prev is None:
+            assert r["res"]["front_matches"] == 0 and r["res"]["bird_matches"] == 0
+        else:
+            pm = np.ascontiguousarray(np.stack([prev[0].kps["x"], prev[0].kps["y"]], 1), np.float32)
+            n_o, m_o = oracle.search_for_initialization(prev[0], F, pm, 100, 0.9, True)
+            nb_o, d_o = oracle.birdview_match(prev[1].kps, prev[1].desc, Bf, 10, 0.9, True)
+            assert r["res"]["front_matches"] == n_o and np.array_equal(r["fm"][:prev[0].N], m_o) and n_o > 100
+            gm = r["bm"][:prev[1].N]
+            assert r["res"]["bird_matches"] == nb_o and nb_o > 50
+            assert np.array_equal(np.stack([np.nonzero(gm > 0)[0], gm[gm > 0]], 1), d_o[:, :2])
+        prev = (F, Bf)
+
+
+def test_shard_equality_and_determinism():
+    """Processing 12 pairs as 1x12, 2x6 or 4x3 (or twice) gives byte-identical per-pair results."""
+    fr, bi = sequence(12, 300)
+    ref = run_pipeline(fr, bi, 12)
+    for batch in (6, 3, 12):
+        got = run_pipeline(fr, bi, batch)
+        for a, b in zip(ref, got):
+            assert a["res"].tobytes() == b["res"].tobytes()
+            assert a["fk"].tobytes() == b["fk"].tobytes() and np.array_equal(a["fd"], b["fd"])
+            assert a["bk"].tobytes() == b["bk"].tobytes() and np.array_equal(a["bd"], b["bd"])
+            nq = len(a["fk"])
+            assert np.array_equal(a["fm"][:nq], b["fm"][:nq])
+
+
+def test_host_step_equals_device_step():
+    import torch
+    from fishbirdeyevisualslam_b200 import _lib
+    from fishbirdeyevisualslam_b200.pipeline import FrontBirdPipeline, PinnedBuffer
+    B = 4
+    fr, bi = sequence(B, 500)
+    p1, p2 = FrontBirdPipeline(B), FrontBirdPipeline(B)
+    dF, dB = torch.from_numpy(fr).cuda(), torch.from_numpy(bi).cuda()
+    p1.step_dev(dF.data_ptr(), dB.data_ptr())
+    r1, f1, b1 = p1.fetch()
+    hF, hB = PinnedBuffer(fr.shape), PinnedBuffer(bi.shape)
+    hF.array[...] = fr
+    hB.array[...] = bi
+    r2 = np.zeros(B, _lib.PAIR_RESULT_DTYPE)
+    f2 = np.zeros((B, p2.front_cap), np.int32)
+    b2 = np.zeros((B, p2.bird_cap), np.int32)
+    p2.step_host(hF.ptr, hB.ptr, r2, f2, b2)
+    assert r1.tobytes() == r2.tobytes()
+    for p in range(1, B):
+        nq, nb = int(r1["n_front"][p - 1]), int(r1["n_bird"][p - 1])
+        assert np.array_equal(f1[p][:nq], f2[p][:nq]) and np.array_equal(b1[p][:nb], b2[p][:nb])

@@ -1,0 +1,69 @@
+"""The restated extractor (oracle/orb_oracle.cpp) against the reference's own ORBextractor.cc: (a) committed outputs of
+the verbatim build (tests/golden/extract.npz), (b) the verbatim build itself when oracle/_ref exists."""
+import zlib
+
+import numpy as np
+import pytest
+
+from fishbirdeyevisualslam_b200 import synth
+
+
+def test_golden_small_full(oracle, extract_golden):
+    g = extract_golden
+    for i in range(3):
+        h, w, nf, nl, seed = g[f"small{i}_cfg"].tolist()
+        img = synth.frame(h, w, seed)
+        assert synth.crc(img) == int(g[f"small{i}_img_crc"]), "synthetic image generator drifted"
+        k, d = oracle.OracleExtractor(nf, 1.2, nl, 15, 5)(img)
+        assert k.view(np.uint8).reshape(-1, 28).tobytes() == g[f"small{i}_kps"].tobytes()
+        assert np.array_equal(d, g[f"small{i}_desc"])
+
+
+def test_golden_baseline_sizes_crc(oracle, extract_golden):
+    for h, w, nf, nl, seed, icrc, n, kcrc, dcrc in extract_golden["big"].tolist():
+        img = synth.frame(h, w, seed)
+        assert synth.crc(img) == icrc
+        k, d = oracle.OracleExtractor(nf, 1.2, nl, 15, 5)(img)
+        assert (len(k), zlib.crc32(k.tobytes()) & 0xFFFFFFFF, zlib.crc32(d.tobytes()) & 0xFFFFFFFF) == (n, kcrc, dcrc)
+
+
+@pytest.mark.parametrize("cfg", [(120, 160, 300, 4, 31), (96, 400, 200, 3, 8), (300, 200, 400, 5, 9), (200, 300, 2000, 5, 5), (150, 150, 50, 2, 6)])
+def test_against_verbatim_reference(oracle, cfg):
+    if oracle.ref() is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    h, w, nf, nl, seed = cfg
+    img = synth.frame(h, w, seed)
+    o, r = oracle.OracleExtractor(nf, 1.2, nl, 15, 5), oracle.RefExtractor(nf, 1.2, nl, 15, 5)
+    ko, do = o(img)
+    kr, dr = r(img)
+    assert ko.tobytes() == kr.tobytes() and np.array_equal(do, dr)
+    for l in range(nl):
+        assert np.array_equal(o.level_padded(l), r.pyramid_level(img, l))
+    tr = r.tables()
+    to = o.tables()
+    for key in tr:
+        assert np.array_equal(tr[key], to[key])
+
+
+def test_flat_and_single_corner(oracle):
+    flat = np.full((120, 160), 77, np.uint8)
+    k, d = oracle.OracleExtractor(300, 1.2, 4, 15, 5)(flat)
+    assert len(k) == 0 and d.shape == (0, 32)
+    one = flat.copy()
+    one[50:70, 60:90] = 200
+    k, d = oracle.OracleExtractor(300, 1.2, 4, 15, 5)(one)
+    assert len(k) > 0 and (k["response"] >= 5).all()
+    if oracle.ref() is not None:
+        kr, dr = oracle.RefExtractor(300, 1.2, 4, 15, 5)(one)
+        assert k.tobytes() == kr.tobytes() and np.array_equal(d, dr)
+
+
+def test_octree_tie_rule_and_overshoot(oracle):
+    # equal-response keys inside a leaf: first in candidate order wins; sweep can return more than N keypoints
+    import ctypes as C
+    L = oracle.lib()
+    xy = np.array([[x, y, 30] for y in range(3, 60, 4) for x in range(3, 120, 4)], np.int32)
+    sel = np.zeros(len(xy), np.int32)
+    n = L.orc_octree(xy.ctypes.data_as(C.c_void_p), len(xy), 0, 124, 0, 64, 40, sel.ctypes.data_as(C.c_void_p), len(sel))
+    assert n >= 40
+    assert len(set(sel[:n].tolist())) == n
