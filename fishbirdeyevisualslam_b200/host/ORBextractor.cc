@@ -1,0 +1,86 @@
+// Host side of the drop-in ORBextractor: marshals cv::Mat / cv::KeyPoint to the C-ABI and back.
+// Error behaviour mirrors the reference (src/ORBextractor.cc:1043-1069): empty image -> return with outputs untouched,
+// non-8UC1 image -> assert, zero keypoints -> descriptors released.  A C-ABI failure (no GPU, unsupported geometry)
+// is fatal -- there is deliberately no CPU fallback.
+#include "ORBextractor.h"
+
+#include <cassert>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "fbe_cabi.h"
+
+namespace ORB_SLAM2 {
+
+static void die(const char* what, int rc) {
+    std::fprintf(stderr, "ORBextractor (fbe-b200): %s failed: %d (%s)\n", what, rc, fbe_last_error());
+    std::abort();
+}
+
+ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
+    : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
+      handle_(NULL) {
+    fbe_extractor_cfg cfg;
+    cfg.nfeatures = _nfeatures; cfg.scale_factor = _scaleFactor; cfg.nlevels = _nlevels;
+    cfg.ini_th_fast = _iniThFAST; cfg.min_th_fast = _minThFAST; cfg.max_batch = 1; cfg.device = 0;
+    if (const char* d = std::getenv("FBE_DEVICE")) cfg.device = std::atoi(d);
+    int rc = fbe_extractor_create(&cfg, &handle_);
+    if (rc != FBE_OK) die("fbe_extractor_create", rc);
+    int32_t n = 0;
+    const float *s, *is, *s2, *is2;
+    fbe_extractor_tables(handle_, &n, &s, &is, &s2, &is2);
+    mvScaleFactor.assign(s, s + n);
+    mvInvScaleFactor.assign(is, is + n);
+    mvLevelSigma2.assign(s2, s2 + n);
+    mvInvLevelSigma2.assign(is2, is2 + n);
+    const int32_t* per;
+    fbe_extractor_features_per_level(handle_, &per);
+    mnFeaturesPerLevel.assign(per, per + n);
+    mvImagePyramid.resize(nlevels);
+}
+
+ORBextractor::~ORBextractor() {
+    if (handle_) fbe_extractor_destroy(handle_);
+}
+
+void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint>& _keypoints,
+                              cv::OutputArray _descriptors) {
+    if (_image.empty()) return;
+    cv::Mat image = _image.getMat();
+    assert(image.type() == CV_8UC1);
+
+    int32_t cap = 0;
+    int rc = fbe_extractor_max_keypoints(handle_, image.rows, image.cols, &cap);
+    if (rc != FBE_OK) die("fbe_extractor_max_keypoints", rc);
+    // cv::KeyPoint is layout-compatible with fbe_keypoint (7 x 4 bytes)
+    static_assert(sizeof(cv::KeyPoint) == sizeof(fbe_keypoint), "cv::KeyPoint layout");
+    std::vector<cv::KeyPoint> kps(cap);
+    std::vector<unsigned char> desc((size_t)cap * 32);
+    int32_t n = 0;
+    rc = fbe_extract(handle_, image.ptr(0), image.rows, image.cols, (size_t)image.step, reinterpret_cast<fbe_keypoint*>(kps.data()),
+                     desc.data(), cap, &n);
+    if (rc != FBE_OK) die("fbe_extract", rc);
+
+    if (n == 0) {
+        _descriptors.release();
+    } else {
+        _descriptors.create(n, 32, CV_8U);
+        cv::Mat d = _descriptors.getMat();
+        for (int i = 0; i < n; ++i) std::memcpy(d.ptr(i), &desc[(size_t)i * 32], 32);
+    }
+    kps.resize(n);
+    _keypoints.swap(kps);
+}
+
+void ORBextractor::SyncImagePyramid() {
+    for (int l = 0; l < nlevels; ++l) {
+        int32_t r = 0, c = 0;
+        if (fbe_pyramid_level(handle_, 0, l, NULL, 0, &r, &c) != FBE_OK) return;
+        cv::Mat padded(r + 38, c + 38, CV_8UC1);
+        fbe_pyramid_level(handle_, 0, l, padded.ptr(0), (size_t)padded.step, &r, &c);
+        mvImagePyramid[l] = padded(cv::Rect(19, 19, c, r));      // ROI view with the 19-px frame around it, like the reference
+    }
+}
+
+}  // namespace ORB_SLAM2

@@ -1,0 +1,258 @@
+// Drop-in bodies for the ORBmatcher methods on the hot path.  This file is compiled INSIDE the reference tree in place
+// of the same-named method bodies of src/ORBmatcher.cc (see INTEGRATION.md for the exact patch); the class declaration
+// include/ORBmatcher.h is unchanged, so Tracking.cc / LocalMapping.cc / LoopClosing.cc call it as before.  Methods that
+// are not on the hot path (SearchForTriangulation, SearchBySim3, Fuse x2, the KF-KF SearchByBoW, the relocalisation and
+// loop-closing SearchByProjection overloads) keep the reference's own CPU code.
+//
+// It cannot be compiled in the build image of this repository (needs the reference's Frame.h/KeyFrame.h/MapPoint.h with
+// OpenCV, Eigen, DBoW2); the marshalling below is mirrored, field for field, by the Python host
+// (fishbirdeyevisualslam_b200/matcher.py), which IS tested against the oracle on the GPU.
+//
+// Everything pointer-valued stays on the host: frames are flattened to (keypoints, descriptors, grid geometry),
+// map points to (projection, level, descriptor) arrays; the C-ABI returns index lists which are turned back into
+// pointer writes here.  cv::Mat arithmetic of the reference (projections, bird pixel conversion, the distance
+// filter of BirdMapPointMatch) is executed here exactly as the reference writes it.
+#include <cmath>
+#include <limits>
+#include <vector>
+
+#include "Converter.h"
+#include "Frame.h"
+#include "KeyFrame.h"
+#include "MapPoint.h"
+#include "MapPointBird.h"
+#include "ORBmatcher.h"
+#include "fbe_cabi.h"
+
+namespace ORB_SLAM2 {
+
+namespace {
+
+static_assert(sizeof(cv::KeyPoint) == sizeof(fbe_keypoint), "cv::KeyPoint must be 28 bytes");
+
+struct Matcher {          // one device matcher per calling thread and per (ratio, orientation) setting
+    fbe_matcher* h;
+    float ratio;
+    bool ori;
+};
+
+fbe_matcher* matcher_for(float ratio, bool ori) {
+    static thread_local std::vector<Matcher> cache;
+    for (size_t i = 0; i < cache.size(); ++i)
+        if (cache[i].ratio == ratio && cache[i].ori == ori) return cache[i].h;
+    Matcher m = {NULL, ratio, ori};
+    if (fbe_matcher_create(ratio, ori ? 1 : 0, 0, &m.h) != FBE_OK) {
+        fprintf(stderr, "ORBmatcher (fbe-b200): %s\n", fbe_last_error());
+        abort();      // no CPU fallback
+    }
+    cache.push_back(m);
+    return m.h;
+}
+
+const unsigned char* desc_ptr(const cv::Mat& d) { return d.empty() ? NULL : d.ptr<unsigned char>(0); }
+
+fbe_frame_view front_view(const Frame& F) {
+    fbe_frame_view v;
+    v.kps = reinterpret_cast<const fbe_keypoint*>(F.mvKeysUn.data());
+    v.desc = desc_ptr(F.mDescriptors);         // rows are contiguous: created by OutputArray::create(n, 32, CV_8U)
+    v.n = F.N;
+    v.min_x = Frame::mnMinX; v.min_y = Frame::mnMinY;
+    v.inv_w = Frame::mfGridElementWidthInv; v.inv_h = Frame::mfGridElementHeightInv;
+    v.gcols = FRAME_GRID_COLS; v.grows = FRAME_GRID_ROWS;
+    return v;
+}
+
+fbe_frame_view bird_view(const Frame& F) {
+    fbe_frame_view v;
+    v.kps = reinterpret_cast<const fbe_keypoint*>(F.mvKeysBird.data());
+    v.desc = desc_ptr(F.mDescriptorsBird);
+    v.n = (int)F.mvKeysBird.size();
+    v.min_x = 0.f; v.min_y = 0.f;
+    v.inv_w = Frame::mfGridElementWidthInvBirdview; v.inv_h = Frame::mfGridElementHeightInvBirdview;
+    v.gcols = FRAME_GRID_BIRD; v.grows = FRAME_GRID_BIRD;
+    return v;
+}
+
+void copy_desc(const cv::Mat& d, unsigned char* dst) { std::memcpy(dst, d.ptr<unsigned char>(0), 32); }
+
+}  // namespace
+
+// src/ORBmatcher.cc:406-521
+int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched,
+                                        std::vector<int>& vnMatches12, int windowSize) {
+    vnMatches12 = std::vector<int>(F1.mvKeysUn.size(), -1);
+    fbe_frame_view v1 = front_view(F1), v2 = front_view(F2);
+    int nmatches = 0;
+    static_assert(sizeof(cv::Point2f) == 8, "Point2f layout");
+    fbe_search_for_initialization(matcher_for(mfNNratio, mbCheckOrientation), &v1, &v2,
+                                  reinterpret_cast<float*>(vbPrevMatched.data()), vnMatches12.data(), windowSize, &nmatches);
+    return nmatches;
+}
+
+// src/ORBmatcher.cc:1329-1471 (monocular: bForward/bBackward are false when bMono)
+int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono) {
+    const cv::Mat Rcw = CurrentFrame.mTcw.rowRange(0, 3).colRange(0, 3);
+    const cv::Mat tcw = CurrentFrame.mTcw.rowRange(0, 3).col(3);
+    const int n = LastFrame.N;
+    std::vector<float> proj(2 * (size_t)n, std::numeric_limits<float>::quiet_NaN());
+    std::vector<unsigned char> mpdesc(32 * (size_t)n, 0), has_obs(n, 1);
+    for (int i = 0; i < n; i++) {
+        MapPoint* pMP = LastFrame.mvpMapPoints[i];
+        if (!pMP || LastFrame.mvbOutlier[i]) continue;
+        cv::Mat x3Dw = pMP->GetWorldPos();
+        cv::Mat x3Dc = Rcw * x3Dw + tcw;
+        const float xc = x3Dc.at<float>(0), yc = x3Dc.at<float>(1);
+        const float invzc = 1.0 / x3Dc.at<float>(2);
+        if (invzc < 0) continue;
+        float u = CurrentFrame.fx * xc * invzc + CurrentFrame.cx;
+        float v = CurrentFrame.fy * yc * invzc + CurrentFrame.cy;
+        if (u < CurrentFrame.mnMinX || u > CurrentFrame.mnMaxX) continue;
+        if (v < CurrentFrame.mnMinY || v > CurrentFrame.mnMaxY) continue;
+        proj[2 * i] = u; proj[2 * i + 1] = v;
+        copy_desc(pMP->GetDescriptor(), &mpdesc[32 * (size_t)i]);
+        has_obs[i] = pMP->Observations() > 0;
+    }
+    std::vector<unsigned char> taken(CurrentFrame.N, 0);
+    for (int k = 0; k < CurrentFrame.N; k++)
+        if (CurrentFrame.mvpMapPoints[k] && CurrentFrame.mvpMapPoints[k]->Observations() > 0) taken[k] = 1;
+    std::vector<int> cur_mp(CurrentFrame.N, -1);
+    fbe_frame_view cv_ = front_view(CurrentFrame);
+    int nmatches = 0;
+    (void)bMono;   // stereo windows (mvuRight) are not part of the hot path of this fork (monocular + bird)
+    fbe_search_by_projection_last(matcher_for(mfNNratio, mbCheckOrientation), &cv_,
+                                  reinterpret_cast<const fbe_keypoint*>(LastFrame.mvKeysUn.data()), proj.data(), mpdesc.data(), n,
+                                  CurrentFrame.mvScaleFactors.data(), (int)CurrentFrame.mvScaleFactors.size(), taken.data(),
+                                  has_obs.data(), th, cur_mp.data(), &nmatches);
+    // pointer writes of :1431 and :1461; entries pruned by the orientation histogram come back as -1, which the
+    // reference turns into NULL only for keypoints it had just written -- identical here because cur_mp is -1
+    // everywhere except for assignments made by this call.
+    for (int k = 0; k < CurrentFrame.N; k++)
+        if (cur_mp[k] >= 0) CurrentFrame.mvpMapPoints[k] = LastFrame.mvpMapPoints[cur_mp[k]];
+    return nmatches;
+}
+
+// src/ORBmatcher.cc:46-130
+int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th) {
+    std::vector<int> src;
+    std::vector<float> proj, viewcos;
+    std::vector<int> level;
+    std::vector<unsigned char> desc, has_obs;
+    for (size_t iMP = 0; iMP < vpMapPoints.size(); iMP++) {
+        MapPoint* pMP = vpMapPoints[iMP];
+        if (!pMP->mbTrackInView || pMP->isBad()) continue;
+        src.push_back((int)iMP);
+        proj.push_back(pMP->mTrackProjX); proj.push_back(pMP->mTrackProjY);
+        level.push_back(pMP->mnTrackScaleLevel);
+        viewcos.push_back(pMP->mTrackViewCos);
+        desc.resize(desc.size() + 32);
+        copy_desc(pMP->GetDescriptor(), &desc[desc.size() - 32]);
+        has_obs.push_back(pMP->Observations() > 0);
+    }
+    std::vector<unsigned char> taken(F.N, 0);
+    for (int k = 0; k < F.N; k++)
+        if (F.mvpMapPoints[k] && F.mvpMapPoints[k]->Observations() > 0) taken[k] = 1;
+    std::vector<int> cur_mp(F.N, -1);
+    fbe_frame_view v = front_view(F);
+    int nmatches = 0;
+    fbe_search_by_projection_map(matcher_for(mfNNratio, mbCheckOrientation), &v, F.mvScaleFactors.data(), (int)F.mvScaleFactors.size(),
+                                 proj.data(), level.data(), viewcos.data(), desc.data(), (int)src.size(), taken.data(),
+                                 has_obs.data(), th, cur_mp.data(), &nmatches);
+    for (int k = 0; k < F.N; k++)
+        if (cur_mp[k] >= 0) F.mvpMapPoints[k] = vpMapPoints[src[cur_mp[k]]];
+    return nmatches;
+}
+
+// src/ORBmatcher.cc:160-289
+int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches) {
+    const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+    vpMapPointMatches = std::vector<MapPoint*>(F.N, static_cast<MapPoint*>(NULL));
+    std::vector<unsigned char> has_mp(vpMapPointsKF.size(), 0);
+    for (size_t i = 0; i < vpMapPointsKF.size(); i++) has_mp[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();
+    // DBoW2::FeatureVector = std::map<NodeId, std::vector<unsigned int>> -> CSR over ascending node ids
+    struct Csr { std::vector<int> ids, start, items; };
+    auto flatten = [](const DBoW2::FeatureVector& fv) {
+        Csr c;
+        c.start.push_back(0);
+        for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+            c.ids.push_back((int)it->first);
+            c.items.insert(c.items.end(), it->second.begin(), it->second.end());
+            c.start.push_back((int)c.items.size());
+        }
+        return c;
+    };
+    Csr a = flatten(pKF->mFeatVec), b = flatten(F.mFeatVec);
+    std::vector<int> f_mp(F.N, -1);
+    int nmatches = 0;
+    fbe_search_by_bow(matcher_for(mfNNratio, mbCheckOrientation), reinterpret_cast<const fbe_keypoint*>(pKF->mvKeysUn.data()),
+                      desc_ptr(pKF->mDescriptors), (int)pKF->mvKeysUn.size(), has_mp.data(), a.ids.data(), a.start.data(),
+                      a.items.data(), (int)a.ids.size(), reinterpret_cast<const fbe_keypoint*>(F.mvKeys.data()), desc_ptr(F.mDescriptors),
+                      F.N, b.ids.data(), b.start.data(), b.items.data(), (int)b.ids.size(), f_mp.data(), &nmatches);
+    for (int k = 0; k < F.N; k++)
+        if (f_mp[k] >= 0) vpMapPointMatches[k] = vpMapPointsKF[f_mp[k]];
+    return nmatches;
+}
+
+// src/ORBmatcher.cc:1602-1760, isProject == 0 (every call site of the reference passes 0)
+int ORBmatcher::BirdviewMatch(Frame& CurF, const std::vector<cv::KeyPoint>& vRefKeysBird, const cv::Mat& DescriptorsBird,
+                              const std::vector<MapPointBird*>& vRefMapPointsBird, std::vector<cv::DMatch>& vDMatches12,
+                              int isProject, int windowSize) {
+    (void)vRefMapPointsBird;
+    if (isProject) { fprintf(stderr, "BirdviewMatch(isProject=1) is not on the accelerated path\n"); abort(); }
+    const int n = (int)vRefKeysBird.size();
+    std::vector<int> dm(3 * (size_t)std::max(n, 1));
+    int nd = 0, nmatches = 0;
+    fbe_frame_view v = bird_view(CurF);
+    fbe_birdview_match(matcher_for(mfNNratio, mbCheckOrientation), reinterpret_cast<const fbe_keypoint*>(vRefKeysBird.data()),
+                       desc_ptr(DescriptorsBird), n, &v, windowSize, dm.data(), &nd, &nmatches);
+    for (int i = 0; i < nd; i++) vDMatches12.push_back(cv::DMatch(dm[3 * i], dm[3 * i + 1], (float)dm[3 * i + 2]));
+    return nmatches;
+}
+
+// src/ORBmatcher.cc:1763-1902
+int ORBmatcher::BirdMapPointMatch(Frame& CurF, const std::vector<MapPointBird*>& vRefMapPointsBird, int windowSize, float filterSize) {
+    const cv::Mat Tbw = Frame::Tbc * CurF.mTcw;
+    const int n = (int)vRefMapPointsBird.size();
+    std::vector<float> pix(2 * (size_t)n, std::numeric_limits<float>::quiet_NaN());
+    std::vector<unsigned char> desc(32 * (size_t)n, 0);
+    for (int i1 = 0; i1 < n; i1++) {
+        MapPointBird* p = vRefMapPointsBird[i1];
+        if (!p) continue;
+        cv::Mat worldPos = p->GetWorldPos();
+        cv::Mat localPos = Tbw.rowRange(0, 3).colRange(0, 3) * worldPos + Tbw.rowRange(0, 3).col(3);
+        if (fabs(localPos.at<float>(2)) > 0.2) continue;
+        cv::Point2f pt = Converter::BaseXY2BirdPixel(cv::Point3f(localPos.at<float>(0), localPos.at<float>(1), localPos.at<float>(2)));
+        if (pt.x < 0 || pt.x >= Frame::birdviewCols || pt.y < 0 || pt.y >= Frame::birdviewRows) continue;
+        pix[2 * i1] = pt.x; pix[2 * i1 + 1] = pt.y;
+        copy_desc(p->GetDescriptor(), &desc[32 * (size_t)i1]);
+    }
+    std::vector<int> vnMatches12(n, -1);
+    int nmatches = 0;
+    fbe_frame_view v = bird_view(CurF);
+    fbe_bird_map_point_match(matcher_for(mfNNratio, mbCheckOrientation), pix.data(), desc.data(), n, &v, windowSize,
+                             vnMatches12.data(), &nmatches);
+    // second pass, :1865-1895, verbatim semantics (host arithmetic, `> 0` quirk, last writer wins)
+    int InlierMatches = 0;
+    cv::Mat Tcw2 = CurF.mTcw;
+    for (int i1 = 0; i1 < n; i1++) {
+        if (vnMatches12[i1] > 0) {
+            MapPointBird* p = vRefMapPointsBird[i1];
+            if (!p) continue;
+            cv::Mat ptwC = p->GetWorldPos();
+            cv::Mat ptc2c = Tcw2.rowRange(0, 3).colRange(0, 3) * ptwC + Tcw2.rowRange(0, 3).col(3);
+            cv::Mat pt2c(CurF.mvKeysBirdCamXYZ[vnMatches12[i1]]);
+            double disC = cv::norm(ptc2c - pt2c, cv::NORM_L2);
+            if (disC < filterSize) {
+                CurF.mvpMapPointsBird[vnMatches12[i1]] = p;
+                InlierMatches++;
+            }
+        }
+    }
+    return InlierMatches;
+}
+
+// src/ORBmatcher.cc:1951-1967 -- stays a host inline (called pairwise from MapPoint.cc:281, MapPointBird.cc:129, Frame.cc:872)
+int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b) {
+    return fbe_hamming256(a.ptr<unsigned char>(), b.ptr<unsigned char>());
+}
+
+}  // namespace ORB_SLAM2

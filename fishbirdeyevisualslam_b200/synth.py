@@ -77,16 +77,21 @@ def crc(a: np.ndarray) -> int:
 
 
 def cheap_batch(n: int, h: int, w: int, seed: int) -> np.ndarray:
-    """n frames for throughput runs: a handful of fully-synthesised scenes, each reused with a per-frame
-    integer displacement and fresh pixel noise (building 4096 scenes from scratch would dominate the bench)."""
+    """n consecutive frames for throughput runs: a handful of fully synthesised scenes, each viewed by a run of
+    consecutive frames through a window that drifts a few pixels per frame with fresh pixel noise (so consecutive frames
+    match, as in a real sequence; building thousands of scenes from scratch would dominate the bench set-up)."""
     nscene = min(n, 8)
-    scenes = [scene(h, w, seed * 1000 + s) for s in range(nscene)]
+    run = (n + nscene - 1) // nscene
     out = np.empty((n, h, w), np.uint8)
     rng = np.random.default_rng(seed ^ 0x5EED)
     m = 8
+    sc = None
     for i in range(n):
-        sc = scenes[i % nscene]
-        dx, dy = int(rng.integers(-m, m + 1)), int(rng.integers(-m, m + 1))
+        j = i % run
+        if j == 0:
+            sc = scene(h, w, seed * 1000 + i // run)
+        k = j % 9                       # drift (+2,+1) px per frame, back and forth inside the +-8 px margin
+        dx, dy = (2 * k - 8 if k <= 8 else 0), (k - 4)
         win = sc[m - dy:m - dy + h, m - dx:m - dx + w]
         out[i] = np.clip(np.rint(win + rng.normal(0.0, 2.0, size=(h, w))), 0, 255).astype(np.uint8)
     return out

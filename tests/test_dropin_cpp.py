@@ -1,0 +1,54 @@
+"""The C++ drop-in ORB_SLAM2::ORBextractor (fishbirdeyevisualslam_b200/host/) compiled against the test-only cv shim:
+CPU: it compiles and links against libfbe_b200.so.  GPU: its outputs equal the oracle's."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from fishbirdeyevisualslam_b200 import synth
+from fishbirdeyevisualslam_b200._lib import KP_DTYPE
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "fishbirdeyevisualslam_b200", "host")
+EXE = os.path.join(ROOT, "tests", "cpp", "dropin_main")
+
+
+def build_exe():
+    pkg = os.path.join(ROOT, "fishbirdeyevisualslam_b200")
+    cmd = ["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "oracle", "cvshim"), "-I", HOST, "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "dropin_main.cc"), os.path.join(HOST, "ORBextractor.cc"),
+           os.path.join(ROOT, "oracle", "cvshim", "shim.cpp"), "-L", pkg, "-lfbe_b200", f"-Wl,-rpath,{pkg}", "-o", EXE]
+    subprocess.run(cmd, check=True)
+
+
+def test_dropin_compiles_and_links(fbe):
+    build_exe()
+    assert os.path.exists(EXE)
+
+
+@pytest.mark.gpu
+def test_dropin_matches_oracle(oracle, tmp_path):
+    build_exe()
+    h, w, nf, nl = 240, 320, 500, 6
+    img = synth.frame(h, w, 32)
+    raw, out = tmp_path / "in.raw", tmp_path / "out.bin"
+    img.tofile(raw)
+    subprocess.run([EXE, str(h), str(w), str(nf), str(nl), str(raw), str(out)], check=True)
+    b = out.read_bytes()
+    n = struct.unpack_from("<i", b, 0)[0]
+    k = np.frombuffer(b, KP_DTYPE, n, 4)
+    d = np.frombuffer(b, np.uint8, n * 32, 4 + n * 28).reshape(n, 32)
+    o = oracle.OracleExtractor(nf, 1.2, nl, 15, 5)
+    ko, do = o(img)
+    assert k.tobytes() == ko.tobytes() and np.array_equal(d, do)
+    off = 4 + n * 60
+    lv = struct.unpack_from("<i", b, off)[0]
+    assert lv == nl
+    sf = np.frombuffer(b, np.float32, lv, off + 4)
+    assert np.array_equal(sf, o.tables()["scale"])
+    off += 4 + 8 * lv
+    tr, tc = struct.unpack_from("<ii", b, off)
+    top = np.frombuffer(b, np.uint8, tr * tc, off + 8).reshape(tr, tc)
+    assert np.array_equal(top, o.level_padded(nl - 1)[19:-19, 19:-19])

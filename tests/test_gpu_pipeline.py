@@ -66,12 +66,13 @@ def test_shard_equality_and_determinism():
     ref = run_pipeline(fr, bi, 12)
     for batch in (6, 3, 12):
         got = run_pipeline(fr, bi, batch)
-        for a, b in zip(ref, got):
+        for i, (a, b) in enumerate(zip(ref, got)):
             assert a["res"].tobytes() == b["res"].tobytes()
             assert a["fk"].tobytes() == b["fk"].tobytes() and np.array_equal(a["fd"], b["fd"])
             assert a["bk"].tobytes() == b["bk"].tobytes() and np.array_equal(a["bd"], b["bd"])
-            nq = len(a["fk"])
-            assert np.array_equal(a["fm"][:nq], b["fm"][:nq])
+            if i:       # match lists are indexed by the PREVIOUS pair's keypoints
+                nq, nb = len(ref[i - 1]["fk"]), len(ref[i - 1]["bk"])
+                assert np.array_equal(a["fm"][:nq], b["fm"][:nq]) and np.array_equal(a["bm"][:nb], b["bm"][:nb])
 
 
 def test_host_step_equals_device_step():
