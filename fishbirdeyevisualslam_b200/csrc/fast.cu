@@ -1,5 +1,7 @@
 // Per-cell FAST-9/16 detection with threshold fallback (ComputeKeyPointsOctTree cell loop,
-// src/ORBextractor.cc:765-829) as ONE kernel: a CTA owns one ~30x30 FAST cell of one level of one image.
+// src/ORBextractor.cc:765-829) as ONE kernel.  A CTA owns a GROUP of up to 8 consecutive ~30x30 FAST cells of one
+// cell row of one level of one image (a strip <= 256 px wide), so that the 3-px ring halo and the per-CTA fixed costs
+// are amortised over ~8k pixels.
 //
 // What the reference does per cell: cv::FAST(roi, iniThFAST, nms) and, when that returns nothing,
 // cv::FAST(roi, minThFAST, nms).  Facts used (pinned against cv2 by the oracle tests):
@@ -10,166 +12,236 @@
 //     the level exactly and NMS never looks across a cell edge (outside counts as score 0).
 //   * FAST(t) == { k in FAST(lo) : k.response >= t } for t >= lo on the same ROI, so one score/NMS pass at the low
 //     threshold yields both answers; the fallback decision is "no NMS survivor with score >= iniThFAST".
+//
+// Phases of a CTA (all in shared memory, 4 block barriers):
+//   0. stage the strip + 3-px halo with aligned 32-bit loads; clear the score tile and the survivor masks.
+//   1. PRETEST every pixel with the 4 compass ring pixels (every 9-arc contains k or k+8 for each k, so
+//      min(max(I0,I8),max(I4,I12)) - c > t  or  c - max(min(I0,I8),min(I4,I12)) > t is necessary); passing pixels are
+//      appended to a work list (warp-aggregated shared atomics) -- this removes the divergence of the score phase.
+//   2. SCORE the work list densely: ring differences are packed as biased s16x2 {I-c+256, c-I+256} with ONE IMAD each, so
+//      that bright and dark arcs share the DPX 3-input min/max (VIMNMX3.S16x2): 16+16 min3 + 8 max3 per pixel.
+//   3. strict 8-neighbour NMS of the listed pixels inside their cell; survivors set a bit in per-cell row masks
+//      (all survivors / survivors with score >= iniThFAST).
+//   4. EMIT: one warp per cell turns the row masks into the (y, x)-ordered slot list of the cell (ballot-free: popc +
+//      warp scan), choosing the iniThFAST mask when it is non-empty, else the minThFAST one.
 // Output per cell: survivors in (y, x) order as packed keys in the cell's private slot range + a count.  The octree
 // kernel concatenates cells in row-major order, which reproduces vToDistributeKeys order.
+#include <algorithm>
 #include "fbe_internal.cuh"
 
 namespace fbe {
 
 constexpr int kFastThreads = 256;
+constexpr int kFastWarps = kFastThreads / 32;
 
-// m for one pixel given its 16 ring differences d[k] = I_k - c (k clockwise).
-__device__ __forceinline__ int fast_m_from_ring(const int (&d)[16]) {
-    // sliding-window minimum (bright) / maximum (dark) of length 9 over the circular array, by doubling
-    int lo1[16], hi1[16];
+struct FastLayout { int tpitch, spitch, off_sc, sc_bytes, off_work, off_mask, mask_words, off_xinfo, total; };
+
+// shared-memory carve-up for a strip of gw x ch pixels covering ncell cells
+__host__ __device__ inline FastLayout fast_layout(int gw, int ch, int ncell) {
+    FastLayout L;
+    L.tpitch = (gw + 6 + 3 + 3) & ~3;                // up to 3 bytes of alignment shift in front of the halo
+    L.spitch = (gw + 2 + 3) & ~3;                    // score tile with a 1-px zero margin
+    int o = (L.tpitch * (ch + 6) + 15) & ~15;
+    L.off_sc = o;
+    L.sc_bytes = (L.spitch * (ch + 2) + 15) & ~15;
+    o += L.sc_bytes;
+    L.off_work = o;
+    o += (gw * ch * 2 + 15) & ~15;
+    L.off_mask = o;
+    L.mask_words = ncell * ch * 4;                   // [lo|ini][cell][row][2] u32
+    o += L.mask_words * 4;
+    L.off_xinfo = o;
+    o += (gw + 15) & ~15;
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { lo1[k] = min(d[k], d[(k + 1) & 15]); hi1[k] = max(d[k], d[(k + 1) & 15]); }
-    int lo2[16], hi2[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { lo2[k] = min(lo1[k], lo1[(k + 2) & 15]); hi2[k] = max(hi1[k], hi1[(k + 2) & 15]); }
-    int lo4[16], hi4[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { lo4[k] = min(lo2[k], lo2[(k + 4) & 15]); hi4[k] = max(hi2[k], hi2[(k + 4) & 15]); }
-    // max over arcs of (-hi9) == -(min over arcs of hi9).  NB: the direct form max(best, max(lo9, -hi9)) is
-    // MISCOMPILED by nvcc 12.9 for sm_100a (the negation is dropped when the chain is fused into 3-input VIMNMX;
-    // reproduced in isolation on a B200, see DESIGN.md "toolchain notes"), so the negation is hoisted out of the chain.
-    int maxlo = -256, minhi = 256;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        maxlo = max(maxlo, min(lo4[k], d[(k + 8) & 15]));     // lo4[k] covers k..k+7
-        minhi = min(minhi, max(hi4[k], d[(k + 8) & 15]));
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
     }
-    return max(0, max(maxlo, -minhi));
+    return v;
 }
 
 __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restrict__ plan, Workspace ws) {
-    extern __shared__ uint8_t smem[];
-    __shared__ int s_warp[kFastThreads / 32];
-    __shared__ int s_ini_count;
-    __shared__ int s_running;
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_nwork;
 
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int b = blockIdx.y;
-    int cell = blockIdx.x;
-    // locate the level of this cell
-    int l = 0;
+    int gid = blockIdx.x, l = 0;
     const int nl = plan->nlevels;
-    while (l + 1 < nl && cell >= plan->lv[l + 1].cell_base) ++l;
-    const LevelGeom g = plan->lv[l];
-    cell -= g.cell_base;
-    const int ci = cell / g.ncols, cj = cell - ci * g.ncols;
+    while (l + 1 < nl && gid >= plan->lv[l + 1].grp_base) ++l;
+    const LevelGeom& g = plan->lv[l];
+    gid -= g.grp_base;
+    const int ngrp = g.ngrp, wcell = g.wcell, hcell = g.hcell, ncols = g.ncols;
+    const int ci = gid / ngrp, gj = gid - ci * ngrp;
+    const int cj0 = gj * g.gcells, ncell = min(g.gcells, ncols - cj0);
 
-    // detection region of the cell in level coordinates
-    const int x0 = kEdge + cj * g.wcell, y0 = kEdge + ci * g.hcell;
-    const int x1 = min(x0 + g.wcell, g.w - kEdge), y1 = min(y0 + g.hcell, g.h - kEdge);
-    const int cw = x1 - x0, ch = y1 - y0;
-    int* count_out = ws.cell_count + (size_t)b * plan->ncells_total + g.cell_base + cell;
-    if (cw <= 0 || ch <= 0) {
-        if (threadIdx.x == 0) *count_out = 0;
+    // detection region of the strip in level coordinates
+    const int x0 = kEdge + cj0 * wcell, y0 = kEdge + ci * hcell;
+    const int x1 = min(x0 + ncell * wcell, g.w - kEdge), y1 = min(y0 + hcell, g.h - kEdge);
+    const int gw = x1 - x0, ch = y1 - y0;
+    const int cell0 = g.cell_base + ci * ncols + cj0;
+    int* count_out = ws.cell_count + (size_t)b * plan->ncells_total + cell0;
+    if (gw <= 0 || ch <= 0) {
+        if (tid < ncell) count_out[tid] = 0;
         return;
     }
-    const int tw = cw + 6, th_ = ch + 6;            // staged tile incl. 3-px ring halo
-    const int tpitch = (tw + 3) & ~3;
-    const int spitch = cw + 2;                      // score tile with a 1-px zero margin
+    const FastLayout L = fast_layout(gw, ch, ncell);
+    const int tpitch = L.tpitch, spitch = L.spitch;
     uint8_t* tile = smem;
-    uint8_t* sc = smem + ((tpitch * th_ + 15) & ~15);
-    uint8_t* sv = sc + (((cw + 2) * (ch + 2) + 15) & ~15);   // survivor scores (0 = not a survivor)
+    uint8_t* sc = smem + L.off_sc;
+    uint16_t* work = reinterpret_cast<uint16_t*>(smem + L.off_work);
+    uint32_t* mask = reinterpret_cast<uint32_t*>(smem + L.off_mask);      // lo masks, then ini masks
+    uint8_t* xinfo = smem + L.off_xinfo;
 
+    // ---- phase 0: stage the strip --------------------------------------------------------------------------------
+    const int pitch = g.pitch;
     const uint8_t* img = ws.pyr + (size_t)b * plan->pyr_bytes + g.img_off;
-    // level (x,y) lives at padded (x+19, y+19)
-    const uint8_t* src = img + (size_t)(y0 - 3 + kEdge) * g.pitch + (x0 - 3 + kEdge);
-    for (int i = threadIdx.x; i < tw * th_; i += kFastThreads) {
-        int ty = i / tw, tx = i - ty * tw;
-        tile[ty * tpitch + tx] = src[(size_t)ty * g.pitch + tx];
-    }
-    for (int i = threadIdx.x; i < (cw + 2) * (ch + 2); i += kFastThreads) sc[i] = 0;
-    if (threadIdx.x == 0) { s_ini_count = 0; s_running = 0; }
-    __syncthreads();
-
-    const int lo_th = min(plan->ini_th, plan->min_th);
-    const int npix = cw * ch;
-    for (int p = threadIdx.x; p < npix; p += kFastThreads) {
-        const int py = p / cw, px = p - py * cw;
-        const uint8_t* c = tile + (py + 3) * tpitch + (px + 3);
-        const int cv = c[0];
-        // exact necessary condition: every 9-arc contains k or k+8 for each k
-        const int d0 = c[3 * tpitch] - cv, d8 = c[-3 * tpitch] - cv;
-        const int d4 = c[3] - cv, d12 = c[-3] - cv;
-        bool br = (d0 > lo_th || d8 > lo_th) && (d4 > lo_th || d12 > lo_th);
-        bool dk = (d0 < -lo_th || d8 < -lo_th) && (d4 < -lo_th || d12 < -lo_th);
-        int score = 0;
-        if (br || dk) {
-            int d[16];
-            d[0] = d0; d[4] = d4; d[8] = d8; d[12] = d12;
-            d[1] = c[3 * tpitch + 1] - cv;  d[2] = c[2 * tpitch + 2] - cv;  d[3] = c[tpitch + 3] - cv;
-            d[5] = c[-tpitch + 3] - cv;     d[6] = c[-2 * tpitch + 2] - cv; d[7] = c[-3 * tpitch + 1] - cv;
-            d[9] = c[-3 * tpitch - 1] - cv; d[10] = c[-2 * tpitch - 2] - cv; d[11] = c[-tpitch - 3] - cv;
-            d[13] = c[tpitch - 3] - cv;     d[14] = c[2 * tpitch - 2] - cv; d[15] = c[3 * tpitch - 1] - cv;
-            const int m = fast_m_from_ring(d);
-            if (m > lo_th) score = m - 1;
+    const int sx = x0 - 3 + kEdge, sy = y0 - 3 + kEdge;          // level (x,y) lives at padded (x+19, y+19)
+    const int shift = sx & 3;
+    const int twords = (shift + gw + 6 + 3) >> 2;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(img + (size_t)sy * pitch + (sx - shift));
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tile);
+        const int pw = pitch >> 2, tw = tpitch >> 2;
+        for (int r = wid; r < ch + 6; r += kFastWarps)
+            for (int wx = lane; wx < twords; wx += 32) dst[r * tw + wx] = __ldg(src + (size_t)r * pw + wx);
+        uint4* z = reinterpret_cast<uint4*>(sc);
+        for (int i = tid; i < (L.sc_bytes >> 4); i += kFastThreads) z[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < L.mask_words; i += kFastThreads) mask[i] = 0u;
+        for (int x = tid; x < gw; x += kFastThreads) {
+            const int cj = x / wcell;
+            const int cx0 = cj * wcell, cx1 = min(cx0 + wcell, gw);
+            xinfo[x] = (uint8_t)(cj | (x == cx0 ? 64 : 0) | (x == cx1 - 1 ? 128 : 0));
         }
-        sc[(py + 1) * spitch + (px + 1)] = (uint8_t)score;
+        if (tid == 0) s_nwork = 0;
     }
     __syncthreads();
 
-    // strict 8-neighbour NMS inside the cell
-    int my_ini = 0;
-    for (int p = threadIdx.x; p < npix; p += kFastThreads) {
-        const int py = p / cw, px = p - py * cw;
-        const uint8_t* q = sc + (py + 1) * spitch + (px + 1);
-        const int s = q[0];
-        int keep = 0;
-        if (s > 0) {
-            int nb = max(max(max(q[-spitch - 1], q[-spitch]), max(q[-spitch + 1], q[-1])),
-                         max(max(q[1], q[spitch - 1]), max(q[spitch], q[spitch + 1])));
-            keep = s > nb;
+    const int ini_th = plan->ini_th, lo_th = min(plan->ini_th, plan->min_th);
+    const uint8_t* t0 = tile + 3 * tpitch + shift + 3;            // strip pixel (0,0)
+
+    // ---- phase 1: compass pretest -> work list --------------------------------------------------------------------
+    for (int py = wid; py < ch; py += kFastWarps) {
+        const uint8_t* rowc = t0 + py * tpitch;
+        for (int xb = 0; xb < gw; xb += 32) {
+            const int px = xb + lane;
+            bool pass = false;
+            if (px < gw) {
+                const uint8_t* c = rowc + px;
+                const int cv = c[0], i0 = c[3 * tpitch], i8 = c[-3 * tpitch], i4 = c[3], i12 = c[-3];
+                const int e = min(max(i0, i8), max(i4, i12));
+                const int f = max(min(i0, i8), min(i4, i12));
+                pass = max(e - cv, cv - f) > lo_th;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_nwork, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pass) work[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((py << 8) | px);
+            }
         }
-        sv[p] = keep ? (uint8_t)s : 0;
-        my_ini += (keep && s >= plan->ini_th);
     }
-    my_ini = __reduce_add_sync(0xffffffffu, my_ini);
-    if ((threadIdx.x & 31) == 0 && my_ini) atomicAdd(&s_ini_count, my_ini);
     __syncthreads();
-    const int emit_th = s_ini_count > 0 ? plan->ini_th : plan->min_th;
+    const int nwork = s_nwork;
 
-    // ordered (y,x) compaction into the cell's slots
-    uint32_t* slots = ws.slots + (size_t)b * plan->slots_total + g.slot_base + (size_t)cell * g.cell_cap;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int base = 0; base < npix; base += kFastThreads) {
-        const int p = base + threadIdx.x;
-        int s = 0;
-        if (p < npix) s = sv[p];
-        const bool flag = s >= emit_th && s > 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, flag);
-        if (lane == 0) s_warp[wid] = __popc(bal);
-        __syncthreads();
-        int before = 0, total = 0;
+    // ---- phase 2: exact score of the listed pixels -----------------------------------------------------------------
+    for (int i = tid; i < nwork; i += kFastThreads) {
+        const int e = work[i];
+        const int px = e & 255, py = e >> 8;
+        const uint8_t* c = t0 + py * tpitch + px;
+        const unsigned cv = c[0];
+        // v = {I - c + 256 (low half), c - I + 256 (high half)}: both halves in [1, 511], no carry between them
+        const unsigned K = (256u - cv) + ((cv + 256u) << 16);
+        unsigned v[16];
+#define FBE_RING(k, dy, dx) v[k] = (unsigned)c[(dy) * tpitch + (dx)] * 0xFFFF0001u + K
+        FBE_RING(0, 3, 0);   FBE_RING(1, 3, 1);    FBE_RING(2, 2, 2);    FBE_RING(3, 1, 3);
+        FBE_RING(4, 0, 3);   FBE_RING(5, -1, 3);   FBE_RING(6, -2, 2);   FBE_RING(7, -3, 1);
+        FBE_RING(8, -3, 0);  FBE_RING(9, -3, -1);  FBE_RING(10, -2, -2); FBE_RING(11, -1, -3);
+        FBE_RING(12, 0, -3); FBE_RING(13, 1, -3);  FBE_RING(14, 2, -2);  FBE_RING(15, 3, -1);
+#undef FBE_RING
+        unsigned m3[16];
 #pragma unroll
-        for (int w = 0; w < kFastThreads / 32; ++w) {
-            int c = s_warp[w];
-            if (w < wid) before += c;
-            total += c;
+        for (int k = 0; k < 16; ++k) m3[k] = __vimin3_s16x2(v[k], v[(k + 1) & 15], v[(k + 2) & 15]);
+        unsigned M = 0u;                                          // halves are >= 1
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+            const unsigned a = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+            const unsigned bq = __vimin3_s16x2(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
+            M = __vimax3_s16x2(M, a, bq);
         }
-        const int run = s_running;
-        if (flag) {
-            const int py = p / cw, px = p - py * cw;
-            slots[run + before + __popc(bal & ((1u << lane) - 1))] = pack_key(x0 + px, y0 + py, s);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) s_running = run + total;
-        // s_running is re-read only after the next __syncthreads in the following iteration
+        const int m = max((int)(M & 0xFFFFu), (int)(M >> 16)) - 256;
+        if (m > lo_th) sc[(py + 1) * spitch + px + 1] = (uint8_t)(m - 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) *count_out = s_running;
+
+    // ---- phase 3: strict 8-neighbour NMS inside the cell -> row masks -----------------------------------------------
+    uint32_t* mask_ini = mask + ncell * ch * 2;
+    for (int i = tid; i < nwork; i += kFastThreads) {
+        const int e = work[i];
+        const int px = e & 255, py = e >> 8;
+        const uint8_t* q = sc + (py + 1) * spitch + px + 1;
+        const int s = q[0];
+        if (s > 0) {
+            const int xi = xinfo[px];
+            int nb = max((int)q[-spitch], (int)q[spitch]);
+            if (!(xi & 64)) nb = max(nb, max(max((int)q[-spitch - 1], (int)q[-1]), (int)q[spitch - 1]));
+            if (!(xi & 128)) nb = max(nb, max(max((int)q[-spitch + 1], (int)q[1]), (int)q[spitch + 1]));
+            if (s > nb) {
+                const int cj = xi & 63;
+                const int xin = px - cj * wcell;
+                const int w = (cj * ch + py) * 2 + (xin >> 5);
+                const unsigned bit = 1u << (xin & 31);
+                atomicOr(&mask[w], bit);
+                if (s >= ini_th) atomicOr(&mask_ini[w], bit);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 4: ordered emission, one warp per cell ---------------------------------------------------------------
+    for (int cj = wid; cj < ncell; cj += kFastWarps) {
+        const uint32_t* ml = mask + cj * ch * 2;
+        const uint32_t* mi = mask_ini + cj * ch * 2;
+        const int r0 = lane, r1 = lane + 32;
+        unsigned long long a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+        if (r0 < ch) { a0 = ml[r0 * 2] | ((unsigned long long)ml[r0 * 2 + 1] << 32); b0 = mi[r0 * 2] | ((unsigned long long)mi[r0 * 2 + 1] << 32); }
+        if (r1 < ch) { a1 = ml[r1 * 2] | ((unsigned long long)ml[r1 * 2 + 1] << 32); b1 = mi[r1 * 2] | ((unsigned long long)mi[r1 * 2 + 1] << 32); }
+        if (__any_sync(0xffffffffu, (b0 | b1) != 0ull)) { a0 = b0; a1 = b1; }
+        const int c0 = __popcll(a0), c1 = __popcll(a1);
+        const int s0 = warp_incl_scan(c0, lane), s1 = warp_incl_scan(c1, lane);
+        const int tot0 = __shfl_sync(0xffffffffu, s0, 31), tot1 = __shfl_sync(0xffffffffu, s1, 31);
+        int o0 = s0 - c0, o1 = tot0 + s1 - c1;
+        uint32_t* slots = ws.slots + (size_t)b * plan->slots_total + g.slot_base + (size_t)(ci * ncols + cj0 + cj) * g.cell_cap;
+        const int cx = cj * wcell;
+        while (a0) {
+            const int x = __ffsll((long long)a0) - 1;
+            a0 &= a0 - 1;
+            slots[o0++] = pack_key(x0 + cx + x, y0 + r0, sc[(r0 + 1) * spitch + cx + x + 1]);
+        }
+        while (a1) {
+            const int x = __ffsll((long long)a1) - 1;
+            a1 &= a1 - 1;
+            slots[o1++] = pack_key(x0 + cx + x, y0 + r1, sc[(r1 + 1) * spitch + cx + x + 1]);
+        }
+        if (lane == 0) count_out[cj] = tot0 + tot1;
+    }
 }
 
 int launch_fast_cells(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st) {
-    const int tw = hp.max_cell_w + 6, th = hp.max_cell_h + 6;
-    const int tpitch = (tw + 3) & ~3;
-    size_t smem = ((tpitch * th + 15) & ~15) + (((hp.max_cell_w + 2) * (hp.max_cell_h + 2) + 15) & ~15) +
-                  ((hp.max_cell_w * hp.max_cell_h + 15) & ~15);
-    if (smem > 200 * 1024) { set_error("FAST cell too large for shared memory"); return FBE_E_UNSUPPORTED; }
+    size_t smem = 0;
+    for (int l = 0; l < hp.nlevels; ++l) {
+        const LevelGeom& g = hp.lv[l];
+        smem = std::max(smem, (size_t)fast_layout(g.gcells * g.wcell, g.hcell, g.gcells).total);
+    }
+    if (smem > 200 * 1024) { set_error("FAST strip too large for shared memory"); return FBE_E_UNSUPPORTED; }
     if (smem > 48 * 1024) FBE_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(hp.ncells_total, nimg);
+    dim3 grid(hp.ngroups_total, nimg);
     k_fast_cells<<<grid, kFastThreads, smem, st>>>(dp, ws);
     count_launch();
     FBE_CUDA(cudaGetLastError());

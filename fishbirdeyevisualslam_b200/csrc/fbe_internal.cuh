@@ -14,6 +14,7 @@ constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE (:73)
 constexpr int kPatch = 31;       // PATCH_SIZE (:72)
 constexpr int kMaxDim = 4095;    // x,y packed in 12 bits each
 constexpr int kMaxGridCells = 64 * 48;
+constexpr int kFastGroupW = 256; // widest run of FAST cells (pixels) one CTA of the FAST kernel owns
 
 // packed candidate / key: score[31:24] | y[23:12] | x[11:0], level pixel coordinates
 __host__ __device__ inline uint32_t pack_key(int x, int y, int s) { return ((uint32_t)s << 24) | ((uint32_t)y << 12) | (uint32_t)x; }
@@ -31,6 +32,9 @@ struct LevelGeom {
     int wcell, hcell;
     int cell_base;       // first cell of this level in the per-slot cell arrays
     int cell_cap;        // candidate slots per cell = ceil(wcell/2)*ceil(hcell/2) (NMS survivors are never adjacent)
+    int gcells;          // FAST kernel: cells per CTA group (consecutive cells of one cell row, group width <= 256 px)
+    int ngrp;            // groups per cell row
+    int grp_base;        // first group of this level in the per-image group numbering
     int slot_base;       // first slot (u32 units) of this level in the per-slot slot array
     int key_cap;         // capacity of the compacted key array of this level ( = ncells*cell_cap )
     int nfeat;           // mnFeaturesPerLevel[level]
@@ -50,6 +54,7 @@ struct Plan {
     int rows, cols;
     int ini_th, min_th;
     int ncells_total;
+    int ngroups_total;   // FAST CTAs per image
     int slots_total;
     int kp_cap_total;
     int nodes_total;

@@ -82,7 +82,7 @@ int build_plan(const fbe_extractor_cfg& cfg, const std::vector<float>& scale, co
     for (int v = 0; v < 16; ++v) p.umax[v] = umax[v];
     if (rows > kMaxDim || cols > kMaxDim) { set_error("image larger than 4095 px per side"); return FBE_E_UNSUPPORTED; }
     tabs.clear();
-    int img_off = 0, cell_base = 0, slot_base = 0, node_base = 0, kp_base = 0;
+    int img_off = 0, cell_base = 0, slot_base = 0, node_base = 0, kp_base = 0, grp_base = 0;
     p.max_cell_w = p.max_cell_h = 0;
     for (int l = 0; l < cfg.nlevels; ++l) {
         LevelGeom& g = p.lv[l];
@@ -116,6 +116,11 @@ int build_plan(const fbe_extractor_cfg& cfg, const std::vector<float>& scale, co
         g.slot_base = slot_base;
         g.key_cap = ncols * nrows * g.cell_cap;
         cell_base += ncols * nrows;
+        if (g.wcell > 64 || g.hcell > 64) { set_error("FAST cell larger than 64 px (cannot happen for 30-px cells)"); return FBE_E_UNSUPPORTED; }
+        g.gcells = std::max(1, std::min(ncols, kFastGroupW / g.wcell));
+        g.ngrp = (ncols + g.gcells - 1) / g.gcells;
+        g.grp_base = grp_base;
+        grp_base += g.ngrp * nrows;
         slot_base += g.key_cap;
         p.max_cell_w = std::max(p.max_cell_w, g.wcell);
         p.max_cell_h = std::max(p.max_cell_h, g.hcell);
@@ -155,6 +160,7 @@ int build_plan(const fbe_extractor_cfg& cfg, const std::vector<float>& scale, co
     }
     p.pyr_bytes = img_off;
     p.ncells_total = cell_base;
+    p.ngroups_total = grp_base;
     p.slots_total = slot_base;
     p.nodes_total = node_base;
     p.kp_cap_total = kp_base;
