@@ -34,16 +34,19 @@ namespace fbe {
 constexpr int kFastThreads = 256;
 constexpr int kFastWarps = kFastThreads / 32;
 
-struct FastLayout { int tpitch, spitch, off_sc, sc_bytes, off_work, off_mask, mask_words, off_xinfo, total; };
+constexpr int kTilePitch = ((kFastGroupW + 3) & ~3) + 16;   // staged strip: column t holds strip x = t - 4
+constexpr int kScorePitch = kFastGroupW + 8;                // score tile: column t holds strip x = t - 1 (zero margin)
+constexpr int kTileW = kTilePitch / 4;                      // in 32-bit words
 
-// shared-memory carve-up for a strip of gw x ch pixels covering ncell cells
+struct FastLayout { int off_sc, sc_bytes, off_work, off_mask, mask_words, off_xinfo, total; };
+
+// shared-memory carve-up for a strip of gw x ch pixels covering ncell cells (pitches are compile-time constants so
+// that every ring / neighbour access is a base register + immediate)
 __host__ __device__ inline FastLayout fast_layout(int gw, int ch, int ncell) {
     FastLayout L;
-    L.tpitch = (gw + 6 + 3 + 3) & ~3;                // up to 3 bytes of alignment shift in front of the halo
-    L.spitch = (gw + 2 + 3) & ~3;                    // score tile with a 1-px zero margin
-    int o = (L.tpitch * (ch + 6) + 15) & ~15;
+    int o = kTilePitch * (ch + 6);
     L.off_sc = o;
-    L.sc_bytes = (L.spitch * (ch + 2) + 15) & ~15;
+    L.sc_bytes = (kScorePitch * (ch + 2) + 15) & ~15;
     o += L.sc_bytes;
     L.off_work = o;
     o += (gw * ch * 2 + 15) & ~15;
@@ -63,6 +66,15 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
         if (lane >= o) v += t;
     }
     return v;
+}
+
+// compass pretest of two pixels held as u16x2 lanes; returns bit 15 / bit 31 set for the lanes that pass
+__device__ __forceinline__ unsigned pretest_pair(unsigned c, unsigned i0, unsigned i8, unsigned i4, unsigned i12, unsigned k2) {
+    const unsigned e = __vminu2(__vmaxu2(i0, i8), __vmaxu2(i4, i12));     // bright: e - c > t
+    const unsigned f = __vmaxu2(__vminu2(i0, i8), __vminu2(i4, i12));     // dark:   c - f > t
+    const unsigned d1 = e + 0x01000100u - c;                               // halves in [1, 511]: no borrow between lanes
+    const unsigned d2 = c + 0x01000100u - f;
+    return (__vmaxu2(d1, d2) + k2) & 0x80008000u;                          // lane > 256 + t  <=>  bit 15 of lane + k set
 }
 
 __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restrict__ plan, Workspace ws) {
@@ -91,25 +103,28 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restr
         return;
     }
     const FastLayout L = fast_layout(gw, ch, ncell);
-    const int tpitch = L.tpitch, spitch = L.spitch;
     uint8_t* tile = smem;
+    uint32_t* tile32 = reinterpret_cast<uint32_t*>(smem);
     uint8_t* sc = smem + L.off_sc;
     uint16_t* work = reinterpret_cast<uint16_t*>(smem + L.off_work);
     uint32_t* mask = reinterpret_cast<uint32_t*>(smem + L.off_mask);      // lo masks, then ini masks
     uint8_t* xinfo = smem + L.off_xinfo;
+    const int nquad = (gw + 3) >> 2;
 
-    // ---- phase 0: stage the strip --------------------------------------------------------------------------------
-    const int pitch = g.pitch;
-    const uint8_t* img = ws.pyr + (size_t)b * plan->pyr_bytes + g.img_off;
-    const int sx = x0 - 3 + kEdge, sy = y0 - 3 + kEdge;          // level (x,y) lives at padded (x+19, y+19)
-    const int shift = sx & 3;
-    const int twords = (shift + gw + 6 + 3) >> 2;
+    // ---- phase 0: stage the strip, realigned so that strip x = 0 sits on a 32-bit boundary ------------------------
     {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(img + (size_t)sy * pitch + (sx - shift));
-        uint32_t* dst = reinterpret_cast<uint32_t*>(tile);
-        const int pw = pitch >> 2, tw = tpitch >> 2;
-        for (int r = wid; r < ch + 6; r += kFastWarps)
-            for (int wx = lane; wx < twords; wx += 32) dst[r * tw + wx] = __ldg(src + (size_t)r * pw + wx);
+        const int pitch = g.pitch;
+        const uint8_t* img = ws.pyr + (size_t)b * plan->pyr_bytes + g.img_off;
+        const int a = x0 + kEdge - 4;                               // padded column of tile column 0
+        const int sh = (a & 3) * 8;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(img + (size_t)(y0 - 3 + kEdge) * pitch + (a & ~3));
+        const int pw = pitch >> 2;
+        const int twords = nquad + 3;                               // tile columns 0 .. 4*nquad + 11
+        for (int r = wid; r < ch + 6; r += kFastWarps) {
+            const uint32_t* srow = src + (size_t)r * pw;
+            for (int wx = lane; wx < twords; wx += 32)
+                tile32[r * kTileW + wx] = __funnelshift_r(__ldg(srow + wx), __ldg(srow + wx + 1), sh);
+        }
         uint4* z = reinterpret_cast<uint4*>(sc);
         for (int i = tid; i < (L.sc_bytes >> 4); i += kFastThreads) z[i] = make_uint4(0, 0, 0, 0);
         for (int i = tid; i < L.mask_words; i += kFastThreads) mask[i] = 0u;
@@ -123,27 +138,45 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restr
     __syncthreads();
 
     const int ini_th = plan->ini_th, lo_th = min(plan->ini_th, plan->min_th);
-    const uint8_t* t0 = tile + 3 * tpitch + shift + 3;            // strip pixel (0,0)
 
-    // ---- phase 1: compass pretest -> work list --------------------------------------------------------------------
-    for (int py = wid; py < ch; py += kFastWarps) {
-        const uint8_t* rowc = t0 + py * tpitch;
-        for (int xb = 0; xb < gw; xb += 32) {
-            const int px = xb + lane;
-            bool pass = false;
-            if (px < gw) {
-                const uint8_t* c = rowc + px;
-                const int cv = c[0], i0 = c[3 * tpitch], i8 = c[-3 * tpitch], i4 = c[3], i12 = c[-3];
-                const int e = min(max(i0, i8), max(i4, i12));
-                const int f = max(min(i0, i8), min(i4, i12));
-                pass = max(e - cv, cv - f) > lo_th;
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, pass);
-            if (bal) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_nwork, __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (pass) work[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((py << 8) | px);
+    // ---- phase 1: compass pretest, 4 pixels per thread (u16x2 SIMD) -> work list -----------------------------------
+    {
+        const unsigned k2 = (unsigned)(0x8000 - 257 - lo_th) * 0x00010001u;
+        const unsigned ltmask = (1u << lane) - 1u;
+        for (int py = wid; py < ch; py += kFastWarps) {
+            const uint32_t* rc = tile32 + (py + 3) * kTileW + 1;     // word of strip x = 0 in the centre row
+            for (int qb = 0; qb < nquad; qb += 32) {
+                const int xq = qb + lane;
+                unsigned p0 = 0, p1 = 0;                             // pass bits of pixels (0,1) and (2,3)
+                if (xq < nquad) {
+                    const unsigned cw = rc[xq], cl = rc[xq - 1], cr = rc[xq + 1];
+                    const unsigned up = rc[xq - 3 * kTileW], dn = rc[xq + 3 * kTileW];
+                    const unsigned lf = __funnelshift_r(cl, cw, 8);   // x-3 .. x
+                    const unsigned rt = __funnelshift_r(cw, cr, 24);  // x+3 .. x+6
+                    p0 = pretest_pair(__byte_perm(cw, 0, 0x4140), __byte_perm(dn, 0, 0x4140), __byte_perm(up, 0, 0x4140),
+                                      __byte_perm(rt, 0, 0x4140), __byte_perm(lf, 0, 0x4140), k2);
+                    p1 = pretest_pair(__byte_perm(cw, 0, 0x4342), __byte_perm(dn, 0, 0x4342), __byte_perm(up, 0, 0x4342),
+                                      __byte_perm(rt, 0, 0x4342), __byte_perm(lf, 0, 0x4342), k2);
+                    const int rem = gw - 4 * xq;                     // pixels of this quad inside the strip (tail quad)
+                    if (rem < 4) {
+                        if (rem < 2) p0 &= 0x8000u;
+                        if (rem < 3) p1 = 0;
+                        else p1 &= 0x8000u;
+                    }
+                }
+                const unsigned b0 = __ballot_sync(0xffffffffu, p0 & 0x8000u), b1 = __ballot_sync(0xffffffffu, p0 >> 31);
+                const unsigned b2 = __ballot_sync(0xffffffffu, p1 & 0x8000u), b3 = __ballot_sync(0xffffffffu, p1 >> 31);
+                if (b0 | b1 | b2 | b3) {
+                    const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_nwork, n0 + n1 + n2 + n3);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const unsigned ent = (unsigned)((py << 8) | (4 * xq));
+                    if (p0 & 0x8000u) work[base + __popc(b0 & ltmask)] = (uint16_t)ent;
+                    if (p0 >> 31) work[base + n0 + __popc(b1 & ltmask)] = (uint16_t)(ent + 1);
+                    if (p1 & 0x8000u) work[base + n0 + n1 + __popc(b2 & ltmask)] = (uint16_t)(ent + 2);
+                    if (p1 >> 31) work[base + n0 + n1 + n2 + __popc(b3 & ltmask)] = (uint16_t)(ent + 3);
+                }
             }
         }
     }
@@ -154,12 +187,12 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restr
     for (int i = tid; i < nwork; i += kFastThreads) {
         const int e = work[i];
         const int px = e & 255, py = e >> 8;
-        const uint8_t* c = t0 + py * tpitch + px;
+        const uint8_t* c = tile + (py + 3) * kTilePitch + px + 4;
         const unsigned cv = c[0];
         // v = {I - c + 256 (low half), c - I + 256 (high half)}: both halves in [1, 511], no carry between them
         const unsigned K = (256u - cv) + ((cv + 256u) << 16);
         unsigned v[16];
-#define FBE_RING(k, dy, dx) v[k] = (unsigned)c[(dy) * tpitch + (dx)] * 0xFFFF0001u + K
+#define FBE_RING(k, dy, dx) v[k] = (unsigned)c[(dy) * kTilePitch + (dx)] * 0xFFFF0001u + K
         FBE_RING(0, 3, 0);   FBE_RING(1, 3, 1);    FBE_RING(2, 2, 2);    FBE_RING(3, 1, 3);
         FBE_RING(4, 0, 3);   FBE_RING(5, -1, 3);   FBE_RING(6, -2, 2);   FBE_RING(7, -3, 1);
         FBE_RING(8, -3, 0);  FBE_RING(9, -3, -1);  FBE_RING(10, -2, -2); FBE_RING(11, -1, -3);
@@ -176,7 +209,7 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restr
             M = __vimax3_s16x2(M, a, bq);
         }
         const int m = max((int)(M & 0xFFFFu), (int)(M >> 16)) - 256;
-        if (m > lo_th) sc[(py + 1) * spitch + px + 1] = (uint8_t)(m - 1);
+        if (m > lo_th) sc[(py + 1) * kScorePitch + px + 1] = (uint8_t)(m - 1);
     }
     __syncthreads();
 
@@ -185,13 +218,13 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restr
     for (int i = tid; i < nwork; i += kFastThreads) {
         const int e = work[i];
         const int px = e & 255, py = e >> 8;
-        const uint8_t* q = sc + (py + 1) * spitch + px + 1;
+        const uint8_t* q = sc + (py + 1) * kScorePitch + px + 1;
         const int s = q[0];
         if (s > 0) {
             const int xi = xinfo[px];
-            int nb = max((int)q[-spitch], (int)q[spitch]);
-            if (!(xi & 64)) nb = max(nb, max(max((int)q[-spitch - 1], (int)q[-1]), (int)q[spitch - 1]));
-            if (!(xi & 128)) nb = max(nb, max(max((int)q[-spitch + 1], (int)q[1]), (int)q[spitch + 1]));
+            int nb = max((int)q[-kScorePitch], (int)q[kScorePitch]);
+            if (!(xi & 64)) nb = max(nb, max(max((int)q[-kScorePitch - 1], (int)q[-1]), (int)q[kScorePitch - 1]));
+            if (!(xi & 128)) nb = max(nb, max(max((int)q[-kScorePitch + 1], (int)q[1]), (int)q[kScorePitch + 1]));
             if (s > nb) {
                 const int cj = xi & 63;
                 const int xin = px - cj * wcell;
@@ -222,12 +255,12 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restr
         while (a0) {
             const int x = __ffsll((long long)a0) - 1;
             a0 &= a0 - 1;
-            slots[o0++] = pack_key(x0 + cx + x, y0 + r0, sc[(r0 + 1) * spitch + cx + x + 1]);
+            slots[o0++] = pack_key(x0 + cx + x, y0 + r0, sc[(r0 + 1) * kScorePitch + cx + x + 1]);
         }
         while (a1) {
             const int x = __ffsll((long long)a1) - 1;
             a1 &= a1 - 1;
-            slots[o1++] = pack_key(x0 + cx + x, y0 + r1, sc[(r1 + 1) * spitch + cx + x + 1]);
+            slots[o1++] = pack_key(x0 + cx + x, y0 + r1, sc[(r1 + 1) * kScorePitch + cx + x + 1]);
         }
         if (lane == 0) count_out[cj] = tot0 + tot1;
     }
