@@ -1,66 +1,103 @@
-// GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) of every pyramid level (src/ORBextractor.cc:1085-1086).
+// GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) of every pyramid level (src/ORBextractor.cc:1085-1086), all levels of
+// all images of the batch in ONE launch.
 // OpenCV >= 3.4.2 evaluates this 8-bit case exactly: integer kernel [18,34,48,56,48,34,18]/256 per axis, no
 // intermediate rounding, out = (sum_y sum_x k_y k_x p + 32768) >> 16 (pinned against cv2 4.13).
 // The reference blurs a clone of the un-padded level with REFLECT_101 at its edge; our padded level already
 // carries that reflection in its 19-px frame, so the stencil reads the padded buffer without edge cases.
-// One CTA = 64x16 output tile; the 70x22 input tile is staged in shared memory, the horizontal pass leaves a
-// 64x22 u16 intermediate in shared memory, the vertical pass writes 4 bytes per thread.
+//
+// One CTA = 128x32 output tile in PADDED coordinates (so every global store is an aligned 32-bit word; the few frame
+// bytes a word may cover are never read by anyone).
+//   * TMA stages the 160x38 input box into shared memory (3-px halo; the box starts 16 px left of the tile because a
+//     TMA box must start on a 16-byte boundary of the innermost dimension -- an unaligned start faults with 'illegal
+//     instruction' on B200, see tools/probe/tma_probe2.cu).
+//   * horizontal pass, u16x2 SIMD: a row sum is <= 255*256 < 2^16, so two pixels share one 32-bit IMAD; the byte pairs
+//     come from PRMT/SHF on three aligned words.  4 outputs per thread task -> one 64-bit shared store.
+//   * vertical pass, 32-bit: a thread owns 4 columns x 4 rows, keeps its 10 input rows in registers, and writes one
+//     aligned word per row (a warp writes 128 contiguous bytes).
 #include "fbe_internal.cuh"
+#include "tma.cuh"
 
 namespace fbe {
 
-constexpr int kBlurTW = 64, kBlurTH = 16;
+constexpr int kBlurRawW = kBlurTW + 32, kBlurRawH = kBlurTH + 6;     // 160 x 38 staged bytes
+constexpr int kBlurRawWords = kBlurRawW / 4;
 
-__global__ void __launch_bounds__(256) k_blur(const Plan* __restrict__ plan, Workspace ws, int level) {
-    __shared__ __align__(16) uint8_t tile[(kBlurTH + 6) * 72];
-    __shared__ __align__(16) uint16_t hsum[(kBlurTH + 6) * kBlurTW];
-    const LevelGeom g = plan->lv[level];
-    const int b = blockIdx.z;
-    const int x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH;     // level coordinates of the tile
-    const uint8_t* img = ws.pyr + (size_t)b * plan->pyr_bytes + g.img_off;
-    uint8_t* out = ws.blur + (size_t)b * plan->pyr_bytes + g.img_off;
-    // stage rows y0-3 .. y0+TH+2, cols x0-3 .. x0+TW+2 (padded coords: +19); clamp reads to the padded extent
-    const int pw = g.w + 2 * kEdge;
-    for (int i = threadIdx.x; i < (kBlurTH + 6) * 70; i += 256) {
-        const int ty = i / 70, tx = i - ty * 70;
-        const int py = min(y0 - 3 + ty + kEdge, g.ph - 1), px = min(x0 - 3 + tx + kEdge, pw - 1);
-        tile[ty * 72 + tx] = img[(size_t)py * g.pitch + px];
+__device__ __forceinline__ unsigned blur_hpair(unsigned a, unsigned b, unsigned c, unsigned d, unsigned e, unsigned f, unsigned g) {
+    return 18u * (a + g) + 34u * (b + f) + 48u * (c + e) + 56u * d;
+}
+
+__global__ void __launch_bounds__(256) k_blur(const Plan* __restrict__ plan, Workspace ws, const __grid_constant__ TmaMaps maps) {
+    __shared__ __align__(128) uint32_t raw[kBlurRawH * kBlurRawWords];
+    __shared__ __align__(16) uint32_t hs[kBlurRawH * (kBlurTW / 2)];      // u16x2: row sums of two adjacent pixels
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    int t = blockIdx.x, l = 0;
+    const int nl = plan->nlevels;
+    while (l + 1 < nl && t >= plan->lv[l + 1].blur_base) ++l;
+    const LevelGeom& g = plan->lv[l];
+    t -= g.blur_base;
+    const int ty = t / g.blur_ntx, tx = t - ty * g.blur_ntx;
+    const int px0 = tx * kBlurTW;                    // padded column of the tile's first output
+    const int y0 = ty * kBlurTH;                     // level row of the tile's first output
+
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, kBlurRawH * kBlurRawW);
+        tma_load_3d(raw, &maps.m[l], &bar, px0 - 16, y0 + kEdge - 3, ws.slot0 + b);
+    }
+    mbar_wait(&bar, 0);
+
+    // ---- horizontal pass: task = (row, quad of 4 output columns) ---------------------------------------------------
+    for (int k = tid; k < kBlurRawH * (kBlurTW / 4); k += 256) {
+        const int row = k >> 5, q = k & 31;
+        const uint32_t* w = raw + row * kBlurRawWords + q + 3;  // w[0] = columns 4q-4 .. 4q-1 relative to the tile's outputs
+        const unsigned w0 = w[0], w1 = w[1], w2 = w[2];
+        // p0..p11 = bytes of w0,w1,w2; outputs 0,1 use taps p1..p7 / p2..p8, outputs 2,3 use p3..p9 / p4..p10
+        const unsigned s1 = __funnelshift_r(w0, w1, 8), s2 = __funnelshift_r(w1, w2, 8);   // p1..p4, p5..p8
+        const unsigned O0 = __byte_perm(s1, 0, 0x4140), O1 = __byte_perm(s1, 0, 0x4342);   // (p1,p2) (p3,p4)
+        const unsigned O2 = __byte_perm(s2, 0, 0x4140), O3 = __byte_perm(s2, 0, 0x4342);   // (p5,p6) (p7,p8)
+        const unsigned O4 = __byte_perm(w2, 0, 0x4241);                                   // (p9,p10)
+        const unsigned E1 = __byte_perm(w0, 0, 0x4342), E2 = __byte_perm(w1, 0, 0x4140);   // (p2,p3) (p4,p5)
+        const unsigned E3 = __byte_perm(w1, 0, 0x4342), E4 = __byte_perm(w2, 0, 0x4140);   // (p6,p7) (p8,p9)
+        uint2 o;
+        o.x = blur_hpair(O0, E1, O1, E2, O2, E3, O3);
+        o.y = blur_hpair(O1, E2, O2, E3, O3, E4, O4);
+        *reinterpret_cast<uint2*>(hs + row * (kBlurTW / 2) + 2 * q) = o;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < (kBlurTH + 6) * kBlurTW; i += 256) {
-        const int ty = i / kBlurTW, tx = i - ty * kBlurTW;
-        const uint8_t* p = tile + ty * 72 + tx;
-        hsum[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-    }
-    __syncthreads();
-    // 64x16 outputs, 4 per thread (one aligned-in-tile 32-bit store)
-    const int tx4 = (threadIdx.x & 15) * 4, ty = threadIdx.x >> 4;
-    const int y = y0 + ty;
-    if (y >= g.h) return;
-    uint32_t v = 0;
+
+    // ---- vertical pass: 4 columns x 4 rows per thread ----------------------------------------------------------------
+    const int cg = tid & 31, band = tid >> 5;
+    unsigned h[10][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint16_t* q = hsum + ty * kBlurTW + tx4 + i;
-        const uint32_t a = 18u * (q[0] + q[6 * kBlurTW]) + 34u * (q[kBlurTW] + q[5 * kBlurTW]) +
-                           48u * (q[2 * kBlurTW] + q[4 * kBlurTW]) + 56u * q[3 * kBlurTW];
-        v |= ((a + 32768u) >> 16) << (8 * i);
+    for (int r = 0; r < 10; ++r) {
+        const uint2 v = *reinterpret_cast<const uint2*>(hs + (band * 4 + r) * (kBlurTW / 2) + 2 * cg);
+        h[r][0] = v.x & 0xFFFFu; h[r][1] = v.x >> 16; h[r][2] = v.y & 0xFFFFu; h[r][3] = v.y >> 16;
     }
-    uint8_t* dst = out + (size_t)(y + kEdge) * g.pitch + (x0 + tx4 + kEdge);
-    const int x = x0 + tx4;
-    if (x + 3 < g.w) {
-        dst[0] = (uint8_t)v; dst[1] = (uint8_t)(v >> 8); dst[2] = (uint8_t)(v >> 16); dst[3] = (uint8_t)(v >> 24);
-    } else {
-        for (int i = 0; i < 4 && x + i < g.w; ++i) dst[i] = (uint8_t)(v >> (8 * i));
+    const int pcol = px0 + 4 * cg;
+    if (pcol >= g.pitch) return;
+    uint8_t* out = ws.blur + (size_t)b * plan->pyr_bytes + g.img_off + pcol;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int y = y0 + band * 4 + r;
+        if (y >= g.h) break;
+        unsigned a[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            a[c] = 18u * (h[r][c] + h[r + 6][c]) + 34u * (h[r + 1][c] + h[r + 5][c]) + 48u * (h[r + 2][c] + h[r + 4][c]) +
+                   56u * h[r + 3][c] + 32768u;
+        // byte 2 of every sum is the result (sum < 2^24)
+        const unsigned lo = __byte_perm(a[0], a[1], 0x0062), hi = __byte_perm(a[2], a[3], 0x0062);
+        *reinterpret_cast<uint32_t*>(out + (size_t)(y + kEdge) * g.pitch) = __byte_perm(lo, hi, 0x5410);
     }
 }
 
-int launch_blur(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st) {
-    for (int l = 0; l < hp.nlevels; ++l) {
-        const LevelGeom& g = hp.lv[l];
-        dim3 grid((g.w + kBlurTW - 1) / kBlurTW, (g.h + kBlurTH - 1) / kBlurTH, nimg);
-        k_blur<<<grid, 256, 0, st>>>(dp, ws, l);
-        count_launch();
-    }
+int launch_blur(const Plan& hp, const Plan* dp, const Workspace& ws, const TmaMaps& maps, int nimg, cudaStream_t st) {
+    dim3 grid(hp.blur_tiles_total, nimg);
+    k_blur<<<grid, 256, 0, st>>>(dp, ws, maps);
+    count_launch();
     FBE_CUDA(cudaGetLastError());
     return FBE_OK;
 }

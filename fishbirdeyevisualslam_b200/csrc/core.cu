@@ -2,9 +2,11 @@
 //   level0/resize x (L-1)  ->  FAST cells  ->  octree  ->  [blur on a 2nd stream]  ->  orient+describe  ->  grid
 // for a batch of equally sized images.  No host round trip inside the sequence.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include "fbe_internal.cuh"
+#include "tma.cuh"
 
 namespace fbe {
 
@@ -41,6 +43,7 @@ int ExtractorCore::free_ws() {
     cudaFree(ws.key_node); cudaFree(ws.oct_scratch); cudaFree(ws.sel); cudaFree(ws.level_n); cudaFree(ws.out_kps);
     cudaFree(ws.out_desc); cudaFree(ws.out_n); cudaFree(ws.out_cell); cudaFree(ws.grid_start); cudaFree(ws.grid_items);
     cudaFree(ws.status); cudaFree(dplan); cudaFree(dtab);
+    delete blur_maps; blur_maps = nullptr;
     std::memset(&ws, 0, sizeof(ws));
     dplan = nullptr; dtab = nullptr; have_ws = false;
     return FBE_OK;
@@ -96,6 +99,13 @@ int ExtractorCore::ensure_plan(int rows, int cols) {
     if (!tabs.empty()) FBE_CUDA(cudaMemcpy(dtab, tabs.data(), tabs.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
     FBE_CUDA(cudaMalloc(&ws.pyr, B * hplan.pyr_bytes));
     FBE_CUDA(cudaMalloc(&ws.blur, B * hplan.pyr_bytes));
+    blur_maps = new TmaMaps();
+    std::memset(blur_maps, 0, sizeof(TmaMaps));
+    for (int l = 0; l < hplan.nlevels; ++l) {
+        const LevelGeom& g = hplan.lv[l];
+        rc = tma_encode_level(&blur_maps->m[l], ws.pyr + g.img_off, g.pitch, g.ph, (int)B, (size_t)hplan.pyr_bytes, kBlurTW + 32, kBlurTH + 6);
+        if (rc != FBE_OK) return rc;
+    }
     FBE_CUDA(cudaMemset(ws.blur, 0, B * hplan.pyr_bytes));
     FBE_CUDA(cudaMalloc(&ws.cell_count, B * hplan.ncells_total * sizeof(int)));
     FBE_CUDA(cudaMalloc(&ws.slots, B * hplan.slots_total * sizeof(uint32_t)));
@@ -121,6 +131,7 @@ int ExtractorCore::ensure_plan(int rows, int cols) {
 
 Workspace ExtractorCore::slot_view(int slot0) const {
     Workspace v = ws;
+    v.slot0 = slot0;
     const size_t s = (size_t)slot0;
     const int gcells = hplan.grid_cols * hplan.grid_rows;
     v.pyr += s * hplan.pyr_bytes; v.blur += s * hplan.pyr_bytes;
@@ -148,26 +159,42 @@ int ExtractorCore::run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, in
         tcount = std::min(tcount + 1, kTimingRing);
     }
 #define FBE_MARK(i, st) do { if (te) FBE_CUDA(cudaEventRecord(te[i], st)); } while (0)
+    // FBE_SYNC_DEBUG=1: synchronise after every stage so that a device fault is attributed to the stage that raised it
+    static const bool sync_debug = std::getenv("FBE_SYNC_DEBUG") != nullptr;
+#define FBE_STAGE(name, st)                                                                              \
+    do {                                                                                                 \
+        if (sync_debug) {                                                                                \
+            cudaError_t _e = cudaStreamSynchronize(st);                                                  \
+            if (_e != cudaSuccess) { set_error(std::string("stage ") + name + ": " + cudaGetErrorString(_e)); return FBE_E_CUDA; } \
+        }                                                                                                \
+    } while (0)
     FBE_MARK(0, stream);
     if ((rc = launch_pyramid(hplan, dplan, v, dtab, nimg, stream)) != FBE_OK) return rc;
     FBE_MARK(1, stream);
+    FBE_STAGE("pyramid", stream);
     // blur depends only on the pyramid: run it on the side stream while FAST + octree proceed
     FBE_CUDA(cudaEventRecord(ev_pyr, stream));
     FBE_CUDA(cudaStreamWaitEvent(stream2, ev_pyr, 0));
     FBE_MARK(6, stream2);
-    if ((rc = launch_blur(hplan, dplan, v, nimg, stream2)) != FBE_OK) return rc;
+    if ((rc = launch_blur(hplan, dplan, v, *blur_maps, nimg, stream2)) != FBE_OK) return rc;
     FBE_MARK(7, stream2);
+    FBE_STAGE("blur", stream2);
     FBE_CUDA(cudaEventRecord(ev_blur, stream2));
     if ((rc = launch_fast_cells(hplan, dplan, v, nimg, stream)) != FBE_OK) return rc;
     FBE_MARK(2, stream);
+    FBE_STAGE("fast", stream);
     if ((rc = launch_octree(hplan, dplan, v, nimg, stream)) != FBE_OK) return rc;
     FBE_MARK(3, stream);
+    FBE_STAGE("octree", stream);
     FBE_CUDA(cudaStreamWaitEvent(stream, ev_blur, 0));
     FBE_MARK(8, stream);
     if ((rc = launch_describe(hplan, dplan, v, nimg, stream)) != FBE_OK) return rc;
     FBE_MARK(4, stream);
+    FBE_STAGE("describe", stream);
     if ((rc = launch_grid(hplan, dplan, v, nimg, stream)) != FBE_OK) return rc;
     FBE_MARK(5, stream);
+    FBE_STAGE("grid", stream);
+#undef FBE_STAGE
 #undef FBE_MARK
     last_nimg = nimg;
     return FBE_OK;

@@ -14,6 +14,7 @@ constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE (:73)
 constexpr int kPatch = 31;       // PATCH_SIZE (:72)
 constexpr int kMaxDim = 4095;    // x,y packed in 12 bits each
 constexpr int kMaxGridCells = 64 * 48;
+constexpr int kBlurTW = 128, kBlurTH = 32;   // blur output tile
 constexpr int kFastGroupW = 256; // widest run of FAST cells (pixels) one CTA of the FAST kernel owns
 
 // packed candidate / key: score[31:24] | y[23:12] | x[11:0], level pixel coordinates
@@ -35,6 +36,7 @@ struct LevelGeom {
     int gcells;          // FAST kernel: cells per CTA group (consecutive cells of one cell row, group width <= 256 px)
     int ngrp;            // groups per cell row
     int grp_base;        // first group of this level in the per-image group numbering
+    int blur_ntx, blur_nty, blur_base;   // blur kernel: 128x32 output tiles in padded coordinates
     int slot_base;       // first slot (u32 units) of this level in the per-slot slot array
     int key_cap;         // capacity of the compacted key array of this level ( = ncells*cell_cap )
     int nfeat;           // mnFeaturesPerLevel[level]
@@ -55,6 +57,7 @@ struct Plan {
     int ini_th, min_th;
     int ncells_total;
     int ngroups_total;   // FAST CTAs per image
+    int blur_tiles_total;
     int slots_total;
     int kp_cap_total;
     int nodes_total;
@@ -69,6 +72,7 @@ struct Plan {
 
 // Per-call device workspace pointers (all arrays are [max_batch] slabs, slot-major).
 struct Workspace {
+    int slot0;             // first batch slot of this view (TMA z coordinate = slot0 + image index)
     const uint8_t* in;     // [B][rows][in_pitch] source images
     int in_pitch, in_slot_stride;
     uint8_t* pyr;          // [B][pyr_bytes]
@@ -110,7 +114,8 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
 int launch_pyramid(const Plan& hp, const Plan* dp, const Workspace& ws, const ResizeTab* d_tab, int nimg, cudaStream_t st);
 int launch_fast_cells(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
 int launch_octree(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
-int launch_blur(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
+struct TmaMaps;
+int launch_blur(const Plan& hp, const Plan* dp, const Workspace& ws, const TmaMaps& maps, int nimg, cudaStream_t st);
 int launch_describe(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
 int launch_grid(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
 size_t octree_scratch_bytes(const Plan& hp);
@@ -133,6 +138,7 @@ struct ExtractorCore {
     Plan hplan;            // valid when plan_rows/cols set
     Plan* dplan = nullptr;
     ResizeTab* dtab = nullptr;
+    TmaMaps* blur_maps = nullptr;   // host copy of the per-level tensor maps over ws.pyr (passed by value at launch)
     int plan_rows = 0, plan_cols = 0;
     Workspace ws;
     uint8_t* d_in = nullptr;      // staging for host-API calls

@@ -82,7 +82,7 @@ int build_plan(const fbe_extractor_cfg& cfg, const std::vector<float>& scale, co
     for (int v = 0; v < 16; ++v) p.umax[v] = umax[v];
     if (rows > kMaxDim || cols > kMaxDim) { set_error("image larger than 4095 px per side"); return FBE_E_UNSUPPORTED; }
     tabs.clear();
-    int img_off = 0, cell_base = 0, slot_base = 0, node_base = 0, kp_base = 0, grp_base = 0;
+    int img_off = 0, cell_base = 0, slot_base = 0, node_base = 0, kp_base = 0, grp_base = 0, blur_base = 0;
     p.max_cell_w = p.max_cell_h = 0;
     for (int l = 0; l < cfg.nlevels; ++l) {
         LevelGeom& g = p.lv[l];
@@ -121,6 +121,10 @@ int build_plan(const fbe_extractor_cfg& cfg, const std::vector<float>& scale, co
         g.ngrp = (ncols + g.gcells - 1) / g.gcells;
         g.grp_base = grp_base;
         grp_base += g.ngrp * nrows;
+        g.blur_ntx = (kEdge + g.w + kBlurTW - 1) / kBlurTW;
+        g.blur_nty = (g.h + kBlurTH - 1) / kBlurTH;
+        g.blur_base = blur_base;
+        blur_base += g.blur_ntx * g.blur_nty;
         slot_base += g.key_cap;
         p.max_cell_w = std::max(p.max_cell_w, g.wcell);
         p.max_cell_h = std::max(p.max_cell_h, g.hcell);
@@ -161,6 +165,7 @@ int build_plan(const fbe_extractor_cfg& cfg, const std::vector<float>& scale, co
     p.pyr_bytes = img_off;
     p.ncells_total = cell_base;
     p.ngroups_total = grp_base;
+    p.blur_tiles_total = blur_base;
     p.slots_total = slot_base;
     p.nodes_total = node_base;
     p.kp_cap_total = kp_base;
