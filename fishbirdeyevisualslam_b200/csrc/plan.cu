@@ -144,6 +144,7 @@ int build_plan(const fbe_extractor_cfg& cfg, const std::vector<float>& scale, co
         // bilinear tables over PADDED destination coordinates (frame pixels map through REFLECT_101)
         if (l > 0) {
             const LevelGeom& s = p.lv[l - 1];
+            while (tabs.size() & 3) tabs.push_back(ResizeTab{0, 0, 0});     // the resize kernel reads 4 column entries as 2 x 16 bytes
             g.tabx_off = (int)tabs.size();
             for (int x = 0; x < g.pitch; ++x) {
                 int xi = reflect101(std::min(x, g.w + 2 * kEdge - 1) - kEdge, g.w);

@@ -37,32 +37,62 @@ __global__ void __launch_bounds__(256) k_level0(const Plan* __restrict__ plan, W
     *reinterpret_cast<uint32_t*>(dst + (size_t)y * g.pitch + x4) = v;
 }
 
+// One CTA = 128 output columns x 64 output rows of one padded level; a thread owns 4 adjacent columns and walks 8 rows.
+// The column coefficients (source offset + two 11-bit weights) stay in registers for the whole walk; the horizontal
+// interpolation of a source row is kept and reused when the next output row needs it again (scale 1.2: consecutive
+// output rows share one of their two source rows most of the time).  Source bytes come through L1/L2 (each source
+// pixel is read by ~1.4 threads); stores are aligned 32-bit words, 128 contiguous bytes per warp.
+constexpr int kRsRowsPerWarp = 8, kRsWarps = 8;
+
 __global__ void __launch_bounds__(256) k_resize(const Plan* __restrict__ plan, Workspace ws,
                                                 const ResizeTab* __restrict__ tab, int level) {
-    const LevelGeom g = plan->lv[level];
-    const LevelGeom s = plan->lv[level - 1];
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y;
+    const LevelGeom& g = plan->lv[level];
+    const LevelGeom& s = plan->lv[level - 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int x4 = (blockIdx.x * 32 + lane) * 4;
     const int b = blockIdx.z;
-    if (x4 >= g.pitch) return;
+    const int pitch = g.pitch, spitch = s.pitch, ph = g.ph;
+    if (x4 >= pitch) return;
     const uint8_t* src = ws.pyr + (size_t)b * plan->pyr_bytes + s.img_off;
-    const ResizeTab ty = tab[g.taby_off + y];
-    const uint8_t* S0 = src + (size_t)ty.ofs * s.pitch;
-    const uint8_t* S1 = S0 + s.pitch;       // row sy+1 exists in the padded source (frame), weight 0 when clamped
-    const int b0 = ty.a0, b1 = ty.a1;
-    uint32_t out = 0;
+    uint8_t* dst = ws.pyr + (size_t)b * plan->pyr_bytes + g.img_off + x4;
+    // 4 column entries = 32 bytes, 32-byte aligned
+    const uint4* tx4 = reinterpret_cast<const uint4*>(tab + g.tabx_off + x4);
+    const uint4 ta = __ldg(tx4), tb = __ldg(tx4 + 1);
+    const int ofs[4] = {(int)ta.x, (int)ta.z, (int)tb.x, (int)tb.z};
+    const int a0[4] = {(int)(short)(ta.y & 0xFFFFu), (int)(short)(ta.w & 0xFFFFu), (int)(short)(tb.y & 0xFFFFu), (int)(short)(tb.w & 0xFFFFu)};
+    const int a1[4] = {(int)ta.y >> 16, (int)ta.w >> 16, (int)tb.y >> 16, (int)tb.w >> 16};
+    const ResizeTab* ty = tab + g.taby_off;
+    int y = blockIdx.y * (kRsRowsPerWarp * kRsWarps) + wid * kRsRowsPerWarp;
+    const int yend = min(y + kRsRowsPerWarp, ph);
+    int cur = -4;                 // source row whose interpolation sits in r_lo (r_hi holds cur + 1)
+    int r_lo[4], r_hi[4];
+    auto hrow = [&](int sy, int (&r)[4]) {
+        const uint8_t* S = src + (size_t)sy * spitch;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const ResizeTab tx = tab[g.tabx_off + x4 + i];
-        const int a0 = tx.a0, a1 = tx.a1;
-        const int r0 = S0[tx.ofs] * a0 + S0[tx.ofs + 1] * a1;
-        const int r1 = S1[tx.ofs] * a0 + S1[tx.ofs + 1] * a1;
-        int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-        v = min(max(v, 0), 255);
-        out |= (uint32_t)v << (8 * i);
+        for (int i = 0; i < 4; ++i) r[i] = ((int)S[ofs[i]] * a0[i] + (int)S[ofs[i] + 1] * a1[i]) >> 4;
+    };
+    for (; y < yend; ++y) {
+        const ResizeTab t = ty[y];
+        const int sy = t.ofs;
+        if (sy == cur + 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r_lo[i] = r_hi[i];
+            hrow(sy + 1, r_hi);      // row sy+1 exists in the padded source (frame), weight 0 when clamped
+        } else if (sy != cur) {
+            hrow(sy, r_lo);
+            hrow(sy + 1, r_hi);
+        }
+        cur = sy;
+        const int b0 = t.a0, b1 = t.a1;
+        uint32_t out = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int v = (((b0 * r_lo[i]) >> 16) + ((b1 * r_hi[i]) >> 16) + 2) >> 2;
+            v = min(max(v, 0), 255);
+            out |= (uint32_t)v << (8 * i);
+        }
+        *reinterpret_cast<uint32_t*>(dst + (size_t)y * pitch) = out;
     }
-    uint8_t* dst = ws.pyr + (size_t)b * plan->pyr_bytes + g.img_off;
-    *reinterpret_cast<uint32_t*>(dst + (size_t)y * g.pitch + x4) = out;
 }
 
 int launch_pyramid(const Plan& hp, const Plan* dp, const Workspace& ws, const ResizeTab* d_tab, int nimg, cudaStream_t st) {
@@ -73,7 +103,10 @@ int launch_pyramid(const Plan& hp, const Plan* dp, const Workspace& ws, const Re
         if (g.pitch / 4 > 128) block.x = 256;
         dim3 grid((g.pitch / 4 + block.x - 1) / block.x, g.ph, nimg);
         if (l == 0) k_level0<<<grid, block, 0, st>>>(dp, ws);
-        else k_resize<<<grid, block, 0, st>>>(dp, ws, d_tab, l);
+        else {
+            dim3 rgrid((g.pitch / 4 + 31) / 32, (g.ph + kRsRowsPerWarp * kRsWarps - 1) / (kRsRowsPerWarp * kRsWarps), nimg);
+            k_resize<<<rgrid, 256, 0, st>>>(dp, ws, d_tab, l);
+        }
         count_launch();
     }
     FBE_CUDA(cudaGetLastError());
