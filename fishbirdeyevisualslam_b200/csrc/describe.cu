@@ -1,13 +1,16 @@
 // Orientation (IC_Angle, src/ORBextractor.cc:77-104), rotated BRIEF-256 (computeOrbDescriptor :108-147) and the
 // operator() epilogue (:1059-1104: octave/size fix-up :837-847, pt *= scale for level > 0, level concatenation).
-// One warp per keypoint:
-//   * moments: lane v+15 sums row v of the radius-15 disc of the UNBLURRED level (int32, exact), warp-reduced;
-//     angle = fastAtan2(m01, m10) -- OpenCV's 7th-order polynomial, evaluated with explicit round-to-nearest fp32
-//     mul/add/div (no FMA contraction) in the reference's operation order.
-//   * descriptor: lane = output byte; 16 rotated samples of the BLURRED level each.  The rotation uses
-//     a = cos, b = sin of angle*(float)(CV_PI/180.f) rounded from double (the reference calls float cos/sin from
-//     libm, which are correctly rounded for all but a ~1e-3 fraction of arguments) and
-//     cvRound(x*b + y*a), cvRound(x*a - y*b) as __float2int_rn of un-contracted fp32 products.
+// One CTA = 32 keypoints, 8 warps x 4 keypoints:
+//   A. moments: lanes are COLUMNS u = -15..15 of the radius-15 disc of the UNBLURRED level and the warp walks the 31 rows,
+//      so every load is one coalesced 31-byte row segment (int32 sums, exact); warp-reduced;
+//      angle = fastAtan2(m01, m10) -- OpenCV's 7th-order polynomial, evaluated with explicit round-to-nearest fp32
+//      mul/add/div (no FMA contraction) in the reference's operation order.
+//   B. a = cos, b = sin of angle*(float)(CV_PI/180.f), computed in double and rounded (the reference calls float cos/sin
+//      from libm, which are correctly rounded for all but a ~1e-3 fraction of arguments): ONE THREAD per keypoint, so the
+//      fp64 pipe sees 1/32 of the warp-instructions a warp-per-keypoint evaluation would issue.
+//   C. descriptor: the warp stages the 37x37 patch of the BLURRED level into shared memory with aligned 32-bit loads
+//      (pattern radius 13 -> rotated reach <= 18), then lane = output byte, 16 rotated samples each, read from shared memory;
+//      cvRound(x*b + y*a), cvRound(x*a - y*b) as __float2int_rn of un-contracted fp32 products.
 #include "fbe_internal.cuh"
 
 namespace fbe {
@@ -16,7 +19,8 @@ __constant__ int8_t c_pattern[256 * 4] = {
 #include "orb_pattern.inc"
 };
 
-constexpr int kDescWarps = 8;
+constexpr int kDescWarps = 8, kDescPerWarp = 4, kDescPerCta = kDescWarps * kDescPerWarp;
+constexpr int kPatchR = 18, kPatchRows = 2 * kPatchR + 1, kPatchWords = 11;      // 37 rows x 44 bytes
 
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     const float s = (float)(180.0 / 3.14159265358979323846);
@@ -39,76 +43,141 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
+// row half-widths of the radius-15 disc (umax, src/ORBextractor.cc:452-469; HALF_PATCH_SIZE is a compile-time constant)
+constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+template <int V> struct UmaxOf { static constexpr int value = kUmax[V < 0 ? -V : V]; };
+
 __global__ void __launch_bounds__(kDescWarps * 32) k_describe(const Plan* __restrict__ plan, Workspace ws) {
-    __shared__ int8_t s_pat[1024];
-    for (int i = threadIdx.x; i < 1024; i += kDescWarps * 32) s_pat[i] = c_pattern[i];
-    __syncthreads();
+    __shared__ float4 s_pat[256];                                       // [j][lane]: pair lane*8 + j as (x0, y0, x1, y1)
+    __shared__ uint32_t s_patch[kDescWarps][kPatchRows * kPatchWords];
+    __shared__ uint32_t s_key[kDescPerCta];
+    __shared__ int s_lvl[kDescPerCta];
+    __shared__ float s_angle[kDescPerCta], s_cos[kDescPerCta], s_sin[kDescPerCta];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int b = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const int gidx = blockIdx.x * kDescWarps + (threadIdx.x >> 5);     // output keypoint index within the image
-    // level of this output index: levels are concatenated 0..L-1 in order
     const int* level_n = ws.level_n + (size_t)b * FBE_MAX_LEVELS;
-    int l = 0, off = 0, total = 0;
     const int nl = plan->nlevels;
+    int total = 0;
     for (int i = 0; i < nl; ++i) total += level_n[i];
-    if (blockIdx.x == 0 && threadIdx.x == 0) ws.out_n[b] = total;
-    if (gidx >= total) return;
-    while (gidx >= off + level_n[l]) { off += level_n[l]; ++l; }
-    const LevelGeom g = plan->lv[l];
-    const uint32_t key = ws.sel[(size_t)b * plan->kp_cap_total + g.kp_base + (gidx - off)];
-    const int kx = key_x(key), ky = key_y(key);
-
-    // ---- IC_Angle on the unblurred level ---------------------------------------------------------------------
-    const uint8_t* img = ws.pyr + (size_t)b * plan->pyr_bytes + g.img_off;
-    const uint8_t* c = img + (size_t)(ky + kEdge) * g.pitch + (kx + kEdge);
-    int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int v = lane - 15;
-        const int d = plan->umax[v < 0 ? -v : v];
-        const uint8_t* row = c + (ptrdiff_t)v * g.pitch;
-        int rs = 0, ws_ = 0;
-        for (int u = -d; u <= d; ++u) { const int p = row[u]; rs += p; ws_ += u * p; }
-        m10 = ws_;
-        m01 = v * rs;
+    if (blockIdx.x == 0 && tid == 0) ws.out_n[b] = total;
+    const int g0 = blockIdx.x * kDescPerCta;
+    if (g0 >= total) return;
+    {
+        const int p = (tid & 31) * 8 + (tid >> 5);                       // s_pat[tid] = pair p
+        s_pat[tid] = make_float4((float)c_pattern[4 * p], (float)c_pattern[4 * p + 1], (float)c_pattern[4 * p + 2], (float)c_pattern[4 * p + 3]);
     }
-    m10 = __reduce_add_sync(0xffffffffu, m10);
-    m01 = __reduce_add_sync(0xffffffffu, m01);
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // ---- rotated BRIEF on the blurred level ------------------------------------------------------------------
-    const float factorPI = (float)(3.14159265358979323846 / 180.0);    // (float)(CV_PI/180.f)
-    const float ang = __fmul_rn(angle, factorPI);
-    const float a = (float)cos((double)ang), bb = (float)sin((double)ang);
-    const uint8_t* bimg = ws.blur + (size_t)b * plan->pyr_bytes + g.img_off;
-    const uint8_t* bc = bimg + (size_t)(ky + kEdge) * g.pitch + (kx + kEdge);
-    unsigned val = 0;
+    // ---- A: IC_Angle on the unblurred level ---------------------------------------------------------------------
+#pragma unroll 1
+    for (int k = 0; k < kDescPerWarp; ++k) {
+        const int slot = wid * kDescPerWarp + k, gidx = g0 + slot;
+        if (gidx >= total) break;
+        int l = 0, off = 0;
+        while (gidx >= off + level_n[l]) { off += level_n[l]; ++l; }
+        const LevelGeom& g = plan->lv[l];
+        const uint32_t key = ws.sel[(size_t)b * plan->kp_cap_total + g.kp_base + (gidx - off)];
+        const int kx = key_x(key), ky = key_y(key), pitch = g.pitch;
+        const uint8_t* c = ws.pyr + (size_t)b * plan->pyr_bytes + g.img_off + (size_t)(ky + kEdge) * pitch + (kx + kEdge);
+        const int u = lane - 15, au = u < 0 ? -u : u;
+        int m10 = 0, m01 = 0;
+        if (lane < 31) {
+            int colsum = 0;
+            const uint8_t* p = c + u - 15 * pitch;                 // walks down the column; one 64-bit add per row
+#define FBE_ROW(V)                                   \
+    if (au <= UmaxOf<V>::value) {                    \
+        const int q = *p;                            \
+        colsum += q;                                 \
+        m01 += (V) * q;                              \
+    }                                                \
+    p += pitch;
+            FBE_ROW(-15) FBE_ROW(-14) FBE_ROW(-13) FBE_ROW(-12) FBE_ROW(-11) FBE_ROW(-10) FBE_ROW(-9) FBE_ROW(-8)
+            FBE_ROW(-7) FBE_ROW(-6) FBE_ROW(-5) FBE_ROW(-4) FBE_ROW(-3) FBE_ROW(-2) FBE_ROW(-1) FBE_ROW(0)
+            FBE_ROW(1) FBE_ROW(2) FBE_ROW(3) FBE_ROW(4) FBE_ROW(5) FBE_ROW(6) FBE_ROW(7) FBE_ROW(8)
+            FBE_ROW(9) FBE_ROW(10) FBE_ROW(11) FBE_ROW(12) FBE_ROW(13) FBE_ROW(14) FBE_ROW(15)
+#undef FBE_ROW
+            m10 = u * colsum;
+        }
+        m10 = __reduce_add_sync(0xffffffffu, m10);
+        m01 = __reduce_add_sync(0xffffffffu, m01);
+        if (lane == 0) {
+            s_angle[slot] = fast_atan2_deg((float)m01, (float)m10);
+            s_key[slot] = key;
+            s_lvl[slot] = l;
+        }
+    }
+    __syncthreads();
+
+    // ---- B: rotation, one thread per keypoint ----------------------------------------------------------------------
+    if (tid < kDescPerCta && g0 + tid < total) {
+        const float factorPI = (float)(3.14159265358979323846 / 180.0);    // (float)(CV_PI/180.f)
+        const float ang = __fmul_rn(s_angle[tid], factorPI);
+        s_cos[tid] = (float)cos((double)ang);
+        s_sin[tid] = (float)sin((double)ang);
+    }
+    __syncthreads();
+
+    // ---- C: rotated BRIEF on the blurred level ---------------------------------------------------------------------
+    uint32_t* patch = s_patch[wid];
+    const uint8_t* patch8 = reinterpret_cast<const uint8_t*>(patch);
+#pragma unroll 1
+    for (int k = 0; k < kDescPerWarp; ++k) {
+        const int slot = wid * kDescPerWarp + k, gidx = g0 + slot;
+        if (gidx >= total) break;
+        const uint32_t key = s_key[slot];
+        const int l = s_lvl[slot];
+        const LevelGeom& g = plan->lv[l];
+        const int kx = key_x(key), ky = key_y(key), pitch = g.pitch;
+        const int pcol = kx + kEdge - kPatchR;                    // padded column of the patch's left edge
+        const int shift = pcol & 3;
+        const uint8_t* src = ws.blur + (size_t)b * plan->pyr_bytes + g.img_off + (size_t)(ky + kEdge - kPatchR) * pitch + (pcol - shift);
+        __syncwarp();
+        {   // 8 rows per pass: lane = (row in pass, word quarter); words wq, wq+4, wq+8 of the 11-word row
+            const int r8 = lane >> 2, wq = lane & 3;
+            const uint32_t* sp = reinterpret_cast<const uint32_t*>(src + (size_t)r8 * pitch) + wq;
+            uint32_t* dp = patch + r8 * kPatchWords + wq;
+            const int pw8 = pitch * 2;                               // 8 rows in 32-bit words
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int8_t* p = s_pat + (lane * 8 + j) * 4;
-        const float x0 = (float)p[0], y0 = (float)p[1], x1 = (float)p[2], y1 = (float)p[3];
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, bb), __fmul_rn(y0, a)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, bb)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, bb), __fmul_rn(y1, a)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, bb)));
-        const int t0 = bc[(ptrdiff_t)r0 * g.pitch + c0], t1 = bc[(ptrdiff_t)r1 * g.pitch + c1];
-        val |= (unsigned)(t0 < t1) << j;
-    }
-    uint8_t* desc = ws.out_desc + ((size_t)b * plan->kp_cap_total + gidx) * 32;
-    desc[lane] = (uint8_t)val;
+            for (int pass = 0; pass < 5; ++pass) {
+                if (pass * 8 + r8 < kPatchRows) {
+                    dp[0] = __ldg(sp);
+                    dp[4] = __ldg(sp + 4);
+                    if (wq < 3) dp[8] = __ldg(sp + 8);
+                }
+                sp += pw8;
+                dp += 8 * kPatchWords;
+            }
+        }
+        __syncwarp();
+        const float a = s_cos[slot], bb = s_sin[slot];
+        const uint8_t* pc = patch8 + kPatchR * (kPatchWords * 4) + kPatchR + shift;      // patch centre
+        unsigned val = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 p = s_pat[j * 32 + lane];
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(p.x, bb), __fmul_rn(p.y, a)));
+            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(p.x, a), __fmul_rn(p.y, bb)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(p.z, bb), __fmul_rn(p.w, a)));
+            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(p.z, a), __fmul_rn(p.w, bb)));
+            const int t0 = pc[r0 * (kPatchWords * 4) + c0], t1 = pc[r1 * (kPatchWords * 4) + c1];
+            val |= (unsigned)(t0 < t1) << j;
+        }
+        ws.out_desc[((size_t)b * plan->kp_cap_total + gidx) * 32 + lane] = (uint8_t)val;
 
-    // ---- keypoint record ---------------------------------------------------------------------------------------
-    if (lane == 0) {
-        fbe_keypoint kp;
-        float fx = (float)kx, fy = (float)ky;
-        if (l != 0) { fx = __fmul_rn(fx, g.scale); fy = __fmul_rn(fy, g.scale); }
-        kp.x = fx; kp.y = fy; kp.size = g.patch_size; kp.angle = angle; kp.response = (float)key_s(key);
-        kp.octave = l; kp.class_id = -1;
-        ws.out_kps[(size_t)b * plan->kp_cap_total + gidx] = kp;
+        // ---- keypoint record -----------------------------------------------------------------------------------
+        if (lane == 0) {
+            fbe_keypoint kp;
+            float fx = (float)kx, fy = (float)ky;
+            if (l != 0) { fx = __fmul_rn(fx, g.scale); fy = __fmul_rn(fy, g.scale); }
+            kp.x = fx; kp.y = fy; kp.size = g.patch_size; kp.angle = s_angle[slot]; kp.response = (float)key_s(key);
+            kp.octave = l; kp.class_id = -1;
+            ws.out_kps[(size_t)b * plan->kp_cap_total + gidx] = kp;
+        }
     }
 }
 
 int launch_describe(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st) {
-    dim3 grid((hp.kp_cap_total + kDescWarps - 1) / kDescWarps, nimg);
+    dim3 grid((hp.kp_cap_total + kDescPerCta - 1) / kDescPerCta, nimg);
     k_describe<<<grid, kDescWarps * 32, 0, st>>>(dp, ws);
     count_launch();
     FBE_CUDA(cudaGetLastError());
