@@ -34,15 +34,13 @@ __device__ __forceinline__ void top2_push(unsigned& k1, unsigned& k2, unsigned k
     if (k < k1) { k2 = k1; k1 = k; }
     else if (k < k2) k2 = k;
 }
+// two smallest keys of the warp, in every lane: two REDUX.MIN instead of five shuffle rounds.  Keys are distinct (the
+// rank field is unique) except for kNoKey, so the runner-up is the smallest key that is not the winner.
 __device__ __forceinline__ void top2_warp_merge(unsigned& k1, unsigned& k2) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned o1 = __shfl_xor_sync(0xffffffffu, k1, o), o2 = __shfl_xor_sync(0xffffffffu, k2, o);
-        // two smallest of {k1,k2,o1,o2}; keys are distinct (rank is unique) except for kNoKey
-        const unsigned lo = min(k1, o1), hi = max(k1, o1);
-        k2 = min(hi, min(k2, o2));
-        k1 = lo;
-    }
+    const unsigned w = __reduce_min_sync(0xffffffffu, k1);
+    const unsigned r = __reduce_min_sync(0xffffffffu, k1 == w ? k2 : k1);
+    k1 = w;
+    k2 = r;
 }
 
 // Warp-collective walk of the window.  fn(idx, pass, rank) is called for every lane of every chunk; `pass` lanes carry
@@ -198,44 +196,100 @@ __device__ inline void three_maxima(const int* histo, int& ind1, int& ind2, int&
     else if ((float)max3 < 0.1f * (float)max1) { ind3 = -1; }
 }
 
-// ---- sequential stage: one warp per problem replays the reference's loop over the stored rows ---------------------
-__global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
+// ---- sequential stage: one CTA per problem replays the reference's loop over the stored rows ----------------------
+// The replay itself is inherently serial (each accepted match changes what later queries may take), so its speed is
+// set by the latency of every dependent access.  All 256 threads first STAGE the problem in shared memory -- the
+// candidate rows compacted back to back (block scan of the row lengths), and for SearchForInitialization the per-target
+// state vMatchedDistance / vnMatches21 -- then warp 0 alone walks the queries with ~30-cycle shared-memory accesses
+// instead of ~600-cycle dependent global loads.  Problems whose rows exceed the shared-memory budget fall back to
+// reading the rows from global memory.
+constexpr int kResolveThreads = 256;
+
+__global__ void __launch_bounds__(kResolveThreads) k_resolve(ResolveArgs a, int row_budget, int state_in_smem) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
     __shared__ int s_hist[FBE_HISTO_LENGTH];
     __shared__ int s_ind[3];
+    __shared__ int s_warp[kResolveThreads / 32];
+    __shared__ int s_carry;
     const int b = blockIdx.x;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nq = a.nq[b], nt = a.nt[b];
     const size_t qb = (size_t)b * a.q_stride, tb = (size_t)b * a.t_stride;
     const bool init = a.mode == kResolveInit;
-    int nm = 0;
-    // state reset
-    if (init) {
-        for (int i = lane; i < nt; i += 32) { a.matched_dist[tb + i] = INT_MAX; a.match21[tb + i] = -1; }
-        for (int i = lane; i < nq; i += 32) a.matches12[qb + i] = -1;
-    } else {
-        for (int i = lane; i < nt; i += 32) a.cur_mp[tb + i] = -1;
+
+    int* s_off = reinterpret_cast<int*>(rs_smem);                       // [q_stride + 1] row starts in s_rows
+    int* s_md = s_off + a.q_stride + 1;                                 // [t_stride] (INIT, state_in_smem)
+    int* s_m21 = s_md + (state_in_smem ? a.t_stride : 0);
+    unsigned* s_rows = reinterpret_cast<unsigned*>(s_m21 + (state_in_smem ? a.t_stride : 0));
+    int* md = state_in_smem ? s_md : a.matched_dist + tb;
+    int* m21 = state_in_smem ? s_m21 : a.match21 + tb;
+
+    // ---- stage: row offsets (exclusive block scan of cnt), rows, state -----------------------------------------------
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nq; base += kResolveThreads) {
+        const int i = base + tid;
+        const int v = i < nq ? a.cnt[qb + i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        int before = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kResolveThreads / 32; ++w) { const int c = s_warp[w]; if (w < wid) before += c; tot += c; }
+        const int carry = s_carry;
+        if (i < nq) s_off[i] = carry + before + inc - v;
+        __syncthreads();
+        if (tid == 0) s_carry = carry + tot;
+        __syncthreads();
     }
-    for (int i = lane; i < nq; i += 32) a.q_bin[qb + i] = -1;
-    if (lane < FBE_HISTO_LENGTH) s_hist[lane] = 0;
-    __syncwarp();
+    const int total_rows = s_carry;
+    if (tid == 0) s_off[nq] = total_rows;
+    const bool staged = total_rows <= row_budget;
+    __syncthreads();                           // s_off[nq] visible
+    if (staged) {
+        // row lengths come from shared memory, so the global row loads of successive queries are independent
+        for (int q = wid; q < nq; q += kResolveThreads / 32) {
+            const int o = s_off[q], c = s_off[q + 1] - o;
+            if (c == 0) continue;
+            const unsigned* row = a.rows + (qb + q) * a.C;
+            for (int j = lane; j < c; j += 32) s_rows[o + j] = row[j];
+        }
+    }
+    if (init) {
+        for (int i = tid; i < nt; i += kResolveThreads) { md[i] = INT_MAX; m21[i] = -1; }
+        for (int i = tid; i < nq; i += kResolveThreads) a.matches12[qb + i] = -1;
+    } else {
+        for (int i = tid; i < nt; i += kResolveThreads) a.cur_mp[tb + i] = -1;
+    }
+    for (int i = tid; i < nq; i += kResolveThreads) a.q_hit[qb + i] = -1;
+    if (tid < FBE_HISTO_LENGTH) s_hist[tid] = 0;
+    __syncthreads();
+    if (wid != 0) return;                      // the replay is one warp; no block barrier below this line
+
+    int nm = 0;
     const int sentinel = init ? INT_MAX : 256;
     // queries without candidates are skipped 32 at a time (most keypoints are not octave-0 queries)
     for (int qbase = 0; qbase < nq; qbase += 32) {
-      const int c_lane = (qbase + lane < nq) ? a.cnt[qb + qbase + lane] : 0;
+      const int c_lane = (qbase + lane < nq) ? s_off[qbase + lane + 1] - s_off[qbase + lane] : 0;
       unsigned todo = __ballot_sync(0xffffffffu, c_lane > 0);
       while (todo) {
         const int jq = __ffs(todo) - 1;
         todo &= todo - 1;
         const int qi = qbase + jq;
         const int c = __shfl_sync(0xffffffffu, c_lane, jq);
-        const unsigned* row = a.rows + (qb + qi) * a.C;
+        const unsigned* row = staged ? (s_rows + s_off[qi]) : (a.rows + (qb + qi) * a.C);
         unsigned k1 = kNoKey, k2 = kNoKey;
         for (int j = lane; j < c; j += 32) {
             const unsigned e = row[j];
             const int idx = (int)(e >> kRowDistBits), dist = (int)(e & ((1u << kRowDistBits) - 1u));
             bool skip;
-            if (init) skip = a.matched_dist[tb + idx] <= dist;          // :445-446
-            else skip = a.taken[tb + idx] != 0 || dist >= 256;          // :88-90, :1404-1406, :210-211
+            if (init) skip = md[idx] <= dist;                              // :445-446
+            else skip = a.taken[tb + idx] != 0 || dist >= 256;            // :88-90, :1404-1406, :210-211
             if (!skip) top2_push(k1, k2, ((unsigned)dist << 20) | (unsigned)j);
         }
         top2_warp_merge(k1, k2);
@@ -261,28 +315,35 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
         if (lane == 0) {
             const int src = a.q_src ? a.q_src[qb + qi] : qi;
             if (init) {
-                const int old = a.match21[tb + bestIdx];
+                const int old = m21[bestIdx];
                 if (old >= 0) { a.matches12[qb + old] = -1; --nm; }          // steal (:464-468)
                 a.matches12[qb + qi] = bestIdx;
-                a.match21[tb + bestIdx] = qi;
-                a.matched_dist[tb + bestIdx] = bestDist;
+                m21[bestIdx] = qi;
+                md[bestIdx] = bestDist;
             } else {
                 a.cur_mp[tb + bestIdx] = src;
                 if (!a.q_has_obs || a.q_has_obs[qb + qi]) a.taken[tb + bestIdx] = 1;
             }
             ++nm;
-            if (a.check_ori && a.mode != kResolveMap) {
-                const int bin = rot_bin(a.q_kps[qb + src].angle, a.t_kps[tb + bestIdx].angle);
-                a.q_bin[qb + qi] = bin;
-                a.q_hit[qb + qi] = bestIdx;
-                s_hist[bin] += 1;
-            }
+            a.q_hit[qb + qi] = bestIdx;        // every accept is one rotHist push (:474-484), stolen or not
         }
         __syncwarp();
       }
     }
     __syncwarp();
     if (a.check_ori && a.mode != kResolveMap) {
+        // rotation histogram of all pushes, off the serial path: bins computed by the whole warp
+        for (int qi = lane; qi < nq; qi += 32) {
+            const int hit = a.q_hit[qb + qi];
+            int bin = -1;
+            if (hit >= 0) {
+                const int src = a.q_src ? a.q_src[qb + qi] : qi;
+                bin = rot_bin(a.q_kps[qb + src].angle, a.t_kps[tb + hit].angle);
+                atomicAdd(&s_hist[bin], 1);
+            }
+            a.q_bin[qb + qi] = bin;
+        }
+        __syncwarp();
         if (lane == 0) { int i1, i2, i3; three_maxima(s_hist, i1, i2, i3); s_ind[0] = i1; s_ind[1] = i2; s_ind[2] = i3; }
         __syncwarp();
         const int i1 = s_ind[0], i2 = s_ind[1], i3 = s_ind[2];
@@ -481,7 +542,17 @@ int launch_window_top2(const FrameDev& f, const QueryDev& qs, int nb, int max_nq
 }
 
 int launch_resolve(const ResolveArgs& a, int nb, cudaStream_t st) {
-    k_resolve<<<nb, 32, 0, st>>>(a);
+    // shared memory: row offsets + (INIT) per-target state + as many staged row entries as fit in the rest
+    const size_t kMax = 200 * 1024;
+    size_t fixed = (size_t)(a.q_stride + 1) * 4;
+    int state_in_smem = 0;
+    if (a.mode == kResolveInit && fixed + (size_t)a.t_stride * 8 <= kMax / 2) { state_in_smem = 1; fixed += (size_t)a.t_stride * 8; }
+    if (fixed > kMax) { set_error("resolve: too many queries for the shared-memory offsets"); return FBE_E_UNSUPPORTED; }
+    // typical rows are far below the capacity C; budget = 16 entries per query on average, capped by what is left
+    size_t budget = std::min((kMax - fixed) / 4, (size_t)a.q_stride * 16 + 1024);
+    const size_t smem = fixed + budget * 4;
+    if (smem > 48 * 1024) FBE_CUDA(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax));
+    k_resolve<<<nb, kResolveThreads, smem, st>>>(a, (int)budget, state_in_smem);
     count_launch();
     FBE_CUDA(cudaGetLastError());
     return FBE_OK;

@@ -59,6 +59,19 @@ __device__ __forceinline__ int quadrant(uint32_t key, const OctNode& nd) {
     return (x < mx ? 0 : 1) + (y < my ? 0 : 2);
 }
 
+// Walk of all keys with the (key, node) loads of 4 iterations issued before any of them is used: the arrays live in
+// global memory (a level can hold > 16k candidates) and every pass of the replay is bound by that latency.
+template <class F>
+__device__ __forceinline__ void for_keys(const uint32_t* __restrict__ keys, const uint32_t* knode, int nk, F&& f) {
+    int k = threadIdx.x;
+    for (; k + 3 * kOctThreads < nk; k += 4 * kOctThreads) {
+        const uint32_t a0 = keys[k], a1 = keys[k + kOctThreads], a2 = keys[k + 2 * kOctThreads], a3 = keys[k + 3 * kOctThreads];
+        const uint32_t n0 = knode[k], n1 = knode[k + kOctThreads], n2 = knode[k + 2 * kOctThreads], n3 = knode[k + 3 * kOctThreads];
+        f(k, a0, n0); f(k + kOctThreads, a1, n1); f(k + 2 * kOctThreads, a2, n2); f(k + 3 * kOctThreads, a3, n3);
+    }
+    for (; k < nk; k += kOctThreads) f(k, keys[k], knode[k]);
+}
+
 __device__ __forceinline__ int nonempty4(const int* c4) { return (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0); }
 
 // The replay proper.  keys/knode: nk entries.  Returns the number of live nodes; `cur` points at the final array.
@@ -112,11 +125,10 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
         // ---- child sizes of every splittable node ------------------------------------------------------------
         for (int i = tid; i < 4 * n; i += kOctThreads) cnt4[i] = 0;
         __syncthreads();
-        for (int k = tid; k < nk; k += kOctThreads) {
-            const int i = (int)knode[k];
-            const OctNode nd = cur[i];
-            if (!nd.nomore) atomicAdd(&cnt4[4 * i + quadrant(keys[k], nd)], 1);
-        }
+        for_keys(keys, knode, nk, [&](int, uint32_t key, uint32_t node) {
+            const OctNode nd = cur[node];
+            if (!nd.nomore) atomicAdd(&cnt4[4 * node + quadrant(key, nd)], 1);
+        });
         __syncthreads();
 
         // ---- processing order of the splittable nodes --------------------------------------------------------
@@ -233,16 +245,18 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
         if (nexp_local) atomicAdd(&s_ctl[2], nexp_local);
         // ---- re-home the keys ----------------------------------------------------------------------------------
         if (n2 <= cap) {
-            for (int k = tid; k < nk; k += kOctThreads) {
-                const int i = (int)knode[k];
+            for_keys(keys, knode, nk, [&](int k, uint32_t key, uint32_t node) {
+                const int i = (int)node;
                 int dst = newidx[i];
                 if (splitf[i]) {
-                    const int q = quadrant(keys[k], cur[i]);
+                    const int q = quadrant(key, cur[i]);
                     const int* c4 = cnt4 + 4 * i;
                     dst += (q > 0 && c4[0] > 0) + (q > 1 && c4[1] > 0) + (q > 2 && c4[2] > 0);
+                    knode[k] = (uint32_t)dst;
+                } else if (dst != i) {
+                    knode[k] = (uint32_t)dst;
                 }
-                knode[k] = (uint32_t)dst;
-            }
+            });
         }
         __syncthreads();
         const int nexp = s_ctl[2];
@@ -311,8 +325,9 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(const Plan* __restrict__
     unsigned* best = reinterpret_cast<unsigned*>(cnt4);
     for (int i = tid; i < n; i += kOctThreads) best[i] = 0u;
     __syncthreads();
-    for (int k = tid; k < nk; k += kOctThreads)
-        atomicMax(&best[knode[k]], ((unsigned)key_s(keys[k]) << 24) | (0xFFFFFFu - (unsigned)k));
+    for_keys(keys, knode, nk, [&](int k, uint32_t key, uint32_t node) {
+        atomicMax(&best[node], ((unsigned)key_s(key) << 24) | (0xFFFFFFu - (unsigned)k));
+    });
     __syncthreads();
     uint32_t* sel = ws.sel + (size_t)b * plan->kp_cap_total + g.kp_base;
     for (int j = tid; j < n && j < g.kp_cap; j += kOctThreads) {
@@ -343,8 +358,9 @@ __global__ void __launch_bounds__(kOctThreads) k_octree_debug(const uint32_t* ke
     unsigned* best = reinterpret_cast<unsigned*>(cnt4);
     for (int i = tid; i < n; i += kOctThreads) best[i] = 0u;
     __syncthreads();
-    for (int k = tid; k < nk; k += kOctThreads)
-        atomicMax(&best[knode[k]], ((unsigned)key_s(keys[k]) << 24) | (0xFFFFFFu - (unsigned)k));
+    for_keys(keys, knode, nk, [&](int k, uint32_t key, uint32_t node) {
+        atomicMax(&best[node], ((unsigned)key_s(key) << 24) | (0xFFFFFFu - (unsigned)k));
+    });
     __syncthreads();
     for (int j = tid; j < n; j += kOctThreads) sel_idx[j] = 0xFFFFFFu - (best[n - 1 - j] & 0xFFFFFFu);
     if (tid == 0) *n_out = n;
