@@ -27,6 +27,13 @@ struct fbe_pipeline {
     fbe_pair_result* d_res = nullptr;
     uint8_t *d_front_in = nullptr, *d_bird_in = nullptr;   // staging for the host-buffer step
     fbe_pair_result* h_res = nullptr;    // pinned
+    // asynchronous host-buffer path: the H2D copy of step N+1 runs on its own stream beside the kernels of step N
+    cudaStream_t copy_stream = nullptr;
+    uint8_t *d_front_q[2] = {nullptr, nullptr}, *d_bird_q[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    bool in_used[2] = {false, false};
+    int* h_flags = nullptr;              // pinned, [2][2]
+    int32_t next_ticket = 0;
 };
 
 namespace {
@@ -71,6 +78,13 @@ void free_all(fbe_pipeline* p) {
                     p->b_bi, p->b_bd, p->b_sd, p->b_m12, p->b_bin, p->b_nm, p->flags, p->d_res, p->d_front_in, p->d_bird_in};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->h_res) cudaFreeHost(p->h_res);
+    if (p->h_flags) cudaFreeHost(p->h_flags);
+    if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
+    for (int k = 0; k < 2; ++k) {
+        if (p->d_front_q[k]) cudaFree(p->d_front_q[k]);
+        if (p->d_bird_q[k]) cudaFree(p->d_bird_q[k]);
+        for (cudaEvent_t e : {p->ev_in_ready[k], p->ev_in_free[k], p->ev_done[k]}) if (e) cudaEventDestroy(e);
+    }
     for (cudaEvent_t e : {p->ev_bird, p->ev_match, p->ev_t0, p->ev_t1}) if (e) cudaEventDestroy(e);
     p->front.destroy();
     p->bird.destroy();
@@ -251,6 +265,61 @@ int fbe_pipeline_fetch_pair(fbe_pipeline* p, int32_t pair, fbe_keypoint* front_k
     if (front_desc) FBE_CUDA(cudaMemcpy(front_desc, f.out_desc, (size_t)p->fcap * 32, cudaMemcpyDeviceToHost));
     if (bird_kps) FBE_CUDA(cudaMemcpy(bird_kps, b.out_kps, (size_t)p->bcap * sizeof(fbe_keypoint), cudaMemcpyDeviceToHost));
     if (bird_desc) FBE_CUDA(cudaMemcpy(bird_desc, b.out_desc, (size_t)p->bcap * 32, cudaMemcpyDeviceToHost));
+    return FBE_OK;
+}
+
+// Asynchronous step through HOST buffers (ideally pinned).  submit() enqueues the H2D copy of the inputs on a copy stream,
+// the step, and the D2H copy of the results into the caller's buffers, then returns a ticket; wait(ticket) blocks until
+// that step's results are in the host buffers.  Two steps may be in flight: the inputs of step N+1 travel while step N
+// computes, so the end-to-end rate is max(copy, compute) instead of their sum.  Steps execute in submit order.
+int fbe_pipeline_submit_host(fbe_pipeline* p, const uint8_t* h_front, const uint8_t* h_bird, fbe_pair_result* res,
+                             int32_t* front_matches12, int32_t* bird_matches12, int32_t* ticket) {
+    if (!p || !h_front || !h_bird || !ticket) return FBE_E_INVALID;
+    const fbe_pipeline_cfg& c = p->cfg;
+    FBE_CUDA(cudaSetDevice(c.device));
+    const size_t B = (size_t)p->B;
+    const size_t fbytes = B * c.front_rows * c.front_cols, bbytes = B * c.bird_rows * c.bird_cols;
+    if (!p->copy_stream) {
+        FBE_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+        FBE_CUDA(cudaMallocHost((void**)&p->h_flags, 4 * sizeof(int)));
+        for (int k = 0; k < 2; ++k) {
+            FBE_CUDA(cudaMalloc(&p->d_front_q[k], fbytes));
+            FBE_CUDA(cudaMalloc(&p->d_bird_q[k], bbytes));
+            FBE_CUDA(cudaEventCreateWithFlags(&p->ev_in_ready[k], cudaEventDisableTiming));
+            FBE_CUDA(cudaEventCreateWithFlags(&p->ev_in_free[k], cudaEventDisableTiming));
+            FBE_CUDA(cudaEventCreateWithFlags(&p->ev_done[k], cudaEventDisableTiming));
+        }
+    }
+    const int32_t t = p->next_ticket++;
+    const int k = t & 1;
+    cudaStream_t cs = p->copy_stream, ms = p->front.stream;
+    // inputs: wait until the step that last used this staging pair has consumed it
+    if (p->in_used[k]) FBE_CUDA(cudaStreamWaitEvent(cs, p->ev_in_free[k], 0));
+    FBE_CUDA(cudaMemcpyAsync(p->d_front_q[k], h_front, fbytes, cudaMemcpyHostToDevice, cs));
+    FBE_CUDA(cudaMemcpyAsync(p->d_bird_q[k], h_bird, bbytes, cudaMemcpyHostToDevice, cs));
+    FBE_CUDA(cudaEventRecord(p->ev_in_ready[k], cs));
+    FBE_CUDA(cudaStreamWaitEvent(ms, p->ev_in_ready[k], 0));
+    FBE_CUDA(cudaStreamWaitEvent(p->bird.stream, p->ev_in_ready[k], 0));
+    FBE_TRY(fbe_pipeline_step_dev(p, p->d_front_q[k], p->d_bird_q[k]));
+    FBE_CUDA(cudaEventRecord(p->ev_in_free[k], ms));       // ms has joined the bird stream inside step_dev
+    p->in_used[k] = true;
+    // results
+    if (res) FBE_CUDA(cudaMemcpyAsync(res, p->d_res, B * sizeof(fbe_pair_result), cudaMemcpyDeviceToHost, ms));
+    FBE_CUDA(cudaMemcpyAsync(p->h_flags + 2 * k, p->flags, 8, cudaMemcpyDeviceToHost, ms));
+    if (front_matches12) FBE_CUDA(cudaMemcpyAsync(front_matches12, p->f_m12, B * p->fcap * 4, cudaMemcpyDeviceToHost, ms));
+    if (bird_matches12) FBE_CUDA(cudaMemcpyAsync(bird_matches12, p->b_m12, B * p->bcap * 4, cudaMemcpyDeviceToHost, ms));
+    FBE_CUDA(cudaEventRecord(p->ev_done[k], ms));
+    // the next step's matching overwrites f_m12 / b_m12 / d_res: it is enqueued on ms after these copies, so ordering holds
+    *ticket = t;
+    return FBE_OK;
+}
+
+int fbe_pipeline_wait(fbe_pipeline* p, int32_t ticket) {
+    if (!p || ticket < 0 || ticket >= p->next_ticket || ticket < p->next_ticket - 2) return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(p->cfg.device));
+    const int k = ticket & 1;
+    FBE_CUDA(cudaEventSynchronize(p->ev_done[k]));
+    if (p->h_flags[2 * k]) { set_error("candidate rows overflow in pipeline (raise row capacity)"); return FBE_E_CAPACITY; }
     return FBE_OK;
 }
 

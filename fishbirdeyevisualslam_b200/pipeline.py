@@ -48,6 +48,16 @@ class FrontBirdPipeline:
         check(self._L.fbe_pipeline_step_host(self._h, C.c_void_p(h_front_ptr), C.c_void_p(h_bird_ptr), ptr(res),
                                              None if fm is None else ptr(fm), None if bm is None else ptr(bm)))
 
+    def submit_host(self, h_front_ptr: int, h_bird_ptr: int, res: np.ndarray, fm: np.ndarray | None = None, bm: np.ndarray | None = None) -> int:
+        """Asynchronous step through host (pinned) buffers; returns a ticket for wait().  Two steps may be in flight."""
+        t = C.c_int32()
+        check(self._L.fbe_pipeline_submit_host(self._h, C.c_void_p(h_front_ptr), C.c_void_p(h_bird_ptr), ptr(res),
+                                               None if fm is None else ptr(fm), None if bm is None else ptr(bm), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int):
+        check(self._L.fbe_pipeline_wait(self._h, C.c_int32(ticket)))
+
     def fetch(self, with_matches=True):
         res = np.zeros(self.batch, PAIR_RESULT_DTYPE)
         fm = np.zeros((self.batch, self.front_cap), np.int32) if with_matches else None

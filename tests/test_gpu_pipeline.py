@@ -96,3 +96,40 @@ def test_host_step_equals_device_step():
     for p in range(1, B):
         nq, nb = int(r1["n_front"][p - 1]), int(r1["n_bird"][p - 1])
         assert np.array_equal(f1[p][:nq], f2[p][:nq]) and np.array_equal(b1[p][:nb], b2[p][:nb])
+
+
+def test_async_submit_equals_sync_steps():
+    """Two steps in flight through host buffers (H2D of step N+1 beside the kernels of step N) give exactly the results
+    of the synchronous step-by-step path."""
+    from fishbirdeyevisualslam_b200 import _lib
+    from fishbirdeyevisualslam_b200.pipeline import FrontBirdPipeline, PinnedBuffer
+    B, S = 3, 4
+    fr, bi = sequence(B * S, 700)
+    p1, p2 = FrontBirdPipeline(B), FrontBirdPipeline(B)
+    want = []
+    hF, hB = [PinnedBuffer((B,) + fr.shape[1:]) for _ in range(S)], [PinnedBuffer((B,) + bi.shape[1:]) for _ in range(S)]
+    for s in range(S):
+        hF[s].array[...] = fr[s * B:(s + 1) * B]
+        hB[s].array[...] = bi[s * B:(s + 1) * B]
+        r = np.zeros(B, _lib.PAIR_RESULT_DTYPE)
+        f = np.zeros((B, p1.front_cap), np.int32)
+        b = np.zeros((B, p1.bird_cap), np.int32)
+        p1.step_host(hF[s].ptr, hB[s].ptr, r, f, b)
+        want.append((r, f, b))
+    res = [PinnedBuffer((B,), _lib.PAIR_RESULT_DTYPE) for _ in range(S)]
+    fm = [PinnedBuffer((B, p2.front_cap), np.int32) for _ in range(S)]
+    bm = [PinnedBuffer((B, p2.bird_cap), np.int32) for _ in range(S)]
+    tickets = []
+    for s in range(S):
+        tickets.append(p2.submit_host(hF[s].ptr, hB[s].ptr, res[s].array, fm[s].array, bm[s].array))
+        if s >= 1:
+            p2.wait(tickets[s - 1])
+    p2.wait(tickets[-1])
+    prev_nf = prev_nb = 0
+    for s in range(S):
+        r, f, b = want[s]
+        assert res[s].array.tobytes() == r.tobytes()
+        for p in range(B):
+            if s or p:
+                assert np.array_equal(fm[s].array[p][:prev_nf], f[p][:prev_nf]) and np.array_equal(bm[s].array[p][:prev_nb], b[p][:prev_nb])
+            prev_nf, prev_nb = int(r["n_front"][p]), int(r["n_bird"][p])
