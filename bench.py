@@ -196,6 +196,7 @@ def run_ours(args):
         e0.record(stream)
         for _ in range(args.steps):
             pipe.step_dev(dF.data_ptr(), dB.data_ptr())
+        pipe.join()           # a step ends on the pipeline's matching stream: order the public stream after it
         e1.record(stream)
         pipe.sync()
         barrier()

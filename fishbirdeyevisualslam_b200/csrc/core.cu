@@ -77,7 +77,7 @@ int ExtractorCore::set_grid(float min_x, float min_y, float inv_w, float inv_h, 
         FBE_CUDA(cudaStreamSynchronize(stream));
         if (realloc_grid) {
             cudaFree(ws.grid_start);
-            FBE_CUDA(cudaMalloc(&ws.grid_start, (size_t)cfg.max_batch * (gcols * grows + 1) * sizeof(int)));
+            FBE_CUDA(cudaMalloc(&ws.grid_start, (size_t)cfg.max_batch * out_sets * (gcols * grows + 1) * sizeof(int)));
         }
     }
     return FBE_OK;
@@ -116,41 +116,43 @@ int ExtractorCore::ensure_plan(int rows, int cols) {
     FBE_CUDA(cudaMalloc(&ws.sel, B * hplan.kp_cap_total * sizeof(uint32_t)));
     FBE_CUDA(cudaMalloc(&ws.level_n, B * FBE_MAX_LEVELS * sizeof(int)));
     FBE_CUDA(cudaMemset(ws.level_n, 0, B * FBE_MAX_LEVELS * sizeof(int)));
-    FBE_CUDA(cudaMalloc(&ws.out_kps, B * hplan.kp_cap_total * sizeof(fbe_keypoint)));
-    FBE_CUDA(cudaMalloc(&ws.out_desc, B * hplan.kp_cap_total * 32));
-    FBE_CUDA(cudaMalloc(&ws.out_n, B * sizeof(int)));
-    FBE_CUDA(cudaMalloc(&ws.out_cell, B * hplan.kp_cap_total * sizeof(int)));
+    const size_t Bo = B * (size_t)out_sets;           // output arrays exist once per output set
+    FBE_CUDA(cudaMalloc(&ws.out_kps, Bo * hplan.kp_cap_total * sizeof(fbe_keypoint)));
+    FBE_CUDA(cudaMalloc(&ws.out_desc, Bo * hplan.kp_cap_total * 32));
+    FBE_CUDA(cudaMalloc(&ws.out_n, Bo * sizeof(int)));
+    FBE_CUDA(cudaMalloc(&ws.out_cell, Bo * hplan.kp_cap_total * sizeof(int)));
     const int gcells = std::max(g_cols * g_rows, kMaxGridCells);
-    FBE_CUDA(cudaMalloc(&ws.grid_start, B * (gcells + 1) * sizeof(int)));
-    FBE_CUDA(cudaMalloc(&ws.grid_items, B * hplan.kp_cap_total * sizeof(int)));
+    FBE_CUDA(cudaMalloc(&ws.grid_start, Bo * (gcells + 1) * sizeof(int)));
+    FBE_CUDA(cudaMalloc(&ws.grid_items, Bo * hplan.kp_cap_total * sizeof(int)));
     FBE_CUDA(cudaMalloc(&ws.status, B * sizeof(int)));
     FBE_CUDA(cudaMemset(ws.status, 0, B * sizeof(int)));
     plan_rows = rows; plan_cols = cols; have_ws = true;
     return FBE_OK;
 }
 
-Workspace ExtractorCore::slot_view(int slot0) const {
+Workspace ExtractorCore::slot_view(int slot0, int out_set) const {
     Workspace v = ws;
     v.slot0 = slot0;
     const size_t s = (size_t)slot0;
+    const size_t so = (size_t)out_set * cfg.max_batch + s;      // slot index inside the output arrays
     const int gcells = hplan.grid_cols * hplan.grid_rows;
     v.pyr += s * hplan.pyr_bytes; v.blur += s * hplan.pyr_bytes;
     v.cell_count += s * hplan.ncells_total;
     v.slots += s * hplan.slots_total; v.keys += s * hplan.slots_total; v.key_node += s * hplan.slots_total;
     v.oct_scratch += s * ws.oct_scratch_bytes;
     v.sel += s * hplan.kp_cap_total; v.level_n += s * FBE_MAX_LEVELS;
-    v.out_kps += s * hplan.kp_cap_total; v.out_desc += s * hplan.kp_cap_total * 32; v.out_n += s;
-    v.out_cell += s * hplan.kp_cap_total; v.grid_start += s * (gcells + 1); v.grid_items += s * hplan.kp_cap_total;
+    v.out_kps += so * hplan.kp_cap_total; v.out_desc += so * hplan.kp_cap_total * 32; v.out_n += so;
+    v.out_cell += so * hplan.kp_cap_total; v.grid_start += so * (gcells + 1); v.grid_items += so * hplan.kp_cap_total;
     v.status += s;
     return v;
 }
 
-int ExtractorCore::run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, int nimg, int rows, int cols, int slot0) {
-    if (nimg < 1 || slot0 < 0 || slot0 + nimg > cfg.max_batch) { set_error("batch larger than max_batch"); return FBE_E_INVALID; }
+int ExtractorCore::run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, int nimg, int rows, int cols, int slot0, int out_set) {
+    if (nimg < 1 || slot0 < 0 || slot0 + nimg > cfg.max_batch || out_set < 0 || out_set >= out_sets) { set_error("batch larger than max_batch"); return FBE_E_INVALID; }
     FBE_CUDA(cudaSetDevice(cfg.device));
     int rc = ensure_plan(rows, cols);
     if (rc != FBE_OK) return rc;
-    Workspace v = slot_view(slot0);
+    Workspace v = slot_view(slot0, out_set);
     v.in = d_imgs; v.in_pitch = pitch; v.in_slot_stride = slot_stride;
     cudaEvent_t* te = nullptr;
     if (timing) {

@@ -168,8 +168,11 @@ struct ExtractorCore {
     int ensure_plan(int rows, int cols);
     int set_grid(float min_x, float min_y, float inv_w, float inv_h, int gcols, int grows);
     // images already on the device: [nimg][rows][pitch]; results go to workspace slots slot0 .. slot0+nimg-1
-    int run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, int nimg, int rows, int cols, int slot0 = 0);
-    Workspace slot_view(int slot0) const;
+    // `out_set` selects one of `out_sets` copies of the OUTPUT arrays (keypoints, descriptors, counts, grid): the batch
+    // pipeline alternates between two so that matching of step N can run beside the extraction of step N+1.
+    int run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, int nimg, int rows, int cols, int slot0 = 0, int out_set = 0);
+    Workspace slot_view(int slot0, int out_set = 0) const;
+    int out_sets = 1;      // set before the first ensure_plan()
     int free_ws();
 };
 

@@ -5,6 +5,8 @@
 // Frame slots: each extractor workspace holds batch+1 frames; slot 0 carries the last frame of the previous step, slots
 // 1..batch receive this step's frames, so "pair p vs pair p-1" is the uniform-stride problem (query slot p, target
 // slot p+1) for p = 0..batch-1.  The bird extractor runs on its own stream beside the front extractor.
+// Matching runs on a third stream and the extractor OUTPUT arrays exist twice (sets alternate per step), so the
+// latency-bound tail of step N (window rows, sequential resolve, bird top-2) overlaps the extraction of step N+1.
 #include <cstring>
 #include <new>
 #include "match_kernels.cuh"
@@ -16,7 +18,11 @@ struct fbe_pipeline {
     ExtractorCore front, bird;
     int B = 0, fcap = 0, bcap = 0, row_cap = 256;
     bool have_prev = false;
-    cudaEvent_t ev_bird = nullptr, ev_match = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaStream_t mstream = nullptr;      // matching
+    cudaEvent_t ev_front = nullptr, ev_bird = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_match_done[2] = {nullptr, nullptr};   // per output set: the matching that read it has finished
+    bool set_used[2] = {false, false};
+    int step_count = 0, last_set = 0;
     // front matching workspace
     float4* fq = nullptr; int2* flv = nullptr; unsigned* frows = nullptr; int* fcnt = nullptr;
     int *f_mdist = nullptr, *f_m21 = nullptr, *f_m12 = nullptr, *f_bin = nullptr, *f_hit = nullptr, *f_nm = nullptr;
@@ -49,8 +55,8 @@ __global__ void k_pair_results(const int* __restrict__ nf, const int* __restrict
     out[p] = r;
 }
 
-FrameDev frame_dev(const ExtractorCore& e, int slot0) {
-    Workspace v = e.slot_view(slot0);
+FrameDev frame_dev(const ExtractorCore& e, int slot0, int set) {
+    Workspace v = e.slot_view(slot0, set);
     FrameDev f;
     f.kps = v.out_kps; f.desc = v.out_desc; f.n = v.out_n; f.start = v.grid_start; f.items = v.grid_items;
     f.kp_stride = e.hplan.kp_cap_total;
@@ -59,8 +65,9 @@ FrameDev frame_dev(const ExtractorCore& e, int slot0) {
     return f;
 }
 
-int carry_last(ExtractorCore& e, int B, cudaStream_t st) {
-    Workspace s = e.slot_view(B), d = e.slot_view(0);
+// last frame of this step (slot B of `set`) becomes slot 0 of the other set, where the next step's matching reads it
+int carry_last(ExtractorCore& e, int B, int set, cudaStream_t st) {
+    Workspace s = e.slot_view(B, set), d = e.slot_view(0, 1 - set);
     const int cap = e.hplan.kp_cap_total, gcells = e.hplan.grid_cols * e.hplan.grid_rows;
     FBE_CUDA(cudaMemcpyAsync(d.out_kps, s.out_kps, (size_t)cap * sizeof(fbe_keypoint), cudaMemcpyDeviceToDevice, st));
     FBE_CUDA(cudaMemcpyAsync(d.out_desc, s.out_desc, (size_t)cap * 32, cudaMemcpyDeviceToDevice, st));
@@ -74,6 +81,7 @@ void free_all(fbe_pipeline* p) {
     cudaSetDevice(p->cfg.device);
     if (p->front.stream) cudaStreamSynchronize(p->front.stream);
     if (p->bird.stream) cudaStreamSynchronize(p->bird.stream);
+    if (p->mstream) { cudaStreamSynchronize(p->mstream); cudaStreamDestroy(p->mstream); p->mstream = nullptr; }
     void* ptrs[] = {p->fq, p->flv, p->frows, p->fcnt, p->f_mdist, p->f_m21, p->f_m12, p->f_bin, p->f_hit, p->f_nm, p->bq, p->blv,
                     p->b_bi, p->b_bd, p->b_sd, p->b_m12, p->b_bin, p->b_nm, p->flags, p->d_res, p->d_front_in, p->d_bird_in};
     for (void* q : ptrs) if (q) cudaFree(q);
@@ -85,7 +93,7 @@ void free_all(fbe_pipeline* p) {
         if (p->d_bird_q[k]) cudaFree(p->d_bird_q[k]);
         for (cudaEvent_t e : {p->ev_in_ready[k], p->ev_in_free[k], p->ev_done[k]}) if (e) cudaEventDestroy(e);
     }
-    for (cudaEvent_t e : {p->ev_bird, p->ev_match, p->ev_t0, p->ev_t1}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {p->ev_front, p->ev_bird, p->ev_match_done[0], p->ev_match_done[1], p->ev_t0, p->ev_t1}) if (e) cudaEventDestroy(e);
     p->front.destroy();
     p->bird.destroy();
 }
@@ -104,6 +112,7 @@ int fbe_pipeline_create(const fbe_pipeline_cfg* cfg, fbe_pipeline** out) {
     fbe_extractor_cfg fc = cfg->front, bc = cfg->bird;
     fc.max_batch = bc.max_batch = cfg->batch + 1;
     fc.device = bc.device = cfg->device;
+    p->front.out_sets = p->bird.out_sets = 2;
     int rc = p->front.init(fc);
     if (rc == FBE_OK) rc = p->bird.init(bc);
     auto fail = [&](int code) { free_all(p); delete p; return code; };
@@ -129,11 +138,12 @@ int fbe_pipeline_create(const fbe_pipeline_cfg* cfg, fbe_pipeline** out) {
     if (!ok) { set_error("pipeline workspace allocation failed"); return fail(FBE_E_CUDA); }
     if (cudaMallocHost((void**)&p->h_res, B * sizeof(fbe_pair_result)) != cudaSuccess) { set_error("pinned alloc failed"); return fail(FBE_E_CUDA); }
     cudaMemset(p->flags, 0, 64);
-    cudaMemset(p->front.ws.out_n, 0, (B + 1) * sizeof(int));
-    cudaMemset(p->bird.ws.out_n, 0, (B + 1) * sizeof(int));
-    cudaMemset(p->front.ws.grid_start, 0, (B + 1) * (64 * 48 + 1) * sizeof(int));
-    cudaMemset(p->bird.ws.grid_start, 0, (B + 1) * (32 * 32 + 1) * sizeof(int));
-    for (cudaEvent_t* e : {&p->ev_bird, &p->ev_match}) cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+    cudaMemset(p->front.ws.out_n, 0, 2 * (B + 1) * sizeof(int));
+    cudaMemset(p->bird.ws.out_n, 0, 2 * (B + 1) * sizeof(int));
+    cudaMemset(p->front.ws.grid_start, 0, 2 * (B + 1) * (64 * 48 + 1) * sizeof(int));
+    cudaMemset(p->bird.ws.grid_start, 0, 2 * (B + 1) * (32 * 32 + 1) * sizeof(int));
+    if (cudaStreamCreateWithFlags(&p->mstream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); return fail(FBE_E_CUDA); }
+    for (cudaEvent_t* e : {&p->ev_front, &p->ev_bird, &p->ev_match_done[0], &p->ev_match_done[1]}) cudaEventCreateWithFlags(e, cudaEventDisableTiming);
     cudaEventCreate(&p->ev_t0); cudaEventCreate(&p->ev_t1);
     cudaDeviceSynchronize();
     *out = p;
@@ -164,17 +174,23 @@ int fbe_pipeline_step_dev(fbe_pipeline* p, const uint8_t* d_front, const uint8_t
     if (!p || !d_front || !d_bird) return FBE_E_INVALID;
     const fbe_pipeline_cfg& c = p->cfg;
     FBE_CUDA(cudaSetDevice(c.device));
-    cudaStream_t ms = p->front.stream, bs = p->bird.stream;
+    cudaStream_t fs = p->front.stream, bs = p->bird.stream, ms = p->mstream;
     const int B = p->B;
-    FBE_CUDA(cudaEventRecord(p->ev_t0, ms));
-    // the bird extractor must not overwrite slots that the previous step's matching still reads
-    FBE_CUDA(cudaStreamWaitEvent(bs, p->ev_match, 0));
-    FBE_TRY(p->front.run_dev(d_front, c.front_cols, c.front_rows * c.front_cols, B, c.front_rows, c.front_cols, 1));
-    FBE_TRY(p->bird.run_dev(d_bird, c.bird_cols, c.bird_rows * c.bird_cols, B, c.bird_rows, c.bird_cols, 1));
+    const int set = p->step_count & 1;
+    FBE_CUDA(cudaEventRecord(p->ev_t0, fs));
+    // the extractors must not overwrite an output set that the matching of two steps ago (same set) still reads
+    if (p->set_used[set]) {
+        FBE_CUDA(cudaStreamWaitEvent(fs, p->ev_match_done[set], 0));
+        FBE_CUDA(cudaStreamWaitEvent(bs, p->ev_match_done[set], 0));
+    }
+    FBE_TRY(p->front.run_dev(d_front, c.front_cols, c.front_rows * c.front_cols, B, c.front_rows, c.front_cols, 1, set));
+    FBE_CUDA(cudaEventRecord(p->ev_front, fs));
+    FBE_TRY(p->bird.run_dev(d_bird, c.bird_cols, c.bird_rows * c.bird_cols, B, c.bird_rows, c.bird_cols, 1, set));
     FBE_CUDA(cudaEventRecord(p->ev_bird, bs));
 
     // ---- front: pair p (slot p+1) against pair p-1 (slot p) --------------------------------------------------------
-    const FrameDev fq = frame_dev(p->front, 0), ft = frame_dev(p->front, 1);
+    FBE_CUDA(cudaStreamWaitEvent(ms, p->ev_front, 0));
+    const FrameDev fq = frame_dev(p->front, 0, set), ft = frame_dev(p->front, 1, set);
     FBE_TRY(launch_queries_from_kps(fq.kps, nullptr, nullptr, fq.n, p->fcap, B, (float)c.front_window, p->fq, p->flv, ms));
     QueryDev fqs{p->fq, p->flv, fq.desc, fq.n, p->fcap};
     FBE_TRY(launch_window_rows(ft, fqs, B, p->fcap, true, p->row_cap, p->frows, p->fcnt, p->flags, ms));
@@ -187,7 +203,7 @@ int fbe_pipeline_step_dev(fbe_pipeline* p, const uint8_t* d_front, const uint8_t
 
     // ---- bird ----------------------------------------------------------------------------------------------------
     FBE_CUDA(cudaStreamWaitEvent(ms, p->ev_bird, 0));
-    const FrameDev bq = frame_dev(p->bird, 0), bt = frame_dev(p->bird, 1);
+    const FrameDev bq = frame_dev(p->bird, 0, set), bt = frame_dev(p->bird, 1, set);
     FBE_TRY(launch_queries_from_kps(bq.kps, nullptr, nullptr, bq.n, p->bcap, B, (float)c.bird_window, p->bq, p->blv, ms));
     QueryDev bqs{p->bq, p->blv, bq.desc, bq.n, p->bcap};
     FBE_TRY(launch_window_top2(bt, bqs, B, p->bcap, false, p->b_bi, p->b_bd, p->b_sd, ms));
@@ -197,14 +213,26 @@ int fbe_pipeline_step_dev(fbe_pipeline* p, const uint8_t* d_front, const uint8_t
     f.matches12 = p->b_m12; f.dmatches = nullptr; f.n_dmatches = nullptr; f.nmatches = p->b_nm; f.q_bin = p->b_bin;
     FBE_TRY(launch_bird_finish(f, B, ms));
 
-    k_pair_results<<<(B + 127) / 128, 128, 0, ms>>>(p->front.ws.out_n, p->bird.ws.out_n, p->f_nm, p->b_nm, B, p->d_res);
+    k_pair_results<<<(B + 127) / 128, 128, 0, ms>>>(fq.n, bq.n, p->f_nm, p->b_nm, B, p->d_res);
     count_launch();
     FBE_CUDA(cudaGetLastError());
-    FBE_TRY(carry_last(p->front, B, ms));
-    FBE_TRY(carry_last(p->bird, B, ms));
-    FBE_CUDA(cudaEventRecord(p->ev_match, ms));
+    FBE_TRY(carry_last(p->front, B, set, ms));
+    FBE_TRY(carry_last(p->bird, B, set, ms));
+    FBE_CUDA(cudaEventRecord(p->ev_match_done[set], ms));
     FBE_CUDA(cudaEventRecord(p->ev_t1, ms));
+    p->set_used[set] = true;
+    p->last_set = set;
+    p->step_count++;
     p->have_prev = true;
+    return FBE_OK;
+}
+
+// Orders the front stream (the one fbe_pipeline_stream() hands out) after everything enqueued so far, without a host
+// synchronisation, so that a caller's event recorded on it afterwards marks the end of the submitted steps.
+int fbe_pipeline_join(fbe_pipeline* p) {
+    if (!p) return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(p->cfg.device));
+    if (p->step_count > 0) FBE_CUDA(cudaStreamWaitEvent(p->front.stream, p->ev_match_done[p->last_set], 0));
     return FBE_OK;
 }
 
@@ -213,6 +241,7 @@ int fbe_pipeline_sync(fbe_pipeline* p) {
     FBE_CUDA(cudaSetDevice(p->cfg.device));
     FBE_CUDA(cudaStreamSynchronize(p->front.stream));
     FBE_CUDA(cudaStreamSynchronize(p->bird.stream));
+    FBE_CUDA(cudaStreamSynchronize(p->mstream));
     return FBE_OK;
 }
 
@@ -226,7 +255,7 @@ int fbe_pipeline_last_step_ms(fbe_pipeline* p, float* ms) {
 int fbe_pipeline_fetch(fbe_pipeline* p, fbe_pair_result* res, int32_t* front_matches12, int32_t* bird_matches12) {
     if (!p) return FBE_E_INVALID;
     FBE_CUDA(cudaSetDevice(p->cfg.device));
-    cudaStream_t ms = p->front.stream;
+    cudaStream_t ms = p->mstream;
     const size_t B = (size_t)p->B;
     int h_flags[2] = {0, 0};
     FBE_CUDA(cudaMemcpyAsync(p->h_res, p->d_res, B * sizeof(fbe_pair_result), cudaMemcpyDeviceToHost, ms));
@@ -248,7 +277,7 @@ int fbe_pipeline_step_host(fbe_pipeline* p, const uint8_t* h_front, const uint8_
     if (!p->d_front_in) FBE_CUDA(cudaMalloc(&p->d_front_in, fbytes));
     if (!p->d_bird_in) FBE_CUDA(cudaMalloc(&p->d_bird_in, bbytes));
     // the previous step may still be reading the staging buffers
-    FBE_CUDA(cudaStreamWaitEvent(p->bird.stream, p->ev_match, 0));
+    FBE_TRY(fbe_pipeline_sync(p));
     FBE_CUDA(cudaMemcpyAsync(p->d_front_in, h_front, fbytes, cudaMemcpyHostToDevice, p->front.stream));
     FBE_CUDA(cudaMemcpyAsync(p->d_bird_in, h_bird, bbytes, cudaMemcpyHostToDevice, p->bird.stream));
     FBE_TRY(fbe_pipeline_step_dev(p, p->d_front_in, p->d_bird_in));
@@ -260,7 +289,7 @@ int fbe_pipeline_fetch_pair(fbe_pipeline* p, int32_t pair, fbe_keypoint* front_k
     if (!p || pair < 0 || pair >= p->B) return FBE_E_INVALID;
     FBE_CUDA(cudaSetDevice(p->cfg.device));
     FBE_TRY(fbe_pipeline_sync(p));
-    Workspace f = p->front.slot_view(pair + 1), b = p->bird.slot_view(pair + 1);
+    Workspace f = p->front.slot_view(pair + 1, p->last_set), b = p->bird.slot_view(pair + 1, p->last_set);
     if (front_kps) FBE_CUDA(cudaMemcpy(front_kps, f.out_kps, (size_t)p->fcap * sizeof(fbe_keypoint), cudaMemcpyDeviceToHost));
     if (front_desc) FBE_CUDA(cudaMemcpy(front_desc, f.out_desc, (size_t)p->fcap * 32, cudaMemcpyDeviceToHost));
     if (bird_kps) FBE_CUDA(cudaMemcpy(bird_kps, b.out_kps, (size_t)p->bcap * sizeof(fbe_keypoint), cudaMemcpyDeviceToHost));
@@ -292,16 +321,16 @@ int fbe_pipeline_submit_host(fbe_pipeline* p, const uint8_t* h_front, const uint
     }
     const int32_t t = p->next_ticket++;
     const int k = t & 1;
-    cudaStream_t cs = p->copy_stream, ms = p->front.stream;
+    cudaStream_t cs = p->copy_stream, ms = p->mstream;
     // inputs: wait until the step that last used this staging pair has consumed it
     if (p->in_used[k]) FBE_CUDA(cudaStreamWaitEvent(cs, p->ev_in_free[k], 0));
     FBE_CUDA(cudaMemcpyAsync(p->d_front_q[k], h_front, fbytes, cudaMemcpyHostToDevice, cs));
     FBE_CUDA(cudaMemcpyAsync(p->d_bird_q[k], h_bird, bbytes, cudaMemcpyHostToDevice, cs));
     FBE_CUDA(cudaEventRecord(p->ev_in_ready[k], cs));
-    FBE_CUDA(cudaStreamWaitEvent(ms, p->ev_in_ready[k], 0));
+    FBE_CUDA(cudaStreamWaitEvent(p->front.stream, p->ev_in_ready[k], 0));
     FBE_CUDA(cudaStreamWaitEvent(p->bird.stream, p->ev_in_ready[k], 0));
     FBE_TRY(fbe_pipeline_step_dev(p, p->d_front_q[k], p->d_bird_q[k]));
-    FBE_CUDA(cudaEventRecord(p->ev_in_free[k], ms));       // ms has joined the bird stream inside step_dev
+    FBE_CUDA(cudaEventRecord(p->ev_in_free[k], ms));       // the match stream has joined both extractor streams inside step_dev
     p->in_used[k] = true;
     // results
     if (res) FBE_CUDA(cudaMemcpyAsync(res, p->d_res, B * sizeof(fbe_pair_result), cudaMemcpyDeviceToHost, ms));

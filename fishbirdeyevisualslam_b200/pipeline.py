@@ -41,6 +41,10 @@ class FrontBirdPipeline:
         """Asynchronous step on device-resident inputs ([batch,rows,cols] u8 each)."""
         check(self._L.fbe_pipeline_step_dev(self._h, C.c_void_p(d_front_ptr), C.c_void_p(d_bird_ptr)))
 
+    def join(self):
+        """Order the pipeline's public stream after all submitted steps (stream-level wait, no host synchronisation)."""
+        check(self._L.fbe_pipeline_join(self._h))
+
     def sync(self):
         check(self._L.fbe_pipeline_sync(self._h))
 

@@ -240,8 +240,11 @@ FBE_API int fbe_pipeline_fetch_pair(fbe_pipeline* p, int32_t pair, fbe_keypoint*
                             fbe_keypoint* bird_kps, uint8_t* bird_desc);
 /* elapsed GPU milliseconds between the first kernel and the last kernel of the last step (CUDA events) */
 FBE_API int fbe_pipeline_last_step_ms(fbe_pipeline* p, float* ms);
-/* raw stream handle (cudaStream_t) so that a caller can record its own events around steps */
+/* raw stream handle (cudaStream_t) so that a caller can record its own events around steps; a step starts on this
+ * stream but ends on the pipeline's matching stream: call fbe_pipeline_join() (stream-level wait, no host sync) before
+ * recording the closing event */
 FBE_API int fbe_pipeline_stream(fbe_pipeline* p, void** stream);
+FBE_API int fbe_pipeline_join(fbe_pipeline* p);
 
 /* live per-stage device timing (CUDA events on the launching streams) for bench.py's roofline block.
  * ms: 12 doubles summed over `steps` steps = front[pyramid, fast, octree, describe, grid, blur], bird[same]. */

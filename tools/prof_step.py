@@ -16,11 +16,15 @@ for _ in range(3):
 pipe.sync()
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
-tot = 0.0
+stream = torch.cuda.ExternalStream(pipe.stream_ptr)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(stream)
 for _ in range(steps):
     pipe.step_dev(dF.data_ptr(), dB.data_ptr())
-    pipe.sync()
-    tot += pipe.last_step_ms()
+pipe.join()
+e1.record(stream)
+pipe.sync()
+tot = e0.elapsed_time(e1)
 torch.cuda.cudart().cudaProfilerStop()
 res, _, _ = pipe.fetch(with_matches=False)
 print(f"batch {B}: {tot / steps:.3f} ms/step, {B * steps / tot * 1e3:.0f} pairs/s; mean kps front {res['n_front'].mean():.1f} bird {res['n_bird'].mean():.1f}; "
