@@ -44,6 +44,7 @@ int ExtractorCore::free_ws() {
     cudaFree(ws.out_desc); cudaFree(ws.out_n); cudaFree(ws.out_cell); cudaFree(ws.grid_start); cudaFree(ws.grid_items);
     cudaFree(ws.status); cudaFree(dplan); cudaFree(dtab);
     delete blur_maps; blur_maps = nullptr;
+    delete fast_maps; fast_maps = nullptr;
     std::memset(&ws, 0, sizeof(ws));
     dplan = nullptr; dtab = nullptr; have_ws = false;
     return FBE_OK;
@@ -100,10 +101,14 @@ int ExtractorCore::ensure_plan(int rows, int cols) {
     FBE_CUDA(cudaMalloc(&ws.pyr, B * hplan.pyr_bytes));
     FBE_CUDA(cudaMalloc(&ws.blur, B * hplan.pyr_bytes));
     blur_maps = new TmaMaps();
+    fast_maps = new TmaMaps();
     std::memset(blur_maps, 0, sizeof(TmaMaps));
+    std::memset(fast_maps, 0, sizeof(TmaMaps));
     for (int l = 0; l < hplan.nlevels; ++l) {
         const LevelGeom& g = hplan.lv[l];
         rc = tma_encode_level(&blur_maps->m[l], ws.pyr + g.img_off, g.pitch, g.ph, (int)B, (size_t)hplan.pyr_bytes, kBlurTW + 32, kBlurTH + 6);
+        if (rc != FBE_OK) return rc;
+        rc = tma_encode_level(&fast_maps->m[l], ws.pyr + g.img_off, g.pitch, g.ph, (int)B, (size_t)hplan.pyr_bytes, 256, g.hcell + 6);
         if (rc != FBE_OK) return rc;
     }
     FBE_CUDA(cudaMemset(ws.blur, 0, B * hplan.pyr_bytes));
@@ -182,7 +187,7 @@ int ExtractorCore::run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, in
     FBE_MARK(7, stream2);
     FBE_STAGE("blur", stream2);
     FBE_CUDA(cudaEventRecord(ev_blur, stream2));
-    if ((rc = launch_fast_cells(hplan, dplan, v, nimg, stream)) != FBE_OK) return rc;
+    if ((rc = launch_fast_cells(hplan, dplan, v, *fast_maps, nimg, stream)) != FBE_OK) return rc;
     FBE_MARK(2, stream);
     FBE_STAGE("fast", stream);
     if ((rc = launch_octree(hplan, dplan, v, nimg, stream)) != FBE_OK) return rc;

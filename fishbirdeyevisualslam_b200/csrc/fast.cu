@@ -1,6 +1,6 @@
 // Per-cell FAST-9/16 detection with threshold fallback (ComputeKeyPointsOctTree cell loop,
 // src/ORBextractor.cc:765-829) as ONE kernel.  A CTA owns a GROUP of up to 8 consecutive ~30x30 FAST cells of one
-// cell row of one level of one image (a strip <= 256 px wide), so that the 3-px ring halo and the per-CTA fixed costs
+// cell row of one level of one image (a strip <= 224 px wide), so that the 3-px ring halo and the per-CTA fixed costs
 // are amortised over ~8k pixels.
 //
 // What the reference does per cell: cv::FAST(roi, iniThFAST, nms) and, when that returns nothing,
@@ -14,10 +14,11 @@
 //     threshold yields both answers; the fallback decision is "no NMS survivor with score >= iniThFAST".
 //
 // Phases of a CTA (all in shared memory, 4 block barriers):
-//   0. stage the strip + 3-px halo with aligned 32-bit loads; clear the score tile and the survivor masks.
+//   0. TMA stages the strip + 3-px halo (box start rounded down to 16 bytes); the score tile and the survivor masks
+//      are cleared while the copy is in flight.
 //   1. PRETEST every pixel with the 4 compass ring pixels (every 9-arc contains k or k+8 for each k, so
 //      min(max(I0,I8),max(I4,I12)) - c > t  or  c - max(min(I0,I8),min(I4,I12)) > t is necessary); passing pixels are
-//      appended to a work list (warp-aggregated shared atomics) -- this removes the divergence of the score phase.
+//      appended to the warp's private work list (ballot ranks, no atomics) -- this removes the divergence of the score phase.
 //   2. SCORE the work list densely: ring differences are packed as biased s16x2 {I-c+256, c-I+256} with ONE IMAD each, so
 //      that bright and dark arcs share the DPX 3-input min/max (VIMNMX3.S16x2): 16+16 min3 + 8 max3 per pixel.
 //   3. strict 8-neighbour NMS of the listed pixels inside their cell; survivors set a bit in per-cell row masks
@@ -28,28 +29,31 @@
 // kernel concatenates cells in row-major order, which reproduces vToDistributeKeys order.
 #include <algorithm>
 #include "fbe_internal.cuh"
+#include "tma.cuh"
 
 namespace fbe {
 
 constexpr int kFastThreads = 256;
 constexpr int kFastWarps = kFastThreads / 32;
 
-constexpr int kTilePitch = ((kFastGroupW + 3) & ~3) + 16;   // staged strip: column t holds strip x = t - 4
+constexpr int kTilePitch = 256;                             // TMA box width: staged tile column t = padded column tcol0 + t
 constexpr int kScorePitch = kFastGroupW + 8;                // score tile: column t holds strip x = t - 1 (zero margin)
 constexpr int kTileW = kTilePitch / 4;                      // in 32-bit words
+static_assert(kFastGroupW + 6 + 15 + 3 <= kTilePitch, "strip + ring halo + 16-byte alignment slack must fit the TMA box");
 
-struct FastLayout { int off_sc, sc_bytes, off_work, off_mask, mask_words, off_xinfo, total; };
+struct FastLayout { int off_sc, sc_bytes, off_work, work_cap, off_mask, mask_words, off_xinfo, total; };
 
-// shared-memory carve-up for a strip of gw x ch pixels covering ncell cells (pitches are compile-time constants so
-// that every ring / neighbour access is a base register + immediate)
-__host__ __device__ inline FastLayout fast_layout(int gw, int ch, int ncell) {
+// shared-memory carve-up for a strip of gw x ch pixels covering ncell cells in a level whose cells are hcell high
+// (pitches are compile-time constants so that every ring / neighbour access is a base register + immediate)
+__host__ __device__ inline FastLayout fast_layout(int gw, int ch, int hcell, int ncell) {
     FastLayout L;
-    int o = kTilePitch * (ch + 6);
+    int o = kTilePitch * (hcell + 6);                // the TMA box always has the level's full cell height
     L.off_sc = o;
     L.sc_bytes = (kScorePitch * (ch + 2) + 15) & ~15;
     o += L.sc_bytes;
     L.off_work = o;
-    o += (gw * ch * 2 + 15) & ~15;
+    L.work_cap = ((ch + kFastWarps - 1) / kFastWarps) * gw;          // per warp: its rows, every pixel
+    o += (L.work_cap * kFastWarps * 2 + 15) & ~15;
     L.off_mask = o;
     L.mask_words = ncell * ch * 4;                   // [lo|ini][cell][row][2] u32
     o += L.mask_words * 4;
@@ -77,9 +81,10 @@ __device__ __forceinline__ unsigned pretest_pair(unsigned c, unsigned i0, unsign
     return (__vmaxu2(d1, d2) + k2) & 0x80008000u;                          // lane > 256 + t  <=>  bit 15 of lane + k set
 }
 
-__global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restrict__ plan, Workspace ws) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int s_nwork;
+__global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restrict__ plan, Workspace ws,
+                                                             const __grid_constant__ TmaMaps maps) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int b = blockIdx.y;
@@ -102,29 +107,26 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restr
         if (tid < ncell) count_out[tid] = 0;
         return;
     }
-    const FastLayout L = fast_layout(gw, ch, ncell);
+    const FastLayout L = fast_layout(gw, ch, hcell, ncell);
     uint8_t* tile = smem;
-    uint32_t* tile32 = reinterpret_cast<uint32_t*>(smem);
+    const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(smem);
     uint8_t* sc = smem + L.off_sc;
-    uint16_t* work = reinterpret_cast<uint16_t*>(smem + L.off_work);
+    uint16_t* work = reinterpret_cast<uint16_t*>(smem + L.off_work) + wid * L.work_cap;   // this warp's private list
     uint32_t* mask = reinterpret_cast<uint32_t*>(smem + L.off_mask);      // lo masks, then ini masks
     uint8_t* xinfo = smem + L.off_xinfo;
-    const int nquad = (gw + 3) >> 2;
 
-    // ---- phase 0: stage the strip, realigned so that strip x = 0 sits on a 32-bit boundary ------------------------
+    // ---- phase 0: TMA stages the strip + 3-px ring halo; the box starts on a 16-byte boundary of the padded row,
+    //      `off` = tile column of strip x = 0 (4 .. 19).  The clears below run while the copy is in flight. ---------------
+    const int pcol0 = x0 + kEdge;                                 // padded column of strip x = 0
+    const int tcol0 = (pcol0 - 4) & ~15;
+    const int off = pcol0 - tcol0;
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, (uint32_t)(kTilePitch * (hcell + 6)));
+        tma_load_3d(tile, &maps.m[l], &bar, tcol0, y0 - 3 + kEdge, ws.slot0 + b);
+    }
     {
-        const int pitch = g.pitch;
-        const uint8_t* img = ws.pyr + (size_t)b * plan->pyr_bytes + g.img_off;
-        const int a = x0 + kEdge - 4;                               // padded column of tile column 0
-        const int sh = (a & 3) * 8;
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(img + (size_t)(y0 - 3 + kEdge) * pitch + (a & ~3));
-        const int pw = pitch >> 2;
-        const int twords = nquad + 3;                               // tile columns 0 .. 4*nquad + 11
-        for (int r = wid; r < ch + 6; r += kFastWarps) {
-            const uint32_t* srow = src + (size_t)r * pw;
-            for (int wx = lane; wx < twords; wx += 32)
-                tile32[r * kTileW + wx] = __funnelshift_r(__ldg(srow + wx), __ldg(srow + wx + 1), sh);
-        }
         uint4* z = reinterpret_cast<uint4*>(sc);
         for (int i = tid; i < (L.sc_bytes >> 4); i += kFastThreads) z[i] = make_uint4(0, 0, 0, 0);
         for (int i = tid; i < L.mask_words; i += kFastThreads) mask[i] = 0u;
@@ -133,21 +135,24 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restr
             const int cx0 = cj * wcell, cx1 = min(cx0 + wcell, gw);
             xinfo[x] = (uint8_t)(cj | (x == cx0 ? 64 : 0) | (x == cx1 - 1 ? 128 : 0));
         }
-        if (tid == 0) s_nwork = 0;
     }
-    __syncthreads();
+    mbar_wait(&bar, 0);
+    __syncthreads();                                              // clears complete before any warp scores
 
     const int ini_th = plan->ini_th, lo_th = min(plan->ini_th, plan->min_th);
+    const unsigned ltmask = (1u << lane) - 1u;
 
-    // ---- phase 1: compass pretest, 4 pixels per thread (u16x2 SIMD) -> work list -----------------------------------
+    // ---- phase 1: compass pretest, 4 pixels per thread (u16x2 SIMD) -> this warp's work list -----------------------
+    int nwork = 0;
     {
         const unsigned k2 = (unsigned)(0x8000 - 257 - lo_th) * 0x00010001u;
-        const unsigned ltmask = (1u << lane) - 1u;
+        const int j0 = off >> 2, nquad = ((off + gw - 1) >> 2) - j0 + 1;       // aligned quads of tile columns covering the strip
         for (int py = wid; py < ch; py += kFastWarps) {
-            const uint32_t* rc = tile32 + (py + 3) * kTileW + 1;     // word of strip x = 0 in the centre row
+            const uint32_t* rc = tile32 + (py + 3) * kTileW + j0;              // centre-row word of the first quad
             for (int qb = 0; qb < nquad; qb += 32) {
                 const int xq = qb + lane;
                 unsigned p0 = 0, p1 = 0;                             // pass bits of pixels (0,1) and (2,3)
+                const int xs = 4 * (j0 + xq) - off;                  // strip x of the quad's first pixel (-3 .. gw-1)
                 if (xq < nquad) {
                     const unsigned cw = rc[xq], cl = rc[xq - 1], cr = rc[xq + 1];
                     const unsigned up = rc[xq - 3 * kTileW], dn = rc[xq + 3 * kTileW];
@@ -157,37 +162,33 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restr
                                       __byte_perm(rt, 0, 0x4140), __byte_perm(lf, 0, 0x4140), k2);
                     p1 = pretest_pair(__byte_perm(cw, 0, 0x4342), __byte_perm(dn, 0, 0x4342), __byte_perm(up, 0, 0x4342),
                                       __byte_perm(rt, 0, 0x4342), __byte_perm(lf, 0, 0x4342), k2);
-                    const int rem = gw - 4 * xq;                     // pixels of this quad inside the strip (tail quad)
-                    if (rem < 4) {
-                        if (rem < 2) p0 &= 0x8000u;
-                        if (rem < 3) p1 = 0;
-                        else p1 &= 0x8000u;
+                    if (xs < 0 || xs + 3 >= gw) {                    // first / last quad: drop the pixels outside the strip
+                        if ((unsigned)xs >= (unsigned)gw) p0 &= ~0x8000u;
+                        if ((unsigned)(xs + 1) >= (unsigned)gw) p0 &= 0x8000u;
+                        if ((unsigned)(xs + 2) >= (unsigned)gw) p1 &= ~0x8000u;
+                        if ((unsigned)(xs + 3) >= (unsigned)gw) p1 &= 0x8000u;
                     }
                 }
                 const unsigned b0 = __ballot_sync(0xffffffffu, p0 & 0x8000u), b1 = __ballot_sync(0xffffffffu, p0 >> 31);
                 const unsigned b2 = __ballot_sync(0xffffffffu, p1 & 0x8000u), b3 = __ballot_sync(0xffffffffu, p1 >> 31);
-                if (b0 | b1 | b2 | b3) {
-                    const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s_nwork, n0 + n1 + n2 + n3);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    const unsigned ent = (unsigned)((py << 8) | (4 * xq));
-                    if (p0 & 0x8000u) work[base + __popc(b0 & ltmask)] = (uint16_t)ent;
-                    if (p0 >> 31) work[base + n0 + __popc(b1 & ltmask)] = (uint16_t)(ent + 1);
-                    if (p1 & 0x8000u) work[base + n0 + n1 + __popc(b2 & ltmask)] = (uint16_t)(ent + 2);
-                    if (p1 >> 31) work[base + n0 + n1 + n2 + __popc(b3 & ltmask)] = (uint16_t)(ent + 3);
-                }
+                const unsigned ent = (unsigned)((py << 8) + xs);
+                const int o1 = nwork + __popc(b0), o2 = o1 + __popc(b1), o3 = o2 + __popc(b2);
+                if (p0 & 0x8000u) work[nwork + __popc(b0 & ltmask)] = (uint16_t)ent;
+                if (p0 >> 31) work[o1 + __popc(b1 & ltmask)] = (uint16_t)(ent + 1);
+                if (p1 & 0x8000u) work[o2 + __popc(b2 & ltmask)] = (uint16_t)(ent + 2);
+                if (p1 >> 31) work[o3 + __popc(b3 & ltmask)] = (uint16_t)(ent + 3);
+                nwork = o3 + __popc(b3);
             }
         }
     }
-    __syncthreads();
-    const int nwork = s_nwork;
+    __syncwarp();
 
-    // ---- phase 2: exact score of the listed pixels -----------------------------------------------------------------
-    for (int i = tid; i < nwork; i += kFastThreads) {
+    // ---- phase 2: exact score of the listed pixels (each warp scores its own list) ---------------------------------
+    const uint8_t* t0 = tile + 3 * kTilePitch + off;              // strip pixel (0,0)
+    for (int i = lane; i < nwork; i += 32) {
         const int e = work[i];
         const int px = e & 255, py = e >> 8;
-        const uint8_t* c = tile + (py + 3) * kTilePitch + px + 4;
+        const uint8_t* c = t0 + py * kTilePitch + px;
         const unsigned cv = c[0];
         // v = {I - c + 256 (low half), c - I + 256 (high half)}: both halves in [1, 511], no carry between them
         const unsigned K = (256u - cv) + ((cv + 256u) << 16);
@@ -211,11 +212,11 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restr
         const int m = max((int)(M & 0xFFFFu), (int)(M >> 16)) - 256;
         if (m > lo_th) sc[(py + 1) * kScorePitch + px + 1] = (uint8_t)(m - 1);
     }
-    __syncthreads();
+    __syncthreads();                                              // neighbours' scores come from other warps
 
     // ---- phase 3: strict 8-neighbour NMS inside the cell -> row masks -----------------------------------------------
     uint32_t* mask_ini = mask + ncell * ch * 2;
-    for (int i = tid; i < nwork; i += kFastThreads) {
+    for (int i = lane; i < nwork; i += 32) {
         const int e = work[i];
         const int px = e & 255, py = e >> 8;
         const uint8_t* q = sc + (py + 1) * kScorePitch + px + 1;
@@ -266,16 +267,16 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restr
     }
 }
 
-int launch_fast_cells(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st) {
+int launch_fast_cells(const Plan& hp, const Plan* dp, const Workspace& ws, const TmaMaps& maps, int nimg, cudaStream_t st) {
     size_t smem = 0;
     for (int l = 0; l < hp.nlevels; ++l) {
         const LevelGeom& g = hp.lv[l];
-        smem = std::max(smem, (size_t)fast_layout(g.gcells * g.wcell, g.hcell, g.gcells).total);
+        smem = std::max(smem, (size_t)fast_layout(g.gcells * g.wcell, g.hcell, g.hcell, g.gcells).total);
     }
     if (smem > 200 * 1024) { set_error("FAST strip too large for shared memory"); return FBE_E_UNSUPPORTED; }
     if (smem > 48 * 1024) FBE_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(hp.ngroups_total, nimg);
-    k_fast_cells<<<grid, kFastThreads, smem, st>>>(dp, ws);
+    k_fast_cells<<<grid, kFastThreads, smem, st>>>(dp, ws, maps);
     count_launch();
     FBE_CUDA(cudaGetLastError());
     return FBE_OK;

@@ -15,7 +15,7 @@ constexpr int kPatch = 31;       // PATCH_SIZE (:72)
 constexpr int kMaxDim = 4095;    // x,y packed in 12 bits each
 constexpr int kMaxGridCells = 64 * 48;
 constexpr int kBlurTW = 128, kBlurTH = 32;   // blur output tile
-constexpr int kFastGroupW = 256; // widest run of FAST cells (pixels) one CTA of the FAST kernel owns
+constexpr int kFastGroupW = 224; // widest run of FAST cells (pixels) one CTA of the FAST kernel owns
 
 // packed candidate / key: score[31:24] | y[23:12] | x[11:0], level pixel coordinates
 __host__ __device__ inline uint32_t pack_key(int x, int y, int s) { return ((uint32_t)s << 24) | ((uint32_t)y << 12) | (uint32_t)x; }
@@ -112,9 +112,9 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
 
 // ---- kernel launchers (each enqueues on `st`) ---------------------------------------------------
 int launch_pyramid(const Plan& hp, const Plan* dp, const Workspace& ws, const ResizeTab* d_tab, int nimg, cudaStream_t st);
-int launch_fast_cells(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
-int launch_octree(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
 struct TmaMaps;
+int launch_fast_cells(const Plan& hp, const Plan* dp, const Workspace& ws, const TmaMaps& maps, int nimg, cudaStream_t st);
+int launch_octree(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
 int launch_blur(const Plan& hp, const Plan* dp, const Workspace& ws, const TmaMaps& maps, int nimg, cudaStream_t st);
 int launch_describe(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
 int launch_grid(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
@@ -138,7 +138,8 @@ struct ExtractorCore {
     Plan hplan;            // valid when plan_rows/cols set
     Plan* dplan = nullptr;
     ResizeTab* dtab = nullptr;
-    TmaMaps* blur_maps = nullptr;   // host copy of the per-level tensor maps over ws.pyr (passed by value at launch)
+    TmaMaps* blur_maps = nullptr;   // host copies of the per-level tensor maps over ws.pyr (passed by value at launch)
+    TmaMaps* fast_maps = nullptr;   // box = 256 x (hcell + 6)
     int plan_rows = 0, plan_cols = 0;
     Workspace ws;
     uint8_t* d_in = nullptr;      // staging for host-API calls
