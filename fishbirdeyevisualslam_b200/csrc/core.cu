@@ -45,6 +45,7 @@ int ExtractorCore::free_ws() {
     cudaFree(ws.status); cudaFree(dplan); cudaFree(dtab);
     delete blur_maps; blur_maps = nullptr;
     delete fast_maps; fast_maps = nullptr;
+    delete rs_maps; rs_maps = nullptr;
     std::memset(&ws, 0, sizeof(ws));
     dplan = nullptr; dtab = nullptr; have_ws = false;
     return FBE_OK;
@@ -102,6 +103,8 @@ int ExtractorCore::ensure_plan(int rows, int cols) {
     FBE_CUDA(cudaMalloc(&ws.blur, B * hplan.pyr_bytes));
     blur_maps = new TmaMaps();
     fast_maps = new TmaMaps();
+    rs_maps = new TmaMaps();
+    std::memset(rs_maps, 0, sizeof(TmaMaps));
     std::memset(blur_maps, 0, sizeof(TmaMaps));
     std::memset(fast_maps, 0, sizeof(TmaMaps));
     for (int l = 0; l < hplan.nlevels; ++l) {
@@ -110,6 +113,11 @@ int ExtractorCore::ensure_plan(int rows, int cols) {
         if (rc != FBE_OK) return rc;
         rc = tma_encode_level(&fast_maps->m[l], ws.pyr + g.img_off, g.pitch, g.ph, (int)B, (size_t)hplan.pyr_bytes, 256, g.hcell + 6);
         if (rc != FBE_OK) return rc;
+        if (l > 0 && g.rs_bw > 0) {
+            const LevelGeom& sg = hplan.lv[l - 1];
+            rc = tma_encode_level(&rs_maps->m[l], ws.pyr + sg.img_off, sg.pitch, sg.ph, (int)B, (size_t)hplan.pyr_bytes, g.rs_bw, g.rs_bh);
+            if (rc != FBE_OK) return rc;
+        }
     }
     FBE_CUDA(cudaMemset(ws.blur, 0, B * hplan.pyr_bytes));
     FBE_CUDA(cudaMalloc(&ws.cell_count, B * hplan.ncells_total * sizeof(int)));
@@ -176,7 +184,7 @@ int ExtractorCore::run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, in
         }                                                                                                \
     } while (0)
     FBE_MARK(0, stream);
-    if ((rc = launch_pyramid(hplan, dplan, v, dtab, nimg, stream)) != FBE_OK) return rc;
+    if ((rc = launch_pyramid(hplan, dplan, v, dtab, *rs_maps, nimg, stream)) != FBE_OK) return rc;
     FBE_MARK(1, stream);
     FBE_STAGE("pyramid", stream);
     // blur depends only on the pyramid: run it on the side stream while FAST + octree proceed

@@ -15,6 +15,8 @@ constexpr int kPatch = 31;       // PATCH_SIZE (:72)
 constexpr int kMaxDim = 4095;    // x,y packed in 12 bits each
 constexpr int kMaxGridCells = 64 * 48;
 constexpr int kBlurTW = 128, kBlurTH = 32;   // blur output tile
+constexpr int kRsTW = 128, kRsTH = 64;       // resize output tile (padded destination coordinates)
+constexpr int kRsMaxTx = (kMaxDim + 38 + 15) / kRsTW + 2, kRsMaxTy = (kMaxDim + 38) / kRsTH + 2;
 constexpr int kFastGroupW = 224; // widest run of FAST cells (pixels) one CTA of the FAST kernel owns
 
 // packed candidate / key: score[31:24] | y[23:12] | x[11:0], level pixel coordinates
@@ -37,6 +39,7 @@ struct LevelGeom {
     int ngrp;            // groups per cell row
     int grp_base;        // first group of this level in the per-image group numbering
     int blur_ntx, blur_nty, blur_base;   // blur kernel: 128x32 output tiles in padded coordinates
+    int rs_bw, rs_bh;    // resize kernel: TMA box (source tile) of a 128x64 output tile; rs_bw == 0 -> direct-global kernel
     int slot_base;       // first slot (u32 units) of this level in the per-slot slot array
     int key_cap;         // capacity of the compacted key array of this level ( = ncells*cell_cap )
     int nfeat;           // mnFeaturesPerLevel[level]
@@ -68,6 +71,9 @@ struct Plan {
     float grid_min_x, grid_min_y, grid_inv_w, grid_inv_h;
     int grid_cols, grid_rows;
     LevelGeom lv[FBE_MAX_LEVELS];
+    // resize kernel: first source column (16-byte aligned) / row of every output tile column / tile row of a level
+    short rs_x0[FBE_MAX_LEVELS][kRsMaxTx];
+    short rs_y0[FBE_MAX_LEVELS][kRsMaxTy];
 };
 
 // Per-call device workspace pointers (all arrays are [max_batch] slabs, slot-major).
@@ -110,9 +116,9 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
         }                                                                                                \
     } while (0)
 
-// ---- kernel launchers (each enqueues on `st`) ---------------------------------------------------
-int launch_pyramid(const Plan& hp, const Plan* dp, const Workspace& ws, const ResizeTab* d_tab, int nimg, cudaStream_t st);
 struct TmaMaps;
+// ---- kernel launchers (each enqueues on `st`) ---------------------------------------------------
+int launch_pyramid(const Plan& hp, const Plan* dp, const Workspace& ws, const ResizeTab* d_tab, const TmaMaps& rs_maps, int nimg, cudaStream_t st);
 int launch_fast_cells(const Plan& hp, const Plan* dp, const Workspace& ws, const TmaMaps& maps, int nimg, cudaStream_t st);
 int launch_octree(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
 int launch_blur(const Plan& hp, const Plan* dp, const Workspace& ws, const TmaMaps& maps, int nimg, cudaStream_t st);
@@ -140,6 +146,7 @@ struct ExtractorCore {
     ResizeTab* dtab = nullptr;
     TmaMaps* blur_maps = nullptr;   // host copies of the per-level tensor maps over ws.pyr (passed by value at launch)
     TmaMaps* fast_maps = nullptr;   // box = 256 x (hcell + 6)
+    TmaMaps* rs_maps = nullptr;     // m[l] = level l-1 as the SOURCE of level l, box = rs_bw x rs_bh
     int plan_rows = 0, plan_cols = 0;
     Workspace ws;
     uint8_t* d_in = nullptr;      // staging for host-API calls

@@ -159,8 +159,32 @@ int build_plan(const fbe_extractor_cfg& cfg, const std::vector<float>& scale, co
                 t.ofs += kEdge;
                 tabs.push_back(t);
             }
+            // source tile of every 128x64 output tile (resize kernel stages it with TMA)
+            int bw = 0, bh = 0;
+            const int ntx = (g.pitch + kRsTW - 1) / kRsTW, nty = (g.ph + kRsTH - 1) / kRsTH;
+            for (int tx = 0; tx < ntx; ++tx) {
+                int lo = 1 << 30, hi = -1;
+                for (int x = tx * kRsTW; x < std::min((tx + 1) * kRsTW, g.pitch); ++x) {
+                    lo = std::min(lo, tabs[g.tabx_off + x].ofs); hi = std::max(hi, tabs[g.tabx_off + x].ofs);
+                }
+                lo &= ~15;
+                p.rs_x0[l][tx] = (short)lo;
+                bw = std::max(bw, hi + 2 - lo);
+            }
+            for (int ty = 0; ty < nty; ++ty) {
+                int lo = 1 << 30, hi = -1;
+                for (int y = ty * kRsTH; y < std::min((ty + 1) * kRsTH, g.ph); ++y) {
+                    lo = std::min(lo, tabs[g.taby_off + y].ofs); hi = std::max(hi, tabs[g.taby_off + y].ofs);
+                }
+                p.rs_y0[l][ty] = (short)lo;
+                bh = std::max(bh, hi + 2 - lo);
+            }
+            bw = (bw + 15) & ~15;
+            if (bw <= 256 && bh <= 256 && (size_t)bw * bh <= 64 * 1024) { g.rs_bw = bw; g.rs_bh = bh; }
+            else g.rs_bw = g.rs_bh = 0;       // scale factor too large for one TMA box: direct-global kernel
         } else {
             g.tabx_off = g.taby_off = 0;
+            g.rs_bw = g.rs_bh = 0;
         }
     }
     p.pyr_bytes = img_off;

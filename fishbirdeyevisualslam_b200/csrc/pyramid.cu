@@ -5,6 +5,7 @@
 //              resize + copyMakeBorder collapse into one pass and one aligned 4-byte store per thread.
 // HBM-bound integer work: each thread produces 4 horizontally adjacent bytes; rows are 16-byte aligned.
 #include "fbe_internal.cuh"
+#include "tma.cuh"
 
 namespace fbe {
 
@@ -16,25 +17,37 @@ __device__ __forceinline__ int reflect101_dev(int p, int len) {
     return p;
 }
 
-__global__ void __launch_bounds__(256) k_level0(const Plan* __restrict__ plan, Workspace ws) {
-    const LevelGeom g = plan->lv[0];
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y;
+// Level 0: a thread writes 16 padded bytes (one 128-bit store).  Interior chunks come from one 32-bit + one 128-bit
+// aligned load of the source row, realigned by a funnel shift (destination column d holds source column d - 19, i.e.
+// the source is displaced by 3 bytes modulo 4); chunks touching the reflected frame, and sources whose base / pitch is
+// not 16-byte aligned, take the per-byte path.
+__global__ void __launch_bounds__(256) k_level0(const Plan* __restrict__ plan, Workspace ws, int aligned16) {
+    const LevelGeom& g = plan->lv[0];
+    const int c16 = (blockIdx.x * 32 + threadIdx.x) * 16;
+    const int y = blockIdx.y * 8 + threadIdx.y;
     const int b = blockIdx.z;
-    if (x4 >= g.pitch) return;
-    const uint8_t* src = ws.in + (size_t)b * ws.in_slot_stride;
-    const int ys = reflect101_dev(y - kEdge, g.h);
-    const uint8_t* row = src + (size_t)ys * ws.in_pitch;
-    uint32_t v = 0;
+    const int w = g.w, pitch = g.pitch;
+    if (c16 >= pitch || y >= g.ph) return;
+    const uint8_t* row = ws.in + (size_t)b * ws.in_slot_stride + (size_t)reflect101_dev(y - kEdge, g.h) * ws.in_pitch;
+    uint4 o;
+    if (aligned16 && c16 >= 32 && c16 <= w) {          // source bytes c16-20 .. c16-1 all inside the row
+        const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(row + c16 - 20));
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(row + c16 - 16));
+        o.x = __funnelshift_r(w0, q.x, 8); o.y = __funnelshift_r(q.x, q.y, 8);
+        o.z = __funnelshift_r(q.y, q.z, 8); o.w = __funnelshift_r(q.z, q.w, 8);
+    } else {
+        uint32_t v[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int x = x4 + i;
-        uint32_t px = 0;
-        if (x < g.w + 2 * kEdge) px = row[reflect101_dev(x - kEdge, g.w)];
-        v |= px << (8 * i);
+        for (int i = 0; i < 16; ++i) {
+            const int x = c16 + i;
+            uint32_t px = 0;
+            if (x < w + 2 * kEdge) px = row[reflect101_dev(x - kEdge, w)];
+            v[i >> 2] |= px << (8 * (i & 3));
+        }
+        o = make_uint4(v[0], v[1], v[2], v[3]);
     }
     uint8_t* dst = ws.pyr + (size_t)b * plan->pyr_bytes + g.img_off;
-    *reinterpret_cast<uint32_t*>(dst + (size_t)y * g.pitch + x4) = v;
+    *reinterpret_cast<uint4*>(dst + (size_t)y * pitch + c16) = o;
 }
 
 // One CTA = 128 output columns x 64 output rows of one padded level; a thread owns 4 adjacent columns and walks 8 rows.
@@ -95,17 +108,87 @@ __global__ void __launch_bounds__(256) k_resize(const Plan* __restrict__ plan, W
     }
 }
 
-int launch_pyramid(const Plan& hp, const Plan* dp, const Workspace& ws, const ResizeTab* d_tab, int nimg, cudaStream_t st) {
+// TMA-staged variant (used whenever the source tile of a 128x64 output tile fits one TMA box, i.e. for every scale
+// factor up to ~1.8): the source tile lands in shared memory, so a source byte costs one LDS with a 32-bit address
+// instead of a 64-bit global address computation; (b*r) >> 16 is a single IMAD.HI on pre-shifted row weights, and the
+// saturation of the reference formula is provably never reached (weights sum to 2047..2049), so the
+// combine is 2 IMAD.HI + IADD3 + SHF per pixel.
+__global__ void __launch_bounds__(256) k_resize_tma(const Plan* __restrict__ plan, Workspace ws, const ResizeTab* __restrict__ tab,
+                                                    int level, const __grid_constant__ CUtensorMap map) {
+    extern __shared__ __align__(128) uint8_t rs_tile[];
+    __shared__ __align__(8) uint64_t bar;
+    const LevelGeom& g = plan->lv[level];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.z;
+    const int bw = g.rs_bw, bh = g.rs_bh;
+    const int x0s = plan->rs_x0[level][blockIdx.x], y0s = plan->rs_y0[level][blockIdx.y];
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, (uint32_t)(bw * bh));
+        tma_load_3d(rs_tile, &map, &bar, x0s, y0s, ws.slot0 + b);
+    }
+    const int x4 = (blockIdx.x * 32 + lane) * 4;
+    const int pitch = g.pitch, ph = g.ph;
+    const bool active = x4 < pitch;
+    int col[4] = {0, 0, 0, 0}, a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+    if (active) {
+        const uint4* tx4 = reinterpret_cast<const uint4*>(tab + g.tabx_off + x4);      // 4 column entries = 32 bytes
+        const uint4 ta = __ldg(tx4), tb = __ldg(tx4 + 1);
+        col[0] = (int)ta.x - x0s; col[1] = (int)ta.z - x0s; col[2] = (int)tb.x - x0s; col[3] = (int)tb.z - x0s;
+        a0[0] = (int)(short)(ta.y & 0xFFFFu); a0[1] = (int)(short)(ta.w & 0xFFFFu); a0[2] = (int)(short)(tb.y & 0xFFFFu); a0[3] = (int)(short)(tb.w & 0xFFFFu);
+        a1[0] = (int)ta.y >> 16; a1[1] = (int)ta.w >> 16; a1[2] = (int)tb.y >> 16; a1[3] = (int)tb.w >> 16;
+    }
+    mbar_wait(&bar, 0);
+    if (!active) return;
+    uint8_t* dst = ws.pyr + (size_t)b * plan->pyr_bytes + g.img_off + x4;
+    const ResizeTab* ty = tab + g.taby_off;
+    int y = blockIdx.y * kRsTH + wid * kRsRowsPerWarp;
+    const int yend = min(y + kRsRowsPerWarp, ph);
+    int cur = -4;                 // source row (tile coordinates) whose interpolation sits in r_lo (r_hi holds cur + 1)
+    unsigned r_lo[4], r_hi[4];
+    auto hrow = [&](int sy, unsigned (&r)[4]) {
+        const uint8_t* S = rs_tile + sy * bw;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[i] = (unsigned)((int)S[col[i]] * a0[i] + (int)S[col[i] + 1] * a1[i]) >> 4;
+    };
+    for (; y < yend; ++y) {
+        const ResizeTab t = ty[y];
+        const int sy = t.ofs - y0s;
+        if (sy == cur + 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r_lo[i] = r_hi[i];
+            hrow(sy + 1, r_hi);      // row sy+1 exists in the padded source (frame), weight 0 when clamped
+        } else if (sy != cur) {
+            hrow(sy, r_lo);
+            hrow(sy + 1, r_hi);
+        }
+        cur = sy;
+        const unsigned b0 = (unsigned)(int)t.a0 << 16, b1 = (unsigned)(int)t.a1 << 16;     // weights are in [0, 2048]
+        unsigned v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = (__umulhi(b0, r_lo[i]) + __umulhi(b1, r_hi[i]) + 2u) >> 2;   // <= 255, see above
+        *reinterpret_cast<uint32_t*>(dst + (size_t)y * pitch) = v[0] + (v[1] << 8) + (v[2] << 16) + (v[3] << 24);
+    }
+}
+
+int launch_pyramid(const Plan& hp, const Plan* dp, const Workspace& ws, const ResizeTab* d_tab, const TmaMaps& rs_maps, int nimg,
+                   cudaStream_t st) {
     for (int l = 0; l < hp.nlevels; ++l) {
         const LevelGeom& g = hp.lv[l];
-        dim3 block(64);
-        if (g.pitch / 4 > 64) block.x = 128;
-        if (g.pitch / 4 > 128) block.x = 256;
-        dim3 grid((g.pitch / 4 + block.x - 1) / block.x, g.ph, nimg);
-        if (l == 0) k_level0<<<grid, block, 0, st>>>(dp, ws);
-        else {
-            dim3 rgrid((g.pitch / 4 + 31) / 32, (g.ph + kRsRowsPerWarp * kRsWarps - 1) / (kRsRowsPerWarp * kRsWarps), nimg);
-            k_resize<<<rgrid, 256, 0, st>>>(dp, ws, d_tab, l);
+        if (l == 0) {
+            const int aligned16 = ((reinterpret_cast<uintptr_t>(ws.in) | (uintptr_t)ws.in_pitch | (uintptr_t)ws.in_slot_stride) & 15) == 0;
+            dim3 grid((g.pitch / 16 + 31) / 32, (g.ph + 7) / 8, nimg);
+            k_level0<<<grid, dim3(32, 8), 0, st>>>(dp, ws, aligned16);
+        } else {
+            dim3 rgrid((g.pitch + kRsTW - 1) / kRsTW, (g.ph + kRsTH - 1) / kRsTH, nimg);
+            if (g.rs_bw > 0) {
+                const size_t smem = (size_t)g.rs_bw * g.rs_bh;
+                if (smem > 48 * 1024) FBE_CUDA(cudaFuncSetAttribute(k_resize_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                k_resize_tma<<<rgrid, 256, smem, st>>>(dp, ws, d_tab, l, rs_maps.m[l]);
+            } else {
+                k_resize<<<rgrid, 256, 0, st>>>(dp, ws, d_tab, l);
+            }
         }
         count_launch();
     }
