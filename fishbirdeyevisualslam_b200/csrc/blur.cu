@@ -32,12 +32,9 @@ __global__ void __launch_bounds__(256) k_blur(const Plan* __restrict__ plan, Wor
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
-    int t = blockIdx.x, l = 0;
-    const int nl = plan->nlevels;
-    while (l + 1 < nl && t >= plan->lv[l + 1].blur_base) ++l;
+    const uint32_t te = __ldg(ws.blur_tab + blockIdx.x);
+    const int l = (int)(te >> 24), ty = (int)((te >> 12) & 0xFFFu), tx = (int)(te & 0xFFFu);
     const LevelGeom& g = plan->lv[l];
-    t -= g.blur_base;
-    const int ty = t / g.blur_ntx, tx = t - ty * g.blur_ntx;
     const int px0 = tx * kBlurTW;                    // padded column of the tile's first output
     const int y0 = ty * kBlurTH;                     // level row of the tile's first output
 

@@ -43,6 +43,7 @@ int ExtractorCore::free_ws() {
     cudaFree(ws.key_node); cudaFree(ws.oct_scratch); cudaFree(ws.sel); cudaFree(ws.level_n); cudaFree(ws.out_kps);
     cudaFree(ws.out_desc); cudaFree(ws.out_n); cudaFree(ws.out_cell); cudaFree(ws.grid_start); cudaFree(ws.grid_items);
     cudaFree(ws.status); cudaFree(dplan); cudaFree(dtab);
+    cudaFree(const_cast<uint32_t*>(ws.fast_tab)); cudaFree(const_cast<uint32_t*>(ws.blur_tab));
     delete blur_maps; blur_maps = nullptr;
     delete fast_maps; fast_maps = nullptr;
     delete rs_maps; rs_maps = nullptr;
@@ -139,6 +140,22 @@ int ExtractorCore::ensure_plan(int rows, int cols) {
     FBE_CUDA(cudaMalloc(&ws.grid_items, Bo * hplan.kp_cap_total * sizeof(int)));
     FBE_CUDA(cudaMalloc(&ws.status, B * sizeof(int)));
     FBE_CUDA(cudaMemset(ws.status, 0, B * sizeof(int)));
+    {
+        std::vector<uint32_t> ft, bt;
+        for (int l = 0; l < hplan.nlevels; ++l) {
+            const LevelGeom& g = hplan.lv[l];
+            for (int ci = 0; ci < g.nrows; ++ci)
+                for (int gj = 0; gj < g.ngrp; ++gj) ft.push_back(((uint32_t)l << 24) | ((uint32_t)ci << 12) | (uint32_t)gj);
+            for (int ty = 0; ty < g.blur_nty; ++ty)
+                for (int tx = 0; tx < g.blur_ntx; ++tx) bt.push_back(((uint32_t)l << 24) | ((uint32_t)ty << 12) | (uint32_t)tx);
+        }
+        uint32_t *dft = nullptr, *dbt = nullptr;
+        FBE_CUDA(cudaMalloc(&dft, ft.size() * 4));
+        FBE_CUDA(cudaMalloc(&dbt, bt.size() * 4));
+        FBE_CUDA(cudaMemcpy(dft, ft.data(), ft.size() * 4, cudaMemcpyHostToDevice));
+        FBE_CUDA(cudaMemcpy(dbt, bt.data(), bt.size() * 4, cudaMemcpyHostToDevice));
+        ws.fast_tab = dft; ws.blur_tab = dbt;
+    }
     plan_rows = rows; plan_cols = cols; have_ws = true;
     return FBE_OK;
 }

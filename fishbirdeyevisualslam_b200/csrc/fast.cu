@@ -88,13 +88,10 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restr
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int b = blockIdx.y;
-    int gid = blockIdx.x, l = 0;
-    const int nl = plan->nlevels;
-    while (l + 1 < nl && gid >= plan->lv[l + 1].grp_base) ++l;
+    const uint32_t te = __ldg(ws.fast_tab + blockIdx.x);
+    const int l = (int)(te >> 24), ci = (int)((te >> 12) & 0xFFFu), gj = (int)(te & 0xFFFu);
     const LevelGeom& g = plan->lv[l];
-    gid -= g.grp_base;
-    const int ngrp = g.ngrp, wcell = g.wcell, hcell = g.hcell, ncols = g.ncols;
-    const int ci = gid / ngrp, gj = gid - ci * ngrp;
+    const int wcell = g.wcell, hcell = g.hcell, ncols = g.ncols;
     const int cj0 = gj * g.gcells, ncell = min(g.gcells, ncols - cj0);
 
     // detection region of the strip in level coordinates
@@ -147,38 +144,44 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restr
     {
         const unsigned k2 = (unsigned)(0x8000 - 257 - lo_th) * 0x00010001u;
         const int j0 = off >> 2, nquad = ((off + gw - 1) >> 2) - j0 + 1;       // aligned quads of tile columns covering the strip
-        for (int py = wid; py < ch; py += kFastWarps) {
-            const uint32_t* rc = tile32 + (py + 3) * kTileW + j0;              // centre-row word of the first quad
-            for (int qb = 0; qb < nquad; qb += 32) {
-                const int xq = qb + lane;
-                unsigned p0 = 0, p1 = 0;                             // pass bits of pixels (0,1) and (2,3)
-                const int xs = 4 * (j0 + xq) - off;                  // strip x of the quad's first pixel (-3 .. gw-1)
-                if (xq < nquad) {
-                    const unsigned cw = rc[xq], cl = rc[xq - 1], cr = rc[xq + 1];
-                    const unsigned up = rc[xq - 3 * kTileW], dn = rc[xq + 3 * kTileW];
-                    const unsigned lf = __funnelshift_r(cl, cw, 8);   // x-3 .. x
-                    const unsigned rt = __funnelshift_r(cw, cr, 24);  // x+3 .. x+6
-                    p0 = pretest_pair(__byte_perm(cw, 0, 0x4140), __byte_perm(dn, 0, 0x4140), __byte_perm(up, 0, 0x4140),
-                                      __byte_perm(rt, 0, 0x4140), __byte_perm(lf, 0, 0x4140), k2);
-                    p1 = pretest_pair(__byte_perm(cw, 0, 0x4342), __byte_perm(dn, 0, 0x4342), __byte_perm(up, 0, 0x4342),
-                                      __byte_perm(rt, 0, 0x4342), __byte_perm(lf, 0, 0x4342), k2);
-                    if (xs < 0 || xs + 3 >= gw) {                    // first / last quad: drop the pixels outside the strip
-                        if ((unsigned)xs >= (unsigned)gw) p0 &= ~0x8000u;
-                        if ((unsigned)(xs + 1) >= (unsigned)gw) p0 &= 0x8000u;
-                        if ((unsigned)(xs + 2) >= (unsigned)gw) p1 &= ~0x8000u;
-                        if ((unsigned)(xs + 3) >= (unsigned)gw) p1 &= 0x8000u;
-                    }
+        // the warp's rows (py = wid, wid + 8, ...) are walked as ONE stream of quads, 32 per iteration, so that only the
+        // last iteration has idle lanes; t / nquad by multiplication (t < 512, nquad <= 64: exact with a 16-bit reciprocal)
+        const int nrows_w = (ch - wid + kFastWarps - 1) / kFastWarps;
+        const int ntask = nrows_w * nquad;
+        const unsigned recip = 65536u / (unsigned)nquad + 1u;
+        for (int tb = 0; tb < ntask; tb += 32) {
+            const int t = tb + lane;
+            const int rl = (int)(((unsigned)t * recip) >> 16);
+            const int xq = t - rl * nquad;
+            const int py = wid + kFastWarps * rl;
+            unsigned p0 = 0, p1 = 0;                             // pass bits of pixels (0,1) and (2,3)
+            const int xs = 4 * (j0 + xq) - off;                  // strip x of the quad's first pixel (-3 .. gw-1)
+            if (t < ntask) {
+                const uint32_t* rc = tile32 + (py + 3) * kTileW + j0 + xq;      // centre-row word of the quad
+                const unsigned cw = rc[0], cl = rc[-1], cr = rc[1];
+                const unsigned up = rc[-3 * kTileW], dn = rc[3 * kTileW];
+                const unsigned lf = __funnelshift_r(cl, cw, 8);   // x-3 .. x
+                const unsigned rt = __funnelshift_r(cw, cr, 24);  // x+3 .. x+6
+                p0 = pretest_pair(__byte_perm(cw, 0, 0x4140), __byte_perm(dn, 0, 0x4140), __byte_perm(up, 0, 0x4140),
+                                  __byte_perm(rt, 0, 0x4140), __byte_perm(lf, 0, 0x4140), k2);
+                p1 = pretest_pair(__byte_perm(cw, 0, 0x4342), __byte_perm(dn, 0, 0x4342), __byte_perm(up, 0, 0x4342),
+                                  __byte_perm(rt, 0, 0x4342), __byte_perm(lf, 0, 0x4342), k2);
+                if (xs < 0 || xs + 3 >= gw) {                    // first / last quad: drop the pixels outside the strip
+                    if ((unsigned)xs >= (unsigned)gw) p0 &= ~0x8000u;
+                    if ((unsigned)(xs + 1) >= (unsigned)gw) p0 &= 0x8000u;
+                    if ((unsigned)(xs + 2) >= (unsigned)gw) p1 &= ~0x8000u;
+                    if ((unsigned)(xs + 3) >= (unsigned)gw) p1 &= 0x8000u;
                 }
-                const unsigned b0 = __ballot_sync(0xffffffffu, p0 & 0x8000u), b1 = __ballot_sync(0xffffffffu, p0 >> 31);
-                const unsigned b2 = __ballot_sync(0xffffffffu, p1 & 0x8000u), b3 = __ballot_sync(0xffffffffu, p1 >> 31);
-                const unsigned ent = (unsigned)((py << 8) + xs);
-                const int o1 = nwork + __popc(b0), o2 = o1 + __popc(b1), o3 = o2 + __popc(b2);
-                if (p0 & 0x8000u) work[nwork + __popc(b0 & ltmask)] = (uint16_t)ent;
-                if (p0 >> 31) work[o1 + __popc(b1 & ltmask)] = (uint16_t)(ent + 1);
-                if (p1 & 0x8000u) work[o2 + __popc(b2 & ltmask)] = (uint16_t)(ent + 2);
-                if (p1 >> 31) work[o3 + __popc(b3 & ltmask)] = (uint16_t)(ent + 3);
-                nwork = o3 + __popc(b3);
             }
+            const unsigned b0 = __ballot_sync(0xffffffffu, p0 & 0x8000u), b1 = __ballot_sync(0xffffffffu, p0 >> 31);
+            const unsigned b2 = __ballot_sync(0xffffffffu, p1 & 0x8000u), b3 = __ballot_sync(0xffffffffu, p1 >> 31);
+            const unsigned ent = (unsigned)((py << 8) + xs);
+            const int o1 = nwork + __popc(b0), o2 = o1 + __popc(b1), o3 = o2 + __popc(b2);
+            if (p0 & 0x8000u) work[nwork + __popc(b0 & ltmask)] = (uint16_t)ent;
+            if (p0 >> 31) work[o1 + __popc(b1 & ltmask)] = (uint16_t)(ent + 1);
+            if (p1 & 0x8000u) work[o2 + __popc(b2 & ltmask)] = (uint16_t)(ent + 2);
+            if (p1 >> 31) work[o3 + __popc(b3 & ltmask)] = (uint16_t)(ent + 3);
+            nwork = o3 + __popc(b3);
         }
     }
     __syncwarp();

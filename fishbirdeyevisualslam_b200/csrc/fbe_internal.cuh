@@ -98,6 +98,9 @@ struct Workspace {
     int* grid_start;       // [B][gcells+1]
     int* grid_items;       // [B][kp_cap_total]
     int* status;           // [B] error flags raised by kernels (capacity overflow ...)
+    // per-plan CTA tables (one 32-bit load instead of a dependent walk over the levels):
+    const uint32_t* fast_tab;   // [ngroups_total]   level << 24 | cell row << 12 | group in row
+    const uint32_t* blur_tab;   // [blur_tiles_total] level << 24 | tile row << 12 | tile column
 };
 
 struct ResizeTab { int ofs; short a0, a1; };   // 8 bytes per padded coordinate
