@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(ResolveArgs a, int 
         bool accept = false;
         switch (a.mode) {
             case kResolveInit: accept = bestDist <= FBE_TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, a.nn_ratio); break;
-            case kResolveLast: accept = bestDist <= FBE_TH_HIGH; break;
+            case kResolveLast: accept = bestDist <= (a.th_dist > 0 ? a.th_dist : FBE_TH_HIGH); break;
             case kResolveMap: {
                 accept = bestDist <= FBE_TH_HIGH;
                 if (accept) {
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(ResolveArgs a, int 
             if (init) {
                 if (a.matches12[qb + qi] >= 0) { a.matches12[qb + qi] = -1; ++dec; }
             } else {
-                a.cur_mp[tb + a.q_hit[qb + qi]] = -1;
+                a.cur_mp[tb + a.q_hit[qb + qi]] = -2;     // assigned by this call, then removed: the reference writes NULL
                 ++dec;
             }
         }

@@ -246,7 +246,7 @@ int fbe_bird_map_point_match(fbe_matcher* m, const float* mp_pix, const uint8_t*
 static int projection_search(fbe_matcher* m, int mode, const fbe_frame_view* cur, const std::vector<float4>& q,
                              const std::vector<int2>& lv, const uint8_t* qdesc, const fbe_keypoint* q_kps, int nq,
                              const uint8_t* cur_taken, const uint8_t* q_has_obs, const int* q_src, int check_ori,
-                             int32_t* cur_mp, int32_t* nmatches) {
+                             int32_t* cur_mp, int32_t* nmatches, int th_dist = 0) {
     const int nt = cur->n;
     FrameDev Cf;
     QueryDev qs;
@@ -262,7 +262,7 @@ static int projection_search(fbe_matcher* m, int mode, const fbe_frame_view* cur
     if (q_src) FBE_TRY(upload(m->i1, q_src, (size_t)nq * 4, m->stream));
     ResolveArgs a{};
     a.mode = mode; a.q_kps = q_kps ? m->fb.kps.as<fbe_keypoint>() : nullptr; a.q_src = q_src ? m->i1.as<int>() : nullptr;
-    a.q_has_obs = m->u1.as<uint8_t>(); a.nn_ratio = m->nn_ratio; a.check_ori = check_ori;
+    a.q_has_obs = m->u1.as<uint8_t>(); a.nn_ratio = m->nn_ratio; a.check_ori = check_ori; a.th_dist = th_dist;
     a.cur_mp = m->i0.as<int>(); a.q_bin = m->i3.as<int>(); a.q_hit = m->i4.as<int>();
     FBE_TRY(m->u0.ensure((size_t)nt));
     a.taken = m->u0.as<uint8_t>();
@@ -296,6 +296,48 @@ int fbe_search_by_projection_last(fbe_matcher* m, const fbe_frame_view* cur, con
     }
     return projection_search(m, kResolveLast, cur, q, lv, last_mp_desc, last_kps, n_last, cur_taken, last_has_obs, nullptr,
                              m->check_ori, cur_mp, nmatches);
+}
+
+// Shared body of the relocalisation and loop-closing SearchByProjection overloads: single best unmatched candidate in
+// th * scale[predicted level], levels [pl-1, pl+level_up], accepted below th_dist; every assignment blocks its keypoint.
+static int search_by_projection_kf(fbe_matcher* m, const fbe_frame_view* cur, const fbe_keypoint* q_kps, const float* proj,
+                                   const int32_t* level, const uint8_t* mp_desc, int32_t n_mp, const float* scale_factors,
+                                   int32_t nlevels, const uint8_t* cur_taken, float th, int th_dist, int level_up, int check_ori,
+                                   int32_t* cur_mp, int32_t* nmatches) {
+    if (!m || !cur || !nmatches || n_mp < 0 || !scale_factors || th_dist <= 0 || (cur->n > 0 && !cur_mp) ||
+        (n_mp > 0 && (!proj || !level || !mp_desc)) || (check_ori && n_mp > 0 && !q_kps)) return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(m->device));
+    *nmatches = 0;
+    for (int k = 0; k < cur->n; ++k) cur_mp[k] = -1;
+    if (n_mp == 0 || cur->n == 0) return FBE_OK;
+    std::vector<float4> q(n_mp);
+    std::vector<int2> lv(n_mp);
+    for (int i = 0; i < n_mp; ++i) {
+        const int pl = level[i];
+        if (pl < 0 || pl >= nlevels) return FBE_E_INVALID;
+        const bool skip = std::isnan(proj[2 * i]);
+        const float radius = th * scale_factors[pl];             // :1527 / :355
+        q[i] = make_float4(skip ? 0.f : proj[2 * i], skip ? 0.f : proj[2 * i + 1], skip ? -1.f : radius, 0.f);
+        lv[i] = make_int2(pl - 1, pl + level_up);
+    }
+    return projection_search(m, kResolveLast, cur, q, lv, mp_desc, check_ori ? q_kps : nullptr, n_mp, cur_taken, nullptr, nullptr,
+                             check_ori, cur_mp, nmatches, th_dist);
+}
+
+int fbe_search_by_projection_reloc(fbe_matcher* m, const fbe_frame_view* cur, const fbe_keypoint* kf_kps, const float* mp_proj,
+                                   const int32_t* mp_level, const uint8_t* mp_desc, int32_t n_mp, const float* scale_factors,
+                                   int32_t nlevels, const uint8_t* cur_taken, float th, int32_t orb_dist, int32_t* cur_mp,
+                                   int32_t* nmatches) {
+    if (!m) return FBE_E_INVALID;
+    return search_by_projection_kf(m, cur, kf_kps, mp_proj, mp_level, mp_desc, n_mp, scale_factors, nlevels, cur_taken, th, orb_dist,
+                                   1, m->check_ori, cur_mp, nmatches);
+}
+
+int fbe_search_by_projection_loop(fbe_matcher* m, const fbe_frame_view* kf, const float* mp_proj, const int32_t* mp_level,
+                                  const uint8_t* mp_desc, int32_t n_mp, const float* scale_factors, int32_t nlevels,
+                                  const uint8_t* kf_matched, int32_t th, int32_t* kf_mp, int32_t* nmatches) {
+    return search_by_projection_kf(m, kf, nullptr, mp_proj, mp_level, mp_desc, n_mp, scale_factors, nlevels, kf_matched, (float)th,
+                                   FBE_TH_LOW, 0, 0, kf_mp, nmatches);
 }
 
 int fbe_search_by_projection_map(fbe_matcher* m, const fbe_frame_view* cur, const float* scale_factors, int32_t nlevels,

@@ -45,6 +45,7 @@ struct ResolveArgs {
     const uint8_t* q_has_obs;    // LAST/MAP: assigned map point blocks its keypoint (NULL = all)
     float nn_ratio;
     int check_ori;
+    int th_dist;                 // LAST: acceptance bound (0 = TH_HIGH; reloc passes ORBdist, loop closing TH_LOW)
     // state / outputs
     int* matched_dist;           // INIT: [nb][t_stride] scratch (vMatchedDistance)
     int* match21;                // INIT: [nb][t_stride] scratch (vnMatches21)

@@ -1,8 +1,7 @@
 // Drop-in bodies for the ORBmatcher methods on the hot path.  This file is compiled INSIDE the reference tree in place
 // of the same-named method bodies of src/ORBmatcher.cc (see INTEGRATION.md for the exact patch); the class declaration
 // include/ORBmatcher.h is unchanged, so Tracking.cc / LocalMapping.cc / LoopClosing.cc call it as before.  Methods that
-// are not on the hot path (SearchForTriangulation, SearchBySim3, Fuse x2, the KF-KF SearchByBoW, the relocalisation and
-// loop-closing SearchByProjection overloads) keep the reference's own CPU code.
+// are not on the hot path (SearchForTriangulation, SearchBySim3, Fuse x2, the KF-KF SearchByBoW) keep the reference's own CPU code.
 //
 // It cannot be compiled in the build image of this repository (needs the reference's Frame.h/KeyFrame.h/MapPoint.h with
 // OpenCV, Eigen, DBoW2); the marshalling below is mirrored, field for field, by the Python host
@@ -14,6 +13,7 @@
 // filter of BirdMapPointMatch) is executed here exactly as the reference writes it.
 #include <cmath>
 #include <limits>
+#include <set>
 #include <vector>
 
 #include "Converter.h"
@@ -123,11 +123,113 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, 
                                   reinterpret_cast<const fbe_keypoint*>(LastFrame.mvKeysUn.data()), proj.data(), mpdesc.data(), n,
                                   CurrentFrame.mvScaleFactors.data(), (int)CurrentFrame.mvScaleFactors.size(), taken.data(),
                                   has_obs.data(), th, cur_mp.data(), &nmatches);
-    // pointer writes of :1431 and :1461; entries pruned by the orientation histogram come back as -1, which the
-    // reference turns into NULL only for keypoints it had just written -- identical here because cur_mp is -1
-    // everywhere except for assignments made by this call.
-    for (int k = 0; k < CurrentFrame.N; k++)
+    // pointer writes of :1431 and :1461: -2 marks keypoints assigned by this call and then removed by the orientation
+    // histogram, where the reference writes NULL whatever the keypoint held before
+    for (int k = 0; k < CurrentFrame.N; k++) {
         if (cur_mp[k] >= 0) CurrentFrame.mvpMapPoints[k] = LastFrame.mvpMapPoints[cur_mp[k]];
+        else if (cur_mp[k] == -2) CurrentFrame.mvpMapPoints[k] = static_cast<MapPoint*>(NULL);
+    }
+    return nmatches;
+}
+
+// src/ORBmatcher.cc:1473-1600 (relocalisation)
+int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th,
+                                   const int ORBdist) {
+    const cv::Mat Rcw = CurrentFrame.mTcw.rowRange(0, 3).colRange(0, 3);
+    const cv::Mat tcw = CurrentFrame.mTcw.rowRange(0, 3).col(3);
+    const cv::Mat Ow = -Rcw.t() * tcw;
+    const std::vector<MapPoint*> vpMPs = pKF->GetMapPointMatches();
+    const int n = (int)vpMPs.size();
+    std::vector<float> proj(2 * (size_t)n, std::numeric_limits<float>::quiet_NaN());
+    std::vector<int> level(n, 0);
+    std::vector<unsigned char> mpdesc(32 * (size_t)n, 0);
+    for (int i = 0; i < n; i++) {
+        MapPoint* pMP = vpMPs[i];
+        if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;
+        cv::Mat x3Dw = pMP->GetWorldPos();
+        cv::Mat x3Dc = Rcw * x3Dw + tcw;
+        const float xc = x3Dc.at<float>(0), yc = x3Dc.at<float>(1);
+        const float invzc = 1.0 / x3Dc.at<float>(2);
+        const float u = CurrentFrame.fx * xc * invzc + CurrentFrame.cx;
+        const float v = CurrentFrame.fy * yc * invzc + CurrentFrame.cy;
+        if (u < CurrentFrame.mnMinX || u > CurrentFrame.mnMaxX) continue;
+        if (v < CurrentFrame.mnMinY || v > CurrentFrame.mnMaxY) continue;
+        cv::Mat PO = x3Dw - Ow;
+        const float dist3D = cv::norm(PO);
+        if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+        level[i] = pMP->PredictScale(dist3D, &CurrentFrame);
+        proj[2 * i] = u; proj[2 * i + 1] = v;
+        copy_desc(pMP->GetDescriptor(), &mpdesc[32 * (size_t)i]);
+    }
+    std::vector<unsigned char> taken(CurrentFrame.N, 0);
+    for (int k = 0; k < CurrentFrame.N; k++)
+        if (CurrentFrame.mvpMapPoints[k]) taken[k] = 1;                 // :1541
+    std::vector<int> cur_mp(CurrentFrame.N, -1);
+    fbe_frame_view cv_ = front_view(CurrentFrame);
+    int nmatches = 0;
+    fbe_search_by_projection_reloc(matcher_for(mfNNratio, mbCheckOrientation), &cv_,
+                                   reinterpret_cast<const fbe_keypoint*>(pKF->mvKeysUn.data()), proj.data(), level.data(),
+                                   mpdesc.data(), n, CurrentFrame.mvScaleFactors.data(), (int)CurrentFrame.mvScaleFactors.size(),
+                                   taken.data(), th, ORBdist, cur_mp.data(), &nmatches);
+    for (int k = 0; k < CurrentFrame.N; k++) {
+        if (cur_mp[k] >= 0) CurrentFrame.mvpMapPoints[k] = vpMPs[cur_mp[k]];
+        else if (cur_mp[k] == -2) CurrentFrame.mvpMapPoints[k] = static_cast<MapPoint*>(NULL);
+    }
+    return nmatches;
+}
+
+// src/ORBmatcher.cc:291-404 (loop closing)
+int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints,
+                                   std::vector<MapPoint*>& vpMatched, int th) {
+    const float &fx = pKF->fx, &fy = pKF->fy, &cx = pKF->cx, &cy = pKF->cy;
+    cv::Mat sRcw = Scw.rowRange(0, 3).colRange(0, 3);
+    const float scw = sqrt(sRcw.row(0).dot(sRcw.row(0)));
+    cv::Mat Rcw = sRcw / scw;
+    cv::Mat tcw = Scw.rowRange(0, 3).col(3) / scw;
+    cv::Mat Ow = -Rcw.t() * tcw;
+    std::set<MapPoint*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+    spAlreadyFound.erase(static_cast<MapPoint*>(NULL));
+    const int n = (int)vpPoints.size();
+    std::vector<float> proj(2 * (size_t)n, std::numeric_limits<float>::quiet_NaN());
+    std::vector<int> level(n, 0);
+    std::vector<unsigned char> mpdesc(32 * (size_t)n, 0);
+    for (int i = 0; i < n; i++) {
+        MapPoint* pMP = vpPoints[i];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+        cv::Mat p3Dw = pMP->GetWorldPos();
+        cv::Mat p3Dc = Rcw * p3Dw + tcw;
+        if (p3Dc.at<float>(2) < 0.0) continue;
+        const float invz = 1 / p3Dc.at<float>(2);
+        const float x = p3Dc.at<float>(0) * invz, y = p3Dc.at<float>(1) * invz;
+        const float u = fx * x + cx, v = fy * y + cy;
+        if (!pKF->IsInImage(u, v)) continue;
+        cv::Mat PO = p3Dw - Ow;
+        const float dist = cv::norm(PO);
+        if (dist < pMP->GetMinDistanceInvariance() || dist > pMP->GetMaxDistanceInvariance()) continue;
+        cv::Mat Pn = pMP->GetNormal();
+        if (PO.dot(Pn) < 0.5 * dist) continue;
+        level[i] = pMP->PredictScale(dist, pKF);
+        proj[2 * i] = u; proj[2 * i + 1] = v;
+        copy_desc(pMP->GetDescriptor(), &mpdesc[32 * (size_t)i]);
+    }
+    const int N = (int)pKF->mvKeysUn.size();
+    std::vector<unsigned char> matched(N, 0);
+    for (int k = 0; k < N; k++)
+        if (vpMatched[k]) matched[k] = 1;                               // :371
+    std::vector<int> kf_mp(N, -1);
+    fbe_frame_view kv;
+    kv.kps = reinterpret_cast<const fbe_keypoint*>(pKF->mvKeysUn.data());
+    kv.desc = desc_ptr(pKF->mDescriptors);
+    kv.n = N;
+    kv.min_x = pKF->mnMinX; kv.min_y = pKF->mnMinY;
+    kv.inv_w = pKF->mfGridElementWidthInv; kv.inv_h = pKF->mfGridElementHeightInv;
+    kv.gcols = pKF->mnGridCols; kv.grows = pKF->mnGridRows;
+    int nmatches = 0;
+    fbe_search_by_projection_loop(matcher_for(mfNNratio, mbCheckOrientation), &kv, proj.data(), level.data(), mpdesc.data(), n,
+                                  pKF->mvScaleFactors.data(), (int)pKF->mvScaleFactors.size(), matched.data(), th, kf_mp.data(),
+                                  &nmatches);
+    for (int k = 0; k < N; k++)
+        if (kf_mp[k] >= 0) vpMatched[k] = vpPoints[kf_mp[k]];
     return nmatches;
 }
 

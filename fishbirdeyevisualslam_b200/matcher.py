@@ -183,6 +183,37 @@ class ORBmatcher:
                                                    None if ho is None else ptr(ho), C.c_float(th), ptr(cur_mp), C.byref(n)))
         return n.value, cur_mp[:F.N]
 
+    def SearchByProjectionReloc(self, CurrentFrame: Frame, kf_kps, mp_proj, mp_level, mp_desc, th: float, orb_dist: int, cur_taken=None):
+        """SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (relocalisation, ORBmatcher.cc:1473-1600) on
+        host-projected map points (NaN u = rejected) with their predicted levels."""
+        kf_kps = np.ascontiguousarray(kf_kps)
+        mp_proj = np.ascontiguousarray(mp_proj, np.float32)
+        mp_level = np.ascontiguousarray(mp_level, np.int32)
+        mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+        cur_mp = np.full(max(CurrentFrame.N, 1), -1, np.int32)
+        n = C.c_int32()
+        v = CurrentFrame.view()
+        sf = np.ascontiguousarray(CurrentFrame.scale_factors, np.float32)
+        tk = None if cur_taken is None else np.ascontiguousarray(cur_taken, np.uint8)
+        check(self._L.fbe_search_by_projection_reloc(self._h, C.byref(v), ptr(kf_kps), ptr(mp_proj), ptr(mp_level), ptr(mp_desc),
+                                                     len(mp_level), ptr(sf), len(sf), None if tk is None else ptr(tk), C.c_float(th),
+                                                     C.c_int32(orb_dist), ptr(cur_mp), C.byref(n)))
+        return n.value, cur_mp[:CurrentFrame.N]
+
+    def SearchByProjectionLoop(self, KF: Frame, mp_proj, mp_level, mp_desc, th: int, kf_matched=None):
+        """SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (loop closing, ORBmatcher.cc:291-404)."""
+        mp_proj = np.ascontiguousarray(mp_proj, np.float32)
+        mp_level = np.ascontiguousarray(mp_level, np.int32)
+        mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+        kf_mp = np.full(max(KF.N, 1), -1, np.int32)
+        n = C.c_int32()
+        v = KF.view()
+        sf = np.ascontiguousarray(KF.scale_factors, np.float32)
+        tk = None if kf_matched is None else np.ascontiguousarray(kf_matched, np.uint8)
+        check(self._L.fbe_search_by_projection_loop(self._h, C.byref(v), ptr(mp_proj), ptr(mp_level), ptr(mp_desc), len(mp_level),
+                                                    ptr(sf), len(sf), None if tk is None else ptr(tk), C.c_int32(th), ptr(kf_mp), C.byref(n)))
+        return n.value, kf_mp[:KF.N]
+
     def SearchByBoW(self, kf_kps, kf_desc, kf_has_mp, kf_featvec, F: Frame, f_featvec):
         """SearchByBoW(KeyFrame*, Frame&, matches).  Feature vectors: (node_ids[nn], start[nn+1], items).
         -> (nmatches, f_mp[int32 N] = key-frame keypoint index per frame keypoint or -1)."""

@@ -165,7 +165,8 @@ FBE_API int fbe_bird_map_point_match(fbe_matcher* m, const float* mp_pix, const 
  * (no map point, outlier, invzc < 0, outside the image bounds).  last_kps supplies octave and angle.
  * cur_taken[k] != 0 iff CurrentFrame.mvpMapPoints[k] has Observations()>0 on entry (NULL = none);
  * last_has_obs[i] != 0 iff that map point has Observations()>0, i.e. blocks its keypoint once assigned (NULL = all).
- * Output: cur_mp[k] = index i of the last-frame map point assigned to keypoint k, -1 none. */
+ * Output: cur_mp[k] = index i of the last-frame map point assigned to keypoint k, -1 untouched, -2 assigned by this call
+ * and then removed by the orientation check (the reference writes NULL there, whatever the keypoint held before). */
 FBE_API int fbe_search_by_projection_last(fbe_matcher* m, const fbe_frame_view* cur, const fbe_keypoint* last_kps,
                                           const float* last_proj, const uint8_t* last_mp_desc, int32_t n_last,
                                           const float* scale_factors, int32_t nlevels, const uint8_t* cur_taken,
@@ -179,6 +180,26 @@ FBE_API int fbe_search_by_projection_map(fbe_matcher* m, const fbe_frame_view* c
                                          const float* mp_viewcos, const uint8_t* mp_desc, int32_t n_mp,
                                          const uint8_t* cur_taken, const uint8_t* mp_has_obs, float th,
                                          int32_t* cur_mp, int32_t* nmatches);
+
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist),
+ * src/ORBmatcher.cc:1473-1600 (relocalisation).  The host shim keeps the reference's cv::Mat work: per key-frame map
+ * point (not bad, not already found) the projection (u,v) (:1496-1509; NaN u = rejected by the bounds or the
+ * min/max-distance test :1511-1521) and nPredictedLevel = MapPoint::PredictScale (src/MapPoint.cc:402-417).
+ * kf_kps[i] supplies pKF->mvKeysUn[i].angle for the rotation histogram.  cur_taken[k] != 0 iff
+ * CurrentFrame.mvpMapPoints[k] is non-NULL on entry.  Output: cur_mp[k] = index i of the assigned map point, -1 none. */
+FBE_API int fbe_search_by_projection_reloc(fbe_matcher* m, const fbe_frame_view* cur, const fbe_keypoint* kf_kps,
+                                           const float* mp_proj, const int32_t* mp_level, const uint8_t* mp_desc, int32_t n_mp,
+                                           const float* scale_factors, int32_t nlevels, const uint8_t* cur_taken, float th,
+                                           int32_t orb_dist, int32_t* cur_mp, int32_t* nmatches);
+
+/* ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched,
+ * int th), src/ORBmatcher.cc:291-404 (loop closing).  Host shim: Sim3 decomposition, projection, IsInImage, depth and
+ * viewing-angle rejections (:300-350; NaN u = rejected) and PredictScale.  kf: the key frame's mvKeysUn / descriptors /
+ * grid (KeyFrame::GetFeaturesInArea, src/KeyFrame.cc:901-940).  kf_matched[k] != 0 iff vpMatched[k] is non-NULL on entry.
+ * Accepts bestDist <= TH_LOW, levels [pl-1, pl], no orientation check.  Output: kf_mp[k] = index into vpPoints or -1. */
+FBE_API int fbe_search_by_projection_loop(fbe_matcher* m, const fbe_frame_view* kf, const float* mp_proj, const int32_t* mp_level,
+                                          const uint8_t* mp_desc, int32_t n_mp, const float* scale_factors, int32_t nlevels,
+                                          const uint8_t* kf_matched, int32_t th, int32_t* kf_mp, int32_t* nmatches);
 
 /* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, matches), src/ORBmatcher.cc:160-289.
  * Feature vectors as CSR over ascending node ids: node_ids[nn], start[nn+1], items[...].

@@ -321,7 +321,57 @@ int orc_search_by_projection_last(const FrameView* cur, const Kp* last_kps, cons
         three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
         for (int i = 0; i < HISTO_LENGTH; ++i)
             if (i != ind1 && i != ind2 && i != ind3)
-                for (size_t j = 0; j < rotHist[i].size(); ++j) { cur_mp[rotHist[i][j]] = -1; nmatches--; }
+                for (size_t j = 0; j < rotHist[i].size(); ++j) { cur_mp[rotHist[i][j]] = -2; nmatches--; }   // -2: the reference writes NULL here
+    }
+    return nmatches;
+}
+
+// SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist)  src/ORBmatcher.cc:1473-1600 (relocalisation) and
+// SearchByProjection(pKF, Scw, vpPoints, vpMatched, th)               src/ORBmatcher.cc:291-404   (loop closing).
+// Both project map points into a frame / key frame, search a radius th * scale[predicted level], take the single best
+// unmatched candidate and accept it below a distance bound; they differ in the level band (+1 / +0 above the
+// predicted level), the bound (ORBdist / TH_LOW) and the orientation histogram (reloc only).  The projection, the
+// bounds / depth / viewing-angle rejections and MapPoint::PredictScale (src/MapPoint.cc:385-417) stay with the caller:
+// proj NaN = rejected, level = nPredictedLevel.  q_kps supplies the key-frame keypoint angle of each map point (reloc).
+// The loop variant filters levels inside the candidate loop after KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:901-940,
+// same cell arithmetic as the Frame version, no level filter); filtering during the walk visits the same candidates in
+// the same order.
+int orc_search_by_projection_kf(const FrameView* cur, const Kp* q_kps, const float* proj, const int32_t* level,
+                                const uint8_t* mp_desc, int n_mp, const float* scale_factors, const uint8_t* cur_taken,
+                                float th, int th_dist, int level_up, int check_ori, int32_t* cur_mp) {
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    Grid g = build_grid(*cur);
+    std::vector<uint8_t> taken(cur->n, 0);
+    for (int k = 0; k < cur->n; ++k) { cur_mp[k] = -1; taken[k] = cur_taken ? cur_taken[k] : 0; }
+    for (int i = 0; i < n_mp; ++i) {
+        const float u = proj[2 * i], v = proj[2 * i + 1];
+        if (std::isnan(u)) continue;
+        const int nPredictedLevel = level[i];
+        const float radius = th * scale_factors[nPredictedLevel];
+        std::vector<int> cand = features_in_area(*cur, g, u, v, radius, nPredictedLevel - 1, nPredictedLevel + level_up, true);
+        if (cand.empty()) continue;
+        const uint8_t* dMP = mp_desc + (size_t)i * 32;
+        int bestDist = 256, bestIdx2 = -1;
+        for (size_t k = 0; k < cand.size(); ++k) {
+            const int i2 = cand[k];
+            if (taken[i2]) continue;
+            const int dist = hamming(dMP, cur->desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= th_dist && bestIdx2 >= 0) {
+            cur_mp[bestIdx2] = i;
+            taken[bestIdx2] = 1;
+            nmatches++;
+            if (check_ori) rotHist[rot_bin(q_kps[i].angle, cur->kps[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); ++j) { cur_mp[rotHist[i][j]] = -2; nmatches--; }   // -2: the reference writes NULL here
     }
     return nmatches;
 }
@@ -410,7 +460,7 @@ int orc_search_by_bow(const Kp* kf_kps, const uint8_t* kf_desc, int n_kf, const 
         three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
         for (int i = 0; i < HISTO_LENGTH; ++i) {
             if (i == ind1 || i == ind2 || i == ind3) continue;
-            for (size_t j = 0; j < rotHist[i].size(); ++j) { f_mp[rotHist[i][j]] = -1; nmatches--; }
+            for (size_t j = 0; j < rotHist[i].size(); ++j) { f_mp[rotHist[i][j]] = -2; nmatches--; }   // -2: the reference writes NULL here
         }
     }
     return nmatches;

@@ -234,6 +234,19 @@ def search_by_projection_last(cur, last_kps, last_proj, last_mp_desc, scale_fact
     return n, cur_mp[:len(cur.kps)]
 
 
+def search_by_projection_kf(cur, q_kps, proj, level, mp_desc, scale_factors, th, th_dist, level_up, check_ori, cur_taken=None):
+    """reloc (level_up=1, th_dist=ORBdist, ori) / loop-closing (level_up=0, th_dist=TH_LOW, no ori) SearchByProjection."""
+    v = _view(cur)
+    q_kps = np.ascontiguousarray(q_kps); proj = np.ascontiguousarray(proj, np.float32)
+    level = np.ascontiguousarray(level, np.int32)
+    mp_desc = np.ascontiguousarray(mp_desc, np.uint8); sf = np.ascontiguousarray(scale_factors, np.float32)
+    cur_mp = np.full(max(len(cur.kps), 1), -1, np.int32)
+    tk = None if cur_taken is None else np.ascontiguousarray(cur_taken, np.uint8)
+    n = lib().orc_search_by_projection_kf(C.byref(v), _p(q_kps), _p(proj), _p(level), _p(mp_desc), len(level), _p(sf),
+                                          None if tk is None else _p(tk), _fp(th), int(th_dist), int(level_up), int(check_ori), _p(cur_mp))
+    return n, cur_mp[:len(cur.kps)]
+
+
 def search_by_projection_map(cur, scale_factors, mp_proj, mp_level, mp_viewcos, mp_desc, th, nn_ratio, cur_taken=None, mp_has_obs=None):
     v = _view(cur)
     sf = np.ascontiguousarray(scale_factors, np.float32); mp_proj = np.ascontiguousarray(mp_proj, np.float32)

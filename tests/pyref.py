@@ -202,6 +202,46 @@ def bird_map_point_match(pix, desc, cur, window, ratio):
     return nm, np.array(m12, np.int32)
 
 
+def search_by_projection_kf(cur, q_kps, proj, level, mp_desc, sf, th, th_dist, level_up, ori, taken0=None):
+    """ORBmatcher.cc:1473-1600 (reloc: level_up=1, ORBdist, ori) and :291-404 (loop: level_up=0, TH_LOW, no ori)."""
+    g = build_grid(cur)
+    n = len(cur.kps)
+    cur_mp = [-1] * n
+    taken = [0] * n if taken0 is None else list(taken0)
+    hist = [[] for _ in range(HISTO)]
+    nm = 0
+    for i in range(len(level)):
+        if np.isnan(proj[i, 0]):
+            continue
+        pl = int(level[i])
+        radius = F32(th) * F32(sf[pl])
+        cand = area(cur, g, proj[i, 0], proj[i, 1], radius, pl - 1, pl + level_up, True)
+        if not cand:
+            continue
+        best, bi = 256, -1
+        for i2 in cand:
+            if taken[i2]:
+                continue
+            d = ham(mp_desc[i], cur.desc[i2])
+            if d < best:
+                best, bi = d, i2
+        if best <= th_dist and bi >= 0:
+            cur_mp[bi] = i
+            taken[bi] = 1
+            nm += 1
+            if ori:
+                hist[rot_bin(q_kps["angle"][i], cur.kps["angle"][bi])].append(bi)
+    if ori:
+        keep = three_maxima(hist)
+        for b in range(HISTO):
+            if b in keep:
+                continue
+            for k in hist[b]:
+                cur_mp[k] = -2
+                nm -= 1
+    return nm, np.array(cur_mp, np.int32)
+
+
 def search_by_projection_last(cur, last_kps, proj, mp_desc, sf, th, ori, taken0=None, has_obs=None):
     g = build_grid(cur)
     n = len(cur.kps)
@@ -237,7 +277,7 @@ def search_by_projection_last(cur, last_kps, proj, mp_desc, sf, th, ori, taken0=
             if b in keep:
                 continue
             for k in hist[b]:
-                cur_mp[k] = -1
+                cur_mp[k] = -2
                 nm -= 1
     return nm, np.array(cur_mp, np.int32)
 
@@ -313,6 +353,6 @@ def search_by_bow(kf_kps, kf_desc, kf_has_mp, kfv, f_kps, f_desc, ffv, ratio, or
             if b in keep:
                 continue
             for k in hist[b]:
-                f_mp[k] = -1
+                f_mp[k] = -2
                 nm -= 1
     return nm, np.array(f_mp, np.int32)

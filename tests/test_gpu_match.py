@@ -143,6 +143,26 @@ def test_search_by_projection_last(oracle, front_pair):
         assert n_g == n_o and np.array_equal(c_g, c_o) and n_g > 100
 
 
+def test_search_by_projection_reloc_and_loop(oracle, front_pair):
+    """a-18: the relocalisation (:1473-1600) and loop-closing (:291-404) overloads."""
+    from fishbirdeyevisualslam_b200.matcher import ORBmatcher
+    F1, F2 = front_pair
+    rng = np.random.default_rng(16)
+    proj = np.stack([F1.kps["x"], F1.kps["y"]], 1).astype(np.float32) + rng.normal(0, 3, (F1.N, 2)).astype(np.float32)
+    proj[rng.random(F1.N) < 0.2, 0] = np.nan
+    level = np.clip(F1.kps["octave"] + rng.integers(-1, 2, F1.N), 0, 7).astype(np.int32)
+    mdesc = flip_bits(rng, F1.desc, 40)
+    taken = (rng.random(F2.N) < 0.1).astype(np.uint8)
+    for th, orbdist, ori in [(10, 100, True), (3, 64, True), (10, 100, False)]:
+        n_g, c_g = ORBmatcher(0.9, ori).SearchByProjectionReloc(F2, F1.kps, proj, level, mdesc, th, orbdist, cur_taken=taken)
+        n_o, c_o = oracle.search_by_projection_kf(F2, F1.kps, proj, level, mdesc, F2.scale_factors, th, orbdist, 1, ori, cur_taken=taken)
+        assert n_g == n_o and np.array_equal(c_g, c_o) and n_g > 100
+    for th in (10, 4):
+        n_g, c_g = ORBmatcher(0.75, True).SearchByProjectionLoop(F2, proj, level, mdesc, th, kf_matched=taken)
+        n_o, c_o = oracle.search_by_projection_kf(F2, F1.kps, proj, level, mdesc, F2.scale_factors, th, 50, 0, False, cur_taken=taken)
+        assert n_g == n_o and np.array_equal(c_g, c_o) and n_g > 50
+
+
 def test_search_by_projection_map(oracle, front_pair):
     from fishbirdeyevisualslam_b200.matcher import ORBmatcher
     _, F2 = front_pair

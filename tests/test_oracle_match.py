@@ -66,6 +66,11 @@ def test_projection_searches(oracle, seed):
         n_p, c_p = pyref.search_by_projection_last(F2, F1.kps, proj, F1.desc, sf, th, ori, taken, ho)
         n_o, c_o = oracle.search_by_projection_last(F2, F1.kps, proj, F1.desc, sf, th, ori, taken, ho)
         assert n_o == n_p and np.array_equal(c_o, c_p)
+    level = np.clip(F1.kps["octave"] + rng.integers(-1, 2, F1.N), 0, 7).astype(np.int32)
+    for th, thd, up, ori in [(10, 100, 1, True), (3, 64, 1, False), (10, 50, 0, False)]:      # reloc x2, loop closing
+        n_p, c_p = pyref.search_by_projection_kf(F2, F1.kps, proj, level, F1.desc, sf, th, thd, up, ori, taken)
+        n_o, c_o = oracle.search_by_projection_kf(F2, F1.kps, proj, level, F1.desc, sf, th, thd, up, ori, taken)
+        assert n_o == n_p and np.array_equal(c_o, c_p)
     nmp = 400
     src = rng.integers(0, F2.N, nmp)
     mproj = np.stack([F2.kps["x"][src], F2.kps["y"][src]], 1).astype(np.float32) + rng.normal(0, 2, (nmp, 2)).astype(np.float32)
