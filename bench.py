@@ -35,6 +35,9 @@ FRONT_FEATURES, BIRD_FEATURES = 2000, 1000
 BYTES_PER_PAIR = 5_742_040
 # pixels of all pyramid levels (what the FAST kernel reads once): front 2 853 088, bird 456 460
 PYR_PIXELS_FRONT, PYR_PIXELS_BIRD = 2_853_088, 456_460
+# dram__bytes_read.sum + dram__bytes_write.sum of one front k_fast_cells launch over 128 images (ncu --set full,
+# profiles/r1_02_fast_ncu.md): 384.74 MB + 37.59 MB
+FAST_DRAM_BYTES_PER_FRONT_IMAGE = int((384.737280e6 + 37.585152e6) / 128)
 METRIC = "front+bird frame-pairs/sec ORB extract+match at 1/2/4/8 B200 vs host CPU ref"
 
 
@@ -47,21 +50,61 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region."""
+    """SM clock + throttle reasons sampled DURING the timed regions: NVML (every ~2 ms) when pynvml is importable,
+    else `nvidia-smi --query-gpu` (every ~100 ms)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.rows, self.stop, self.index = [], False, index
+        self.sm, self.mx, self.seen, self.stop, self.index, self.src = [], [], set(), False, index, "nvidia-smi"
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.src = "nvml"
+        except Exception:
+            self.nvml = None
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
+        if self.nvml is not None:
+            n = self.nvml
+            bits = [(getattr(n, "nvmlClocksEventReasonHwSlowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)), "hw_slowdown"),
+                    (getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)), "hw_thermal_slowdown"),
+                    (getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)), "sw_thermal_slowdown"),
+                    (getattr(n, "nvmlClocksEventReasonSwPowerCap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)), "sw_power_cap")]
+            get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            try:
+                self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)))
+            except Exception:
+                pass
+            while not self.stop:
+                try:
+                    self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                    r = int(get_reasons(self.h))
+                    for b, name in bits:
+                        if r & b:
+                            self.seen.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.002)
+            return
         while not self.stop:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+                    r = [c.strip() for c in out.splitlines()[0].split(",")]
+                    if r[0].replace(".", "").isdigit():
+                        self.sm.append(float(r[0]))
+                    if r[1].replace(".", "").isdigit():
+                        self.mx.append(float(r[1]))
+                    for i, name in enumerate(self.NAMES):
+                        if len(r) > 2 + i and r[2 + i].lower().startswith("active"):
+                            self.seen.add(name)
             except Exception:
                 pass
             time.sleep(0.1)
@@ -75,14 +118,10 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "source": self.src}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": [n for n in self.NAMES if n in self.seen], "samples": len(self.sm), "source": self.src}
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
@@ -192,7 +231,9 @@ def run_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = L.fbe_kernel_launch_count()
-    with ClockSampler(local) as clk:
+    clk = ClockSampler(local)
+    clk.__enter__()                      # samples through BOTH timed regions (device-resident loop and e2e loop)
+    if True:
         e0.record(stream)
         for _ in range(args.steps):
             pipe.step_dev(dF.data_ptr(), dB.data_ptr())
@@ -242,12 +283,26 @@ def run_ours(args):
     e2e_loop(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clk.__exit__(None, None, None)
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(t.item())
     h2d = int(fr.nbytes + bi.nbytes)
     d2h = int(hres[0].nbytes + hfm[0].nbytes + hbm[0].nbytes)
+    # what the host link gives a plain pinned->device copy of the same bytes (the ceiling of any host-buffer path)
+    hp = torch.empty(h2d, dtype=torch.uint8, pin_memory=True)
+    dp = torch.empty(h2d, dtype=torch.uint8, device="cuda")
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dp.copy_(hp, non_blocking=True)
+    torch.cuda.synchronize()
+    c0.record()
+    for _ in range(5):
+        dp.copy_(hp, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    link_gbs = 5 * h2d / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del hp, dp
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -268,11 +323,14 @@ def run_ours(args):
                 "config": {"workload": "C2/C4: 1280x720@2000 front + 384x384@1000 bird, extract + grid + frame-to-frame match",
                            "pairs_per_step_per_gpu": B, "parallelism": f"frames sharded over {world} GPU(s), no collective",
                            "l2": f"inputs {h2d / 1e6:.0f} MB per step per GPU (> 126 MB L2)" if h2d > 126e6 else "inputs smaller than L2: raise --batch"},
-                "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "h2d_link_gbs_measured": link_gbs, "h2d_gbs_used": e2e_value / world * (h2d / B) / 1e9,
+                        "note": "two steps in flight: input copy of step i+1 overlaps the kernels of step i; bound = max(copy, compute)"},
                 "gpu_launches": int(launches),
                 "clocks": clk.summary(),
                 "roofline": {"bound": "hbm", "kernel": "k_fast_cells (front)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / peak, "traffic": FAST_DRAM_BYTES_PER_FRONT_IMAGE * B, "peak_source": peak_src,
+                             "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of k_fast_cells (front), per image x images per launch; profiles/r1_02_fast_ncu.md",
                              "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": fast_ms,
                              "whole_step": {"bytes_per_pair": BYTES_PER_PAIR, "achieved_gbs": value / world * BYTES_PER_PAIR / 1e9,
                                             "frac": value / world * BYTES_PER_PAIR / 1e9 / peak}},
@@ -291,7 +349,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=128, help="frame pairs per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
