@@ -5,21 +5,21 @@
 // The reference blurs a clone of the un-padded level with REFLECT_101 at its edge; our padded level already
 // carries that reflection in its 19-px frame, so the stencil reads the padded buffer without edge cases.
 //
-// One CTA = 128x32 output tile in PADDED coordinates (so every global store is an aligned 32-bit word; the few frame
+// One CTA = 128x64 output tile in PADDED coordinates (so every global store is an aligned 32-bit word; the few frame
 // bytes a word may cover are never read by anyone).
-//   * TMA stages the 160x38 input box into shared memory (3-px halo; the box starts 16 px left of the tile because a
+//   * TMA stages the 160x70 input box into shared memory (3-px halo; the box starts 16 px left of the tile because a
 //     TMA box must start on a 16-byte boundary of the innermost dimension -- an unaligned start faults with 'illegal
 //     instruction' on B200, see tools/probe/tma_probe2.cu).
 //   * horizontal pass, u16x2 SIMD: a row sum is <= 255*256 < 2^16, so two pixels share one 32-bit IMAD; the byte pairs
 //     come from PRMT/SHF on three aligned words.  4 outputs per thread task -> one 64-bit shared store.
-//   * vertical pass, 32-bit: a thread owns 4 columns x 4 rows, keeps its 10 input rows in registers, and writes one
+//   * vertical pass, 32-bit: a thread owns 4 columns x 8 rows, keeps its 14 input rows in registers, and writes one
 //     aligned word per row (a warp writes 128 contiguous bytes).
 #include "fbe_internal.cuh"
 #include "tma.cuh"
 
 namespace fbe {
 
-constexpr int kBlurRawW = kBlurTW + 32, kBlurRawH = kBlurTH + 6;     // 160 x 38 staged bytes
+constexpr int kBlurRawW = kBlurTW + 32, kBlurRawH = kBlurTH + 6;     // 160 x 70 staged bytes
 constexpr int kBlurRawWords = kBlurRawW / 4;
 
 __device__ __forceinline__ unsigned blur_hpair(unsigned a, unsigned b, unsigned c, unsigned d, unsigned e, unsigned f, unsigned g) {
@@ -65,20 +65,21 @@ __global__ void __launch_bounds__(256) k_blur(const Plan* __restrict__ plan, Wor
     }
     __syncthreads();
 
-    // ---- vertical pass: 4 columns x 4 rows per thread ----------------------------------------------------------------
+    // ---- vertical pass: 4 columns x 8 rows per thread ----------------------------------------------------------------
+    constexpr int kRows = kBlurTH / 8;               // output rows per thread (8 warps = 8 bands)
     const int cg = tid & 31, band = tid >> 5;
-    unsigned h[10][4];
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint2 v = *reinterpret_cast<const uint2*>(hs + (band * 4 + r) * (kBlurTW / 2) + 2 * cg);
-        h[r][0] = v.x & 0xFFFFu; h[r][1] = v.x >> 16; h[r][2] = v.y & 0xFFFFu; h[r][3] = v.y >> 16;
-    }
     const int pcol = px0 + 4 * cg;
     if (pcol >= g.pitch) return;
+    unsigned h[kRows + 6][4];
+#pragma unroll
+    for (int r = 0; r < kRows + 6; ++r) {
+        const uint2 v = *reinterpret_cast<const uint2*>(hs + (band * kRows + r) * (kBlurTW / 2) + 2 * cg);
+        h[r][0] = v.x & 0xFFFFu; h[r][1] = v.x >> 16; h[r][2] = v.y & 0xFFFFu; h[r][3] = v.y >> 16;
+    }
     uint8_t* out = ws.blur + (size_t)b * plan->pyr_bytes + g.img_off + pcol;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int y = y0 + band * 4 + r;
+    for (int r = 0; r < kRows; ++r) {
+        const int y = y0 + band * kRows + r;
         if (y >= g.h) break;
         unsigned a[4];
 #pragma unroll

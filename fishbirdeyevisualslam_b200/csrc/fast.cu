@@ -137,7 +137,6 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restr
     __syncthreads();                                              // clears complete before any warp scores
 
     const int ini_th = plan->ini_th, lo_th = min(plan->ini_th, plan->min_th);
-    const unsigned ltmask = (1u << lane) - 1u;
 
     // ---- phase 1: compass pretest, 4 pixels per thread (u16x2 SIMD) -> this warp's work list -----------------------
     int nwork = 0;
@@ -173,15 +172,21 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restr
                     if ((unsigned)(xs + 3) >= (unsigned)gw) p1 &= 0x8000u;
                 }
             }
-            const unsigned b0 = __ballot_sync(0xffffffffu, p0 & 0x8000u), b1 = __ballot_sync(0xffffffffu, p0 >> 31);
-            const unsigned b2 = __ballot_sync(0xffffffffu, p1 & 0x8000u), b3 = __ballot_sync(0xffffffffu, p1 >> 31);
+            // append the passing pixels of all lanes: popcount per lane, warp scan by shuffles, at most 4 predicated stores
+            const int c = __popc(p0) + __popc(p1);
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += up;
+            }
+            uint16_t* wp = work + nwork + inc - c;
+            nwork += __shfl_sync(0xffffffffu, inc, 31);
             const unsigned ent = (unsigned)((py << 8) + xs);
-            const int o1 = nwork + __popc(b0), o2 = o1 + __popc(b1), o3 = o2 + __popc(b2);
-            if (p0 & 0x8000u) work[nwork + __popc(b0 & ltmask)] = (uint16_t)ent;
-            if (p0 >> 31) work[o1 + __popc(b1 & ltmask)] = (uint16_t)(ent + 1);
-            if (p1 & 0x8000u) work[o2 + __popc(b2 & ltmask)] = (uint16_t)(ent + 2);
-            if (p1 >> 31) work[o3 + __popc(b3 & ltmask)] = (uint16_t)(ent + 3);
-            nwork = o3 + __popc(b3);
+            if (p0 & 0x8000u) *wp++ = (uint16_t)ent;
+            if ((int)p0 < 0) *wp++ = (uint16_t)(ent + 1);
+            if (p1 & 0x8000u) *wp++ = (uint16_t)(ent + 2);
+            if ((int)p1 < 0) *wp = (uint16_t)(ent + 3);
         }
     }
     __syncwarp();

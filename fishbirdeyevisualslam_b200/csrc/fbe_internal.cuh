@@ -14,7 +14,7 @@ constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE (:73)
 constexpr int kPatch = 31;       // PATCH_SIZE (:72)
 constexpr int kMaxDim = 4095;    // x,y packed in 12 bits each
 constexpr int kMaxGridCells = 64 * 48;
-constexpr int kBlurTW = 128, kBlurTH = 32;   // blur output tile
+constexpr int kBlurTW = 128, kBlurTH = 64;   // blur output tile
 constexpr int kRsTW = 128, kRsTH = 64;       // resize output tile (padded destination coordinates)
 constexpr int kRsMaxTx = (kMaxDim + 38 + 15) / kRsTW + 2, kRsMaxTy = (kMaxDim + 38) / kRsTH + 2;
 constexpr int kFastGroupW = 224; // widest run of FAST cells (pixels) one CTA of the FAST kernel owns
