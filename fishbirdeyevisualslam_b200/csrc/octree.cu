@@ -77,7 +77,7 @@ __device__ __forceinline__ int nonempty4(const int* c4) { return (c4[0] > 0) + (
 // The replay proper.  keys/knode: nk entries.  Returns the number of live nodes; `cur` points at the final array.
 // All pointers may be shared or global memory.
 __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode, int nk, int nini, float hx, int H,
-                             int N, int cap, OctNode* nodesA, OctNode* nodesB, int* cnt4, int* newidx, int* splitf,
+                             int N, int cap, OctNode* nodesA, OctNode* nodesB, int* cnt4, int* cnt4b, int* newidx, int* splitf,
                              int* order, unsigned long long* sortbuf, BlockScan& bs, int* s_ctl, OctNode** out_nodes) {
     const int tid = threadIdx.x;
     OctNode* cur = nodesA;
@@ -119,17 +119,18 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
     int n = s_ctl[0];
     __syncthreads();
 
+    // ---- child sizes of every splittable root; later rounds get theirs from the re-homing pass of the round before ----
+    for (int i = tid; i < 4 * n; i += kOctThreads) cnt4[i] = 0;
+    __syncthreads();
+    for_keys(keys, knode, nk, [&](int, uint32_t key, uint32_t node) {
+        const OctNode nd = cur[node];
+        if (!nd.nomore) atomicAdd(&cnt4[4 * node + quadrant(key, nd)], 1);
+    });
+    __syncthreads();
+
     bool refine = false;
     while (true) {
         const int prev = n;
-        // ---- child sizes of every splittable node ------------------------------------------------------------
-        for (int i = tid; i < 4 * n; i += kOctThreads) cnt4[i] = 0;
-        __syncthreads();
-        for_keys(keys, knode, nk, [&](int, uint32_t key, uint32_t node) {
-            const OctNode nd = cur[node];
-            if (!nd.nomore) atomicAdd(&cnt4[4 * node + quadrant(key, nd)], 1);
-        });
-        __syncthreads();
 
         // ---- processing order of the splittable nodes --------------------------------------------------------
         int m = 0;   // number of splittable nodes
@@ -241,9 +242,11 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
         }
         const int n2 = nsurv + nchild;
         if (tid == 0) s_ctl[2] = 0;
+        if (n2 <= cap)
+            for (int i = tid; i < 4 * n2; i += kOctThreads) cnt4b[i] = 0;
         __syncthreads();
         if (nexp_local) atomicAdd(&s_ctl[2], nexp_local);
-        // ---- re-home the keys ----------------------------------------------------------------------------------
+        // ---- re-home the keys and, in the same pass, count the child sizes of their NEW nodes (next round's input) ----
         if (n2 <= cap) {
             for_keys(keys, knode, nk, [&](int k, uint32_t key, uint32_t node) {
                 const int i = (int)node;
@@ -256,12 +259,15 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
                 } else if (dst != i) {
                     knode[k] = (uint32_t)dst;
                 }
+                const OctNode nd = nxt[dst];
+                if (!nd.nomore) atomicAdd(&cnt4b[4 * dst + quadrant(key, nd)], 1);
             });
         }
         __syncthreads();
         const int nexp = s_ctl[2];
         __syncthreads();
         OctNode* t = cur; cur = nxt; nxt = t;
+        int* tc = cnt4; cnt4 = cnt4b; cnt4b = tc;
         if (n2 > cap) { n = -1; break; }          // cannot happen (see DESIGN.md bound); guarded anyway
         n = n2;
         if (n >= N || n == prev) break;
@@ -301,20 +307,21 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(const Plan* __restrict__
 
     // ---- scratch carve-up -----------------------------------------------------------------------------------------
     const int cap = g.node_cap;
-    // global fallback: level l starts at node_base*80 + l*128 (oct_level_bytes(cap) <= 76*cap + 64)
-    uint8_t* base_ptr = use_smem ? dyn : ws.oct_scratch + (size_t)b * ws.oct_scratch_bytes + (size_t)g.node_base * 80 + (size_t)l * 128;
+    // global fallback: level l starts at node_base*96 + l*128 (oct_level_bytes(cap) <= 92*cap + 64)
+    uint8_t* base_ptr = use_smem ? dyn : ws.oct_scratch + (size_t)b * ws.oct_scratch_bytes + (size_t)g.node_base * 96 + (size_t)l * 128;
     OctNode* nodesA = reinterpret_cast<OctNode*>(base_ptr);
     OctNode* nodesB = nodesA + cap;
     unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(nodesB + cap);
     int* cnt4 = reinterpret_cast<int*>(sortbuf + pow2_ceil(cap));
-    int* newidx = cnt4 + 4 * cap;
+    int* cnt4b = cnt4 + 4 * cap;
+    int* newidx = cnt4b + 4 * cap;
     int* splitf = newidx + cap;
     int* order = splitf + cap;
 
     const int W = g.w - 2 * kEdge + 6, H = g.h - 2 * kEdge + 6;   // maxBorder - minBorder
     (void)W;
     OctNode* fin = nullptr;
-    int n = octree_replay(keys, knode, nk, g.nini, g.hx, H, g.nfeat, cap, nodesA, nodesB, cnt4, newidx, splitf, order,
+    int n = octree_replay(keys, knode, nk, g.nini, g.hx, H, g.nfeat, cap, nodesA, nodesB, cnt4, cnt4b, newidx, splitf, order,
                           sortbuf, bs, s_ctl, &fin);
     int* level_n = ws.level_n + (size_t)b * FBE_MAX_LEVELS + l;
     if (n < 0) {
@@ -349,11 +356,12 @@ __global__ void __launch_bounds__(kOctThreads) k_octree_debug(const uint32_t* ke
     OctNode* nodesB = nodesA + cap;
     unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(nodesB + cap);
     int* cnt4 = reinterpret_cast<int*>(sortbuf + pow2_ceil(cap));
-    int* newidx = cnt4 + 4 * cap;
+    int* cnt4b = cnt4 + 4 * cap;
+    int* newidx = cnt4b + 4 * cap;
     int* splitf = newidx + cap;
     int* order = splitf + cap;
     OctNode* fin = nullptr;
-    int n = octree_replay(keys, knode, nk, nini, hx, H, N, cap, nodesA, nodesB, cnt4, newidx, splitf, order, sortbuf, bs, s_ctl, &fin);
+    int n = octree_replay(keys, knode, nk, nini, hx, H, N, cap, nodesA, nodesB, cnt4, cnt4b, newidx, splitf, order, sortbuf, bs, s_ctl, &fin);
     if (n < 0) { if (tid == 0) *n_out = -1; return; }
     unsigned* best = reinterpret_cast<unsigned*>(cnt4);
     for (int i = tid; i < n; i += kOctThreads) best[i] = 0u;
@@ -369,11 +377,11 @@ __global__ void __launch_bounds__(kOctThreads) k_octree_debug(const uint32_t* ke
 static size_t oct_level_bytes(int cap) {
     int p2 = 1;
     while (p2 < cap) p2 <<= 1;
-    return (size_t)cap * (16 + 16 + 16 + 4 + 4 + 4) + (size_t)p2 * 8 + 64;
+    return (size_t)cap * (16 + 16 + 16 + 16 + 4 + 4 + 4) + (size_t)p2 * 8 + 64;
 }
 
 size_t octree_scratch_bytes(const Plan& hp) {
-    return (size_t)hp.nodes_total * 80 + (size_t)hp.nlevels * 128 + 1024;
+    return (size_t)hp.nodes_total * 96 + (size_t)hp.nlevels * 128 + 1024;
 }
 
 size_t octree_debug_scratch_bytes(int cap) { return oct_level_bytes(cap); }
