@@ -72,6 +72,14 @@ __device__ __forceinline__ void for_keys(const uint32_t* __restrict__ keys, cons
     for (; k < nk; k += kOctThreads) f(k, keys[k], knode[k]);
 }
 
+// counter[idx] += 1 for every calling lane, with the lanes of a warp that hit the same counter folded into ONE shared-memory
+// atomic (MATCH.ANY): the first rounds have a handful of nodes, so 16k keys would otherwise serialise on <= 8 addresses.
+__device__ __forceinline__ void agg_inc(int* counter, int idx) {
+    const unsigned mask = __activemask();
+    const unsigned peers = __match_any_sync(mask, idx);
+    if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&counter[idx], __popc(peers));
+}
+
 __device__ __forceinline__ int nonempty4(const int* c4) { return (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0); }
 
 // The replay proper.  keys/knode: nk entries.  Returns the number of live nodes; `cur` points at the final array.
@@ -91,7 +99,7 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
         int r = (int)__fdiv_rn((float)x, hx);         // vpIniNodes[kp.pt.x/hX]
         r = min(max(r, 0), nini - 1);
         knode[k] = (uint32_t)r;
-        atomicAdd(&cnt4[r], 1);
+        agg_inc(cnt4, r);
     }
     __syncthreads();
     // array position of root r = number of non-empty roots with a larger index (root 0 is the list front = last)
@@ -124,7 +132,7 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
     __syncthreads();
     for_keys(keys, knode, nk, [&](int, uint32_t key, uint32_t node) {
         const OctNode nd = cur[node];
-        if (!nd.nomore) atomicAdd(&cnt4[4 * node + quadrant(key, nd)], 1);
+        if (!nd.nomore) agg_inc(cnt4, 4 * (int)node + quadrant(key, nd));
     });
     __syncthreads();
 
@@ -260,7 +268,7 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
                     knode[k] = (uint32_t)dst;
                 }
                 const OctNode nd = nxt[dst];
-                if (!nd.nomore) atomicAdd(&cnt4b[4 * dst + quadrant(key, nd)], 1);
+                if (!nd.nomore) agg_inc(cnt4b, 4 * dst + quadrant(key, nd));
             });
         }
         __syncthreads();
