@@ -60,6 +60,25 @@ class Frame:
         return grid_assign(self.kps, self.min_x, self.min_y, self.inv_w, self.inv_h, self.gcols, self.grows)
 
 
+def UndistortKeyPoints(kps: np.ndarray, K, D, device: int = 0) -> np.ndarray:
+    """Frame::UndistortKeyPoints (Frame.cc:638-669): keypoints with pt replaced by cv::fisheye::undistortPoints(pt, K, D, P=K)."""
+    L = _lib.load()
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    out = np.empty_like(kps)
+    K = np.ascontiguousarray(K, np.float32); D = np.ascontiguousarray(D, np.float32)
+    check(L.fbe_undistort_keypoints(ptr(kps), len(kps), ptr(K), ptr(D), C.c_int32(device), ptr(out)))
+    return out
+
+
+def ComputeImageBounds(cols: int, rows: int, K, D, device: int = 0):
+    """Frame::ComputeImageBounds (Frame.cc:741-795) -> (mnMinX, mnMaxX, mnMinY, mnMaxY)."""
+    L = _lib.load()
+    K = np.ascontiguousarray(K, np.float32); D = np.ascontiguousarray(D, np.float32)
+    b = np.zeros(4, np.float32)
+    check(L.fbe_image_bounds(C.c_int32(cols), C.c_int32(rows), ptr(K), ptr(D), C.c_int32(device), ptr(b)))
+    return tuple(float(v) for v in b)
+
+
 def grid_assign(kps, min_x, min_y, inv_w, inv_h, gcols, grows):
     L = _lib.load()
     kps = np.ascontiguousarray(kps)

@@ -112,6 +112,18 @@ FBE_API int fbe_debug_blurred(fbe_extractor* e, int32_t slot, int32_t level, uin
 FBE_API int fbe_debug_octree(const int32_t* xys, int32_t n, int32_t min_x, int32_t max_x, int32_t min_y, int32_t max_y,
                      int32_t nfeat, int32_t* sel, int32_t cap, int32_t* n_sel);
 
+/* ---- Frame undistortion (next row f-1) ----------------------------------------------------------- */
+/* Frame::UndistortKeyPoints, src/Frame.cc:638-669: cv::fisheye::undistortPoints(pts, pts, mK, mDistCoef, Mat(), mK) on the
+ * keypoint positions (OpenCV 4.13 semantics: double-precision Newton solve, <= 10 iterations, eps 1e-8; (-1e6,-1e6) when
+ * it fails).  K = {fx, fy, cx, cy}, D = mDistCoef {k1, k2, p1, p2} read as the four fisheye coefficients, exactly as the
+ * reference passes them.  D[0] == 0 copies the keypoints (:640-644).  out may alias kps.  Tolerance, not bit-exactness,
+ * is the parity bar for this row (tan / division ulp); see tests/test_gpu_undistort.py. */
+FBE_API int fbe_undistort_keypoints(const fbe_keypoint* kps, int32_t n, const float K[4], const float D[4], int32_t device,
+                                    fbe_keypoint* out);
+/* Frame::ComputeImageBounds, src/Frame.cc:741-795: bounds = {mnMinX, mnMaxX, mnMinY, mnMaxY} from the four undistorted
+ * image corners (or the image rectangle when D[0] == 0). */
+FBE_API int fbe_image_bounds(int32_t cols, int32_t rows, const float K[4], const float D[4], int32_t device, float bounds[4]);
+
 /* ---- Frame grid -------------------------------------------------------------------------------- */
 /* Frame::AssignFeaturesToGrid / PosInGrid / PosInGridBirdview, src/Frame.cc:381-411,548-570.
  * cell = (round((x-min_x)*inv_w), round((y-min_y)*inv_h)), dropped when outside gcols x grows.

@@ -481,3 +481,38 @@ void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* t, int nt, int
 }
 
 }  // extern "C"
+
+// cv::fisheye::undistortPoints(distorted, undistorted, K, D, noArray(), K) as OpenCV 4.13 evaluates it (pinned against cv2 by
+// tests/golden/undistort.npz): Frame::UndistortKeyPoints / ComputeImageBounds, src/Frame.cc:638-669, 741-795.
+extern "C" void orc_fisheye_undistort(const float* pts, int n, const float* K, const float* D, float* out) {
+    const double fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+    const double k0 = D[0], k1 = D[1], k2 = D[2], k3 = D[3];
+    const double half_pi = 3.1415926535897932384626433832795 / 2.;
+    for (int i = 0; i < n; ++i) {
+        const double wx = ((double)pts[2 * i] - cx) / fx, wy = ((double)pts[2 * i + 1] - cy) / fy;
+        double theta_d = std::sqrt(wx * wx + wy * wy);
+        theta_d = std::min(std::max(-half_pi, theta_d), half_pi);
+        bool converged = false;
+        double theta = theta_d, scale = 0.0;
+        if (std::fabs(theta_d) > 1e-8) {
+            for (int j = 0; j < 10; ++j) {
+                const double t2 = theta * theta, t4 = t2 * t2, t6 = t4 * t2, t8 = t6 * t2;
+                const double a = k0 * t2, b = k1 * t4, c = k2 * t6, d = k3 * t8;
+                const double fix = (theta * (1 + a + b + c + d) - theta_d) / (1 + 3 * a + 5 * b + 7 * c + 9 * d);
+                theta = theta - fix;
+                if (std::fabs(fix) < 1e-8) { converged = true; break; }
+            }
+            scale = std::tan(theta) / theta_d;
+        } else {
+            converged = true;
+        }
+        const bool flipped = (theta_d < 0 && theta > 0) || (theta_d > 0 && theta < 0);
+        if (converged && !flipped) {
+            const double ux = wx * scale, uy = wy * scale;
+            out[2 * i] = (float)(fx * ux + cx);
+            out[2 * i + 1] = (float)(fy * uy + cy);
+        } else {
+            out[2 * i] = -1000000.0f; out[2 * i + 1] = -1000000.0f;
+        }
+    }
+}

@@ -276,3 +276,12 @@ def bruteforce_top2(q, t):
     bi, bd, sd = (np.zeros(max(len(q), 1), np.int32) for _ in range(3))
     lib().orc_bruteforce_top2(_p(q), len(q), _p(t), len(t), _p(bi), _p(bd), _p(sd))
     return bi[:len(q)], bd[:len(q)], sd[:len(q)]
+
+
+def fisheye_undistort(pts, K, D):
+    """cv::fisheye::undistortPoints(pts, K, D, R=I, P=K) restated (OpenCV 4.13 semantics); pts float32 [n,2]."""
+    pts = np.ascontiguousarray(pts, np.float32)
+    K = np.ascontiguousarray(K, np.float32); D = np.ascontiguousarray(D, np.float32)
+    out = np.empty_like(pts)
+    lib().orc_fisheye_undistort(_p(pts), len(pts), _p(K), _p(D), _p(out))
+    return out
