@@ -219,7 +219,7 @@ int fbe_debug_octree(const int32_t* xys, int32_t n, int32_t min_x, int32_t max_x
     FBE_CUDA(cudaMalloc(&d_keys, keys.size() * 4));
     FBE_CUDA(cudaMalloc(&d_knode, keys.size() * 4));
     FBE_CUDA(cudaMalloc(&d_sel, (size_t)ncap * 4));
-    FBE_CUDA(cudaMalloc(&d_scr, octree_debug_scratch_bytes(ncap)));
+    FBE_CUDA(cudaMalloc(&d_scr, octree_debug_scratch_bytes(ncap, nini, nfeat)));
     FBE_CUDA(cudaMalloc(&d_n, 4));
     FBE_CUDA(cudaMemcpy(d_keys, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice));
     int rc = launch_octree_debug(d_keys, d_knode, n, nini, hx, H, nfeat, ncap, d_scr, d_sel, d_n, 0);

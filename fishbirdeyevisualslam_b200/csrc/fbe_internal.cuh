@@ -131,7 +131,7 @@ size_t octree_scratch_bytes(const Plan& hp);
 // stand-alone octree on caller candidates (device arrays): keys packed with level coordinates (= relative + 16)
 int launch_octree_debug(const uint32_t* d_keys, uint32_t* d_knode, int nk, int nini, float hx, int H, int nfeat, int cap,
                         uint8_t* d_scratch, uint32_t* d_sel_idx, int* d_n, cudaStream_t st);
-size_t octree_debug_scratch_bytes(int cap);
+size_t octree_debug_scratch_bytes(int cap, int nini, int nfeat);
 
 // stand-alone grid build on arbitrary keypoint arrays (device pointers), used by the matchers
 int launch_grid_build(const fbe_keypoint* d_kps, const int* d_n, int n_stride, int nframes, float min_x, float min_y,

@@ -20,7 +20,11 @@ namespace fbe {
 
 constexpr int kOctThreads = 512;
 
-struct __align__(16) OctNode { short x0, y0, x1, y1; int cnt; int nomore; };   // bounds relative to (16,16): UL=(x0,y0) BR=(x1,y1)
+// bounds relative to (16,16): UL=(x0,y0) BR=(x1,y1).  A node is final (bNoMore) iff cnt == 1.  pd = depth << 26 | path
+// index: the node's position in the data-independent quad-tree geometry (root r, then one base-4 digit per split).
+struct __align__(16) OctNode { short x0, y0, x1, y1; int cnt; int pd; };
+constexpr int kPdShift = 26;
+__device__ __forceinline__ bool nomore(const OctNode& nd) { return nd.cnt == 1; }
 
 __device__ __forceinline__ int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
@@ -82,24 +86,109 @@ __device__ __forceinline__ void agg_inc(int* counter, int idx) {
 
 __device__ __forceinline__ int nonempty4(const int* c4) { return (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0); }
 
+// ---- histogram mode ----------------------------------------------------------------------------------------------
+// The geometry of the quad tree (node bounds at every depth) does not depend on the data: only which children exist
+// and in which order nodes are processed does.  One pass therefore records, for every key, the depth-D cell of the
+// geometry it falls into (histogram of nini * 4^D counters); the counters of all coarser depths are sums of those.
+// While no node deeper than D - 1 has to be split, every round of the replay takes its child sizes from the histogram
+// and the keys are not touched at all; they are assigned to their final nodes in one pass at the end (or at the
+// moment a node at depth D must be split, after which the replay continues with per-key passes).
+// depth of the histogram for a level with nini roots and N wanted nodes: one more than the depth at which the full tree
+// has N nodes (so that the refinement round is covered too), reduced until the counters fit 16k ints
+__host__ __device__ inline int oct_hist_depth(int nini, int N) {
+    int d = 0;
+    while ((nini << (2 * d)) < N && d < 8) ++d;
+    int D = d + 1;
+    while (D > 0 && nini * (((1 << (2 * (D + 1))) - 1) / 3) > 16384) --D;
+    return D;
+}
+__host__ __device__ inline int oct_hist_entries(int nini, int D) { return D > 0 ? nini * (((1 << (2 * (D + 1))) - 1) / 3) : 0; }
+
+__device__ __forceinline__ int hist_offset(int nini, int d) { return nini * (((1 << (2 * d)) - 1) / 3); }   // sum_{j<d} nini*4^j
+
+// walks key (x,y) down the geometry from root r; calls visit(depth, path) at every depth 0..D until it returns true
+template <class F>
+__device__ __forceinline__ void descend(int x, int y, int r, float hx, int H, int D, F&& visit) {
+    int x0 = (int)__fmul_rn(hx, (float)r), x1 = (int)__fmul_rn(hx, (float)(r + 1)), y0 = 0, y1 = H;
+    int path = r;
+    for (int d = 0;; ++d) {
+        if (visit(d, path) || d == D) return;
+        const int mx = x0 + ((x1 - x0 + 1) >> 1), my = y0 + ((y1 - y0 + 1) >> 1);
+        int q = 0;
+        if (x < mx) x1 = mx; else { x0 = mx; q = 1; }
+        if (y < my) y1 = my; else { y0 = my; q += 2; }
+        path = 4 * path + q;
+    }
+}
+
+__device__ __forceinline__ int root_of(uint32_t key, float hx, int nini) {
+    const int x = key_x(key) - 16;
+    const int r = (int)__fdiv_rn((float)x, hx);         // vpIniNodes[kp.pt.x/hX]
+    return min(max(r, 0), nini - 1);
+}
+
+// assigns every key to the live node it belongs to: table[off(depth) + path] = node index for live nodes, -1 elsewhere
+__device__ void materialise_knode(const uint32_t* __restrict__ keys, uint32_t* knode, int nk, const OctNode* cur, int n, int nini,
+                                  float hx, int H, int D, int* table, int table_n) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < table_n; i += kOctThreads) table[i] = -1;
+    __syncthreads();
+    for (int i = tid; i < n; i += kOctThreads) {
+        const int pd = cur[i].pd;
+        table[hist_offset(nini, pd >> kPdShift) + (pd & ((1 << kPdShift) - 1))] = i;
+    }
+    __syncthreads();
+    for (int k = tid; k < nk; k += kOctThreads) {
+        const uint32_t key = keys[k];
+        int node = 0;
+        descend(key_x(key) - 16, key_y(key) - 16, root_of(key, hx, nini), hx, H, D, [&](int d, int path) {
+            const int t = table[hist_offset(nini, d) + path];
+            if (t >= 0) { node = t; return true; }
+            return false;
+        });
+        knode[k] = (uint32_t)node;
+    }
+    __syncthreads();
+}
+
 // The replay proper.  keys/knode: nk entries.  Returns the number of live nodes; `cur` points at the final array.
 // All pointers may be shared or global memory.
 __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode, int nk, int nini, float hx, int H,
                              int N, int cap, OctNode* nodesA, OctNode* nodesB, int* cnt4, int* cnt4b, int* newidx, int* splitf,
-                             int* order, unsigned long long* sortbuf, BlockScan& bs, int* s_ctl, OctNode** out_nodes) {
+                             int* order, unsigned long long* sortbuf, BlockScan& bs, int* s_ctl, OctNode** out_nodes, int* hist, int D) {
     const int tid = threadIdx.x;
     OctNode* cur = nodesA;
     OctNode* nxt = nodesB;
+    bool hist_mode = D > 0;                       // D == 0: no histogram (too large for the scratch), per-key passes only
+    const int hist_n = hist_mode ? hist_offset(nini, D + 1) : 0;
 
     // ---- roots (:543-585) -------------------------------------------------------------------------------------
-    for (int r = tid; r < nini; r += kOctThreads) cnt4[r] = 0;
-    __syncthreads();
-    for (int k = tid; k < nk; k += kOctThreads) {
-        const int x = key_x(keys[k]) - 16;
-        int r = (int)__fdiv_rn((float)x, hx);         // vpIniNodes[kp.pt.x/hX]
-        r = min(max(r, 0), nini - 1);
-        knode[k] = (uint32_t)r;
-        agg_inc(cnt4, r);
+    if (hist_mode) {
+        for (int i = tid; i < hist_n; i += kOctThreads) hist[i] = 0;
+        __syncthreads();
+        int* hD = hist + hist_offset(nini, D);
+        for (int k = tid; k < nk; k += kOctThreads) {
+            const uint32_t key = keys[k];
+            int leaf = 0;
+            descend(key_x(key) - 16, key_y(key) - 16, root_of(key, hx, nini), hx, H, D, [&](int d, int path) { leaf = path; return false; });
+            agg_inc(hD, leaf);
+        }
+        __syncthreads();
+        for (int d = D - 1; d >= 0; --d) {        // coarser depths = sums of their four children
+            int* hd = hist + hist_offset(nini, d);
+            const int* hc = hist + hist_offset(nini, d + 1);
+            for (int i = tid; i < (nini << (2 * d)); i += kOctThreads) hd[i] = hc[4 * i] + hc[4 * i + 1] + hc[4 * i + 2] + hc[4 * i + 3];
+            __syncthreads();
+        }
+        for (int r = tid; r < nini; r += kOctThreads) cnt4[r] = hist[r];
+    } else {
+        for (int r = tid; r < nini; r += kOctThreads) cnt4[r] = 0;
+        __syncthreads();
+        for (int k = tid; k < nk; k += kOctThreads) {
+            const int r = root_of(keys[k], hx, nini);
+            knode[k] = (uint32_t)r;
+            agg_inc(cnt4, r);
+        }
     }
     __syncthreads();
     // array position of root r = number of non-empty roots with a larger index (root 0 is the list front = last)
@@ -113,7 +202,7 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
             nd.x1 = (short)(int)__fmul_rn(hx, (float)(r + 1));
             nd.y0 = 0; nd.y1 = (short)H;
             nd.cnt = cnt4[r];
-            nd.nomore = cnt4[r] == 1;
+            nd.pd = r;                                   // depth 0, path = root index
             cur[pos] = nd;
         }
     }
@@ -123,22 +212,54 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
         s_ctl[0] = n;
     }
     __syncthreads();
-    for (int k = tid; k < nk; k += kOctThreads) knode[k] = (uint32_t)newidx[knode[k]];
     int n = s_ctl[0];
-    __syncthreads();
-
-    // ---- child sizes of every splittable root; later rounds get theirs from the re-homing pass of the round before ----
-    for (int i = tid; i < 4 * n; i += kOctThreads) cnt4[i] = 0;
-    __syncthreads();
-    for_keys(keys, knode, nk, [&](int, uint32_t key, uint32_t node) {
-        const OctNode nd = cur[node];
-        if (!nd.nomore) agg_inc(cnt4, 4 * (int)node + quadrant(key, nd));
-    });
+    if (!hist_mode) {
+        for (int k = tid; k < nk; k += kOctThreads) knode[k] = (uint32_t)newidx[knode[k]];
+        __syncthreads();
+        // ---- child sizes of every splittable root; later rounds get theirs from the re-homing pass of the round before ----
+        for (int i = tid; i < 4 * n; i += kOctThreads) cnt4[i] = 0;
+        __syncthreads();
+        for_keys(keys, knode, nk, [&](int, uint32_t key, uint32_t node) {
+            const OctNode nd = cur[node];
+            if (!nomore(nd)) agg_inc(cnt4, 4 * (int)node + quadrant(key, nd));
+        });
+    }
     __syncthreads();
 
     bool refine = false;
     while (true) {
         const int prev = n;
+        if (hist_mode) {
+            // child sizes from the histogram -- unless a node that must be split already sits at depth D
+            if (tid == 0) s_ctl[3] = 0;
+            __syncthreads();
+            bool deep = false;
+            for (int i = tid; i < n; i += kOctThreads) {
+                const OctNode nd = cur[i];
+                deep |= !nomore(nd) && (nd.pd >> kPdShift) >= D;
+            }
+            if (deep) s_ctl[3] = 1;
+            __syncthreads();
+            if (s_ctl[3]) {
+                hist_mode = false;               // leave histogram mode: keys get their nodes, then per-key counting
+                materialise_knode(keys, knode, nk, cur, n, nini, hx, H, D, hist, hist_n);
+                for (int i = tid; i < 4 * n; i += kOctThreads) cnt4[i] = 0;
+                __syncthreads();
+                for_keys(keys, knode, nk, [&](int, uint32_t key, uint32_t node) {
+                    const OctNode nd = cur[node];
+                    if (!nomore(nd)) agg_inc(cnt4, 4 * (int)node + quadrant(key, nd));
+                });
+            } else {
+                for (int i = tid; i < n; i += kOctThreads) {
+                    const OctNode nd = cur[i];
+                    if (!nomore(nd)) {
+                        const int* hc = hist + hist_offset(nini, (nd.pd >> kPdShift) + 1) + 4 * (nd.pd & ((1 << kPdShift) - 1));
+                        cnt4[4 * i] = hc[0]; cnt4[4 * i + 1] = hc[1]; cnt4[4 * i + 2] = hc[2]; cnt4[4 * i + 3] = hc[3];
+                    }
+                }
+            }
+            __syncthreads();
+        }
 
         // ---- processing order of the splittable nodes --------------------------------------------------------
         int m = 0;   // number of splittable nodes
@@ -147,19 +268,19 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
             for (int base = 0; base < n; base += kOctThreads) {
                 const int j = base + tid;            // j-th node from the back
                 const int i = n - 1 - j;
-                const int f = (j < n) && !cur[i].nomore;
+                const int f = (j < n) && !nomore(cur[i]);
                 int tot;
                 const int ex = bs.exclusive(f, tot);
                 if (f) order[m + ex] = i;
                 m += tot;
             }
             __syncthreads();
-            for (int i = tid; i < n; i += kOctThreads) splitf[i] = !cur[i].nomore;
+            for (int i = tid; i < n; i += kOctThreads) splitf[i] = !nomore(cur[i]);
         } else {
             // refinement: (size, creation rank) descending; stop once the live count reaches N (:685-732)
             for (int base = 0; base < n; base += kOctThreads) {
                 const int i = base + tid;
-                const int f = (i < n) && !cur[i].nomore;
+                const int f = (i < n) && !nomore(cur[i]);
                 int tot;
                 const int ex = bs.exclusive(f, tot);
                 if (f) sortbuf[m + ex] = ((unsigned long long)(unsigned)cur[i].cnt << 32) | (unsigned)i;
@@ -239,7 +360,8 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
                             OctNode ch;
                             ch.x0 = (q & 1) ? (short)mx : nd.x0;  ch.x1 = (q & 1) ? nd.x1 : (short)mx;
                             ch.y0 = (q & 2) ? (short)my : nd.y0;  ch.y1 = (q & 2) ? nd.y1 : (short)my;
-                            ch.cnt = cq; ch.nomore = cq == 1;
+                            ch.cnt = cq;
+                            ch.pd = (((nd.pd >> kPdShift) + 1) << kPdShift) | (4 * (nd.pd & ((1 << kPdShift) - 1)) + q);
                             nxt[pos++] = ch;
                             nexp_local += cq > 1;
                         }
@@ -250,12 +372,12 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
         }
         const int n2 = nsurv + nchild;
         if (tid == 0) s_ctl[2] = 0;
-        if (n2 <= cap)
+        if (n2 <= cap && !hist_mode)
             for (int i = tid; i < 4 * n2; i += kOctThreads) cnt4b[i] = 0;
         __syncthreads();
         if (nexp_local) atomicAdd(&s_ctl[2], nexp_local);
         // ---- re-home the keys and, in the same pass, count the child sizes of their NEW nodes (next round's input) ----
-        if (n2 <= cap) {
+        if (n2 <= cap && !hist_mode) {
             for_keys(keys, knode, nk, [&](int k, uint32_t key, uint32_t node) {
                 const int i = (int)node;
                 int dst = newidx[i];
@@ -268,24 +390,25 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
                     knode[k] = (uint32_t)dst;
                 }
                 const OctNode nd = nxt[dst];
-                if (!nd.nomore) agg_inc(cnt4b, 4 * dst + quadrant(key, nd));
+                if (!nomore(nd)) agg_inc(cnt4b, 4 * dst + quadrant(key, nd));
             });
         }
         __syncthreads();
         const int nexp = s_ctl[2];
         __syncthreads();
         OctNode* t = cur; cur = nxt; nxt = t;
-        int* tc = cnt4; cnt4 = cnt4b; cnt4b = tc;
+        if (!hist_mode) { int* tc = cnt4; cnt4 = cnt4b; cnt4b = tc; }
         if (n2 > cap) { n = -1; break; }          // cannot happen (see DESIGN.md bound); guarded anyway
         n = n2;
         if (n >= N || n == prev) break;
         if (!refine && n + 3 * nexp > N) refine = true;
     }
+    if (hist_mode && n > 0) materialise_knode(keys, knode, nk, cur, n, nini, hx, H, D, hist, hist_n);
     *out_nodes = cur;
     return n;
 }
 
-__global__ void __launch_bounds__(kOctThreads) k_octree(const Plan* __restrict__ plan, Workspace ws, int use_smem) {
+__global__ void __launch_bounds__(kOctThreads) k_octree(const Plan* __restrict__ plan, Workspace ws, int use_smem, int level_stride) {
     extern __shared__ __align__(16) uint8_t dyn[];
     __shared__ int s_warp[kOctThreads / 32 + 1];
     __shared__ int s_ctl[4];
@@ -315,8 +438,8 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(const Plan* __restrict__
 
     // ---- scratch carve-up -----------------------------------------------------------------------------------------
     const int cap = g.node_cap;
-    // global fallback: level l starts at node_base*96 + l*128 (oct_level_bytes(cap) <= 92*cap + 64)
-    uint8_t* base_ptr = use_smem ? dyn : ws.oct_scratch + (size_t)b * ws.oct_scratch_bytes + (size_t)g.node_base * 96 + (size_t)l * 128;
+    // global fallback: every level owns `level_stride` bytes of the per-image scratch
+    uint8_t* base_ptr = use_smem ? dyn : ws.oct_scratch + (size_t)b * ws.oct_scratch_bytes + (size_t)l * level_stride;
     OctNode* nodesA = reinterpret_cast<OctNode*>(base_ptr);
     OctNode* nodesB = nodesA + cap;
     unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(nodesB + cap);
@@ -325,12 +448,14 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(const Plan* __restrict__
     int* newidx = cnt4b + 4 * cap;
     int* splitf = newidx + cap;
     int* order = splitf + cap;
+    int* hist = order + cap;
+    const int D = oct_hist_depth(g.nini, g.nfeat);
 
     const int W = g.w - 2 * kEdge + 6, H = g.h - 2 * kEdge + 6;   // maxBorder - minBorder
     (void)W;
     OctNode* fin = nullptr;
     int n = octree_replay(keys, knode, nk, g.nini, g.hx, H, g.nfeat, cap, nodesA, nodesB, cnt4, cnt4b, newidx, splitf, order,
-                          sortbuf, bs, s_ctl, &fin);
+                          sortbuf, bs, s_ctl, &fin, hist, D);
     int* level_n = ws.level_n + (size_t)b * FBE_MAX_LEVELS + l;
     if (n < 0) {
         if (tid == 0) { *level_n = 0; atomicOr(ws.status + b, 1); }
@@ -368,8 +493,10 @@ __global__ void __launch_bounds__(kOctThreads) k_octree_debug(const uint32_t* ke
     int* newidx = cnt4b + 4 * cap;
     int* splitf = newidx + cap;
     int* order = splitf + cap;
+    int* hist = order + cap;
     OctNode* fin = nullptr;
-    int n = octree_replay(keys, knode, nk, nini, hx, H, N, cap, nodesA, nodesB, cnt4, cnt4b, newidx, splitf, order, sortbuf, bs, s_ctl, &fin);
+    int n = octree_replay(keys, knode, nk, nini, hx, H, N, cap, nodesA, nodesB, cnt4, cnt4b, newidx, splitf, order, sortbuf, bs, s_ctl, &fin,
+                          hist, oct_hist_depth(nini, N));
     if (n < 0) { if (tid == 0) *n_out = -1; return; }
     unsigned* best = reinterpret_cast<unsigned*>(cnt4);
     for (int i = tid; i < n; i += kOctThreads) best[i] = 0u;
@@ -382,17 +509,22 @@ __global__ void __launch_bounds__(kOctThreads) k_octree_debug(const uint32_t* ke
     if (tid == 0) *n_out = n;
 }
 
-static size_t oct_level_bytes(int cap) {
+static size_t oct_level_bytes(int cap, int nini, int N) {
     int p2 = 1;
     while (p2 < cap) p2 <<= 1;
-    return (size_t)cap * (16 + 16 + 16 + 16 + 4 + 4 + 4) + (size_t)p2 * 8 + 64;
+    const size_t hist = (size_t)oct_hist_entries(nini, oct_hist_depth(nini, N)) * 4;
+    return (((size_t)cap * (16 + 16 + 16 + 16 + 4 + 4 + 4) + (size_t)p2 * 8 + hist + 64) + 127) & ~(size_t)127;
 }
 
-size_t octree_scratch_bytes(const Plan& hp) {
-    return (size_t)hp.nodes_total * 96 + (size_t)hp.nlevels * 128 + 1024;
+static size_t oct_level_stride(const Plan& hp) {
+    size_t need = 0;
+    for (int l = 0; l < hp.nlevels; ++l) need = std::max(need, oct_level_bytes(hp.lv[l].node_cap, hp.lv[l].nini, hp.lv[l].nfeat));
+    return need;
 }
 
-size_t octree_debug_scratch_bytes(int cap) { return oct_level_bytes(cap); }
+size_t octree_scratch_bytes(const Plan& hp) { return oct_level_stride(hp) * hp.nlevels + 1024; }
+
+size_t octree_debug_scratch_bytes(int cap, int nini, int N) { return oct_level_bytes(cap, nini, N); }
 
 int launch_octree_debug(const uint32_t* d_keys, uint32_t* d_knode, int nk, int nini, float hx, int H, int nfeat, int cap,
                         uint8_t* d_scratch, uint32_t* d_sel_idx, int* d_n, cudaStream_t st) {
@@ -403,13 +535,12 @@ int launch_octree_debug(const uint32_t* d_keys, uint32_t* d_knode, int nk, int n
 }
 
 int launch_octree(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st) {
-    size_t need = 0;
-    for (int l = 0; l < hp.nlevels; ++l) need = std::max(need, oct_level_bytes(hp.lv[l].node_cap));
+    const size_t need = oct_level_stride(hp);
     const int use_smem = need <= 160 * 1024;
     size_t smem = use_smem ? need : 0;
     if (smem > 48 * 1024) FBE_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(hp.nlevels, nimg);
-    k_octree<<<grid, kOctThreads, smem, st>>>(dp, ws, use_smem);
+    k_octree<<<grid, kOctThreads, smem, st>>>(dp, ws, use_smem, (int)need);
     count_launch();
     FBE_CUDA(cudaGetLastError());
     return FBE_OK;
