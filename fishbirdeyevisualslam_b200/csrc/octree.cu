@@ -286,20 +286,36 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
                 if (f) sortbuf[m + ex] = ((unsigned long long)(unsigned)cur[i].cnt << 32) | (unsigned)i;
                 m += tot;
             }
-            const int mp = pow2_ceil(max(m, 1));
-            for (int j = m + tid; j < mp; j += kOctThreads) sortbuf[j] = 0ull;
-            __syncthreads();
-            for (int k2 = 2; k2 <= mp; k2 <<= 1) {
-                for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-                    for (int t = tid; t < mp; t += kOctThreads) {
-                        const int p = t ^ j2;
-                        if (p > t) {
-                            const unsigned long long a = sortbuf[t], c = sortbuf[p];
-                            const bool desc = (t & k2) == 0;      // descending overall
-                            if (desc ? (a < c) : (a > c)) { sortbuf[t] = c; sortbuf[p] = a; }
+            // descending sort of the m unique (size, rank) keys.  Small m (the normal case: a few hundred splittable nodes):
+            // rank sort -- every thread counts the keys greater than its own, ONE barrier; large m: bitonic network.
+            unsigned long long* sorted = sortbuf;
+            if (m <= 2 * kOctThreads) {
+                __syncthreads();
+                unsigned long long* out = reinterpret_cast<unsigned long long*>(cnt4b);      // free until the re-homing pass
+                for (int t = tid; t < m; t += kOctThreads) {
+                    const unsigned long long mine = sortbuf[t];
+                    int rank = 0;
+                    for (int u = 0; u < m; ++u) rank += sortbuf[u] > mine;
+                    out[rank] = mine;
+                }
+                sorted = out;
+                __syncthreads();
+            } else {
+                const int mp = pow2_ceil(max(m, 1));
+                for (int j = m + tid; j < mp; j += kOctThreads) sortbuf[j] = 0ull;
+                __syncthreads();
+                for (int k2 = 2; k2 <= mp; k2 <<= 1) {
+                    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                        for (int t = tid; t < mp; t += kOctThreads) {
+                            const int p = t ^ j2;
+                            if (p > t) {
+                                const unsigned long long a = sortbuf[t], c = sortbuf[p];
+                                const bool desc = (t & k2) == 0;      // descending overall
+                                if (desc ? (a < c) : (a > c)) { sortbuf[t] = c; sortbuf[p] = a; }
+                            }
                         }
+                        __syncthreads();
                     }
-                    __syncthreads();
                 }
             }
             for (int i = tid; i < n; i += kOctThreads) splitf[i] = 0;
@@ -312,7 +328,7 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
             for (int base = 0; base < m; base += kOctThreads) {
                 const int j = base + tid;
                 int gain = 0, i = 0;
-                if (j < m) { i = (int)(sortbuf[j] & 0xffffffffu); gain = nonempty4(cnt4 + 4 * i) - 1; }
+                if (j < m) { i = (int)(sorted[j] & 0xffffffffu); gain = nonempty4(cnt4 + 4 * i) - 1; }
                 int tot;
                 const int ex = bs.exclusive(gain, tot);
                 const int live_before = n + carry + ex;          // live count before this split
@@ -424,15 +440,21 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(const Plan* __restrict__
     const int ncells = g.ncols * g.nrows;
 
     // ---- vToDistributeKeys: concatenate the cells in row-major order ----------------------------------------------
+    // (cell offsets by a block scan, parked in the not-yet-used knode array; then one warp per cell copies coalesced)
     int nk = 0;
     for (int base = 0; base < ncells; base += kOctThreads) {
         const int c = base + tid;
         const int cnt = c < ncells ? ccount[c] : 0;
         int tot;
         const int ex = bs.exclusive(cnt, tot);
-        const uint32_t* src = slots + (size_t)c * g.cell_cap;
-        for (int i = 0; i < cnt; ++i) keys[nk + ex + i] = src[i];
+        if (c < ncells) knode[c] = (uint32_t)(nk + ex);
         nk += tot;
+    }
+    __syncthreads();
+    for (int c = tid >> 5; c < ncells; c += kOctThreads / 32) {
+        const int cnt = ccount[c], off = (int)knode[c];
+        const uint32_t* src = slots + (size_t)c * g.cell_cap;
+        for (int i = tid & 31; i < cnt; i += 32) keys[off + i] = src[i];
     }
     __syncthreads();
 
