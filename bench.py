@@ -258,8 +258,8 @@ def run_ours(args):
     # ---- end to end through host buffers (`e2e`) ----------------------------------------------------------------
     # The public host-buffer API: submit(step i) enqueues H2D of the inputs, the step and D2H of the results; wait(i-1)
     # collects the previous step.  Inputs and results live in pinned host memory; every step's H2D + D2H is inside the
-    # timed region (two steps in flight, so the copies of step i+1 travel while step i computes).
-    NBUF = 2
+    # timed region (three steps in flight, so the copies of steps i+1, i+2 travel while step i computes).
+    NBUF = 3
     hF, hB = PinnedBuffer(fr.shape), PinnedBuffer(bi.shape)
     hF.array[...] = fr
     hB.array[...] = bi
@@ -268,16 +268,16 @@ def run_ours(args):
     hbm = [PinnedBuffer((B, pipe.bird_cap), np.int32) for _ in range(NBUF)]
 
     def e2e_loop(n):
-        prev = None
+        q = []
         for i in range(n):
             k = i % NBUF
-            t = pipe.submit_host(hF.ptr, hB.ptr, hres[k].array, hfm[k].array, hbm[k].array)
-            if prev is not None:
-                pipe.wait(prev)
-            prev = t
-        pipe.wait(prev)
+            q.append(pipe.submit_host(hF.ptr, hB.ptr, hres[k].array, hfm[k].array, hbm[k].array))
+            if len(q) >= NBUF:
+                pipe.wait(q.pop(0))           # the results of step i - 2 are now in hres / hfm / hbm [k']
+        for t in q:
+            pipe.wait(t)
 
-    e2e_loop(3)
+    e2e_loop(4)
     barrier()
     t0 = time.perf_counter()
     e2e_loop(args.steps)
@@ -325,7 +325,7 @@ def run_ours(args):
                            "l2": f"inputs {h2d / 1e6:.0f} MB per step per GPU (> 126 MB L2)" if h2d > 126e6 else "inputs smaller than L2: raise --batch"},
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "h2d_link_gbs_measured": link_gbs, "h2d_gbs_used": e2e_value / world * (h2d / B) / 1e9,
-                        "note": "two steps in flight: input copy of step i+1 overlaps the kernels of step i; bound = max(copy, compute)"},
+                        "note": "three steps in flight: the input copies of the next steps overlap the kernels of step i; bound = max(copy, compute)"},
                 "gpu_launches": int(launches),
                 "clocks": clk.summary(),
                 "roofline": {"bound": "hbm", "kernel": "k_fast_cells (front)", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -35,10 +35,12 @@ struct fbe_pipeline {
     fbe_pair_result* h_res = nullptr;    // pinned
     // asynchronous host-buffer path: the H2D copy of step N+1 runs on its own stream beside the kernels of step N
     cudaStream_t copy_stream = nullptr;
-    uint8_t *d_front_q[2] = {nullptr, nullptr}, *d_bird_q[2] = {nullptr, nullptr};
-    cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-    bool in_used[2] = {false, false};
-    int* h_flags = nullptr;              // pinned, [2][2]
+    static constexpr int kQ = 3;         // steps in flight on the host-buffer path (input staging ring)
+    uint8_t *d_front_q[kQ] = {}, *d_bird_q[kQ] = {};
+    cudaEvent_t ev_in_ready[kQ] = {}, ev_in_free[kQ] = {}, ev_done[kQ] = {};
+    cudaEvent_t ev_copy0[kQ] = {};       // timing: start of the input copy (ev_in_ready is its end)
+    bool in_used[kQ] = {};
+    int* h_flags = nullptr;              // pinned, [kQ][2]
     int32_t next_ticket = 0;
 };
 
@@ -88,10 +90,10 @@ void free_all(fbe_pipeline* p) {
     if (p->h_res) cudaFreeHost(p->h_res);
     if (p->h_flags) cudaFreeHost(p->h_flags);
     if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < fbe_pipeline::kQ; ++k) {
         if (p->d_front_q[k]) cudaFree(p->d_front_q[k]);
         if (p->d_bird_q[k]) cudaFree(p->d_bird_q[k]);
-        for (cudaEvent_t e : {p->ev_in_ready[k], p->ev_in_free[k], p->ev_done[k]}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : {p->ev_in_ready[k], p->ev_in_free[k], p->ev_done[k], p->ev_copy0[k]}) if (e) cudaEventDestroy(e);
     }
     for (cudaEvent_t e : {p->ev_front, p->ev_bird, p->ev_match_done[0], p->ev_match_done[1], p->ev_t0, p->ev_t1}) if (e) cudaEventDestroy(e);
     p->front.destroy();
@@ -299,7 +301,7 @@ int fbe_pipeline_fetch_pair(fbe_pipeline* p, int32_t pair, fbe_keypoint* front_k
 
 // Asynchronous step through HOST buffers (ideally pinned).  submit() enqueues the H2D copy of the inputs on a copy stream,
 // the step, and the D2H copy of the results into the caller's buffers, then returns a ticket; wait(ticket) blocks until
-// that step's results are in the host buffers.  Two steps may be in flight: the inputs of step N+1 travel while step N
+// that step's results are in the host buffers.  Up to three steps may be in flight: the inputs of step N+1 travel while step N
 // computes, so the end-to-end rate is max(copy, compute) instead of their sum.  Steps execute in submit order.
 int fbe_pipeline_submit_host(fbe_pipeline* p, const uint8_t* h_front, const uint8_t* h_bird, fbe_pair_result* res,
                              int32_t* front_matches12, int32_t* bird_matches12, int32_t* ticket) {
@@ -310,20 +312,22 @@ int fbe_pipeline_submit_host(fbe_pipeline* p, const uint8_t* h_front, const uint
     const size_t fbytes = B * c.front_rows * c.front_cols, bbytes = B * c.bird_rows * c.bird_cols;
     if (!p->copy_stream) {
         FBE_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
-        FBE_CUDA(cudaMallocHost((void**)&p->h_flags, 4 * sizeof(int)));
-        for (int k = 0; k < 2; ++k) {
+        FBE_CUDA(cudaMallocHost((void**)&p->h_flags, 2 * fbe_pipeline::kQ * sizeof(int)));
+        for (int k = 0; k < fbe_pipeline::kQ; ++k) {
             FBE_CUDA(cudaMalloc(&p->d_front_q[k], fbytes));
             FBE_CUDA(cudaMalloc(&p->d_bird_q[k], bbytes));
-            FBE_CUDA(cudaEventCreateWithFlags(&p->ev_in_ready[k], cudaEventDisableTiming));
+            FBE_CUDA(cudaEventCreate(&p->ev_in_ready[k]));
+            FBE_CUDA(cudaEventCreate(&p->ev_copy0[k]));
             FBE_CUDA(cudaEventCreateWithFlags(&p->ev_in_free[k], cudaEventDisableTiming));
             FBE_CUDA(cudaEventCreateWithFlags(&p->ev_done[k], cudaEventDisableTiming));
         }
     }
     const int32_t t = p->next_ticket++;
-    const int k = t & 1;
+    const int k = t % fbe_pipeline::kQ;
     cudaStream_t cs = p->copy_stream, ms = p->mstream;
     // inputs: wait until the step that last used this staging pair has consumed it
     if (p->in_used[k]) FBE_CUDA(cudaStreamWaitEvent(cs, p->ev_in_free[k], 0));
+    FBE_CUDA(cudaEventRecord(p->ev_copy0[k], cs));
     FBE_CUDA(cudaMemcpyAsync(p->d_front_q[k], h_front, fbytes, cudaMemcpyHostToDevice, cs));
     FBE_CUDA(cudaMemcpyAsync(p->d_bird_q[k], h_bird, bbytes, cudaMemcpyHostToDevice, cs));
     FBE_CUDA(cudaEventRecord(p->ev_in_ready[k], cs));
@@ -343,10 +347,19 @@ int fbe_pipeline_submit_host(fbe_pipeline* p, const uint8_t* h_front, const uint
     return FBE_OK;
 }
 
+// device milliseconds the input copy of a completed ticket took (diagnostic for the end-to-end number)
+int fbe_pipeline_copy_ms(fbe_pipeline* p, int32_t ticket, float* ms) {
+    if (!p || !ms || ticket < 0 || ticket >= p->next_ticket || ticket < p->next_ticket - fbe_pipeline::kQ) return FBE_E_INVALID;
+    const int k = ticket % fbe_pipeline::kQ;
+    FBE_CUDA(cudaEventSynchronize(p->ev_in_ready[k]));
+    FBE_CUDA(cudaEventElapsedTime(ms, p->ev_copy0[k], p->ev_in_ready[k]));
+    return FBE_OK;
+}
+
 int fbe_pipeline_wait(fbe_pipeline* p, int32_t ticket) {
-    if (!p || ticket < 0 || ticket >= p->next_ticket || ticket < p->next_ticket - 2) return FBE_E_INVALID;
+    if (!p || ticket < 0 || ticket >= p->next_ticket || ticket < p->next_ticket - fbe_pipeline::kQ) return FBE_E_INVALID;
     FBE_CUDA(cudaSetDevice(p->cfg.device));
-    const int k = ticket & 1;
+    const int k = ticket % fbe_pipeline::kQ;
     FBE_CUDA(cudaEventSynchronize(p->ev_done[k]));
     if (p->h_flags[2 * k]) { set_error("candidate rows overflow in pipeline (raise row capacity)"); return FBE_E_CAPACITY; }
     return FBE_OK;

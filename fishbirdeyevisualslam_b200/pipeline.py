@@ -53,7 +53,7 @@ class FrontBirdPipeline:
                                              None if fm is None else ptr(fm), None if bm is None else ptr(bm)))
 
     def submit_host(self, h_front_ptr: int, h_bird_ptr: int, res: np.ndarray, fm: np.ndarray | None = None, bm: np.ndarray | None = None) -> int:
-        """Asynchronous step through host (pinned) buffers; returns a ticket for wait().  Two steps may be in flight."""
+        """Asynchronous step through host (pinned) buffers; returns a ticket for wait().  Up to three steps may be in flight."""
         t = C.c_int32()
         check(self._L.fbe_pipeline_submit_host(self._h, C.c_void_p(h_front_ptr), C.c_void_p(h_bird_ptr), ptr(res),
                                                None if fm is None else ptr(fm), None if bm is None else ptr(bm), C.byref(t)))

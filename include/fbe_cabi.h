@@ -259,11 +259,13 @@ FBE_API int fbe_pipeline_step_host(fbe_pipeline* p, const uint8_t* h_front, cons
                            int32_t* bird_matches12 /* [batch][bird_cap] or NULL */);
 /* Asynchronous variant: enqueue H2D of the inputs (own copy stream), the step and the D2H of the results into the
  * caller's buffers; returns a ticket.  fbe_pipeline_wait(ticket) blocks until that step's results are in the host
- * buffers.  At most two steps may be in flight (submit N+1 before waiting for N): the inputs of step N+1 are copied
- * while step N computes.  Host buffers must stay valid (and should be pinned) until the wait returns. */
+ * buffers.  At most three steps may be in flight (submit N+1, N+2 before waiting for N): the inputs of the next steps
+ * are copied while step N computes.  Host buffers must stay valid (and should be pinned) until the wait returns. */
 FBE_API int fbe_pipeline_submit_host(fbe_pipeline* p, const uint8_t* h_front, const uint8_t* h_bird, fbe_pair_result* res,
                                      int32_t* front_matches12, int32_t* bird_matches12, int32_t* ticket);
 FBE_API int fbe_pipeline_wait(fbe_pipeline* p, int32_t ticket);
+/* diagnostic: device milliseconds the H2D input copy of a (still current) ticket took */
+FBE_API int fbe_pipeline_copy_ms(fbe_pipeline* p, int32_t ticket, float* ms);
 FBE_API int fbe_pipeline_sync(fbe_pipeline* p);
 FBE_API int fbe_pipeline_caps(const fbe_pipeline* p, int32_t* front_cap, int32_t* bird_cap);
 /* copy back the results of the last step */

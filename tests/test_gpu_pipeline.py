@@ -99,11 +99,11 @@ def test_host_step_equals_device_step():
 
 
 def test_async_submit_equals_sync_steps():
-    """Two steps in flight through host buffers (H2D of step N+1 beside the kernels of step N) give exactly the results
-    of the synchronous step-by-step path."""
+    """Up to three steps in flight through host buffers (H2D of the next steps beside the kernels of step N) give exactly
+    the results of the synchronous step-by-step path."""
     from fishbirdeyevisualslam_b200 import _lib
     from fishbirdeyevisualslam_b200.pipeline import FrontBirdPipeline, PinnedBuffer
-    B, S = 3, 4
+    B, S = 3, 6
     fr, bi = sequence(B * S, 700)
     p1, p2 = FrontBirdPipeline(B), FrontBirdPipeline(B)
     want = []
@@ -122,8 +122,9 @@ def test_async_submit_equals_sync_steps():
     tickets = []
     for s in range(S):
         tickets.append(p2.submit_host(hF[s].ptr, hB[s].ptr, res[s].array, fm[s].array, bm[s].array))
-        if s >= 1:
-            p2.wait(tickets[s - 1])
+        if s >= 2:
+            p2.wait(tickets[s - 2])
+    p2.wait(tickets[-2])
     p2.wait(tickets[-1])
     prev_nf = prev_nb = 0
     for s in range(S):
