@@ -201,3 +201,26 @@ def test_idempotent_and_deterministic():
     for _ in range(3):
         k2, d2 = g(img)
         assert k1.tobytes() == k2.tobytes() and np.array_equal(d1, d2)
+
+
+def test_distinct_instances_run_concurrently(oracle):
+    """SURVEY §8b threading: distinct ORBextractor instances (own stream + workspace) are used from different threads at
+    the same time (the reference's stereo constructor does exactly that, Frame.cc:124-127); results equal the oracle's."""
+    import threading
+    from fishbirdeyevisualslam_b200.extractor import ORBextractor
+    imgs = [synth.frame(240, 320, 70 + i) for i in range(4)]
+    want = [oracle.OracleExtractor(500, 1.2, 6, 15, 5)(im) for im in imgs]
+    got = [None] * 4
+
+    def work(i):
+        ex = ORBextractor(500, 1.2, 6, 15, 5)
+        for _ in range(5):
+            got[i] = ex(imgs[i])
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for (k, d), (ko, do) in zip(got, want):
+        assert k.tobytes() == ko.tobytes() and np.array_equal(d, do)
