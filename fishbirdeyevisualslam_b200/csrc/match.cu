@@ -489,7 +489,10 @@ __global__ void __launch_bounds__(kBfThreads) k_bruteforce(const uint8_t* __rest
             const uint4 b0 = s_t[2 * j], b1 = s_t[2 * j + 1];
             const int d = __popc(qd[0] ^ b0.x) + __popc(qd[1] ^ b0.y) + __popc(qd[2] ^ b0.z) + __popc(qd[3] ^ b0.w) +
                           __popc(qd[4] ^ b1.x) + __popc(qd[5] ^ b1.y) + __popc(qd[6] ^ b1.z) + __popc(qd[7] ^ b1.w);
-            top2_push(k1, k2, ((unsigned)d << 20) | (unsigned)(base + j));
+            // keep the two smallest keys with min/max only (no branches): k2' = min(k2, max(k1, k)), k1' = min(k1, k)
+            const unsigned k = ((unsigned)d << 20) | (unsigned)(base + j);
+            k2 = min(k2, max(k1, k));
+            k1 = min(k1, k);
         }
     }
     if (qi < nq) {

@@ -431,7 +431,8 @@ int fbe_bruteforce_top2(fbe_matcher* m, const uint8_t* q_desc, int32_t nq, const
     FBE_CUDA(cudaSetDevice(m->device));
     if (nq == 0) return FBE_OK;
     const int qblocks = (nq + 127) / 128;
-    int nchunks = std::max(1, std::min((2 * 148 + qblocks - 1) / qblocks, (nt + 255) / 256));
+    // enough CTAs for ~32 resident warps per SM: the POPC pipe (16 lanes/clk/SM) needs many warps in flight to stay busy
+    int nchunks = std::max(1, std::min((8 * 148 + qblocks - 1) / qblocks, (nt + 255) / 256));
     FBE_TRY(upload(m->qdesc, q_desc, (size_t)nq * 32, m->stream));
     FBE_TRY(upload(m->fa.desc, t_desc, (size_t)nt * 32, m->stream));
     FBE_TRY(m->partial.ensure((size_t)nchunks * nq * 8));
