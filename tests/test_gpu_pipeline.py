@@ -134,3 +134,60 @@ def test_async_submit_equals_sync_steps():
             if s or p:
                 assert np.array_equal(fm[s].array[p][:prev_nf], f[p][:prev_nf]) and np.array_equal(bm[s].array[p][:prev_nb], b[p][:prev_nb])
             prev_nf, prev_nb = int(r["n_front"][p]), int(r["n_bird"][p])
+
+
+def test_bench_size_properties():
+    """Size-independent properties at the bench shape (128 pairs per step, consecutive frames): the same 256 pairs as 2 x 128
+    and 4 x 64 give identical records and match lists; every match obeys the reference's acceptance rules; a sample of
+    pairs equals the oracle extraction bit for bit."""
+    import torch
+    from fishbirdeyevisualslam_b200 import _lib
+    from fishbirdeyevisualslam_b200.pipeline import FrontBirdPipeline
+    from oracle import oracle as O
+    n = 256
+    fr, bi = synth.cheap_batch(n, FH, FW, 900), synth.cheap_batch(n, BH, BW, 901)
+    dF, dB = torch.from_numpy(fr).cuda(), torch.from_numpy(bi).cuda()
+
+    def run(batch, keep=()):
+        pipe = FrontBirdPipeline(batch)
+        recs, fms, bms, kept = [], [], [], {}
+        for s in range(n // batch):
+            pipe.step_dev(dF[s * batch:].data_ptr(), dB[s * batch:].data_ptr())
+            res, fm, bm = pipe.fetch()
+            recs.append(res.copy()); fms.append(fm.copy()); bms.append(bm.copy())
+            for g in keep:
+                if s * batch <= g < (s + 1) * batch:
+                    kept[g] = pipe.fetch_pair(g - s * batch)
+        pipe.close()
+        return np.concatenate(recs), np.concatenate(fms), np.concatenate(bms), kept
+
+    sample = (0, 63, 64, 127, 128, 200, 255)
+    r1, f1, b1, k1 = run(128, sample + tuple(g - 1 for g in sample if g))
+    r2, f2, b2, _ = run(64)
+    assert r1.tobytes() == r2.tobytes()
+    assert (r1["n_front"] >= 2000).all() and (r1["n_bird"] >= 1000).all()
+    for g in range(1, n):
+        nq, nb = int(r1["n_front"][g - 1]), int(r1["n_bird"][g - 1])
+        assert np.array_equal(f1[g][:nq], f2[g][:nq]) and np.array_equal(b1[g][:nb], b2[g][:nb])
+        # front matches: one-to-one (the steal rule leaves at most one query per target), count = record
+        m = f1[g][:nq]
+        hit = m[m >= 0]
+        assert len(hit) == r1["front_matches"][g] and len(np.unique(hit)) == len(hit) and (hit < r1["n_front"][g]).all()
+        assert (b1[g][:nb] >= 0).sum() == r1["bird_matches"][g]
+    # accepted front matches obey TH_LOW on the actual descriptors, queries are octave-0 keypoints
+    for g in sample:
+        if g == 0:
+            continue
+        (qk, qd, _, _), (tk, td, _, _) = k1[g - 1], k1[g]
+        m = f1[g][:int(r1["n_front"][g - 1])]
+        qi = np.nonzero(m >= 0)[0]
+        assert (qk["octave"][qi] == 0).all()
+        d = np.unpackbits(qd[qi] ^ td[m[qi]], axis=1).sum(1)
+        assert (d <= 50).all()
+    # sampled pairs equal the oracle extraction
+    of, ob = O.OracleExtractor(2000, 1.2, 8, 15, 5), O.OracleExtractor(1000, 1.2, 8, 15, 5)
+    for g in (0, 127, 128, 255):
+        fk, fd, bk, bd = k1[g]
+        kf, df = of(fr[g]); kb, db = ob(bi[g])
+        assert fk[:len(kf)].tobytes() == kf.tobytes() and np.array_equal(fd[:len(kf)], df)
+        assert bk[:len(kb)].tobytes() == kb.tobytes() and np.array_equal(bd[:len(kb)], db)
