@@ -1,0 +1,3 @@
+// ORACLE (test infrastructure): see opencv2/core/core.hpp
+#pragma once
+#include "core/core.hpp"

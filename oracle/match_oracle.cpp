@@ -1,11 +1,14 @@
 // ORACLE (test infrastructure, never shipped, never on the product path).
 //
 // CPU restatement, on plain arrays, of the reference's keypoint grid and of the named ORBmatcher searches.
-// The reference translation units (src/Frame.cc, src/ORBmatcher.cc) drag in Eigen/g2o/DBoW2/OpenCV and cannot be
-// compiled in this image, so these functions follow the reference line by line instead (file:line below, relative
-// to /root/reference).  "parity unpinned" for this file: the reference ships no tests or golden vectors for these
-// paths; it is pinned only by review against the cited lines and by hand-built cases in
-// tests/test_oracle_match.py that exercise each documented quirk.
+// These functions follow the reference line by line on POD arrays (file:line below, relative to /root/reference).
+// PINNED: the reference ships no tests or golden vectors for these paths, so the pin is the reference's own
+// compiled code -- src/ORBmatcher.cc built VERBATIM against a header-only cv::Mat shim, together with the verbatim
+// Frame::AssignFeaturesToGrid / GetFeaturesInArea[Birdview], KeyFrame::GetFeaturesInArea, MapPoint::PredictScale and
+// Converter::BaseXY2BirdPixel (oracle/Makefile target `refmatch`, oracle/gen_ref_parts.py, oracle/ref_match_wrap.cpp ->
+// oracle/_ref/libfbe_refmatch.so).  tests/test_oracle_vs_refmatch.py demands equality with that build on seeded scenes
+// and, on machines without it, with its committed outputs (tests/golden/match.npz); tests/test_oracle_match.py adds an
+// independent pure-Python restatement and hand-built cases for each documented quirk.
 //   Frame::AssignFeaturesToGrid / PosInGrid / PosInGridBirdview   src/Frame.cc:381-411, 548-570
 //   Frame::GetFeaturesInArea / GetFeaturesInAreaBirdview           src/Frame.cc:493-546, 572-626
 //   ORBmatcher::DescriptorDistance                                 src/ORBmatcher.cc:1951-1967

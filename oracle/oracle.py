@@ -285,3 +285,109 @@ def fisheye_undistort(pts, K, D):
     out = np.empty_like(pts)
     lib().orc_fisheye_undistort(_p(pts), len(pts), _p(K), _p(D), _p(out))
     return out
+
+
+# ---- the reference's OWN matcher (src/ORBmatcher.cc compiled verbatim, oracle/_ref/libfbe_refmatch.so) -----------------
+_refm = None
+
+
+def refmatch():
+    """ctypes handle of the verbatim matcher build, or None when oracle/_ref was not built (no /root/reference)."""
+    global _refm
+    if _refm is None:
+        path = os.path.join(HERE, "_ref", "libfbe_refmatch.so")
+        if not os.path.exists(path):
+            return None
+        _refm = C.CDLL(path)
+    return _refm
+
+
+class RefMatch:
+    """Same call shapes as the restated functions above, executed by the reference's compiled code."""
+
+    def __init__(self):
+        self.L = refmatch()
+        assert self.L is not None
+
+    def grid_assign(self, kps, min_x, min_y, inv_w, inv_h, gcols, grows):
+        kps = np.ascontiguousarray(kps)
+        start = np.zeros(gcols * grows + 1, np.int32)
+        items = np.zeros(max(len(kps), 1), np.int32)
+        n = self.L.refm_grid_assign(_p(kps), len(kps), _fp(min_x), _fp(min_y), _fp(inv_w), _fp(inv_h), gcols, grows, _p(start), _p(items))
+        return start, items[:n].copy()
+
+    def features_in_area(self, f, x, y, r, min_level=-1, max_level=-1, upper_inclusive=True):
+        v = _view(f)
+        out = np.zeros(max(len(f.kps), 1), np.int32)
+        n = self.L.refm_features_in_area(C.byref(v), _fp(x), _fp(y), _fp(r), int(min_level), int(max_level), int(upper_inclusive), _p(out), len(out))
+        return out[:n].copy()
+
+    def search_for_initialization(self, f1, f2, prev_matched, window, nn_ratio, check_ori):
+        v1, v2 = _view(f1), _view(f2)
+        m12 = np.full(max(len(f1.kps), 1), -1, np.int32)
+        n = self.L.refm_search_for_initialization(C.byref(v1), C.byref(v2), _p(prev_matched), _p(m12), int(window), _fp(nn_ratio), int(check_ori))
+        return n, m12[:len(f1.kps)]
+
+    def birdview_match(self, ref_kps, ref_desc, cur, window, nn_ratio, check_ori):
+        v = _view(cur)
+        ref_kps = np.ascontiguousarray(ref_kps); ref_desc = np.ascontiguousarray(ref_desc, np.uint8)
+        dm = np.zeros((max(len(ref_kps), 1), 3), np.int32)
+        nd = C.c_int32()
+        n = self.L.refm_birdview_match(_p(ref_kps), _p(ref_desc), len(ref_kps), C.byref(v), int(window), _fp(nn_ratio), int(check_ori), _p(dm), C.byref(nd))
+        return n, dm[:nd.value].copy()
+
+    def bird_map_point_match(self, mp_base, mp_desc, cur, window, nn_ratio):
+        """-> (inliers, pixels the reference searched around [n,2] (NaN = rejected), assigned[cur.N])"""
+        v = _view(cur)
+        mp_base = np.ascontiguousarray(mp_base, np.float32); mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+        pix = np.zeros((len(mp_base), 2), np.float32)
+        assigned = np.full(max(len(cur.kps), 1), -1, np.int32)
+        n = self.L.refm_bird_map_point_match(_p(mp_base), _p(mp_desc), len(mp_base), C.byref(v), int(window), _fp(nn_ratio), _p(pix), _p(assigned))
+        return n, pix, assigned[:len(cur.kps)]
+
+    def search_by_projection_last(self, cur, last_kps, last_proj, last_mp_desc, scale_factors, th, check_ori, cur_taken=None, last_has_obs=None):
+        v = _view(cur)
+        last_kps = np.ascontiguousarray(last_kps); last_proj = np.ascontiguousarray(last_proj, np.float32)
+        last_mp_desc = np.ascontiguousarray(last_mp_desc, np.uint8); sf = np.ascontiguousarray(scale_factors, np.float32)
+        cur_mp = np.full(max(len(cur.kps), 1), -1, np.int32)
+        tk = None if cur_taken is None else np.ascontiguousarray(cur_taken, np.uint8)
+        ho = None if last_has_obs is None else np.ascontiguousarray(last_has_obs, np.uint8)
+        n = self.L.refm_search_by_projection_last(C.byref(v), _p(last_kps), _p(last_proj), _p(last_mp_desc), len(last_kps), _p(sf),
+                                                  None if tk is None else _p(tk), None if ho is None else _p(ho), _fp(th), int(check_ori), _p(cur_mp))
+        return n, cur_mp[:len(cur.kps)]
+
+    def search_by_projection_map(self, cur, scale_factors, mp_proj, mp_level, mp_viewcos, mp_desc, th, nn_ratio, cur_taken=None, mp_has_obs=None):
+        v = _view(cur)
+        sf = np.ascontiguousarray(scale_factors, np.float32); mp_proj = np.ascontiguousarray(mp_proj, np.float32)
+        mp_level = np.ascontiguousarray(mp_level, np.int32); mp_viewcos = np.ascontiguousarray(mp_viewcos, np.float32)
+        mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+        cur_mp = np.full(max(len(cur.kps), 1), -1, np.int32)
+        tk = None if cur_taken is None else np.ascontiguousarray(cur_taken, np.uint8)
+        ho = None if mp_has_obs is None else np.ascontiguousarray(mp_has_obs, np.uint8)
+        n = self.L.refm_search_by_projection_map(C.byref(v), _p(sf), _p(mp_proj), _p(mp_level), _p(mp_viewcos), _p(mp_desc), len(mp_level),
+                                                 None if tk is None else _p(tk), None if ho is None else _p(ho), _fp(th), _fp(nn_ratio), _p(cur_mp))
+        return n, cur_mp[:len(cur.kps)]
+
+    def search_by_projection_kf(self, cur, q_kps, proj, level, mp_desc, scale_factors, th, th_dist, level_up, check_ori, cur_taken=None):
+        v = _view(cur)
+        q_kps = np.ascontiguousarray(q_kps); proj = np.ascontiguousarray(proj, np.float32); level = np.ascontiguousarray(level, np.int32)
+        mp_desc = np.ascontiguousarray(mp_desc, np.uint8); sf = np.ascontiguousarray(scale_factors, np.float32)
+        cur_mp = np.full(max(len(cur.kps), 1), -1, np.int32)
+        tk = None if cur_taken is None else np.ascontiguousarray(cur_taken, np.uint8)
+        n = self.L.refm_search_by_projection_kf(C.byref(v), _p(q_kps), _p(proj), _p(level), _p(mp_desc), len(level), _p(sf),
+                                                None if tk is None else _p(tk), _fp(th), int(th_dist), int(level_up), int(check_ori), _p(cur_mp))
+        return n, cur_mp[:len(cur.kps)]
+
+    def search_by_bow(self, kf_kps, kf_desc, kf_has_mp, kf_fv, f_kps, f_desc, f_fv, nn_ratio, check_ori):
+        kf_kps = np.ascontiguousarray(kf_kps); kf_desc = np.ascontiguousarray(kf_desc, np.uint8)
+        kf_has_mp = np.ascontiguousarray(kf_has_mp, np.uint8)
+        f_kps = np.ascontiguousarray(f_kps); f_desc = np.ascontiguousarray(f_desc, np.uint8)
+        ka, kb, kc = (np.ascontiguousarray(a, np.int32) for a in kf_fv)
+        fa, fb, fc = (np.ascontiguousarray(a, np.int32) for a in f_fv)
+        f_mp = np.full(max(len(f_kps), 1), -1, np.int32)
+        n = self.L.refm_search_by_bow(_p(kf_kps), _p(kf_desc), len(kf_kps), _p(kf_has_mp), _p(ka), _p(kb), _p(kc), len(ka),
+                                      _p(f_kps), _p(f_desc), len(f_kps), _p(fa), _p(fb), _p(fc), len(fa), _fp(nn_ratio), int(check_ori), _p(f_mp))
+        return n, f_mp[:len(f_kps)]
+
+    def hamming256(self, a, b):
+        return self.L.refm_hamming256(_p(np.ascontiguousarray(a, np.uint8)), _p(np.ascontiguousarray(b, np.uint8)))

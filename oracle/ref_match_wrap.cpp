@@ -1,0 +1,423 @@
+// ORACLE (test infrastructure): C entry points around the reference's OWN ORBmatcher, compiled VERBATIM from
+// /root/reference/src/ORBmatcher.cc (plus the Frame / KeyFrame / MapPoint / Converter members it calls, cut out of the
+// reference sources at build time by oracle/gen_ref_parts.py) against oracle/cvshim_m.  Recipe: oracle/Makefile ->
+// oracle/_ref/libfbe_refmatch.so.  The entry points take the same POD arguments as the restated oracle
+// (oracle/match_oracle.cpp: orc_*), build real ORB_SLAM2::Frame / KeyFrame / MapPoint objects from them and call the
+// reference method, so that tests can demand  restated oracle == reference's compiled code  on the same inputs.
+//
+// What this file itself supplies are only members that are NOT on the hot path (constructors, trivial accessors of
+// MapPoint / MapPointBird / Map that the reference defines in translation units which cannot be compiled here); the
+// camera is the identity (fx = fy = 1, cx = cy = 0, Tcw = I), so a map point at world (u, v, 1) projects to exactly (u, v).
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <list>
+#include <map>
+#include <mutex>
+#include <set>
+#include <string>
+#include <vector>
+#include "ORBVocabulary.h"
+#include "opencv2/core/core.hpp"
+#define private public
+#define protected public
+#include "Frame.h"
+#include "KeyFrame.h"
+#include "Map.h"
+#include "MapPoint.h"
+#include "MapPointBird.h"
+#include "ORBmatcher.h"
+#include "Converter.h"
+#undef private
+#undef protected
+
+namespace ORB_SLAM2 {
+
+// ---- members the reference defines elsewhere; minimal equivalents for a test harness ---------------------------------
+long unsigned int MapPoint::nNextId = 0;
+std::mutex MapPoint::mGlobalMutex;
+MapPoint::MapPoint(const cv::Mat& Pos, KeyFrame* pRefKF, Map* pMap)
+    : mnFirstKFid(0), mnFirstFrame(0), nObs(0), mnTrackReferenceForFrame(0), mnLastFrameSeen(0), mnBALocalForKF(0), mnFuseCandidateForKF(0),
+      mnLoopPointForKF(0), mnCorrectedByKF(0), mnCorrectedReference(0), mnBAGlobalForKF(0), mpRefKF(pRefKF), mnVisible(1), mnFound(1),
+      mbBad(false), mpReplaced(static_cast<MapPoint*>(NULL)), mfMinDistance(0), mfMaxDistance(0), mpMap(pMap) {
+    Pos.copyTo(mWorldPos);
+    mNormalVector = cv::Mat::zeros(3, 1, CV_32F);
+    mnId = nNextId++;
+}
+cv::Mat MapPoint::GetWorldPos() { return mWorldPos.clone(); }
+cv::Mat MapPoint::GetNormal() { return mNormalVector.clone(); }
+cv::Mat MapPoint::GetDescriptor() { return mDescriptor.clone(); }
+bool MapPoint::isBad() { return mbBad; }
+int MapPoint::Observations() { return nObs; }
+bool MapPoint::IsInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) != 0; }
+void MapPoint::AddObservation(KeyFrame* pKF, size_t idx) { if (!mObservations.count(pKF)) { mObservations[pKF] = idx; nObs++; } }
+int MapPoint::GetIndexInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) ? (int)mObservations[pKF] : -1; }
+void MapPoint::Replace(MapPoint*) {}
+float MapPoint::GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }      // src/MapPoint.cc:373-377
+float MapPoint::GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }      // src/MapPoint.cc:379-383
+
+long unsigned int MapPointBird::nNextId = 0;
+MapPointBird::MapPointBird(const cv::Mat& Pos, KeyFrame* pRefKF, Map* pMap) : mpRefKF(pRefKF), mpMap(pMap) {
+    Pos.copyTo(mWorldPos);
+    mnId = nNextId++;
+}
+cv::Mat MapPointBird::GetWorldPos() { return mWorldPos.clone(); }
+cv::Mat MapPointBird::GetDescriptor() { return mDescriptor.clone(); }
+void MapPointBird::AddObservation(KeyFrame*, size_t) {}
+std::map<KeyFrame*, size_t> MapPointBird::GetObservations() { return mObservations; }
+void MapPointBird::ComputeDistinctiveDescriptors() {}
+void Map::AddMapPointBird(MapPointBird*) {}
+
+void KeyFrame::SetPose(const cv::Mat& Tcw_) { Tcw_.copyTo(Tcw); }
+cv::Mat KeyFrame::GetRotation() { return Tcw.rowRange(0, 3).colRange(0, 3).clone(); }
+cv::Mat KeyFrame::GetTranslation() { return Tcw.rowRange(0, 3).col(3).clone(); }
+cv::Mat KeyFrame::GetCameraCenter() { return cv::Mat::zeros(3, 1, CV_32F); }
+void KeyFrame::AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }
+std::set<MapPoint*> KeyFrame::GetMapPoints() { return std::set<MapPoint*>(); }
+
+}  // namespace ORB_SLAM2
+
+using namespace ORB_SLAM2;
+
+namespace {
+
+struct Kp { float x, y, size, angle, response; int32_t octave, class_id; };
+struct FrameView {
+    const Kp* kps;
+    const uint8_t* desc;
+    int32_t n;
+    float min_x, min_y, inv_w, inv_h;
+    int32_t gcols, grows;
+};
+
+std::vector<cv::KeyPoint> to_kps(const Kp* k, int n) {
+    std::vector<cv::KeyPoint> v(n);
+    static_assert(sizeof(cv::KeyPoint) == sizeof(Kp), "KeyPoint layout");
+    if (n) std::memcpy(v.data(), k, (size_t)n * sizeof(Kp));
+    return v;
+}
+cv::Mat to_desc(const uint8_t* d, int n) {
+    cv::Mat m(std::max(n, 0), 32, CV_8U);
+    for (int i = 0; i < n; ++i) std::memcpy(m.ptr(i), d + (size_t)i * 32, 32);
+    return m;
+}
+cv::Mat desc_row(const uint8_t* d) { return to_desc(d, 1); }
+cv::Mat point3(float x, float y, float z) { cv::Mat m(3, 1, CV_32F); m.at<float>(0) = x; m.at<float>(1) = y; m.at<float>(2) = z; return m; }
+
+const float kScale = 1.2f;
+const int kLevels = 8;
+
+void set_front_statics(const FrameView& f) {
+    Frame::fx = 1.f; Frame::fy = 1.f; Frame::cx = 0.f; Frame::cy = 0.f; Frame::invfx = 1.f; Frame::invfy = 1.f;
+    Frame::mnMinX = f.min_x; Frame::mnMinY = f.min_y;
+    Frame::mnMaxX = f.min_x + (float)FRAME_GRID_COLS / f.inv_w; Frame::mnMaxY = f.min_y + (float)FRAME_GRID_ROWS / f.inv_h;
+    Frame::mfGridElementWidthInv = f.inv_w; Frame::mfGridElementHeightInv = f.inv_h;
+}
+
+// a reference Frame holding `f` as its undistorted front keypoints, bucketed by the reference's own AssignFeaturesToGrid
+void fill_front(Frame& F, const FrameView& f, const float* scale_factors = nullptr) {
+    F.N = f.n; F.Nbird = 0;
+    F.mvKeys = to_kps(f.kps, f.n); F.mvKeysUn = F.mvKeys;
+    F.mDescriptors = to_desc(f.desc, f.n);
+    F.mvpMapPoints.assign(f.n, static_cast<MapPoint*>(NULL));
+    F.mvbOutlier.assign(f.n, false);
+    F.mnScaleLevels = kLevels; F.mfScaleFactor = kScale; F.mfLogScaleFactor = logf(kScale);
+    F.mvScaleFactors.assign(kLevels, 1.f);
+    for (int i = 0; i < kLevels; ++i) F.mvScaleFactors[i] = scale_factors ? scale_factors[i] : (i ? F.mvScaleFactors[i - 1] * kScale : 1.f);
+    F.mTcw = cv::Mat::eye(4, 4, CV_32F);
+    F.mb = 0.f; F.mbf = 0.f; F.mThDepth = 0.f;
+    F.mvuRight.assign(f.n, -1.f); F.mvDepth.assign(f.n, -1.f);
+    F.mpORBvocabulary = NULL; F.mpORBextractorLeft = NULL; F.mpORBextractorRight = NULL; F.mpReferenceKF = NULL;
+    F.mK = cv::Mat::eye(3, 3, CV_32F);
+    F.AssignFeaturesToGrid();
+}
+
+void fill_bird(Frame& F, const FrameView& f) {
+    F.N = 0; F.Nbird = f.n;
+    F.mvKeysBird = to_kps(f.kps, f.n);
+    F.mDescriptorsBird = to_desc(f.desc, f.n);
+    F.mvpMapPointsBird.assign(f.n, static_cast<MapPointBird*>(NULL));
+    Frame::mfGridElementWidthInvBirdview = f.inv_w; Frame::mfGridElementHeightInvBirdview = f.inv_h;
+    Frame::birdviewCols = (int)lroundf((float)FRAME_GRID_BIRD / f.inv_w); Frame::birdviewRows = (int)lroundf((float)FRAME_GRID_BIRD / f.inv_h);
+    F.mTcw = cv::Mat::eye(4, 4, CV_32F);
+    Frame::Tbc = cv::Mat::eye(4, 4, CV_32F);
+    F.AssignFeaturesToGrid();
+}
+
+MapPoint* make_mp(float u, float v, const uint8_t* desc, int level, int nobs) {
+    MapPoint* p = new MapPoint(point3(u, v, 1.f), NULL, NULL);
+    p->mDescriptor = desc_row(desc);
+    p->nObs = nobs;
+    // PredictScale = ceil(log(mfMaxDistance / dist) / log(1.2)): place the ratio half a level below `level`
+    const float dist = sqrtf(u * u + v * v + 1.f);
+    p->mfMaxDistance = dist * powf(kScale, (float)level - 0.5f);
+    p->mfMinDistance = 0.f;
+    p->mNormalVector = point3(u / dist, v / dist, 1.f / dist);        // viewing angle 0: passes the 60 degree test
+    return p;
+}
+
+struct Pool {       // owns the objects of one call
+    std::vector<MapPoint*> mps; std::vector<MapPointBird*> mpbs; std::vector<KeyFrame*> kfs;
+    ~Pool() { for (auto p : mps) delete p; for (auto p : mpbs) delete p; for (auto p : kfs) delete p; }
+};
+
+bool check_grid(const FrameView& f, int cols, int rows) { return f.gcols == cols && f.grows == rows; }
+
+}  // namespace
+
+extern "C" {
+
+// Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:381-411, 548-558) as CSR [ix*rows+iy]
+int refm_grid_assign(const Kp* kps, int n, float min_x, float min_y, float inv_w, float inv_h, int gcols, int grows,
+                     int32_t* cell_start, int32_t* cell_items) {
+    FrameView f{kps, nullptr, n, min_x, min_y, inv_w, inv_h, gcols, grows};
+    std::vector<uint8_t> zero((size_t)std::max(n, 1) * 32, 0);
+    f.desc = zero.data();
+    int off = 0;
+    Frame F;
+    if (gcols == FRAME_GRID_COLS && grows == FRAME_GRID_ROWS) {
+        set_front_statics(f); fill_front(F, f);
+        for (int ix = 0; ix < gcols; ++ix)
+            for (int iy = 0; iy < grows; ++iy) {
+                cell_start[ix * grows + iy] = off;
+                for (size_t j = 0; j < F.mGrid[ix][iy].size(); ++j) cell_items[off++] = (int)F.mGrid[ix][iy][j];
+            }
+    } else if (gcols == FRAME_GRID_BIRD && grows == FRAME_GRID_BIRD) {
+        fill_bird(F, f);
+        for (int ix = 0; ix < gcols; ++ix)
+            for (int iy = 0; iy < grows; ++iy) {
+                cell_start[ix * grows + iy] = off;
+                for (size_t j = 0; j < F.mGridBirdview[ix][iy].size(); ++j) cell_items[off++] = (int)F.mGridBirdview[ix][iy][j];
+            }
+    } else return -1;
+    cell_start[gcols * grows] = off;
+    return off;
+}
+
+// Frame::GetFeaturesInArea / GetFeaturesInAreaBirdview (src/Frame.cc:493-546, 572-626)
+int refm_features_in_area(const FrameView* f, float x, float y, float r, int minLevel, int maxLevel, int upper_inclusive,
+                          int32_t* out, int cap) {
+    Frame F;
+    std::vector<size_t> v;
+    if (upper_inclusive) { if (!check_grid(*f, FRAME_GRID_COLS, FRAME_GRID_ROWS)) return -1; set_front_statics(*f); fill_front(F, *f); v = F.GetFeaturesInArea(x, y, r, minLevel, maxLevel); }
+    else { if (!check_grid(*f, FRAME_GRID_BIRD, FRAME_GRID_BIRD)) return -1; fill_bird(F, *f); v = F.GetFeaturesInAreaBirdview(x, y, r, minLevel, maxLevel); }
+    for (size_t i = 0; i < v.size() && (int)i < cap; ++i) out[i] = (int)v[i];
+    return (int)v.size();
+}
+
+// ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:406-521)
+int refm_search_for_initialization(const FrameView* f1, const FrameView* f2, float* prev_matched, int32_t* matches12, int window,
+                                   float nn_ratio, int check_ori) {
+    if (!check_grid(*f2, FRAME_GRID_COLS, FRAME_GRID_ROWS)) return -1;
+    set_front_statics(*f2);
+    Frame F1, F2;
+    fill_front(F1, *f1); fill_front(F2, *f2);
+    std::vector<cv::Point2f> prev(f1->n);
+    for (int i = 0; i < f1->n; ++i) prev[i] = cv::Point2f(prev_matched[2 * i], prev_matched[2 * i + 1]);
+    std::vector<int> m12;
+    ORBmatcher m(nn_ratio, check_ori != 0);
+    const int n = m.SearchForInitialization(F1, F2, prev, m12, window);
+    for (int i = 0; i < f1->n; ++i) { matches12[i] = m12[i]; prev_matched[2 * i] = prev[i].x; prev_matched[2 * i + 1] = prev[i].y; }
+    return n;
+}
+
+// ORBmatcher::BirdviewMatch, isProject == 0 (src/ORBmatcher.cc:1602-1760)
+int refm_birdview_match(const Kp* ref_kps, const uint8_t* ref_desc, int n_ref, const FrameView* cur, int window, float nn_ratio,
+                        int check_ori, int32_t* dmatches, int32_t* n_dmatches) {
+    if (!check_grid(*cur, FRAME_GRID_BIRD, FRAME_GRID_BIRD)) return -1;
+    Frame F;
+    fill_bird(F, *cur);
+    std::vector<cv::KeyPoint> rk = to_kps(ref_kps, n_ref);
+    cv::Mat rd = to_desc(ref_desc, n_ref);
+    std::vector<MapPointBird*> rmp(n_ref, static_cast<MapPointBird*>(NULL));
+    std::vector<cv::DMatch> dm;
+    ORBmatcher m(nn_ratio, check_ori != 0);
+    const int n = m.BirdviewMatch(F, rk, rd, rmp, dm, 0, window);
+    for (size_t i = 0; i < dm.size(); ++i) { dmatches[3 * i] = dm[i].queryIdx; dmatches[3 * i + 1] = dm[i].trainIdx; dmatches[3 * i + 2] = (int)dm[i].distance; }
+    *n_dmatches = (int)dm.size();
+    return n;
+}
+
+// ORBmatcher::BirdMapPointMatch first pass (src/ORBmatcher.cc:1763-1863).  mp_base: n x 3 positions in the BASE frame
+// (Tbw = I here), NaN x = NULL map point.  The reference itself applies the |z| > 0.2 test, Converter::BaseXY2BirdPixel
+// and the image test; pix_out returns the pixel it searched around (NaN x = rejected) so that the restated oracle can be
+// given exactly the same input.  matches12 is recovered from mvpMapPointsBird with filterSize = +inf and camera points
+// equal to the map points... it is returned through the inlier assignment: assigned[k] = map point index or -1.
+int refm_bird_map_point_match(const float* mp_base, const uint8_t* mp_desc, int n_mp, const FrameView* cur, int window, float nn_ratio,
+                              float* pix_out, int32_t* assigned) {
+    if (!check_grid(*cur, FRAME_GRID_BIRD, FRAME_GRID_BIRD)) return -1;
+    Frame F;
+    fill_bird(F, *cur);
+    F.mvKeysBirdCamXYZ.assign(cur->n, cv::Point3f(0.f, 0.f, 0.f));
+    Pool pool;
+    std::vector<MapPointBird*> mps(n_mp, static_cast<MapPointBird*>(NULL));
+    std::map<MapPointBird*, int> index;
+    for (int i = 0; i < n_mp; ++i) {
+        pix_out[2 * i] = pix_out[2 * i + 1] = std::numeric_limits<float>::quiet_NaN();
+        if (std::isnan(mp_base[3 * i])) continue;
+        MapPointBird* p = new MapPointBird(point3(mp_base[3 * i], mp_base[3 * i + 1], mp_base[3 * i + 2]), NULL, NULL);
+        p->mDescriptor = desc_row(mp_desc + (size_t)i * 32);
+        pool.mpbs.push_back(p); mps[i] = p; index[p] = i;
+        if (fabs(mp_base[3 * i + 2]) > 0.2) continue;
+        const cv::Point2f pt = Converter::BaseXY2BirdPixel(cv::Point3f(mp_base[3 * i], mp_base[3 * i + 1], mp_base[3 * i + 2]));
+        if (pt.x < 0 || pt.x >= Frame::birdviewCols || pt.y < 0 || pt.y >= Frame::birdviewRows) continue;
+        pix_out[2 * i] = pt.x; pix_out[2 * i + 1] = pt.y;
+    }
+    ORBmatcher m(nn_ratio, true);
+    const int inl = m.BirdMapPointMatch(F, mps, window, std::numeric_limits<float>::infinity());
+    for (int k = 0; k < cur->n; ++k) assigned[k] = F.mvpMapPointsBird[k] ? index[F.mvpMapPointsBird[k]] : -1;
+    return inl;
+}
+
+// ORBmatcher::SearchByProjection(Frame&, const Frame& LastFrame, th, bMono = true) (src/ORBmatcher.cc:1329-1471)
+int refm_search_by_projection_last(const FrameView* cur, const Kp* last_kps, const float* last_proj, const uint8_t* last_mp_desc, int n_last,
+                                   const float* scale_factors, const uint8_t* cur_taken, const uint8_t* last_has_obs, float th, int check_ori,
+                                   int32_t* cur_mp) {
+    if (!check_grid(*cur, FRAME_GRID_COLS, FRAME_GRID_ROWS)) return -1;
+    set_front_statics(*cur);
+    Frame C, L;
+    fill_front(C, *cur, scale_factors);
+    FrameView lv = *cur; lv.kps = last_kps; lv.n = n_last;
+    std::vector<uint8_t> zero((size_t)std::max(n_last, 1) * 32, 0);
+    lv.desc = zero.data();
+    fill_front(L, lv, scale_factors);
+    Pool pool;
+    std::map<MapPoint*, int> index;
+    for (int i = 0; i < n_last; ++i) {
+        if (std::isnan(last_proj[2 * i])) continue;
+        MapPoint* p = make_mp(last_proj[2 * i], last_proj[2 * i + 1], last_mp_desc + (size_t)i * 32, 0, (!last_has_obs || last_has_obs[i]) ? 1 : 0);
+        pool.mps.push_back(p); L.mvpMapPoints[i] = p; index[p] = i;
+    }
+    // `blocker` stands for "a map point with observations" on taken keypoints; every other keypoint starts with `weak`, a
+    // map point WITHOUT observations (it does not block, :1404-1406), so that afterwards "untouched" (still weak) can be told
+    // from "assigned by this call and then set to NULL by the orientation check" (-2 in the C-ABI convention)
+    MapPoint* blocker = make_mp(0, 0, zero.data(), 0, 1);
+    MapPoint* weak = make_mp(0, 0, zero.data(), 0, 0);
+    pool.mps.push_back(blocker); pool.mps.push_back(weak);
+    for (int k = 0; k < cur->n; ++k) C.mvpMapPoints[k] = (cur_taken && cur_taken[k]) ? blocker : weak;
+    ORBmatcher m(0.9f, check_ori != 0);
+    const int n = m.SearchByProjection(C, L, th, true);
+    for (int k = 0; k < cur->n; ++k) {
+        MapPoint* p = C.mvpMapPoints[k];
+        cur_mp[k] = (p == blocker || p == weak) ? -1 : (p ? index[p] : -2);
+    }
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:46-130)
+int refm_search_by_projection_map(const FrameView* cur, const float* scale_factors, const float* mp_proj, const int32_t* mp_level,
+                                  const float* mp_viewcos, const uint8_t* mp_desc, int n_mp, const uint8_t* cur_taken,
+                                  const uint8_t* mp_has_obs, float th, float nn_ratio, int32_t* cur_mp) {
+    if (!check_grid(*cur, FRAME_GRID_COLS, FRAME_GRID_ROWS)) return -1;
+    set_front_statics(*cur);
+    Frame C;
+    fill_front(C, *cur, scale_factors);
+    Pool pool;
+    std::map<MapPoint*, int> index;
+    std::vector<MapPoint*> mps(n_mp);
+    for (int i = 0; i < n_mp; ++i) {
+        MapPoint* p = make_mp(0, 0, mp_desc + (size_t)i * 32, 0, (!mp_has_obs || mp_has_obs[i]) ? 1 : 0);
+        p->mbTrackInView = true; p->mTrackProjX = mp_proj[2 * i]; p->mTrackProjY = mp_proj[2 * i + 1];
+        p->mnTrackScaleLevel = mp_level[i]; p->mTrackViewCos = mp_viewcos[i];
+        pool.mps.push_back(p); mps[i] = p; index[p] = i;
+    }
+    std::vector<uint8_t> zero(32, 0);
+    MapPoint* blocker = make_mp(0, 0, zero.data(), 0, 1);
+    pool.mps.push_back(blocker);
+    for (int k = 0; k < cur->n; ++k) if (cur_taken && cur_taken[k]) C.mvpMapPoints[k] = blocker;
+    ORBmatcher m(nn_ratio, true);
+    const int n = m.SearchByProjection(C, mps, th);
+    for (int k = 0; k < cur->n; ++k) {
+        MapPoint* p = C.mvpMapPoints[k];
+        cur_mp[k] = (!p || p == blocker) ? -1 : index[p];
+    }
+    return n;
+}
+
+// relocalisation (src/ORBmatcher.cc:1473-1600, level_up = 1) and loop closing (:291-404, level_up = 0) SearchByProjection
+int refm_search_by_projection_kf(const FrameView* cur, const Kp* q_kps, const float* proj, const int32_t* level, const uint8_t* mp_desc,
+                                 int n_mp, const float* scale_factors, const uint8_t* cur_taken, float th, int th_dist, int level_up,
+                                 int check_ori, int32_t* cur_mp) {
+    if (!check_grid(*cur, FRAME_GRID_COLS, FRAME_GRID_ROWS)) return -1;
+    set_front_statics(*cur);
+    Pool pool;
+    std::map<MapPoint*, int> index;
+    std::vector<MapPoint*> mps(n_mp, static_cast<MapPoint*>(NULL));
+    for (int i = 0; i < n_mp; ++i) {
+        if (std::isnan(proj[2 * i])) continue;
+        MapPoint* p = make_mp(proj[2 * i], proj[2 * i + 1], mp_desc + (size_t)i * 32, level[i], 1);
+        pool.mps.push_back(p); mps[i] = p; index[p] = i;
+    }
+    std::vector<uint8_t> zero((size_t)std::max(n_mp, 1) * 32, 0);
+    MapPoint* blocker = make_mp(0, 0, zero.data(), 0, 1);
+    pool.mps.push_back(blocker);
+    int n = 0;
+    if (level_up == 1) {
+        // relocalisation: the map points hang on a key frame whose keypoints supply the angles
+        Frame C, K;
+        fill_front(C, *cur, scale_factors);
+        FrameView kv = *cur; kv.kps = q_kps; kv.n = n_mp; kv.desc = zero.data();
+        fill_front(K, kv, scale_factors);
+        K.mvpMapPoints = mps;
+        KeyFrame* kf = new KeyFrame(K, NULL, NULL);
+        pool.kfs.push_back(kf);
+        for (int k = 0; k < cur->n; ++k) if (cur_taken && cur_taken[k]) C.mvpMapPoints[k] = blocker;
+        ORBmatcher m(0.9f, check_ori != 0);
+        std::set<MapPoint*> found;
+        n = m.SearchByProjection(C, kf, found, th, th_dist);
+        for (int k = 0; k < cur->n; ++k) {
+            MapPoint* p = C.mvpMapPoints[k];
+            if (cur_taken && cur_taken[k]) cur_mp[k] = p == blocker ? -1 : (p ? index[p] : -2);
+            else cur_mp[k] = p ? index[p] : -1;
+        }
+    } else {
+        // loop closing: the searched frame is a key frame; Scw = identity; candidate points come as a list
+        Frame K;
+        fill_front(K, *cur, scale_factors);
+        KeyFrame* kf = new KeyFrame(K, NULL, NULL);
+        pool.kfs.push_back(kf);
+        std::vector<MapPoint*> pts, matched(cur->n, static_cast<MapPoint*>(NULL));
+        std::vector<int> pt_index;
+        for (int i = 0; i < n_mp; ++i) if (mps[i]) { pts.push_back(mps[i]); pt_index.push_back(i); }
+        for (int k = 0; k < cur->n; ++k) if (cur_taken && cur_taken[k]) matched[k] = blocker;
+        ORBmatcher m(0.75f, true);
+        n = m.SearchByProjection(kf, cv::Mat::eye(4, 4, CV_32F), pts, matched, (int)th);
+        for (int k = 0; k < cur->n; ++k) cur_mp[k] = (!matched[k] || matched[k] == blocker) ? -1 : index[matched[k]];
+    }
+    return n;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, matches) (src/ORBmatcher.cc:160-289)
+int refm_search_by_bow(const Kp* kf_kps, const uint8_t* kf_desc, int n_kf, const uint8_t* kf_has_mp, const int32_t* kf_node_ids,
+                       const int32_t* kf_start, const int32_t* kf_items, int kf_nn, const Kp* f_kps, const uint8_t* f_desc, int n_f,
+                       const int32_t* f_node_ids, const int32_t* f_start, const int32_t* f_items, int f_nn, float nn_ratio, int check_ori,
+                       int32_t* f_mp) {
+    FrameView kv{kf_kps, kf_desc, n_kf, 0.f, 0.f, 64.f / 1280.f, 48.f / 720.f, FRAME_GRID_COLS, FRAME_GRID_ROWS};
+    FrameView fv{f_kps, f_desc, n_f, 0.f, 0.f, 64.f / 1280.f, 48.f / 720.f, FRAME_GRID_COLS, FRAME_GRID_ROWS};
+    set_front_statics(kv);
+    Frame K, F;
+    fill_front(K, kv); fill_front(F, fv);
+    Pool pool;
+    std::map<MapPoint*, int> index;
+    std::vector<uint8_t> zero(32, 0);
+    for (int i = 0; i < n_kf; ++i)
+        if (kf_has_mp[i]) { MapPoint* p = make_mp(0, 0, zero.data(), 0, 1); pool.mps.push_back(p); K.mvpMapPoints[i] = p; index[p] = i; }
+    for (int a = 0; a < kf_nn; ++a)
+        for (int p = kf_start[a]; p < kf_start[a + 1]; ++p) K.mFeatVec[kf_node_ids[a]].push_back((unsigned)kf_items[p]);
+    for (int b = 0; b < f_nn; ++b)
+        for (int p = f_start[b]; p < f_start[b + 1]; ++p) F.mFeatVec[f_node_ids[b]].push_back((unsigned)f_items[p]);
+    KeyFrame* kf = new KeyFrame(K, NULL, NULL);
+    pool.kfs.push_back(kf);
+    std::vector<MapPoint*> out;
+    ORBmatcher m(nn_ratio, check_ori != 0);
+    const int n = m.SearchByBoW(kf, F, out);
+    for (int k = 0; k < n_f; ++k) f_mp[k] = out[k] ? index[out[k]] : -1;
+    return n;
+}
+
+int refm_hamming256(const uint8_t* a, const uint8_t* b) { return ORBmatcher::DescriptorDistance(desc_row(a), desc_row(b)); }
+
+}  // extern "C"
