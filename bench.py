@@ -208,6 +208,10 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # NCCL prints its version banner on stdout; keep stdout for the single JSON line (everything else goes to stderr)
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = _lib.load()
@@ -339,7 +343,10 @@ def run_ours(args):
                                  "sample": f"{2 * threads} pairs ({2} consecutive pairs on each of {threads} host threads)"},
                 "check": {"mean_front_kps": float(res["n_front"].mean()), "mean_bird_kps": float(res["n_bird"].mean()),
                           "mean_front_matches": float(res["front_matches"].mean()), "mean_bird_matches": float(res["bird_matches"].mean())}}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
