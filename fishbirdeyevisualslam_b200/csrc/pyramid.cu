@@ -9,45 +9,55 @@
 
 namespace fbe {
 
-__device__ __forceinline__ int reflect101_dev(int p, int len) {
-    // |p| excursion is at most 19 and len >= 20 for every level that passes build_plan, one fold suffices;
-    // the loop keeps it correct for any len.
-    if (len == 1) return 0;
-    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
-    return p;
+
+// Level 0 in two launches so that no warp mixes the two paths:
+//   k_level0       : interior 16-byte chunks (destination column d holds source column d - 19, i.e. the source is displaced
+//                    by 3 bytes modulo 4): one 32-bit + one 128-bit aligned load of the source row, realigned by a funnel
+//                    shift, one 128-bit store.  Needs a 16-byte aligned source (base, pitch, image stride).
+//   k_level0_border: the chunks that touch the reflected frame (and every chunk of an unaligned source): per-byte
+//                    REFLECT_101 gather (one fold suffices: the excursion is 19 and every level is at least 20 px).
+__device__ __forceinline__ int reflect101_once(int p, int len) {
+    p = p < 0 ? -p : p;
+    return p >= len ? 2 * (len - 1) - p : p;
 }
 
-// Level 0: a thread writes 16 padded bytes (one 128-bit store).  Interior chunks come from one 32-bit + one 128-bit
-// aligned load of the source row, realigned by a funnel shift (destination column d holds source column d - 19, i.e.
-// the source is displaced by 3 bytes modulo 4); chunks touching the reflected frame, and sources whose base / pitch is
-// not 16-byte aligned, take the per-byte path.
-__global__ void __launch_bounds__(256) k_level0(const Plan* __restrict__ plan, Workspace ws, int aligned16) {
+__global__ void __launch_bounds__(256) k_level0(const Plan* __restrict__ plan, Workspace ws, int first_chunk, int nchunks) {
     const LevelGeom& g = plan->lv[0];
-    const int c16 = (blockIdx.x * 32 + threadIdx.x) * 16;
+    const int ci = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
     const int b = blockIdx.z;
-    const int w = g.w, pitch = g.pitch;
-    if (c16 >= pitch || y >= g.ph) return;
-    const uint8_t* row = ws.in + (size_t)b * ws.in_slot_stride + (size_t)reflect101_dev(y - kEdge, g.h) * ws.in_pitch;
+    if (ci >= nchunks || y >= g.ph) return;
+    const int c16 = (first_chunk + ci) * 16;
+    const uint8_t* row = ws.in + (size_t)b * ws.in_slot_stride + (size_t)reflect101_once(y - kEdge, g.h) * ws.in_pitch;
+    const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(row + c16 - 20));
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(row + c16 - 16));
     uint4 o;
-    if (aligned16 && c16 >= 32 && c16 <= w) {          // source bytes c16-20 .. c16-1 all inside the row
-        const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(row + c16 - 20));
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(row + c16 - 16));
-        o.x = __funnelshift_r(w0, q.x, 8); o.y = __funnelshift_r(q.x, q.y, 8);
-        o.z = __funnelshift_r(q.y, q.z, 8); o.w = __funnelshift_r(q.z, q.w, 8);
-    } else {
-        uint32_t v[4] = {0, 0, 0, 0};
+    o.x = __funnelshift_r(w0, q.x, 8); o.y = __funnelshift_r(q.x, q.y, 8);
+    o.z = __funnelshift_r(q.y, q.z, 8); o.w = __funnelshift_r(q.z, q.w, 8);
+    uint8_t* dst = ws.pyr + (size_t)b * plan->pyr_bytes + g.img_off;
+    *reinterpret_cast<uint4*>(dst + (size_t)y * g.pitch + c16) = o;
+}
+
+// border chunks: chunk index = bc < nlead ? bc : first_tail + (bc - nlead)
+__global__ void __launch_bounds__(256) k_level0_border(const Plan* __restrict__ plan, Workspace ws, int nlead, int first_tail, int nborder) {
+    const LevelGeom& g = plan->lv[0];
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int b = blockIdx.z;
+    const int y = t / nborder, bc = t - y * nborder;
+    if (y >= g.ph) return;
+    const int c16 = (bc < nlead ? bc : first_tail + (bc - nlead)) * 16;
+    const int w = g.w;
+    const uint8_t* row = ws.in + (size_t)b * ws.in_slot_stride + (size_t)reflect101_once(y - kEdge, g.h) * ws.in_pitch;
+    uint32_t v[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int x = c16 + i;
-            uint32_t px = 0;
-            if (x < w + 2 * kEdge) px = row[reflect101_dev(x - kEdge, w)];
-            v[i >> 2] |= px << (8 * (i & 3));
-        }
-        o = make_uint4(v[0], v[1], v[2], v[3]);
+    for (int i = 0; i < 16; ++i) {
+        const int x = c16 + i;
+        uint32_t px = 0;
+        if (x < w + 2 * kEdge) px = row[reflect101_once(x - kEdge, w)];
+        v[i >> 2] |= px << (8 * (i & 3));
     }
     uint8_t* dst = ws.pyr + (size_t)b * plan->pyr_bytes + g.img_off;
-    *reinterpret_cast<uint4*>(dst + (size_t)y * pitch + c16) = o;
+    *reinterpret_cast<uint4*>(dst + (size_t)y * g.pitch + c16) = make_uint4(v[0], v[1], v[2], v[3]);
 }
 
 // One CTA = 128 output columns x 64 output rows of one padded level; a thread owns 4 adjacent columns and walks 8 rows.
@@ -178,8 +188,19 @@ int launch_pyramid(const Plan& hp, const Plan* dp, const Workspace& ws, const Re
         const LevelGeom& g = hp.lv[l];
         if (l == 0) {
             const int aligned16 = ((reinterpret_cast<uintptr_t>(ws.in) | (uintptr_t)ws.in_pitch | (uintptr_t)ws.in_slot_stride) & 15) == 0;
-            dim3 grid((g.pitch / 16 + 31) / 32, (g.ph + 7) / 8, nimg);
-            k_level0<<<grid, dim3(32, 8), 0, st>>>(dp, ws, aligned16);
+            const int nchunk = g.pitch / 16;
+            // interior chunks: source bytes c16-20 .. c16-1 all inside the row  <=>  32 <= c16 <= w
+            const int first = 2, last = std::min(g.w / 16, nchunk - 1);
+            const int nint = (aligned16 && last >= first) ? last - first + 1 : 0;
+            if (nint > 0) {
+                dim3 grid((nint + 31) / 32, (g.ph + 7) / 8, nimg);
+                k_level0<<<grid, dim3(32, 8), 0, st>>>(dp, ws, first, nint);
+                count_launch();
+            }
+            const int nlead = nint > 0 ? first : nchunk, first_tail = last + 1;
+            const int nborder = nint > 0 ? nlead + (nchunk - first_tail) : nchunk;
+            dim3 bgrid((g.ph * nborder + 255) / 256, 1, nimg);
+            k_level0_border<<<bgrid, 256, 0, st>>>(dp, ws, nlead, first_tail, nborder);
         } else {
             dim3 rgrid((g.pitch + kRsTW - 1) / kRsTW, (g.ph + kRsTH - 1) / kRsTH, nimg);
             if (g.rs_bw > 0) {
