@@ -336,6 +336,9 @@ def run_ours(args):
                              "frac": achieved / peak, "traffic": FAST_DRAM_BYTES_PER_FRONT_IMAGE * B, "peak_source": peak_src,
                              "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of k_fast_cells (front), per image x images per launch; profiles/r1_02_fast_ncu.md",
                              "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": fast_ms,
+                             "note": "k_fast_cells is instruction-bound, not memory-bound: ncu (profiles/r1_02_fast_ncu.md) shows 79-81 % issue-slot "
+                                     "utilisation, 72 % alu pipe, 3.0 warp-instructions per SM per clock and 4 % of DRAM throughput; ~100 integer "
+                                     "instructions per pixel bound it, so frac of the HBM peak stays small by construction",
                              "whole_step": {"bytes_per_pair": BYTES_PER_PAIR, "achieved_gbs": value / world * BYTES_PER_PAIR / 1e9,
                                             "frac": value / world * BYTES_PER_PAIR / 1e9 / peak}},
                 "stage_ms": stage_ms,
