@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(ResolveArgs a, int 
                     if (lvl1 == lvl2 && (float)bestDist > __fmul_rn(a.nn_ratio, (float)bestDist2)) accept = false;
                 }
             } break;
-            default: accept = bestDist <= FBE_TH_LOW && (float)bestDist < __fmul_rn(a.nn_ratio, (float)bestDist2); break;
+            default: accept = bestDist <= (a.th_dist > 0 ? a.th_dist : FBE_TH_LOW) && (float)bestDist < __fmul_rn(a.nn_ratio, (float)bestDist2); break;
         }
         if (!accept) continue;
         if (lane == 0) {

@@ -364,10 +364,13 @@ int fbe_search_by_projection_map(fbe_matcher* m, const fbe_frame_view* cur, cons
     return projection_search(m, kResolveMap, cur, q, lv, mp_desc, nullptr, n_mp, cur_taken, mp_has_obs, nullptr, 0, cur_mp, nmatches);
 }
 
-int fbe_search_by_bow(fbe_matcher* m, const fbe_keypoint* kf_kps, const uint8_t* kf_desc, int32_t n_kf, const uint8_t* kf_has_mp,
+// shared body of the two SearchByBoW overloads: f_blocked[k] != 0 keeps frame / key-frame-2 feature k out of the search
+// from the start (KF-KF: no good map point); strict_low selects `< TH_LOW` (:599) instead of `<= TH_LOW` (:247)
+static int bow_search(fbe_matcher* m, const fbe_keypoint* kf_kps, const uint8_t* kf_desc, int32_t n_kf, const uint8_t* kf_has_mp,
                       const int32_t* kf_node_ids, const int32_t* kf_start, const int32_t* kf_items, int32_t kf_nn,
                       const fbe_keypoint* f_kps, const uint8_t* f_desc, int32_t n_f, const int32_t* f_node_ids,
-                      const int32_t* f_start, const int32_t* f_items, int32_t f_nn, int32_t* f_mp, int32_t* nmatches) {
+                      const int32_t* f_start, const int32_t* f_items, int32_t f_nn, const uint8_t* f_blocked, int strict_low,
+                      int32_t* f_mp, int32_t* nmatches) {
     if (!m || !nmatches || n_kf < 0 || n_f < 0 || kf_nn < 0 || f_nn < 0 || (n_f > 0 && !f_mp)) return FBE_E_INVALID;
     FBE_CUDA(cudaSetDevice(m->device));
     *nmatches = 0;
@@ -407,7 +410,8 @@ int fbe_search_by_bow(fbe_matcher* m, const fbe_keypoint* kf_kps, const uint8_t*
     FBE_TRY(m->rows.ensure((size_t)nq * C * 4)); FBE_TRY(m->cnt.ensure((size_t)nq * 4));
     FBE_TRY(m->i0.ensure((size_t)n_f * 4)); FBE_TRY(m->i3.ensure((size_t)nq * 4)); FBE_TRY(m->i4.ensure((size_t)nq * 4));
     FBE_TRY(m->u0.ensure((size_t)n_f)); FBE_TRY(m->misc.ensure(64));
-    FBE_CUDA(cudaMemsetAsync(m->u0.p, 0, (size_t)n_f, m->stream));
+    if (f_blocked) FBE_CUDA(cudaMemcpyAsync(m->u0.p, f_blocked, (size_t)n_f, cudaMemcpyHostToDevice, m->stream));
+    else FBE_CUDA(cudaMemsetAsync(m->u0.p, 0, (size_t)n_f, m->stream));
     FBE_TRY(launch_bow_rows(m->fb.desc.as<uint8_t>(), m->fa.desc.as<uint8_t>(), m->i1.as<int>(), m->i2.as<int>(), m->partial.as<int>(),
                             m->fa.items.as<int>(), nq, C, m->rows.as<unsigned>(), m->cnt.as<int>(), m->stream));
     ResolveArgs r{};
@@ -415,12 +419,40 @@ int fbe_search_by_bow(fbe_matcher* m, const fbe_keypoint* kf_kps, const uint8_t*
     r.q_stride = nq; r.t_stride = n_f; r.nt = m->fa.n.as<int>(); r.q_kps = m->fb.kps.as<fbe_keypoint>(); r.q_src = m->i1.as<int>();
     r.t_kps = m->fa.kps.as<fbe_keypoint>(); r.q_has_obs = nullptr; r.nn_ratio = m->nn_ratio; r.check_ori = m->check_ori;
     r.taken = m->u0.as<uint8_t>(); r.cur_mp = m->i0.as<int>(); r.q_bin = m->i3.as<int>(); r.q_hit = m->i4.as<int>();
-    r.nmatches = m->misc.as<int>();
+    r.nmatches = m->misc.as<int>(); r.th_dist = strict_low ? FBE_TH_LOW - 1 : 0;
     // q_kps is indexed by the key-frame keypoint index: give the resolve kernel a q_stride-independent view
     FBE_TRY(launch_resolve(r, 1, m->stream));
     FBE_CUDA(cudaMemcpyAsync(f_mp, m->i0.p, (size_t)n_f * 4, cudaMemcpyDeviceToHost, m->stream));
     FBE_CUDA(cudaMemcpyAsync(nmatches, m->misc.p, 4, cudaMemcpyDeviceToHost, m->stream));
     FBE_CUDA(cudaStreamSynchronize(m->stream));
+    return FBE_OK;
+}
+
+int fbe_search_by_bow(fbe_matcher* m, const fbe_keypoint* kf_kps, const uint8_t* kf_desc, int32_t n_kf, const uint8_t* kf_has_mp,
+                      const int32_t* kf_node_ids, const int32_t* kf_start, const int32_t* kf_items, int32_t kf_nn,
+                      const fbe_keypoint* f_kps, const uint8_t* f_desc, int32_t n_f, const int32_t* f_node_ids,
+                      const int32_t* f_start, const int32_t* f_items, int32_t f_nn, int32_t* f_mp, int32_t* nmatches) {
+    return bow_search(m, kf_kps, kf_desc, n_kf, kf_has_mp, kf_node_ids, kf_start, kf_items, kf_nn, f_kps, f_desc, n_f, f_node_ids, f_start,
+                      f_items, f_nn, nullptr, 0, f_mp, nmatches);
+}
+
+int fbe_search_by_bow_kf(fbe_matcher* m, const fbe_keypoint* kf1_kps, const uint8_t* kf1_desc, int32_t n1, const uint8_t* kf1_has_mp,
+                         const int32_t* kf1_node_ids, const int32_t* kf1_start, const int32_t* kf1_items, int32_t kf1_nn,
+                         const fbe_keypoint* kf2_kps, const uint8_t* kf2_desc, int32_t n2, const uint8_t* kf2_has_mp,
+                         const int32_t* kf2_node_ids, const int32_t* kf2_start, const int32_t* kf2_items, int32_t kf2_nn,
+                         int32_t* matches12, int32_t* nmatches) {
+    if (!m || !nmatches || n1 < 0 || n2 < 0 || (n1 > 0 && !matches12) || (n2 > 0 && !kf2_has_mp)) return FBE_E_INVALID;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    std::vector<uint8_t> blocked(std::max(n2, 1));
+    for (int k = 0; k < n2; ++k) blocked[k] = kf2_has_mp[k] ? 0 : 1;          // `!pMP2 || pMP2->isBad()` (:575-579)
+    std::vector<int32_t> f_mp(std::max(n2, 1), -1);
+    const int rc = bow_search(m, kf1_kps, kf1_desc, n1, kf1_has_mp, kf1_node_ids, kf1_start, kf1_items, kf1_nn, kf2_kps, kf2_desc, n2,
+                              kf2_node_ids, kf2_start, kf2_items, kf2_nn, blocked.data(), 1, f_mp.data(), nmatches);
+    if (rc != FBE_OK) return rc;
+    // the search assigns every key-frame-2 feature at most once (vbMatched2) and every key-frame-1 feature at most once, so
+    // the target-indexed result inverts into vpMatches12; entries removed by the orientation check stay -1 (NULL, :646)
+    for (int k = 0; k < n2; ++k)
+        if (f_mp[k] >= 0 && f_mp[k] < n1) matches12[f_mp[k]] = k;
     return FBE_OK;
 }
 

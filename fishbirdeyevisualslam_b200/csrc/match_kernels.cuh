@@ -45,7 +45,8 @@ struct ResolveArgs {
     const uint8_t* q_has_obs;    // LAST/MAP: assigned map point blocks its keypoint (NULL = all)
     float nn_ratio;
     int check_ori;
-    int th_dist;                 // LAST: acceptance bound (0 = TH_HIGH; reloc passes ORBdist, loop closing TH_LOW)
+    int th_dist;                 // LAST: acceptance bound (0 = TH_HIGH; reloc passes ORBdist, loop closing TH_LOW); BOW: 0 = TH_LOW,
+                                 //       TH_LOW - 1 for the key-frame/key-frame overload (`< TH_LOW`)
     // state / outputs
     int* matched_dist;           // INIT: [nb][t_stride] scratch (vMatchedDistance)
     int* match21;                // INIT: [nb][t_stride] scratch (vnMatches21)

@@ -1,11 +1,11 @@
 // Drop-in bodies for the ORBmatcher methods on the hot path.  This file is compiled INSIDE the reference tree in place
 // of the same-named method bodies of src/ORBmatcher.cc (see INTEGRATION.md for the exact patch); the class declaration
 // include/ORBmatcher.h is unchanged, so Tracking.cc / LocalMapping.cc / LoopClosing.cc call it as before.  Methods that
-// are not on the hot path (SearchForTriangulation, SearchBySim3, Fuse x2, the KF-KF SearchByBoW) keep the reference's own CPU code.
+// are not on the hot path (SearchForTriangulation, SearchBySim3, Fuse x2) keep the reference's own CPU code.
 //
-// It cannot be compiled in the build image of this repository (needs the reference's Frame.h/KeyFrame.h/MapPoint.h with
-// OpenCV, Eigen, DBoW2); the marshalling below is mirrored, field for field, by the Python host
-// (fishbirdeyevisualslam_b200/matcher.py), which IS tested against the oracle on the GPU.
+// In the build image of this repository it is compiled against the reference's own headers with OpenCV replaced by the
+// test shim oracle/cvshim_m (oracle/Makefile target `dropinmatch`) and checked on the GPU against the outputs of the
+// reference's verbatim CPU build (tests/test_gpu_dropin_match.py).
 //
 // Everything pointer-valued stays on the host: frames are flattened to (keypoints, descriptors, grid geometry),
 // map points to (projection, level, descriptor) arrays; the C-ABI returns index lists which are turned back into
@@ -264,24 +264,31 @@ int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMap
     return nmatches;
 }
 
+namespace {
+// DBoW2::FeatureVector = std::map<NodeId, std::vector<unsigned int>> -> CSR over ascending node ids
+struct Csr { std::vector<int> ids, start, items; };
+Csr flatten(const DBoW2::FeatureVector& fv) {
+    Csr c;
+    c.start.push_back(0);
+    for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+        c.ids.push_back((int)it->first);
+        c.items.insert(c.items.end(), it->second.begin(), it->second.end());
+        c.start.push_back((int)c.items.size());
+    }
+    return c;
+}
+std::vector<unsigned char> good_points(const std::vector<MapPoint*>& v) {
+    std::vector<unsigned char> has(v.size(), 0);
+    for (size_t i = 0; i < v.size(); i++) has[i] = v[i] && !v[i]->isBad();
+    return has;
+}
+}  // namespace
+
 // src/ORBmatcher.cc:160-289
 int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches) {
     const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
     vpMapPointMatches = std::vector<MapPoint*>(F.N, static_cast<MapPoint*>(NULL));
-    std::vector<unsigned char> has_mp(vpMapPointsKF.size(), 0);
-    for (size_t i = 0; i < vpMapPointsKF.size(); i++) has_mp[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();
-    // DBoW2::FeatureVector = std::map<NodeId, std::vector<unsigned int>> -> CSR over ascending node ids
-    struct Csr { std::vector<int> ids, start, items; };
-    auto flatten = [](const DBoW2::FeatureVector& fv) {
-        Csr c;
-        c.start.push_back(0);
-        for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
-            c.ids.push_back((int)it->first);
-            c.items.insert(c.items.end(), it->second.begin(), it->second.end());
-            c.start.push_back((int)c.items.size());
-        }
-        return c;
-    };
+    const std::vector<unsigned char> has_mp = good_points(vpMapPointsKF);
     Csr a = flatten(pKF->mFeatVec), b = flatten(F.mFeatVec);
     std::vector<int> f_mp(F.N, -1);
     int nmatches = 0;
@@ -291,6 +298,24 @@ int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpM
                       F.N, b.ids.data(), b.start.data(), b.items.data(), (int)b.ids.size(), f_mp.data(), &nmatches);
     for (int k = 0; k < F.N; k++)
         if (f_mp[k] >= 0) vpMapPointMatches[k] = vpMapPointsKF[f_mp[k]];
+    return nmatches;
+}
+
+// src/ORBmatcher.cc:523-656 (loop closing: key frame against key frame)
+int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12) {
+    const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+    vpMatches12 = std::vector<MapPoint*>(vpMapPoints1.size(), static_cast<MapPoint*>(NULL));
+    const std::vector<unsigned char> has1 = good_points(vpMapPoints1), has2 = good_points(vpMapPoints2);
+    Csr a = flatten(pKF1->mFeatVec), b = flatten(pKF2->mFeatVec);
+    std::vector<int> m12(std::max<size_t>(vpMapPoints1.size(), 1), -1);
+    int nmatches = 0;
+    fbe_search_by_bow_kf(matcher_for(mfNNratio, mbCheckOrientation), reinterpret_cast<const fbe_keypoint*>(pKF1->mvKeysUn.data()),
+                         desc_ptr(pKF1->mDescriptors), (int)vpMapPoints1.size(), has1.data(), a.ids.data(), a.start.data(), a.items.data(),
+                         (int)a.ids.size(), reinterpret_cast<const fbe_keypoint*>(pKF2->mvKeysUn.data()), desc_ptr(pKF2->mDescriptors),
+                         (int)vpMapPoints2.size(), has2.data(), b.ids.data(), b.start.data(), b.items.data(), (int)b.ids.size(),
+                         m12.data(), &nmatches);
+    for (size_t i = 0; i < vpMapPoints1.size(); i++)
+        if (m12[i] >= 0) vpMatches12[i] = vpMapPoints2[m12[i]];
     return nmatches;
 }
 

@@ -247,6 +247,19 @@ class ORBmatcher:
                                         ptr(F.kps), ptr(F.desc), F.N, ptr(fa), ptr(fb), ptr(fc), len(fa), ptr(f_mp), C.byref(n)))
         return n.value, f_mp[:F.N]
 
+    def SearchByBoWKF(self, kf1_kps, kf1_desc, kf1_has_mp, kf1_featvec, kf2_kps, kf2_desc, kf2_has_mp, kf2_featvec):
+        """SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (loop closing, ORBmatcher.cc:523-656).
+        -> (nmatches, matches12[int32 n1] = key-frame-2 feature index per key-frame-1 feature or -1)."""
+        k1 = np.ascontiguousarray(kf1_kps); d1 = np.ascontiguousarray(kf1_desc, np.uint8); h1 = np.ascontiguousarray(kf1_has_mp, np.uint8)
+        k2 = np.ascontiguousarray(kf2_kps); d2 = np.ascontiguousarray(kf2_desc, np.uint8); h2 = np.ascontiguousarray(kf2_has_mp, np.uint8)
+        a1, b1, c1 = (np.ascontiguousarray(a, np.int32) for a in kf1_featvec)
+        a2, b2, c2 = (np.ascontiguousarray(a, np.int32) for a in kf2_featvec)
+        m12 = np.full(max(len(k1), 1), -1, np.int32)
+        n = C.c_int32()
+        check(self._L.fbe_search_by_bow_kf(self._h, ptr(k1), ptr(d1), len(k1), ptr(h1), ptr(a1), ptr(b1), ptr(c1), len(a1),
+                                           ptr(k2), ptr(d2), len(k2), ptr(h2), ptr(a2), ptr(b2), ptr(c2), len(a2), ptr(m12), C.byref(n)))
+        return n.value, m12[:len(k1)]
+
     def BruteForceTop2(self, q_desc, t_desc):
         q_desc = np.ascontiguousarray(q_desc, np.uint8)
         t_desc = np.ascontiguousarray(t_desc, np.uint8)

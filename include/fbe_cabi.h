@@ -223,6 +223,17 @@ FBE_API int fbe_search_by_bow(fbe_matcher* m, const fbe_keypoint* kf_kps, const 
                       int32_t n_f, const int32_t* f_node_ids, const int32_t* f_start, const int32_t* f_items,
                       int32_t f_nn, int32_t* f_mp, int32_t* nmatches);
 
+/* ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12), src/ORBmatcher.cc:523-656 (loop
+ * closing).  Both sides are key frames: kfX_has_mp[i] != 0 iff feature i has a good map point.  Differences to the
+ * frame overload: `bestDist1 < TH_LOW` (strict), key-frame-2 features are blocked once matched (vbMatched2), the result
+ * is indexed by key-frame-1 feature.  Output: matches12[i] = key-frame-2 feature index whose map point is assigned to
+ * feature i of key frame 1, -1 none. */
+FBE_API int fbe_search_by_bow_kf(fbe_matcher* m, const fbe_keypoint* kf1_kps, const uint8_t* kf1_desc, int32_t n1,
+                                 const uint8_t* kf1_has_mp, const int32_t* kf1_node_ids, const int32_t* kf1_start,
+                                 const int32_t* kf1_items, int32_t kf1_nn, const fbe_keypoint* kf2_kps, const uint8_t* kf2_desc,
+                                 int32_t n2, const uint8_t* kf2_has_mp, const int32_t* kf2_node_ids, const int32_t* kf2_start,
+                                 const int32_t* kf2_items, int32_t kf2_nn, int32_t* matches12, int32_t* nmatches);
+
 /* Brute-force Hamming top-2 (stress config C5): for each of nq queries best / second-best over nt targets,
  * ties -> lowest target index (traversal order). */
 FBE_API int fbe_bruteforce_top2(fbe_matcher* m, const uint8_t* q_desc, int32_t nq, const uint8_t* t_desc, int32_t nt,

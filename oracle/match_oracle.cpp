@@ -470,6 +470,50 @@ int orc_search_by_bow(const Kp* kf_kps, const uint8_t* kf_desc, int n_kf, const 
 }
 
 // brute-force top-2 (stress config C5): ties -> lowest target index, second counts duplicates
+// SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12)  src/ORBmatcher.cc:523-656 (loop closing): both sides key frames,
+// `bestDist1 < TH_LOW` strict, vbMatched2 blocks matched key-frame-2 features, result indexed by key-frame-1 feature.
+int orc_search_by_bow_kf(const Kp* k1, const uint8_t* d1, int n1, const uint8_t* has1, const int32_t* ids1, const int32_t* st1,
+                         const int32_t* it1, int nn1, const Kp* k2, const uint8_t* d2, int n2, const uint8_t* has2,
+                         const int32_t* ids2, const int32_t* st2, const int32_t* it2, int nn2, float nn_ratio, int check_ori,
+                         int32_t* matches12) {
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    std::vector<uint8_t> vbMatched2(std::max(n2, 1), 0);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int nmatches = 0, a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (ids1[a] == ids2[b]) {
+            for (int p1 = st1[a]; p1 < st1[a + 1]; ++p1) {
+                const int idx1 = it1[p1];
+                if (!has1[idx1]) continue;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int p2 = st2[b]; p2 < st2[b + 1]; ++p2) {
+                    const int idx2 = it2[p2];
+                    if (vbMatched2[idx2] || !has2[idx2]) continue;
+                    const int dist = hamming(d1 + (size_t)idx1 * 32, d2 + (size_t)idx2 * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < TH_LOW && (float)bestDist1 < nn_ratio * (float)bestDist2) {
+                    matches12[idx1] = bestIdx2;
+                    vbMatched2[bestIdx2] = 1;
+                    if (check_ori) rotHist[rot_bin(k1[idx1].angle, k2[bestIdx2].angle)].push_back(idx1);
+                    nmatches++;
+                }
+            }
+            ++a; ++b;
+        } else if (ids1[a] < ids2[b]) ++a;
+        else ++b;
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); ++j) { matches12[rotHist[i][j]] = -1; nmatches--; }
+    }
+    return nmatches;
+}
+
 void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* best_idx, int32_t* best_dist,
                          int32_t* second_dist) {
     for (int i = 0; i < nq; ++i) {

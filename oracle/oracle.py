@@ -271,6 +271,18 @@ def search_by_bow(kf_kps, kf_desc, kf_has_mp, kf_fv, f_kps, f_desc, f_fv, nn_rat
     return n, f_mp[:len(f_kps)]
 
 
+def search_by_bow_kf(k1, d1, has1, fv1, k2, d2, has2, fv2, nn_ratio, check_ori, _L=None, _fn="orc_search_by_bow_kf"):
+    """SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (loop closing) -> (nmatches, matches12[n1] = key-frame-2 feature or -1)."""
+    k1 = np.ascontiguousarray(k1); d1 = np.ascontiguousarray(d1, np.uint8); has1 = np.ascontiguousarray(has1, np.uint8)
+    k2 = np.ascontiguousarray(k2); d2 = np.ascontiguousarray(d2, np.uint8); has2 = np.ascontiguousarray(has2, np.uint8)
+    a1, b1, c1 = (np.ascontiguousarray(a, np.int32) for a in fv1)
+    a2, b2, c2 = (np.ascontiguousarray(a, np.int32) for a in fv2)
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    n = getattr(_L or lib(), _fn)(_p(k1), _p(d1), len(k1), _p(has1), _p(a1), _p(b1), _p(c1), len(a1), _p(k2), _p(d2), len(k2), _p(has2),
+                                 _p(a2), _p(b2), _p(c2), len(a2), _fp(nn_ratio), int(check_ori), _p(m12))
+    return n, m12[:len(k1)]
+
+
 def bruteforce_top2(q, t):
     q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
     bi, bd, sd = (np.zeros(max(len(q), 1), np.int32) for _ in range(3))
@@ -302,11 +314,27 @@ def refmatch():
     return _refm
 
 
-class RefMatch:
-    """Same call shapes as the restated functions above, executed by the reference's compiled code."""
+_dropm = None
 
-    def __init__(self):
-        self.L = refmatch()
+
+def dropinmatch():
+    """ctypes handle of the DROP-IN matcher build (the reference's ORBmatcher class with host/ORBmatcher_fbe.cc's bodies on
+    libfbe_b200.so, oracle/Makefile target dropinmatch), or None when it was not built.  Needs a GPU to be called."""
+    global _dropm
+    if _dropm is None:
+        path = os.path.join(HERE, "_ref", "libfbe_dropinmatch.so")
+        if not os.path.exists(path):
+            return None
+        _dropm = C.CDLL(path)
+    return _dropm
+
+
+class RefMatch:
+    """Same call shapes as the restated functions above, executed by the reference's compiled code (or, with
+    lib=dropinmatch(), by the reference's class with the drop-in bodies)."""
+
+    def __init__(self, lib=None):
+        self.L = lib if lib is not None else refmatch()
         assert self.L is not None
 
     def grid_assign(self, kps, min_x, min_y, inv_w, inv_h, gcols, grows):
@@ -388,6 +416,9 @@ class RefMatch:
         n = self.L.refm_search_by_bow(_p(kf_kps), _p(kf_desc), len(kf_kps), _p(kf_has_mp), _p(ka), _p(kb), _p(kc), len(ka),
                                       _p(f_kps), _p(f_desc), len(f_kps), _p(fa), _p(fb), _p(fc), len(fa), _fp(nn_ratio), int(check_ori), _p(f_mp))
         return n, f_mp[:len(f_kps)]
+
+    def search_by_bow_kf(self, k1, d1, has1, fv1, k2, d2, has2, fv2, nn_ratio, check_ori):
+        return search_by_bow_kf(k1, d1, has1, fv1, k2, d2, has2, fv2, nn_ratio, check_ori, _L=self.L, _fn="refm_search_by_bow_kf")
 
     def hamming256(self, a, b):
         return self.L.refm_hamming256(_p(np.ascontiguousarray(a, np.uint8)), _p(np.ascontiguousarray(b, np.uint8)))

@@ -418,6 +418,32 @@ int refm_search_by_bow(const Kp* kf_kps, const uint8_t* kf_desc, int n_kf, const
     return n;
 }
 
+// ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (src/ORBmatcher.cc:523-656)
+int refm_search_by_bow_kf(const Kp* k1, const uint8_t* d1, int n1, const uint8_t* has1, const int32_t* ids1, const int32_t* st1,
+                          const int32_t* it1, int nn1, const Kp* k2, const uint8_t* d2, int n2, const uint8_t* has2, const int32_t* ids2,
+                          const int32_t* st2, const int32_t* it2, int nn2, float nn_ratio, int check_ori, int32_t* matches12) {
+    FrameView v1{k1, d1, n1, 0.f, 0.f, 64.f / 1280.f, 48.f / 720.f, FRAME_GRID_COLS, FRAME_GRID_ROWS};
+    FrameView v2{k2, d2, n2, 0.f, 0.f, 64.f / 1280.f, 48.f / 720.f, FRAME_GRID_COLS, FRAME_GRID_ROWS};
+    set_front_statics(v1);
+    Frame F1, F2;
+    fill_front(F1, v1); fill_front(F2, v2);
+    Pool pool;
+    std::map<MapPoint*, int> index2;
+    std::vector<uint8_t> zero(32, 0);
+    for (int i = 0; i < n1; ++i) if (has1[i]) { MapPoint* p = make_mp(0, 0, zero.data(), 0, 1); pool.mps.push_back(p); F1.mvpMapPoints[i] = p; }
+    for (int i = 0; i < n2; ++i) if (has2[i]) { MapPoint* p = make_mp(0, 0, zero.data(), 0, 1); pool.mps.push_back(p); F2.mvpMapPoints[i] = p; index2[p] = i; }
+    for (int a = 0; a < nn1; ++a) for (int p = st1[a]; p < st1[a + 1]; ++p) F1.mFeatVec[ids1[a]].push_back((unsigned)it1[p]);
+    for (int b = 0; b < nn2; ++b) for (int p = st2[b]; p < st2[b + 1]; ++p) F2.mFeatVec[ids2[b]].push_back((unsigned)it2[p]);
+    KeyFrame* kf1 = new KeyFrame(F1, NULL, NULL);
+    KeyFrame* kf2 = new KeyFrame(F2, NULL, NULL);
+    pool.kfs.push_back(kf1); pool.kfs.push_back(kf2);
+    std::vector<MapPoint*> out;
+    ORBmatcher m(nn_ratio, check_ori != 0);
+    const int n = m.SearchByBoW(kf1, kf2, out);
+    for (int i = 0; i < n1; ++i) matches12[i] = out[i] ? index2[out[i]] : -1;
+    return n;
+}
+
 int refm_hamming256(const uint8_t* a, const uint8_t* b) { return ORBmatcher::DescriptorDistance(desc_row(a), desc_row(b)); }
 
 }  // extern "C"

@@ -356,3 +356,46 @@ def search_by_bow(kf_kps, kf_desc, kf_has_mp, kfv, f_kps, f_desc, ffv, ratio, or
                 f_mp[k] = -2
                 nm -= 1
     return nm, np.array(f_mp, np.int32)
+
+
+def search_by_bow_kf(k1, d1, has1, fv1, k2, d2, has2, fv2, ratio, ori):
+    """key frame vs key frame (ORBmatcher.cc:523-656): strict TH_LOW, matched key-frame-2 features are blocked."""
+    (a1, s1, i1), (a2, s2, i2) = fv1, fv2
+    m12 = [-1] * len(k1)
+    used2 = [False] * len(k2)
+    hist = [[] for _ in range(HISTO)]
+    nm = 0
+    map2 = {int(n): j for j, n in enumerate(a2)}
+    for a, node in enumerate(a1):
+        b = map2.get(int(node))
+        if b is None:
+            continue
+        for p in range(s1[a], s1[a + 1]):
+            x1 = int(i1[p])
+            if not has1[x1]:
+                continue
+            best = best2 = 256
+            bi = -1
+            for q in range(s2[b], s2[b + 1]):
+                x2 = int(i2[q])
+                if used2[x2] or not has2[x2]:
+                    continue
+                d = ham(d1[x1], d2[x2])
+                if d < best:
+                    best2, best, bi = best, d, x2
+                elif d < best2:
+                    best2 = d
+            if best < TH_LOW and F32(best) < F32(ratio) * F32(best2):
+                m12[x1] = bi
+                used2[bi] = True
+                if ori:
+                    hist[rot_bin(k1["angle"][x1], k2["angle"][bi])].append(x1)
+                nm += 1
+    if ori:
+        keep = three_maxima(hist)
+        for b in range(HISTO):
+            if b not in keep:
+                for x1 in hist[b]:
+                    m12[x1] = -1
+                    nm -= 1
+    return nm, np.array(m12, np.int32)

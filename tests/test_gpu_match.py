@@ -192,6 +192,14 @@ def test_search_by_bow(oracle, front_pair):
         n_g, f_g = ORBmatcher(ratio, ori).SearchByBoW(F1.kps, F1.desc, has_mp, kfv, F2, ffv)
         n_o, f_o = oracle.search_by_bow(F1.kps, F1.desc, has_mp, kfv, F2.kps, F2.desc, ffv, ratio, ori)
         assert n_g == n_o and np.array_equal(f_g, f_o) and n_g > 50
+    # key frame vs key frame (loop closing): strict threshold, matched key-frame-2 features blocked, result indexed by kf1
+    has_mp2 = (np.random.default_rng(9).random(F2.N) < 0.85).astype(np.uint8)
+    one1, one2 = featvec(np.zeros(F1.N, int)), featvec(np.zeros(F2.N, int))
+    for fv1, fv2 in ((kfv, ffv), (one1, one2)):
+        for ratio, ori in [(0.75, True), (0.9, False)]:
+            n_g, m_g = ORBmatcher(ratio, ori).SearchByBoWKF(F1.kps, F1.desc, has_mp, fv1, F2.kps, F2.desc, has_mp2, fv2)
+            n_o, m_o = oracle.search_by_bow_kf(F1.kps, F1.desc, has_mp, fv1, F2.kps, F2.desc, has_mp2, fv2, ratio, ori)
+            assert n_g == n_o and np.array_equal(m_g, m_o) and n_g > 50
 
 
 @pytest.mark.parametrize("seed", range(3))

@@ -94,6 +94,14 @@ def test_search_by_bow(oracle, seed):
         n_p, f_p = pyref.search_by_bow(F1.kps, F1.desc, has_mp, featvec(node1), F2.kps, F2.desc, featvec(node2), ratio, ori)
         n_o, f_o = oracle.search_by_bow(F1.kps, F1.desc, has_mp, featvec(node1), F2.kps, F2.desc, featvec(node2), ratio, ori)
         assert n_o == n_p and np.array_equal(f_o, f_p)
+    has_mp2 = (rng.random(F2.N) < 0.7).astype(np.uint8)
+    for n1, n2 in ((node1, node2), (np.zeros(F1.N, int), np.zeros(F2.N, int))):     # second: one node, full contention
+        for ratio, ori in [(0.75, True), (0.95, False)]:
+            n_p, m_p = pyref.search_by_bow_kf(F1.kps, F1.desc, has_mp, featvec(n1), F2.kps, F2.desc, has_mp2, featvec(n2), ratio, ori)
+            n_o, m_o = oracle.search_by_bow_kf(F1.kps, F1.desc, has_mp, featvec(n1), F2.kps, F2.desc, has_mp2, featvec(n2), ratio, ori)
+            assert n_o == n_p and np.array_equal(m_o, m_p)
+            hit = m_o[m_o >= 0]
+            assert len(np.unique(hit)) == len(hit) and has_mp2[hit].all() and has_mp[m_o >= 0].all()
 
 
 # ---- hand-built quirk cases ------------------------------------------------------------------

@@ -86,13 +86,18 @@ def scene_outputs(impl, seed, is_ref):
         n, c = impl.search_by_projection_map(F2, sf, mproj, mlev, mcos, mdesc, th, ratio, taken, ho)
         out[f"map{j}"] = np.concatenate([[n], c]).astype(np.int32)
     # SearchByBoW on synthetic vocabulary nodes
-    node1 = rng.integers(0, 40, F1.N)
-    node2 = np.concatenate([node1[rng.permutation(F1.N)], rng.integers(0, 40, F2.N - F1.N)])
+    def spatial_nodes(k, dx, dy):                    # same scene point -> (mostly) the same word, like a real vocabulary
+        return (np.floor((k["x"] - dx) / 64).astype(int) * 16 + np.floor((k["y"] - dy) / 60).astype(int)) * 4 + np.minimum(k["octave"], 3)
+    node1, node2 = spatial_nodes(F1.kps, 0, 0), spatial_nodes(F2.kps, 3, 2)
     has_mp = (rng.random(F1.N) < 0.8).astype(np.uint8)
     for j, (ratio, ori) in enumerate([(0.7, True), (0.9, False)]):
         n, c = impl.search_by_bow(F1.kps, F1.desc, has_mp, featvec(node1), F2.kps, F2.desc, featvec(node2), ratio, ori)
         c = np.where(c == -2, -1, c)
         out[f"bow{j}"] = np.concatenate([[n], c]).astype(np.int32)
+    has_mp2 = (rng.random(F2.N) < 0.85).astype(np.uint8)
+    for j, (ratio, ori) in enumerate([(0.75, True), (0.9, False)]):            # key frame vs key frame (loop closing)
+        n, c = impl.search_by_bow_kf(F1.kps, F1.desc, has_mp, featvec(node1), F2.kps, F2.desc, has_mp2, featvec(node2), ratio, ori)
+        out[f"bowkf{j}"] = np.concatenate([[n], c]).astype(np.int32)
     return out
 
 
@@ -116,6 +121,7 @@ def test_restated_oracle_equals_verbatim_reference(oracle, seed):
             continue
         assert np.array_equal(got[k], v, equal_nan=True), k
     assert ref["init0"][0] > 20 and ref["bird0"][0] > 10 and ref["last0"][0] > 50 and ref["map0"][0] > 50 and ref["birdmap"][0] > 20
+    assert ref["bow1"][0] > 50 and ref["bowkf0"][0] > 50
 
 
 @pytest.mark.parametrize("seed", SEEDS)
