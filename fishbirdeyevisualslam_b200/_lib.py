@@ -37,6 +37,13 @@ class FrameView(C.Structure):
                 ("gcols", C.c_int32), ("grows", C.c_int32)]
 
 
+class FrustumView(C.Structure):
+    """fbe_frustum_view (include/fbe_cabi.h): the Frame members Frame::isInFrustum reads."""
+    _fields_ = [("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("Ow", C.c_float * 3), ("fx", C.c_float), ("fy", C.c_float),
+                ("cx", C.c_float), ("cy", C.c_float), ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float),
+                ("max_y", C.c_float), ("mbf", C.c_float), ("log_scale_factor", C.c_float), ("n_levels", C.c_int32)]
+
+
 class PipelineCfg(C.Structure):
     _fields_ = [("front", ExtractorCfg), ("bird", ExtractorCfg),
                 ("front_rows", C.c_int32), ("front_cols", C.c_int32), ("bird_rows", C.c_int32), ("bird_cols", C.c_int32),

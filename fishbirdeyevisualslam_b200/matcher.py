@@ -70,6 +70,22 @@ def UndistortKeyPoints(kps: np.ndarray, K, D, device: int = 0) -> np.ndarray:
     return out
 
 
+def isInFrustum(view, pos, normal, min_dist, max_dist, viewing_cos_limit: float, device: int = 0):
+    """Frame::isInFrustum (Frame.cc:435-491) for n map points at once.  `view` is a _lib.FrustumView (or anything with the
+    same ctypes layout); pos / normal n x 3, min_dist / max_dist = mfMinDistance / mfMaxDistance.
+    -> dict(in_view u8, proj n x 2, proj_xr, level, view_cos): mbTrackInView, mTrackProjX/Y, mTrackProjXR, mnTrackScaleLevel,
+    mTrackViewCos per point."""
+    L = _lib.load()
+    pos = np.ascontiguousarray(pos, np.float32); normal = np.ascontiguousarray(normal, np.float32)
+    mn = np.ascontiguousarray(min_dist, np.float32); mx = np.ascontiguousarray(max_dist, np.float32)
+    n = len(pos)
+    o = dict(in_view=np.zeros(n, np.uint8), proj=np.zeros((n, 2), np.float32), proj_xr=np.zeros(n, np.float32),
+             level=np.zeros(n, np.int32), view_cos=np.zeros(n, np.float32))
+    check(L.fbe_is_in_frustum(C.byref(view), ptr(pos), ptr(normal), ptr(mn), ptr(mx), C.c_int32(n), C.c_float(float(viewing_cos_limit)),
+                              C.c_int32(device), ptr(o["in_view"]), ptr(o["proj"]), ptr(o["proj_xr"]), ptr(o["level"]), ptr(o["view_cos"])))
+    return o
+
+
 def ComputeImageBounds(cols: int, rows: int, K, D, device: int = 0):
     """Frame::ComputeImageBounds (Frame.cc:741-795) -> (mnMinX, mnMaxX, mnMinY, mnMaxY)."""
     L = _lib.load()

@@ -112,6 +112,32 @@ FBE_API int fbe_debug_blurred(fbe_extractor* e, int32_t slot, int32_t level, uin
 FBE_API int fbe_debug_octree(const int32_t* xys, int32_t n, int32_t min_x, int32_t max_x, int32_t min_y, int32_t max_y,
                      int32_t nfeat, int32_t* sel, int32_t cap, int32_t* n_sel);
 
+/* ---- Frame::isInFrustum (next row f-2) ------------------------------------------------------------- */
+/* The pose and calibration members Frame::isInFrustum reads (src/Frame.cc:435-491): mRcw (row-major 3x3), mtcw, mOw as
+ * Frame::UpdatePoseMatrices left them (:425-433 stays on the host), fx fy cx cy, the image bounds, mbf, and the scale
+ * pyramid members MapPoint::PredictScale(dist, Frame*) reads (src/MapPoint.cc:402-417). */
+typedef struct fbe_frustum_view {
+    float Rcw[9], tcw[3], Ow[3];
+    float fx, fy, cx, cy;
+    float min_x, max_x, min_y, max_y; /* mnMinX, mnMaxX, mnMinY, mnMaxY */
+    float mbf;
+    float log_scale_factor;           /* mfLogScaleFactor */
+    int32_t n_levels;                 /* mnScaleLevels */
+} fbe_frustum_view;
+/* Frame::isInFrustum for n map points at once (Tracking::SearchLocalPoints calls it per local map point,
+ * src/Tracking.cc; its outputs are the query set of SearchByProjection(Frame&, vector<MapPoint*>&, th)).
+ * pos / normal: n x 3 floats (GetWorldPos, GetNormal); min_dist / max_dist: mfMinDistance / mfMaxDistance (the 0.8 / 1.2
+ * invariance factors of src/MapPoint.cc:373-383 are applied inside).  Arithmetic follows OpenCV's for these cv::Mat
+ * expressions (3x3 * 3x1 + 3x1 through the small-matrix gemm path: float products and sums left to right, the addend in
+ * double; cv::norm and Mat::dot accumulate in double), pinned against cv2 4.13 in tests/test_frustum.py.
+ * Outputs per point: in_view (mbTrackInView), proj = (mTrackProjX, mTrackProjY), proj_xr = mTrackProjXR, level =
+ * mnTrackScaleLevel, view_cos = mTrackViewCos; entries of rejected points are left as 0.  Any output pointer may be NULL.
+ * Parity bar: in_view / proj / view_cos bit-equal to the oracle; level equal except where logf(ratio) / mfLogScaleFactor
+ * lies within 4 ulp of an integer (device logf vs glibc logf), which the oracle flags. */
+FBE_API int fbe_is_in_frustum(const fbe_frustum_view* v, const float* pos, const float* normal, const float* min_dist,
+                              const float* max_dist, int32_t n, float viewing_cos_limit, int32_t device, uint8_t* in_view,
+                              float* proj, float* proj_xr, int32_t* level, float* view_cos);
+
 /* ---- Frame undistortion (next row f-1) ----------------------------------------------------------- */
 /* Frame::UndistortKeyPoints, src/Frame.cc:638-669: cv::fisheye::undistortPoints(pts, pts, mK, mDistCoef, Mat(), mK) on the
  * keypoint positions (OpenCV 4.13 semantics: double-precision Newton solve, <= 10 iterations, eps 1e-8; (-1e6,-1e6) when

@@ -514,6 +514,51 @@ int orc_search_by_bow_kf(const Kp* k1, const uint8_t* d1, int n1, const uint8_t*
     return nmatches;
 }
 
+// Frame::isInFrustum  src/Frame.cc:435-491 with MapPoint::PredictScale(dist, Frame*)  src/MapPoint.cc:402-417 and the
+// invariance distances  src/MapPoint.cc:373-383.  The cv::Mat expressions are evaluated the way OpenCV evaluates them
+// (pinned against cv2 4.13 by tests/test_frustum.py): `mRcw*P+mtcw` is ONE gemm through the small-matrix path -- float
+// products and sums left to right, then (float)((double)t*alpha + (double)c*beta); cv::norm and Mat::dot accumulate in
+// double.  `level_boundary` flags points whose predicted level sits within 4 ulp of an integer quotient (the only place
+// where a different-but-valid logf may change the answer).
+struct FrustumView { float Rcw[9], tcw[3], Ow[3], fx, fy, cx, cy, min_x, max_x, min_y, max_y, mbf, log_scale_factor; int32_t n_levels; };
+void orc_is_in_frustum(const FrustumView* v, const float* pos, const float* normal, const float* min_dist, const float* max_dist,
+                       int n, float cos_limit, uint8_t* in_view, float* proj, float* proj_xr, int32_t* level, float* view_cos,
+                       uint8_t* level_boundary) {
+    for (int i = 0; i < n; ++i) {
+        in_view[i] = 0; proj[2 * i] = proj[2 * i + 1] = 0.f; proj_xr[i] = 0.f; level[i] = 0; view_cos[i] = 0.f; level_boundary[i] = 0;
+        const float* P = pos + 3 * i;
+        float Pc[3];
+        for (int r = 0; r < 3; ++r) {
+            const float t = v->Rcw[3 * r] * P[0] + v->Rcw[3 * r + 1] * P[1] + v->Rcw[3 * r + 2] * P[2];
+            Pc[r] = (float)((double)t * 1.0 + (double)v->tcw[r] * 1.0);
+        }
+        const float PcX = Pc[0], PcY = Pc[1], PcZ = Pc[2];
+        if (PcZ < 0.0f) continue;
+        const float invz = 1.0f / PcZ;
+        const float u = v->fx * PcX * invz + v->cx;
+        const float w = v->fy * PcY * invz + v->cy;
+        if (u < v->min_x || u > v->max_x) continue;
+        if (w < v->min_y || w > v->max_y) continue;
+        const float maxDistance = 1.2f * max_dist[i], minDistance = 0.8f * min_dist[i];
+        const float PO[3] = {P[0] - v->Ow[0], P[1] - v->Ow[1], P[2] - v->Ow[2]};
+        double ss = 0;
+        for (int k = 0; k < 3; ++k) ss += (double)PO[k] * (double)PO[k];
+        const float dist = (float)std::sqrt(ss);
+        if (dist < minDistance || dist > maxDistance) continue;
+        double dot = 0;
+        for (int k = 0; k < 3; ++k) dot += (double)PO[k] * (double)normal[3 * i + k];
+        const float viewCos = (float)(dot / dist);
+        if (viewCos < cos_limit) continue;
+        const float ratio = max_dist[i] / dist;
+        const float q = std::log(ratio) / v->log_scale_factor;                 // float overloads (using namespace std in the reference TU)
+        int nScale = (int)std::ceil(q);
+        if (nScale < 0) nScale = 0;
+        else if (nScale >= v->n_levels) nScale = v->n_levels - 1;
+        level_boundary[i] = std::fabs(q - std::nearbyint(q)) <= 4.f * 1.1920929e-7f * std::fmax(1.f, std::fabs(q));
+        in_view[i] = 1; proj[2 * i] = u; proj[2 * i + 1] = w; proj_xr[i] = u - v->mbf * invz; level[i] = nScale; view_cos[i] = viewCos;
+    }
+}
+
 void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* best_idx, int32_t* best_dist,
                          int32_t* second_dist) {
     for (int i = 0; i < nq; ++i) {

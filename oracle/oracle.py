@@ -283,6 +283,35 @@ def search_by_bow_kf(k1, d1, has1, fv1, k2, d2, has2, fv2, nn_ratio, check_ori, 
     return n, m12[:len(k1)]
 
 
+class FrustumViewC(C.Structure):
+    _fields_ = [("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("Ow", C.c_float * 3), ("fx", C.c_float), ("fy", C.c_float),
+                ("cx", C.c_float), ("cy", C.c_float), ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float),
+                ("max_y", C.c_float), ("mbf", C.c_float), ("log_scale_factor", C.c_float), ("n_levels", C.c_int32)]
+
+
+def frustum_view(Rcw, tcw, Ow, K, bounds, mbf, log_scale_factor, n_levels):
+    v = FrustumViewC()
+    v.Rcw[:] = [float(x) for x in np.asarray(Rcw, np.float32).ravel()]
+    v.tcw[:] = [float(x) for x in np.asarray(tcw, np.float32).ravel()]
+    v.Ow[:] = [float(x) for x in np.asarray(Ow, np.float32).ravel()]
+    v.fx, v.fy, v.cx, v.cy = (float(np.float32(x)) for x in K)
+    v.min_x, v.max_x, v.min_y, v.max_y = (float(np.float32(x)) for x in bounds)
+    v.mbf, v.log_scale_factor, v.n_levels = float(np.float32(mbf)), float(np.float32(log_scale_factor)), int(n_levels)
+    return v
+
+
+def is_in_frustum(view, pos, normal, min_dist, max_dist, cos_limit):
+    """Frame::isInFrustum for n map points -> dict(in_view, proj, proj_xr, level, view_cos, level_boundary)."""
+    pos = np.ascontiguousarray(pos, np.float32); normal = np.ascontiguousarray(normal, np.float32)
+    mn = np.ascontiguousarray(min_dist, np.float32); mx = np.ascontiguousarray(max_dist, np.float32)
+    n = len(pos)
+    o = dict(in_view=np.zeros(n, np.uint8), proj=np.zeros((n, 2), np.float32), proj_xr=np.zeros(n, np.float32),
+             level=np.zeros(n, np.int32), view_cos=np.zeros(n, np.float32), level_boundary=np.zeros(n, np.uint8))
+    lib().orc_is_in_frustum(C.byref(view), _p(pos), _p(normal), _p(mn), _p(mx), n, _fp(cos_limit), _p(o["in_view"]), _p(o["proj"]),
+                            _p(o["proj_xr"]), _p(o["level"]), _p(o["view_cos"]), _p(o["level_boundary"]))
+    return o
+
+
 def bruteforce_top2(q, t):
     q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
     bi, bd, sd = (np.zeros(max(len(q), 1), np.int32) for _ in range(3))
