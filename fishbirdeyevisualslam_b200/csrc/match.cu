@@ -598,4 +598,45 @@ int launch_bruteforce(const uint8_t* q, int nq, const uint8_t* t, int nt, unsign
     return FBE_OK;
 }
 
+// ---- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307) -------------------------------------------------
+// One warp per map point, one lane per row of its N x N distance matrix.  The row median sorted_row[(N-1)/2] is found
+// without storing the row: bisection on the value v in [0, 256] with count(dist <= v) recomputed per step (9 passes of
+// N Hamming distances; N is the number of observations of a map point, tens at most, and the descriptors of one point are
+// 32 x N contiguous bytes that stay in L1).  The first row with the least median wins (`median < BestMedian`, :293).
+__global__ void __launch_bounds__(128) k_distinctive(const uint8_t* __restrict__ desc, const int* __restrict__ start, int npts,
+                                                     int* __restrict__ best, int* __restrict__ best_median) {
+    const int p = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (p >= npts) return;
+    const int s = start[p], N = start[p + 1] - s;
+    if (N <= 0) {
+        if (lane == 0) { best[p] = -1; if (best_median) best_median[p] = 0; }
+        return;
+    }
+    const int need = (N - 1) / 2 + 1;                              // rank (int)(0.5*(N-1)) -> that many values <= median
+    const uint8_t* d0 = desc + (size_t)s * 32;
+    unsigned key = 0xFFFFFFFFu;
+    for (int i = lane; i < N; i += 32) {
+        uint32_t a[8];
+        load_desc(a, d0 + (size_t)i * 32);
+        int lo = 0, hi = 256;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            int cnt = 0;
+            for (int j = 0; j < N; ++j) cnt += hamming256(a, d0 + (size_t)j * 32) <= mid;
+            if (cnt >= need) hi = mid; else lo = mid + 1;
+        }
+        key = min(key, ((unsigned)lo << 20) | (unsigned)i);
+    }
+    key = __reduce_min_sync(0xffffffffu, key);
+    if (lane == 0) { best[p] = (int)(key & 0xFFFFFu); if (best_median) best_median[p] = (int)(key >> 20); }
+}
+
+int launch_distinctive(const uint8_t* desc, const int* start, int npts, int* best, int* best_median, cudaStream_t st) {
+    if (npts <= 0) return FBE_OK;
+    k_distinctive<<<(npts + 3) / 4, 128, 0, st>>>(desc, start, npts, best, best_median);
+    count_launch();
+    FBE_CUDA(cudaGetLastError());
+    return FBE_OK;
+}
+
 }  // namespace fbe

@@ -456,6 +456,27 @@ int fbe_search_by_bow_kf(fbe_matcher* m, const fbe_keypoint* kf1_kps, const uint
     return FBE_OK;
 }
 
+int fbe_distinctive_descriptors(fbe_matcher* m, const uint8_t* desc, const int32_t* start, int32_t npts, int32_t* best,
+                                int32_t* best_median) {
+    if (!m || npts < 0 || (npts > 0 && (!start || !best))) return FBE_E_INVALID;
+    if (npts == 0) return FBE_OK;
+    const int total = start[npts];
+    if (start[0] != 0 || total < 0 || (total > 0 && !desc)) return FBE_E_INVALID;
+    for (int p = 0; p < npts; ++p) {
+        if (start[p + 1] < start[p]) return FBE_E_INVALID;
+        if (start[p + 1] - start[p] >= (1 << 20)) { set_error("more than 2^20 observations of one map point"); return FBE_E_UNSUPPORTED; }
+    }
+    FBE_CUDA(cudaSetDevice(m->device));
+    FBE_TRY(upload(m->fa.desc, desc, (size_t)total * 32, m->stream));
+    FBE_TRY(upload(m->i1, start, (size_t)(npts + 1) * 4, m->stream));
+    FBE_TRY(m->i2.ensure((size_t)npts * 4)); FBE_TRY(m->i3.ensure((size_t)npts * 4));
+    FBE_TRY(launch_distinctive(m->fa.desc.as<uint8_t>(), m->i1.as<int>(), npts, m->i2.as<int>(), m->i3.as<int>(), m->stream));
+    FBE_CUDA(cudaMemcpyAsync(best, m->i2.p, (size_t)npts * 4, cudaMemcpyDeviceToHost, m->stream));
+    if (best_median) FBE_CUDA(cudaMemcpyAsync(best_median, m->i3.p, (size_t)npts * 4, cudaMemcpyDeviceToHost, m->stream));
+    FBE_CUDA(cudaStreamSynchronize(m->stream));
+    return FBE_OK;
+}
+
 int fbe_bruteforce_top2(fbe_matcher* m, const uint8_t* q_desc, int32_t nq, const uint8_t* t_desc, int32_t nt, int32_t* best_idx,
                         int32_t* best_dist, int32_t* second_dist) {
     if (!m || nq < 0 || nt < 0 || (nq > 0 && (!q_desc || !best_idx || !best_dist || !second_dist)) || (nt > 0 && !t_desc)) return FBE_E_INVALID;

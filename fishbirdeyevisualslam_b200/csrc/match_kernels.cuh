@@ -83,6 +83,7 @@ int launch_map_finish(const int* best_idx, const int* best_dist, const int* seco
                       int* matches12, int* nmatches, cudaStream_t st);
 int launch_bow_rows(const uint8_t* kf_desc, const uint8_t* f_desc, const int* q_src, const int* q_beg, const int* q_end,
                     const int* f_items, int nq, int C, unsigned* rows, int* cnt, cudaStream_t st);
+int launch_distinctive(const uint8_t* desc, const int* start, int npts, int* best, int* best_median, cudaStream_t st);
 int launch_bruteforce(const uint8_t* q, int nq, const uint8_t* t, int nt, unsigned* partial, int nchunks, int* best_idx,
                       int* best_dist, int* second_dist, cudaStream_t st);
 

@@ -276,6 +276,15 @@ class ORBmatcher:
                                            ptr(k2), ptr(d2), len(k2), ptr(h2), ptr(a2), ptr(b2), ptr(c2), len(a2), ptr(m12), C.byref(n)))
         return n.value, m12[:len(k1)]
 
+    def ComputeDistinctiveDescriptors(self, desc, start):
+        """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:242-307) for many map points: `desc` rows start[p]..start[p+1]-1
+        are the descriptors observed for point p.  -> (best index inside each list or -1, that row's median distance)."""
+        desc = np.ascontiguousarray(desc, np.uint8); start = np.ascontiguousarray(start, np.int32)
+        npts = len(start) - 1
+        best = np.full(max(npts, 1), -1, np.int32); med = np.zeros(max(npts, 1), np.int32)
+        check(self._L.fbe_distinctive_descriptors(self._h, ptr(desc), ptr(start), npts, ptr(best), ptr(med)))
+        return best[:npts], med[:npts]
+
     def BruteForceTop2(self, q_desc, t_desc):
         q_desc = np.ascontiguousarray(q_desc, np.uint8)
         t_desc = np.ascontiguousarray(t_desc, np.uint8)

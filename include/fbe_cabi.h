@@ -260,6 +260,16 @@ FBE_API int fbe_search_by_bow_kf(fbe_matcher* m, const fbe_keypoint* kf1_kps, co
                                  int32_t n2, const uint8_t* kf2_has_mp, const int32_t* kf2_node_ids, const int32_t* kf2_start,
                                  const int32_t* kf2_items, int32_t kf2_nn, int32_t* matches12, int32_t* nmatches);
 
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307; MapPointBird.cc:90-155 is the same computation) for
+ * npts map points at once (next row f-4).  The descriptors observed for point p are rows start[p] .. start[p+1]-1 of
+ * `desc` (x 32 bytes), in the order the reference walks them (std::map<KeyFrame*, size_t> iteration order; the bird
+ * variant may put its current mDescriptor first).  For each point: all pairwise Hamming distances, per row the median
+ * `sorted_row[(int)(0.5*(N-1))]` (the row contains its own 0), and the FIRST row with the least median.
+ * Output: best[p] = index inside the point's own list (the reference then clones that descriptor), -1 for an empty list;
+ * best_median[p] (may be NULL) = that row's median. */
+FBE_API int fbe_distinctive_descriptors(fbe_matcher* m, const uint8_t* desc, const int32_t* start, int32_t npts, int32_t* best,
+                                        int32_t* best_median);
+
 /* Brute-force Hamming top-2 (stress config C5): for each of nq queries best / second-best over nt targets,
  * ties -> lowest target index (traversal order). */
 FBE_API int fbe_bruteforce_top2(fbe_matcher* m, const uint8_t* q_desc, int32_t nq, const uint8_t* t_desc, int32_t nt,

@@ -559,6 +559,34 @@ void orc_is_in_frustum(const FrustumView* v, const float* pos, const float* norm
     }
 }
 
+// MapPoint::ComputeDistinctiveDescriptors  src/MapPoint.cc:242-307 (MapPointBird.cc:90-155 repeats it): for each map point
+// the observed descriptors start[p] .. start[p+1]-1 in the reference's walking order -> index of the chosen one (-1: none).
+void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* start, int npts, int32_t* best, int32_t* best_median) {
+    for (int p = 0; p < npts; ++p) {
+        const size_t N = (size_t)(start[p + 1] - start[p]);
+        best[p] = -1; best_median[p] = 0;
+        if (N == 0) continue;
+        const uint8_t* d0 = desc + (size_t)start[p] * 32;
+        std::vector<float> Distances(N * N);
+        for (size_t i = 0; i < N; i++) {
+            Distances[i * N + i] = 0;
+            for (size_t j = i + 1; j < N; j++) {
+                const int distij = hamming(d0 + i * 32, d0 + j * 32);
+                Distances[i * N + j] = distij;
+                Distances[j * N + i] = distij;
+            }
+        }
+        int BestMedian = INT_MAX, BestIdx = 0;
+        for (size_t i = 0; i < N; i++) {
+            std::vector<int> vDists(Distances.begin() + i * N, Distances.begin() + (i + 1) * N);
+            std::sort(vDists.begin(), vDists.end());
+            const int median = vDists[0.5 * (N - 1)];
+            if (median < BestMedian) { BestMedian = median; BestIdx = (int)i; }
+        }
+        best[p] = BestIdx; best_median[p] = BestMedian;
+    }
+}
+
 void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* best_idx, int32_t* best_dist,
                          int32_t* second_dist) {
     for (int i = 0; i < nq; ++i) {

@@ -312,6 +312,18 @@ def is_in_frustum(view, pos, normal, min_dist, max_dist, cos_limit):
     return o
 
 
+def distinctive_descriptors(desc, start, _L=None):
+    """MapPoint::ComputeDistinctiveDescriptors for CSR lists of observed descriptors -> (best index per point, its median)."""
+    desc = np.ascontiguousarray(desc, np.uint8); start = np.ascontiguousarray(start, np.int32)
+    npts = len(start) - 1
+    best = np.full(max(npts, 1), -1, np.int32); med = np.zeros(max(npts, 1), np.int32)
+    if _L is None:
+        lib().orc_distinctive_descriptors(_p(desc), _p(start), npts, _p(best), _p(med))
+        return best[:npts], med[:npts]
+    _L.refm_distinctive_descriptors(_p(desc), _p(start), npts, _p(best))
+    return best[:npts], None
+
+
 def bruteforce_top2(q, t):
     q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
     bi, bd, sd = (np.zeros(max(len(q), 1), np.int32) for _ in range(3))
@@ -448,6 +460,9 @@ class RefMatch:
 
     def search_by_bow_kf(self, k1, d1, has1, fv1, k2, d2, has2, fv2, nn_ratio, check_ori):
         return search_by_bow_kf(k1, d1, has1, fv1, k2, d2, has2, fv2, nn_ratio, check_ori, _L=self.L, _fn="refm_search_by_bow_kf")
+
+    def distinctive_descriptors(self, desc, start):
+        return distinctive_descriptors(desc, start, _L=self.L)
 
     def hamming256(self, a, b):
         return self.L.refm_hamming256(_p(np.ascontiguousarray(a, np.uint8)), _p(np.ascontiguousarray(b, np.uint8)))

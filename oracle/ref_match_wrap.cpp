@@ -71,6 +71,7 @@ std::map<KeyFrame*, size_t> MapPointBird::GetObservations() { return mObservatio
 void MapPointBird::ComputeDistinctiveDescriptors() {}
 void Map::AddMapPointBird(MapPointBird*) {}
 
+bool KeyFrame::isBad() { return mbBad; }
 void KeyFrame::SetPose(const cv::Mat& Tcw_) { Tcw_.copyTo(Tcw); }
 cv::Mat KeyFrame::GetRotation() { return Tcw.rowRange(0, 3).colRange(0, 3).clone(); }
 cv::Mat KeyFrame::GetTranslation() { return Tcw.rowRange(0, 3).col(3).clone(); }
@@ -442,6 +443,39 @@ int refm_search_by_bow_kf(const Kp* k1, const uint8_t* d1, int n1, const uint8_t
     const int n = m.SearchByBoW(kf1, kf2, out);
     for (int i = 0; i < n1; ++i) matches12[i] = out[i] ? index2[out[i]] : -1;
     return n;
+}
+
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307).  Each observed descriptor sits in a key frame of
+// its own; the key frames are constructed in one array so that std::map<KeyFrame*, size_t> walks them in input order.
+void refm_distinctive_descriptors(const uint8_t* desc, const int32_t* start, int npts, int32_t* best) {
+    Kp kp = {10.f, 10.f, 31.f, 0.f, 1.f, 0, -1};
+    for (int p = 0; p < npts; ++p) {
+        const int N = start[p + 1] - start[p];
+        best[p] = -1;
+        if (N == 0) continue;
+        const uint8_t* d0 = desc + (size_t)start[p] * 32;
+        KeyFrame* kfs = static_cast<KeyFrame*>(::operator new(sizeof(KeyFrame) * (size_t)N));
+        std::vector<uint8_t> two(64);
+        MapPoint* mp = make_mp(0, 0, d0, 0, 0);
+        for (int i = 0; i < N; ++i) {
+            // two features per key frame: a decoy in row 0 and the observation in row 1 (exercises `mDescriptors.row(idx)`)
+            for (int b = 0; b < 32; ++b) { two[b] = (uint8_t)(~d0[(size_t)i * 32 + b]); two[32 + b] = d0[(size_t)i * 32 + b]; }
+            Kp k2[2] = {kp, kp};
+            FrameView v{k2, two.data(), 2, 0.f, 0.f, 64.f / 1280.f, 48.f / 720.f, FRAME_GRID_COLS, FRAME_GRID_ROWS};
+            set_front_statics(v);
+            Frame F;
+            fill_front(F, v);
+            new (&kfs[i]) KeyFrame(F, NULL, NULL);
+            kfs[i].mbBad = false;
+            mp->mObservations[&kfs[i]] = 1;
+        }
+        mp->ComputeDistinctiveDescriptors();
+        for (int i = 0; i < N && best[p] < 0; ++i)      // first input row equal to the chosen descriptor
+            if (std::memcmp(mp->mDescriptor.ptr(0), d0 + (size_t)i * 32, 32) == 0) best[p] = i;
+        for (int i = 0; i < N; ++i) kfs[i].~KeyFrame();
+        ::operator delete(kfs);
+        delete mp;
+    }
 }
 
 int refm_hamming256(const uint8_t* a, const uint8_t* b) { return ORBmatcher::DescriptorDistance(desc_row(a), desc_row(b)); }

@@ -202,6 +202,19 @@ def test_search_by_bow(oracle, front_pair):
             assert n_g == n_o and np.array_equal(m_g, m_o) and n_g > 50
 
 
+def test_distinctive_descriptors(oracle):
+    from fishbirdeyevisualslam_b200.matcher import ORBmatcher
+    from test_oracle_vs_refmatch import distinct_lists
+    rng = np.random.default_rng(21)
+    sizes = tuple(int(x) for x in rng.integers(0, 45, 400)) + (0, 1, 2, 300, 129, 64, 33, 32, 31)
+    dd, st = distinct_lists(rng, sizes)
+    b_g, m_g = ORBmatcher(0.9, True).ComputeDistinctiveDescriptors(dd, st)
+    b_o, m_o = oracle.distinctive_descriptors(dd, st)
+    assert np.array_equal(b_g, b_o) and np.array_equal(m_g, m_o)
+    e_b, e_m = ORBmatcher(0.9, True).ComputeDistinctiveDescriptors(np.zeros((0, 32), np.uint8), np.zeros(3, np.int32))
+    assert e_b.tolist() == [-1, -1] and e_m.tolist() == [0, 0]
+
+
 @pytest.mark.parametrize("seed", range(3))
 def test_random_scenes_all_matchers(oracle, seed):
     """Synthetic scenes with quantised coordinates (exact cell-boundary and window-boundary hits) and duplicates (ties)."""

@@ -104,6 +104,22 @@ def test_search_by_bow(oracle, seed):
             assert len(np.unique(hit)) == len(hit) and has_mp2[hit].all() and has_mp[m_o >= 0].all()
 
 
+def test_distinctive_descriptors_against_numpy(oracle):
+    """Row medians by numpy sort (MapPoint.cc:283-299): sorted_row[int(0.5*(N-1))], first least median wins."""
+    from test_oracle_vs_refmatch import distinct_lists
+    rng = np.random.default_rng(77)
+    dd, st = distinct_lists(rng, sizes=(0, 1, 2, 3, 6, 6, 9, 30, 64, 101))
+    best, med = oracle.distinctive_descriptors(dd, st)
+    for p in range(len(st) - 1):
+        d = dd[st[p]:st[p + 1]]
+        if len(d) == 0:
+            assert best[p] == -1
+            continue
+        D = np.unpackbits(d[:, None, :] ^ d[None, :, :], axis=2).sum(2)
+        m = np.sort(D, axis=1)[:, int(0.5 * (len(d) - 1))]
+        assert best[p] == int(np.argmin(m)) and med[p] == int(m.min())
+
+
 # ---- hand-built quirk cases (SURVEY Appendix B) ------------------------------------------------------------------
 def test_q1_grid_uses_round_and_drops_last_half_cell(oracle):
     # 640x480 front grid: cell width 10 px.  x = 14.9 -> round(1.49) = 1; x = 15.0 -> round(1.5) = 2 (half away from zero);

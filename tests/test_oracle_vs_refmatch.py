@@ -98,7 +98,28 @@ def scene_outputs(impl, seed, is_ref):
     for j, (ratio, ori) in enumerate([(0.75, True), (0.9, False)]):            # key frame vs key frame (loop closing)
         n, c = impl.search_by_bow_kf(F1.kps, F1.desc, has_mp, featvec(node1), F2.kps, F2.desc, has_mp2, featvec(node2), ratio, ori)
         out[f"bowkf{j}"] = np.concatenate([[n], c]).astype(np.int32)
+    # MapPoint::ComputeDistinctiveDescriptors on clusters of observed descriptors (sizes 0 .. 40, duplicates = median ties)
+    dd, st = distinct_lists(rng)
+    best, _ = impl.distinctive_descriptors(dd, st)
+    chosen = np.zeros((len(best), 32), np.uint8)                 # compare the chosen DESCRIPTOR (what the reference stores)
+    for p, b in enumerate(best):
+        if b >= 0:
+            chosen[p] = dd[st[p] + b]
+    out["distinct"] = chosen
+    out["distinct_none"] = (best < 0).astype(np.int32)
     return out
+
+
+def distinct_lists(rng, sizes=(0, 1, 2, 3, 4, 5, 8, 13, 21, 40, 7, 7, 2, 1, 0, 33)):
+    lists = []
+    for n in sizes:
+        base = rng.integers(0, 256, (1, 32), dtype=np.uint8)
+        d = flip_bits(rng, np.repeat(base, n, 0), 60) if n else np.zeros((0, 32), np.uint8)
+        if n >= 4:
+            d[n - 1] = d[0]                                      # an exact duplicate
+        lists.append(d)
+    start = np.concatenate([[0], np.cumsum([len(l) for l in lists])]).astype(np.int32)
+    return np.concatenate(lists), start
 
 
 _REF_PIX = {}
