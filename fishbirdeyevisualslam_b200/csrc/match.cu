@@ -639,4 +639,86 @@ int launch_distinctive(const uint8_t* desc, const int* start, int npts, int* bes
     return FBE_OK;
 }
 
+// ---- ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:658-824) -------------------------------------------------
+// The reference never sets vbMatched2, so queries do not interact: each key-frame-1 feature takes, among the key-frame-2
+// features of its vocabulary node that clear the filters (no map point, dist <= TH_LOW, not within 100*scale of the
+// epipole for monocular pairs, CheckDistEpipolarLine :141-158), the one with the smallest distance, the LAST one on ties
+// (`dist>bestDist` skips, equality replaces).  One warp per query, lanes over the node list, one packed-key warp minimum.
+__global__ void __launch_bounds__(256) k_tri_rows(const TriArgs a) {
+    const int q = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (q >= a.nq) return;
+    const int i1 = a.q_src[q], beg = a.q_beg[q], end = a.q_end[q];
+    const fbe_keypoint kp1 = a.kps1[i1];
+    const bool st1 = a.stereo1[i1] != 0;
+    uint32_t d1[8];
+    load_desc(d1, a.desc1 + (size_t)i1 * 32);
+    // epipolar line in the second image l = x1' F12 (:144-146)
+    const float la = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, a.F[0]), __fmul_rn(kp1.y, a.F[3])), a.F[6]);
+    const float lb = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, a.F[1]), __fmul_rn(kp1.y, a.F[4])), a.F[7]);
+    const float lc = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, a.F[2]), __fmul_rn(kp1.y, a.F[5])), a.F[8]);
+    const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+    unsigned key = 0xFFFFFFFFu;
+    for (int p = beg + lane; p < end; p += 32) {
+        const int i2 = a.items2[p];
+        if (a.skip2[i2]) continue;
+        const int dist = hamming256(d1, a.desc2 + (size_t)i2 * 32);
+        if (dist > FBE_TH_LOW) continue;
+        const fbe_keypoint kp2 = a.kps2[i2];
+        if (!st1 && !a.stereo2[i2]) {
+            const float dx = __fsub_rn(a.ex, kp2.x), dy = __fsub_rn(a.ey, kp2.y);
+            if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.0f, a.scale[kp2.octave])) continue;
+        }
+        const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, kp2.x), __fmul_rn(lb, kp2.y)), lc);
+        if (den == 0.0f) continue;
+        const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+        if (!((double)dsqr < 3.84 * (double)a.sigma2[kp2.octave])) continue;
+        key = min(key, ((unsigned)dist << 20) | (0xFFFFFu - (unsigned)(p - beg)));
+    }
+    key = __reduce_min_sync(0xffffffffu, key);
+    if (lane == 0) {
+        int best = -1, bin = -1;
+        if (key != 0xFFFFFFFFu) {
+            best = a.items2[beg + (int)(0xFFFFFu - (key & 0xFFFFFu))];
+            if (a.check_ori) bin = rot_bin(kp1.angle, a.kps2[best].angle);
+        }
+        a.q_best[q] = best; a.q_bin[q] = bin;
+    }
+}
+
+// rotation-consistency prune (:779-797) and the scatter into vMatches12
+__global__ void __launch_bounds__(256) k_tri_finish(const TriArgs a) {
+    __shared__ int s_hist[FBE_HISTO_LENGTH], s_ind[3], s_nm;
+    const int tid = threadIdx.x;
+    if (tid < FBE_HISTO_LENGTH) s_hist[tid] = 0;
+    if (tid == 0) { s_nm = 0; s_ind[0] = s_ind[1] = s_ind[2] = -1; }
+    __syncthreads();
+    if (a.check_ori)
+        for (int q = tid; q < a.nq; q += 256)
+            if (a.q_best[q] >= 0) atomicAdd(&s_hist[a.q_bin[q]], 1);
+    __syncthreads();
+    if (a.check_ori && tid == 0) { int i1, i2, i3; three_maxima(s_hist, i1, i2, i3); s_ind[0] = i1; s_ind[1] = i2; s_ind[2] = i3; }
+    __syncthreads();
+    int nm = 0;
+    for (int q = tid; q < a.nq; q += 256) {
+        const int best = a.q_best[q];
+        if (best < 0) continue;
+        const int bin = a.q_bin[q];
+        if (a.check_ori && bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) continue;
+        a.matches12[a.q_src[q]] = best;
+        ++nm;
+    }
+    if (nm) atomicAdd(&s_nm, nm);
+    __syncthreads();
+    if (tid == 0) *a.nmatches = s_nm;
+}
+
+int launch_triangulation(const TriArgs& a, cudaStream_t st) {
+    if (a.nq <= 0) return FBE_OK;
+    k_tri_rows<<<(a.nq + 7) / 8, 256, 0, st>>>(a);
+    k_tri_finish<<<1, 256, 0, st>>>(a);
+    count_launch(2);
+    FBE_CUDA(cudaGetLastError());
+    return FBE_OK;
+}
+
 }  // namespace fbe

@@ -456,6 +456,80 @@ int fbe_search_by_bow_kf(fbe_matcher* m, const fbe_keypoint* kf1_kps, const uint
     return FBE_OK;
 }
 
+int fbe_search_for_triangulation(fbe_matcher* m, const fbe_keypoint* kf1_kps, const uint8_t* kf1_desc, int32_t n1,
+                                 const uint8_t* kf1_skip, const uint8_t* kf1_stereo, const int32_t* kf1_node_ids,
+                                 const int32_t* kf1_start, const int32_t* kf1_items, int32_t kf1_nn, const fbe_keypoint* kf2_kps,
+                                 const uint8_t* kf2_desc, int32_t n2, const uint8_t* kf2_skip, const uint8_t* kf2_stereo,
+                                 const int32_t* kf2_node_ids, const int32_t* kf2_start, const int32_t* kf2_items, int32_t kf2_nn,
+                                 const float F12[9], float ex, float ey, const float* kf2_scale_factors,
+                                 const float* kf2_level_sigma2, int32_t nlevels, int32_t* matches12, int32_t* nmatches) {
+    if (!m || !nmatches || n1 < 0 || n2 < 0 || kf1_nn < 0 || kf2_nn < 0 || (n1 > 0 && !matches12) || !F12 || !kf2_scale_factors ||
+        !kf2_level_sigma2 || nlevels < 1 || nlevels > FBE_MAX_LEVELS)
+        return FBE_E_INVALID;
+    *nmatches = 0;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    if (n1 == 0 || n2 == 0 || kf1_nn == 0 || kf2_nn == 0) return FBE_OK;
+    if (!kf1_kps || !kf1_desc || !kf1_skip || !kf1_stereo || !kf1_node_ids || !kf1_start || !kf1_items || !kf2_kps || !kf2_desc ||
+        !kf2_skip || !kf2_stereo || !kf2_node_ids || !kf2_start || !kf2_items)
+        return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(m->device));
+    for (int k = 0; k < n2; ++k)
+        if (kf2_kps[k].octave < 0 || kf2_kps[k].octave >= nlevels) { set_error("key frame 2 keypoint octave outside the scale tables"); return FBE_E_INVALID; }
+    // merge-walk of the two feature vectors (:694-776; lower_bound jumps land where ++ would): the query list
+    std::vector<int> q_src, q_beg, q_end;
+    int a = 0, b = 0;
+    while (a < kf1_nn && b < kf2_nn) {
+        if (kf1_node_ids[a] == kf2_node_ids[b]) {
+            if (kf2_start[b + 1] - kf2_start[b] >= (1 << 20)) { set_error("more than 2^20 features under one vocabulary node"); return FBE_E_UNSUPPORTED; }
+            for (int p = kf1_start[a]; p < kf1_start[a + 1]; ++p) {
+                const int i = kf1_items[p];
+                if (i < 0 || i >= n1) return FBE_E_INVALID;
+                if (kf1_skip[i]) continue;
+                q_src.push_back(i); q_beg.push_back(kf2_start[b]); q_end.push_back(kf2_start[b + 1]);
+            }
+            ++a; ++b;
+        } else if (kf1_node_ids[a] < kf2_node_ids[b]) ++a;
+        else ++b;
+    }
+    const int nq = (int)q_src.size();
+    if (nq == 0) return FBE_OK;
+    const int n_items = kf2_start[kf2_nn];
+    for (int p = 0; p < n_items; ++p)
+        if (kf2_items[p] < 0 || kf2_items[p] >= n2) return FBE_E_INVALID;
+    FBE_TRY(upload(m->fb.kps, kf1_kps, (size_t)n1 * sizeof(fbe_keypoint), m->stream));
+    FBE_TRY(upload(m->fb.desc, kf1_desc, (size_t)n1 * 32, m->stream));
+    FBE_TRY(upload(m->fa.kps, kf2_kps, (size_t)n2 * sizeof(fbe_keypoint), m->stream));
+    FBE_TRY(upload(m->fa.desc, kf2_desc, (size_t)n2 * 32, m->stream));
+    FBE_TRY(upload(m->fa.items, kf2_items, (size_t)n_items * 4, m->stream));
+    FBE_TRY(upload(m->i1, q_src.data(), (size_t)nq * 4, m->stream));
+    FBE_TRY(upload(m->i2, q_beg.data(), (size_t)nq * 4, m->stream));
+    FBE_TRY(upload(m->partial, q_end.data(), (size_t)nq * 4, m->stream));
+    FBE_TRY(upload(m->u0, kf2_skip, (size_t)n2, m->stream));
+    // the two stereo flag arrays share one buffer: [kf1 | kf2]
+    FBE_TRY(m->u1.ensure((size_t)n1 + (size_t)n2 + 16));
+    FBE_CUDA(cudaMemcpyAsync(m->u1.p, kf1_stereo, (size_t)n1, cudaMemcpyHostToDevice, m->stream));
+    FBE_CUDA(cudaMemcpyAsync(m->u1.as<uint8_t>() + n1, kf2_stereo, (size_t)n2, cudaMemcpyHostToDevice, m->stream));
+    FBE_TRY(m->i0.ensure((size_t)n1 * 4)); FBE_TRY(m->i3.ensure((size_t)nq * 4)); FBE_TRY(m->i4.ensure((size_t)nq * 4));
+    FBE_TRY(m->misc.ensure(64));
+    FBE_CUDA(cudaMemsetAsync(m->i0.p, 0xFF, (size_t)n1 * 4, m->stream));
+    FBE_CUDA(cudaMemsetAsync(m->misc.p, 0, 4, m->stream));
+    TriArgs t{};
+    t.kps1 = m->fb.kps.as<fbe_keypoint>(); t.desc1 = m->fb.desc.as<uint8_t>(); t.stereo1 = m->u1.as<uint8_t>();
+    t.kps2 = m->fa.kps.as<fbe_keypoint>(); t.desc2 = m->fa.desc.as<uint8_t>(); t.stereo2 = m->u1.as<uint8_t>() + n1;
+    t.skip2 = m->u0.as<uint8_t>(); t.items2 = m->fa.items.as<int>();
+    t.q_src = m->i1.as<int>(); t.q_beg = m->i2.as<int>(); t.q_end = m->partial.as<int>(); t.nq = nq;
+    for (int k = 0; k < 9; ++k) t.F[k] = F12[k];
+    t.ex = ex; t.ey = ey;
+    for (int k = 0; k < FBE_MAX_LEVELS; ++k) { t.scale[k] = k < nlevels ? kf2_scale_factors[k] : 0.f; t.sigma2[k] = k < nlevels ? kf2_level_sigma2[k] : 0.f; }
+    t.check_ori = m->check_ori;
+    t.q_best = m->i3.as<int>(); t.q_bin = m->i4.as<int>(); t.matches12 = m->i0.as<int>(); t.nmatches = m->misc.as<int>();
+    FBE_TRY(launch_triangulation(t, m->stream));
+    FBE_CUDA(cudaMemcpyAsync(matches12, m->i0.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, m->stream));
+    FBE_CUDA(cudaMemcpyAsync(nmatches, m->misc.p, 4, cudaMemcpyDeviceToHost, m->stream));
+    FBE_CUDA(cudaStreamSynchronize(m->stream));
+    return FBE_OK;
+}
+
 int fbe_distinctive_descriptors(fbe_matcher* m, const uint8_t* desc, const int32_t* start, int32_t npts, int32_t* best,
                                 int32_t* best_median) {
     if (!m || npts < 0 || (npts > 0 && (!start || !best))) return FBE_E_INVALID;

@@ -83,6 +83,17 @@ int launch_map_finish(const int* best_idx, const int* best_dist, const int* seco
                       int* matches12, int* nmatches, cudaStream_t st);
 int launch_bow_rows(const uint8_t* kf_desc, const uint8_t* f_desc, const int* q_src, const int* q_beg, const int* q_end,
                     const int* f_items, int nq, int C, unsigned* rows, int* cnt, cudaStream_t st);
+// SearchForTriangulation (src/ORBmatcher.cc:658-824): per-query arguments of the candidate kernel and its epilogue
+struct TriArgs {
+    const fbe_keypoint* kps1; const uint8_t* desc1; const uint8_t* stereo1;     // key frame 1
+    const fbe_keypoint* kps2; const uint8_t* desc2; const uint8_t* stereo2; const uint8_t* skip2; const int* items2;   // key frame 2
+    const int* q_src; const int* q_beg; const int* q_end; int nq;               // query = kf1 feature, candidates = items2[beg, end)
+    float F[9]; float ex, ey; float scale[FBE_MAX_LEVELS]; float sigma2[FBE_MAX_LEVELS];
+    int check_ori;
+    int* q_best; int* q_bin;                                                     // per query: chosen kf2 feature / rotation bin
+    int* matches12; int* nmatches;                                               // per kf1 feature (pre-set to -1) / total
+};
+int launch_triangulation(const TriArgs& a, cudaStream_t st);
 int launch_distinctive(const uint8_t* desc, const int* start, int npts, int* best, int* best_median, cudaStream_t st);
 int launch_bruteforce(const uint8_t* q, int nq, const uint8_t* t, int nt, unsigned* partial, int nchunks, int* best_idx,
                       int* best_dist, int* second_dist, cudaStream_t st);

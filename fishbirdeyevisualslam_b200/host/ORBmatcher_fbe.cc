@@ -1,7 +1,7 @@
 // Drop-in bodies for the ORBmatcher methods on the hot path.  This file is compiled INSIDE the reference tree in place
 // of the same-named method bodies of src/ORBmatcher.cc (see INTEGRATION.md for the exact patch); the class declaration
 // include/ORBmatcher.h is unchanged, so Tracking.cc / LocalMapping.cc / LoopClosing.cc call it as before.  Methods that
-// are not on the hot path (SearchForTriangulation, SearchBySim3, Fuse x2) keep the reference's own CPU code.
+// are not on the hot path (SearchBySim3, Fuse x2) keep the reference's own CPU code.
 //
 // In the build image of this repository it is compiled against the reference's own headers with OpenCV replaced by the
 // test shim oracle/cvshim_m (oracle/Makefile target `dropinmatch`) and checked on the GPU against the outputs of the
@@ -316,6 +316,47 @@ int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint
                          m12.data(), &nmatches);
     for (size_t i = 0; i < vpMapPoints1.size(); i++)
         if (m12[i] >= 0) vpMatches12[i] = vpMapPoints2[m12[i]];
+    return nmatches;
+}
+
+// src/ORBmatcher.cc:658-824 (LocalMapping::CreateNewMapPoints)
+int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12,
+                                       std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo) {
+    // epipole in the second image, exactly as :666-672
+    cv::Mat Cw = pKF1->GetCameraCenter();
+    cv::Mat R2w = pKF2->GetRotation();
+    cv::Mat t2w = pKF2->GetTranslation();
+    cv::Mat C2 = R2w * Cw + t2w;
+    const float invz = 1.0f / C2.at<float>(2);
+    const float ex = pKF2->fx * C2.at<float>(0) * invz + pKF2->cx;
+    const float ey = pKF2->fy * C2.at<float>(1) * invz + pKF2->cy;
+
+    const int n1 = pKF1->N, n2 = pKF2->N;
+    std::vector<unsigned char> skip1(std::max(n1, 1)), st1(std::max(n1, 1)), skip2(std::max(n2, 1)), st2(std::max(n2, 1));
+    for (int i = 0; i < n1; i++) {
+        st1[i] = pKF1->mvuRight[i] >= 0;
+        skip1[i] = pKF1->GetMapPoint(i) != NULL || (bOnlyStereo && !st1[i]);
+    }
+    for (int i = 0; i < n2; i++) {
+        st2[i] = pKF2->mvuRight[i] >= 0;
+        skip2[i] = pKF2->GetMapPoint(i) != NULL || (bOnlyStereo && !st2[i]);
+    }
+    Csr a = flatten(pKF1->mFeatVec), b = flatten(pKF2->mFeatVec);
+    float F[9];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) F[3 * r + c] = F12.at<float>(r, c);
+    std::vector<int> m12(std::max(n1, 1), -1);
+    int nmatches = 0;
+    fbe_search_for_triangulation(matcher_for(mfNNratio, mbCheckOrientation), reinterpret_cast<const fbe_keypoint*>(pKF1->mvKeysUn.data()),
+                                 desc_ptr(pKF1->mDescriptors), n1, skip1.data(), st1.data(), a.ids.data(), a.start.data(), a.items.data(),
+                                 (int)a.ids.size(), reinterpret_cast<const fbe_keypoint*>(pKF2->mvKeysUn.data()),
+                                 desc_ptr(pKF2->mDescriptors), n2, skip2.data(), st2.data(), b.ids.data(), b.start.data(), b.items.data(),
+                                 (int)b.ids.size(), F, ex, ey, pKF2->mvScaleFactors.data(), pKF2->mvLevelSigma2.data(),
+                                 (int)pKF2->mvScaleFactors.size(), m12.data(), &nmatches);
+    vMatchedPairs.clear();
+    vMatchedPairs.reserve(nmatches);
+    for (int i = 0; i < n1; i++)
+        if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)m12[i]));
     return nmatches;
 }
 

@@ -276,6 +276,27 @@ class ORBmatcher:
                                            ptr(k2), ptr(d2), len(k2), ptr(h2), ptr(a2), ptr(b2), ptr(c2), len(a2), ptr(m12), C.byref(n)))
         return n.value, m12[:len(k1)]
 
+    def SearchForTriangulation(self, kf1_kps, kf1_desc, kf1_has_mp, kf1_stereo, kf1_featvec, kf2_kps, kf2_desc, kf2_has_mp, kf2_stereo,
+                               kf2_featvec, F12, epipole, kf2_scale_factors, kf2_level_sigma2, bOnlyStereo=False):
+        """SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (ORBmatcher.cc:658-824).  kfN_stereo = mvuRight >= 0;
+        epipole = (ex, ey) of :666-672.  -> (nmatches, matches12[n1]); vMatchedPairs = [(i, m) for i, m in enumerate(matches12) if m >= 0]."""
+        k1 = np.ascontiguousarray(kf1_kps); d1 = np.ascontiguousarray(kf1_desc, np.uint8)
+        k2 = np.ascontiguousarray(kf2_kps); d2 = np.ascontiguousarray(kf2_desc, np.uint8)
+        s1 = np.ascontiguousarray(kf1_stereo, np.uint8); s2 = np.ascontiguousarray(kf2_stereo, np.uint8)
+        skip1 = np.ascontiguousarray((np.asarray(kf1_has_mp) != 0) | ((s1 == 0) if bOnlyStereo else False), np.uint8)
+        skip2 = np.ascontiguousarray((np.asarray(kf2_has_mp) != 0) | ((s2 == 0) if bOnlyStereo else False), np.uint8)
+        a1, b1, c1 = (np.ascontiguousarray(a, np.int32) for a in kf1_featvec)
+        a2, b2, c2 = (np.ascontiguousarray(a, np.int32) for a in kf2_featvec)
+        F = np.ascontiguousarray(F12, np.float32).ravel()
+        sc = np.ascontiguousarray(kf2_scale_factors, np.float32); sg = np.ascontiguousarray(kf2_level_sigma2, np.float32)
+        m12 = np.full(max(len(k1), 1), -1, np.int32)
+        n = C.c_int32()
+        check(self._L.fbe_search_for_triangulation(self._h, ptr(k1), ptr(d1), len(k1), ptr(skip1), ptr(s1), ptr(a1), ptr(b1), ptr(c1), len(a1),
+                                                   ptr(k2), ptr(d2), len(k2), ptr(skip2), ptr(s2), ptr(a2), ptr(b2), ptr(c2), len(a2), ptr(F),
+                                                   C.c_float(float(epipole[0])), C.c_float(float(epipole[1])), ptr(sc), ptr(sg), len(sc),
+                                                   ptr(m12), C.byref(n)))
+        return n.value, m12[:len(k1)]
+
     def ComputeDistinctiveDescriptors(self, desc, start):
         """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:242-307) for many map points: `desc` rows start[p]..start[p+1]-1
         are the descriptors observed for point p.  -> (best index inside each list or -1, that row's median distance)."""

@@ -260,6 +260,23 @@ FBE_API int fbe_search_by_bow_kf(fbe_matcher* m, const fbe_keypoint* kf1_kps, co
                                  int32_t n2, const uint8_t* kf2_has_mp, const int32_t* kf2_node_ids, const int32_t* kf2_start,
                                  const int32_t* kf2_items, int32_t kf2_nn, int32_t* matches12, int32_t* nmatches);
 
+/* ORBmatcher::SearchForTriangulation, src/ORBmatcher.cc:658-824 (LocalMapping::CreateNewMapPoints; next row f-4).
+ * kfN_skip[i] != 0 iff feature i cannot take part: it already has a map point (GetMapPoint(i) != NULL), or bOnlyStereo is
+ * set and mvuRight[i] < 0.  kfN_stereo[i] != 0 iff mvuRight[i] >= 0.  F12: row-major 3x3 fundamental matrix;
+ * (ex, ey): the epipole in key frame 2, computed by the host shim exactly as :666-672 do (cv::Mat arithmetic);
+ * kf2_scale_factors / kf2_level_sigma2: mvScaleFactors / mvLevelSigma2 of key frame 2.
+ * Output: matches12[n1] = key-frame-2 feature or -1 (vMatchedPairs is the list of (i, matches12[i]) with matches12[i] >= 0
+ * in index order); nmatches as returned by the reference.  Note that the reference never sets vbMatched2 in this method:
+ * a key-frame-2 feature may be matched by several key-frame-1 features, and so it is here. */
+FBE_API int fbe_search_for_triangulation(fbe_matcher* m, const fbe_keypoint* kf1_kps, const uint8_t* kf1_desc, int32_t n1,
+                                         const uint8_t* kf1_skip, const uint8_t* kf1_stereo, const int32_t* kf1_node_ids,
+                                         const int32_t* kf1_start, const int32_t* kf1_items, int32_t kf1_nn,
+                                         const fbe_keypoint* kf2_kps, const uint8_t* kf2_desc, int32_t n2,
+                                         const uint8_t* kf2_skip, const uint8_t* kf2_stereo, const int32_t* kf2_node_ids,
+                                         const int32_t* kf2_start, const int32_t* kf2_items, int32_t kf2_nn, const float F12[9],
+                                         float ex, float ey, const float* kf2_scale_factors, const float* kf2_level_sigma2,
+                                         int32_t nlevels, int32_t* matches12, int32_t* nmatches);
+
 /* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307; MapPointBird.cc:90-155 is the same computation) for
  * npts map points at once (next row f-4).  The descriptors observed for point p are rows start[p] .. start[p+1]-1 of
  * `desc` (x 32 bytes), in the order the reference walks them (std::map<KeyFrame*, size_t> iteration order; the bird

@@ -559,6 +559,66 @@ void orc_is_in_frustum(const FrustumView* v, const float* pos, const float* norm
     }
 }
 
+// ORBmatcher::SearchForTriangulation  src/ORBmatcher.cc:658-824 with CheckDistEpipolarLine :141-158.  skipN = feature has a
+// map point or fails the bOnlyStereo filter; stereoN = mvuRight >= 0; (ex, ey) = epipole in key frame 2 (:666-672, computed
+// by the caller).  vbMatched2 exists in the reference but is never set, which is reproduced by not having it.
+int orc_search_for_triangulation(const Kp* k1, const uint8_t* d1, int n1, const uint8_t* skip1, const uint8_t* stereo1,
+                                 const int32_t* ids1, const int32_t* st1, const int32_t* it1, int nn1, const Kp* k2, const uint8_t* d2,
+                                 int n2, const uint8_t* skip2, const uint8_t* stereo2, const int32_t* ids2, const int32_t* st2,
+                                 const int32_t* it2, int nn2, const float* F12, float ex, float ey, const float* scale2,
+                                 const float* sigma2, int check_ori, int32_t* matches12) {
+    (void)n2;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int nmatches = 0, a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (ids1[a] < ids2[b]) { ++a; continue; }
+        if (ids1[a] > ids2[b]) { ++b; continue; }
+        for (int p1 = st1[a]; p1 < st1[a + 1]; ++p1) {
+            const int idx1 = it1[p1];
+            if (skip1[idx1]) continue;
+            const bool bStereo1 = stereo1[idx1] != 0;
+            const Kp& kp1 = k1[idx1];
+            int bestDist = TH_LOW, bestIdx2 = -1;
+            for (int p2 = st2[b]; p2 < st2[b + 1]; ++p2) {
+                const int idx2 = it2[p2];
+                if (skip2[idx2]) continue;
+                const int dist = hamming(d1 + (size_t)idx1 * 32, d2 + (size_t)idx2 * 32);
+                if (dist > TH_LOW || dist > bestDist) continue;
+                const Kp& kp2 = k2[idx2];
+                if (!bStereo1 && !stereo2[idx2]) {
+                    const float distex = ex - kp2.x, distey = ey - kp2.y;
+                    if (distex * distex + distey * distey < 100 * scale2[kp2.octave]) continue;
+                }
+                // CheckDistEpipolarLine
+                const float la = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+                const float lb = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+                const float lc = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+                const float num = la * kp2.x + lb * kp2.y + lc;
+                const float den = la * la + lb * lb;
+                if (den == 0) continue;
+                const float dsqr = num * num / den;
+                if (dsqr < 3.84 * sigma2[kp2.octave]) { bestIdx2 = idx2; bestDist = dist; }
+            }
+            if (bestIdx2 >= 0) {
+                matches12[idx1] = bestIdx2;
+                nmatches++;
+                if (check_ori) rotHist[rot_bin(kp1.angle, k2[bestIdx2].angle)].push_back(idx1);
+            }
+        }
+        ++a; ++b;
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); ++j) { matches12[rotHist[i][j]] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
 // MapPoint::ComputeDistinctiveDescriptors  src/MapPoint.cc:242-307 (MapPointBird.cc:90-155 repeats it): for each map point
 // the observed descriptors start[p] .. start[p+1]-1 in the reference's walking order -> index of the chosen one (-1: none).
 void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* start, int npts, int32_t* best, int32_t* best_median) {

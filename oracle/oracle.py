@@ -312,6 +312,30 @@ def is_in_frustum(view, pos, normal, min_dist, max_dist, cos_limit):
     return o
 
 
+def search_for_triangulation(k1, d1, has_mp1, stereo1, fv1, k2, d2, has_mp2, stereo2, fv2, F12, epipole, scale2, sigma2, only_stereo,
+                             nn_ratio, check_ori, _L=None):
+    """SearchForTriangulation -> (nmatches, matches12[n1])."""
+    k1 = np.ascontiguousarray(k1); d1 = np.ascontiguousarray(d1, np.uint8); k2 = np.ascontiguousarray(k2); d2 = np.ascontiguousarray(d2, np.uint8)
+    h1 = np.ascontiguousarray(has_mp1, np.uint8); h2 = np.ascontiguousarray(has_mp2, np.uint8)
+    s1 = np.ascontiguousarray(stereo1, np.uint8); s2 = np.ascontiguousarray(stereo2, np.uint8)
+    a1, b1, c1 = (np.ascontiguousarray(a, np.int32) for a in fv1)
+    a2, b2, c2 = (np.ascontiguousarray(a, np.int32) for a in fv2)
+    F = np.ascontiguousarray(F12, np.float32).ravel(); sc = np.ascontiguousarray(scale2, np.float32); sg = np.ascontiguousarray(sigma2, np.float32)
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    if _L is None:
+        skip1 = (h1 != 0) | ((s1 == 0) if only_stereo else False)
+        skip2 = (h2 != 0) | ((s2 == 0) if only_stereo else False)
+        skip1 = np.ascontiguousarray(skip1, np.uint8); skip2 = np.ascontiguousarray(skip2, np.uint8)
+        n = lib().orc_search_for_triangulation(_p(k1), _p(d1), len(k1), _p(skip1), _p(s1), _p(a1), _p(b1), _p(c1), len(a1), _p(k2), _p(d2),
+                                               len(k2), _p(skip2), _p(s2), _p(a2), _p(b2), _p(c2), len(a2), _p(F), _fp(epipole[0]),
+                                               _fp(epipole[1]), _p(sc), _p(sg), int(check_ori), _p(m12))
+    else:
+        n = _L.refm_search_for_triangulation(_p(k1), _p(d1), len(k1), _p(h1), _p(s1), _p(a1), _p(b1), _p(c1), len(a1), _p(k2), _p(d2), len(k2),
+                                             _p(h2), _p(s2), _p(a2), _p(b2), _p(c2), len(a2), _p(F), _fp(epipole[0]), _fp(epipole[1]),
+                                             _p(sc), _p(sg), int(only_stereo), _fp(nn_ratio), int(check_ori), _p(m12))
+    return n, m12[:len(k1)]
+
+
 def distinctive_descriptors(desc, start, _L=None):
     """MapPoint::ComputeDistinctiveDescriptors for CSR lists of observed descriptors -> (best index per point, its median)."""
     desc = np.ascontiguousarray(desc, np.uint8); start = np.ascontiguousarray(start, np.int32)
@@ -463,6 +487,9 @@ class RefMatch:
 
     def distinctive_descriptors(self, desc, start):
         return distinctive_descriptors(desc, start, _L=self.L)
+
+    def search_for_triangulation(self, *a):
+        return search_for_triangulation(*a, _L=self.L)
 
     def hamming256(self, a, b):
         return self.L.refm_hamming256(_p(np.ascontiguousarray(a, np.uint8)), _p(np.ascontiguousarray(b, np.uint8)))

@@ -445,6 +445,43 @@ int refm_search_by_bow_kf(const Kp* k1, const uint8_t* d1, int n1, const uint8_t
     return n;
 }
 
+// ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:658-824).  The camera is the identity and GetCameraCenter() of
+// key frame 1 is the origin, so the epipole of :666-672 is t2w.xy / t2w.z: key frame 2 gets t2w = (ex, ey, 1).
+int refm_search_for_triangulation(const Kp* k1, const uint8_t* d1, int n1, const uint8_t* has_mp1, const uint8_t* stereo1,
+                                  const int32_t* ids1, const int32_t* st1, const int32_t* it1, int nn1, const Kp* k2, const uint8_t* d2,
+                                  int n2, const uint8_t* has_mp2, const uint8_t* stereo2, const int32_t* ids2, const int32_t* st2,
+                                  const int32_t* it2, int nn2, const float* F12, float ex, float ey, const float* scale2,
+                                  const float* sigma2, int only_stereo, float nn_ratio, int check_ori, int32_t* matches12) {
+    FrameView v1{k1, d1, n1, 0.f, 0.f, 64.f / 1280.f, 48.f / 720.f, FRAME_GRID_COLS, FRAME_GRID_ROWS};
+    FrameView v2{k2, d2, n2, 0.f, 0.f, 64.f / 1280.f, 48.f / 720.f, FRAME_GRID_COLS, FRAME_GRID_ROWS};
+    set_front_statics(v1);
+    Frame F1, F2;
+    fill_front(F1, v1, scale2); fill_front(F2, v2, scale2);
+    F2.mvLevelSigma2.assign(sigma2, sigma2 + kLevels); F1.mvLevelSigma2 = F2.mvLevelSigma2;
+    for (int i = 0; i < n1; ++i) F1.mvuRight[i] = stereo1[i] ? 1.f : -1.f;
+    for (int i = 0; i < n2; ++i) F2.mvuRight[i] = stereo2[i] ? 1.f : -1.f;
+    Pool pool;
+    std::vector<uint8_t> zero(32, 0);
+    for (int i = 0; i < n1; ++i) if (has_mp1[i]) { MapPoint* p = make_mp(0, 0, zero.data(), 0, 1); pool.mps.push_back(p); F1.mvpMapPoints[i] = p; }
+    for (int i = 0; i < n2; ++i) if (has_mp2[i]) { MapPoint* p = make_mp(0, 0, zero.data(), 0, 1); pool.mps.push_back(p); F2.mvpMapPoints[i] = p; }
+    for (int a = 0; a < nn1; ++a) for (int p = st1[a]; p < st1[a + 1]; ++p) F1.mFeatVec[ids1[a]].push_back((unsigned)it1[p]);
+    for (int b = 0; b < nn2; ++b) for (int p = st2[b]; p < st2[b + 1]; ++p) F2.mFeatVec[ids2[b]].push_back((unsigned)it2[p]);
+    KeyFrame* kf1 = new KeyFrame(F1, NULL, NULL);
+    KeyFrame* kf2 = new KeyFrame(F2, NULL, NULL);
+    pool.kfs.push_back(kf1); pool.kfs.push_back(kf2);
+    cv::Mat T2 = cv::Mat::eye(4, 4, CV_32F);
+    T2.at<float>(0, 3) = ex; T2.at<float>(1, 3) = ey; T2.at<float>(2, 3) = 1.f;
+    kf2->SetPose(T2);
+    cv::Mat F(3, 3, CV_32F);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) F.at<float>(r, c) = F12[3 * r + c];
+    std::vector<std::pair<size_t, size_t> > pairs;
+    ORBmatcher m(nn_ratio, check_ori != 0);
+    const int n = m.SearchForTriangulation(kf1, kf2, F, pairs, only_stereo != 0);
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    for (size_t k = 0; k < pairs.size(); ++k) matches12[pairs[k].first] = (int)pairs[k].second;
+    return n;
+}
+
 // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307).  Each observed descriptor sits in a key frame of
 // its own; the key frames are constructed in one array so that std::map<KeyFrame*, size_t> walks them in input order.
 void refm_distinctive_descriptors(const uint8_t* desc, const int32_t* start, int npts, int32_t* best) {

@@ -202,6 +202,25 @@ def test_search_by_bow(oracle, front_pair):
             assert n_g == n_o and np.array_equal(m_g, m_o) and n_g > 50
 
 
+def test_search_for_triangulation(oracle):
+    from fishbirdeyevisualslam_b200.matcher import ORBmatcher
+    from test_oracle_vs_refmatch import triangulation_args
+    rng = np.random.default_rng(31)
+    F1, F2 = frame_pair(rng, 1500)
+
+    def nodes(k, shift):
+        return (np.floor((k["x"] - shift[0]) / 80).astype(int) * 16 + np.floor((k["y"] - shift[1]) / 80).astype(int)) * 8 + k["octave"]
+    has1, has2 = (rng.random(F1.N) < 0.5).astype(np.uint8), (rng.random(F2.N) < 0.5).astype(np.uint8)
+    for node2 in (nodes(F2.kps, (3, 2)), np.zeros(F2.N, int)):
+        node1 = nodes(F1.kps, (0, 0)) if node2.any() else np.zeros(F1.N, int)
+        args = triangulation_args(F1, F2, has1, has2, node1, node2, 3)
+        for only_stereo, ori in [(False, True), (False, False), (True, True)]:
+            n_g, m_g = ORBmatcher(0.6, ori).SearchForTriangulation(*args, bOnlyStereo=only_stereo)
+            n_o, m_o = oracle.search_for_triangulation(*args, only_stereo, 0.6, ori)
+            assert n_g == n_o and np.array_equal(m_g, m_o)
+            assert n_g > (5 if only_stereo else 40)
+
+
 def test_distinctive_descriptors(oracle):
     from fishbirdeyevisualslam_b200.matcher import ORBmatcher
     from test_oracle_vs_refmatch import distinct_lists

@@ -98,6 +98,10 @@ def scene_outputs(impl, seed, is_ref):
     for j, (ratio, ori) in enumerate([(0.75, True), (0.9, False)]):            # key frame vs key frame (loop closing)
         n, c = impl.search_by_bow_kf(F1.kps, F1.desc, has_mp, featvec(node1), F2.kps, F2.desc, has_mp2, featvec(node2), ratio, ori)
         out[f"bowkf{j}"] = np.concatenate([[n], c]).astype(np.int32)
+    # SearchForTriangulation: F12 of a sideways translation (x2 = x1 + (3, 2) * depth factor), slightly perturbed
+    for j, (ratio, ori, only_stereo) in enumerate([(0.6, True, False), (0.6, False, False), (0.6, True, True)]):
+        n, c = impl.search_for_triangulation(*triangulation_args(F1, F2, has_mp, has_mp2, node1, node2, seed), only_stereo, ratio, ori)
+        out[f"tri{j}"] = np.concatenate([[n], c]).astype(np.int32)
     # MapPoint::ComputeDistinctiveDescriptors on clusters of observed descriptors (sizes 0 .. 40, duplicates = median ties)
     dd, st = distinct_lists(rng)
     best, _ = impl.distinctive_descriptors(dd, st)
@@ -108,6 +112,18 @@ def scene_outputs(impl, seed, is_ref):
     out["distinct"] = chosen
     out["distinct_none"] = (best < 0).astype(np.int32)
     return out
+
+
+def triangulation_args(F1, F2, has_mp1, has_mp2, node1, node2, seed):
+    """(k1, d1, has_mp1, stereo1, fv1, k2, d2, has_mp2, stereo2, fv2, F12, epipole, scale2, sigma2) for both implementations."""
+    r = np.random.default_rng(5000 + seed)
+    F12 = (np.array([[0, 0, -2], [0, 0, 3], [2, -3, 0]], np.float64) * 0.37 + r.normal(0, 3e-7, (3, 3))).astype(np.float32)
+    stereo1 = (r.random(F1.N) < 0.3).astype(np.uint8)
+    stereo2 = (r.random(F2.N) < 0.3).astype(np.uint8)
+    sf = F2.scale_factors
+    return (F1.kps, F1.desc, (np.asarray(has_mp1) * (r.random(F1.N) < 0.4)).astype(np.uint8), stereo1, featvec(node1), F2.kps, F2.desc,
+            (np.asarray(has_mp2) * (r.random(F2.N) < 0.3)).astype(np.uint8), stereo2, featvec(node2), F12, (320.5, 240.25), sf,
+            (sf * sf).astype(np.float32))
 
 
 def distinct_lists(rng, sizes=(0, 1, 2, 3, 4, 5, 8, 13, 21, 40, 7, 7, 2, 1, 0, 33)):
@@ -142,7 +158,7 @@ def test_restated_oracle_equals_verbatim_reference(oracle, seed):
             continue
         assert np.array_equal(got[k], v, equal_nan=True), k
     assert ref["init0"][0] > 20 and ref["bird0"][0] > 10 and ref["last0"][0] > 50 and ref["map0"][0] > 50 and ref["birdmap"][0] > 20
-    assert ref["bow1"][0] > 50 and ref["bowkf0"][0] > 50
+    assert ref["bow1"][0] > 50 and ref["bowkf0"][0] > 50 and ref["tri0"][0] > 50 and ref["tri2"][0] > 5
 
 
 @pytest.mark.parametrize("seed", SEEDS)
