@@ -137,7 +137,10 @@ __global__ void __launch_bounds__(256) k_window_rows(FrameDev f, QueryDev qs, bo
 }
 
 // ---- parallel stage, order-independent searches: top-2 directly ------------------------------------------------------
-__global__ void __launch_bounds__(256) k_window_top2(FrameDev f, QueryDev qs, bool incl, int* __restrict__ best_idx,
+// kReproj adds the per-candidate reprojection gate of ORBmatcher::Fuse (src/ORBmatcher.cc:911-937): q.w carries ur, the
+// chi-square bounds are compared in double like the reference's `e2*invSigma2 > 5.99` (float product, double literal).
+template <bool kReproj>
+__global__ void __launch_bounds__(256) k_window_top2(FrameDev f, QueryDev qs, bool incl, ReprojGate rg, int* __restrict__ best_idx,
                                                      int* __restrict__ best_dist, int* __restrict__ second_dist) {
     const int b = blockIdx.y;
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -154,6 +157,19 @@ __global__ void __launch_bounds__(256) k_window_top2(FrameDev f, QueryDev qs, bo
         window_walk(f.kps + (size_t)b * f.kp_stride, f.start + (size_t)b * (f.gcols * f.grows + 1),
                     f.items + (size_t)b * f.kp_stride, f.min_x, f.min_y, f.inv_w, f.inv_h, f.gcols, f.grows, q.x, q.y, q.z, lv.x,
                     lv.y, incl, [&](int idx, bool pass, int rank) {
+                        if (kReproj && pass) {
+                            const fbe_keypoint* kp = f.kps + (size_t)b * f.kp_stride + idx;
+                            const float ex = __fsub_rn(q.x, kp->x), ey = __fsub_rn(q.y, kp->y);
+                            float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                            const float kpr = rg.t_uright ? rg.t_uright[idx] : -1.0f;
+                            double bound = 5.99;
+                            if (kpr >= 0.0f) {
+                                const float er = __fsub_rn(q.w, kpr);
+                                e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                                bound = 7.8;
+                            }
+                            if ((double)__fmul_rn(e2, rg.inv_sigma2[kp->octave]) > bound) pass = false;
+                        }
                         if (pass) {
                             const unsigned k = ((unsigned)hamming256(qd, tdesc + (size_t)idx * 32) << 20) | (unsigned)min(rank, 0xFFFFF);
                             if (k < k1) my_idx = idx;
@@ -538,7 +554,17 @@ int launch_window_top2(const FrameDev& f, const QueryDev& qs, int nb, int max_nq
                        int* second_dist, cudaStream_t st) {
     if (max_nq <= 0) return FBE_OK;
     dim3 grid((max_nq + 7) / 8, nb);
-    k_window_top2<<<grid, 256, 0, st>>>(f, qs, incl, best_idx, best_dist, second_dist);
+    k_window_top2<false><<<grid, 256, 0, st>>>(f, qs, incl, ReprojGate(), best_idx, best_dist, second_dist);
+    count_launch();
+    FBE_CUDA(cudaGetLastError());
+    return FBE_OK;
+}
+
+int launch_window_top2_reproj(const FrameDev& f, const QueryDev& qs, int max_nq, const ReprojGate& rg, int* best_idx, int* best_dist,
+                              int* second_dist, cudaStream_t st) {
+    if (max_nq <= 0) return FBE_OK;
+    dim3 grid((max_nq + 7) / 8, 1);
+    k_window_top2<true><<<grid, 256, 0, st>>>(f, qs, true, rg, best_idx, best_dist, second_dist);
     count_launch();
     FBE_CUDA(cudaGetLastError());
     return FBE_OK;

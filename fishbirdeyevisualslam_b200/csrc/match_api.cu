@@ -530,6 +530,45 @@ int fbe_search_for_triangulation(fbe_matcher* m, const fbe_keypoint* kf1_kps, co
     return FBE_OK;
 }
 
+int fbe_fuse_search(fbe_matcher* m, const fbe_frame_view* kf, const float* kf_uright, const float* inv_level_sigma2, int32_t nlevels,
+                    const float* proj, const float* proj_ur, const int32_t* level, const float* radius, const uint8_t* mp_desc,
+                    int32_t n, int32_t check_chi2, int32_t* best_idx, int32_t* best_dist) {
+    if (!m || !kf || n < 0 || (n > 0 && (!proj || !level || !radius || !mp_desc || !best_idx || !best_dist)) ||
+        (check_chi2 && (!inv_level_sigma2 || nlevels < 1 || nlevels > FBE_MAX_LEVELS)))
+        return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(m->device));
+    for (int i = 0; i < n; ++i) { best_idx[i] = -1; best_dist[i] = INT_MAX; }
+    if (n == 0 || kf->n == 0) return FBE_OK;
+    if (check_chi2)
+        for (int k = 0; k < kf->n; ++k)
+            if (kf->kps[k].octave < 0 || kf->kps[k].octave >= nlevels) { set_error("key frame keypoint octave outside mvInvLevelSigma2"); return FBE_E_INVALID; }
+    std::vector<float4> q(n);
+    std::vector<int2> lv(n);
+    for (int i = 0; i < n; ++i) {
+        const bool skip = std::isnan(proj[2 * i]);
+        q[i] = make_float4(skip ? 0.f : proj[2 * i], skip ? 0.f : proj[2 * i + 1], skip ? -1.f : radius[i], proj_ur ? proj_ur[i] : 0.f);
+        // `kpLevel<nPredictedLevel-1 || kpLevel>nPredictedLevel` (:905, :1065); level 0 -> minLevel -1 filters nothing below
+        lv[i] = make_int2(level[i] - 1, level[i]);
+    }
+    FrameDev Kf;
+    QueryDev qs;
+    FBE_TRY(upload_frame(m, m->fa, kf, true, Kf));
+    FBE_TRY(upload_queries(m, q, lv, mp_desc, n, qs));
+    FBE_TRY(m->i0.ensure((size_t)n * 4)); FBE_TRY(m->i1.ensure((size_t)n * 4)); FBE_TRY(m->i2.ensure((size_t)n * 4));
+    if (check_chi2) {
+        ReprojGate rg;
+        for (int k = 0; k < nlevels; ++k) rg.inv_sigma2[k] = inv_level_sigma2[k];
+        if (kf_uright) { FBE_TRY(upload(m->f0, kf_uright, (size_t)kf->n * 4, m->stream)); rg.t_uright = m->f0.as<float>(); }
+        FBE_TRY(launch_window_top2_reproj(Kf, qs, n, rg, m->i0.as<int>(), m->i1.as<int>(), m->i2.as<int>(), m->stream));
+    } else {
+        FBE_TRY(launch_window_top2(Kf, qs, 1, n, true, m->i0.as<int>(), m->i1.as<int>(), m->i2.as<int>(), m->stream));
+    }
+    FBE_CUDA(cudaMemcpyAsync(best_idx, m->i0.p, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    FBE_CUDA(cudaMemcpyAsync(best_dist, m->i1.p, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    FBE_CUDA(cudaStreamSynchronize(m->stream));
+    return FBE_OK;
+}
+
 int fbe_distinctive_descriptors(fbe_matcher* m, const uint8_t* desc, const int32_t* start, int32_t npts, int32_t* best,
                                 int32_t* best_median) {
     if (!m || npts < 0 || (npts > 0 && (!start || !best))) return FBE_E_INVALID;

@@ -25,6 +25,9 @@ struct QueryDev {
     int stride;
 };
 
+// Reprojection gate of ORBmatcher::Fuse: target-side mvuRight (NULL = monocular) and mvInvLevelSigma2
+struct ReprojGate { const float* t_uright = nullptr; float inv_sigma2[FBE_MAX_LEVELS] = {}; };
+
 constexpr unsigned kNoKey = 0xFFFFFFFFu;     // "no candidate" in packed (dist << 20 | rank) keys
 constexpr int kRowDistBits = 9;              // rows: (idx << 9) | dist, dist in [0,256]
 
@@ -77,6 +80,8 @@ int launch_window_rows(const FrameDev& f, const QueryDev& qs, int nb, int max_nq
                        int* cnt, int* overflow, cudaStream_t st);
 int launch_window_top2(const FrameDev& f, const QueryDev& qs, int nb, int max_nq, bool upper_inclusive, int* best_idx,
                        int* best_dist, int* second_dist, cudaStream_t st);
+int launch_window_top2_reproj(const FrameDev& f, const QueryDev& qs, int max_nq, const ReprojGate& rg, int* best_idx, int* best_dist,
+                              int* second_dist, cudaStream_t st);
 int launch_resolve(const ResolveArgs& a, int nb, cudaStream_t st);
 int launch_bird_finish(const BirdFinishArgs& a, int nb, cudaStream_t st);
 int launch_map_finish(const int* best_idx, const int* best_dist, const int* second_dist, int n, float nn_ratio, int th_dist,

@@ -1,7 +1,7 @@
 // Drop-in bodies for the ORBmatcher methods on the hot path.  This file is compiled INSIDE the reference tree in place
 // of the same-named method bodies of src/ORBmatcher.cc (see INTEGRATION.md for the exact patch); the class declaration
 // include/ORBmatcher.h is unchanged, so Tracking.cc / LocalMapping.cc / LoopClosing.cc call it as before.  Methods that
-// are not on the hot path (SearchBySim3, Fuse x2) keep the reference's own CPU code.
+// are not on the hot path (SearchBySim3) keep the reference's own CPU code.
 //
 // In the build image of this repository it is compiled against the reference's own headers with OpenCV replaced by the
 // test shim oracle/cvshim_m (oracle/Makefile target `dropinmatch`) and checked on the GPU against the outputs of the
@@ -11,6 +11,7 @@
 // map points to (projection, level, descriptor) arrays; the C-ABI returns index lists which are turned back into
 // pointer writes here.  cv::Mat arithmetic of the reference (projections, bird pixel conversion, the distance
 // filter of BirdMapPointMatch) is executed here exactly as the reference writes it.
+#include <climits>
 #include <cmath>
 #include <limits>
 #include <set>
@@ -358,6 +359,142 @@ int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F
     for (int i = 0; i < n1; i++)
         if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)m12[i]));
     return nmatches;
+}
+
+namespace {
+fbe_frame_view keyframe_view(KeyFrame* pKF) {
+    fbe_frame_view kv;
+    kv.kps = reinterpret_cast<const fbe_keypoint*>(pKF->mvKeysUn.data());
+    kv.desc = desc_ptr(pKF->mDescriptors);
+    kv.n = (int)pKF->mvKeysUn.size();
+    kv.min_x = pKF->mnMinX; kv.min_y = pKF->mnMinY;
+    kv.inv_w = pKF->mfGridElementWidthInv; kv.inv_h = pKF->mfGridElementHeightInv;
+    kv.gcols = pKF->mnGridCols; kv.grows = pKF->mnGridRows;
+    return kv;
+}
+}  // namespace
+
+// src/ORBmatcher.cc:826-976.  The candidate search runs on the device for every point that is eligible on entry; the map
+// updates are then replayed in order on the host, re-checking isBad() / IsInKeyFrame() at that moment (an eligible point
+// can only become ineligible through the replay, never the other way round; the search does not read map state).
+int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th) {
+    cv::Mat Rcw = pKF->GetRotation();
+    cv::Mat tcw = pKF->GetTranslation();
+    const float &fx = pKF->fx, &fy = pKF->fy, &cx = pKF->cx, &cy = pKF->cy, &bf = pKF->mbf;
+    cv::Mat Ow = pKF->GetCameraCenter();
+    const int nMPs = (int)vpMapPoints.size();
+    std::vector<float> proj(2 * (size_t)std::max(nMPs, 1), std::numeric_limits<float>::quiet_NaN()), pur(std::max(nMPs, 1), 0.f), radius(std::max(nMPs, 1), 0.f);
+    std::vector<int> level(std::max(nMPs, 1), 0);
+    std::vector<unsigned char> mpdesc(32 * (size_t)std::max(nMPs, 1), 0);
+    for (int i = 0; i < nMPs; i++) {
+        MapPoint* pMP = vpMapPoints[i];
+        if (!pMP) continue;
+        if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+        cv::Mat p3Dw = pMP->GetWorldPos();
+        cv::Mat p3Dc = Rcw * p3Dw + tcw;
+        if (p3Dc.at<float>(2) < 0.0f) continue;
+        const float invz = 1 / p3Dc.at<float>(2);
+        const float x = p3Dc.at<float>(0) * invz, y = p3Dc.at<float>(1) * invz;
+        const float u = fx * x + cx, v = fy * y + cy;
+        if (!pKF->IsInImage(u, v)) continue;
+        const float ur = u - bf * invz;
+        const float maxDistance = pMP->GetMaxDistanceInvariance(), minDistance = pMP->GetMinDistanceInvariance();
+        cv::Mat PO = p3Dw - Ow;
+        const float dist3D = cv::norm(PO);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        cv::Mat Pn = pMP->GetNormal();
+        if (PO.dot(Pn) < 0.5 * dist3D) continue;
+        const int nPredictedLevel = pMP->PredictScale(dist3D, pKF);
+        level[i] = nPredictedLevel;
+        radius[i] = th * pKF->mvScaleFactors[nPredictedLevel];
+        proj[2 * i] = u; proj[2 * i + 1] = v; pur[i] = ur;
+        copy_desc(pMP->GetDescriptor(), &mpdesc[32 * (size_t)i]);
+    }
+    std::vector<int> best_idx(std::max(nMPs, 1), -1), best_dist(std::max(nMPs, 1), INT_MAX);
+    fbe_frame_view kv = keyframe_view(pKF);
+    fbe_fuse_search(matcher_for(mfNNratio, mbCheckOrientation), &kv, pKF->mvuRight.data(), pKF->mvInvLevelSigma2.data(),
+                    (int)pKF->mvInvLevelSigma2.size(), proj.data(), pur.data(), level.data(), radius.data(), mpdesc.data(), nMPs, 1,
+                    best_idx.data(), best_dist.data());
+    int nFused = 0;
+    for (int i = 0; i < nMPs; i++) {
+        MapPoint* pMP = vpMapPoints[i];
+        if (!pMP || proj[2 * i] != proj[2 * i]) continue;
+        if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+        if (best_dist[i] <= TH_LOW) {
+            const int bestIdx = best_idx[i];
+            MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx);
+            if (pMPinKF) {
+                if (!pMPinKF->isBad()) {
+                    if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                    else pMPinKF->Replace(pMP);
+                }
+            } else {
+                pMP->AddObservation(pKF, bestIdx);
+                pKF->AddMapPoint(pMP, bestIdx);
+            }
+            nFused++;
+        }
+    }
+    return nFused;
+}
+
+// src/ORBmatcher.cc:978-1101 (loop closing)
+int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, float th, std::vector<MapPoint*>& vpReplacePoint) {
+    const float &fx = pKF->fx, &fy = pKF->fy, &cx = pKF->cx, &cy = pKF->cy;
+    cv::Mat sRcw = Scw.rowRange(0, 3).colRange(0, 3);
+    const float scw = sqrt(sRcw.row(0).dot(sRcw.row(0)));
+    cv::Mat Rcw = sRcw / scw;
+    cv::Mat tcw = Scw.rowRange(0, 3).col(3) / scw;
+    cv::Mat Ow = -Rcw.t() * tcw;
+    const std::set<MapPoint*> spAlreadyFound = pKF->GetMapPoints();
+    const int nPoints = (int)vpPoints.size();
+    std::vector<float> proj(2 * (size_t)std::max(nPoints, 1), std::numeric_limits<float>::quiet_NaN()), radius(std::max(nPoints, 1), 0.f);
+    std::vector<int> level(std::max(nPoints, 1), 0);
+    std::vector<unsigned char> mpdesc(32 * (size_t)std::max(nPoints, 1), 0);
+    for (int iMP = 0; iMP < nPoints; iMP++) {
+        MapPoint* pMP = vpPoints[iMP];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+        cv::Mat p3Dw = pMP->GetWorldPos();
+        cv::Mat p3Dc = Rcw * p3Dw + tcw;
+        if (p3Dc.at<float>(2) < 0.0f) continue;
+        const float invz = 1.0 / p3Dc.at<float>(2);
+        const float x = p3Dc.at<float>(0) * invz, y = p3Dc.at<float>(1) * invz;
+        const float u = fx * x + cx, v = fy * y + cy;
+        if (!pKF->IsInImage(u, v)) continue;
+        const float maxDistance = pMP->GetMaxDistanceInvariance(), minDistance = pMP->GetMinDistanceInvariance();
+        cv::Mat PO = p3Dw - Ow;
+        const float dist3D = cv::norm(PO);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        cv::Mat Pn = pMP->GetNormal();
+        if (PO.dot(Pn) < 0.5 * dist3D) continue;
+        const int nPredictedLevel = pMP->PredictScale(dist3D, pKF);
+        level[iMP] = nPredictedLevel;
+        radius[iMP] = th * pKF->mvScaleFactors[nPredictedLevel];
+        proj[2 * iMP] = u; proj[2 * iMP + 1] = v;
+        copy_desc(pMP->GetDescriptor(), &mpdesc[32 * (size_t)iMP]);
+    }
+    std::vector<int> best_idx(std::max(nPoints, 1), -1), best_dist(std::max(nPoints, 1), INT_MAX);
+    fbe_frame_view kv = keyframe_view(pKF);
+    fbe_fuse_search(matcher_for(mfNNratio, mbCheckOrientation), &kv, NULL, NULL, 0, proj.data(), NULL, level.data(), radius.data(),
+                    mpdesc.data(), nPoints, 0, best_idx.data(), best_dist.data());
+    int nFused = 0;
+    for (int iMP = 0; iMP < nPoints; iMP++) {
+        MapPoint* pMP = vpPoints[iMP];
+        if (proj[2 * iMP] != proj[2 * iMP]) continue;
+        if (pMP->isBad()) continue;                      // spAlreadyFound is a snapshot taken on entry (:998), already applied
+        if (best_dist[iMP] <= TH_LOW) {
+            const int bestIdx = best_idx[iMP];
+            MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx);
+            if (pMPinKF) {
+                if (!pMPinKF->isBad()) vpReplacePoint[iMP] = pMPinKF;
+            } else {
+                pMP->AddObservation(pKF, bestIdx);
+                pKF->AddMapPoint(pMP, bestIdx);
+            }
+            nFused++;
+        }
+    }
+    return nFused;
 }
 
 // src/ORBmatcher.cc:1602-1760, isProject == 0 (every call site of the reference passes 0)

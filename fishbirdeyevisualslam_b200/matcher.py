@@ -297,6 +297,22 @@ class ORBmatcher:
                                                    ptr(m12), C.byref(n)))
         return n.value, m12[:len(k1)]
 
+    def FuseSearch(self, KF: Frame, kf_uright, inv_level_sigma2, proj, proj_ur, level, radius, mp_desc, check_chi2: bool):
+        """The candidate search of both ORBmatcher::Fuse overloads (ORBmatcher.cc:826-976 with the reprojection gate,
+        :978-1101 without).  -> (best_idx[n], best_dist[n]); the caller applies `bestDist <= TH_LOW` and replays the map updates."""
+        proj = np.ascontiguousarray(proj, np.float32); level = np.ascontiguousarray(level, np.int32)
+        radius = np.ascontiguousarray(radius, np.float32); mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+        inv = np.ascontiguousarray(inv_level_sigma2, np.float32)
+        ur = None if kf_uright is None else np.ascontiguousarray(kf_uright, np.float32)
+        pur = None if proj_ur is None else np.ascontiguousarray(proj_ur, np.float32)
+        n = len(level)
+        bi = np.full(max(n, 1), -1, np.int32); bd = np.zeros(max(n, 1), np.int32)
+        v = KF.view()
+        check(self._L.fbe_fuse_search(self._h, C.byref(v), None if ur is None else ptr(ur), ptr(inv), len(inv), ptr(proj),
+                                      None if pur is None else ptr(pur), ptr(level), ptr(radius), ptr(mp_desc), n, C.c_int32(bool(check_chi2)),
+                                      ptr(bi), ptr(bd)))
+        return bi[:n], bd[:n]
+
     def ComputeDistinctiveDescriptors(self, desc, start):
         """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:242-307) for many map points: `desc` rows start[p]..start[p+1]-1
         are the descriptors observed for point p.  -> (best index inside each list or -1, that row's median distance)."""

@@ -277,6 +277,21 @@ FBE_API int fbe_search_for_triangulation(fbe_matcher* m, const fbe_keypoint* kf1
                                          float ex, float ey, const float* kf2_scale_factors, const float* kf2_level_sigma2,
                                          int32_t nlevels, int32_t* matches12, int32_t* nmatches);
 
+/* The candidate search of both ORBmatcher::Fuse overloads, src/ORBmatcher.cc:826-976 (local mapping) and :978-1101 (loop
+ * closing; next row f-4).  The projection, depth / viewing-angle rejections, MapPoint::PredictScale and the radius
+ * (th * mvScaleFactors[level]) stay in the host shim like for the other projection searches: proj is n x 2 (u, v), NaN u =
+ * skipped; proj_ur = u - bf*invz (only read when check_chi2 != 0 and the key frame has stereo features; may be NULL);
+ * level = nPredictedLevel; radius per point.  kf: the key frame (mvKeysUn, mDescriptors, its 64x48 grid geometry);
+ * kf_uright = mvuRight (NULL = monocular: all -1); inv_level_sigma2 = mvInvLevelSigma2.
+ * check_chi2 != 0 applies the reprojection gate of the first overload (:911-937: 5.99 mono / 7.8 stereo), 0 = second
+ * overload (no gate).  Output per point: best_idx = the most similar key-frame feature among the candidates of levels
+ * [level-1, level] (first on ties, -1 = none), best_dist = its distance (INT_MAX = none).  The caller applies
+ * `bestDist <= TH_LOW` and replays Replace / AddObservation / AddMapPoint / vpReplacePoint in map-point order, re-checking
+ * isBad() / IsInKeyFrame at that moment (the search itself does not depend on map state). */
+FBE_API int fbe_fuse_search(fbe_matcher* m, const fbe_frame_view* kf, const float* kf_uright, const float* inv_level_sigma2,
+                            int32_t nlevels, const float* proj, const float* proj_ur, const int32_t* level, const float* radius,
+                            const uint8_t* mp_desc, int32_t n, int32_t check_chi2, int32_t* best_idx, int32_t* best_dist);
+
 /* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307; MapPointBird.cc:90-155 is the same computation) for
  * npts map points at once (next row f-4).  The descriptors observed for point p are rows start[p] .. start[p+1]-1 of
  * `desc` (x 32 bytes), in the order the reference walks them (std::map<KeyFrame*, size_t> iteration order; the bird

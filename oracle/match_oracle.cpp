@@ -559,6 +559,88 @@ void orc_is_in_frustum(const FrustumView* v, const float* pos, const float* norm
     }
 }
 
+// The candidate search shared by both ORBmatcher::Fuse overloads (src/ORBmatcher.cc:893-948, :1053-1079): walk
+// KeyFrame::GetFeaturesInArea(u, v, radius) (src/KeyFrame.cc:901-940, no level filter, inclusive cell bounds), keep levels
+// [nPredictedLevel-1, nPredictedLevel], optionally gate on the reprojection error (:911-937), strict `dist<bestDist`.
+static void fuse_search_one(const FrameView* kf, const Grid& g, const float* uright, const float* inv_sigma2, float u, float v, float ur,
+                            int nPredictedLevel, float radius, const uint8_t* dMP, int check_chi2, int& bestIdx, int& bestDist) {
+    bestIdx = -1; bestDist = INT_MAX;
+    std::vector<int> vIndices = features_in_area(*kf, g, u, v, radius, -1, -1, true);
+    for (size_t c = 0; c < vIndices.size(); ++c) {
+        const int idx = vIndices[c];
+        const Kp& kp = kf->kps[idx];
+        const int kpLevel = kp.octave;
+        if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+        if (check_chi2) {
+            if (uright && uright[idx] >= 0) {
+                const float ex = u - kp.x, ey = v - kp.y, er = ur - uright[idx];
+                const float e2 = ex * ex + ey * ey + er * er;
+                if (e2 * inv_sigma2[kpLevel] > 7.8) continue;
+            } else {
+                const float ex = u - kp.x, ey = v - kp.y;
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * inv_sigma2[kpLevel] > 5.99) continue;
+            }
+        }
+        const int dist = hamming(dMP, kf->desc + (size_t)idx * 32);
+        if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+    }
+}
+
+void orc_fuse_search(const FrameView* kf, const float* uright, const float* inv_sigma2, const float* proj, const float* proj_ur,
+                     const int32_t* level, const float* radius, const uint8_t* mp_desc, int n, int check_chi2, int32_t* best_idx,
+                     int32_t* best_dist) {
+    Grid g = build_grid(*kf);
+    for (int i = 0; i < n; ++i) {
+        best_idx[i] = -1; best_dist[i] = INT_MAX;
+        if (std::isnan(proj[2 * i])) continue;
+        fuse_search_one(kf, g, uright, inv_sigma2, proj[2 * i], proj[2 * i + 1], proj_ur ? proj_ur[i] : 0.f, level[i], radius[i],
+                        mp_desc + (size_t)i * 32, check_chi2, best_idx[i], best_dist[i]);
+    }
+}
+
+// ORBmatcher::Fuse end to end, overload 1 (:826-976) or 2 (:978-1101), on an abstract map state: per point Observations() /
+// isBad() / IsInKeyFrame(pKF), per key-frame slot an occupant id with its own Observations() / isBad().  MapPoint::Replace
+// is treated as a recorded no-op (what the verbatim harness does), AddObservation / AddMapPoint update the state.
+// act: 0 nothing, 1 pMP->Replace(pMPinKF), 2 pMPinKF->Replace(pMP), 3 added to the empty slot, 5 vpReplacePoint[i] set.
+int orc_fuse(const FrameView* kf, const float* uright, const float* inv_sigma2, const float* proj, const float* proj_ur,
+             const int32_t* level, const float* radius, const uint8_t* mp_desc, const int32_t* mp_nobs, const uint8_t* mp_bad,
+             const uint8_t* mp_in_kf, int n, const int32_t* occ, const int32_t* occ_nobs, const uint8_t* occ_bad, int overload,
+             int32_t* act, int32_t* slot) {
+    Grid g = build_grid(*kf);
+    // slot state: -1 empty, j >= 0 original occupant j, -(i+2) map point i added by this call
+    std::vector<int> cur(occ, occ + kf->n);
+    std::vector<int> nobs(mp_nobs, mp_nobs + n);
+    std::vector<uint8_t> inkf(mp_in_kf, mp_in_kf + n);
+    int nFused = 0;
+    for (int i = 0; i < n; ++i) {
+        act[i] = 0; slot[i] = -1;
+        if (std::isnan(proj[2 * i])) continue;
+        if (mp_bad[i] || (overload == 1 && inkf[i])) continue;
+        int bestIdx, bestDist;
+        fuse_search_one(kf, g, uright, inv_sigma2, proj[2 * i], proj[2 * i + 1], proj_ur ? proj_ur[i] : 0.f, level[i], radius[i],
+                        mp_desc + (size_t)i * 32, overload == 1, bestIdx, bestDist);
+        if (bestDist <= TH_LOW) {
+            const int o = cur[bestIdx];
+            if (o != -1) {
+                const bool o_bad = o >= 0 ? occ_bad[o] != 0 : mp_bad[-o - 2] != 0;
+                const int o_nobs = o >= 0 ? occ_nobs[o] : nobs[-o - 2];
+                if (!o_bad) {
+                    if (overload == 1) act[i] = o_nobs > nobs[i] ? 1 : 2;
+                    else act[i] = 5;
+                    slot[i] = bestIdx;
+                }
+            } else {
+                nobs[i]++; inkf[i] = 1;                  // AddObservation
+                cur[bestIdx] = -(i + 2);                 // AddMapPoint
+                act[i] = 3; slot[i] = bestIdx;
+            }
+            nFused++;
+        }
+    }
+    return nFused;
+}
+
 // ORBmatcher::SearchForTriangulation  src/ORBmatcher.cc:658-824 with CheckDistEpipolarLine :141-158.  skipN = feature has a
 // map point or fails the bOnlyStereo filter; stereoN = mvuRight >= 0; (ex, ey) = epipole in key frame 2 (:666-672, computed
 // by the caller).  vbMatched2 exists in the reference but is never set, which is reproduced by not having it.

@@ -336,6 +336,41 @@ def search_for_triangulation(k1, d1, has_mp1, stereo1, fv1, k2, d2, has_mp2, ste
     return n, m12[:len(k1)]
 
 
+def fuse_search(kf, uright, inv_sigma2, proj, proj_ur, level, radius, mp_desc, check_chi2):
+    """The candidate search of ORBmatcher::Fuse -> (best_idx[n], best_dist[n])."""
+    proj = np.ascontiguousarray(proj, np.float32); level = np.ascontiguousarray(level, np.int32); radius = np.ascontiguousarray(radius, np.float32)
+    mp_desc = np.ascontiguousarray(mp_desc, np.uint8); inv = np.ascontiguousarray(inv_sigma2, np.float32)
+    ur = None if uright is None else np.ascontiguousarray(uright, np.float32)
+    pur = None if proj_ur is None else np.ascontiguousarray(proj_ur, np.float32)
+    n = len(level)
+    bi = np.full(max(n, 1), -1, np.int32); bd = np.zeros(max(n, 1), np.int32)
+    v = _view(kf)
+    lib().orc_fuse_search(C.byref(v), None if ur is None else _p(ur), _p(inv), _p(proj), None if pur is None else _p(pur), _p(level), _p(radius),
+                          _p(mp_desc), n, int(check_chi2), _p(bi), _p(bd))
+    return bi[:n], bd[:n]
+
+
+def fuse(kf, uright, inv_sigma2, proj, level, mp_desc, mp_nobs, mp_bad, mp_in_kf, occ, occ_nobs, occ_bad, th, overload, _L=None):
+    """ORBmatcher::Fuse overload 1 / 2 on an abstract map state (bf = 0: ur = u) -> (nFused, act[n], slot[n])."""
+    proj = np.ascontiguousarray(proj, np.float32); level = np.ascontiguousarray(level, np.int32); mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+    inv = np.ascontiguousarray(inv_sigma2, np.float32); ur = None if uright is None else np.ascontiguousarray(uright, np.float32)
+    nobs = np.ascontiguousarray(mp_nobs, np.int32); bad = np.ascontiguousarray(mp_bad, np.uint8); inkf = np.ascontiguousarray(mp_in_kf, np.uint8)
+    occ = np.ascontiguousarray(occ, np.int32); onobs = np.ascontiguousarray(occ_nobs, np.int32); obad = np.ascontiguousarray(occ_bad, np.uint8)
+    n = len(level)
+    act = np.zeros(max(n, 1), np.int32); slot = np.full(max(n, 1), -1, np.int32)
+    v = _view(kf)
+    sf = np.ascontiguousarray(kf.scale_factors, np.float32)
+    if _L is None:
+        radius = (np.float32(th) * sf[level]).astype(np.float32)
+        pur = np.ascontiguousarray(proj[:, 0])
+        nf = lib().orc_fuse(C.byref(v), None if ur is None else _p(ur), _p(inv), _p(proj), _p(pur), _p(level), _p(radius), _p(mp_desc), _p(nobs),
+                            _p(bad), _p(inkf), n, _p(occ), _p(onobs), _p(obad), int(overload), _p(act), _p(slot))
+    else:
+        nf = _L.refm_fuse(C.byref(v), None if ur is None else _p(ur), _p(sf), _p(inv), _p(proj), _p(level), _p(mp_desc), _p(nobs), _p(bad), _p(inkf),
+                          n, _p(occ), _p(onobs), _p(obad), len(onobs), _fp(th), int(overload), _p(act), _p(slot))
+    return nf, act[:n], slot[:n]
+
+
 def distinctive_descriptors(desc, start, _L=None):
     """MapPoint::ComputeDistinctiveDescriptors for CSR lists of observed descriptors -> (best index per point, its median)."""
     desc = np.ascontiguousarray(desc, np.uint8); start = np.ascontiguousarray(start, np.int32)
@@ -490,6 +525,9 @@ class RefMatch:
 
     def search_for_triangulation(self, *a):
         return search_for_triangulation(*a, _L=self.L)
+
+    def fuse(self, *a):
+        return fuse(*a, _L=self.L)
 
     def hamming256(self, a, b):
         return self.L.refm_hamming256(_p(np.ascontiguousarray(a, np.uint8)), _p(np.ascontiguousarray(b, np.uint8)))

@@ -55,7 +55,8 @@ int MapPoint::Observations() { return nObs; }
 bool MapPoint::IsInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) != 0; }
 void MapPoint::AddObservation(KeyFrame* pKF, size_t idx) { if (!mObservations.count(pKF)) { mObservations[pKF] = idx; nObs++; } }
 int MapPoint::GetIndexInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) ? (int)mObservations[pKF] : -1; }
-void MapPoint::Replace(MapPoint*) {}
+static std::vector<std::pair<MapPoint*, MapPoint*> > g_replace_log;      // (this, argument) of every Replace call
+void MapPoint::Replace(MapPoint* pMP) { g_replace_log.push_back(std::make_pair(this, pMP)); }
 float MapPoint::GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }      // src/MapPoint.cc:373-377
 float MapPoint::GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }      // src/MapPoint.cc:379-383
 
@@ -443,6 +444,68 @@ int refm_search_by_bow_kf(const Kp* k1, const uint8_t* d1, int n1, const uint8_t
     const int n = m.SearchByBoW(kf1, kf2, out);
     for (int i = 0; i < n1; ++i) matches12[i] = out[i] ? index2[out[i]] : -1;
     return n;
+}
+
+// ORBmatcher::Fuse, both overloads (src/ORBmatcher.cc:826-976 with th, :978-1101 with Scw = identity).  Map points sit at
+// (u, v, 1) in front of an identity camera; occupants of key-frame slots are separate map points.  Replace is a logging
+// no-op here, so the map state only evolves through AddObservation / AddMapPoint -- the restated oracle models the same.
+// act: 0 nothing, 1 pMP->Replace(pMPinKF), 2 pMPinKF->Replace(pMP), 3 added to the empty slot, 5 vpReplacePoint (overload 2).
+int refm_fuse(const FrameView* kfv, const float* uright, const float* scale_factors, const float* inv_sigma2, const float* proj,
+              const int32_t* level, const uint8_t* mp_desc, const int32_t* mp_nobs, const uint8_t* mp_bad, const uint8_t* mp_in_kf, int n,
+              const int32_t* occ, const int32_t* occ_nobs, const uint8_t* occ_bad, int n_occ, float th, int overload, int32_t* act,
+              int32_t* slot) {
+    if (!check_grid(*kfv, FRAME_GRID_COLS, FRAME_GRID_ROWS)) return -1;
+    set_front_statics(*kfv);
+    Pool pool;
+    Frame K;
+    fill_front(K, *kfv, scale_factors);
+    K.mvInvLevelSigma2.assign(inv_sigma2, inv_sigma2 + kLevels);
+    for (int k = 0; k < kfv->n; ++k) K.mvuRight[k] = uright ? uright[k] : -1.f;
+    std::vector<uint8_t> zero(32, 0);
+    std::vector<MapPoint*> occmp(n_occ);
+    for (int j = 0; j < n_occ; ++j) { occmp[j] = make_mp(0, 0, zero.data(), 0, occ_nobs[j]); occmp[j]->mbBad = occ_bad[j] != 0; pool.mps.push_back(occmp[j]); }
+    for (int k = 0; k < kfv->n; ++k) K.mvpMapPoints[k] = occ[k] >= 0 ? occmp[occ[k]] : static_cast<MapPoint*>(NULL);
+    KeyFrame* kf = new KeyFrame(K, NULL, NULL);
+    pool.kfs.push_back(kf);
+    std::vector<MapPoint*> pts(n, static_cast<MapPoint*>(NULL));
+    std::map<MapPoint*, int> index;
+    for (int i = 0; i < n; ++i) {
+        act[i] = 0; slot[i] = -1;
+        if (std::isnan(proj[2 * i])) continue;          // overload 1 tolerates NULL entries; overload 2 gets a compacted list
+        MapPoint* p = make_mp(proj[2 * i], proj[2 * i + 1], mp_desc + (size_t)i * 32, level[i], mp_nobs[i]);
+        p->mbBad = mp_bad[i] != 0;
+        if (mp_in_kf[i]) p->mObservations[kf] = 0;
+        pool.mps.push_back(p); pts[i] = p; index[p] = i;
+    }
+    g_replace_log.clear();
+    ORBmatcher m(0.6f, true);
+    int nFused;
+    std::vector<MapPoint*> list, repl;
+    std::vector<int> list_i;
+    if (overload == 1) {
+        nFused = m.Fuse(kf, pts, th);
+    } else {
+        for (int i = 0; i < n; ++i) if (pts[i]) { list.push_back(pts[i]); list_i.push_back(i); }
+        repl.assign(list.size(), static_cast<MapPoint*>(NULL));
+        nFused = m.Fuse(kf, cv::Mat::eye(4, 4, CV_32F), list, th, repl);
+    }
+    std::map<MapPoint*, int> slot_of;
+    for (int k = 0; k < kfv->n; ++k) if (kf->mvpMapPoints[k]) slot_of[kf->mvpMapPoints[k]] = k;
+    for (int k = 0; k < kfv->n; ++k) {
+        MapPoint* p = kf->mvpMapPoints[k];
+        if (p && index.count(p)) { act[index[p]] = 3; slot[index[p]] = k; }
+    }
+    for (size_t e = 0; e < g_replace_log.size(); ++e) {
+        MapPoint *a = g_replace_log[e].first, *b = g_replace_log[e].second;
+        const bool a_occ = slot_of.count(a) != 0 && !(index.count(a) && act[index[a]] != 3);
+        // exactly one of the two sits in a key-frame slot: the occupant; the other is the point being fused
+        if (slot_of.count(b) && index.count(a) && !(slot_of.count(a))) { act[index[a]] = 1; slot[index[a]] = slot_of[b]; }
+        else if (slot_of.count(a) && index.count(b)) { act[index[b]] = 2; slot[index[b]] = slot_of[a]; }
+        (void)a_occ;
+    }
+    for (size_t e = 0; e < repl.size(); ++e)
+        if (repl[e]) { act[list_i[e]] = 5; slot[list_i[e]] = slot_of[repl[e]]; }
+    return nFused;
 }
 
 // ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:658-824).  The camera is the identity and GetCameraCenter() of

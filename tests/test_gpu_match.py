@@ -221,6 +221,23 @@ def test_search_for_triangulation(oracle):
             assert n_g > (5 if only_stereo else 40)
 
 
+def test_fuse_search(oracle):
+    """The candidate search of both Fuse overloads (with / without the reprojection gate, mono + stereo key-frame features)."""
+    from fishbirdeyevisualslam_b200.matcher import ORBmatcher
+    from test_oracle_vs_refmatch import fuse_args
+    rng = np.random.default_rng(41)
+    _, KF = frame_pair(rng, 1500)
+    kf, uright, inv, proj, level, desc = fuse_args(KF, 5, n=4000)[:6]
+    sf = KF.scale_factors
+    pur = (proj[:, 0] - np.float32(0.5)).astype(np.float32)
+    for th, chi2, ur in [(3.0, True, uright), (3.0, True, None), (4.0, False, None), (0.5, True, uright)]:
+        radius = (np.float32(th) * sf[level]).astype(np.float32)
+        bi_g, bd_g = ORBmatcher(0.6, True).FuseSearch(kf, ur, inv, proj, pur, level, radius, desc, chi2)
+        bi_o, bd_o = oracle.fuse_search(kf, ur, inv, proj, pur, level, radius, desc, chi2)
+        assert np.array_equal(bi_g, bi_o) and np.array_equal(bd_g, bd_o)
+        assert (bi_o >= 0).sum() > (100 if th < 1 else 1500)
+
+
 def test_distinctive_descriptors(oracle):
     from fishbirdeyevisualslam_b200.matcher import ORBmatcher
     from test_oracle_vs_refmatch import distinct_lists

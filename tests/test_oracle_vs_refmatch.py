@@ -102,6 +102,11 @@ def scene_outputs(impl, seed, is_ref):
     for j, (ratio, ori, only_stereo) in enumerate([(0.6, True, False), (0.6, False, False), (0.6, True, True)]):
         n, c = impl.search_for_triangulation(*triangulation_args(F1, F2, has_mp, has_mp2, node1, node2, seed), only_stereo, ratio, ori)
         out[f"tri{j}"] = np.concatenate([[n], c]).astype(np.int32)
+    # Fuse, both overloads: map points projected near key-frame features, slots partly occupied, mixed Observations()
+    fa = fuse_args(F2, seed)
+    for j, (th, overload) in enumerate([(3.0, 1), (2.5, 1), (4.0, 2)]):
+        nf, act, slot = impl.fuse(*fa, th, overload)
+        out[f"fuse{j}"] = np.concatenate([[nf], act, slot]).astype(np.int32)
     # MapPoint::ComputeDistinctiveDescriptors on clusters of observed descriptors (sizes 0 .. 40, duplicates = median ties)
     dd, st = distinct_lists(rng)
     best, _ = impl.distinctive_descriptors(dd, st)
@@ -124,6 +129,25 @@ def triangulation_args(F1, F2, has_mp1, has_mp2, node1, node2, seed):
     return (F1.kps, F1.desc, (np.asarray(has_mp1) * (r.random(F1.N) < 0.4)).astype(np.uint8), stereo1, featvec(node1), F2.kps, F2.desc,
             (np.asarray(has_mp2) * (r.random(F2.N) < 0.3)).astype(np.uint8), stereo2, featvec(node2), F12, (320.5, 240.25), sf,
             (sf * sf).astype(np.float32))
+
+
+def fuse_args(KF, seed, n=500):
+    """(kf, uright, inv_sigma2, proj, level, mp_desc, mp_nobs, mp_bad, mp_in_kf, occ, occ_nobs, occ_bad) for both implementations."""
+    r = np.random.default_rng(6000 + seed)
+    src = r.integers(0, KF.N, n)
+    proj = np.stack([KF.kps["x"][src], KF.kps["y"][src]], 1).astype(np.float32) + r.normal(0, 1.6, (n, 2)).astype(np.float32)
+    proj[(proj[:, 0] < 0) | (proj[:, 0] >= 640) | (proj[:, 1] < 0) | (proj[:, 1] >= 480), 0] = np.nan
+    proj[r.random(n) < 0.05, 0] = np.nan
+    level = np.clip(KF.kps["octave"][src] + r.integers(0, 2, n), 0, 7).astype(np.int32)
+    desc = flip_bits(r, KF.desc[src], 70)
+    sf = KF.scale_factors
+    uright = np.where(r.random(KF.N) < 0.3, KF.kps["x"] - r.uniform(0, 3, KF.N), -1).astype(np.float32)
+    occ = np.where(r.random(KF.N) < 0.5, np.arange(KF.N), -1).astype(np.int32)
+    occ_ids = np.nonzero(occ >= 0)[0]
+    occ[occ_ids] = np.arange(len(occ_ids))
+    return (KF, uright, (1.0 / (sf * sf)).astype(np.float32), proj, level, desc, r.integers(0, 6, n).astype(np.int32),
+            (r.random(n) < 0.08).astype(np.uint8), (r.random(n) < 0.08).astype(np.uint8), occ,
+            r.integers(0, 6, len(occ_ids)).astype(np.int32), (r.random(len(occ_ids)) < 0.1).astype(np.uint8))
 
 
 def distinct_lists(rng, sizes=(0, 1, 2, 3, 4, 5, 8, 13, 21, 40, 7, 7, 2, 1, 0, 33)):
