@@ -1,7 +1,7 @@
 // Drop-in bodies for the ORBmatcher methods on the hot path.  This file is compiled INSIDE the reference tree in place
 // of the same-named method bodies of src/ORBmatcher.cc (see INTEGRATION.md for the exact patch); the class declaration
 // include/ORBmatcher.h is unchanged, so Tracking.cc / LocalMapping.cc / LoopClosing.cc call it as before.  Methods that
-// are not on the hot path (SearchBySim3) keep the reference's own CPU code.
+// are not searches (ComputeThreeMaxima, RadiusByViewingCos, CheckDistEpipolarLine) keep the reference's own CPU code.
 //
 // In the build image of this repository it is compiled against the reference's own headers with OpenCV replaced by the
 // test shim oracle/cvshim_m (oracle/Makefile target `dropinmatch`) and checked on the GPU against the outputs of the
@@ -495,6 +495,80 @@ int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& v
         }
     }
     return nFused;
+}
+
+namespace {
+// one direction of SearchBySim3 (:1152-1222 / :1225-1295): points of `src` projected into `dst` with dst_from_src(p3Dc_src)
+void sim3_direction(ORBmatcher* self, fbe_matcher* m, KeyFrame* src, KeyFrame* dst, const std::vector<MapPoint*>& pts,
+                    const std::vector<bool>& already, const cv::Mat& Rsw, const cv::Mat& tsw, const cv::Mat& sRds, const cv::Mat& tds,
+                    float th, std::vector<int>& match) {
+    (void)self; (void)src;
+    const float &fx = dst->fx, &fy = dst->fy, &cx = dst->cx, &cy = dst->cy;     // same camera for both key frames
+    const int N = (int)pts.size();
+    std::vector<float> proj(2 * (size_t)std::max(N, 1), std::numeric_limits<float>::quiet_NaN()), radius(std::max(N, 1), 0.f);
+    std::vector<int> level(std::max(N, 1), 0);
+    std::vector<unsigned char> mpdesc(32 * (size_t)std::max(N, 1), 0);
+    for (int i = 0; i < N; i++) {
+        MapPoint* pMP = pts[i];
+        if (!pMP || already[i]) continue;
+        if (pMP->isBad()) continue;
+        cv::Mat p3Dw = pMP->GetWorldPos();
+        cv::Mat p3Dcs = Rsw * p3Dw + tsw;
+        cv::Mat p3Dcd = sRds * p3Dcs + tds;
+        if (p3Dcd.at<float>(2) < 0.0) continue;
+        const float invz = 1.0 / p3Dcd.at<float>(2);
+        const float x = p3Dcd.at<float>(0) * invz, y = p3Dcd.at<float>(1) * invz;
+        const float u = fx * x + cx, v = fy * y + cy;
+        if (!dst->IsInImage(u, v)) continue;
+        const float maxDistance = pMP->GetMaxDistanceInvariance(), minDistance = pMP->GetMinDistanceInvariance();
+        const float dist3D = cv::norm(p3Dcd);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const int nPredictedLevel = pMP->PredictScale(dist3D, dst);
+        level[i] = nPredictedLevel;
+        radius[i] = th * dst->mvScaleFactors[nPredictedLevel];
+        proj[2 * i] = u; proj[2 * i + 1] = v;
+        copy_desc(pMP->GetDescriptor(), &mpdesc[32 * (size_t)i]);
+    }
+    std::vector<int> best_idx(std::max(N, 1), -1), best_dist(std::max(N, 1), INT_MAX);
+    fbe_frame_view kv = keyframe_view(dst);
+    fbe_fuse_search(m, &kv, NULL, NULL, 0, proj.data(), NULL, level.data(), radius.data(), mpdesc.data(), N, 0, best_idx.data(),
+                    best_dist.data());
+    match.assign(N, -1);
+    for (int i = 0; i < N; i++)
+        if (best_dist[i] <= ORBmatcher::TH_HIGH) match[i] = best_idx[i];
+}
+}  // namespace
+
+// src/ORBmatcher.cc:1103-1327 (loop closing): the two directional searches use the Fuse candidate search (same level band,
+// no reprojection gate, strict best distance); the agreement check stays on the host.
+int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12,
+                             const cv::Mat& t12, const float th) {
+    cv::Mat R1w = pKF1->GetRotation(), t1w = pKF1->GetTranslation();
+    cv::Mat R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
+    cv::Mat sR12 = s12 * R12;
+    cv::Mat sR21 = (1.0 / s12) * R12.t();
+    cv::Mat t21 = -sR21 * t12;
+    const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+    const int N1 = (int)vpMapPoints1.size(), N2 = (int)vpMapPoints2.size();
+    std::vector<bool> vbAlreadyMatched1(N1, false), vbAlreadyMatched2(N2, false);
+    for (int i = 0; i < N1; i++) {
+        MapPoint* pMP = vpMatches12[i];
+        if (pMP) {
+            vbAlreadyMatched1[i] = true;
+            int idx2 = pMP->GetIndexInKeyFrame(pKF2);
+            if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[idx2] = true;
+        }
+    }
+    fbe_matcher* m = matcher_for(mfNNratio, mbCheckOrientation);
+    std::vector<int> vnMatch1, vnMatch2;
+    sim3_direction(this, m, pKF1, pKF2, vpMapPoints1, vbAlreadyMatched1, R1w, t1w, sR21, t21, th, vnMatch1);
+    sim3_direction(this, m, pKF2, pKF1, vpMapPoints2, vbAlreadyMatched2, R2w, t2w, sR12, t12, th, vnMatch2);
+    int nFound = 0;
+    for (int i1 = 0; i1 < N1; i1++) {
+        const int idx2 = vnMatch1[i1];
+        if (idx2 >= 0 && vnMatch2[idx2] == i1) { vpMatches12[i1] = vpMapPoints2[idx2]; nFound++; }
+    }
+    return nFound;
 }
 
 // src/ORBmatcher.cc:1602-1760, isProject == 0 (every call site of the reference passes 0)

@@ -313,6 +313,23 @@ class ORBmatcher:
                                       ptr(bi), ptr(bd)))
         return bi[:n], bd[:n]
 
+    def SearchBySim3(self, KF1: Frame, KF2: Frame, proj12, level12, desc1, proj21, level21, desc2, pre12, th: float):
+        """SearchBySim3 (ORBmatcher.cc:1103-1327) after the host-side projections: proj12 / level12 = key-frame-1 map points in
+        key frame 2 (NaN u = skipped), proj21 / level21 the other direction; pre12 = vpMatches12 on entry as key-frame-2
+        indices (-1 = NULL).  Two device searches (the Fuse candidate search without the reprojection gate, bound TH_HIGH)
+        and the agreement check, exactly what host/ORBmatcher_fbe.cc does.  -> (nFound, matches12[n1])."""
+        sf = np.ascontiguousarray(KF1.scale_factors, np.float32)
+        level12 = np.ascontiguousarray(level12, np.int32); level21 = np.ascontiguousarray(level21, np.int32)
+        bi1, bd1 = self.FuseSearch(KF2, None, sf, proj12, None, level12, (np.float32(th) * sf[level12]).astype(np.float32), desc1, False)
+        bi2, bd2 = self.FuseSearch(KF1, None, sf, proj21, None, level21, (np.float32(th) * sf[level21]).astype(np.float32), desc2, False)
+        m1 = np.where(bd1 <= 100, bi1, -1)
+        m2 = np.where(bd2 <= 100, bi2, -1)
+        out = np.ascontiguousarray(pre12, np.int32).copy()
+        i1 = np.nonzero(m1 >= 0)[0]
+        ok = i1[m2[m1[i1]] == i1]
+        out[ok] = m1[ok]
+        return len(ok), out
+
     def ComputeDistinctiveDescriptors(self, desc, start):
         """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:242-307) for many map points: `desc` rows start[p]..start[p+1]-1
         are the descriptors observed for point p.  -> (best index inside each list or -1, that row's median distance)."""

@@ -641,6 +641,37 @@ int orc_fuse(const FrameView* kf, const float* uright, const float* inv_sigma2, 
     return nFused;
 }
 
+// ORBmatcher::SearchBySim3  src/ORBmatcher.cc:1103-1327 after the projections: proj12 / level12 = key-frame-1 map points in
+// key frame 2 (NaN u = no point, already matched, bad, or rejected by depth / image / distance tests), proj21 / level21 the
+// other direction; radius = th * mvScaleFactors[level]; pre12 = vpMatches12 on entry as key-frame-2 indices (kept).
+int orc_search_by_sim3(const FrameView* kf1, const FrameView* kf2, const float* scale_factors, const float* proj12, const int32_t* level12,
+                       const uint8_t* desc1, const float* proj21, const int32_t* level21, const uint8_t* desc2, const int32_t* pre12,
+                       float th, int32_t* matches12) {
+    Grid g1 = build_grid(*kf1), g2 = build_grid(*kf2);
+    std::vector<int> vnMatch1(kf1->n, -1), vnMatch2(kf2->n, -1);
+    for (int i1 = 0; i1 < kf1->n; ++i1) {
+        if (std::isnan(proj12[2 * i1])) continue;
+        int bestIdx, bestDist;
+        fuse_search_one(kf2, g2, nullptr, nullptr, proj12[2 * i1], proj12[2 * i1 + 1], 0.f, level12[i1], th * scale_factors[level12[i1]],
+                        desc1 + (size_t)i1 * 32, 0, bestIdx, bestDist);
+        if (bestDist <= TH_HIGH) vnMatch1[i1] = bestIdx;
+    }
+    for (int i2 = 0; i2 < kf2->n; ++i2) {
+        if (std::isnan(proj21[2 * i2])) continue;
+        int bestIdx, bestDist;
+        fuse_search_one(kf1, g1, nullptr, nullptr, proj21[2 * i2], proj21[2 * i2 + 1], 0.f, level21[i2], th * scale_factors[level21[i2]],
+                        desc2 + (size_t)i2 * 32, 0, bestIdx, bestDist);
+        if (bestDist <= TH_HIGH) vnMatch2[i2] = bestIdx;
+    }
+    int nFound = 0;
+    for (int i1 = 0; i1 < kf1->n; ++i1) {
+        matches12[i1] = pre12[i1];
+        const int idx2 = vnMatch1[i1];
+        if (idx2 >= 0 && vnMatch2[idx2] == i1) { matches12[i1] = idx2; nFound++; }
+    }
+    return nFound;
+}
+
 // ORBmatcher::SearchForTriangulation  src/ORBmatcher.cc:658-824 with CheckDistEpipolarLine :141-158.  skipN = feature has a
 // map point or fails the bOnlyStereo filter; stereoN = mvuRight >= 0; (ex, ey) = epipole in key frame 2 (:666-672, computed
 // by the caller).  vbMatched2 exists in the reference but is never set, which is reproduced by not having it.

@@ -371,6 +371,36 @@ def fuse(kf, uright, inv_sigma2, proj, level, mp_desc, mp_nobs, mp_bad, mp_in_kf
     return nf, act[:n], slot[:n]
 
 
+def search_by_sim3(F1, F2, pos1, lvl1, desc1, pos2, lvl2, desc2, pre12, t12, th, _L=None):
+    """SearchBySim3 with identity poses, s12 = 1, R12 = I, t12 = (tx, ty, 0): pos1 / pos2 are the image positions (u, v) of the
+    map points hanging on the features of key frame 1 / 2 (NaN = none), lvl their scale level.  -> (nFound, matches12[n1])."""
+    pos1 = np.ascontiguousarray(pos1, np.float32); pos2 = np.ascontiguousarray(pos2, np.float32)
+    lvl1 = np.ascontiguousarray(lvl1, np.int32); lvl2 = np.ascontiguousarray(lvl2, np.int32)
+    desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+    pre12 = np.ascontiguousarray(pre12, np.int32)
+    sf = np.ascontiguousarray(F1.scale_factors, np.float32)
+    m12 = np.full(max(F1.N, 1), -1, np.int32)
+    v1, v2 = _view(F1), _view(F2)
+    tx, ty = np.float32(t12[0]), np.float32(t12[1])
+    if _L is not None:
+        n = _L.refm_search_by_sim3(C.byref(v1), C.byref(v2), _p(sf), _p(pos1), _p(lvl1), _p(desc1), _p(pos2), _p(lvl2), _p(desc2), _p(pre12),
+                                   _fp(tx), _fp(ty), _fp(th), _p(m12))
+        return n, m12[:F1.N]
+    # the projections of :1160-1176 / :1233-1249 for this camera set-up: key frame 2 sees p - t12, key frame 1 sees p + t12
+    pre = np.where((pre12 >= 0) & ~np.isnan(pos2[np.maximum(pre12, 0), 0]), pre12, -1).astype(np.int32)
+    p12 = (pos1 - np.array([tx, ty], np.float32)).astype(np.float32)
+    p21 = (pos2 + np.array([tx, ty], np.float32)).astype(np.float32)
+    w, h = np.float32(F1.gcols / F1.inv_w), np.float32(F1.grows / F1.inv_h)
+    for p in (p12, p21):
+        out = ~((p[:, 0] >= F1.min_x) & (p[:, 0] < F1.min_x + w) & (p[:, 1] >= F1.min_y) & (p[:, 1] < F1.min_y + h))
+        p[out, 0] = np.nan
+    p12[pre >= 0, 0] = np.nan
+    p21[pre[pre >= 0], 0] = np.nan
+    n = lib().orc_search_by_sim3(C.byref(v1), C.byref(v2), _p(sf), _p(p12), _p(lvl1), _p(desc1), _p(p21), _p(lvl2), _p(desc2), _p(pre), _fp(th),
+                                 _p(m12))
+    return n, m12[:F1.N]
+
+
 def distinctive_descriptors(desc, start, _L=None):
     """MapPoint::ComputeDistinctiveDescriptors for CSR lists of observed descriptors -> (best index per point, its median)."""
     desc = np.ascontiguousarray(desc, np.uint8); start = np.ascontiguousarray(start, np.int32)
@@ -528,6 +558,9 @@ class RefMatch:
 
     def fuse(self, *a):
         return fuse(*a, _L=self.L)
+
+    def search_by_sim3(self, *a):
+        return search_by_sim3(*a, _L=self.L)
 
     def hamming256(self, a, b):
         return self.L.refm_hamming256(_p(np.ascontiguousarray(a, np.uint8)), _p(np.ascontiguousarray(b, np.uint8)))

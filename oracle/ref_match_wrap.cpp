@@ -508,6 +508,37 @@ int refm_fuse(const FrameView* kfv, const float* uright, const float* scale_fact
     return nFused;
 }
 
+// ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1103-1327).  Both key frames sit at the world origin (identity poses), the
+// relative transform is s12 = 1, R12 = I, t12 = (tx, ty, 0): a key-frame-1 point at (u, v, 1) projects to (u - tx, v - ty)
+// in key frame 2 and vice versa.  pre12[i1] >= 0 pre-fills vpMatches12 (already matched, :1131-1141).
+int refm_search_by_sim3(const FrameView* v1, const FrameView* v2, const float* scale_factors, const float* pos1, const int32_t* lvl1,
+                        const uint8_t* desc1, const float* pos2, const int32_t* lvl2, const uint8_t* desc2, const int32_t* pre12, float tx,
+                        float ty, float th, int32_t* matches12) {
+    set_front_statics(*v1);
+    Pool pool;
+    Frame F1, F2;
+    fill_front(F1, *v1, scale_factors); fill_front(F2, *v2, scale_factors);
+    std::map<MapPoint*, int> index2;
+    for (int i = 0; i < v1->n; ++i)
+        if (!std::isnan(pos1[2 * i])) { MapPoint* p = make_mp(pos1[2 * i], pos1[2 * i + 1], desc1 + (size_t)i * 32, lvl1[i], 1); pool.mps.push_back(p); F1.mvpMapPoints[i] = p; }
+    for (int i = 0; i < v2->n; ++i)
+        if (!std::isnan(pos2[2 * i])) { MapPoint* p = make_mp(pos2[2 * i], pos2[2 * i + 1], desc2 + (size_t)i * 32, lvl2[i], 1); pool.mps.push_back(p); F2.mvpMapPoints[i] = p; index2[p] = i; }
+    KeyFrame* kf1 = new KeyFrame(F1, NULL, NULL);
+    KeyFrame* kf2 = new KeyFrame(F2, NULL, NULL);
+    pool.kfs.push_back(kf1); pool.kfs.push_back(kf2);
+    kf1->SetPose(cv::Mat::eye(4, 4, CV_32F)); kf2->SetPose(cv::Mat::eye(4, 4, CV_32F));
+    std::vector<MapPoint*> m12(v1->n, static_cast<MapPoint*>(NULL));
+    for (int i = 0; i < v1->n; ++i)
+        if (pre12[i] >= 0 && kf2->mvpMapPoints[pre12[i]]) { m12[i] = kf2->mvpMapPoints[pre12[i]]; m12[i]->mObservations[kf2] = (size_t)pre12[i]; }
+    cv::Mat R12 = cv::Mat::eye(3, 3, CV_32F), t12(3, 1, CV_32F);
+    t12.at<float>(0) = tx; t12.at<float>(1) = ty; t12.at<float>(2) = 0.f;
+    ORBmatcher m(0.75f, true);
+    const float s12 = 1.0f;
+    const int n = m.SearchBySim3(kf1, kf2, m12, s12, R12, t12, th);
+    for (int i = 0; i < v1->n; ++i) matches12[i] = m12[i] ? index2[m12[i]] : -1;
+    return n;
+}
+
 // ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:658-824).  The camera is the identity and GetCameraCenter() of
 // key frame 1 is the origin, so the epipole of :666-672 is t2w.xy / t2w.z: key frame 2 gets t2w = (ex, ey, 1).
 int refm_search_for_triangulation(const Kp* k1, const uint8_t* d1, int n1, const uint8_t* has_mp1, const uint8_t* stereo1,

@@ -238,6 +238,23 @@ def test_fuse_search(oracle):
         assert (bi_o >= 0).sum() > (100 if th < 1 else 1500)
 
 
+def test_search_by_sim3(oracle):
+    from fishbirdeyevisualslam_b200.matcher import ORBmatcher
+    from test_oracle_vs_refmatch import sim3_args
+    rng = np.random.default_rng(51)
+    F1, F2 = frame_pair(rng, 1500)
+    _, _, pos1, lvl1, d1, pos2, lvl2, d2, pre = sim3_args(F1, F2, 9)
+    pre[:] = -1
+    t = np.float32([-3.0, -2.0])
+    p12 = (pos1 - t).astype(np.float32); p21 = (pos2 + t).astype(np.float32)
+    for p in (p12, p21):
+        p[~((p[:, 0] >= 0) & (p[:, 0] < 640) & (p[:, 1] >= 0) & (p[:, 1] < 480)), 0] = np.nan
+    for th in (7.5, 3.0):
+        n_g, m_g = ORBmatcher(0.75, True).SearchBySim3(F1, F2, p12, lvl1, d1, p21, lvl2, d2, pre, th)
+        n_o, m_o = oracle.search_by_sim3(F1, F2, pos1, lvl1, d1, pos2, lvl2, d2, pre, t, th)
+        assert n_g == n_o and np.array_equal(m_g, m_o) and n_g > 300
+
+
 def test_distinctive_descriptors(oracle):
     from fishbirdeyevisualslam_b200.matcher import ORBmatcher
     from test_oracle_vs_refmatch import distinct_lists

@@ -107,6 +107,11 @@ def scene_outputs(impl, seed, is_ref):
     for j, (th, overload) in enumerate([(3.0, 1), (2.5, 1), (4.0, 2)]):
         nf, act, slot = impl.fuse(*fa, th, overload)
         out[f"fuse{j}"] = np.concatenate([[nf], act, slot]).astype(np.int32)
+    # SearchBySim3: both key frames at the origin, t12 = -(3, 2, 0) (F2 is F1 shifted by (3, 2))
+    sa = sim3_args(F1, F2, seed)
+    for j, th in enumerate([7.5, 3.0]):
+        n, c = impl.search_by_sim3(*sa, (-3.0, -2.0), th)
+        out[f"sim3_{j}"] = np.concatenate([[n], c]).astype(np.int32)
     # MapPoint::ComputeDistinctiveDescriptors on clusters of observed descriptors (sizes 0 .. 40, duplicates = median ties)
     dd, st = distinct_lists(rng)
     best, _ = impl.distinctive_descriptors(dd, st)
@@ -129,6 +134,23 @@ def triangulation_args(F1, F2, has_mp1, has_mp2, node1, node2, seed):
     return (F1.kps, F1.desc, (np.asarray(has_mp1) * (r.random(F1.N) < 0.4)).astype(np.uint8), stereo1, featvec(node1), F2.kps, F2.desc,
             (np.asarray(has_mp2) * (r.random(F2.N) < 0.3)).astype(np.uint8), stereo2, featvec(node2), F12, (320.5, 240.25), sf,
             (sf * sf).astype(np.float32))
+
+
+def sim3_args(F1, F2, seed):
+    """(F1, F2, pos1, lvl1, desc1, pos2, lvl2, desc2, pre12): a map point on ~80 % of the features of either key frame."""
+    r = np.random.default_rng(8000 + seed)
+    def side(F):
+        pos = np.stack([F.kps["x"], F.kps["y"]], 1).astype(np.float32) + r.normal(0, 0.8, (F.N, 2)).astype(np.float32)
+        pos[r.random(F.N) < 0.2, 0] = np.nan
+        # the verbatim harness puts the point at (u, v, 1): close to the optical axis a 3 px shift changes its distance by
+        # several percent and with it PredictScale; keep the points whose predicted level is the given one in both frames
+        pos[np.hypot(pos[:, 0], pos[:, 1]) < 120, 0] = np.nan
+        lvl = np.clip(F.kps["octave"] + r.integers(0, 2, F.N), 0, 7).astype(np.int32)
+        return pos, lvl, flip_bits(r, F.desc, 40)
+    pos1, lvl1, d1 = side(F1)
+    pos2, lvl2, d2 = side(F2)
+    pre12 = np.where(r.random(F1.N) < 0.1, r.integers(0, F2.N, F1.N), -1).astype(np.int32)
+    return F1, F2, pos1, lvl1, d1, pos2, lvl2, d2, pre12
 
 
 def fuse_args(KF, seed, n=500):
