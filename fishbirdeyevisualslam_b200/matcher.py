@@ -86,6 +86,31 @@ def isInFrustum(view, pos, normal, min_dist, max_dist, viewing_cos_limit: float,
     return o
 
 
+def _check_models(kps1, kps2, matches, A, B, sigma, device):
+    L = _lib.load()
+    k1 = np.ascontiguousarray(kps1, KP_DTYPE); k2 = np.ascontiguousarray(kps2, KP_DTYPE)
+    m = np.ascontiguousarray(matches, np.int32).reshape(-1, 2)
+    A = np.ascontiguousarray(A, np.float32).reshape(-1, 9)
+    K, n = len(A), len(m)
+    scores = np.zeros(max(K, 1), np.float32); inl = np.zeros(max(K * n, 1), np.uint8)
+    if B is not None:
+        Bm = np.ascontiguousarray(B, np.float32).reshape(-1, 9)
+        check(L.fbe_check_homography(ptr(k1), ptr(k2), ptr(m), n, ptr(A), ptr(Bm), K, C.c_float(float(sigma)), C.c_int32(device), ptr(scores), ptr(inl)))
+    else:
+        check(L.fbe_check_fundamental(ptr(k1), ptr(k2), ptr(m), n, ptr(A), K, C.c_float(float(sigma)), C.c_int32(device), ptr(scores), ptr(inl)))
+    return scores[:K], inl[:K * n].reshape(K, n)
+
+
+def CheckHomography(kps1, kps2, matches, H21, H12, sigma: float = 1.0, device: int = 0):
+    """Initializer::CheckHomography (Initializer.cc:391-474) for K hypotheses (H21, H12: K x 3 x 3) -> (scores[K], inliers[K, n])."""
+    return _check_models(kps1, kps2, matches, H21, H12, sigma, device)
+
+
+def CheckFundamental(kps1, kps2, matches, F21, sigma: float = 1.0, device: int = 0):
+    """Initializer::CheckFundamental (Initializer.cc:476-554) for K hypotheses (F21: K x 3 x 3) -> (scores[K], inliers[K, n])."""
+    return _check_models(kps1, kps2, matches, F21, None, sigma, device)
+
+
 def ComputeImageBounds(cols: int, rows: int, K, D, device: int = 0):
     """Frame::ComputeImageBounds (Frame.cc:741-795) -> (mnMinX, mnMaxX, mnMinY, mnMaxY)."""
     L = _lib.load()

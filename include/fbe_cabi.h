@@ -138,6 +138,20 @@ FBE_API int fbe_is_in_frustum(const fbe_frustum_view* v, const float* pos, const
                               const float* max_dist, int32_t n, float viewing_cos_limit, int32_t device, uint8_t* in_view,
                               float* proj, float* proj_xr, int32_t* level, float* view_cos);
 
+/* ---- Initializer RANSAC scoring (next row f-2) --------------------------------------------------- */
+/* Initializer::CheckHomography (src/Initializer.cc:391-474) for K hypotheses at once: the consumer of vnMatches12 in
+ * Initializer::FindHomography (:211-260), which scores one H per RANSAC iteration over all matches.  The 8-point solves
+ * (cv::SVD) stay on the host; this scores them.  kps1 / kps2: mvKeys1 / mvKeys2; matches: n pairs (first, second) =
+ * mvMatches12; H21 / H12: K row-major 3x3 matrices.  Outputs: scores[K]; inliers[K x n] (may be NULL).
+ * Bit-exact: every float expression is evaluated in the reference's order without FMA contraction (`1.0/(...)` in double
+ * as written), and the score is accumulated sequentially over the matches like the reference's `score +=`. */
+FBE_API int fbe_check_homography(const fbe_keypoint* kps1, const fbe_keypoint* kps2, const int32_t* matches, int32_t n,
+                                 const float* H21, const float* H12, int32_t K, float sigma, int32_t device, float* scores,
+                                 uint8_t* inliers);
+/* Initializer::CheckFundamental (src/Initializer.cc:476-554), same batching; F21: K row-major 3x3 matrices. */
+FBE_API int fbe_check_fundamental(const fbe_keypoint* kps1, const fbe_keypoint* kps2, const int32_t* matches, int32_t n,
+                                  const float* F21, int32_t K, float sigma, int32_t device, float* scores, uint8_t* inliers);
+
 /* ---- Frame undistortion (next row f-1) ----------------------------------------------------------- */
 /* Frame::UndistortKeyPoints, src/Frame.cc:638-669: cv::fisheye::undistortPoints(pts, pts, mK, mDistCoef, Mat(), mK) on the
  * keypoint positions (OpenCV 4.13 semantics: double-precision Newton solve, <= 10 iterations, eps 1e-8; (-1e6,-1e6) when

@@ -760,6 +760,45 @@ void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* start, int 
     }
 }
 
+// Initializer::CheckHomography (src/Initializer.cc:391-474) and CheckFundamental (:476-554) for K hypotheses.  A = H21 or
+// F21, B = H12 (homography), row-major 3x3 each.  Compiled with -ffp-contract=off: every operation rounds on its own.
+void orc_check_models(const Kp* k1, const Kp* k2, const int32_t* matches, int n, const float* A, const float* B, int K, float sigma,
+                      int homography, float* scores, uint8_t* inliers) {
+    const float invSigmaSquare = 1.0 / (sigma * sigma);
+    for (int k = 0; k < K; ++k) {
+        const float* a = A + k * 9;
+        const float* b = homography ? B + k * 9 : nullptr;
+        float score = 0;
+        const float th = homography ? 5.991 : 3.841, thScore = 5.991;
+        for (int i = 0; i < n; ++i) {
+            const float u1 = k1[matches[2 * i]].x, v1 = k1[matches[2 * i]].y, u2 = k2[matches[2 * i + 1]].x, v2 = k2[matches[2 * i + 1]].y;
+            float chiSquare1, chiSquare2;
+            if (homography) {
+                const float w2in1inv = 1.0 / (b[6] * u2 + b[7] * v2 + b[8]);
+                const float u2in1 = (b[0] * u2 + b[1] * v2 + b[2]) * w2in1inv;
+                const float v2in1 = (b[3] * u2 + b[4] * v2 + b[5]) * w2in1inv;
+                chiSquare1 = ((u1 - u2in1) * (u1 - u2in1) + (v1 - v2in1) * (v1 - v2in1)) * invSigmaSquare;
+                const float w1in2inv = 1.0 / (a[6] * u1 + a[7] * v1 + a[8]);
+                const float u1in2 = (a[0] * u1 + a[1] * v1 + a[2]) * w1in2inv;
+                const float v1in2 = (a[3] * u1 + a[4] * v1 + a[5]) * w1in2inv;
+                chiSquare2 = ((u2 - u1in2) * (u2 - u1in2) + (v2 - v1in2) * (v2 - v1in2)) * invSigmaSquare;
+            } else {
+                const float a2 = a[0] * u1 + a[1] * v1 + a[2], b2 = a[3] * u1 + a[4] * v1 + a[5], c2 = a[6] * u1 + a[7] * v1 + a[8];
+                const float num2 = a2 * u2 + b2 * v2 + c2;
+                chiSquare1 = num2 * num2 / (a2 * a2 + b2 * b2) * invSigmaSquare;
+                const float a1 = a[0] * u2 + a[3] * v2 + a[6], b1 = a[1] * u2 + a[4] * v2 + a[7], c1 = a[2] * u2 + a[5] * v2 + a[8];
+                const float num1 = a1 * u1 + b1 * v1 + c1;
+                chiSquare2 = num1 * num1 / (a1 * a1 + b1 * b1) * invSigmaSquare;
+            }
+            bool bIn = true;
+            if (chiSquare1 > th) bIn = false; else score += thScore - chiSquare1;
+            if (chiSquare2 > th) bIn = false; else score += thScore - chiSquare2;
+            inliers[(size_t)k * n + i] = bIn;
+        }
+        scores[k] = score;
+    }
+}
+
 void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* best_idx, int32_t* best_dist,
                          int32_t* second_dist) {
     for (int i = 0; i < nq; ++i) {

@@ -401,6 +401,22 @@ def search_by_sim3(F1, F2, pos1, lvl1, desc1, pos2, lvl2, desc2, pre12, t12, th,
     return n, m12[:F1.N]
 
 
+def check_models(k1, k2, matches, A, B, sigma, homography, _L=None):
+    """Initializer::CheckHomography (A = H21, B = H12) / CheckFundamental (A = F21) for K hypotheses -> (scores[K], inliers[K, n])."""
+    k1 = np.ascontiguousarray(k1); k2 = np.ascontiguousarray(k2); matches = np.ascontiguousarray(matches, np.int32).reshape(-1, 2)
+    A = np.ascontiguousarray(A, np.float32).reshape(-1, 9); K, n = len(A), len(matches)
+    Bp = None if B is None else np.ascontiguousarray(B, np.float32).reshape(-1, 9)
+    scores = np.zeros(max(K, 1), np.float32); inl = np.zeros((max(K, 1), max(n, 1)), np.uint8)
+    inl_flat = np.zeros(max(K * n, 1), np.uint8)
+    if _L is None:
+        lib().orc_check_models(_p(k1), _p(k2), _p(matches), n, _p(A), None if Bp is None else _p(Bp), K, _fp(sigma), int(homography), _p(scores),
+                               _p(inl_flat))
+    else:
+        _L.refm_check_models(_p(k1), len(k1), _p(k2), len(k2), _p(matches), n, _p(A), None if Bp is None else _p(Bp), K, _fp(sigma),
+                             int(homography), _p(scores), _p(inl_flat))
+    return scores[:K], inl_flat[:K * n].reshape(K, n)
+
+
 def distinctive_descriptors(desc, start, _L=None):
     """MapPoint::ComputeDistinctiveDescriptors for CSR lists of observed descriptors -> (best index per point, its median)."""
     desc = np.ascontiguousarray(desc, np.uint8); start = np.ascontiguousarray(start, np.int32)
@@ -561,6 +577,9 @@ class RefMatch:
 
     def search_by_sim3(self, *a):
         return search_by_sim3(*a, _L=self.L)
+
+    def check_models(self, *a):
+        return check_models(*a, _L=self.L)
 
     def hamming256(self, a, b):
         return self.L.refm_hamming256(_p(np.ascontiguousarray(a, np.uint8)), _p(np.ascontiguousarray(b, np.uint8)))

@@ -30,6 +30,7 @@
 #include "MapPoint.h"
 #include "MapPointBird.h"
 #include "ORBmatcher.h"
+#include "Initializer.h"
 #include "Converter.h"
 #undef private
 #undef protected
@@ -73,6 +74,7 @@ void MapPointBird::ComputeDistinctiveDescriptors() {}
 void Map::AddMapPointBird(MapPointBird*) {}
 
 bool KeyFrame::isBad() { return mbBad; }
+Initializer::Initializer(const Frame&, float sigma, int iterations) : mSigma(sigma), mSigma2(sigma * sigma), mMaxIterations(iterations) {}
 void KeyFrame::SetPose(const cv::Mat& Tcw_) { Tcw_.copyTo(Tcw); }
 cv::Mat KeyFrame::GetRotation() { return Tcw.rowRange(0, 3).colRange(0, 3).clone(); }
 cv::Mat KeyFrame::GetTranslation() { return Tcw.rowRange(0, 3).col(3).clone(); }
@@ -606,6 +608,22 @@ void refm_distinctive_descriptors(const uint8_t* desc, const int32_t* start, int
         for (int i = 0; i < N; ++i) kfs[i].~KeyFrame();
         ::operator delete(kfs);
         delete mp;
+    }
+}
+
+// Initializer::CheckHomography / CheckFundamental (src/Initializer.cc:391-554) for K hypotheses, one call each
+void refm_check_models(const Kp* k1, int n1, const Kp* k2, int n2, const int32_t* matches, int n, const float* A, const float* B, int K,
+                       float sigma, int homography, float* scores, uint8_t* inliers) {
+    Frame dummy;
+    Initializer init(dummy, sigma, 200);
+    init.mvKeys1 = to_kps(k1, n1); init.mvKeys2 = to_kps(k2, n2);
+    for (int i = 0; i < n; ++i) init.mvMatches12.push_back(std::make_pair(matches[2 * i], matches[2 * i + 1]));
+    for (int k = 0; k < K; ++k) {
+        cv::Mat M(3, 3, CV_32F), Minv(3, 3, CV_32F);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { M.at<float>(r, c) = A[k * 9 + 3 * r + c]; if (B) Minv.at<float>(r, c) = B[k * 9 + 3 * r + c]; }
+        std::vector<bool> in;
+        scores[k] = homography ? init.CheckHomography(M, Minv, in, sigma) : init.CheckFundamental(M, in, sigma);
+        for (int i = 0; i < n; ++i) inliers[(size_t)k * n + i] = in[i];
     }
 }
 

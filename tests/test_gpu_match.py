@@ -255,6 +255,32 @@ def test_search_by_sim3(oracle):
         assert n_g == n_o and np.array_equal(m_g, m_o) and n_g > 300
 
 
+def test_ransac_scoring(oracle):
+    """Initializer::CheckHomography / CheckFundamental for 200 hypotheses x ~1000 matches: scores bit-identical (sequential
+    float accumulation order reproduced), inlier masks identical; n > one shared-memory chunk is covered by the 5000-match case."""
+    from fishbirdeyevisualslam_b200.matcher import CheckFundamental, CheckHomography
+    from test_oracle_vs_refmatch import model_args
+    rng = np.random.default_rng(61)
+    for npts in (1500, 7000):
+        F1, F2 = frame_pair(rng, npts)
+        prev = np.ascontiguousarray(np.stack([F1.kps["x"], F1.kps["y"]], 1), np.float32)
+        _, m12 = oracle.search_for_initialization(F1, F2, prev, 100, 0.9, False)
+        (k1, k2, matches), models = model_args(F1, F2, m12, 3, K=200)
+        assert len(matches) > (500 if npts == 1500 else 2100)
+        for sigma in (1.0, 0.7):
+            H21, H12, _ = models["H"]
+            s_g, i_g = CheckHomography(k1, k2, matches, H21, H12, sigma)
+            s_o, i_o = oracle.check_models(k1, k2, matches, H21, H12, sigma, True)
+            assert np.array_equal(s_g.view(np.int32), s_o.view(np.int32)) and np.array_equal(i_g, i_o)
+            F21 = models["F"][0]
+            s_g, i_g = CheckFundamental(k1, k2, matches, F21, sigma)
+            s_o, i_o = oracle.check_models(k1, k2, matches, F21, None, sigma, False)
+            assert np.array_equal(s_g.view(np.int32), s_o.view(np.int32)) and np.array_equal(i_g, i_o)
+            assert 0.05 < i_o.mean() < 0.95
+    s, i = CheckHomography(k1, k2, np.zeros((0, 2), np.int32), H21[:3], H12[:3], 1.0)
+    assert s.tolist() == [0.0, 0.0, 0.0]
+
+
 def test_distinctive_descriptors(oracle):
     from fishbirdeyevisualslam_b200.matcher import ORBmatcher
     from test_oracle_vs_refmatch import distinct_lists

@@ -112,6 +112,12 @@ def scene_outputs(impl, seed, is_ref):
     for j, th in enumerate([7.5, 3.0]):
         n, c = impl.search_by_sim3(*sa, (-3.0, -2.0), th)
         out[f"sim3_{j}"] = np.concatenate([[n], c]).astype(np.int32)
+    # Initializer::CheckHomography / CheckFundamental: 40 perturbed hypotheses over the accepted init0 matches
+    ma = model_args(F1, F2, out["init0"][1:], seed)
+    for tag, (A, B, hom) in ma[1].items():
+        sc, inl = impl.check_models(*ma[0], A, B, 1.0, hom)
+        out[f"score_{tag}"] = sc.view(np.int32).copy()                # float bit patterns: bit-exact or nothing
+        out[f"inl_{tag}"] = inl.astype(np.int32).ravel()
     # MapPoint::ComputeDistinctiveDescriptors on clusters of observed descriptors (sizes 0 .. 40, duplicates = median ties)
     dd, st = distinct_lists(rng)
     best, _ = impl.distinctive_descriptors(dd, st)
@@ -134,6 +140,23 @@ def triangulation_args(F1, F2, has_mp1, has_mp2, node1, node2, seed):
     return (F1.kps, F1.desc, (np.asarray(has_mp1) * (r.random(F1.N) < 0.4)).astype(np.uint8), stereo1, featvec(node1), F2.kps, F2.desc,
             (np.asarray(has_mp2) * (r.random(F2.N) < 0.3)).astype(np.uint8), stereo2, featvec(node2), F12, (320.5, 240.25), sf,
             (sf * sf).astype(np.float32))
+
+
+def model_args(F1, F2, m12, seed, K=40):
+    """((kps1, kps2, matches), {"H": (H21, H12, True), "F": (F21, None, False)}): hypotheses around the true shift (3, 2)."""
+    r = np.random.default_rng(9000 + seed)
+    i1 = np.nonzero(m12 >= 0)[0]
+    matches = np.stack([i1, m12[i1]], 1).astype(np.int32)
+    H = np.tile(np.array([[1, 0, 3], [0, 1, 2], [0, 0, 1]], np.float64), (K, 1, 1))
+    H[:, :2, :2] += r.normal(0, 2e-3, (K, 2, 2)); H[:, :2, 2] += r.normal(0, 0.8, (K, 2)); H[:, 2, :2] += r.normal(0, 2e-6, (K, 2))
+    H21 = H.astype(np.float32)
+    H12 = np.linalg.inv(H).astype(np.float32)
+    F = np.tile(np.array([[0, 0, -2], [0, 0, 3], [2, -3, 0]], np.float64) * 0.01, (K, 1, 1)) + r.normal(0, 2e-8, (K, 3, 3))
+    F[:, 2, :2] += r.normal(0, 2e-4, (K, 2)); F[:, :2, 2] += r.normal(0, 2e-4, (K, 2))
+    # F21: l2 = F21 x1; for x2 = x1 + (3, 2) the line through x1 with direction (3, 2) is (2, -3, -2 x1 + 3 y1) = F x1 with
+    # F = [[0, 0, 2], [0, 0, -3], [-2, 3, 0]]: use the transpose convention of the table above
+    F21 = np.transpose(F, (0, 2, 1)).astype(np.float32)
+    return (F1.kps, F2.kps, matches), {"H": (H21, H12, True), "F": (F21, None, False)}
 
 
 def sim3_args(F1, F2, seed):
