@@ -36,8 +36,10 @@ BYTES_PER_PAIR = 5_742_040
 # pixels of all pyramid levels (what the FAST kernel reads once): front 2 853 088, bird 456 460
 PYR_PIXELS_FRONT, PYR_PIXELS_BIRD = 2_853_088, 456_460
 # dram__bytes_read.sum + dram__bytes_write.sum of one front k_fast_cells launch over 128 images (ncu --set full,
-# profiles/r1_02_fast_ncu.md): 384.74 MB + 37.59 MB
+# profiles/r1_02_fast_ncu.md; r1_08 re-capture: 385 MB + 36 MB): 384.74 MB + 37.59 MB
 FAST_DRAM_BYTES_PER_FRONT_IMAGE = int((384.737280e6 + 37.585152e6) / 128)
+# warp-instructions executed by the same launch (sm__inst_executed.sum of the r1_08 capture, profiles/r1_08_fast_ncu.md)
+FAST_WARP_INST_PER_FRONT_IMAGE = 1_165_051_823 / 128
 METRIC = "front+bird frame-pairs/sec ORB extract+match at 1/2/4/8 B200 vs host CPU ref"
 
 
@@ -195,6 +197,33 @@ def run_reference(args):
     return 0
 
 
+def bind_to_gpu_numa(index):
+    """Pin this rank's host threads to the CPU cores of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is
+    allocated (first touch places the pages there), so that with 8 ranks the H2D copies of a rank do not cross the socket
+    interconnect.  Returns the node number or None when the topology is not exposed (then nothing is changed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:                # NVML prints an 8-digit domain, sysfs uses 4
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -207,6 +236,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path (use --impl reference for the CPU arm)")
+    numa_node = bind_to_gpu_numa(local) if world > 1 else None
     torch.cuda.set_device(local)
     # NCCL prints its version banner on stdout; keep stdout for the single JSON line (everything else goes to stderr)
     sys.stdout.flush()
@@ -329,6 +359,7 @@ def run_ours(args):
                            "l2": f"inputs {h2d / 1e6:.0f} MB per step per GPU (> 126 MB L2)" if h2d > 126e6 else "inputs smaller than L2: raise --batch"},
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "h2d_link_gbs_measured": link_gbs, "h2d_gbs_used": e2e_value / world * (h2d / B) / 1e9,
+                        "host_numa_node_rank0": numa_node,
                         "note": "three steps in flight: the input copies of the next steps overlap the kernels of step i; bound = max(copy, compute)"},
                 "gpu_launches": int(launches),
                 "clocks": clk.summary(),
@@ -339,6 +370,11 @@ def run_ours(args):
                              "note": "k_fast_cells is instruction-bound, not memory-bound: ncu (profiles/r1_02_fast_ncu.md) shows 79-81 % issue-slot "
                                      "utilisation, 72 % alu pipe, 3.0 warp-instructions per SM per clock and 4 % of DRAM throughput; ~100 integer "
                                      "instructions per pixel bound it, so frac of the HBM peak stays small by construction",
+                             "issue": {"what": "the roof this kernel actually sits under: warp-instruction issue (148 SMs x 4 schedulers x SM clock)",
+                                       "achieved_gwarp_inst_s": FAST_WARP_INST_PER_FRONT_IMAGE * B / (fast_ms * 1e-3) / 1e9,
+                                       "peak_gwarp_inst_s": 148 * 4 * (clk.summary().get("sm_mhz") or 1965.0) * 1e6 / 1e9,
+                                       "frac": FAST_WARP_INST_PER_FRONT_IMAGE * B / (fast_ms * 1e-3) / (148 * 4 * (clk.summary().get("sm_mhz") or 1965.0) * 1e6),
+                                       "source": "sm__inst_executed.sum of one launch (ncu --set full, profiles/r1_08_fast_ncu.md) / live launch time"},
                              "whole_step": {"bytes_per_pair": BYTES_PER_PAIR, "achieved_gbs": value / world * BYTES_PER_PAIR / 1e9,
                                             "frac": value / world * BYTES_PER_PAIR / 1e9 / peak}},
                 "stage_ms": stage_ms,
