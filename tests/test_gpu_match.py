@@ -360,3 +360,47 @@ def test_bruteforce_top2_c5_size(oracle):
     dist = np.unpackbits(q[idx] ^ t[g[0][idx]], axis=1).sum(1)
     assert np.array_equal(dist, g[1][idx])
     assert (g[2] >= g[1]).all()
+
+
+def test_widened_entry_points_edge_cases(oracle):
+    """Empty and degenerate inputs of the rows added after the core path: they return cleanly with empty / -1 outputs."""
+    import ctypes as C
+    from fishbirdeyevisualslam_b200 import _lib
+    from fishbirdeyevisualslam_b200.matcher import CheckFundamental, ORBmatcher
+    rng = np.random.default_rng(71)
+    F1, F2 = frame_pair(rng, 200)
+    m = ORBmatcher(0.6, True)
+    empty_fv = (np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32))
+    one1, one2 = featvec(np.zeros(F1.N, int)), featvec(np.zeros(F2.N, int))
+    z1, z2 = np.zeros(F1.N, np.uint8), np.zeros(F2.N, np.uint8)
+    sf = F2.scale_factors
+    Fm = np.float32([[0, 0, -2], [0, 0, 3], [2, -3, 0]])
+    # no shared vocabulary node / no eligible feature on either side
+    n, m12 = m.SearchForTriangulation(F1.kps, F1.desc, z1, z1, empty_fv, F2.kps, F2.desc, z2, z2, one2, Fm, (0, 0), sf, sf * sf)
+    assert n == 0 and (m12 == -1).all()
+    n, m12 = m.SearchForTriangulation(F1.kps, F1.desc, z1 + 1, z1, one1, F2.kps, F2.desc, z2, z2, one2, Fm, (0, 0), sf, sf * sf)
+    assert n == 0 and (m12 == -1).all()
+    n, m12 = m.SearchByBoWKF(F1.kps, F1.desc, z1 + 1, one1, F2.kps, F2.desc, z2, one2)          # key frame 2 has no map points
+    assert n == 0 and (m12 == -1).all()
+    # degenerate fundamental matrix (den == 0 for every feature): CheckDistEpipolarLine returns false (:153-154)
+    n, m12 = m.SearchForTriangulation(F1.kps, F1.desc, z1, z1, one1, F2.kps, F2.desc, z2, z2, one2, np.zeros((3, 3), np.float32), (-1e4, -1e4), sf, sf * sf)
+    n_o, m_o = oracle.search_for_triangulation(F1.kps, F1.desc, z1, z1, one1, F2.kps, F2.desc, z2, z2, one2, np.zeros((3, 3), np.float32), (-1e4, -1e4), sf, sf * sf, False, 0.6, True)
+    assert n == n_o == 0 and np.array_equal(m12, m_o)
+    # Fuse search: every projection skipped / radius so small that no feature falls inside
+    nanp = np.full((5, 2), np.nan, np.float32)
+    bi, bd = m.FuseSearch(F2, None, 1 / (sf * sf), nanp, None, np.zeros(5, np.int32), np.ones(5, np.float32), np.zeros((5, 32), np.uint8), True)
+    assert (bi == -1).all() and (bd == np.iinfo(np.int32).max).all()
+    proj = np.stack([F2.kps["x"][:50] + 0.4, F2.kps["y"][:50] + 0.4], 1).astype(np.float32)
+    bi, bd = m.FuseSearch(F2, None, 1 / (sf * sf), proj, None, F2.kps["octave"][:50].astype(np.int32), np.full(50, 1e-3, np.float32), F2.desc[:50], False)
+    bi_o, bd_o = oracle.fuse_search(F2, None, 1 / (sf * sf), proj, None, F2.kps["octave"][:50].astype(np.int32), np.full(50, 1e-3, np.float32), F2.desc[:50], False)
+    assert np.array_equal(bi, bi_o) and np.array_equal(bd, bd_o)
+    # scoring with zero hypotheses; invalid match index is rejected, not read
+    s, i = CheckFundamental(F1.kps, F2.kps, np.zeros((3, 2), np.int32), np.zeros((0, 3, 3), np.float32))
+    assert len(s) == 0
+    L = _lib.load()
+    bad = np.array([[0, -1]], np.int32)
+    sc = np.zeros(1, np.float32)
+    rc = L.fbe_check_fundamental(F1.kps.ctypes.data_as(C.c_void_p), F2.kps.ctypes.data_as(C.c_void_p), bad.ctypes.data_as(C.c_void_p), 1,
+                                 Fm.ctypes.data_as(C.c_void_p), 1, C.c_float(1.0), 0, sc.ctypes.data_as(C.c_void_p), None)
+    assert rc != 0
+
