@@ -16,7 +16,7 @@
 // Phases of a CTA (all in shared memory, 4 block barriers):
 //   0. TMA stages the strip + 3-px halo (box start rounded down to 16 bytes); the score tile and the survivor masks
 //      are cleared while the copy is in flight.
-//   1. PRETEST every pixel with the 4 compass ring pixels (every 9-arc contains k or k+8 for each k, so
+//   1. PRETEST every pixel (8 per thread) with the 4 compass ring pixels (every 9-arc contains k or k+8 for each k, so
 //      min(max(I0,I8),max(I4,I12)) - c > t  or  c - max(min(I0,I8),min(I4,I12)) > t is necessary); passing pixels are
 //      appended to the warp's private work list (ballot ranks, no atomics) -- this removes the divergence of the score phase.
 //   2. SCORE the work list densely: ring differences are packed as biased s16x2 {I-c+256, c-I+256} with ONE IMAD each, so
@@ -138,55 +138,65 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restr
 
     const int ini_th = plan->ini_th, lo_th = min(plan->ini_th, plan->min_th);
 
-    // ---- phase 1: compass pretest, 4 pixels per thread (u16x2 SIMD) -> this warp's work list -----------------------
+    // ---- phase 1: compass pretest, 8 pixels per thread (four u16x2 pairs) -> this warp's work list ------------------
     int nwork = 0;
     {
         const unsigned k2 = (unsigned)(0x8000 - 257 - lo_th) * 0x00010001u;
-        const int j0 = off >> 2, nquad = ((off + gw - 1) >> 2) - j0 + 1;       // aligned quads of tile columns covering the strip
-        // the warp's rows (py = wid, wid + 8, ...) are walked as ONE stream of quads, 32 per iteration, so that only the
-        // last iteration has idle lanes; t / nquad by multiplication (t < 512, nquad <= 64: exact with a 16-bit reciprocal)
+        // aligned octets (8 tile columns = one 64-bit word pair) covering the strip; the warp's rows (py = wid, wid + 8, ...)
+        // are walked as ONE stream of octets, 32 per iteration, so that only the last iteration has idle lanes;
+        // t / noct by multiplication (t < 512, noct <= 32: exact with a 16-bit reciprocal)
+        const int o0 = off >> 3, noct = ((off + gw - 1) >> 3) - o0 + 1;
         const int nrows_w = (ch - wid + kFastWarps - 1) / kFastWarps;
-        const int ntask = nrows_w * nquad;
-        const unsigned recip = 65536u / (unsigned)nquad + 1u;
+        const int ntask = nrows_w * noct;
+        const unsigned recip = 65536u / (unsigned)noct + 1u;
         for (int tb = 0; tb < ntask; tb += 32) {
             const int t = tb + lane;
             const int rl = (int)(((unsigned)t * recip) >> 16);
-            const int xq = t - rl * nquad;
+            const int xq = t - rl * noct;
             const int py = wid + kFastWarps * rl;
-            unsigned p0 = 0, p1 = 0;                             // pass bits of pixels (0,1) and (2,3)
-            const int xs = 4 * (j0 + xq) - off;                  // strip x of the quad's first pixel (-3 .. gw-1)
+            const int xs = 8 * (o0 + xq) - off;                  // strip x of the octet's first pixel (-7 .. gw-1)
+            // pass bits: pixel 2i -> bit 2i, pixel 2i+1 -> bit 16 + 2i
+            unsigned q = 0;
             if (t < ntask) {
-                const uint32_t* rc = tile32 + (py + 3) * kTileW + j0 + xq;      // centre-row word of the quad
-                const unsigned cw = rc[0], cl = rc[-1], cr = rc[1];
-                const unsigned up = rc[-3 * kTileW], dn = rc[3 * kTileW];
-                const unsigned lf = __funnelshift_r(cl, cw, 8);   // x-3 .. x
-                const unsigned rt = __funnelshift_r(cw, cr, 24);  // x+3 .. x+6
-                p0 = pretest_pair(__byte_perm(cw, 0, 0x4140), __byte_perm(dn, 0, 0x4140), __byte_perm(up, 0, 0x4140),
-                                  __byte_perm(rt, 0, 0x4140), __byte_perm(lf, 0, 0x4140), k2);
-                p1 = pretest_pair(__byte_perm(cw, 0, 0x4342), __byte_perm(dn, 0, 0x4342), __byte_perm(up, 0, 0x4342),
-                                  __byte_perm(rt, 0, 0x4342), __byte_perm(lf, 0, 0x4342), k2);
-                if (xs < 0 || xs + 3 >= gw) {                    // first / last quad: drop the pixels outside the strip
-                    if ((unsigned)xs >= (unsigned)gw) p0 &= ~0x8000u;
-                    if ((unsigned)(xs + 1) >= (unsigned)gw) p0 &= 0x8000u;
-                    if ((unsigned)(xs + 2) >= (unsigned)gw) p1 &= ~0x8000u;
-                    if ((unsigned)(xs + 3) >= (unsigned)gw) p1 &= 0x8000u;
+                const uint32_t* rc = tile32 + (py + 3) * kTileW + 2 * (o0 + xq);       // centre-row word pair of the octet
+                const uint2 cw = *reinterpret_cast<const uint2*>(rc);
+                const unsigned cl = rc[-1], cr = rc[2];
+                const uint2 up = *reinterpret_cast<const uint2*>(rc - 3 * kTileW);
+                const uint2 dn = *reinterpret_cast<const uint2*>(rc + 3 * kTileW);
+                const unsigned lf0 = __funnelshift_r(cl, cw.x, 8), lf1 = __funnelshift_r(cw.x, cw.y, 8);      // x-3 ..
+                const unsigned rt0 = __funnelshift_r(cw.x, cw.y, 24), rt1 = __funnelshift_r(cw.y, cr, 24);    // x+3 ..
+                const unsigned p0 = pretest_pair(__byte_perm(cw.x, 0, 0x4140), __byte_perm(dn.x, 0, 0x4140), __byte_perm(up.x, 0, 0x4140),
+                                                 __byte_perm(rt0, 0, 0x4140), __byte_perm(lf0, 0, 0x4140), k2);
+                const unsigned p1 = pretest_pair(__byte_perm(cw.x, 0, 0x4342), __byte_perm(dn.x, 0, 0x4342), __byte_perm(up.x, 0, 0x4342),
+                                                 __byte_perm(rt0, 0, 0x4342), __byte_perm(lf0, 0, 0x4342), k2);
+                const unsigned p2 = pretest_pair(__byte_perm(cw.y, 0, 0x4140), __byte_perm(dn.y, 0, 0x4140), __byte_perm(up.y, 0, 0x4140),
+                                                 __byte_perm(rt1, 0, 0x4140), __byte_perm(lf1, 0, 0x4140), k2);
+                const unsigned p3 = pretest_pair(__byte_perm(cw.y, 0, 0x4342), __byte_perm(dn.y, 0, 0x4342), __byte_perm(up.y, 0, 0x4342),
+                                                 __byte_perm(rt1, 0, 0x4342), __byte_perm(lf1, 0, 0x4342), k2);
+                q = (p0 >> 15) | (p1 >> 13) | (p2 >> 11) | (p3 >> 9);
+                if (xs < 0 || xs + 7 >= gw) {                    // first / last octet: drop the pixels outside the strip
+                    unsigned keep = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if ((unsigned)(xs + k) < (unsigned)gw) keep |= 1u << ((k & 1) * 16 + (k >> 1) * 2);
+                    q &= keep;
                 }
             }
-            // append the passing pixels of all lanes: popcount per lane, warp scan by shuffles, at most 4 predicated stores
-            const int c = __popc(p0) + __popc(p1);
+            // append the passing pixels of all lanes: one popcount per lane, warp scan by shuffles, predicated stores
+            // (the order of the list is irrelevant: scores go to the score tile, survivors to the row masks)
+            const int c = __popc(q);
             int inc = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int up = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += up;
+                const int up_ = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += up_;
             }
             uint16_t* wp = work + nwork + inc - c;
             nwork += __shfl_sync(0xffffffffu, inc, 31);
             const unsigned ent = (unsigned)((py << 8) + xs);
-            if (p0 & 0x8000u) *wp++ = (uint16_t)ent;
-            if ((int)p0 < 0) *wp++ = (uint16_t)(ent + 1);
-            if (p1 & 0x8000u) *wp++ = (uint16_t)(ent + 2);
-            if ((int)p1 < 0) *wp = (uint16_t)(ent + 3);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (q & (1u << ((k & 1) * 16 + (k >> 1) * 2))) *wp++ = (uint16_t)(ent + k);
         }
     }
     __syncwarp();
