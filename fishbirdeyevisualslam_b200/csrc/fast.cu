@@ -81,7 +81,7 @@ __device__ __forceinline__ unsigned pretest_pair(unsigned c, unsigned i0, unsign
     return (__vmaxu2(d1, d2) + k2) & 0x80008000u;                          // lane > 256 + t  <=>  bit 15 of lane + k set
 }
 
-__global__ void __launch_bounds__(kFastThreads) k_fast_cells(const Plan* __restrict__ plan, Workspace ws,
+__global__ void __launch_bounds__(kFastThreads, 4) k_fast_cells(const Plan* __restrict__ plan, Workspace ws,
                                                              const __grid_constant__ TmaMaps maps) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
