@@ -47,7 +47,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 template <int V> struct UmaxOf { static constexpr int value = kUmax[V < 0 ? -V : V]; };
 
-__global__ void __launch_bounds__(kDescWarps * 32) k_describe(const Plan* __restrict__ plan, Workspace ws) {
+__global__ void __launch_bounds__(kDescWarps * 32, 8) k_describe(const Plan* __restrict__ plan, Workspace ws) {
     __shared__ float4 s_pat[256];                                       // [j][lane]: pair lane*8 + j as (x0, y0, x1, y1)
     __shared__ uint32_t s_patch[kDescWarps][kPatchRows * kPatchWords];
     __shared__ uint32_t s_key[kDescPerCta];

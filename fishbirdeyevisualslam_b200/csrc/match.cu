@@ -107,7 +107,7 @@ __global__ void k_queries_from_kps(const fbe_keypoint* __restrict__ kps, const f
 }
 
 // ---- parallel stage: rows of (candidate, distance) in traversal order -----------------------------------------------
-__global__ void __launch_bounds__(256) k_window_rows(FrameDev f, QueryDev qs, bool incl, int C, unsigned* __restrict__ rows,
+__global__ void __launch_bounds__(256, 6) k_window_rows(FrameDev f, QueryDev qs, bool incl, int C, unsigned* __restrict__ rows,
                                                      int* __restrict__ cnt, int* __restrict__ overflow) {
     const int b = blockIdx.y;
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) k_window_rows(FrameDev f, QueryDev qs, bo
 // kReproj adds the per-candidate reprojection gate of ORBmatcher::Fuse (src/ORBmatcher.cc:911-937): q.w carries ur, the
 // chi-square bounds are compared in double like the reference's `e2*invSigma2 > 5.99` (float product, double literal).
 template <bool kReproj>
-__global__ void __launch_bounds__(256) k_window_top2(FrameDev f, QueryDev qs, bool incl, ReprojGate rg, int* __restrict__ best_idx,
+__global__ void __launch_bounds__(256, 6) k_window_top2(FrameDev f, QueryDev qs, bool incl, ReprojGate rg, int* __restrict__ best_idx,
                                                      int* __restrict__ best_dist, int* __restrict__ second_dist) {
     const int b = blockIdx.y;
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
