@@ -36,10 +36,10 @@ BYTES_PER_PAIR = 5_742_040
 # pixels of all pyramid levels (what the FAST kernel reads once): front 2 853 088, bird 456 460
 PYR_PIXELS_FRONT, PYR_PIXELS_BIRD = 2_853_088, 456_460
 # dram__bytes_read.sum + dram__bytes_write.sum of one front k_fast_cells launch over 128 images (ncu --set full,
-# profiles/r1_02_fast_ncu.md; r1_08 re-capture: 385 MB + 36 MB): 384.74 MB + 37.59 MB
-FAST_DRAM_BYTES_PER_FRONT_IMAGE = int((384.737280e6 + 37.585152e6) / 128)
-# warp-instructions executed by the same launch (sm__inst_executed.sum of the r1_08 capture, profiles/r1_08_fast_ncu.md)
-FAST_WARP_INST_PER_FRONT_IMAGE = 1_165_051_823 / 128
+# profiles/r1_10_fast_ncu.md): 384.76 MB + 35.90 MB
+FAST_DRAM_BYTES_PER_FRONT_IMAGE = int((384.759040e6 + 35.900416e6) / 128)
+# warp-instructions executed by the same launch (sm__inst_executed.sum of the same capture)
+FAST_WARP_INST_PER_FRONT_IMAGE = 1_063_465_360 / 128
 METRIC = "front+bird frame-pairs/sec ORB extract+match at 1/2/4/8 B200 vs host CPU ref"
 
 
@@ -365,16 +365,16 @@ def run_ours(args):
                 "clocks": clk.summary(),
                 "roofline": {"bound": "hbm", "kernel": "k_fast_cells (front)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": FAST_DRAM_BYTES_PER_FRONT_IMAGE * B, "peak_source": peak_src,
-                             "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of k_fast_cells (front), per image x images per launch; profiles/r1_02_fast_ncu.md",
+                             "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of k_fast_cells (front), per image x images per launch; profiles/r1_10_fast_ncu.md",
                              "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": fast_ms,
-                             "note": "k_fast_cells is instruction-bound, not memory-bound: ncu (profiles/r1_02_fast_ncu.md) shows 79-81 % issue-slot "
-                                     "utilisation, 72 % alu pipe, 3.0 warp-instructions per SM per clock and 4 % of DRAM throughput; ~100 integer "
+                             "note": "k_fast_cells is instruction-bound, not memory-bound: ncu (profiles/r1_10_fast_ncu.md) shows 77 % issue-slot "
+                                     "utilisation, 72 % alu pipe, 3.0 warp-instructions per SM per clock and 4 % of DRAM throughput; ~90 integer "
                                      "instructions per pixel bound it, so frac of the HBM peak stays small by construction",
                              "issue": {"what": "the roof this kernel actually sits under: warp-instruction issue (148 SMs x 4 schedulers x SM clock)",
                                        "achieved_gwarp_inst_s": FAST_WARP_INST_PER_FRONT_IMAGE * B / (fast_ms * 1e-3) / 1e9,
                                        "peak_gwarp_inst_s": 148 * 4 * (clk.summary().get("sm_mhz") or 1965.0) * 1e6 / 1e9,
                                        "frac": FAST_WARP_INST_PER_FRONT_IMAGE * B / (fast_ms * 1e-3) / (148 * 4 * (clk.summary().get("sm_mhz") or 1965.0) * 1e6),
-                                       "source": "sm__inst_executed.sum of one launch (ncu --set full, profiles/r1_08_fast_ncu.md) / live launch time"},
+                                       "source": "sm__inst_executed.sum of one launch (ncu --set full, profiles/r1_10_fast_ncu.md) / live launch time"},
                              "whole_step": {"bytes_per_pair": BYTES_PER_PAIR, "achieved_gbs": value / world * BYTES_PER_PAIR / 1e9,
                                             "frac": value / world * BYTES_PER_PAIR / 1e9 / peak}},
                 "stage_ms": stage_ms,

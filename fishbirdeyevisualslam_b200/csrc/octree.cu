@@ -424,7 +424,7 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
     return n;
 }
 
-__global__ void __launch_bounds__(kOctThreads) k_octree(const Plan* __restrict__ plan, Workspace ws, int use_smem, int level_stride) {
+__global__ void __launch_bounds__(kOctThreads, 3) k_octree(const Plan* __restrict__ plan, Workspace ws, int use_smem, int level_stride) {
     extern __shared__ __align__(16) uint8_t dyn[];
     __shared__ int s_warp[kOctThreads / 32 + 1];
     __shared__ int s_ctl[4];
