@@ -152,6 +152,24 @@ FBE_API int fbe_check_homography(const fbe_keypoint* kps1, const fbe_keypoint* k
 FBE_API int fbe_check_fundamental(const fbe_keypoint* kps1, const fbe_keypoint* kps2, const int32_t* matches, int32_t n,
                                   const float* F21, int32_t K, float sigma, int32_t device, float* scores, uint8_t* inliers);
 
+/* ---- DBoW2 vocabulary descent (next row f-4) ------------------------------------------------------ */
+/* The tree of DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h) on the
+ * device.  Nodes 1 .. n_nodes in creation order, node 0 is the root: exactly the rows of the text format read by
+ * loadFromTextFile (:1338-1436) -- parent id, nIsLeaf flag (> 0: the node becomes the next word id), 32 descriptor bytes,
+ * weight.  A node is a leaf iff nothing names it as parent (Node::isLeaf(), :328). */
+typedef struct fbe_vocabulary fbe_vocabulary;
+FBE_API int fbe_vocabulary_create(int32_t k, int32_t L, const int32_t* parent, const uint8_t* is_word, const uint8_t* desc,
+                                  const double* weight, int32_t n_nodes, int32_t device, fbe_vocabulary** out);
+FBE_API int fbe_vocabulary_destroy(fbe_vocabulary* v);
+/* TemplatedVocabulary::transform(feature, word_id, weight, &nid, levelsup) (:1218-1263) for n descriptors at once: the
+ * per-feature part of transform(features, BowVector&, FeatureVector&, levelsup) (:1127-1205) that Frame::ComputeBoW /
+ * KeyFrame::ComputeBoW call with levelsup = 4.  At every level the child with the smallest Hamming distance wins, the
+ * FIRST one on ties (`d < best_d`).  Outputs per feature: word_id, node_id = the node passed at level L - levelsup (0 = root
+ * when L - levelsup <= 0), weight = the word's weight.  The caller folds them into the BowVector (addWeight in feature
+ * order, then normalize) and the FeatureVector (addFeature) exactly as :1150-1204 do; features with weight 0 are skipped. */
+FBE_API int fbe_bow_transform(fbe_vocabulary* v, const uint8_t* desc, int32_t n, int32_t levelsup, int32_t* word_id,
+                              int32_t* node_id, double* weight);
+
 /* ---- Frame undistortion (next row f-1) ----------------------------------------------------------- */
 /* Frame::UndistortKeyPoints, src/Frame.cc:638-669: cv::fisheye::undistortPoints(pts, pts, mK, mDistCoef, Mat(), mK) on the
  * keypoint positions (OpenCV 4.13 semantics: double-precision Newton solve, <= 10 iterations, eps 1e-8; (-1e6,-1e6) when

@@ -84,6 +84,7 @@ public:
         buf_ = std::make_shared<std::vector<uchar> >((size_t)r * step_ + 16, 0);
         data_ = buf_->data();
     }
+    void release() { buf_.reset(); data_ = nullptr; rows = cols = 0; step_ = 0; }
     int type() const { return type_; }
     bool empty() const { return data_ == nullptr || rows == 0 || cols == 0; }
     size_t esz() const { return type_ == CV_32F ? 4 : 1; }
@@ -173,6 +174,30 @@ inline Mat operator*(double s, const Mat& a) { return scale(a, s); }
 inline Mat operator*(const Mat& a, double s) { return scale(a, s); }
 inline Mat operator/(const Mat& a, double s) { return scale(a, 1.0 / s); }
 inline double norm(const Mat& a, int = NORM_L2) { return std::sqrt(a.dot(a)); }
+
+// cv::FileStorage / FileNode: DBoW2's TemplatedVocabulary has virtual YAML save / load members that must compile; the
+// harness only ever uses loadFromTextFile, so these are inert.
+class FileNode {
+public:
+    FileNode operator[](const std::string&) const { return FileNode(); }
+    FileNode operator[](const char*) const { return FileNode(); }
+    FileNode operator[](int) const { return FileNode(); }
+    size_t size() const { return 0; }
+    operator int() const { return 0; }
+    operator double() const { return 0.0; }
+    operator std::string() const { return std::string(); }
+};
+class FileStorage {
+public:
+    enum { READ = 0, WRITE = 1 };
+    FileStorage(const char*, int) {}
+    FileStorage(const std::string&, int) {}
+    bool isOpened() const { return false; }
+    void release() {}
+    FileNode operator[](const std::string&) const { return FileNode(); }
+    FileNode operator[](const char*) const { return FileNode(); }
+    template <class T> FileStorage& operator<<(const T&) { return *this; }
+};
 
 // declarations only (ORBextractor.h mentions them; the matcher build never calls the extractor)
 class _InputArray; class _OutputArray;

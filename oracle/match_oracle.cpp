@@ -799,6 +799,37 @@ void orc_check_models(const Kp* k1, const Kp* k2, const int32_t* matches, int n,
     }
 }
 
+// DBoW2 TemplatedVocabulary::transform(feature, word_id, weight, &nid, levelsup)  Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1263
+// on a tree given as the rows of the text format (loadFromTextFile :1338-1436): nodes 1..n in creation order, parent id,
+// nIsLeaf flag, descriptor, weight.  Pinned against the verbatim template (oracle/ref_voc_wrap.cpp, tests/test_vocabulary.py).
+void orc_bow_transform(int L, const int32_t* parent, const uint8_t* is_word, const uint8_t* ndesc, const double* nweight, int n_nodes,
+                       const uint8_t* desc, int n, int levelsup, int32_t* word_id, int32_t* node_id, double* weight) {
+    std::vector<std::vector<int> > children(n_nodes + 1);
+    std::vector<int> word(n_nodes + 1, 0);
+    int nwords = 0;
+    for (int i = 1; i <= n_nodes; ++i) {
+        children[parent[i - 1]].push_back(i);
+        if (is_word[i - 1] > 0) word[i] = nwords++;
+    }
+    const int nid_level = L - levelsup;
+    for (int f = 0; f < n; ++f) {
+        int nid = 0;                                    // the reference leaves *nid untouched when the level is never reached
+        int final_id = 0, current_level = 0;
+        do {
+            ++current_level;
+            const std::vector<int>& nodes = children[final_id];
+            final_id = nodes[0];
+            double best_d = hamming(desc + (size_t)f * 32, ndesc + (size_t)(final_id - 1) * 32);
+            for (size_t c = 1; c < nodes.size(); ++c) {
+                const double d = hamming(desc + (size_t)f * 32, ndesc + (size_t)(nodes[c] - 1) * 32);
+                if (d < best_d) { best_d = d; final_id = nodes[c]; }
+            }
+            if (current_level == nid_level) nid = final_id;
+        } while (!children[final_id].empty());
+        word_id[f] = word[final_id]; node_id[f] = nid; weight[f] = nweight[final_id - 1];
+    }
+}
+
 void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* best_idx, int32_t* best_dist,
                          int32_t* second_dist) {
     for (int i = 0; i < nq; ++i) {

@@ -417,6 +417,52 @@ def check_models(k1, k2, matches, A, B, sigma, homography, _L=None):
     return scores[:K], inl_flat[:K * n].reshape(K, n)
 
 
+def bow_transform(L, parent, is_word, ndesc, nweight, desc, levelsup):
+    """Per-feature part of DBoW2 TemplatedVocabulary::transform -> (word_id[n], node_id[n], weight[n])."""
+    parent = np.ascontiguousarray(parent, np.int32); is_word = np.ascontiguousarray(is_word, np.uint8)
+    ndesc = np.ascontiguousarray(ndesc, np.uint8); nweight = np.ascontiguousarray(nweight, np.float64)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    n = len(desc)
+    w = np.zeros(max(n, 1), np.int32); nd = np.zeros(max(n, 1), np.int32); wt = np.zeros(max(n, 1), np.float64)
+    lib().orc_bow_transform(int(L), _p(parent), _p(is_word), _p(ndesc), _p(nweight), len(parent), _p(desc), n, int(levelsup), _p(w), _p(nd), _p(wt))
+    return w[:n], nd[:n], wt[:n]
+
+
+_refv = None
+
+
+def refvoc():
+    """ctypes handle of the verbatim DBoW2 vocabulary build (oracle/_ref/libfbe_refvoc.so) or None."""
+    global _refv
+    if _refv is None:
+        path = os.path.join(HERE, "_ref", "libfbe_refvoc.so")
+        if not os.path.exists(path):
+            return None
+        _refv = C.CDLL(path)
+        _refv.refv_load_text.restype = C.c_void_p
+        _refv.refv_load_text.argtypes = [C.c_char_p]
+        _refv.refv_free.argtypes = [C.c_void_p]
+        _refv.refv_size.argtypes = [C.c_void_p]
+    return _refv
+
+
+def ref_voc_transform(text_path, desc, levelsup):
+    """The reference's own loadFromTextFile + transform(features, BowVector&, FeatureVector&, levelsup)
+    -> (bow ids, bow values, (fv node ids, start, items), number of words in the vocabulary)."""
+    L_ = refvoc()
+    h = L_.refv_load_text(text_path.encode())
+    assert h
+    desc = np.ascontiguousarray(desc, np.uint8)
+    n = len(desc)
+    ids = np.zeros(max(n, 1), np.int32); vals = np.zeros(max(n, 1), np.float64)
+    fid = np.zeros(max(n, 1), np.int32); fst = np.zeros(max(n, 1) + 1, np.int32); fit = np.zeros(max(n, 1), np.int32)
+    nn = C.c_int32()
+    k = L_.refv_transform(C.c_void_p(h), _p(desc), n, int(levelsup), _p(ids), _p(vals), _p(fid), _p(fst), _p(fit), C.byref(nn))
+    size = L_.refv_size(C.c_void_p(h))
+    L_.refv_free(C.c_void_p(h))
+    return ids[:k].copy(), vals[:k].copy(), (fid[:nn.value].copy(), fst[:nn.value + 1].copy(), fit[:fst[nn.value]].copy()), size
+
+
 def distinctive_descriptors(desc, start, _L=None):
     """MapPoint::ComputeDistinctiveDescriptors for CSR lists of observed descriptors -> (best index per point, its median)."""
     desc = np.ascontiguousarray(desc, np.uint8); start = np.ascontiguousarray(start, np.int32)
