@@ -30,7 +30,7 @@ int ExtractorCore::init(const fbe_extractor_cfg& c) {
     }
     FBE_CUDA(cudaSetDevice(cfg.device));
     compute_extractor_tables(cfg.nfeatures, cfg.scale_factor, cfg.nlevels, scale, inv_scale, sigma2, inv_sigma2, per_level, umax);
-    FBE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    FBE_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, stream_priority));
     FBE_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
     FBE_CUDA(cudaEventCreateWithFlags(&ev_pyr, cudaEventDisableTiming));
     FBE_CUDA(cudaEventCreateWithFlags(&ev_blur, cudaEventDisableTiming));

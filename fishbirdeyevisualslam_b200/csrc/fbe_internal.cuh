@@ -174,6 +174,7 @@ struct ExtractorCore {
     int enable_timing(bool on);
     int collect_timing(double* ms_sum /*[kStages]*/, int* nsteps);
 
+    int stream_priority = 0;       // CUDA priority of the main stream (0 = default, negative = more urgent); set before init
     int init(const fbe_extractor_cfg& c);
     void destroy();
     int ensure_plan(int rows, int cols);

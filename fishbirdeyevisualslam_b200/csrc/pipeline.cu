@@ -115,6 +115,14 @@ int fbe_pipeline_create(const fbe_pipeline_cfg* cfg, fbe_pipeline** out) {
     fc.max_batch = bc.max_batch = cfg->batch + 1;
     fc.device = bc.device = cfg->device;
     p->front.out_sets = p->bird.out_sets = 2;
+    // The front extractor's main stream (pyramid -> FAST -> octree -> describe -> grid) is the critical path of a step: the
+    // blur side stream, the bird extractor and the matching fill in around it.  FBE_STREAM_PRIO=0 disables (A/B runs).
+    {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        const char* pe = getenv("FBE_STREAM_PRIO");
+        if (!(pe && pe[0] == '0')) p->front.stream_priority = prio_hi;
+    }
     int rc = p->front.init(fc);
     if (rc == FBE_OK) rc = p->bird.init(bc);
     auto fail = [&](int code) { free_all(p); delete p; return code; };
