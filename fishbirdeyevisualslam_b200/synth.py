@@ -95,3 +95,48 @@ def cheap_batch(n: int, h: int, w: int, seed: int) -> np.ndarray:
         win = sc[m - dy:m - dy + h, m - dx:m - dx + w]
         out[i] = np.clip(np.rint(win + rng.normal(0.0, 2.0, size=(h, w))), 0, 255).astype(np.uint8)
     return out
+
+
+def road_frame(h: int, w: int, seed: int, shift=(0, 0), margin: int = 8) -> np.ndarray:
+    """A frame with road-scene statistics (a SECOND workload beside the SURVEY recipe above, whose 4-px noise texture makes
+    ~20 % of all pixels FAST corners): smooth low-frequency shading, a horizon, a few dozen low-contrast facades / vehicles,
+    bright lane markings, sensor noise N(0, 1.2).  A few percent of the pixels are corners and many cells need the
+    minThFAST fallback, like camera footage."""
+    rng = np.random.default_rng(seed * 31 + 7)
+    H, W = h + 2 * margin, w + 2 * margin
+    coarse = rng.uniform(60, 170, size=(H // 64 + 3, W // 64 + 3))
+    ys, xs = np.arange(H) / 64.0, np.arange(W) / 64.0
+    y0, x0 = np.floor(ys).astype(int), np.floor(xs).astype(int)
+    fy, fx = (ys - y0)[:, None], (xs - x0)[None, :]
+    im = (coarse[y0][:, x0] * (1 - fx) + coarse[y0][:, x0 + 1] * fx) * (1 - fy) + (coarse[y0 + 1][:, x0] * (1 - fx) + coarse[y0 + 1][:, x0 + 1] * fx) * fy
+    hz = int(H * rng.uniform(0.35, 0.5))
+    im[hz:] = im[hz:] * 0.6 + 25                                   # darker road below the horizon
+    for _ in range(60):                                            # facades, vehicles, signs above / around the horizon
+        rw, rh = int(rng.integers(10, W // 6)), int(rng.integers(8, H // 5))
+        x, y = int(rng.integers(0, W - rw)), int(rng.integers(0, max(1, hz + H // 8 - rh)))
+        im[y:y + rh, x:x + rw] = im[y:y + rh, x:x + rw] * 0.3 + rng.uniform(20, 220) * 0.7
+        if rng.random() < 0.5:                                     # windows
+            for wy in range(y + 3, y + rh - 6, 9):
+                for wx in range(x + 3, x + rw - 6, 11):
+                    im[wy:wy + 4, wx:wx + 6] -= rng.uniform(15, 60)
+    for k in range(int(rng.integers(3, 7))):                       # lane markings: bright dashes converging to the horizon
+        xb = rng.uniform(0.1, 0.9) * W
+        for t in np.arange(0.05, 1.0, 0.12):
+            yy = int(hz + t * (H - hz))
+            xx = int(W / 2 + (xb - W / 2) * t)
+            ww, hh = max(2, int(10 * t)), max(2, int(22 * t))
+            im[yy:yy + hh, xx:xx + ww] = rng.uniform(190, 240)
+    dx, dy = shift
+    win = im[margin - dy:margin - dy + h, margin - dx:margin - dx + w]
+    nrng = np.random.default_rng(seed * 7919 + 17 + 13 * (dx + 50) + (dy + 50))
+    return np.ascontiguousarray(np.clip(np.rint(win + nrng.normal(0.0, 1.2, size=(h, w))), 0, 255).astype(np.uint8))
+
+
+def road_batch(n: int, h: int, w: int, seed: int) -> np.ndarray:
+    """n consecutive road-like frames (scene changes every 8 frames, window drifts (+2, +1) px per frame)."""
+    out = np.empty((n, h, w), np.uint8)
+    for i in range(n):
+        k = i % 8
+        out[i] = road_frame(h, w, seed * 100 + i // 8, (2 * k - 7, k - 4))
+    return out
+

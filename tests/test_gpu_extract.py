@@ -224,3 +224,21 @@ def test_distinct_instances_run_concurrently(oracle):
         t.join()
     for (k, d), (ko, do) in zip(got, want):
         assert k.tobytes() == ko.tobytes() and np.array_equal(d, do)
+
+
+@pytest.mark.parametrize("cfg", [(720, 1280, 2000, 1), (384, 384, 1000, 2), (400, 950, 2000, 3)])
+def test_road_like_scenes(oracle, cfg):
+    """Road-scene statistics (smooth road, textured facades, ~5 % corners): most cells of the lower half need the
+    minThFAST fallback, the octree sees strongly clustered candidates."""
+    from fishbirdeyevisualslam_b200.extractor import ORBextractor
+    h, w, nf, seed = cfg
+    img = synth.road_frame(h, w, seed)
+    o = oracle.OracleExtractor(nf, 1.2, 8, 15, 5)
+    ko, do = o(img)
+    g = ORBextractor(nf, 1.2, 8, 15, 5)
+    kg, dg = g(img)
+    for l in (0, 3, 7):
+        assert np.array_equal(g.debug_candidates(l), o.candidates(l)), f"candidates level {l}"
+    compare(kg, dg, ko, do, o.boundary)
+    assert len(ko) >= nf * 0.9
+

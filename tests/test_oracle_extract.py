@@ -67,3 +67,15 @@ def test_octree_tie_rule_and_overshoot(oracle):
     n = L.orc_octree(xy.ctypes.data_as(C.c_void_p), len(xy), 0, 124, 0, 64, 40, sel.ctypes.data_as(C.c_void_p), len(sel))
     assert n >= 40
     assert len(set(sel[:n].tolist())) == n
+
+
+def test_road_like_scene_against_verbatim_reference(oracle):
+    """A frame with road-scene statistics (synth.road_frame): restated extractor == the reference's own ORBextractor.cc."""
+    if oracle.ref() is None:
+        pytest.skip("oracle/_ref/libfbe_ref.so not built")
+    from fishbirdeyevisualslam_b200 import synth
+    img = synth.road_frame(400, 950, 3)
+    ko, do = oracle.OracleExtractor(2000, 1.2, 8, 15, 5)(img)
+    kr, dr = oracle.RefExtractor(2000, 1.2, 8, 15, 5)(img)
+    assert ko.tobytes() == kr.tobytes() and np.array_equal(do, dr) and len(ko) > 1800
+

@@ -9,8 +9,10 @@ from fishbirdeyevisualslam_b200.pipeline import FrontBirdPipeline
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 pipe = FrontBirdPipeline(B)
-dF = torch.from_numpy(synth.cheap_batch(B, 720, 1280, 100)).cuda()
-dB = torch.from_numpy(synth.cheap_batch(B, 384, 384, 200)).cuda()
+scene = sys.argv[3] if len(sys.argv) > 3 else "survey"          # "survey" = the SURVEY recipe of bench.py, "road" = road-scene statistics
+mk = synth.road_batch if scene == "road" else synth.cheap_batch
+dF = torch.from_numpy(mk(B, 720, 1280, 100)).cuda()
+dB = torch.from_numpy(mk(B, 384, 384, 200)).cuda()
 for _ in range(3):
     pipe.step_dev(dF.data_ptr(), dB.data_ptr())
 pipe.sync()
