@@ -40,7 +40,8 @@ int ExtractorCore::init(const fbe_extractor_cfg& c) {
 
 int ExtractorCore::free_ws() {
     cudaFree(ws.pyr); cudaFree(ws.blur); cudaFree(ws.cell_count); cudaFree(ws.slots); cudaFree(ws.keys);
-    cudaFree(ws.key_node); cudaFree(ws.oct_scratch); cudaFree(ws.sel); cudaFree(ws.level_n); cudaFree(ws.out_kps);
+    cudaFree(ws.key_node); cudaFree(ws.oct_scratch); cudaFree(ws.sel); cudaFree(ws.level_n); if (ws.out_kps_un != ws.out_kps) cudaFree(ws.out_kps_un);
+    cudaFree(ws.out_kps);
     cudaFree(ws.out_desc); cudaFree(ws.out_n); cudaFree(ws.out_cell); cudaFree(ws.grid_start); cudaFree(ws.grid_items);
     cudaFree(ws.status); cudaFree(dplan); cudaFree(dtab);
     cudaFree(const_cast<uint32_t*>(ws.fast_tab)); cudaFree(const_cast<uint32_t*>(ws.blur_tab));
@@ -67,6 +68,15 @@ void ExtractorCore::destroy() {
     if (stream) cudaStreamDestroy(stream);
     if (stream2) cudaStreamDestroy(stream2);
     stream = stream2 = nullptr;
+}
+
+int ExtractorCore::set_fisheye(const float K[4], const float D[4]) {
+    if (!K || !D) return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(cfg.device));
+    if (have_ws) { FBE_CUDA(cudaStreamSynchronize(stream)); FBE_CUDA(cudaStreamSynchronize(stream2)); free_ws(); have_ws = false; }
+    fisheye = true;
+    for (int i = 0; i < 4; ++i) { fish_K[i] = K[i]; fish_D[i] = D[i]; }
+    return FBE_OK;
 }
 
 int ExtractorCore::set_grid(float min_x, float min_y, float inv_w, float inv_h, int gcols, int grows) {
@@ -132,6 +142,8 @@ int ExtractorCore::ensure_plan(int rows, int cols) {
     FBE_CUDA(cudaMemset(ws.level_n, 0, B * FBE_MAX_LEVELS * sizeof(int)));
     const size_t Bo = B * (size_t)out_sets;           // output arrays exist once per output set
     FBE_CUDA(cudaMalloc(&ws.out_kps, Bo * hplan.kp_cap_total * sizeof(fbe_keypoint)));
+    if (fisheye) FBE_CUDA(cudaMalloc(&ws.out_kps_un, Bo * hplan.kp_cap_total * sizeof(fbe_keypoint)));
+    else ws.out_kps_un = ws.out_kps;
     FBE_CUDA(cudaMalloc(&ws.out_desc, Bo * hplan.kp_cap_total * 32));
     FBE_CUDA(cudaMalloc(&ws.out_n, Bo * sizeof(int)));
     FBE_CUDA(cudaMalloc(&ws.out_cell, Bo * hplan.kp_cap_total * sizeof(int)));
@@ -171,7 +183,7 @@ Workspace ExtractorCore::slot_view(int slot0, int out_set) const {
     v.slots += s * hplan.slots_total; v.keys += s * hplan.slots_total; v.key_node += s * hplan.slots_total;
     v.oct_scratch += s * ws.oct_scratch_bytes;
     v.sel += s * hplan.kp_cap_total; v.level_n += s * FBE_MAX_LEVELS;
-    v.out_kps += so * hplan.kp_cap_total; v.out_desc += so * hplan.kp_cap_total * 32; v.out_n += so;
+    v.out_kps += so * hplan.kp_cap_total; v.out_kps_un += so * hplan.kp_cap_total; v.out_desc += so * hplan.kp_cap_total * 32; v.out_n += so;
     v.out_cell += so * hplan.kp_cap_total; v.grid_start += so * (gcells + 1); v.grid_items += so * hplan.kp_cap_total;
     v.status += s;
     return v;
@@ -223,6 +235,11 @@ int ExtractorCore::run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, in
     if ((rc = launch_describe(hplan, dplan, v, nimg, stream)) != FBE_OK) return rc;
     FBE_MARK(4, stream);
     FBE_STAGE("describe", stream);
+    if (fisheye && fish_D[0] != 0.0f) {            // Frame::UndistortKeyPoints (src/Frame.cc:638-669); k1 == 0 copies (:640-644)
+        if ((rc = launch_undistort_batch(v.out_kps, v.out_n, hplan.kp_cap_total, nimg, fish_K, fish_D, v.out_kps_un, stream)) != FBE_OK) return rc;
+    } else if (fisheye) {
+        FBE_CUDA(cudaMemcpyAsync(v.out_kps_un, v.out_kps, (size_t)nimg * hplan.kp_cap_total * sizeof(fbe_keypoint), cudaMemcpyDeviceToDevice, stream));
+    }
     if ((rc = launch_grid(hplan, dplan, v, nimg, stream)) != FBE_OK) return rc;
     FBE_MARK(5, stream);
     FBE_STAGE("grid", stream);

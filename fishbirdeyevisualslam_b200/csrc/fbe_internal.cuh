@@ -91,7 +91,8 @@ struct Workspace {
     size_t oct_scratch_bytes;   // per slot
     uint32_t* sel;         // [B][kp_cap_total] selected keys per level in output order
     int* level_n;          // [B][FBE_MAX_LEVELS] keypoints per level
-    fbe_keypoint* out_kps; // [B][kp_cap_total]
+    fbe_keypoint* out_kps; // [B][kp_cap_total]   mvKeys
+    fbe_keypoint* out_kps_un; // mvKeysUn: == out_kps unless a fisheye model is set (then its own [B][kp_cap_total] array)
     uint8_t* out_desc;     // [B][kp_cap_total][32]
     int* out_n;            // [B]
     int* out_cell;         // [B][kp_cap_total] grid cell id per keypoint or -1
@@ -127,6 +128,8 @@ int launch_octree(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg,
 int launch_blur(const Plan& hp, const Plan* dp, const Workspace& ws, const TmaMaps& maps, int nimg, cudaStream_t st);
 int launch_describe(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
 int launch_grid(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st);
+int launch_undistort_batch(const fbe_keypoint* in, const int* n_arr, int stride, int nimg, const float K[4], const float D[4],
+                           fbe_keypoint* out, cudaStream_t st);
 size_t octree_scratch_bytes(const Plan& hp);
 // stand-alone octree on caller candidates (device arrays): keys packed with level coordinates (= relative + 16)
 int launch_octree_debug(const uint32_t* d_keys, uint32_t* d_knode, int nk, int nini, float hx, int H, int nfeat, int cap,
@@ -174,6 +177,9 @@ struct ExtractorCore {
     int enable_timing(bool on);
     int collect_timing(double* ms_sum /*[kStages]*/, int* nsteps);
 
+    bool fisheye = false;          // Frame::UndistortKeyPoints on the device between describe and grid (set_fisheye)
+    float fish_K[4] = {0, 0, 0, 0}, fish_D[4] = {0, 0, 0, 0};
+    int set_fisheye(const float K[4], const float D[4]);
     int stream_priority = 0;       // CUDA priority of the main stream (0 = default, negative = more urgent); set before init
     int init(const fbe_extractor_cfg& c);
     void destroy();

@@ -97,7 +97,7 @@ int launch_grid_build(const fbe_keypoint* d_kps, const int* d_n, int n_stride, i
 int launch_grid(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st) {
     (void)dp;
     if (hp.grid_cols <= 0) return FBE_OK;
-    return launch_grid_build(ws.out_kps, ws.out_n, hp.kp_cap_total, nimg, hp.grid_min_x, hp.grid_min_y, hp.grid_inv_w,
+    return launch_grid_build(ws.out_kps_un, ws.out_n, hp.kp_cap_total, nimg, hp.grid_min_x, hp.grid_min_y, hp.grid_inv_w,
                              hp.grid_inv_h, hp.grid_cols, hp.grid_rows, ws.out_cell, ws.grid_start, ws.grid_items, st);
 }
 

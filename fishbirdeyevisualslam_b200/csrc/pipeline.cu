@@ -23,6 +23,7 @@ struct fbe_pipeline {
     cudaEvent_t ev_match_done[2] = {nullptr, nullptr};   // per output set: the matching that read it has finished
     bool set_used[2] = {false, false};
     int step_count = 0, last_set = 0;
+    float bounds[4] = {0, 0, 0, 0};      // mnMinX, mnMaxX, mnMinY, mnMaxY of the front frames
     // front matching workspace
     float4* fq = nullptr; int2* flv = nullptr; unsigned* frows = nullptr; int* fcnt = nullptr;
     int *f_mdist = nullptr, *f_m21 = nullptr, *f_m12 = nullptr, *f_bin = nullptr, *f_hit = nullptr, *f_nm = nullptr;
@@ -60,7 +61,7 @@ __global__ void k_pair_results(const int* __restrict__ nf, const int* __restrict
 FrameDev frame_dev(const ExtractorCore& e, int slot0, int set) {
     Workspace v = e.slot_view(slot0, set);
     FrameDev f;
-    f.kps = v.out_kps; f.desc = v.out_desc; f.n = v.out_n; f.start = v.grid_start; f.items = v.grid_items;
+    f.kps = v.out_kps_un; f.desc = v.out_desc; f.n = v.out_n; f.start = v.grid_start; f.items = v.grid_items;     // matchers see mvKeysUn
     f.kp_stride = e.hplan.kp_cap_total;
     f.min_x = e.hplan.grid_min_x; f.min_y = e.hplan.grid_min_y; f.inv_w = e.hplan.grid_inv_w; f.inv_h = e.hplan.grid_inv_h;
     f.gcols = e.hplan.grid_cols; f.grows = e.hplan.grid_rows;
@@ -72,6 +73,7 @@ int carry_last(ExtractorCore& e, int B, int set, cudaStream_t st) {
     Workspace s = e.slot_view(B, set), d = e.slot_view(0, 1 - set);
     const int cap = e.hplan.kp_cap_total, gcells = e.hplan.grid_cols * e.hplan.grid_rows;
     FBE_CUDA(cudaMemcpyAsync(d.out_kps, s.out_kps, (size_t)cap * sizeof(fbe_keypoint), cudaMemcpyDeviceToDevice, st));
+    if (s.out_kps_un != s.out_kps) FBE_CUDA(cudaMemcpyAsync(d.out_kps_un, s.out_kps_un, (size_t)cap * sizeof(fbe_keypoint), cudaMemcpyDeviceToDevice, st));
     FBE_CUDA(cudaMemcpyAsync(d.out_desc, s.out_desc, (size_t)cap * 32, cudaMemcpyDeviceToDevice, st));
     FBE_CUDA(cudaMemcpyAsync(d.out_n, s.out_n, sizeof(int), cudaMemcpyDeviceToDevice, st));
     FBE_CUDA(cudaMemcpyAsync(d.grid_start, s.grid_start, (size_t)(gcells + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -128,7 +130,13 @@ int fbe_pipeline_create(const fbe_pipeline_cfg* cfg, fbe_pipeline** out) {
     auto fail = [&](int code) { free_all(p); delete p; return code; };
     if (rc != FBE_OK) return fail(rc);
     // k1 == 0 image bounds: mnMinX = 0, mnMaxX = cols (src/Frame.cc:741-795); grid constants of src/Frame.cc:276-283
-    if ((rc = p->front.set_grid(0.f, 0.f, 64.f / (float)cfg->front_cols, 48.f / (float)cfg->front_rows, 64, 48)) != FBE_OK) return fail(rc);
+    p->bounds[0] = 0.f; p->bounds[1] = (float)cfg->front_cols; p->bounds[2] = 0.f; p->bounds[3] = (float)cfg->front_rows;
+    if (cfg->front_fisheye) {
+        if ((rc = p->front.set_fisheye(cfg->front_K, cfg->front_D)) != FBE_OK) return fail(rc);
+        if ((rc = fbe_image_bounds(cfg->front_cols, cfg->front_rows, cfg->front_K, cfg->front_D, cfg->device, p->bounds)) != FBE_OK) return fail(rc);
+    }
+    // mfGridElementWidthInv = FRAME_GRID_COLS / (mnMaxX - mnMinX), src/Frame.cc:276-283
+    if ((rc = p->front.set_grid(p->bounds[0], p->bounds[2], 64.f / (p->bounds[1] - p->bounds[0]), 48.f / (p->bounds[3] - p->bounds[2]), 64, 48)) != FBE_OK) return fail(rc);
     if ((rc = p->bird.set_grid(0.f, 0.f, 32.f / (float)cfg->bird_cols, 32.f / (float)cfg->bird_rows, 32, 32)) != FBE_OK) return fail(rc);
     if ((rc = p->front.ensure_plan(cfg->front_rows, cfg->front_cols)) != FBE_OK) return fail(rc);
     if ((rc = p->bird.ensure_plan(cfg->bird_rows, cfg->bird_cols)) != FBE_OK) return fail(rc);
@@ -292,6 +300,16 @@ int fbe_pipeline_step_host(fbe_pipeline* p, const uint8_t* h_front, const uint8_
     FBE_CUDA(cudaMemcpyAsync(p->d_bird_in, h_bird, bbytes, cudaMemcpyHostToDevice, p->bird.stream));
     FBE_TRY(fbe_pipeline_step_dev(p, p->d_front_in, p->d_bird_in));
     return fbe_pipeline_fetch(p, res, front_matches12, bird_matches12);
+}
+
+int fbe_pipeline_fetch_front_undistorted(fbe_pipeline* p, int32_t pair, fbe_keypoint* front_kps_un, float bounds[4]) {
+    if (!p || pair < 0 || pair >= p->B) return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(p->cfg.device));
+    FBE_TRY(fbe_pipeline_sync(p));
+    Workspace f = p->front.slot_view(pair + 1, p->last_set);
+    if (front_kps_un) FBE_CUDA(cudaMemcpy(front_kps_un, f.out_kps_un, (size_t)p->fcap * sizeof(fbe_keypoint), cudaMemcpyDeviceToHost));
+    if (bounds) for (int i = 0; i < 4; ++i) bounds[i] = p->bounds[i];
+    return FBE_OK;
 }
 
 int fbe_pipeline_fetch_pair(fbe_pipeline* p, int32_t pair, fbe_keypoint* front_kps, uint8_t* front_desc, fbe_keypoint* bird_kps,

@@ -54,6 +54,28 @@ __global__ void k_undistort(const fbe_keypoint* __restrict__ in, int n, float fx
     out[i] = kp;
 }
 
+// the same per-point arithmetic over the device-resident keypoints of a batch (n_arr[b] valid entries per image)
+__global__ void k_undistort_batch(const fbe_keypoint* __restrict__ in, const int* __restrict__ n_arr, int stride, float fx, float fy,
+                                  float cx, float cy, float k0, float k1, float k2, float k3, fbe_keypoint* __restrict__ out) {
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_arr[b]) return;
+    fbe_keypoint kp = in[(size_t)b * stride + i];
+    float x, y;
+    fisheye_undistort_point((double)kp.x, (double)kp.y, (double)fx, (double)fy, (double)cx, (double)cy, (double)k0, (double)k1,
+                            (double)k2, (double)k3, &x, &y);
+    kp.x = x; kp.y = y;
+    out[(size_t)b * stride + i] = kp;
+}
+
+int launch_undistort_batch(const fbe_keypoint* in, const int* n_arr, int stride, int nimg, const float K[4], const float D[4],
+                           fbe_keypoint* out, cudaStream_t st) {
+    dim3 grid((stride + 127) / 128, nimg);
+    k_undistort_batch<<<grid, 128, 0, st>>>(in, n_arr, stride, K[0], K[1], K[2], K[3], D[0], D[1], D[2], D[3], out);
+    count_launch();
+    FBE_CUDA(cudaGetLastError());
+    return FBE_OK;
+}
+
 }  // namespace fbe
 
 using namespace fbe;

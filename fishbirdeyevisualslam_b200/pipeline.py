@@ -13,7 +13,9 @@ from ._lib import KP_DTYPE, PAIR_RESULT_DTYPE, ExtractorCfg, PipelineCfg, check,
 class FrontBirdPipeline:
     def __init__(self, batch: int, front_shape=(720, 1280), bird_shape=(384, 384), front_features=2000, bird_features=1000,
                  scale=1.2, nlevels=8, ini_th=15, min_th=5, nn_ratio=0.9, check_orientation=True, front_window=100,
-                 bird_window=10, device=0):
+                 bird_window=10, device=0, front_fisheye=None):
+        """front_fisheye = (K, D) with K = (fx, fy, cx, cy), D = (k1, k2, p1, p2): undistort the front keypoints on the device
+        before the grid (Frame::UndistortKeyPoints), as the reference's Frame constructor does for its fisheye camera."""
         self._L = _lib.load()
         self.batch = batch
         self.front_shape, self.bird_shape = tuple(front_shape), tuple(bird_shape)
@@ -21,6 +23,10 @@ class FrontBirdPipeline:
                           ExtractorCfg(bird_features, scale, nlevels, ini_th, min_th, batch + 1, device),
                           front_shape[0], front_shape[1], bird_shape[0], bird_shape[1], batch, nn_ratio,
                           int(check_orientation), front_window, bird_window, device)
+        if front_fisheye is not None:
+            cfg.front_fisheye = 1
+            cfg.front_K[:] = [float(x) for x in front_fisheye[0]]
+            cfg.front_D[:] = [float(x) for x in front_fisheye[1]]
         self._h = C.c_void_p()
         check(self._L.fbe_pipeline_create(C.byref(cfg), C.byref(self._h)))
         fc, bc = C.c_int32(), C.c_int32()
@@ -74,6 +80,13 @@ class FrontBirdPipeline:
         bk = np.zeros(self.bird_cap, KP_DTYPE); bd = np.zeros((self.bird_cap, 32), np.uint8)
         check(self._L.fbe_pipeline_fetch_pair(self._h, pair, ptr(fk), ptr(fd), ptr(bk), ptr(bd)))
         return fk, fd, bk, bd
+
+    def fetch_front_undistorted(self, pair: int):
+        """(mvKeysUn of one front frame of the last step, (mnMinX, mnMaxX, mnMinY, mnMaxY))."""
+        fk = np.zeros(self.front_cap, KP_DTYPE)
+        b = np.zeros(4, np.float32)
+        check(self._L.fbe_pipeline_fetch_front_undistorted(self._h, pair, ptr(fk), ptr(b)))
+        return fk, tuple(float(x) for x in b)
 
     def last_step_ms(self) -> float:
         ms = C.c_float()

@@ -351,6 +351,12 @@ typedef struct fbe_pipeline_cfg {
     int32_t front_window; /* SearchForInitialization window (100) */
     int32_t bird_window;  /* BirdviewMatch window (10) */
     int32_t device;
+    /* Front camera model.  front_fisheye != 0: Frame::UndistortKeyPoints (src/Frame.cc:638-669) runs on the device between
+     * the descriptors and the grid, the grid spans Frame::ComputeImageBounds (:741-795) and the matching works on mvKeysUn,
+     * exactly like the reference's Frame constructor orders it -- no host round trip.  K = {fx, fy, cx, cy}, D = mDistCoef
+     * {k1, k2, p1, p2}.  0 = k1 == 0 behaviour: mvKeysUn = mvKeys, bounds 0 .. cols / rows. */
+    int32_t front_fisheye;
+    float front_K[4], front_D[4];
 } fbe_pipeline_cfg;
 
 typedef struct fbe_pair_result { /* per frame pair, fixed stride */
@@ -382,6 +388,9 @@ FBE_API int fbe_pipeline_caps(const fbe_pipeline* p, int32_t* front_cap, int32_t
 /* copy back the results of the last step */
 FBE_API int fbe_pipeline_fetch(fbe_pipeline* p, fbe_pair_result* res, int32_t* front_matches12, int32_t* bird_matches12);
 /* full outputs of one pair of the last step (for parity tests at batch sizes) */
+/* mvKeysUn of one front frame of the last step (equals the keypoints of fbe_pipeline_fetch_pair when front_fisheye == 0)
+ * and the grid geometry in use: bounds = {mnMinX, mnMaxX, mnMinY, mnMaxY}.  Either pointer may be NULL. */
+FBE_API int fbe_pipeline_fetch_front_undistorted(fbe_pipeline* p, int32_t pair, fbe_keypoint* front_kps_un, float bounds[4]);
 FBE_API int fbe_pipeline_fetch_pair(fbe_pipeline* p, int32_t pair, fbe_keypoint* front_kps, uint8_t* front_desc,
                             fbe_keypoint* bird_kps, uint8_t* bird_desc);
 /* elapsed GPU milliseconds between the first kernel and the last kernel of the last step (CUDA events) */

@@ -191,3 +191,44 @@ def test_bench_size_properties():
         kf, df = of(fr[g]); kb, db = ob(bi[g])
         assert fk[:len(kf)].tobytes() == kf.tobytes() and np.array_equal(fd[:len(kf)], df)
         assert bk[:len(kb)].tobytes() == kb.tobytes() and np.array_equal(bd[:len(kb)], db)
+
+
+def test_fisheye_front_camera(oracle):
+    """The reference's real front camera (fisheye.yaml: k1 != 0): keypoints are undistorted ON THE DEVICE between descriptors
+    and grid, the grid spans the undistorted image bounds, and the frame-to-frame search runs on mvKeysUn -- the order of
+    the reference's Frame constructor (ExtractORB -> UndistortKeyPoints -> AssignFeaturesToGrid)."""
+    import torch
+    from fishbirdeyevisualslam_b200.matcher import ComputeImageBounds, Frame
+    from fishbirdeyevisualslam_b200.pipeline import FrontBirdPipeline
+    K, D = (348.5 * 1280 / 960, 347.0 * 720 / 600, 640.0, 362.0), (-0.0488316, 0.000298406, -0.00591118, 0.00193258)
+    n, B = 4, 2
+    fr, bi = sequence(n, 800)
+    pipe = FrontBirdPipeline(B, front_fisheye=(K, D))
+    dF, dB = torch.from_numpy(fr).cuda(), torch.from_numpy(bi).cuda()
+    of = oracle.OracleExtractor(2000, 1.2, 8, 15, 5)
+    bounds_want = ComputeImageBounds(FW, FH, K, D)
+    prev = None
+    for s in range(n // B):
+        pipe.step_dev(dF[s * B:].data_ptr(), dB[s * B:].data_ptr())
+        res, fm, bm = pipe.fetch()
+        for p in range(B):
+            i = s * B + p
+            fk, fd, _, _ = pipe.fetch_pair(p)
+            fu, bounds = pipe.fetch_front_undistorted(p)
+            kf, df = of(fr[i])
+            nf = len(kf)
+            assert fk[:nf].tobytes() == kf.tobytes() and np.array_equal(fd[:nf], df)            # mvKeys stay distorted
+            up = oracle.fisheye_undistort(np.stack([kf["x"], kf["y"]], 1), K, D)
+            un = kf.copy()
+            un["x"], un["y"] = up[:, 0], up[:, 1]
+            assert fu[:nf].tobytes() == un.tobytes() and bounds == bounds_want
+            assert np.abs(un["x"] - kf["x"]).max() > 2.0                                        # the model really moves points
+            F = Frame(un, df, bounds[0], bounds[2], float(np.float32(64) / (np.float32(bounds[1]) - np.float32(bounds[0]))),
+                      float(np.float32(48) / (np.float32(bounds[3]) - np.float32(bounds[2]))), 64, 48)
+            if prev is not None:
+                pm = np.ascontiguousarray(np.stack([prev.kps["x"], prev.kps["y"]], 1), np.float32)
+                n_o, m_o = oracle.search_for_initialization(prev, F, pm, 100, 0.9, True)
+                assert res["front_matches"][p] == n_o and np.array_equal(fm[p][:prev.N], m_o) and n_o > 100
+            prev = F
+    pipe.close()
+
