@@ -35,3 +35,15 @@ def test_dropin_descriptor_distance(dropin):
     a, b = rng.integers(0, 256, (64, 32), dtype=np.uint8), rng.integers(0, 256, (64, 32), dtype=np.uint8)
     for x, y in zip(a, b):
         assert dropin.hamming256(x, y) == int(np.unpackbits(x ^ y).sum())
+
+
+@pytest.mark.parametrize("seed", range(3, 13))
+def test_dropin_class_equals_verbatim_reference_live(oracle, dropin, seed):
+    """Seeds without committed outputs: the verbatim CPU build (shipped prebuilt in oracle/_ref) runs beside the drop-in class."""
+    if oracle.refmatch() is None:
+        pytest.skip("oracle/_ref/libfbe_refmatch.so not built")
+    want = T.scene_outputs(oracle.RefMatch(), seed, True)
+    got = T.scene_outputs(dropin, seed, True)
+    for k, v in want.items():
+        assert np.array_equal(got[k], v, equal_nan=True), k
+
