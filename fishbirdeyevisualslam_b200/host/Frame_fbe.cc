@@ -1,0 +1,45 @@
+// Drop-in body for Frame::AssignFeaturesToGrid (src/Frame.cc:381-411): both grids (64x48 over the undistorted front
+// keypoints, 32x32 over the bird keypoints) are bucketed on the device (fbe_grid_assign -> CSR) and copied into the
+// reference's mGrid / mGridBirdview vectors, so that GetFeaturesInArea[Birdview] and every other reader see what the
+// reference's loop would have produced (same cells, same in-cell order).  Compiled INSIDE the reference tree in place of
+// that one method; in this repository it is built against the reference's own Frame.h with the test shim
+// oracle/cvshim_m (oracle/Makefile target `dropinmatch`) and checked on the GPU by tests/test_gpu_dropin_match.py.
+// PosInGrid / PosInGridBirdview (:548-570) stay as they are: other code calls them per keypoint.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "Frame.h"
+#include "fbe_cabi.h"
+
+namespace ORB_SLAM2 {
+
+namespace {
+static_assert(sizeof(cv::KeyPoint) == sizeof(fbe_keypoint), "cv::KeyPoint must be 28 bytes");
+
+template <int COLS, int ROWS>
+void fill_grid(const std::vector<cv::KeyPoint>& keys, int n, float min_x, float min_y, float inv_w, float inv_h,
+               std::vector<std::size_t> (&grid)[COLS][ROWS]) {
+    std::vector<int> start(COLS * ROWS + 1, 0), items(n > 0 ? n : 1, 0);
+    int assigned = 0;
+    if (n > 0 && fbe_grid_assign(reinterpret_cast<const fbe_keypoint*>(keys.data()), n, min_x, min_y, inv_w, inv_h, COLS, ROWS,
+                                 start.data(), items.data(), &assigned) != FBE_OK) {
+        fprintf(stderr, "Frame::AssignFeaturesToGrid (fbe-b200): %s\n", fbe_last_error());
+        abort();      // no CPU fallback
+    }
+    for (int ix = 0; ix < COLS; ix++)
+        for (int iy = 0; iy < ROWS; iy++) {
+            const int c = ix * ROWS + iy;
+            grid[ix][iy].assign(items.begin() + start[c], items.begin() + start[c + 1]);
+        }
+}
+}  // namespace
+
+void Frame::AssignFeaturesToGrid() {
+    fill_grid<FRAME_GRID_COLS, FRAME_GRID_ROWS>(mvKeysUn, N, mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv, mGrid);
+    // PosInGridBirdview: round(x * mfGridElementWidthInvBirdview), no origin shift (:560-570)
+    fill_grid<FRAME_GRID_BIRD, FRAME_GRID_BIRD>(mvKeysBird, Nbird, 0.f, 0.f, mfGridElementWidthInvBirdview, mfGridElementHeightInvBirdview,
+                                                mGridBirdview);
+}
+
+}  // namespace ORB_SLAM2

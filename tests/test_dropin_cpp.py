@@ -52,3 +52,20 @@ def test_dropin_matches_oracle(oracle, tmp_path):
     tr, tc = struct.unpack_from("<ii", b, off)
     top = np.frombuffer(b, np.uint8, tr * tc, off + 8).reshape(tr, tc)
     assert np.array_equal(top, o.level_padded(nl - 1)[19:-19, 19:-19])
+
+
+def test_dropin_matcher_library_links(fbe):
+    """The drop-in ORBmatcher / Frame bodies (host/ORBmatcher_fbe.cc, host/Frame_fbe.cc) built against the reference's own
+    headers link against libfbe_b200.so and export the harness entry points (the build needs the reference sources, so the
+    library is prebuilt in the build container and shipped in oracle/_ref; absent -> skipped)."""
+    import ctypes as C
+    path = os.path.join(ROOT, "oracle", "_ref", "libfbe_dropinmatch.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libfbe_dropinmatch.so not built")
+    L = C.CDLL(path)
+    for name in ("refm_grid_assign", "refm_features_in_area", "refm_search_for_initialization", "refm_search_by_bow_kf",
+                 "refm_search_for_triangulation", "refm_fuse", "refm_search_by_sim3", "refm_hamming256"):
+        assert getattr(L, name) is not None
+    a = np.arange(32, dtype=np.uint8)
+    assert L.refm_hamming256(a.ctypes.data_as(C.c_void_p), (a ^ 1).astype(np.uint8).ctypes.data_as(C.c_void_p)) == 32      # host inline
+
