@@ -232,3 +232,14 @@ def test_fisheye_front_camera(oracle):
             prev = F
     pipe.close()
 
+
+@pytest.mark.parametrize("mode", ["dev", "host"])
+def test_soak_repeated_steps_reproduce(mode):
+    """tools/soak.py in short form: four input batches cycled for 40 steps (device-resident or through the asynchronous
+    host path with three steps in flight); every step must reproduce the first pass over the same (batch, predecessor)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "soak.py"), "40", "12", mode], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "mismatches: 0" in r.stdout
+
