@@ -1,10 +1,13 @@
-// Drop-in body for Frame::AssignFeaturesToGrid (src/Frame.cc:381-411): both grids (64x48 over the undistorted front
+// Drop-in bodies for two Frame methods.
+// Frame::AssignFeaturesToGrid (src/Frame.cc:381-411): both grids (64x48 over the undistorted front
 // keypoints, 32x32 over the bird keypoints) are bucketed on the device (fbe_grid_assign -> CSR) and copied into the
 // reference's mGrid / mGridBirdview vectors, so that GetFeaturesInArea[Birdview] and every other reader see what the
 // reference's loop would have produced (same cells, same in-cell order).  Compiled INSIDE the reference tree in place of
 // that one method; in this repository it is built against the reference's own Frame.h with the test shim
 // oracle/cvshim_m (oracle/Makefile target `dropinmatch`) and checked on the GPU by tests/test_gpu_dropin_match.py.
 // PosInGrid / PosInGridBirdview (:548-570) stay as they are: other code calls them per keypoint.
+// Frame::UndistortKeyPoints (:638-669): the cv::fisheye::undistortPoints call on the keypoint positions becomes
+// fbe_undistort_keypoints (same K, same mDistCoef, P = K); the k1 == 0 copy stays.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -40,6 +43,21 @@ void Frame::AssignFeaturesToGrid() {
     // PosInGridBirdview: round(x * mfGridElementWidthInvBirdview), no origin shift (:560-570)
     fill_grid<FRAME_GRID_BIRD, FRAME_GRID_BIRD>(mvKeysBird, Nbird, 0.f, 0.f, mfGridElementWidthInvBirdview, mfGridElementHeightInvBirdview,
                                                 mGridBirdview);
+}
+
+void Frame::UndistortKeyPoints() {
+    if (mDistCoef.at<float>(0) == 0.0) {
+        mvKeysUn = mvKeys;
+        return;
+    }
+    const float K[4] = {mK.at<float>(0, 0), mK.at<float>(1, 1), mK.at<float>(0, 2), mK.at<float>(1, 2)};
+    const float D[4] = {mDistCoef.at<float>(0), mDistCoef.at<float>(1), mDistCoef.at<float>(2), mDistCoef.at<float>(3)};
+    mvKeysUn.resize(N);
+    if (N > 0 && fbe_undistort_keypoints(reinterpret_cast<const fbe_keypoint*>(mvKeys.data()), N, K, D, 0,
+                                         reinterpret_cast<fbe_keypoint*>(mvKeysUn.data())) != FBE_OK) {
+        fprintf(stderr, "Frame::UndistortKeyPoints (fbe-b200): %s\n", fbe_last_error());
+        abort();
+    }
 }
 
 }  // namespace ORB_SLAM2

@@ -627,6 +627,22 @@ void refm_check_models(const Kp* k1, int n1, const Kp* k2, int n2, const int32_t
     }
 }
 
+#ifdef FBE_DROPIN
+// Frame::UndistortKeyPoints through the drop-in body (host/Frame_fbe.cc); only the drop-in build has it -- the reference's
+// own body calls cv::fisheye::undistortPoints, which no shim here provides (its arithmetic is pinned by tests/test_undistort.py).
+void refm_undistort_keypoints(const Kp* kps, int n, const float* K, const float* D, Kp* out) {
+    Frame F;
+    F.N = n;
+    F.mvKeys = to_kps(kps, n);
+    F.mK = cv::Mat::eye(3, 3, CV_32F);
+    F.mK.at<float>(0, 0) = K[0]; F.mK.at<float>(1, 1) = K[1]; F.mK.at<float>(0, 2) = K[2]; F.mK.at<float>(1, 2) = K[3];
+    F.mDistCoef = cv::Mat(4, 1, CV_32F);
+    for (int i = 0; i < 4; ++i) F.mDistCoef.at<float>(i) = D[i];
+    F.UndistortKeyPoints();
+    if (n) std::memcpy(out, F.mvKeysUn.data(), (size_t)n * sizeof(Kp));
+}
+#endif
+
 int refm_hamming256(const uint8_t* a, const uint8_t* b) { return ORBmatcher::DescriptorDistance(desc_row(a), desc_row(b)); }
 
 }  // extern "C"

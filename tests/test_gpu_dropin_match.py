@@ -47,3 +47,26 @@ def test_dropin_class_equals_verbatim_reference_live(oracle, dropin, seed):
     for k, v in want.items():
         assert np.array_equal(got[k], v, equal_nan=True), k
 
+
+def test_dropin_frame_undistort_keypoints(oracle, dropin):
+    """Frame::UndistortKeyPoints through host/Frame_fbe.cc on a real Frame object: mvKeysUn equals the oracle (which is pinned
+    to cv2's fisheye.undistortPoints); k1 == 0 copies the keypoints."""
+    import ctypes as C
+    from conftest import make_kps
+    rng = np.random.default_rng(12)
+    n = 3000
+    kps = make_kps(rng.uniform(0, 960, n).astype(np.float32), rng.uniform(0, 600, n).astype(np.float32),
+                   rng.integers(0, 8, n).astype(np.int32), rng.uniform(0, 360, n).astype(np.float32))
+    K = np.float32([348.5, 347.0, 480.0, 302.0])
+    for D in (np.float32([-0.0488316, 0.000298406, -0.00591118, 0.00193258]), np.float32([0, 0.1, 0, 0])):
+        out = np.empty_like(kps)
+        dropin.L.refm_undistort_keypoints(kps.ctypes.data_as(C.c_void_p), n, K.ctypes.data_as(C.c_void_p), D.ctypes.data_as(C.c_void_p),
+                                          out.ctypes.data_as(C.c_void_p))
+        if D[0] == 0:
+            assert out.tobytes() == kps.tobytes()
+            continue
+        want = oracle.fisheye_undistort(np.stack([kps["x"], kps["y"]], 1), K, D)
+        assert np.array_equal(out["x"], want[:, 0]) and np.array_equal(out["y"], want[:, 1])
+        for f in ("size", "angle", "response", "octave", "class_id"):
+            assert np.array_equal(out[f], kps[f])
+
