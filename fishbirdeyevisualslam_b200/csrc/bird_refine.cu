@@ -1,0 +1,258 @@
+// The per-keypoint steps of the reference's bird-view feature path between detection and description:
+//   Frame::GuidenceKeyBirdPts / nearEdges  (src/Frame.cc:671-684, 717-739): keep a keypoint when any pixel of the ~21x21 window
+//     of mBirdviewContourICP around it is >= 10 (edge or free space), in input order;
+//   cv::cornerSubPix(mBirdviewImg, pts, Size(5,5), Size(-1,-1), {EPS+MAX_ITER, 40, 0.001})  (src/Frame.cc:349-352).
+// Both are one warp per keypoint.  nearEdges: the lanes stride over the window, one ballot per 32 pixels, early exit.
+// cornerSubPix: per iteration the lanes sample the (2*hw+3) x (2*hh+3) bilinear patch into shared memory (cv::getRectSubPix
+// arithmetic), compute the five per-pixel terms of the normal equations in double, and five lanes add one accumulator each IN
+// PIXEL ORDER -- the reference's sequential double sums, so the iteration count and the float result are those of the CPU code
+// (pinned to cv2 4.13.0 for windows inside the image; tests/test_bird_refine.py).  The exp() weights come from the host so that
+// they are glibc's, like the reference's.
+#include <cfloat>
+#include <cmath>
+#include <vector>
+#include "fbe_internal.cuh"
+
+namespace fbe {
+
+constexpr int kWarpsPerCta = 4;
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_near_edges(const uint8_t* __restrict__ contour, int rows, int cols, size_t step, const fbe_keypoint* __restrict__ kps, int n,
+             uint8_t* __restrict__ keep) {
+    const int k = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= n) return;
+    const float r = 10.f, x = kps[k].x, y = kps[k].y;
+    const float pt1x = (x - r) > 0 ? (x - r) : 0.f, pt1y = (y - r) > 0 ? (y - r) : 0.f;
+    const float pt2x = (x + r) < (float)cols ? (x + r) : (float)cols, pt2y = (y + r) < (float)rows ? (y + r) : (float)rows;
+    bool hit = false;
+    if (pt1x < pt2x && pt1y < pt2y) {
+        // `size_t row = pt1x; row < pt2x` : truncation below, first integer not below pt2x above
+        const int r0 = (int)pt1x, r1 = (int)ceilf(pt2x), c0 = (int)pt1y, c1 = (int)ceilf(pt2y);
+        const int nc = c1 - c0, total = (r1 - r0) * nc;
+        const size_t limit = (size_t)rows * step;
+        for (int base = 0; base < total; base += 32) {
+            const int i = base + lane;
+            bool h = false;
+            if (i < total) {
+                const size_t a = (size_t)(r0 + i / nc) * step + (size_t)(c0 + i % nc);   // at<uchar>(row = x range, col = y range)
+                h = a < limit && contour[a] >= 10;
+            }
+            if (__ballot_sync(0xffffffffu, h)) { hit = true; break; }
+        }
+    }
+    if (lane == 0) keep[k] = hit ? 1 : 0;
+}
+
+// ordered compaction of the kept keypoints (mvKeysBird.push_back in input order); n is a few thousand: one CTA
+__global__ void __launch_bounds__(1024)
+k_compact_kept(const fbe_keypoint* __restrict__ kps, const uint8_t* __restrict__ keep, int n, fbe_keypoint* __restrict__ out, int* __restrict__ n_out) {
+    __shared__ int warp_sum[32];
+    __shared__ int running;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const bool kp = i < n && keep[i];
+        const unsigned m = __ballot_sync(0xffffffffu, kp);
+        if (lane == 0) warp_sum[w] = __popc(m);
+        __syncthreads();
+        int before = running;
+        for (int j = 0; j < w; ++j) before += warp_sum[j];
+        if (kp) out[before + __popc(m & ((1u << lane) - 1u))] = kps[i];
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int j = 0; j < 32; ++j) t += warp_sum[j]; running += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_out = running;
+}
+
+// one bilinear sample of cv::getRectSubPix(8U -> 32F): window origin (ipx, ipy), fractions folded into a11..b2
+__device__ __forceinline__ float rect_sample(const uint8_t* __restrict__ img, int rows, int cols, size_t step, int ipx, int ipy, int i, int j,
+                                             bool inside, int rx, int rw, float a11, float a12, float a21, float a22, float b1, float b2) {
+    if (inside) {
+        const uint8_t* p = img + (size_t)(ipy + i) * step + (ipx + j);
+        return ((float)p[0] * a11 + (float)p[1] * a12) + ((float)p[step] * a21 + (float)p[step + 1] * a22);
+    }
+    // window crosses the border: rows clamp (replicated), columns left of rx / right of rw take the edge column
+    const int yt = min(max(ipy + i, 0), rows - 1), yb = min(max(ipy + i + 1, 0), rows - 1);
+    const uint8_t* pt = img + (size_t)yt * step;
+    const uint8_t* pb = img + (size_t)yb * step;
+    if (j < rx || j >= rw) {
+        const int c = j < rx ? max(ipx, 0) : cols - 1;
+        return (float)pt[c] * b1 + (float)pb[c] * b2;
+    }
+    const int c = ipx + j;
+    return ((float)pt[c] * a11 + (float)pt[c + 1] * a12) + ((float)pb[c] * a21 + (float)pb[c + 1] * a22);
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_corner_subpix(const uint8_t* __restrict__ img, int rows, int cols, size_t step, fbe_keypoint* __restrict__ kps, const int* __restrict__ n_ptr,
+                int n_max, int hw, int hh, int max_iter, double eps2, const float* __restrict__ mask, int* __restrict__ iters) {
+    extern __shared__ double smem_d[];
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * kWarpsPerCta + w;
+    if (k >= n) return;
+    const int ww = 2 * hw + 1, wh = 2 * hh + 1, pw = ww + 2, ph = wh + 2, nq = ww * wh;
+    double* terms = smem_d + (size_t)w * (5 * nq + (pw * ph + 1) / 2);       // [5][nq] doubles, then the float patch
+    float* patch = reinterpret_cast<float*>(terms + 5 * nq);
+
+    const float tx = kps[k].x, ty = kps[k].y;
+    float ix = tx, iy = ty;
+    int iter = 0;
+    double err = 0;
+    do {
+        // ---- getRectSubPix(img, (pw, ph), (ix, iy)) -> patch
+        const float ox = ix - (pw - 1) * 0.5f, oy = iy - (ph - 1) * 0.5f;
+        const int ipx = (int)floorf(ox), ipy = (int)floorf(oy);
+        const float a = ox - (float)ipx, b = oy - (float)ipy;
+        const float a11 = (1.f - a) * (1.f - b), a12 = a * (1.f - b), a21 = (1.f - a) * b, a22 = a * b, b1 = 1.f - b, b2 = b;
+        const bool inside = 0 <= ipx && ipx < cols - pw && 0 <= ipy && ipy < rows - ph;
+        int rx = 0, rw = pw;
+        if (!inside) {
+            if (ipx < 0) rx = min(-ipx, pw);
+            if (!(ipx < cols - pw)) rw = max(cols - ipx - 1, 0);
+        }
+        for (int e = lane; e < pw * ph; e += 32)
+            patch[e] = rect_sample(img, rows, cols, step, ipx, ipy, e / pw, e % pw, inside, rx, rw, a11, a12, a21, a22, b1, b2);
+        __syncwarp();
+        // ---- per-pixel terms of the 2x2 normal equations (double, like the reference)
+        for (int q = lane; q < nq; q += 32) {
+            const int i = q / ww, j = q % ww;
+            const float* sp = patch + (i + 1) * pw + (j + 1);
+            const double m = (double)mask[q];
+            const double tgx = (double)(sp[1] - sp[-1]);
+            const double tgy = (double)(sp[pw] - sp[-pw]);
+            const double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
+            const double px = (double)(j - hw), py = (double)(i - hh);
+            terms[q] = gxx; terms[nq + q] = gxy; terms[2 * nq + q] = gyy;
+            terms[3 * nq + q] = gxx * px + gxy * py;
+            terms[4 * nq + q] = gxy * px + gyy * py;
+        }
+        __syncwarp();
+        // ---- five lanes add one accumulator each, in pixel order (sequential sums of the reference)
+        double acc = 0;
+        if (lane < 5) {
+            const double* t = terms + lane * nq;
+            for (int q = 0; q < nq; ++q) acc += t[q];
+        }
+        const double sa = __shfl_sync(0xffffffffu, acc, 0), sb = __shfl_sync(0xffffffffu, acc, 1), sc = __shfl_sync(0xffffffffu, acc, 2);
+        const double bb1 = __shfl_sync(0xffffffffu, acc, 3), bb2 = __shfl_sync(0xffffffffu, acc, 4);
+        const double det = sa * sc - sb * sb;
+        if (fabs(det) <= DBL_EPSILON * DBL_EPSILON) break;
+        const double scale = 1.0 / det;
+        const float nx = (float)((double)ix + sc * scale * bb1 - sb * scale * bb2);
+        const float ny = (float)((double)iy - sb * scale * bb1 + sa * scale * bb2);
+        err = (double)(nx - ix) * (double)(nx - ix) + (double)(ny - iy) * (double)(ny - iy);
+        ix = nx; iy = ny;
+        if (ix < 0 || ix >= (float)cols || iy < 0 || iy >= (float)rows) { ++iter; break; }
+    } while (++iter < max_iter && err > eps2);
+    if (fabsf(ix - tx) > (float)hw || fabsf(iy - ty) > (float)hh) { ix = tx; iy = ty; }   // moved too far: keep the input point
+    if (lane == 0) {
+        kps[k].x = ix; kps[k].y = iy;
+        if (iters) iters[k] = iter;
+    }
+}
+
+static void subpix_mask(int hw, int hh, std::vector<float>& mask) {
+    const int ww = 2 * hw + 1, wh = 2 * hh + 1;
+    mask.resize((size_t)ww * wh);
+    for (int i = 0; i < wh; ++i) {
+        const float y = (float)(i - hh) / hh;
+        const float vy = std::exp(-y * y);
+        for (int j = 0; j < ww; ++j) {
+            const float x = (float)(j - hw) / hw;
+            mask[(size_t)i * ww + j] = (float)(vy * std::exp(-x * x));
+        }
+    }
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+static cudaError_t upload_image(DevBuf& d, const uint8_t* img, int rows, int cols, size_t step) {
+    cudaError_t e = d.alloc((size_t)rows * cols);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy2D(d.p, (size_t)cols, img, step, (size_t)cols, (size_t)rows, cudaMemcpyHostToDevice);
+}
+
+}  // namespace fbe
+
+using namespace fbe;
+
+#define FBE_TRY(expr)                                                                        \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); return FBE_E_CUDA; } \
+    } while (0)
+
+extern "C" {
+
+int fbe_bird_refine(const uint8_t* contour, size_t contour_step, const uint8_t* img, size_t img_step, int32_t rows, int32_t cols,
+                    const fbe_keypoint* kps, int32_t n, int32_t half_w, int32_t half_h, int32_t max_iter, double eps, int32_t device,
+                    uint8_t* keep, fbe_keypoint* out_kps, int32_t* n_out, int32_t* iters) {
+    if (n < 0 || rows <= 0 || cols <= 0 || (!contour && !img) || !n_out || (n > 0 && (!kps || !out_kps))) return FBE_E_INVALID;
+    if (contour && contour_step < (size_t)cols) return FBE_E_INVALID;
+    if (img && (img_step < (size_t)cols || half_w < 1 || half_h < 1 || half_w > 10 || half_h > 10)) return FBE_E_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_error("no CUDA device: this library has no CPU path"); return FBE_E_CUDA; }
+    FBE_TRY(cudaSetDevice(device));
+    *n_out = 0;
+    if (n == 0) return FBE_OK;
+    DevBuf d_contour, d_img, d_in, d_out, d_keep, d_n, d_mask, d_iters;
+    FBE_TRY(d_in.alloc((size_t)n * sizeof(fbe_keypoint)));
+    FBE_TRY(d_out.alloc((size_t)n * sizeof(fbe_keypoint)));
+    FBE_TRY(d_keep.alloc((size_t)n));
+    FBE_TRY(d_n.alloc(sizeof(int)));
+    FBE_TRY(cudaMemcpy(d_in.p, kps, (size_t)n * sizeof(fbe_keypoint), cudaMemcpyHostToDevice));
+    const int ctas = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    fbe_keypoint* d_cur = d_in.as<fbe_keypoint>();
+    const int* d_count = nullptr;
+    if (contour) {          // GuidenceKeyBirdPts: filter + ordered compaction
+        FBE_TRY(upload_image(d_contour, contour, rows, cols, contour_step));
+        k_near_edges<<<ctas, kWarpsPerCta * 32>>>(d_contour.as<uint8_t>(), rows, cols, (size_t)cols, d_cur, n, d_keep.as<uint8_t>());
+        k_compact_kept<<<1, 1024>>>(d_cur, d_keep.as<uint8_t>(), n, d_out.as<fbe_keypoint>(), d_n.as<int>());
+        count_launch(2);
+        d_cur = d_out.as<fbe_keypoint>();
+        d_count = d_n.as<int>();
+    }
+    if (img) {              // cornerSubPix on the kept points (count read on the device: no host round trip in between)
+        FBE_TRY(upload_image(d_img, img, rows, cols, img_step));
+        std::vector<float> mask;
+        subpix_mask(half_w, half_h, mask);
+        FBE_TRY(d_mask.alloc(mask.size() * sizeof(float)));
+        FBE_TRY(cudaMemcpy(d_mask.p, mask.data(), mask.size() * sizeof(float), cudaMemcpyHostToDevice));
+        FBE_TRY(d_iters.alloc((size_t)n * sizeof(int)));
+        FBE_TRY(cudaMemset(d_iters.p, 0, (size_t)n * sizeof(int)));
+        if (max_iter < 1) max_iter = 1;
+        if (max_iter > 100) max_iter = 100;
+        double e2 = eps > 0 ? eps : 0;
+        e2 *= e2;
+        const int nq = (2 * half_w + 1) * (2 * half_h + 1), np = (2 * half_w + 3) * (2 * half_h + 3);
+        const size_t smem = (size_t)kWarpsPerCta * (5 * nq + (np + 1) / 2) * sizeof(double);
+        FBE_TRY(cudaFuncSetAttribute(k_corner_subpix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_corner_subpix<<<ctas, kWarpsPerCta * 32, smem>>>(d_img.as<uint8_t>(), rows, cols, (size_t)cols, d_cur, d_count, n, half_w, half_h,
+                                                           max_iter, e2, d_mask.as<float>(), d_iters.as<int>());
+        count_launch();
+    }
+    FBE_TRY(cudaGetLastError());
+    int kept = n;
+    if (contour) {
+        FBE_TRY(cudaMemcpy(&kept, d_n.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (keep) FBE_TRY(cudaMemcpy(keep, d_keep.p, (size_t)n, cudaMemcpyDeviceToHost));
+    } else if (keep) {
+        for (int i = 0; i < n; ++i) keep[i] = 1;
+    }
+    FBE_TRY(cudaMemcpy(out_kps, d_cur, (size_t)kept * sizeof(fbe_keypoint), cudaMemcpyDeviceToHost));
+    if (iters && img) FBE_TRY(cudaMemcpy(iters, d_iters.p, (size_t)kept * sizeof(int), cudaMemcpyDeviceToHost));
+    *n_out = kept;
+    return FBE_OK;
+}
+
+}  // extern "C"

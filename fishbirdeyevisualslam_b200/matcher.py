@@ -70,6 +70,25 @@ def UndistortKeyPoints(kps: np.ndarray, K, D, device: int = 0) -> np.ndarray:
     return out
 
 
+def BirdGuideRefine(contour, img, kps: np.ndarray, half_win=(5, 5), max_iter: int = 40, eps: float = 0.001, device: int = 0):
+    """Frame::GuidenceKeyBirdPts (Frame.cc:671-684, nearEdges :717-739) + cv::cornerSubPix (Frame.cc:345-352) on the device.
+    contour / img: 8-bit images of one size (either may be None to skip that step).
+    -> (keep u8[n], kept keypoints in input order with refined pt, iterations per kept point)."""
+    L = _lib.load()
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    ref = contour if contour is not None else img
+    rows, cols = ref.shape
+    n = len(kps)
+    keep = np.zeros(n, np.uint8); out = np.empty_like(kps); iters = np.zeros(n, np.int32); n_out = C.c_int32(0)
+    cp = C.c_void_p(contour.ctypes.data) if contour is not None else None
+    ip = C.c_void_p(img.ctypes.data) if img is not None else None
+    check(L.fbe_bird_refine(cp, C.c_size_t(contour.strides[0] if contour is not None else 0), ip,
+                            C.c_size_t(img.strides[0] if img is not None else 0), C.c_int32(rows), C.c_int32(cols), ptr(kps),
+                            C.c_int32(n), C.c_int32(half_win[0]), C.c_int32(half_win[1]), C.c_int32(max_iter), C.c_double(eps),
+                            C.c_int32(device), ptr(keep), ptr(out), C.byref(n_out), ptr(iters)))
+    return keep, out[:n_out.value].copy(), iters[:n_out.value].copy()
+
+
 def isInFrustum(view, pos, normal, min_dist, max_dist, viewing_cos_limit: float, device: int = 0):
     """Frame::isInFrustum (Frame.cc:435-491) for n map points at once.  `view` is a _lib.FrustumView (or anything with the
     same ctypes layout); pos / normal n x 3, min_dist / max_dist = mfMinDistance / mfMaxDistance.

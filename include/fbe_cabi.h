@@ -182,6 +182,26 @@ FBE_API int fbe_undistort_keypoints(const fbe_keypoint* kps, int32_t n, const fl
  * image corners (or the image rectangle when D[0] == 0). */
 FBE_API int fbe_image_bounds(int32_t cols, int32_t rows, const float K[4], const float D[4], int32_t device, float bounds[4]);
 
+/* ---- Bird-view keypoint guidance + sub-pixel refinement (next row f-3, the part between detect and compute) ------------ */
+/* Frame::GuidenceKeyBirdPts / Frame::nearEdges, src/Frame.cc:671-684, 717-739, followed by
+ * cv::cornerSubPix(mBirdviewImg, pts, Size(half_w, half_h), Size(-1,-1), TermCriteria(EPS+MAX_ITER, max_iter, eps)),
+ * src/Frame.cc:345-352 (the reference passes 5, 5, 40, 0.001), in one call with no host round trip in between.
+ *   contour : mBirdviewContourICP (8-bit, rows x cols, contour_step bytes per row); NULL skips the filter (all kept).
+ *             A keypoint is kept when any pixel of the window [x-10, x+10) x [y-10, y+10) (clipped; float -> size_t
+ *             truncation below, `i < bound` compared in float above) is >= 10.  The reference indexes the window as
+ *             at<uchar>(row = x range, col = y range) -- x and y swapped -- and so does this; an address beyond the image
+ *             (possible only for non-square images, undefined in the reference) reads as 0.
+ *   img     : mBirdviewImg (8-bit, same size, img_step bytes per row); NULL skips the refinement.  half_w, half_h in 1..10.
+ *             cornerSubPix is OpenCV arithmetic, pinned to 4.13.0: float results equal cv2's bit for bit while the sampled
+ *             window stays inside the image (always the case behind cv::ORB's 31-pixel edge threshold); near the border the
+ *             replicated samples may differ from cv2 by one float ulp, the stated bar there is 1e-3 px.
+ * Output: keep[n] (may be NULL) = nearEdges per input keypoint; out_kps[0 .. *n_out) = the kept keypoints in input order
+ * (mvKeysBird) with pt refined and every other field untouched; iters[0 .. *n_out) (may be NULL) = gradient solves per
+ * kept point.  out_kps needs room for n records. */
+FBE_API int fbe_bird_refine(const uint8_t* contour, size_t contour_step, const uint8_t* img, size_t img_step, int32_t rows,
+                            int32_t cols, const fbe_keypoint* kps, int32_t n, int32_t half_w, int32_t half_h, int32_t max_iter,
+                            double eps, int32_t device, uint8_t* keep, fbe_keypoint* out_kps, int32_t* n_out, int32_t* iters);
+
 /* ---- Frame grid -------------------------------------------------------------------------------- */
 /* Frame::AssignFeaturesToGrid / PosInGrid / PosInGridBirdview, src/Frame.cc:381-411,548-570.
  * cell = (round((x-min_x)*inv_w), round((y-min_y)*inv_h)), dropped when outside gcols x grows.

@@ -491,6 +491,32 @@ def fisheye_undistort(pts, K, D):
     return out
 
 
+def bird_near_edges(contour, xy):
+    """Frame::nearEdges (Frame.cc:717-739) for points xy float32 [n,2] -> u8[n]."""
+    contour = np.asarray(contour); xy = np.ascontiguousarray(xy, np.float32)
+    assert contour.dtype == np.uint8 and contour.strides[1] == 1
+    keep = np.zeros(len(xy), np.uint8)
+    lib().orc_bird_near_edges(_p(contour), contour.shape[0], contour.shape[1], contour.strides[0], _p(xy), len(xy), _p(keep))
+    return keep
+
+
+def corner_subpix(img, xy, half_win=(5, 5), max_iter=40, eps=0.001):
+    """cv::cornerSubPix(img, xy, half_win, (-1,-1), (EPS+MAX_ITER, max_iter, eps)) restated (OpenCV 4.13) -> (xy', iterations)."""
+    img = np.asarray(img); out = np.array(xy, np.float32, order="C")
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    it = np.zeros(len(out), np.int32)
+    lib().orc_corner_subpix(_p(img), img.shape[0], img.shape[1], img.strides[0], _p(out), len(out), int(half_win[0]), int(half_win[1]),
+                            int(max_iter), C.c_double(eps), _p(it))
+    return out, it
+
+
+def rect_subpix(img, cx, cy, ww, wh):
+    """cv::getRectSubPix(img u8, (ww, wh), (cx, cy), patchType=CV_32F) restated."""
+    img = np.asarray(img); out = np.zeros((wh, ww), np.float32)
+    lib().orc_rect_subpix(_p(img), img.shape[0], img.shape[1], img.strides[0], C.c_float(cx), C.c_float(cy), ww, wh, _p(out))
+    return out
+
+
 # ---- the reference's OWN matcher (src/ORBmatcher.cc compiled verbatim, oracle/_ref/libfbe_refmatch.so) -----------------
 _refm = None
 

@@ -1,0 +1,151 @@
+"""Row f-3, the per-keypoint part: Frame::GuidenceKeyBirdPts / nearEdges (src/Frame.cc:671-684, 717-739) and the
+cv::cornerSubPix call of src/Frame.cc:345-352.
+CPU: the oracle's cornerSubPix / getRectSubPix restatement equals cv2 4.13.0 bit for bit on the committed known answers
+(tests/golden/bird_refine.npz, tools/gen_golden_bird_refine.py) for points at least 31 px inside the image (cv::ORB's edge
+threshold -- the only points the reference ever refines); nearEdges equals a literal Python transcription of the reference loop.
+GPU: fbe_bird_refine equals the oracle bit for bit (keep flags, order, refined coordinates, iteration counts), border windows
+included.  Stated floating-point bar for this row: 1e-3 px; in practice the results are identical."""
+import os
+
+import numpy as np
+import pytest
+
+import bird_scenes as S
+from fishbirdeyevisualslam_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bird_refine.npz")
+TOL_PX = 1e-3
+
+
+def test_oracle_subpix_equals_cv2_golden(oracle):
+    g = np.load(GOLD)
+    assert str(g["cv2_version"]) == "4.13.0"
+    for i in range(int(g["ncases"])):
+        img = S.bird_image(i)
+        assert synth.crc(img) == int(g[f"crc{i}"])
+        got, it = oracle.corner_subpix(img, g[f"pts{i}"])
+        assert got.tobytes() == g[f"out{i}"].tobytes()
+        assert it.min() >= 1 and it.max() <= 40
+        for (x, y), patch in zip(g[f"rc{i}"], g[f"rp{i}"]):
+            assert oracle.rect_subpix(img, float(x), float(y), 13, 13).tobytes() == patch.tobytes()
+
+
+def test_oracle_subpix_equals_cv2_live(oracle):
+    cv2 = pytest.importorskip("cv2")
+    crit = (cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_MAX_ITER, 40, 0.001)
+    for seed, shape in ((11, (384, 384)), (12, (200, 320))):
+        img = S.bird_image(seed, *shape)
+        pts = S.corner_points(img, seed, 600)
+        ref = cv2.cornerSubPix(img, pts.copy().reshape(-1, 1, 2), (5, 5), (-1, -1), crit).reshape(-1, 2)
+        got, _ = oracle.corner_subpix(img, pts)
+        assert got.tobytes() == ref.tobytes()
+        # other window sizes / criteria go through the same code
+        ref = cv2.cornerSubPix(img, pts.copy().reshape(-1, 1, 2), (3, 4), (-1, -1), (crit[0], 7, 0.01)).reshape(-1, 2)
+        got, _ = oracle.corner_subpix(img, pts, (3, 4), 7, 0.01)
+        assert got.tobytes() == ref.tobytes()
+        # windows crossing the border: replicated samples may differ from cv2 by an ulp; the bar there is TOL_PX unless
+        # the iteration is chaotic (a point that leaves its window is reset to the input by both)
+        b = S.border_points(*shape, seed, 100)
+        ref = cv2.cornerSubPix(img, b.copy().reshape(-1, 1, 2), (5, 5), (-1, -1), crit).reshape(-1, 2)
+        got, _ = oracle.corner_subpix(img, b)
+        assert (np.abs(got - ref).max(1) <= TOL_PX).mean() > 0.9
+
+
+def _near_edges_py(contour, x, y):
+    """src/Frame.cc:717-739 transcribed literally (float32 arithmetic, truncating size_t loop variables)."""
+    f = np.float32
+    r = 10
+    rows, cols = contour.shape
+    pt1x = f(x) - f(r) if f(x) - f(r) > 0 else f(0)
+    pt1y = f(y) - f(r) if f(y) - f(r) > 0 else f(0)
+    pt2x = f(x) + f(r) if f(x) + f(r) < cols else f(cols)
+    pt2y = f(y) + f(r) if f(y) + f(r) < rows else f(rows)
+    flat = contour.reshape(-1)
+    row = int(pt1x)
+    while f(row) < pt2x:
+        col = int(pt1y)
+        while f(col) < pt2y:
+            a = row * contour.strides[0] + col              # at<uchar>(row, col): row from the x range, col from the y range
+            v = flat[a] if a < flat.size else 0
+            if v >= 10:
+                return True
+            col += 1
+        row += 1
+    return False
+
+
+def test_oracle_near_edges_equals_transcription(oracle):
+    for seed, shape in ((0, (384, 384)), (1, (384, 384)), (2, (300, 260))):
+        c = S.contour_image(seed, *shape)
+        rng = np.random.default_rng(seed)
+        xy = np.stack([rng.uniform(-15, shape[1] + 15, 400), rng.uniform(-15, shape[0] + 15, 400)], 1).astype(np.float32)
+        xy[:50] = np.round(xy[:50])
+        keep = oracle.bird_near_edges(c, xy)
+        want = np.array([_near_edges_py(c, x, y) for x, y in xy], np.uint8)
+        assert np.array_equal(keep, want)
+        assert 0 < keep.sum() < len(keep)
+    # x / y swap is observable: a single marked pixel at (row 40, col 200) attracts keypoints near x = 40, y = 200
+    c = np.zeros((384, 384), np.uint8); c[40, 200] = 200
+    assert list(oracle.bird_near_edges(c, np.float32([[40, 200], [200, 40]]))) == [1, 0]
+
+
+@pytest.mark.gpu
+def test_gpu_bird_refine_equals_oracle(oracle, fbe):
+    from fishbirdeyevisualslam_b200.matcher import BirdGuideRefine
+    g = np.load(GOLD)
+    for seed, shape in ((0, (384, 384)), (1, (384, 384)), (2, (384, 384)), (5, (300, 260))):
+        img, contour = S.bird_image(seed, *shape), S.contour_image(seed, *shape)
+        xy = np.concatenate([S.corner_points(img, seed, 1500), S.border_points(*shape, seed, 300)])
+        if seed < 3:
+            xy = np.concatenate([g[f"pts{seed}"], S.border_points(*shape, seed, 300)])
+        kin = S.as_kps(xy)
+        keep, kout, it = BirdGuideRefine(contour, img, kin)
+        okeep = oracle.bird_near_edges(contour, xy)
+        assert np.array_equal(keep, okeep) and 0 < keep.sum() < len(keep)
+        sel = np.flatnonzero(okeep)
+        oxy, oit = oracle.corner_subpix(img, xy[sel])
+        got = np.stack([kout["x"], kout["y"]], 1)
+        assert len(kout) == len(sel)
+        assert np.abs(got - oxy).max() <= TOL_PX
+        assert got.tobytes() == oxy.tobytes() and np.array_equal(it, oit)
+        for f in ("size", "angle", "response", "octave", "class_id"):            # records kept whole, in input order
+            assert np.array_equal(kout[f], kin[f][sel])
+        # refinement alone (no contour): every point, and equal to cv2's committed answers on the ORB-range points
+        keep2, kall, it2 = BirdGuideRefine(None, img, kin)
+        oall, oit2 = oracle.corner_subpix(img, xy)
+        assert keep2.all() and np.stack([kall["x"], kall["y"]], 1).tobytes() == oall.tobytes() and np.array_equal(it2, oit2)
+        if seed < 3:
+            n = len(g[f"pts{seed}"])
+            assert np.stack([kall["x"], kall["y"]], 1)[:n].tobytes() == g[f"out{seed}"].tobytes()
+        # guidance alone (no image): kept records unchanged
+        keep3, kg, _ = BirdGuideRefine(contour, None, kin)
+        assert np.array_equal(keep3, okeep) and kg.tobytes() == kin[sel].tobytes()
+    # other window / criteria; strided (ROI) inputs
+    big = np.zeros((400, 512), np.uint8); big[5:389, 100:484] = S.bird_image(3)
+    roi = big[5:389, 100:484]
+    xy = S.corner_points(np.ascontiguousarray(roi), 3, 500)
+    _, k, it = BirdGuideRefine(None, roi, S.as_kps(xy), (3, 4), 7, 0.01)
+    o, oit = oracle.corner_subpix(np.ascontiguousarray(roi), xy, (3, 4), 7, 0.01)
+    assert np.stack([k["x"], k["y"]], 1).tobytes() == o.tobytes() and np.array_equal(it, oit)
+
+
+@pytest.mark.gpu
+def test_gpu_bird_refine_edge_cases(oracle, fbe):
+    from fishbirdeyevisualslam_b200._lib import FbeError
+    from fishbirdeyevisualslam_b200.matcher import BirdGuideRefine
+    img, contour = S.bird_image(4), S.contour_image(4)
+    keep, k, it = BirdGuideRefine(contour, img, S.as_kps(np.zeros((0, 2), np.float32)))
+    assert len(keep) == 0 and len(k) == 0
+    # nothing kept / everything kept
+    far = S.as_kps(np.float32([[-100, -100], [1000, 50], [50, 1000]]))
+    keep, k, _ = BirdGuideRefine(np.zeros_like(contour), img, S.as_kps(S.corner_points(img, 4, 64)))
+    assert keep.sum() == 0 and len(k) == 0
+    keep, k, _ = BirdGuideRefine(np.full_like(contour, 10), img, far)
+    assert list(keep) == list(oracle.bird_near_edges(np.full_like(contour, 10), np.stack([far["x"], far["y"]], 1)))
+    # a flat image: singular normal equations, points unchanged after one solve attempt
+    flat = np.full((384, 384), 77, np.uint8)
+    xy = S.corner_points(img, 4, 64)
+    _, k, it = BirdGuideRefine(None, flat, S.as_kps(xy))
+    assert np.stack([k["x"], k["y"]], 1).tobytes() == xy.tobytes() and (it == 0).all()
+    with pytest.raises(FbeError):
+        BirdGuideRefine(None, img, S.as_kps(xy), (0, 5))
