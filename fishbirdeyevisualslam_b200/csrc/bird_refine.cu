@@ -136,7 +136,17 @@ k_corner_subpix(const uint8_t* __restrict__ img, int rows, int cols, size_t step
         double acc = 0;
         if (lane < 5) {
             const double* t = terms + lane * nq;
-            for (int q = 0; q < nq; ++q) acc += t[q];
+            // the adds form one dependent chain (that IS the reference order); unrolling lets the shared-memory loads of the
+            // next terms issue ahead of it, so the chain runs at the DADD latency instead of load + add
+#pragma unroll 1
+            for (int q0 = 0; q0 + 11 <= nq; q0 += 11) {
+                double v[11];
+#pragma unroll
+                for (int u = 0; u < 11; ++u) v[u] = t[q0 + u];
+#pragma unroll
+                for (int u = 0; u < 11; ++u) acc += v[u];
+            }
+            for (int q = nq - nq % 11; q < nq; ++q) acc += t[q];
         }
         const double sa = __shfl_sync(0xffffffffu, acc, 0), sb = __shfl_sync(0xffffffffu, acc, 1), sc = __shfl_sync(0xffffffffu, acc, 2);
         const double bb1 = __shfl_sync(0xffffffffu, acc, 3), bb2 = __shfl_sync(0xffffffffu, acc, 4);
@@ -169,18 +179,29 @@ static void subpix_mask(int hw, int hh, std::vector<float>& mask) {
     }
 }
 
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-    template <class T> T* as() const { return static_cast<T*>(p); }
+// Per-thread device arena that only grows: a call carves its buffers out of one allocation, so the steady state issues no
+// cudaMalloc / cudaFree (the entry point is re-entrant across threads like the other stateless calls of the C-ABI).
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, used = 0;
+    int dev = -1;
+    ~Arena() { if (base) cudaFree(base); }
+    cudaError_t reserve(size_t bytes, int device) {
+        used = 0;
+        if (dev == device && cap >= bytes) return cudaSuccess;
+        if (base) { cudaFree(base); base = nullptr; cap = 0; }
+        dev = device;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&base), bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    template <class T> T* take(size_t count) {
+        T* r = reinterpret_cast<T*>(base + used);
+        used += (count * sizeof(T) + 255) & ~(size_t)255;
+        return r;
+    }
 };
-
-static cudaError_t upload_image(DevBuf& d, const uint8_t* img, int rows, int cols, size_t step) {
-    cudaError_t e = d.alloc((size_t)rows * cols);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy2D(d.p, (size_t)cols, img, step, (size_t)cols, (size_t)rows, cudaMemcpyHostToDevice);
-}
+inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 }  // namespace fbe
 
@@ -205,52 +226,60 @@ int fbe_bird_refine(const uint8_t* contour, size_t contour_step, const uint8_t* 
     FBE_TRY(cudaSetDevice(device));
     *n_out = 0;
     if (n == 0) return FBE_OK;
-    DevBuf d_contour, d_img, d_in, d_out, d_keep, d_n, d_mask, d_iters;
-    FBE_TRY(d_in.alloc((size_t)n * sizeof(fbe_keypoint)));
-    FBE_TRY(d_out.alloc((size_t)n * sizeof(fbe_keypoint)));
-    FBE_TRY(d_keep.alloc((size_t)n));
-    FBE_TRY(d_n.alloc(sizeof(int)));
-    FBE_TRY(cudaMemcpy(d_in.p, kps, (size_t)n * sizeof(fbe_keypoint), cudaMemcpyHostToDevice));
+    static thread_local Arena arena;
+    const size_t kp_bytes = (size_t)n * sizeof(fbe_keypoint), img_bytes = (size_t)rows * cols;
+    const int nq = (2 * half_w + 1) * (2 * half_h + 1), np = (2 * half_w + 3) * (2 * half_h + 3);
+    FBE_TRY(arena.reserve(2 * pad256(kp_bytes) + pad256((size_t)n) + 256 + pad256((size_t)n * sizeof(int)) + 2 * pad256(img_bytes) +
+                          pad256(441 * sizeof(float)), device));
+    fbe_keypoint* d_in = arena.take<fbe_keypoint>(n);
+    fbe_keypoint* d_out = arena.take<fbe_keypoint>(n);
+    uint8_t* d_keep = arena.take<uint8_t>(n);
+    int* d_n = arena.take<int>(1);
+    int* d_iters = arena.take<int>(n);
+    uint8_t* d_contour = arena.take<uint8_t>(img_bytes);
+    uint8_t* d_img = arena.take<uint8_t>(img_bytes);
+    float* d_mask = arena.take<float>(441);
+    cudaStream_t st = cudaStreamPerThread;
+    FBE_TRY(cudaMemcpyAsync(d_in, kps, kp_bytes, cudaMemcpyHostToDevice, st));
     const int ctas = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-    fbe_keypoint* d_cur = d_in.as<fbe_keypoint>();
+    fbe_keypoint* d_cur = d_in;
     const int* d_count = nullptr;
     if (contour) {          // GuidenceKeyBirdPts: filter + ordered compaction
-        FBE_TRY(upload_image(d_contour, contour, rows, cols, contour_step));
-        k_near_edges<<<ctas, kWarpsPerCta * 32>>>(d_contour.as<uint8_t>(), rows, cols, (size_t)cols, d_cur, n, d_keep.as<uint8_t>());
-        k_compact_kept<<<1, 1024>>>(d_cur, d_keep.as<uint8_t>(), n, d_out.as<fbe_keypoint>(), d_n.as<int>());
+        FBE_TRY(cudaMemcpy2DAsync(d_contour, (size_t)cols, contour, contour_step, (size_t)cols, (size_t)rows, cudaMemcpyHostToDevice, st));
+        k_near_edges<<<ctas, kWarpsPerCta * 32, 0, st>>>(d_contour, rows, cols, (size_t)cols, d_cur, n, d_keep);
+        k_compact_kept<<<1, 1024, 0, st>>>(d_cur, d_keep, n, d_out, d_n);
         count_launch(2);
-        d_cur = d_out.as<fbe_keypoint>();
-        d_count = d_n.as<int>();
+        d_cur = d_out;
+        d_count = d_n;
     }
     if (img) {              // cornerSubPix on the kept points (count read on the device: no host round trip in between)
-        FBE_TRY(upload_image(d_img, img, rows, cols, img_step));
+        FBE_TRY(cudaMemcpy2DAsync(d_img, (size_t)cols, img, img_step, (size_t)cols, (size_t)rows, cudaMemcpyHostToDevice, st));
         std::vector<float> mask;
         subpix_mask(half_w, half_h, mask);
-        FBE_TRY(d_mask.alloc(mask.size() * sizeof(float)));
-        FBE_TRY(cudaMemcpy(d_mask.p, mask.data(), mask.size() * sizeof(float), cudaMemcpyHostToDevice));
-        FBE_TRY(d_iters.alloc((size_t)n * sizeof(int)));
-        FBE_TRY(cudaMemset(d_iters.p, 0, (size_t)n * sizeof(int)));
+        FBE_TRY(cudaMemcpyAsync(d_mask, mask.data(), mask.size() * sizeof(float), cudaMemcpyHostToDevice, st));   // pageable: staged before return
+        FBE_TRY(cudaMemsetAsync(d_iters, 0, (size_t)n * sizeof(int), st));
         if (max_iter < 1) max_iter = 1;
         if (max_iter > 100) max_iter = 100;
         double e2 = eps > 0 ? eps : 0;
         e2 *= e2;
-        const int nq = (2 * half_w + 1) * (2 * half_h + 1), np = (2 * half_w + 3) * (2 * half_h + 3);
         const size_t smem = (size_t)kWarpsPerCta * (5 * nq + (np + 1) / 2) * sizeof(double);
         FBE_TRY(cudaFuncSetAttribute(k_corner_subpix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_corner_subpix<<<ctas, kWarpsPerCta * 32, smem>>>(d_img.as<uint8_t>(), rows, cols, (size_t)cols, d_cur, d_count, n, half_w, half_h,
-                                                           max_iter, e2, d_mask.as<float>(), d_iters.as<int>());
+        k_corner_subpix<<<ctas, kWarpsPerCta * 32, smem, st>>>(d_img, rows, cols, (size_t)cols, d_cur, d_count, n, half_w, half_h, max_iter, e2,
+                                                               d_mask, d_iters);
         count_launch();
     }
     FBE_TRY(cudaGetLastError());
     int kept = n;
     if (contour) {
-        FBE_TRY(cudaMemcpy(&kept, d_n.p, sizeof(int), cudaMemcpyDeviceToHost));
-        if (keep) FBE_TRY(cudaMemcpy(keep, d_keep.p, (size_t)n, cudaMemcpyDeviceToHost));
+        FBE_TRY(cudaMemcpyAsync(&kept, d_n, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (keep) FBE_TRY(cudaMemcpyAsync(keep, d_keep, (size_t)n, cudaMemcpyDeviceToHost, st));
+        FBE_TRY(cudaStreamSynchronize(st));
     } else if (keep) {
         for (int i = 0; i < n; ++i) keep[i] = 1;
     }
-    FBE_TRY(cudaMemcpy(out_kps, d_cur, (size_t)kept * sizeof(fbe_keypoint), cudaMemcpyDeviceToHost));
-    if (iters && img) FBE_TRY(cudaMemcpy(iters, d_iters.p, (size_t)kept * sizeof(int), cudaMemcpyDeviceToHost));
+    FBE_TRY(cudaMemcpyAsync(out_kps, d_cur, (size_t)kept * sizeof(fbe_keypoint), cudaMemcpyDeviceToHost, st));
+    if (iters && img) FBE_TRY(cudaMemcpyAsync(iters, d_iters, (size_t)kept * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FBE_TRY(cudaStreamSynchronize(st));
     *n_out = kept;
     return FBE_OK;
 }
