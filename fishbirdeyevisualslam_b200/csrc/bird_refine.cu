@@ -18,8 +18,11 @@ namespace fbe {
 constexpr int kWarpsPerCta = 4;
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_near_edges(const uint8_t* __restrict__ contour, int rows, int cols, size_t step, const fbe_keypoint* __restrict__ kps, int n,
-             uint8_t* __restrict__ keep) {
+k_near_edges(const uint8_t* __restrict__ contour, int rows, int cols, size_t step, size_t img_stride, const fbe_keypoint* __restrict__ kps,
+             const int* __restrict__ n_arr, int cap, uint8_t* __restrict__ keep) {
+    const int b = blockIdx.y;                      // frame of the batch: images img_stride bytes apart, keypoint lists cap records apart
+    contour += (size_t)b * img_stride; kps += (size_t)b * cap; keep += (size_t)b * cap;
+    const int n = min(n_arr[b], cap);
     const int k = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (k >= n) return;
     const float r = 10.f, x = kps[k].x, y = kps[k].y;
@@ -46,7 +49,10 @@ k_near_edges(const uint8_t* __restrict__ contour, int rows, int cols, size_t ste
 
 // ordered compaction of the kept keypoints (mvKeysBird.push_back in input order); n is a few thousand: one CTA
 __global__ void __launch_bounds__(1024)
-k_compact_kept(const fbe_keypoint* __restrict__ kps, const uint8_t* __restrict__ keep, int n, fbe_keypoint* __restrict__ out, int* __restrict__ n_out) {
+k_compact_kept(const fbe_keypoint* __restrict__ kps, const uint8_t* __restrict__ keep, const int* __restrict__ n_arr, int cap,
+               fbe_keypoint* __restrict__ out, int* __restrict__ n_out) {
+    const int b = blockIdx.y, n = min(n_arr[b], cap);
+    kps += (size_t)b * cap; keep += (size_t)b * cap; out += (size_t)b * cap; n_out += b;
     __shared__ int warp_sum[32];
     __shared__ int running;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -88,10 +94,12 @@ __device__ __forceinline__ float rect_sample(const uint8_t* __restrict__ img, in
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_corner_subpix(const uint8_t* __restrict__ img, int rows, int cols, size_t step, fbe_keypoint* __restrict__ kps, const int* __restrict__ n_ptr,
-                int n_max, int hw, int hh, int max_iter, double eps2, const float* __restrict__ mask, int* __restrict__ iters) {
+k_corner_subpix(const uint8_t* __restrict__ img, int rows, int cols, size_t step, size_t img_stride, fbe_keypoint* __restrict__ kps,
+                const int* __restrict__ n_arr, int cap, int hw, int hh, int max_iter, double eps2, const float* __restrict__ mask,
+                int* __restrict__ iters) {
     extern __shared__ double smem_d[];
-    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    const int b = blockIdx.y, n = min(n_arr[b], cap);
+    img += (size_t)b * img_stride; kps += (size_t)b * cap; iters += (size_t)b * cap;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k = blockIdx.x * kWarpsPerCta + w;
     if (k >= n) return;
@@ -162,7 +170,7 @@ k_corner_subpix(const uint8_t* __restrict__ img, int rows, int cols, size_t step
     if (fabsf(ix - tx) > (float)hw || fabsf(iy - ty) > (float)hh) { ix = tx; iy = ty; }   // moved too far: keep the input point
     if (lane == 0) {
         kps[k].x = ix; kps[k].y = iy;
-        if (iters) iters[k] = iter;
+        iters[k] = iter;
     }
 }
 
@@ -213,75 +221,106 @@ using namespace fbe;
         if (_e != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); return FBE_E_CUDA; } \
     } while (0)
 
-extern "C" {
-
-int fbe_bird_refine(const uint8_t* contour, size_t contour_step, const uint8_t* img, size_t img_step, int32_t rows, int32_t cols,
-                    const fbe_keypoint* kps, int32_t n, int32_t half_w, int32_t half_h, int32_t max_iter, double eps, int32_t device,
-                    uint8_t* keep, fbe_keypoint* out_kps, int32_t* n_out, int32_t* iters) {
-    if (n < 0 || rows <= 0 || cols <= 0 || (!contour && !img) || !n_out || (n > 0 && (!kps || !out_kps))) return FBE_E_INVALID;
+// B frames of one size: contours / imgs are B images `*_stride` bytes apart (rows of `*_step` bytes), kps / out_kps / keep / iters
+// B lists `cap` records apart, n / n_out B counts.  The single-frame entry point is the B = 1 case.
+static int bird_refine_impl(const uint8_t* contour, size_t contour_step, size_t contour_stride, const uint8_t* img, size_t img_step,
+                            size_t img_stride, int rows, int cols, int B, const fbe_keypoint* kps, const int32_t* n, int cap, int half_w,
+                            int half_h, int max_iter, double eps, int device, uint8_t* keep, fbe_keypoint* out_kps, int32_t* n_out,
+                            int32_t* iters) {
+    if (B <= 0 || cap < 0 || rows <= 0 || cols <= 0 || (!contour && !img) || !n || !n_out || (cap > 0 && (!kps || !out_kps))) return FBE_E_INVALID;
     if (contour && contour_step < (size_t)cols) return FBE_E_INVALID;
     if (img && (img_step < (size_t)cols || half_w < 1 || half_h < 1 || half_w > 10 || half_h > 10)) return FBE_E_INVALID;
+    int n_max = 0;
+    for (int b = 0; b < B; ++b) {
+        if (n[b] < 0 || n[b] > cap) return FBE_E_INVALID;
+        n_max = n[b] > n_max ? n[b] : n_max;
+        n_out[b] = 0;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_error("no CUDA device: this library has no CPU path"); return FBE_E_CUDA; }
     FBE_TRY(cudaSetDevice(device));
-    *n_out = 0;
-    if (n == 0) return FBE_OK;
+    if (n_max == 0) return FBE_OK;
     static thread_local Arena arena;
-    const size_t kp_bytes = (size_t)n * sizeof(fbe_keypoint), img_bytes = (size_t)rows * cols;
+    const size_t total = (size_t)B * cap, kp_bytes = total * sizeof(fbe_keypoint), img_bytes = (size_t)rows * cols;
     const int nq = (2 * half_w + 1) * (2 * half_h + 1), np = (2 * half_w + 3) * (2 * half_h + 3);
-    FBE_TRY(arena.reserve(2 * pad256(kp_bytes) + pad256((size_t)n) + 256 + pad256((size_t)n * sizeof(int)) + 2 * pad256(img_bytes) +
-                          pad256(441 * sizeof(float)), device));
-    fbe_keypoint* d_in = arena.take<fbe_keypoint>(n);
-    fbe_keypoint* d_out = arena.take<fbe_keypoint>(n);
-    uint8_t* d_keep = arena.take<uint8_t>(n);
-    int* d_n = arena.take<int>(1);
-    int* d_iters = arena.take<int>(n);
-    uint8_t* d_contour = arena.take<uint8_t>(img_bytes);
-    uint8_t* d_img = arena.take<uint8_t>(img_bytes);
+    FBE_TRY(arena.reserve(2 * pad256(kp_bytes) + pad256(total) + 2 * pad256((size_t)B * sizeof(int)) + pad256(total * sizeof(int)) +
+                          2 * pad256(img_bytes * B) + pad256(441 * sizeof(float)), device));
+    fbe_keypoint* d_in = arena.take<fbe_keypoint>(total);
+    fbe_keypoint* d_out = arena.take<fbe_keypoint>(total);
+    uint8_t* d_keep = arena.take<uint8_t>(total);
+    int* d_nin = arena.take<int>(B);
+    int* d_nkept = arena.take<int>(B);
+    int* d_iters = arena.take<int>(total);
+    uint8_t* d_contour = arena.take<uint8_t>(img_bytes * B);
+    uint8_t* d_img = arena.take<uint8_t>(img_bytes * B);
     float* d_mask = arena.take<float>(441);
     cudaStream_t st = cudaStreamPerThread;
     FBE_TRY(cudaMemcpyAsync(d_in, kps, kp_bytes, cudaMemcpyHostToDevice, st));
-    const int ctas = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    FBE_TRY(cudaMemcpyAsync(d_nin, n, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, st));
+    const dim3 grid((n_max + kWarpsPerCta - 1) / kWarpsPerCta, B);
     fbe_keypoint* d_cur = d_in;
-    const int* d_count = nullptr;
+    const int* d_count = d_nin;
+    auto upload = [&](uint8_t* dst, const uint8_t* src, size_t step, size_t stride) -> cudaError_t {
+        if (stride == step * (size_t)rows || B == 1)       // frames back to back: one 2-D copy over B*rows rows
+            return cudaMemcpy2DAsync(dst, (size_t)cols, src, step, (size_t)cols, (size_t)rows * B, cudaMemcpyHostToDevice, st);
+        for (int b = 0; b < B; ++b) {
+            cudaError_t e = cudaMemcpy2DAsync(dst + img_bytes * b, (size_t)cols, src + stride * b, step, (size_t)cols, (size_t)rows, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
     if (contour) {          // GuidenceKeyBirdPts: filter + ordered compaction
-        FBE_TRY(cudaMemcpy2DAsync(d_contour, (size_t)cols, contour, contour_step, (size_t)cols, (size_t)rows, cudaMemcpyHostToDevice, st));
-        k_near_edges<<<ctas, kWarpsPerCta * 32, 0, st>>>(d_contour, rows, cols, (size_t)cols, d_cur, n, d_keep);
-        k_compact_kept<<<1, 1024, 0, st>>>(d_cur, d_keep, n, d_out, d_n);
+        FBE_TRY(upload(d_contour, contour, contour_step, contour_stride));
+        k_near_edges<<<grid, kWarpsPerCta * 32, 0, st>>>(d_contour, rows, cols, (size_t)cols, img_bytes, d_cur, d_nin, cap, d_keep);
+        k_compact_kept<<<dim3(1, B), 1024, 0, st>>>(d_cur, d_keep, d_nin, cap, d_out, d_nkept);
         count_launch(2);
         d_cur = d_out;
-        d_count = d_n;
+        d_count = d_nkept;
     }
-    if (img) {              // cornerSubPix on the kept points (count read on the device: no host round trip in between)
-        FBE_TRY(cudaMemcpy2DAsync(d_img, (size_t)cols, img, img_step, (size_t)cols, (size_t)rows, cudaMemcpyHostToDevice, st));
+    if (img) {              // cornerSubPix on the kept points (counts read on the device: no host round trip in between)
+        FBE_TRY(upload(d_img, img, img_step, img_stride));
         std::vector<float> mask;
         subpix_mask(half_w, half_h, mask);
         FBE_TRY(cudaMemcpyAsync(d_mask, mask.data(), mask.size() * sizeof(float), cudaMemcpyHostToDevice, st));   // pageable: staged before return
-        FBE_TRY(cudaMemsetAsync(d_iters, 0, (size_t)n * sizeof(int), st));
+        FBE_TRY(cudaMemsetAsync(d_iters, 0, total * sizeof(int), st));
         if (max_iter < 1) max_iter = 1;
         if (max_iter > 100) max_iter = 100;
         double e2 = eps > 0 ? eps : 0;
         e2 *= e2;
         const size_t smem = (size_t)kWarpsPerCta * (5 * nq + (np + 1) / 2) * sizeof(double);
         FBE_TRY(cudaFuncSetAttribute(k_corner_subpix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_corner_subpix<<<ctas, kWarpsPerCta * 32, smem, st>>>(d_img, rows, cols, (size_t)cols, d_cur, d_count, n, half_w, half_h, max_iter, e2,
-                                                               d_mask, d_iters);
+        k_corner_subpix<<<grid, kWarpsPerCta * 32, smem, st>>>(d_img, rows, cols, (size_t)cols, img_bytes, d_cur, d_count, cap, half_w, half_h,
+                                                               max_iter, e2, d_mask, d_iters);
         count_launch();
     }
     FBE_TRY(cudaGetLastError());
-    int kept = n;
-    if (contour) {
-        FBE_TRY(cudaMemcpyAsync(&kept, d_n, sizeof(int), cudaMemcpyDeviceToHost, st));
-        if (keep) FBE_TRY(cudaMemcpyAsync(keep, d_keep, (size_t)n, cudaMemcpyDeviceToHost, st));
-        FBE_TRY(cudaStreamSynchronize(st));
-    } else if (keep) {
-        for (int i = 0; i < n; ++i) keep[i] = 1;
+    FBE_TRY(cudaMemcpyAsync(n_out, d_count, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (keep) {
+        if (contour) FBE_TRY(cudaMemcpyAsync(keep, d_keep, total, cudaMemcpyDeviceToHost, st));
+        else for (int b = 0; b < B; ++b) for (int i = 0; i < cap; ++i) keep[(size_t)b * cap + i] = i < n[b];
     }
-    FBE_TRY(cudaMemcpyAsync(out_kps, d_cur, (size_t)kept * sizeof(fbe_keypoint), cudaMemcpyDeviceToHost, st));
-    if (iters && img) FBE_TRY(cudaMemcpyAsync(iters, d_iters, (size_t)kept * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FBE_TRY(cudaMemcpyAsync(out_kps, d_cur, kp_bytes, cudaMemcpyDeviceToHost, st));
+    if (iters && img) FBE_TRY(cudaMemcpyAsync(iters, d_iters, total * sizeof(int), cudaMemcpyDeviceToHost, st));
     FBE_TRY(cudaStreamSynchronize(st));
-    *n_out = kept;
     return FBE_OK;
+}
+
+extern "C" {
+
+int fbe_bird_refine(const uint8_t* contour, size_t contour_step, const uint8_t* img, size_t img_step, int32_t rows, int32_t cols,
+                    const fbe_keypoint* kps, int32_t n, int32_t half_w, int32_t half_h, int32_t max_iter, double eps, int32_t device,
+                    uint8_t* keep, fbe_keypoint* out_kps, int32_t* n_out, int32_t* iters) {
+    if (n < 0 || !n_out) return FBE_E_INVALID;
+    return bird_refine_impl(contour, contour_step, 0, img, img_step, 0, rows, cols, 1, kps, &n, n, half_w, half_h, max_iter, eps, device, keep,
+                            out_kps, n_out, iters);
+}
+
+int fbe_bird_refine_batch(const uint8_t* contours, size_t contour_step, size_t contour_stride, const uint8_t* imgs, size_t img_step,
+                          size_t img_stride, int32_t rows, int32_t cols, int32_t nframes, const fbe_keypoint* kps, const int32_t* n,
+                          int32_t cap, int32_t half_w, int32_t half_h, int32_t max_iter, double eps, int32_t device, uint8_t* keep,
+                          fbe_keypoint* out_kps, int32_t* n_out, int32_t* iters) {
+    return bird_refine_impl(contours, contour_step, contour_stride, imgs, img_step, img_stride, rows, cols, nframes, kps, n, cap, half_w, half_h,
+                            max_iter, eps, device, keep, out_kps, n_out, iters);
 }
 
 }  // extern "C"

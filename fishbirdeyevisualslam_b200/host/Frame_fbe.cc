@@ -60,4 +60,24 @@ void Frame::UndistortKeyPoints() {
     }
 }
 
+// Frame::GuidenceKeyBirdPts (:671-684): genEdgesPC() keeps the reference's code (it feeds the ICP); the per-keypoint nearEdges
+// filter (:717-739) and the push_back in detection order become one fbe_bird_refine call with no image (filter + ordered
+// compaction only).  In the bird-view Frame constructor the following cv::cornerSubPix block (:345-352) folds into the same
+// call by passing mBirdviewImg as well -- INTEGRATION.md shows that form.
+void Frame::GuidenceKeyBirdPts(std::vector<cv::KeyPoint>& preKeysBird) {
+    genEdgesPC();
+    const int n = (int)preKeysBird.size();
+    if (n == 0) return;
+    const cv::Mat& c = mBirdviewContourICP;
+    const size_t step = c.rows > 1 ? (size_t)(c.ptr(1) - c.ptr(0)) : (size_t)c.cols;
+    std::vector<cv::KeyPoint> kept(n);
+    int32_t nkept = 0;
+    if (fbe_bird_refine(c.ptr(0), step, NULL, 0, c.rows, c.cols, reinterpret_cast<const fbe_keypoint*>(preKeysBird.data()), n, 5, 5, 40,
+                        0.001, 0, NULL, reinterpret_cast<fbe_keypoint*>(kept.data()), &nkept, NULL) != FBE_OK) {
+        fprintf(stderr, "Frame::GuidenceKeyBirdPts (fbe-b200): %s\n", fbe_last_error());
+        abort();
+    }
+    mvKeysBird.insert(mvKeysBird.end(), kept.begin(), kept.begin() + nkept);
+}
+
 }  // namespace ORB_SLAM2

@@ -89,6 +89,27 @@ def BirdGuideRefine(contour, img, kps: np.ndarray, half_win=(5, 5), max_iter: in
     return keep, out[:n_out.value].copy(), iters[:n_out.value].copy()
 
 
+def BirdGuideRefineBatch(contours, imgs, kps: np.ndarray, n, half_win=(5, 5), max_iter: int = 40, eps: float = 0.001, device: int = 0):
+    """fbe_bird_refine_batch: the two steps of BirdGuideRefine for B frames in one call.  contours / imgs u8 [B, rows, cols]
+    (either may be None), kps KP_DTYPE [B, cap], n int32 [B].  -> (keep u8 [B, cap], out KP_DTYPE [B, cap], n_out [B], iters [B, cap])."""
+    L = _lib.load()
+    kps = np.ascontiguousarray(kps, KP_DTYPE); n = np.ascontiguousarray(n, np.int32)
+    B, cap = kps.shape
+    ref = contours if contours is not None else imgs
+    assert ref.ndim == 3 and ref.shape[0] == B and ref.strides[2] == 1
+    rows, cols = ref.shape[1:]
+    keep = np.zeros((B, cap), np.uint8); out = np.zeros_like(kps); iters = np.zeros((B, cap), np.int32); n_out = np.zeros(B, np.int32)
+    cp = C.c_void_p(contours.ctypes.data) if contours is not None else None
+    ip = C.c_void_p(imgs.ctypes.data) if imgs is not None else None
+    cs = contours.strides if contours is not None else (0, 0, 0)
+    is_ = imgs.strides if imgs is not None else (0, 0, 0)
+    check(L.fbe_bird_refine_batch(cp, C.c_size_t(cs[1]), C.c_size_t(cs[0]), ip, C.c_size_t(is_[1]), C.c_size_t(is_[0]), C.c_int32(rows),
+                                  C.c_int32(cols), C.c_int32(B), ptr(kps), ptr(n), C.c_int32(cap), C.c_int32(half_win[0]),
+                                  C.c_int32(half_win[1]), C.c_int32(max_iter), C.c_double(eps), C.c_int32(device), ptr(keep), ptr(out),
+                                  ptr(n_out), ptr(iters)))
+    return keep, out, n_out, iters
+
+
 def isInFrustum(view, pos, normal, min_dist, max_dist, viewing_cos_limit: float, device: int = 0):
     """Frame::isInFrustum (Frame.cc:435-491) for n map points at once.  `view` is a _lib.FrustumView (or anything with the
     same ctypes layout); pos / normal n x 3, min_dist / max_dist = mfMinDistance / mfMaxDistance.

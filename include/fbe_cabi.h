@@ -201,6 +201,15 @@ FBE_API int fbe_image_bounds(int32_t cols, int32_t rows, const float K[4], const
 FBE_API int fbe_bird_refine(const uint8_t* contour, size_t contour_step, const uint8_t* img, size_t img_step, int32_t rows,
                             int32_t cols, const fbe_keypoint* kps, int32_t n, int32_t half_w, int32_t half_h, int32_t max_iter,
                             double eps, int32_t device, uint8_t* keep, fbe_keypoint* out_kps, int32_t* n_out, int32_t* iters);
+/* The same two steps for nframes bird-view frames of one size in one call (offline batches, config C4): contours / imgs are
+ * nframes images `*_stride` bytes apart with rows of `*_step` bytes (either may be NULL as above); kps, keep, out_kps and iters
+ * are nframes lists `cap` records apart, n[f] <= cap candidates in frame f, n_out[f] kept.  Every frame gets exactly the result
+ * of its own fbe_bird_refine call. */
+FBE_API int fbe_bird_refine_batch(const uint8_t* contours, size_t contour_step, size_t contour_stride, const uint8_t* imgs,
+                                  size_t img_step, size_t img_stride, int32_t rows, int32_t cols, int32_t nframes,
+                                  const fbe_keypoint* kps, const int32_t* n, int32_t cap, int32_t half_w, int32_t half_h,
+                                  int32_t max_iter, double eps, int32_t device, uint8_t* keep, fbe_keypoint* out_kps,
+                                  int32_t* n_out, int32_t* iters);
 
 /* ---- Frame grid -------------------------------------------------------------------------------- */
 /* Frame::AssignFeaturesToGrid / PosInGrid / PosInGridBirdview, src/Frame.cc:381-411,548-570.

@@ -627,6 +627,19 @@ void refm_check_models(const Kp* k1, int n1, const Kp* k2, int n2, const int32_t
     }
 }
 
+// Frame::GuidenceKeyBirdPts (src/Frame.cc:671-684: genEdgesPC + the nearEdges filter) on a real Frame object: the verbatim
+// build runs the reference's own bodies, the drop-in build runs host/Frame_fbe.cc (filter on the GPU, genEdgesPC unchanged).
+// out receives mvKeysBird; counts = {mvKeysBird.size(), mEdgeFree.size(), mEdgeSign.size()}.
+void refm_guidance_key_bird_pts(const uint8_t* contour, int rows, int cols, const Kp* kps, int n, Kp* out, int* counts) {
+    Frame F;
+    F.mBirdviewContourICP = cv::Mat(rows, cols, CV_8U);
+    for (int y = 0; y < rows; ++y) std::memcpy(F.mBirdviewContourICP.ptr(y), contour + (size_t)y * cols, (size_t)cols);
+    std::vector<cv::KeyPoint> pre = to_kps(kps, n);
+    F.GuidenceKeyBirdPts(pre);
+    counts[0] = (int)F.mvKeysBird.size(); counts[1] = (int)F.mEdgeFree.size(); counts[2] = (int)F.mEdgeSign.size();
+    if (counts[0]) std::memcpy(out, F.mvKeysBird.data(), (size_t)counts[0] * sizeof(Kp));
+}
+
 #ifdef FBE_DROPIN
 // Frame::UndistortKeyPoints through the drop-in body (host/Frame_fbe.cc); only the drop-in build has it -- the reference's
 // own body calls cv::fisheye::undistortPoints, which no shim here provides (its arithmetic is pinned by tests/test_undistort.py).

@@ -89,6 +89,38 @@ def test_oracle_near_edges_equals_transcription(oracle):
     assert list(oracle.bird_near_edges(c, np.float32([[40, 200], [200, 40]]))) == [1, 0]
 
 
+def _guidance(lib, contour, kps):
+    """Frame::GuidenceKeyBirdPts on a real reference Frame object (oracle/ref_match_wrap.cpp) -> (mvKeysBird, |mEdgeFree|, |mEdgeSign|)."""
+    import ctypes as C
+    contour = np.ascontiguousarray(contour); kps = np.ascontiguousarray(kps)
+    out = np.empty_like(kps); counts = np.zeros(3, np.int32)
+    lib.refm_guidance_key_bird_pts(contour.ctypes.data_as(C.c_void_p), contour.shape[0], contour.shape[1], kps.ctypes.data_as(C.c_void_p),
+                                   len(kps), out.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p))
+    return out[:counts[0]], int(counts[1]), int(counts[2])
+
+
+def _guidance_cases():
+    for seed in range(4):
+        c = S.contour_image(seed)
+        rng = np.random.default_rng(40 + seed)
+        xy = np.stack([rng.uniform(-15, 399, 1500), rng.uniform(-15, 399, 1500)], 1).astype(np.float32)
+        xy[:200] = np.round(xy[:200])
+        yield c, xy
+
+
+def test_oracle_near_edges_equals_verbatim_reference(oracle):
+    """The reference's OWN Frame::GuidenceKeyBirdPts / nearEdges / genEdgesPC, compiled from where they lie (oracle/_ref)."""
+    lib = oracle.refmatch()
+    if lib is None:
+        pytest.skip("oracle/_ref/libfbe_refmatch.so not built (needs the reference sources at build time)")
+    for c, xy in _guidance_cases():
+        kin = S.as_kps(xy)
+        kept, nfree, nsign = _guidance(lib, c, kin)
+        keep = oracle.bird_near_edges(c, xy)
+        assert kept.tobytes() == kin[keep > 0].tobytes() and 0 < len(kept) < len(kin)
+        assert nfree == int((c >= 150).sum()) and nsign == int(((c >= 10) & (c < 150)).sum())
+
+
 @pytest.mark.gpu
 def test_gpu_bird_refine_equals_oracle(oracle, fbe):
     from fishbirdeyevisualslam_b200.matcher import BirdGuideRefine
@@ -149,3 +181,49 @@ def test_gpu_bird_refine_edge_cases(oracle, fbe):
     assert np.stack([k["x"], k["y"]], 1).tobytes() == xy.tobytes() and (it == 0).all()
     with pytest.raises(FbeError):
         BirdGuideRefine(None, img, S.as_kps(xy), (0, 5))
+
+
+@pytest.mark.gpu
+def test_gpu_dropin_frame_guidance_equals_verbatim_reference(oracle, fbe):
+    """Frame::GuidenceKeyBirdPts through host/Frame_fbe.cc (filter on the GPU, genEdgesPC unchanged) on a real Frame object,
+    against the reference's own body on the same object."""
+    drop, ref = oracle.dropinmatch(), oracle.refmatch()
+    if drop is None or ref is None:
+        pytest.skip("oracle/_ref drop-in / verbatim libraries not built")
+    for c, xy in _guidance_cases():
+        kin = S.as_kps(xy)
+        got, want = _guidance(drop, c, kin), _guidance(ref, c, kin)
+        assert got[0].tobytes() == want[0].tobytes() and got[1:] == want[1:]
+    got = _guidance(drop, S.contour_image(0), S.as_kps(np.zeros((0, 2), np.float32)))
+    assert len(got[0]) == 0 and got[1] > 0
+
+
+@pytest.mark.gpu
+def test_gpu_bird_refine_batch_equals_single_calls(oracle, fbe):
+    """fbe_bird_refine_batch: every frame of a ragged batch gets exactly the result of its own single-frame call (and so the oracle's)."""
+    from fishbirdeyevisualslam_b200._lib import KP_DTYPE
+    from fishbirdeyevisualslam_b200.matcher import BirdGuideRefine, BirdGuideRefineBatch
+    B, cap = 6, 900
+    imgs = np.stack([S.bird_image(20 + b) for b in range(B)]); contours = np.stack([S.contour_image(20 + b) for b in range(B)])
+    n = np.int32([900, 0, 517, 1, 899, 640])
+    kps = np.zeros((B, cap), KP_DTYPE)
+    for b in range(B):
+        xy = np.concatenate([S.corner_points(imgs[b], 20 + b, 700), S.border_points(384, 384, 20 + b, 194)])
+        kps[b] = S.as_kps(xy)
+    for cont, im in ((contours, imgs), (None, imgs), (contours, None)):
+        keep, out, n_out, iters = BirdGuideRefineBatch(cont, im, kps, n)
+        for b in range(B):
+            k1, o1, i1 = BirdGuideRefine(None if cont is None else cont[b], None if im is None else im[b], kps[b, :n[b]])
+            assert n_out[b] == len(o1) and np.array_equal(keep[b, :n[b]], k1) and not keep[b, n[b]:].any()
+            assert out[b, :n_out[b]].tobytes() == o1.tobytes()
+            if im is not None:
+                assert np.array_equal(iters[b, :n_out[b]], i1)
+    # against the oracle directly, frames given as strided views of a larger buffer
+    big = np.zeros((B, 400, 512), np.uint8); big[:, 8:392, 64:448] = imgs
+    keep, out, n_out, _ = BirdGuideRefineBatch(contours, big[:, 8:392, 64:448], kps, n)
+    for b in range(B):
+        xy = np.stack([kps[b, :n[b]]["x"], kps[b, :n[b]]["y"]], 1)
+        ok = oracle.bird_near_edges(contours[b], xy) if n[b] else np.zeros(0, np.uint8)
+        oxy, _ = oracle.corner_subpix(imgs[b], xy[ok > 0])
+        assert n_out[b] == int(ok.sum())
+        assert np.stack([out[b, :n_out[b]]["x"], out[b, :n_out[b]]["y"]], 1).tobytes() == oxy.tobytes()
