@@ -271,6 +271,7 @@ static int bird_refine_impl(const uint8_t* contour, size_t contour_step, size_t 
     };
     if (contour) {          // GuidenceKeyBirdPts: filter + ordered compaction
         FBE_TRY(upload(d_contour, contour, contour_step, contour_stride));
+        FBE_TRY(cudaMemsetAsync(d_keep, 0, total, st));          // entries past n[f] of a ragged batch read as not kept
         k_near_edges<<<grid, kWarpsPerCta * 32, 0, st>>>(d_contour, rows, cols, (size_t)cols, img_bytes, d_cur, d_nin, cap, d_keep);
         k_compact_kept<<<dim3(1, B), 1024, 0, st>>>(d_cur, d_keep, d_nin, cap, d_out, d_nkept);
         count_launch(2);

@@ -33,5 +33,21 @@ try:
     line["cv2_subpix_ms_1thread"] = (time.perf_counter() - t) / 5 * 1e3
 except ImportError:
     pass
+# a batch of frames in one call (config C4 style): 64 frames x 2 000 candidates
+from fishbirdeyevisualslam_b200.matcher import BirdGuideRefineBatch
+from fishbirdeyevisualslam_b200._lib import KP_DTYPE
+B = 64
+imgs = np.stack([S.bird_image(b % 8) for b in range(B)]); conts = np.stack([S.contour_image(b % 8) for b in range(B)])
+kb = np.zeros((B, 2000), KP_DTYPE)
+for b in range(B):
+    kb[b] = S.as_kps(S.corner_points(imgs[b], b % 8, 2000))
+nb = np.full(B, 2000, np.int32)
+for _ in range(3):
+    BirdGuideRefineBatch(conts, imgs, kb, nb)
+t = time.perf_counter()
+for _ in range(10):
+    _, ob, nob, itb = BirdGuideRefineBatch(conts, imgs, kb, nb)
+bms = (time.perf_counter() - t) / 10 * 1e3
+line["batch"] = {"frames": B, "kept_total": int(nob.sum()), "gpu_host_api_ms": bms, "ms_per_frame": bms / B}
 import json
 print(json.dumps(line))
