@@ -215,12 +215,6 @@ inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 using namespace fbe;
 
-#define FBE_TRY(expr)                                                                        \
-    do {                                                                                     \
-        cudaError_t _e = (expr);                                                             \
-        if (_e != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); return FBE_E_CUDA; } \
-    } while (0)
-
 // B frames of one size: contours / imgs are B images `*_stride` bytes apart (rows of `*_step` bytes), kps / out_kps / keep / iters
 // B lists `cap` records apart, n / n_out B counts.  The single-frame entry point is the B = 1 case.
 static int bird_refine_impl(const uint8_t* contour, size_t contour_step, size_t contour_stride, const uint8_t* img, size_t img_step,
@@ -238,12 +232,12 @@ static int bird_refine_impl(const uint8_t* contour, size_t contour_step, size_t 
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_error("no CUDA device: this library has no CPU path"); return FBE_E_CUDA; }
-    FBE_TRY(cudaSetDevice(device));
+    FBE_CUDA(cudaSetDevice(device));
     if (n_max == 0) return FBE_OK;
     static thread_local Arena arena;
     const size_t total = (size_t)B * cap, kp_bytes = total * sizeof(fbe_keypoint), img_bytes = (size_t)rows * cols;
     const int nq = (2 * half_w + 1) * (2 * half_h + 1), np = (2 * half_w + 3) * (2 * half_h + 3);
-    FBE_TRY(arena.reserve(2 * pad256(kp_bytes) + pad256(total) + 2 * pad256((size_t)B * sizeof(int)) + pad256(total * sizeof(int)) +
+    FBE_CUDA(arena.reserve(2 * pad256(kp_bytes) + pad256(total) + 2 * pad256((size_t)B * sizeof(int)) + pad256(total * sizeof(int)) +
                           2 * pad256(img_bytes * B) + pad256(441 * sizeof(float)), device));
     fbe_keypoint* d_in = arena.take<fbe_keypoint>(total);
     fbe_keypoint* d_out = arena.take<fbe_keypoint>(total);
@@ -255,8 +249,8 @@ static int bird_refine_impl(const uint8_t* contour, size_t contour_step, size_t 
     uint8_t* d_img = arena.take<uint8_t>(img_bytes * B);
     float* d_mask = arena.take<float>(441);
     cudaStream_t st = cudaStreamPerThread;
-    FBE_TRY(cudaMemcpyAsync(d_in, kps, kp_bytes, cudaMemcpyHostToDevice, st));
-    FBE_TRY(cudaMemcpyAsync(d_nin, n, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, st));
+    FBE_CUDA(cudaMemcpyAsync(d_in, kps, kp_bytes, cudaMemcpyHostToDevice, st));
+    FBE_CUDA(cudaMemcpyAsync(d_nin, n, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, st));
     const dim3 grid((n_max + kWarpsPerCta - 1) / kWarpsPerCta, B);
     fbe_keypoint* d_cur = d_in;
     const int* d_count = d_nin;
@@ -270,8 +264,8 @@ static int bird_refine_impl(const uint8_t* contour, size_t contour_step, size_t 
         return cudaSuccess;
     };
     if (contour) {          // GuidenceKeyBirdPts: filter + ordered compaction
-        FBE_TRY(upload(d_contour, contour, contour_step, contour_stride));
-        FBE_TRY(cudaMemsetAsync(d_keep, 0, total, st));          // entries past n[f] of a ragged batch read as not kept
+        FBE_CUDA(upload(d_contour, contour, contour_step, contour_stride));
+        FBE_CUDA(cudaMemsetAsync(d_keep, 0, total, st));          // entries past n[f] of a ragged batch read as not kept
         k_near_edges<<<grid, kWarpsPerCta * 32, 0, st>>>(d_contour, rows, cols, (size_t)cols, img_bytes, d_cur, d_nin, cap, d_keep);
         k_compact_kept<<<dim3(1, B), 1024, 0, st>>>(d_cur, d_keep, d_nin, cap, d_out, d_nkept);
         count_launch(2);
@@ -279,30 +273,30 @@ static int bird_refine_impl(const uint8_t* contour, size_t contour_step, size_t 
         d_count = d_nkept;
     }
     if (img) {              // cornerSubPix on the kept points (counts read on the device: no host round trip in between)
-        FBE_TRY(upload(d_img, img, img_step, img_stride));
+        FBE_CUDA(upload(d_img, img, img_step, img_stride));
         std::vector<float> mask;
         subpix_mask(half_w, half_h, mask);
-        FBE_TRY(cudaMemcpyAsync(d_mask, mask.data(), mask.size() * sizeof(float), cudaMemcpyHostToDevice, st));   // pageable: staged before return
-        FBE_TRY(cudaMemsetAsync(d_iters, 0, total * sizeof(int), st));
+        FBE_CUDA(cudaMemcpyAsync(d_mask, mask.data(), mask.size() * sizeof(float), cudaMemcpyHostToDevice, st));   // pageable: staged before return
+        FBE_CUDA(cudaMemsetAsync(d_iters, 0, total * sizeof(int), st));
         if (max_iter < 1) max_iter = 1;
         if (max_iter > 100) max_iter = 100;
         double e2 = eps > 0 ? eps : 0;
         e2 *= e2;
         const size_t smem = (size_t)kWarpsPerCta * (5 * nq + (np + 1) / 2) * sizeof(double);
-        FBE_TRY(cudaFuncSetAttribute(k_corner_subpix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FBE_CUDA(cudaFuncSetAttribute(k_corner_subpix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_corner_subpix<<<grid, kWarpsPerCta * 32, smem, st>>>(d_img, rows, cols, (size_t)cols, img_bytes, d_cur, d_count, cap, half_w, half_h,
                                                                max_iter, e2, d_mask, d_iters);
         count_launch();
     }
-    FBE_TRY(cudaGetLastError());
-    FBE_TRY(cudaMemcpyAsync(n_out, d_count, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FBE_CUDA(cudaGetLastError());
+    FBE_CUDA(cudaMemcpyAsync(n_out, d_count, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (keep) {
-        if (contour) FBE_TRY(cudaMemcpyAsync(keep, d_keep, total, cudaMemcpyDeviceToHost, st));
+        if (contour) FBE_CUDA(cudaMemcpyAsync(keep, d_keep, total, cudaMemcpyDeviceToHost, st));
         else for (int b = 0; b < B; ++b) for (int i = 0; i < cap; ++i) keep[(size_t)b * cap + i] = i < n[b];
     }
-    FBE_TRY(cudaMemcpyAsync(out_kps, d_cur, kp_bytes, cudaMemcpyDeviceToHost, st));
-    if (iters && img) FBE_TRY(cudaMemcpyAsync(iters, d_iters, total * sizeof(int), cudaMemcpyDeviceToHost, st));
-    FBE_TRY(cudaStreamSynchronize(st));
+    FBE_CUDA(cudaMemcpyAsync(out_kps, d_cur, kp_bytes, cudaMemcpyDeviceToHost, st));
+    if (iters && img) FBE_CUDA(cudaMemcpyAsync(iters, d_iters, total * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FBE_CUDA(cudaStreamSynchronize(st));
     return FBE_OK;
 }
 
