@@ -107,6 +107,8 @@ k_corner_subpix(const uint8_t* __restrict__ img, int rows, int cols, size_t step
     double* terms = smem_d + (size_t)w * (5 * nq + (pw * ph + 1) / 2);       // [5][nq] doubles, then the float patch
     float* patch = reinterpret_cast<float*>(terms + 5 * nq);
 
+    // (e + 0.5) / pw is at least 0.5 / pw away from an integer: the float product truncates to the exact quotient for these sizes
+    const float inv_pw = 1.f / (float)pw, inv_ww = 1.f / (float)ww;
     const float tx = kps[k].x, ty = kps[k].y;
     float ix = tx, iy = ty;
     int iter = 0;
@@ -123,12 +125,14 @@ k_corner_subpix(const uint8_t* __restrict__ img, int rows, int cols, size_t step
             if (ipx < 0) rx = min(-ipx, pw);
             if (!(ipx < cols - pw)) rw = max(cols - ipx - 1, 0);
         }
-        for (int e = lane; e < pw * ph; e += 32)
-            patch[e] = rect_sample(img, rows, cols, step, ipx, ipy, e / pw, e % pw, inside, rx, rw, a11, a12, a21, a22, b1, b2);
+        for (int e = lane; e < pw * ph; e += 32) {
+            const int i = (int)(((float)e + 0.5f) * inv_pw), j = e - i * pw;       // e / pw, e % pw without the emulated division
+            patch[e] = rect_sample(img, rows, cols, step, ipx, ipy, i, j, inside, rx, rw, a11, a12, a21, a22, b1, b2);
+        }
         __syncwarp();
         // ---- per-pixel terms of the 2x2 normal equations (double, like the reference)
         for (int q = lane; q < nq; q += 32) {
-            const int i = q / ww, j = q % ww;
+            const int i = (int)(((float)q + 0.5f) * inv_ww), j = q - i * ww;
             const float* sp = patch + (i + 1) * pw + (j + 1);
             const double m = (double)mask[q];
             const double tgx = (double)(sp[1] - sp[-1]);

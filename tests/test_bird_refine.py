@@ -181,6 +181,13 @@ def test_gpu_bird_refine_edge_cases(oracle, fbe):
     assert np.stack([k["x"], k["y"]], 1).tobytes() == xy.tobytes() and (it == 0).all()
     with pytest.raises(FbeError):
         BirdGuideRefine(None, img, S.as_kps(xy), (0, 5))
+    # non-finite and far-away coordinates through the filter alone: same verdicts as the oracle (NaN bounds fall back to the
+    # whole image in the reference's comparisons, +inf / far outside select an empty window)
+    odd = np.float32([[np.nan, 50], [50, np.nan], [np.nan, np.nan], [np.inf, 50], [50, -np.inf], [1e9, 1e9], [-1e9, 20], [393.9, 393.9],
+                      [394, 394], [-10, -10], [-9.99, -9.99]])
+    for c in (contour, np.zeros_like(contour), np.pad(np.full((1, 1), 200, np.uint8), ((383, 0), (383, 0)))):
+        keep, k, _ = BirdGuideRefine(c, None, S.as_kps(odd))
+        assert np.array_equal(keep, oracle.bird_near_edges(c, odd)) and len(k) == int(keep.sum())
 
 
 @pytest.mark.gpu
