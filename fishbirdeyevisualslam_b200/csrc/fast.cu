@@ -20,9 +20,11 @@
 //      min(max(I0,I8),max(I4,I12)) - c > t  or  c - max(min(I0,I8),min(I4,I12)) > t is necessary); passing pixels are
 //      appended to the warp's private work list (ballot ranks, no atomics) -- this removes the divergence of the score phase.
 //   2. SCORE the work list densely: ring differences are packed as biased s16x2 {I-c+256, c-I+256} with ONE IMAD each, so
-//      that bright and dark arcs share the DPX 3-input min/max (VIMNMX3.S16x2): 16+16 min3 + 8 max3 per pixel.
-//   3. strict 8-neighbour NMS of the listed pixels inside their cell; survivors set a bit in per-cell row masks
-//      (all survivors / survivors with score >= iniThFAST).
+//      that bright and dark arcs share the DPX 3-input min/max (VIMNMX3.S16x2): 16+16 min3 + 8 max3 per pixel.  The corners
+//      (m > minThFAST) get their score written to the score tile and are compacted IN PLACE to the front of the list.
+//   3. strict 8-neighbour NMS of the corners inside their cell (dense: no divergence on non-corners; cells are separated by
+//      a zero column in the score tile, so there are no edge cases); survivors set a bit in per-cell row masks (all
+//      survivors / survivors with score >= iniThFAST).
 //   4. EMIT: one warp per cell turns the row masks into the (y, x)-ordered slot list of the cell (ballot-free: popc +
 //      warp scan), choosing the iniThFAST mask when it is non-empty, else the minThFAST one.
 // Output per cell: survivors in (y, x) order as packed keys in the cell's private slot range + a count.  The octree
@@ -37,9 +39,13 @@ constexpr int kFastThreads = 256;
 constexpr int kFastWarps = kFastThreads / 32;
 
 constexpr int kTilePitch = 256;                             // TMA box width: staged tile column t = padded column tcol0 + t
-constexpr int kScorePitch = kFastGroupW + 8;                // score tile: column t holds strip x = t - 1 (zero margin)
+constexpr int kFastMaxCells = 7;                            // cells are >= 30 px wide, a strip <= 224 px
+constexpr int kScorePitch = 256;                            // score tile: strip pixel x of cell cj lives in column x + cj + 1 (one zero column
+                                                            // per cell edge, so NMS needs no edge cases); pitch == tile pitch, so a work-list
+                                                            // entry (py << 8 | px) addresses both tiles
 constexpr int kTileW = kTilePitch / 4;                      // in 32-bit words
 static_assert(kFastGroupW + 6 + 15 + 3 <= kTilePitch, "strip + ring halo + 16-byte alignment slack must fit the TMA box");
+static_assert(kFastGroupW + kFastMaxCells + 2 <= kScorePitch, "strip + one zero column per cell edge must fit the score tile");
 
 struct FastLayout { int off_sc, sc_bytes, off_work, work_cap, off_mask, mask_words, off_xinfo, total; };
 
@@ -128,9 +134,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast_cells(const Plan* __re
         for (int i = tid; i < (L.sc_bytes >> 4); i += kFastThreads) z[i] = make_uint4(0, 0, 0, 0);
         for (int i = tid; i < L.mask_words; i += kFastThreads) mask[i] = 0u;
         for (int x = tid; x < gw; x += kFastThreads) {
-            const int cj = x / wcell;
-            const int cx0 = cj * wcell, cx1 = min(cx0 + wcell, gw);
-            xinfo[x] = (uint8_t)(cj | (x == cx0 ? 64 : 0) | (x == cx1 - 1 ? 128 : 0));
+            xinfo[x] = (uint8_t)(x / wcell);                       // cell index of the strip column
         }
     }
     mbar_wait(&bar, 0);
@@ -203,10 +207,12 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast_cells(const Plan* __re
 
     // ---- phase 2: exact score of the listed pixels (each warp scores its own list) ---------------------------------
     const uint8_t* t0 = tile + 3 * kTilePitch + off;              // strip pixel (0,0)
-    for (int i = lane; i < nwork; i += 32) {
-        const int e = work[i];
-        const int px = e & 255, py = e >> 8;
-        const uint8_t* c = t0 + py * kTilePitch + px;
+    const unsigned lt = (1u << lane) - 1u;
+    int ncorner = 0;                                              // corners (m > lo_th) are compacted IN PLACE to work[0 .. ncorner)
+    for (int base = 0; base < nwork; base += 32) {
+        const int i = base + lane;
+        const int e = work[i < nwork ? i : base];
+        const uint8_t* c = t0 + e;                                // e = py << 8 | px and the tile pitch is 256
         const unsigned cv = c[0];
         // v = {I - c + 256 (low half), c - I + 256 (high half)}: both halves in [1, 511], no carry between them
         const unsigned K = (256u - cv) + ((cv + 256u) << 16);
@@ -228,30 +234,36 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast_cells(const Plan* __re
             M = __vimax3_s16x2(M, a, bq);
         }
         const int m = max((int)(M & 0xFFFFu), (int)(M >> 16)) - 256;
-        if (m > lo_th) sc[(py + 1) * kScorePitch + px + 1] = (uint8_t)(m - 1);
+        const bool ok = i < nwork && m > lo_th;
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        __syncwarp();                                             // every lane has read its entry before any slot is overwritten
+        if (ok) {
+            sc[e + xinfo[e & 255] + (kScorePitch + 1)] = (uint8_t)(m - 1);
+            work[ncorner + __popc(bal & lt)] = (uint16_t)e;
+        }
+        ncorner += __popc(bal);
     }
     __syncthreads();                                              // neighbours' scores come from other warps
 
     // ---- phase 3: strict 8-neighbour NMS inside the cell -> row masks -----------------------------------------------
     uint32_t* mask_ini = mask + ncell * ch * 2;
-    for (int i = lane; i < nwork; i += 32) {
+    __syncwarp();
+    for (int i = lane; i < ncorner; i += 32) {
         const int e = work[i];
         const int px = e & 255, py = e >> 8;
-        const uint8_t* q = sc + (py + 1) * kScorePitch + px + 1;
-        const int s = q[0];
-        if (s > 0) {
-            const int xi = xinfo[px];
-            int nb = max((int)q[-kScorePitch], (int)q[kScorePitch]);
-            if (!(xi & 64)) nb = max(nb, max(max((int)q[-kScorePitch - 1], (int)q[-1]), (int)q[kScorePitch - 1]));
-            if (!(xi & 128)) nb = max(nb, max(max((int)q[-kScorePitch + 1], (int)q[1]), (int)q[kScorePitch + 1]));
-            if (s > nb) {
-                const int cj = xi & 63;
-                const int xin = px - cj * wcell;
-                const int w = (cj * ch + py) * 2 + (xin >> 5);
-                const unsigned bit = 1u << (xin & 31);
-                atomicOr(&mask[w], bit);
-                if (s >= ini_th) atomicOr(&mask_ini[w], bit);
-            }
+        const int cj = xinfo[px];
+        const uint8_t* q = sc + e + cj + (kScorePitch + 1);
+        const unsigned s = q[0];
+        unsigned nb = __vimax3_u32(q[-kScorePitch - 1], q[-kScorePitch], q[-kScorePitch + 1]);
+        nb = __vimax3_u32(nb, q[-1], q[1]);
+        nb = __vimax3_u32(nb, q[kScorePitch - 1], q[kScorePitch]);
+        nb = max(nb, (unsigned)q[kScorePitch + 1]);
+        if (s > nb) {
+            const int xin = px - cj * wcell;
+            const int w = (cj * ch + py) * 2 + (xin >> 5);
+            const unsigned bit = 1u << (xin & 31);
+            atomicOr(&mask[w], bit);
+            if ((int)s >= ini_th) atomicOr(&mask_ini[w], bit);
         }
     }
     __syncthreads();
@@ -271,15 +283,16 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast_cells(const Plan* __re
         int o0 = s0 - c0, o1 = tot0 + s1 - c1;
         uint32_t* slots = ws.slots + (size_t)b * plan->slots_total + g.slot_base + (size_t)(ci * ncols + cj0 + cj) * g.cell_cap;
         const int cx = cj * wcell;
+        const uint8_t* scc = sc + cx + cj + 1;                   // score column of the cell's x = 0
         while (a0) {
             const int x = __ffsll((long long)a0) - 1;
             a0 &= a0 - 1;
-            slots[o0++] = pack_key(x0 + cx + x, y0 + r0, sc[(r0 + 1) * kScorePitch + cx + x + 1]);
+            slots[o0++] = pack_key(x0 + cx + x, y0 + r0, scc[(r0 + 1) * kScorePitch + x]);
         }
         while (a1) {
             const int x = __ffsll((long long)a1) - 1;
             a1 &= a1 - 1;
-            slots[o1++] = pack_key(x0 + cx + x, y0 + r1, sc[(r1 + 1) * kScorePitch + cx + x + 1]);
+            slots[o1++] = pack_key(x0 + cx + x, y0 + r1, scc[(r1 + 1) * kScorePitch + x]);
         }
         if (lane == 0) count_out[cj] = tot0 + tot1;
     }
@@ -289,6 +302,7 @@ int launch_fast_cells(const Plan& hp, const Plan* dp, const Workspace& ws, const
     size_t smem = 0;
     for (int l = 0; l < hp.nlevels; ++l) {
         const LevelGeom& g = hp.lv[l];
+        if (g.gcells > kFastMaxCells) { set_error("FAST strip with more than 7 cells (cells are at least 30 px wide)"); return FBE_E_UNSUPPORTED; }
         smem = std::max(smem, (size_t)fast_layout(g.gcells * g.wcell, g.hcell, g.hcell, g.gcells).total);
     }
     if (smem > 200 * 1024) { set_error("FAST strip too large for shared memory"); return FBE_E_UNSUPPORTED; }

@@ -36,6 +36,10 @@ struct fbe_pipeline {
     fbe_pair_result* h_res = nullptr;    // pinned
     // asynchronous host-buffer path: the H2D copy of step N+1 runs on its own stream beside the kernels of step N
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t out_stream = nullptr;   // D2H of the extractor outputs (keypoints + descriptors) beside the matching
+    cudaEvent_t ev_feat_done[2] = {nullptr, nullptr};    // per output set: its feature copy-out has finished
+    bool feat_used[2] = {false, false};
+    int step_seq = 0;                    // steps submitted so far (error reports)
     static constexpr int kQ = 3;         // steps in flight on the host-buffer path (input staging ring)
     uint8_t *d_front_q[kQ] = {}, *d_bird_q[kQ] = {};
     cudaEvent_t ev_in_ready[kQ] = {}, ev_in_free[kQ] = {}, ev_done[kQ] = {};
@@ -92,6 +96,8 @@ void free_all(fbe_pipeline* p) {
     if (p->h_res) cudaFreeHost(p->h_res);
     if (p->h_flags) cudaFreeHost(p->h_flags);
     if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
+    if (p->out_stream) { cudaStreamSynchronize(p->out_stream); cudaStreamDestroy(p->out_stream); }
+    for (cudaEvent_t e : {p->ev_feat_done[0], p->ev_feat_done[1]}) if (e) cudaEventDestroy(e);
     for (int k = 0; k < fbe_pipeline::kQ; ++k) {
         if (p->d_front_q[k]) cudaFree(p->d_front_q[k]);
         if (p->d_bird_q[k]) cudaFree(p->d_bird_q[k]);
@@ -113,6 +119,7 @@ int fbe_pipeline_create(const fbe_pipeline_cfg* cfg, fbe_pipeline** out) {
     if (!p) return FBE_E_INVALID;
     p->cfg = *cfg;
     p->B = cfg->batch;
+    if (cfg->front_row_cap > 0) p->row_cap = cfg->front_row_cap;
     fbe_extractor_cfg fc = cfg->front, bc = cfg->bird;
     fc.max_batch = bc.max_batch = cfg->batch + 1;
     fc.device = bc.device = cfg->device;
@@ -201,6 +208,11 @@ int fbe_pipeline_step_dev(fbe_pipeline* p, const uint8_t* d_front, const uint8_t
         FBE_CUDA(cudaStreamWaitEvent(fs, p->ev_match_done[set], 0));
         FBE_CUDA(cudaStreamWaitEvent(bs, p->ev_match_done[set], 0));
     }
+    if (p->feat_used[set]) {             // ... nor one whose copy-out to the host is still running
+        FBE_CUDA(cudaStreamWaitEvent(fs, p->ev_feat_done[set], 0));
+        FBE_CUDA(cudaStreamWaitEvent(bs, p->ev_feat_done[set], 0));
+        p->feat_used[set] = false;
+    }
     FBE_TRY(p->front.run_dev(d_front, c.front_cols, c.front_rows * c.front_cols, B, c.front_rows, c.front_cols, 1, set));
     FBE_CUDA(cudaEventRecord(p->ev_front, fs));
     FBE_TRY(p->bird.run_dev(d_bird, c.bird_cols, c.bird_rows * c.bird_cols, B, c.bird_rows, c.bird_cols, 1, set));
@@ -208,6 +220,9 @@ int fbe_pipeline_step_dev(fbe_pipeline* p, const uint8_t* d_front, const uint8_t
 
     // ---- front: pair p (slot p+1) against pair p-1 (slot p) --------------------------------------------------------
     FBE_CUDA(cudaStreamWaitEvent(ms, p->ev_front, 0));
+    // flags of THIS step only ([0] rows overflow, [1] first offending query, [2] octree workspace overflow): every fetch /
+    // wait reads them after the step's last kernel on this stream, so one dense frame does not poison the handle
+    FBE_CUDA(cudaMemsetAsync(p->flags, 0, 64, ms));
     const FrameDev fq = frame_dev(p->front, 0, set), ft = frame_dev(p->front, 1, set);
     FBE_TRY(launch_queries_from_kps(fq.kps, nullptr, nullptr, fq.n, p->fcap, B, (float)c.front_window, p->fq, p->flv, ms));
     QueryDev fqs{p->fq, p->flv, fq.desc, fq.n, p->fcap};

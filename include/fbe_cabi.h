@@ -386,6 +386,10 @@ typedef struct fbe_pipeline_cfg {
      * {k1, k2, p1, p2}.  0 = k1 == 0 behaviour: mvKeysUn = mvKeys, bounds 0 .. cols / rows. */
     int32_t front_fisheye;
     float front_K[4], front_D[4];
+    /* Candidates kept per front query in the window search (0 = 256).  The reference has no such limit: a search window that
+     * holds more keypoints than this makes THAT step fail with FBE_E_CAPACITY (reported by the fetch / wait of the step, with the
+     * offending pair in fbe_last_error(); later steps are unaffected) -- re-create the pipeline with a larger value. */
+    int32_t front_row_cap;
 } fbe_pipeline_cfg;
 
 typedef struct fbe_pair_result { /* per frame pair, fixed stride */
@@ -410,6 +414,23 @@ FBE_API int fbe_pipeline_step_host(fbe_pipeline* p, const uint8_t* h_front, cons
 FBE_API int fbe_pipeline_submit_host(fbe_pipeline* p, const uint8_t* h_front, const uint8_t* h_bird, fbe_pair_result* res,
                                      int32_t* front_matches12, int32_t* bird_matches12, int32_t* ticket);
 FBE_API int fbe_pipeline_wait(fbe_pipeline* p, int32_t ticket);
+/* The same step returning what ORBextractor::operator() returns for every frame of the batch (src/ORBextractor.cc:1041-1104:
+ * keypoints + descriptors) next to the match results: fixed-stride host arrays, entries past n_front / n_bird of a pair
+ * (fbe_pair_result) are unspecified.  Any pointer may be NULL.  The copies run on their own stream beside the matching. */
+typedef struct fbe_pipeline_features {
+    fbe_keypoint* front_kps; /* [batch][front_cap] */
+    uint8_t* front_desc;     /* [batch][front_cap][32] */
+    fbe_keypoint* bird_kps;  /* [batch][bird_cap] */
+    uint8_t* bird_desc;      /* [batch][bird_cap][32] */
+} fbe_pipeline_features;
+FBE_API int fbe_pipeline_submit_host_features(fbe_pipeline* p, const uint8_t* h_front, const uint8_t* h_bird, fbe_pair_result* res,
+                                              int32_t* front_matches12, int32_t* bird_matches12, const fbe_pipeline_features* feat,
+                                              int32_t* ticket);
+/* Device addresses of the last step's match records, for a caller that moves them between GPUs itself (NCCL all-gather of
+ * the shards' results, north_star): res = fbe_pair_result[batch], front_matches12 = int32[batch][front_cap],
+ * bird_matches12 = int32[batch][bird_cap].  Valid until the pipeline is destroyed; contents change with every step
+ * (order reads after fbe_pipeline_join() on the stream of fbe_pipeline_stream()). */
+FBE_API int fbe_pipeline_device_results(fbe_pipeline* p, void** res, void** front_matches12, void** bird_matches12);
 /* diagnostic: device milliseconds the H2D input copy of a (still current) ticket took */
 FBE_API int fbe_pipeline_copy_ms(fbe_pipeline* p, int32_t ticket, float* ms);
 FBE_API int fbe_pipeline_sync(fbe_pipeline* p);

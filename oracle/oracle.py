@@ -47,9 +47,35 @@ def lib() -> C.CDLL:
     return _lib
 
 
-def ref():
-    """The reference's own ORBextractor.cc compiled verbatim, or None when oracle/_ref was not built."""
-    global _ref
+def host_runs_timing_build() -> bool:
+    """The -O3 -march=x86-64-v3 timing variants (oracle/Makefile `timing`) need AVX2, FMA and BMI2 on the host they RUN on."""
+    try:
+        flags = set()
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                flags = set(line.split(":", 1)[1].split())
+                break
+        return {"avx2", "fma", "bmi2"} <= flags
+    except OSError:
+        return False
+
+
+_ref_o3 = None
+
+
+def ref(timing: bool = False):
+    """The reference's own ORBextractor.cc compiled verbatim, or None when oracle/_ref was not built.
+    timing=True: the -O3 -march=x86-64-v3 variant for bench.py's CPU legs (None when absent or the host lacks AVX2)."""
+    global _ref, _ref_o3
+    if timing:
+        if _ref_o3 is None:
+            path = os.path.join(HERE, "_ref", "libfbe_ref_o3.so")
+            if not os.path.exists(path) or not host_runs_timing_build():
+                return None
+            _ref_o3 = C.CDLL(path)
+            _ref_o3.ref_extractor_create.restype = C.c_void_p
+            _ref_o3.ref_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        return _ref_o3
     if _ref is None:
         path = os.path.join(HERE, "_ref", "libfbe_ref.so")
         if not os.path.exists(path):
@@ -127,10 +153,10 @@ class OracleExtractor:
 class RefExtractor:
     """The reference's ORBextractor (verbatim TU) through oracle/_ref/libfbe_ref.so."""
 
-    def __init__(self, nfeatures=1000, scale=1.2, nlevels=8, ini_th=15, min_th=5):
-        self.R = ref()
+    def __init__(self, nfeatures=1000, scale=1.2, nlevels=8, ini_th=15, min_th=5, timing=False):
+        self.R = ref(timing)
         if self.R is None:
-            raise RuntimeError("oracle/_ref/libfbe_ref.so not built")
+            raise RuntimeError("oracle/_ref/libfbe_ref%s.so not built" % ("_o3" if timing else ""))
         self.nlevels = nlevels
         self.cap = max(4 * nfeatures, 4096)
         self.h = C.c_void_p(self.R.ref_extractor_create(nfeatures, scale, nlevels, ini_th, min_th))
@@ -521,9 +547,20 @@ def rect_subpix(img, cx, cy, ww, wh):
 _refm = None
 
 
-def refmatch():
-    """ctypes handle of the verbatim matcher build, or None when oracle/_ref was not built (no /root/reference)."""
-    global _refm
+_refm_o3 = None
+
+
+def refmatch(timing: bool = False):
+    """ctypes handle of the verbatim matcher build, or None when oracle/_ref was not built (no /root/reference).
+    timing=True: the -O3 -march=x86-64-v3 variant for bench.py's CPU legs."""
+    global _refm, _refm_o3
+    if timing:
+        if _refm_o3 is None:
+            path = os.path.join(HERE, "_ref", "libfbe_refmatch_o3.so")
+            if not os.path.exists(path) or not host_runs_timing_build():
+                return None
+            _refm_o3 = C.CDLL(path)
+        return _refm_o3
     if _refm is None:
         path = os.path.join(HERE, "_ref", "libfbe_refmatch.so")
         if not os.path.exists(path):
