@@ -1,16 +1,19 @@
 #!/usr/bin/env python3
-"""bench.py -- front+bird frame-pairs/sec, ORB extract + grid + match (BASELINE.json metric, config C2/C4 shape).
+"""bench.py -- front+bird frame-pairs/sec, ORB extract + grid + match (BASELINE.json metric, config C4).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--pairs P] [--impl ours|reference]
 
-ours      : the sm_100a pipeline through the C-ABI.  One step = one batch of B synthetic front(1280x720 @2000) +
-            bird(384x384 @1000) pairs: extract both, build both grids, match every pair against the previous one
-            (front: SearchForInitialization, window 100; bird: BirdviewMatch, window 10).  `value` = device-timed
-            pairs/s with inputs resident in HBM; `e2e` = the same through HOST (pinned) buffers, H2D + D2H inside the
-            timed region.  Under torchrun each rank owns B pairs per step (weak scaling, no data-path collective).
-reference : the reference's own CPU code path on the host cores -- its ORBextractor.cc compiled verbatim
-            (oracle/_ref/libfbe_ref.so) when that was built, else the oracle port -- plus the restated matchers,
-            all host threads, a bounded sample per step.
+Workload (both arms, BASELINE.json configs[3] on the pair shape of configs[1]): an offline job of P = 4096 synthetic frame pairs
+per GPU -- front 1280x720 @2000 features + bird 384x384 @1000 features -- sharded by frame (rank r owns pairs
+[r*P, (r+1)*P); no data-path collective), processed in steps of B = 128 pairs: extract both views, build both grids, match
+every pair against its predecessor (front: SearchForInitialization, window 100; bird: BirdviewMatch, window 10).  The P
+pairs are P/B DISTINCT batches (distinct seeds per rank and batch); steps cycle through them.
+
+ours      : the sm_100a pipeline through the C-ABI.  `value` = device-timed pairs/s with all P pairs resident in HBM;
+            `e2e` = the same through HOST (pinned) buffers: every step's input H2D and the D2H of what the reference's calls
+            return (keypoints + descriptors of every frame, match lists, counts) are inside the timed region.
+reference : the reference's own CPU code on the host cores: ORBextractor.cc and ORBmatcher.cc compiled verbatim
+            (oracle/_ref, -O3 timing variants) on all host threads, a bounded sample of the same pairs per step.
 """
 from __future__ import annotations
 
@@ -22,6 +25,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 import numpy as np
 
@@ -36,11 +40,42 @@ BYTES_PER_PAIR = 5_742_040
 # pixels of all pyramid levels (what the FAST kernel reads once): front 2 853 088, bird 456 460
 PYR_PIXELS_FRONT, PYR_PIXELS_BIRD = 2_853_088, 456_460
 # dram__bytes_read.sum + dram__bytes_write.sum of one front k_fast_cells launch over 128 images (ncu --set full,
-# profiles/r1_10_fast_ncu.md): 384.76 MB + 35.90 MB
-FAST_DRAM_BYTES_PER_FRONT_IMAGE = int((384.759040e6 + 35.900416e6) / 128)
-# warp-instructions executed by the same launch (sm__inst_executed.sum of the same capture)
-FAST_WARP_INST_PER_FRONT_IMAGE = 1_063_465_360 / 128
+# profiles/r2_01_fast_blur_ncu.md): 384.72 MB + 36.17 MB
+FAST_DRAM_BYTES_PER_FRONT_IMAGE = int((384.715520e6 + 36.172544e6) / 128)
+# warp-instructions executed by the same launch (smsp__inst_executed.sum of the same capture)
+FAST_WARP_INST_PER_FRONT_IMAGE = 1_055_011_309 / 128
+FAST_PROFILE = "profiles/r2_01_fast_blur_ncu.md"
 METRIC = "front+bird frame-pairs/sec ORB extract+match at 1/2/4/8 B200 vs host CPU ref"
+WORKLOAD = ("C4: offline job of 4096 synthetic front(1280x720 @2000)+bird(384x384 @1000) frame pairs per GPU, sharded by frame; "
+            "extract + grid + frame-to-frame match (pair shape of C2)")
+
+
+def config_dict(world: int, batch: int, pairs: int) -> dict:
+    """The SAME dict in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "pairs_per_gpu": pairs, "pairs_per_step_per_gpu": batch, "distinct_batches_per_gpu": pairs // batch,
+            "seeds": "front 10000 + 100*rank + batch, bird 20000 + 100*rank + batch (synth.cheap_batch)",
+            "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
+            "l2": f"{batch * (FRONT[0] * FRONT[1] + BIRD[0] * BIRD[1]) / 1e6:.0f} MB of distinct input per step per GPU (> 126 MB L2), "
+                  f"{pairs // batch} distinct batches cycled"}
+
+
+def batch_seeds(rank: int, k: int):
+    return 10000 + 100 * rank + k, 20000 + 100 * rank + k
+
+
+def synth_batches(rank: int, nbatch: int, batch: int, out_front: np.ndarray, out_bird: np.ndarray):
+    """Fill out_front [nbatch, batch, 720, 1280] / out_bird [nbatch, batch, 384, 384] with this rank's distinct batches
+    (host threads in parallel: numpy releases the GIL inside the big array operations)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from fishbirdeyevisualslam_b200 import synth
+
+    def one(k):
+        sf, sb = batch_seeds(rank, k)
+        out_front[k] = synth.cheap_batch(batch, FRONT[0], FRONT[1], sf)
+        out_bird[k] = synth.cheap_batch(batch, BIRD[0], BIRD[1], sb)
+
+    with ThreadPoolExecutor(min(nbatch, max(2, (os.cpu_count() or 4)))) as ex:
+        list(ex.map(one, range(nbatch)))
 
 
 def peaks():
@@ -127,12 +162,30 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
+def _cpu_libs():
+    """(extractor factory, matcher, kind, build) -- the verbatim reference builds (timing variants when the host runs them),
+    else the oracle port."""
+    from oracle import oracle as O
+    O.lib()
+    if O.ref(True) is not None and O.refmatch(True) is not None:
+        return (lambda nf: O.RefExtractor(nf, 1.2, 8, 15, 5, timing=True)), O.RefMatch(O.refmatch(True)), "reference", \
+            "verbatim ORBextractor.cc + ORBmatcher.cc, g++ -O3 -march=x86-64-v3 -ffp-contract=off, scalar OpenCV shim"
+    if O.ref() is not None and O.refmatch() is not None:
+        return (lambda nf: O.RefExtractor(nf, 1.2, 8, 15, 5)), O.RefMatch(O.refmatch()), "reference", \
+            "verbatim ORBextractor.cc + ORBmatcher.cc, g++ -O2 -ffp-contract=off, scalar OpenCV shim"
+
+    class _Port:
+        search_for_initialization = staticmethod(O.search_for_initialization)
+        birdview_match = staticmethod(O.birdview_match)
+        grid_assign = staticmethod(O.grid_assign)
+    return (lambda nf: O.OracleExtractor(nf, 1.2, 8, 15, 5)), _Port, "port", "oracle restatement, g++ -O2"
+
+
 def _cpu_worker(args):
     """extract front+bird for a run of consecutive pairs and match each against its predecessor, on one host thread"""
     from fishbirdeyevisualslam_b200.matcher import Frame
-    from oracle import oracle as O
-    fronts, birds, use_ref = args
-    mk = (lambda nf: O.RefExtractor(nf, 1.2, 8, 15, 5)) if use_ref else (lambda nf: O.OracleExtractor(nf, 1.2, 8, 15, 5))
+    fronts, birds = args
+    mk, M, _, _ = _cpu_libs()
     ef, eb = mk(FRONT_FEATURES), mk(BIRD_FEATURES)
     prev = None
     nm = 0
@@ -140,57 +193,123 @@ def _cpu_worker(args):
         kf, df = ef(f)
         kb, db = eb(b)
         F, Bf = Frame.front(kf, df, FRONT[1], FRONT[0]), Frame.bird(kb, db, BIRD[1], BIRD[0])
-        O.grid_assign(kf, F.min_x, F.min_y, F.inv_w, F.inv_h, 64, 48)
-        O.grid_assign(kb, 0.0, 0.0, Bf.inv_w, Bf.inv_h, 32, 32)
+        M.grid_assign(kf, F.min_x, F.min_y, F.inv_w, F.inv_h, 64, 48)          # Frame::AssignFeaturesToGrid (also runs inside the
+        M.grid_assign(kb, 0.0, 0.0, Bf.inv_w, Bf.inv_h, 32, 32)                # matcher wrapper's Frame construction)
         if prev is not None:
             pm = np.ascontiguousarray(np.stack([prev[0].kps["x"], prev[0].kps["y"]], 1), np.float32)
-            nm += O.search_for_initialization(prev[0], F, pm, 100, 0.9, True)[0]
-            nm += O.birdview_match(prev[1].kps, prev[1].desc, Bf, 10, 0.9, True)[0]
+            nm += M.search_for_initialization(prev[0], F, pm, 100, 0.9, True)[0]
+            nm += M.birdview_match(prev[1].kps, prev[1].desc, Bf, 10, 0.9, True)[0]
         prev = (F, Bf)
     return nm
 
 
-def cpu_reference_rate(pairs_per_thread: int, threads: int, repeats: int = 1):
-    """-> (pairs/s, kind, cores).  ctypes releases the GIL, so plain threads use all cores."""
+def cpu_reference_rate(fr, bi, pairs_per_thread: int, threads: int):
+    """-> pairs/s of `threads` host threads each working through `pairs_per_thread` consecutive pairs of (fr, bi).
+    ctypes releases the GIL, so plain threads use all cores."""
     from concurrent.futures import ThreadPoolExecutor
-    from fishbirdeyevisualslam_b200 import synth
-    from oracle import oracle as O
-    O.lib()
-    use_ref = O.ref() is not None
-    fr = synth.cheap_batch(pairs_per_thread * threads, FRONT[0], FRONT[1], 11)
-    bi = synth.cheap_batch(pairs_per_thread * threads, BIRD[0], BIRD[1], 12)
-    jobs = [(fr[t * pairs_per_thread:(t + 1) * pairs_per_thread], bi[t * pairs_per_thread:(t + 1) * pairs_per_thread], use_ref)
-            for t in range(threads)]
-    best = None
-    with ThreadPoolExecutor(threads) as ex:
-        for _ in range(repeats):
-            t0 = time.perf_counter()
+    n = len(fr)
+    jobs = []
+    for t in range(threads):
+        idx = [(t * pairs_per_thread + j) % n for j in range(pairs_per_thread)]
+        jobs.append((fr[idx], bi[idx]))
+    _cpu_libs()
+    t0 = time.perf_counter()
+    if threads == 1:
+        _cpu_worker(jobs[0])
+    else:
+        with ThreadPoolExecutor(threads) as ex:
             list(ex.map(_cpu_worker, jobs))
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-    return pairs_per_thread * threads / best, ("reference" if use_ref else "port"), threads
+    return pairs_per_thread * threads / (time.perf_counter() - t0)
+
+
+def cv2_primitives_ms(front: np.ndarray, bird: np.ndarray):
+    """Second data point: the OpenCV primitives the reference calls, through SIMD-tuned cv2 on ONE thread --
+    ComputePyramid (resize + copyMakeBorder), the per-cell FAST calls with threshold fallback, GaussianBlur -- for one
+    front+bird pair.  The shim primitives of the verbatim build are scalar; this bounds what a tuned OpenCV build saves."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    cv2.setNumThreads(1)
+    ini, mn = cv2.FastFeatureDetector_create(15, True), cv2.FastFeatureDetector_create(5, True)
+    out = {"pyramid": 0.0, "fast_per_cell": 0.0, "blur": 0.0}
+    for img in (front, bird):
+        t0 = time.perf_counter()
+        levels = []
+        h0, w0 = img.shape
+        sc = 1.0
+        for l in range(8):
+            w, h = int(round(w0 / sc)), int(round(h0 / sc))
+            src = img if l == 0 else cv2.resize(levels[-1][19:-19, 19:-19], (w, h), interpolation=cv2.INTER_LINEAR)
+            levels.append(cv2.copyMakeBorder(src, 19, 19, 19, 19, cv2.BORDER_REFLECT_101))
+            sc *= 1.2
+        t1 = time.perf_counter()
+        for lv in levels:                                        # the reference's cell loop (src/ORBextractor.cc:765-829)
+            H, W = lv.shape[0] - 38, lv.shape[1] - 38
+            minb, maxbx, maxby = 16, W - 16, H - 16
+            ncols, nrows = (maxbx - minb) // 30, (maxby - minb) // 30
+            wc, hc = -(-(maxbx - minb) // ncols), -(-(maxby - minb) // nrows)
+            for i in range(nrows):
+                iy = minb + i * hc
+                if iy >= maxby - 3:
+                    continue
+                my = min(iy + hc + 6, maxby)
+                for j in range(ncols):
+                    ix = minb + j * wc
+                    if ix >= maxbx - 6:
+                        continue
+                    mx = min(ix + wc + 6, maxbx)
+                    cell = lv[19 + iy:19 + my, 19 + ix:19 + mx]
+                    if not ini.detect(cell):
+                        mn.detect(cell)
+        t2 = time.perf_counter()
+        for lv in levels:
+            cv2.GaussianBlur(lv[19:-19, 19:-19], (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+        t3 = time.perf_counter()
+        out["pyramid"] += 1e3 * (t1 - t0); out["fast_per_cell"] += 1e3 * (t2 - t1); out["blur"] += 1e3 * (t3 - t2)
+    out["total_ms_per_pair"] = sum(out.values())
+    out["note"] = "cv2 %s, setNumThreads(1); per-cell FAST includes the Python call overhead of ~3000 cv2 calls per pair" % cv2.__version__
+    return out
+
+
+def cpu_baseline_block(fr, bi):
+    """cpu_baseline of the 1-GPU line: all host threads (the headline `value`), one core, and the cv2-primitive data point."""
+    threads = os.cpu_count() or 1
+    _, _, kind, build = _cpu_libs()
+    one = cpu_reference_rate(fr, bi, 6, 1)                       # ~1.6 core-seconds
+    per_thread = 6
+    allc = cpu_reference_rate(fr, bi, per_thread, threads)       # ~1.6 s of wall time, ~1.6 x threads core-seconds
+    prim = cv2_primitives_ms(fr[0], bi[0])
+    return {"value": allc, "unit": "pairs/s", "cores": threads, "kind": kind, "build": build,
+            "sample": f"{per_thread * threads} pairs of rank 0's batch 0 ({per_thread} consecutive pairs on each of {threads} host threads)",
+            "one_core": {"value": one, "unit": "pairs/s", "cores": 1, "sample": "6 consecutive pairs on one thread"},
+            "all_cores": {"value": allc, "unit": "pairs/s", "cores": threads},
+            "cv2_primitives_one_core": prim}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    from fishbirdeyevisualslam_b200 import synth
     threads = os.cpu_count() or 1
     per_thread = 4
+    sf, sb = batch_seeds(0, 0)
+    fr, bi = synth.cheap_batch(args.batch, FRONT[0], FRONT[1], sf), synth.cheap_batch(args.batch, BIRD[0], BIRD[1], sb)
+    _, _, kind, build = _cpu_libs()
     rates = []
-    kind = "port"
     for i in range(args.warmup + args.steps):
-        r, kind, _ = cpu_reference_rate(per_thread, threads)
+        r = cpu_reference_rate(fr, bi, per_thread, threads)
         if i >= args.warmup:
             rates.append(r)
     v = statistics.median(rates)
-    sample = f"{per_thread * threads} pairs per step ({per_thread} consecutive pairs on each of {threads} threads)"
+    sample = f"{per_thread * threads} pairs of rank 0's batch 0 per step ({per_thread} consecutive pairs on each of {threads} threads)"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * per_thread * threads / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "C2/C4: 1280x720@2000 front + 384x384@1000 bird, extract + grid + frame-to-frame match",
-                       "note": "reference CPU code path on host cores (not a GPU run)"},
-            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind, "sample": sample},
+            "config": config_dict(args.gpus, args.batch, args.pairs),
+            "note": "reference CPU code path on the host cores (not a GPU run); each step is a bounded sample of the workload",
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind, "build": build, "sample": sample},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -225,10 +344,45 @@ def bind_to_gpu_numa(index):
 
 
 # ------------------------------------------------------------------------------------------------------- our arm
+def parity_check(pipe_cls, hF_last, hB_last, feat, res, fm, bm, pairs):
+    """In-run parity: the e2e loop's LAST step (what the public host-buffer call actually returned) against the CPU oracle for a
+    few sampled pairs -- keypoints, descriptors, match lists, counts, byte for byte."""
+    from fishbirdeyevisualslam_b200.matcher import Frame
+    from oracle import oracle as O
+    of, ob = O.OracleExtractor(FRONT_FEATURES, 1.2, 8, 15, 5), O.OracleExtractor(BIRD_FEATURES, 1.2, 8, 15, 5)
+    fk, fd, bk, bd = feat
+    ok = True
+    detail = []
+    crc = 0
+    for p in pairs:
+        frames = []
+        for q in (p - 1, p):
+            kf, df = of(hF_last[q])
+            kb, db = ob(hB_last[q])
+            nf, nb = int(res["n_front"][q]), int(res["n_bird"][q])
+            same = (nf == len(kf) and nb == len(kb) and fk[q][:nf].tobytes() == kf.tobytes() and np.array_equal(fd[q][:nf], df)
+                    and bk[q][:nb].tobytes() == kb.tobytes() and np.array_equal(bd[q][:nb], db))
+            ok &= bool(same)
+            crc = zlib.crc32(fk[q][:nf].tobytes() + fd[q][:nf].tobytes() + bk[q][:nb].tobytes() + bd[q][:nb].tobytes(), crc)
+            frames.append((Frame.front(kf, df, FRONT[1], FRONT[0]), Frame.bird(kb, db, BIRD[1], BIRD[0])))
+        (F0, B0), (F1, B1) = frames
+        pm = np.ascontiguousarray(np.stack([F0.kps["x"], F0.kps["y"]], 1), np.float32)
+        n_o, m_o = O.search_for_initialization(F0, F1, pm, 100, 0.9, True)
+        nb_o, d_o = O.birdview_match(B0.kps, B0.desc, B1, 10, 0.9, True)
+        gm = bm[p][:B0.N]
+        same = (int(res["front_matches"][p]) == n_o and np.array_equal(fm[p][:F0.N], m_o) and int(res["bird_matches"][p]) == nb_o
+                and np.array_equal(np.stack([np.nonzero(gm > 0)[0], gm[gm > 0]], 1), d_o[:, :2]))
+        ok &= bool(same)
+        crc = zlib.crc32(fm[p][:F0.N].tobytes() + gm.tobytes(), crc)
+        detail.append({"pair": int(p), "front_kps": int(F1.N), "bird_kps": int(B1.N), "front_matches": int(n_o), "bird_matches": int(nb_o)})
+    return {"parity": bool(ok), "pairs_checked": detail, "crc32_of_checked_outputs": crc & 0xFFFFFFFF,
+            "against": "oracle (CPU restatement pinned to the verbatim reference build), on the outputs the last e2e step returned"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from fishbirdeyevisualslam_b200 import _lib, synth
+    from fishbirdeyevisualslam_b200 import _lib, shard
     from fishbirdeyevisualslam_b200.pipeline import FrontBirdPipeline, PinnedBuffer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -246,147 +400,232 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = _lib.load()
     B = args.batch
+    nbatch = max(1, args.pairs // B)
+    pairs = nbatch * B
+    t_setup = time.perf_counter()
     pipe = FrontBirdPipeline(B, FRONT, BIRD, FRONT_FEATURES, BIRD_FEATURES, device=local)
-    fr = synth.cheap_batch(B, FRONT[0], FRONT[1], 100 + rank)
-    bi = synth.cheap_batch(B, BIRD[0], BIRD[1], 200 + rank)
-    dF, dB = torch.from_numpy(fr).cuda(), torch.from_numpy(bi).cuda()
+    # this rank's P pairs: pinned host copy (e2e inputs) + device-resident copy (`value` inputs)
+    hF, hB = PinnedBuffer((nbatch, B) + FRONT), PinnedBuffer((nbatch, B) + BIRD)
+    synth_batches(rank, nbatch, B, hF.array, hB.array)
+    dF = torch.empty((nbatch, B) + FRONT, dtype=torch.uint8, device="cuda")
+    dB = torch.empty((nbatch, B) + BIRD, dtype=torch.uint8, device="cuda")
+    dF.copy_(torch.from_numpy(hF.array), non_blocking=True)
+    dB.copy_(torch.from_numpy(hB.array), non_blocking=True)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
     stream = torch.cuda.ExternalStream(pipe.stream_ptr, device=local)
+    fstride, bstride = B * FRONT[0] * FRONT[1], B * BIRD[0] * BIRD[1]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- device-resident throughput (`value`) ------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        pipe.step_dev(dF.data_ptr(), dB.data_ptr())
+    W = max(args.warmup, 3)
+    for i in range(W):
+        pipe.step_dev(dF.data_ptr() + (i % nbatch) * fstride, dB.data_ptr() + (i % nbatch) * bstride)
     pipe.sync()
     pipe._L.fbe_pipeline_stage_timing(pipe._h, 1)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = L.fbe_kernel_launch_count()
     clk = ClockSampler(local)
-    clk.__enter__()                      # samples through BOTH timed regions (device-resident loop and e2e loop)
-    if True:
-        e0.record(stream)
-        for _ in range(args.steps):
-            pipe.step_dev(dF.data_ptr(), dB.data_ptr())
-        pipe.join()           # a step ends on the pipeline's matching stream: order the public stream after it
-        e1.record(stream)
-        pipe.sync()
-        barrier()
+    clk.__enter__()                      # samples through ALL timed regions (device-resident loop and the e2e loops)
+    e0.record(stream)
+    for i in range(args.steps):
+        k = (W + i) % nbatch
+        pipe.step_dev(dF.data_ptr() + k * fstride, dB.data_ptr() + k * bstride)
+    pipe.join()               # a step ends on the pipeline's matching stream: order the public stream after it
+    e1.record(stream)
+    pipe.sync()
+    barrier()
     launches = L.fbe_kernel_launch_count() - launches0
-    ms = e0.elapsed_time(e1)
     import ctypes as C
     stage = (C.c_double * 12)()
     nst = C.c_int32()
     pipe._L.fbe_pipeline_stage_ms(pipe._h, stage, C.byref(nst))
     pipe._L.fbe_pipeline_stage_timing(pipe._h, 0)
-    res, _, _ = pipe.fetch(with_matches=False)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    res_dev, _, _ = pipe.fetch(with_matches=False)
+    ms = allmax(e0.elapsed_time(e1))
     value = world * B * args.steps / (ms * 1e-3)
 
+    # ---- the north_star collective: NCCL all-gather of the last step's match records (outside `value`) -----------
+    rec_bytes = shard.match_record_bytes(pipe.front_cap, pipe.bird_cap)
+    shard.gather_matches(pipe, world)
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    g0.record()
+    NG = 10
+    for _ in range(NG):
+        gres, gfm, gbm = shard.gather_matches(pipe, world)
+    g1.record()
+    torch.cuda.synchronize()
+    gather_ms = allmax(g0.elapsed_time(g1) / NG)
+
     # ---- end to end through host buffers (`e2e`) ----------------------------------------------------------------
-    # The public host-buffer API: submit(step i) enqueues H2D of the inputs, the step and D2H of the results; wait(i-1)
-    # collects the previous step.  Inputs and results live in pinned host memory; every step's H2D + D2H is inside the
+    # The public host-buffer API: submit(step i) enqueues H2D of the inputs, the step and D2H of the results; wait(i-2)
+    # collects an earlier step.  Inputs and results live in pinned host memory; every step's H2D + D2H is inside the
     # timed region (three steps in flight, so the copies of steps i+1, i+2 travel while step i computes).
     NBUF = 3
-    hF, hB = PinnedBuffer(fr.shape), PinnedBuffer(bi.shape)
-    hF.array[...] = fr
-    hB.array[...] = bi
     hres = [PinnedBuffer((B,), _lib.PAIR_RESULT_DTYPE) for _ in range(NBUF)]
     hfm = [PinnedBuffer((B, pipe.front_cap), np.int32) for _ in range(NBUF)]
     hbm = [PinnedBuffer((B, pipe.bird_cap), np.int32) for _ in range(NBUF)]
+    hfeat = [(PinnedBuffer((B, pipe.front_cap), _lib.KP_DTYPE), PinnedBuffer((B, pipe.front_cap, 32), np.uint8),
+              PinnedBuffer((B, pipe.bird_cap), _lib.KP_DTYPE), PinnedBuffer((B, pipe.bird_cap, 32), np.uint8)) for _ in range(NBUF)]
 
-    def e2e_loop(n):
+    def e2e_loop(n, first, with_features):
         q = []
         for i in range(n):
-            k = i % NBUF
-            q.append(pipe.submit_host(hF.ptr, hB.ptr, hres[k].array, hfm[k].array, hbm[k].array))
+            j = i % NBUF
+            k = (first + i) % nbatch
+            feats = tuple(b.array for b in hfeat[j]) if with_features else None
+            q.append(pipe.submit_host(hF.ptr + k * fstride, hB.ptr + k * bstride, hres[j].array, hfm[j].array, hbm[j].array, features=feats))
             if len(q) >= NBUF:
-                pipe.wait(q.pop(0))           # the results of step i - 2 are now in hres / hfm / hbm [k']
+                pipe.wait(q.pop(0))           # the results of step i - 2 are now in the host buffers
         for t in q:
             pipe.wait(t)
 
-    e2e_loop(4)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loop(args.steps)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    def timed_e2e(with_features):
+        e2e_loop(4, 0, with_features)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(args.steps, 4, with_features)
+        torch.cuda.synchronize()
+        return world * B * args.steps / allmax(time.perf_counter() - t0)
+
+    e2e_matches_only = timed_e2e(False)
+    e2e_value = timed_e2e(True)
     clk.__exit__(None, None, None)
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(t.item())
-    h2d = int(fr.nbytes + bi.nbytes)
-    d2h = int(hres[0].nbytes + hfm[0].nbytes + hbm[0].nbytes)
-    # what the host link gives a plain pinned->device copy of the same bytes (the ceiling of any host-buffer path)
+    h2d = int(fstride + bstride)
+    d2h_matches = int(hres[0].nbytes + hfm[0].nbytes + hbm[0].nbytes)
+    d2h_feat = int(sum(b.nbytes for b in hfeat[0]))
+    # what the host link gives a plain pinned->device copy of the same bytes (the ceiling of any host-buffer path), every rank
+    # copying at the same time
     hp = torch.empty(h2d, dtype=torch.uint8, pin_memory=True)
     dp = torch.empty(h2d, dtype=torch.uint8, device="cuda")
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dp.copy_(hp, non_blocking=True)
-    torch.cuda.synchronize()
+    barrier()
     c0.record()
     for _ in range(5):
         dp.copy_(hp, non_blocking=True)
     c1.record()
     torch.cuda.synchronize()
     link_gbs = 5 * h2d / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    link_all = [link_gbs]
+    if world > 1:
+        lt = torch.tensor([link_gbs], dtype=torch.float64, device="cuda")
+        lall = [torch.zeros_like(lt) for _ in range(world)]
+        dist.all_gather(lall, lt)
+        link_all = [float(x.item()) for x in lall]
     del hp, dp
+
+    # ---- checks (outside every timed region) -----------------------------------------------------------------------
+    # (1) parity of what the last e2e step returned, against the CPU oracle (rank 0)
+    last_i = args.steps - 1
+    last_j, last_k = last_i % NBUF, (4 + last_i) % nbatch
+    check = {}
+    if rank == 0:
+        lastres = hres[last_j].array
+        check = {"mean_front_kps": float(lastres["n_front"].mean()), "mean_bird_kps": float(lastres["n_bird"].mean()),
+                 "mean_front_matches": float(lastres["front_matches"][1:].mean()), "mean_bird_matches": float(lastres["bird_matches"][1:].mean())}
+        sample = sorted({1, B // 3, (2 * B) // 3, B - 1} - {0})
+        check.update(parity_check(FrontBirdPipeline, hF.array[last_k], hB.array[last_k], tuple(b.array for b in hfeat[last_j]),
+                                  lastres, hfm[last_j].array, hbm[last_j].array, sample))
+    # (2) sharded == single: every rank runs its batches 0 and 1 on a FRESH pipeline and the records are all-gathered on the
+    #     device; rank 0 then re-computes the LAST rank's two batches itself (regenerated from their seeds) and compares bytes
+    vp = FrontBirdPipeline(B, FRONT, BIRD, FRONT_FEATURES, BIRD_FEATURES, device=local)
+    gathered = []
+    for k in range(min(2, nbatch)):
+        vp.step_dev(dF.data_ptr() + k * fstride, dB.data_ptr() + k * bstride)
+        gathered.append(tuple(t.cpu().numpy() for t in shard.gather_matches(vp, world)))
+    vp.close()
+    if rank == 0:
+        src = world - 1
+        if src == 0:
+            rf, rb = hF.array[:2], hB.array[:2]
+        else:
+            rf = np.empty((min(2, nbatch), B) + FRONT, np.uint8)
+            rb = np.empty((min(2, nbatch), B) + BIRD, np.uint8)
+            synth_batches(src, min(2, nbatch), B, rf, rb)
+        sp = FrontBirdPipeline(B, FRONT, BIRD, FRONT_FEATURES, BIRD_FEATURES, device=local)
+        same = True
+        for k in range(min(2, nbatch)):
+            tF, tB = torch.from_numpy(rf[k]).cuda(), torch.from_numpy(rb[k]).cuda()
+            sp.step_dev(tF.data_ptr(), tB.data_ptr())
+            r1, f1, b1 = sp.fetch()
+            g = gathered[k]
+            same &= g[0][src].tobytes() == r1.tobytes()
+            for p in range(B):
+                if k == 0 and p == 0:
+                    continue                                    # the first pair of a run has no predecessor: its lists are unspecified
+                nq = int(r1["n_front"][p - 1]) if p else int(gathered[k - 1][0][src][B - 1][0])
+                nb = int(r1["n_bird"][p - 1]) if p else int(gathered[k - 1][0][src][B - 1][1])
+                same &= bool(np.array_equal(g[1][src][p][:nq], f1[p][:nq]) and np.array_equal(g[2][src][p][:nb], b1[p][:nb]))
+        sp.close()
+        check["sharded_equals_single"] = bool(same)
+        check["sharded_equals_single_what"] = (f"rank {src}'s first {min(2, nbatch) * B} pairs: NCCL-gathered device records vs rank 0 recomputing them "
+                                               "alone on a fresh pipeline (counts + front / bird match lists, bytes)")
+    barrier()
 
     if rank == 0:
         peak, peak_src = peaks()
         n = max(nst.value, 1)
-        names = ["pyramid", "fast_cells", "octree", "describe", "grid", "blur"]
-        stage_ms = {("front_" + names[i]): stage[i] / n for i in range(6)}
-        stage_ms.update({("bird_" + names[i]): stage[6 + i] / n for i in range(6)})
+        fast_ms = stage[1] / n
         # dominant kernel = FAST cells of the front extractor: one launch reads every pyramid pixel of B images once
-        fast_ms = stage_ms["front_fast_cells"]
         alg_bytes = B * PYR_PIXELS_FRONT
         achieved = alg_bytes / (fast_ms * 1e-3) / 1e9 if fast_ms > 0 else 0.0
-        # CPU baseline beside it (bounded sample: ~2 pairs per host thread)
-        threads = os.cpu_count() or 1
-        CPU_PAIRS_PER_THREAD = 8            # ~20 core-seconds of the reference CPU path, ~1.3 s of wall time on 16 threads
         if world == 1:
-            cpu_rate, kind, cores = cpu_reference_rate(CPU_PAIRS_PER_THREAD, threads)
-            cpu_sample = f"{CPU_PAIRS_PER_THREAD * threads} pairs ({CPU_PAIRS_PER_THREAD} consecutive pairs on each of {threads} host threads)"
+            cpu = cpu_baseline_block(hF.array[0], hB.array[0])
         else:                               # the CPU baseline is a property of the host, measured once: on the 1-GPU line
-            cpu_rate, kind, cores, cpu_sample = None, "reference", 0, "measured at N=1 only (see the 1-GPU line / --impl reference)"
-        line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            cpu = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "reference", "sample": "measured at N=1 only (see the 1-GPU line / --impl reference)"}
+        sm_mhz = clk.summary().get("sm_mhz") or 1965.0
+        issue_peak = 148 * 4 * sm_mhz * 1e6
+        line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",
-                "config": {"workload": "C2/C4: 1280x720@2000 front + 384x384@1000 bird, extract + grid + frame-to-frame match",
-                           "pairs_per_step_per_gpu": B, "parallelism": f"frames sharded over {world} GPU(s), no collective",
-                           "l2": f"inputs {h2d / 1e6:.0f} MB per step per GPU (> 126 MB L2)" if h2d > 126e6 else "inputs smaller than L2: raise --batch"},
-                "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "h2d_link_gbs_measured": link_gbs, "h2d_gbs_used": e2e_value / world * (h2d / B) / 1e9,
-                        "host_numa_node_rank0": numa_node,
+                "config": config_dict(world, B, pairs),
+                "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_matches + d2h_feat,
+                        "returns": "per frame keypoints + descriptors (what ORBextractor::operator() returns), per pair match index lists + counts",
+                        "with_features": {"value": e2e_value, "d2h_bytes_per_step": d2h_matches + d2h_feat},
+                        "matches_only": {"value": e2e_matches_only, "d2h_bytes_per_step": d2h_matches},
+                        "h2d_link_gbs_measured": link_gbs, "h2d_link_gbs_measured_per_rank": link_all,
+                        "h2d_gbs_used": e2e_value / world * (h2d / B) / 1e9, "host_numa_node_rank0": numa_node,
                         "note": "three steps in flight: the input copies of the next steps overlap the kernels of step i; bound = max(copy, compute)"},
                 "gpu_launches": int(launches),
                 "clocks": clk.summary(),
                 "roofline": {"bound": "hbm", "kernel": "k_fast_cells (front)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": FAST_DRAM_BYTES_PER_FRONT_IMAGE * B, "peak_source": peak_src,
-                             "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of k_fast_cells (front), per image x images per launch; profiles/r1_10_fast_ncu.md",
+                             "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of k_fast_cells (front), per image x images per launch; " + FAST_PROFILE,
                              "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": fast_ms,
-                             "note": "k_fast_cells is instruction-bound, not memory-bound: ncu (profiles/r1_10_fast_ncu.md) shows 77 % issue-slot "
-                                     "utilisation, 72 % alu pipe, 3.0 warp-instructions per SM per clock and 4 % of DRAM throughput; ~90 integer "
+                             "note": "k_fast_cells is bound by the integer ALU pipe, not by memory: ncu (" + FAST_PROFILE + ") shows 81 % issue-slot "
+                                     "utilisation, 74 % alu pipe (VIMNMX3 / PRMT run at half rate) and 4 % of DRAM throughput; ~90 integer "
                                      "instructions per pixel bound it, so frac of the HBM peak stays small by construction",
                              "issue": {"what": "the roof this kernel actually sits under: warp-instruction issue (148 SMs x 4 schedulers x SM clock)",
-                                       "achieved_gwarp_inst_s": FAST_WARP_INST_PER_FRONT_IMAGE * B / (fast_ms * 1e-3) / 1e9,
-                                       "peak_gwarp_inst_s": 148 * 4 * (clk.summary().get("sm_mhz") or 1965.0) * 1e6 / 1e9,
-                                       "frac": FAST_WARP_INST_PER_FRONT_IMAGE * B / (fast_ms * 1e-3) / (148 * 4 * (clk.summary().get("sm_mhz") or 1965.0) * 1e6),
-                                       "source": "sm__inst_executed.sum of one launch (ncu --set full, profiles/r1_10_fast_ncu.md) / live launch time"},
+                                       "achieved_gwarp_inst_s": FAST_WARP_INST_PER_FRONT_IMAGE * B / (fast_ms * 1e-3) / 1e9 if fast_ms > 0 else 0.0,
+                                       "peak_gwarp_inst_s": issue_peak / 1e9,
+                                       "frac": FAST_WARP_INST_PER_FRONT_IMAGE * B / (fast_ms * 1e-3) / issue_peak if fast_ms > 0 else 0.0,
+                                       "source": "smsp__inst_executed.sum of one launch (ncu --set full, " + FAST_PROFILE + ") / live launch time"},
                              "whole_step": {"bytes_per_pair": BYTES_PER_PAIR, "achieved_gbs": value / world * BYTES_PER_PAIR / 1e9,
                                             "frac": value / world * BYTES_PER_PAIR / 1e9 / peak}},
-                "stage_ms": stage_ms,
-                "cpu_baseline": {"value": cpu_rate, "unit": "pairs/s", "cores": cores, "kind": kind,
-                                 "sample": cpu_sample},
-                "check": {"mean_front_kps": float(res["n_front"].mean()), "mean_bird_kps": float(res["n_bird"].mean()),
-                          "mean_front_matches": float(res["front_matches"].mean()), "mean_bird_matches": float(res["bird_matches"].mean())}}
+                "stage_ms": {"front_fast_cells": fast_ms,
+                             "note": "CUDA events around the front FAST launch on its own (highest-priority) stream: agrees with the ncu launch "
+                                     "time. The other stages overlap across four streams, so their event spans are neither additive nor kernel "
+                                     "times and are not reported (see the ncu launch list under profiles/)"},
+                "gather": {"what": "NCCL all_gather_into_tensor of the last step's fixed-stride match records, device-resident (no host staging); outside `value`",
+                           "ms": gather_ms, "record_bytes_per_pair": rec_bytes, "bytes_per_rank": rec_bytes * B,
+                           "algbw_gbs": rec_bytes * B * world / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else None, "ranks": world},
+                "cpu_baseline": cpu,
+                "setup_s": setup_s,
+                "check": check}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
@@ -400,9 +639,10 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=128, help="frame pairs per step per GPU")
+    ap.add_argument("--pairs", type=int, default=4096, help="distinct frame pairs per GPU (the offline job of config C4)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":

@@ -49,7 +49,13 @@ class PipelineCfg(C.Structure):
                 ("front_rows", C.c_int32), ("front_cols", C.c_int32), ("bird_rows", C.c_int32), ("bird_cols", C.c_int32),
                 ("batch", C.c_int32), ("nn_ratio", C.c_float), ("check_orientation", C.c_int32),
                 ("front_window", C.c_int32), ("bird_window", C.c_int32), ("device", C.c_int32),
-                ("front_fisheye", C.c_int32), ("front_K", C.c_float * 4), ("front_D", C.c_float * 4)]
+                ("front_fisheye", C.c_int32), ("front_K", C.c_float * 4), ("front_D", C.c_float * 4),
+                ("front_row_cap", C.c_int32)]
+
+
+class PipelineFeatures(C.Structure):
+    """fbe_pipeline_features: host buffers for the extractor outputs of one step (any pointer may be NULL)."""
+    _fields_ = [("front_kps", C.c_void_p), ("front_desc", C.c_void_p), ("bird_kps", C.c_void_p), ("bird_desc", C.c_void_p)]
 
 
 PAIR_RESULT_DTYPE = np.dtype([("n_front", "<i4"), ("n_bird", "<i4"), ("front_matches", "<i4"), ("bird_matches", "<i4")])

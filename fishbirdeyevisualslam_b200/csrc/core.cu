@@ -212,6 +212,7 @@ int ExtractorCore::run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, in
             if (_e != cudaSuccess) { set_error(std::string("stage ") + name + ": " + cudaGetErrorString(_e)); return FBE_E_CUDA; } \
         }                                                                                                \
     } while (0)
+    FBE_CUDA(cudaMemsetAsync(v.status, 0, (size_t)nimg * sizeof(int), stream));   // octree workspace-overflow flags of THIS run
     FBE_MARK(0, stream);
     if ((rc = launch_pyramid(hplan, dplan, v, dtab, *rs_maps, nimg, stream)) != FBE_OK) return rc;
     FBE_MARK(1, stream);

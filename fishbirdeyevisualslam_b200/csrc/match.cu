@@ -132,7 +132,10 @@ __global__ void __launch_bounds__(256, 6) k_window_rows(FrameDev f, QueryDev qs,
     }
     if ((threadIdx.x & 31) == 0) {
         cnt[qoff] = min(total, C);
-        if (total > C) atomicExch(overflow, 1);
+        if (total > C) {                      // overflow[0] = flag, overflow[4] = 1 + (problem << 16 | query) of one offender
+            atomicExch(overflow, 1);
+            atomicMax(overflow + 4, ((b << 16) | min(qi, 0xFFFF)) + 1);
+        }
     }
 }
 

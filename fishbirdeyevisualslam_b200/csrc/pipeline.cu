@@ -9,6 +9,7 @@
 // latency-bound tail of step N (window rows, sequential resolve, bird top-2) overlaps the extraction of step N+1.
 #include <cstring>
 #include <new>
+#include <string>
 #include "match_kernels.cuh"
 
 using namespace fbe;
@@ -44,6 +45,8 @@ struct fbe_pipeline {
     uint8_t *d_front_q[kQ] = {}, *d_bird_q[kQ] = {};
     cudaEvent_t ev_in_ready[kQ] = {}, ev_in_free[kQ] = {}, ev_done[kQ] = {};
     cudaEvent_t ev_copy0[kQ] = {};       // timing: start of the input copy (ev_in_ready is its end)
+    cudaEvent_t ev_feat_q[kQ] = {};      // per ticket: the feature copy-out of that step has finished
+    bool feat_q_used[kQ] = {};
     bool in_used[kQ] = {};
     int* h_flags = nullptr;              // pinned, [kQ][2]
     int32_t next_ticket = 0;
@@ -54,12 +57,29 @@ namespace {
 #define FBE_TRY(expr) do { int _rc = (expr); if (_rc != FBE_OK) return _rc; } while (0)
 
 __global__ void k_pair_results(const int* __restrict__ nf, const int* __restrict__ nb, const int* __restrict__ fm,
-                               const int* __restrict__ bm, int B, fbe_pair_result* __restrict__ out) {
+                               const int* __restrict__ bm, const int* __restrict__ fstatus, const int* __restrict__ bstatus,
+                               int B, fbe_pair_result* __restrict__ out, int* __restrict__ flags) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
     fbe_pair_result r;
     r.n_front = nf[p + 1]; r.n_bird = nb[p + 1]; r.front_matches = fm[p]; r.bird_matches = bm[p];
     out[p] = r;
+    // octree workspace overflow of either extractor (slot p + 1 of this step): flags[2] = 1 + pair
+    if (fstatus[p] | bstatus[p]) atomicMax(flags + 2, p + 1);
+}
+
+// the per-step flag record copied to the host with every result: [0] candidate-row overflow, [2] 1 + pair whose octree
+// workspace overflowed, [4] 1 + (pair << 16 | query) of one overflowing window
+constexpr int kFlagInts = 8;
+int check_flags(const int* h, int row_cap) {
+    if (h[0]) {
+        const int w = h[4] - 1;
+        set_error("candidate rows overflow in pipeline step: pair " + std::to_string(w >> 16) + ", front query " + std::to_string(w & 0xFFFF) +
+                  " has more than " + std::to_string(row_cap) + " keypoints in its search window (raise fbe_pipeline_cfg.front_row_cap)");
+        return FBE_E_CAPACITY;
+    }
+    if (h[2]) { set_error("octree workspace overflow in pipeline step: pair " + std::to_string(h[2] - 1)); return FBE_E_CAPACITY; }
+    return FBE_OK;
 }
 
 FrameDev frame_dev(const ExtractorCore& e, int slot0, int set) {
@@ -101,7 +121,7 @@ void free_all(fbe_pipeline* p) {
     for (int k = 0; k < fbe_pipeline::kQ; ++k) {
         if (p->d_front_q[k]) cudaFree(p->d_front_q[k]);
         if (p->d_bird_q[k]) cudaFree(p->d_bird_q[k]);
-        for (cudaEvent_t e : {p->ev_in_ready[k], p->ev_in_free[k], p->ev_done[k], p->ev_copy0[k]}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : {p->ev_in_ready[k], p->ev_in_free[k], p->ev_done[k], p->ev_copy0[k], p->ev_feat_q[k]}) if (e) cudaEventDestroy(e);
     }
     for (cudaEvent_t e : {p->ev_front, p->ev_bird, p->ev_match_done[0], p->ev_match_done[1], p->ev_t0, p->ev_t1}) if (e) cudaEventDestroy(e);
     p->front.destroy();
@@ -246,7 +266,8 @@ int fbe_pipeline_step_dev(fbe_pipeline* p, const uint8_t* d_front, const uint8_t
     f.matches12 = p->b_m12; f.dmatches = nullptr; f.n_dmatches = nullptr; f.nmatches = p->b_nm; f.q_bin = p->b_bin;
     FBE_TRY(launch_bird_finish(f, B, ms));
 
-    k_pair_results<<<(B + 127) / 128, 128, 0, ms>>>(fq.n, bq.n, p->f_nm, p->b_nm, B, p->d_res);
+    k_pair_results<<<(B + 127) / 128, 128, 0, ms>>>(fq.n, bq.n, p->f_nm, p->b_nm, p->front.slot_view(1, set).status,
+                                                   p->bird.slot_view(1, set).status, B, p->d_res, p->flags);
     count_launch();
     FBE_CUDA(cudaGetLastError());
     FBE_TRY(carry_last(p->front, B, set, ms));
@@ -290,13 +311,13 @@ int fbe_pipeline_fetch(fbe_pipeline* p, fbe_pair_result* res, int32_t* front_mat
     FBE_CUDA(cudaSetDevice(p->cfg.device));
     cudaStream_t ms = p->mstream;
     const size_t B = (size_t)p->B;
-    int h_flags[2] = {0, 0};
+    int h_flags[kFlagInts] = {};
     FBE_CUDA(cudaMemcpyAsync(p->h_res, p->d_res, B * sizeof(fbe_pair_result), cudaMemcpyDeviceToHost, ms));
-    FBE_CUDA(cudaMemcpyAsync(h_flags, p->flags, 8, cudaMemcpyDeviceToHost, ms));
+    FBE_CUDA(cudaMemcpyAsync(h_flags, p->flags, sizeof(h_flags), cudaMemcpyDeviceToHost, ms));
     if (front_matches12) FBE_CUDA(cudaMemcpyAsync(front_matches12, p->f_m12, B * p->fcap * 4, cudaMemcpyDeviceToHost, ms));
     if (bird_matches12) FBE_CUDA(cudaMemcpyAsync(bird_matches12, p->b_m12, B * p->bcap * 4, cudaMemcpyDeviceToHost, ms));
     FBE_CUDA(cudaStreamSynchronize(ms));
-    if (h_flags[0]) { set_error("candidate rows overflow in pipeline (raise row capacity)"); return FBE_E_CAPACITY; }
+    FBE_TRY(check_flags(h_flags, p->row_cap));
     if (res) std::memcpy(res, p->h_res, B * sizeof(fbe_pair_result));
     return FBE_OK;
 }
@@ -344,8 +365,9 @@ int fbe_pipeline_fetch_pair(fbe_pipeline* p, int32_t pair, fbe_keypoint* front_k
 // the step, and the D2H copy of the results into the caller's buffers, then returns a ticket; wait(ticket) blocks until
 // that step's results are in the host buffers.  Up to three steps may be in flight: the inputs of step N+1 travel while step N
 // computes, so the end-to-end rate is max(copy, compute) instead of their sum.  Steps execute in submit order.
-int fbe_pipeline_submit_host(fbe_pipeline* p, const uint8_t* h_front, const uint8_t* h_bird, fbe_pair_result* res,
-                             int32_t* front_matches12, int32_t* bird_matches12, int32_t* ticket) {
+int fbe_pipeline_submit_host_features(fbe_pipeline* p, const uint8_t* h_front, const uint8_t* h_bird, fbe_pair_result* res,
+                                      int32_t* front_matches12, int32_t* bird_matches12, const fbe_pipeline_features* feat,
+                                      int32_t* ticket) {
     if (!p || !h_front || !h_bird || !ticket) return FBE_E_INVALID;
     const fbe_pipeline_cfg& c = p->cfg;
     FBE_CUDA(cudaSetDevice(c.device));
@@ -353,7 +375,7 @@ int fbe_pipeline_submit_host(fbe_pipeline* p, const uint8_t* h_front, const uint
     const size_t fbytes = B * c.front_rows * c.front_cols, bbytes = B * c.bird_rows * c.bird_cols;
     if (!p->copy_stream) {
         FBE_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
-        FBE_CUDA(cudaMallocHost((void**)&p->h_flags, 2 * fbe_pipeline::kQ * sizeof(int)));
+        FBE_CUDA(cudaMallocHost((void**)&p->h_flags, kFlagInts * fbe_pipeline::kQ * sizeof(int)));
         for (int k = 0; k < fbe_pipeline::kQ; ++k) {
             FBE_CUDA(cudaMalloc(&p->d_front_q[k], fbytes));
             FBE_CUDA(cudaMalloc(&p->d_bird_q[k], bbytes));
@@ -375,16 +397,53 @@ int fbe_pipeline_submit_host(fbe_pipeline* p, const uint8_t* h_front, const uint
     FBE_CUDA(cudaStreamWaitEvent(p->front.stream, p->ev_in_ready[k], 0));
     FBE_CUDA(cudaStreamWaitEvent(p->bird.stream, p->ev_in_ready[k], 0));
     FBE_TRY(fbe_pipeline_step_dev(p, p->d_front_q[k], p->d_bird_q[k]));
+    const int set = p->last_set;
+    if (feat && (feat->front_kps || feat->front_desc || feat->bird_kps || feat->bird_desc)) {
+        // what ORBextractor::operator() hands back, for the batch frames (slots 1 .. B of this step's output set): copied on
+        // its own stream as soon as each extractor is done, beside the matching; the set is not reused before ev_feat_done
+        if (!p->out_stream) {
+            FBE_CUDA(cudaStreamCreateWithFlags(&p->out_stream, cudaStreamNonBlocking));
+            for (cudaEvent_t* e : {&p->ev_feat_done[0], &p->ev_feat_done[1], &p->ev_feat_q[0], &p->ev_feat_q[1], &p->ev_feat_q[2]})
+                FBE_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        }
+        cudaStream_t os = p->out_stream;
+        const Workspace f = p->front.slot_view(1, set), b = p->bird.slot_view(1, set);
+        FBE_CUDA(cudaStreamWaitEvent(os, p->ev_front, 0));
+        if (feat->front_kps) FBE_CUDA(cudaMemcpyAsync(feat->front_kps, f.out_kps, B * p->fcap * sizeof(fbe_keypoint), cudaMemcpyDeviceToHost, os));
+        if (feat->front_desc) FBE_CUDA(cudaMemcpyAsync(feat->front_desc, f.out_desc, B * p->fcap * 32, cudaMemcpyDeviceToHost, os));
+        FBE_CUDA(cudaStreamWaitEvent(os, p->ev_bird, 0));
+        if (feat->bird_kps) FBE_CUDA(cudaMemcpyAsync(feat->bird_kps, b.out_kps, B * p->bcap * sizeof(fbe_keypoint), cudaMemcpyDeviceToHost, os));
+        if (feat->bird_desc) FBE_CUDA(cudaMemcpyAsync(feat->bird_desc, b.out_desc, B * p->bcap * 32, cudaMemcpyDeviceToHost, os));
+        FBE_CUDA(cudaEventRecord(p->ev_feat_done[set], os));
+        FBE_CUDA(cudaEventRecord(p->ev_feat_q[k], os));
+        p->feat_used[set] = true;
+        p->feat_q_used[k] = true;
+    } else {
+        p->feat_q_used[k] = false;
+    }
     FBE_CUDA(cudaEventRecord(p->ev_in_free[k], ms));       // the match stream has joined both extractor streams inside step_dev
     p->in_used[k] = true;
     // results
     if (res) FBE_CUDA(cudaMemcpyAsync(res, p->d_res, B * sizeof(fbe_pair_result), cudaMemcpyDeviceToHost, ms));
-    FBE_CUDA(cudaMemcpyAsync(p->h_flags + 2 * k, p->flags, 8, cudaMemcpyDeviceToHost, ms));
+    FBE_CUDA(cudaMemcpyAsync(p->h_flags + kFlagInts * k, p->flags, kFlagInts * sizeof(int), cudaMemcpyDeviceToHost, ms));
     if (front_matches12) FBE_CUDA(cudaMemcpyAsync(front_matches12, p->f_m12, B * p->fcap * 4, cudaMemcpyDeviceToHost, ms));
     if (bird_matches12) FBE_CUDA(cudaMemcpyAsync(bird_matches12, p->b_m12, B * p->bcap * 4, cudaMemcpyDeviceToHost, ms));
     FBE_CUDA(cudaEventRecord(p->ev_done[k], ms));
     // the next step's matching overwrites f_m12 / b_m12 / d_res: it is enqueued on ms after these copies, so ordering holds
     *ticket = t;
+    return FBE_OK;
+}
+
+int fbe_pipeline_submit_host(fbe_pipeline* p, const uint8_t* h_front, const uint8_t* h_bird, fbe_pair_result* res,
+                             int32_t* front_matches12, int32_t* bird_matches12, int32_t* ticket) {
+    return fbe_pipeline_submit_host_features(p, h_front, h_bird, res, front_matches12, bird_matches12, nullptr, ticket);
+}
+
+int fbe_pipeline_device_results(fbe_pipeline* p, void** res, void** front_matches12, void** bird_matches12) {
+    if (!p) return FBE_E_INVALID;
+    if (res) *res = p->d_res;
+    if (front_matches12) *front_matches12 = p->f_m12;
+    if (bird_matches12) *bird_matches12 = p->b_m12;
     return FBE_OK;
 }
 
@@ -402,8 +461,8 @@ int fbe_pipeline_wait(fbe_pipeline* p, int32_t ticket) {
     FBE_CUDA(cudaSetDevice(p->cfg.device));
     const int k = ticket % fbe_pipeline::kQ;
     FBE_CUDA(cudaEventSynchronize(p->ev_done[k]));
-    if (p->h_flags[2 * k]) { set_error("candidate rows overflow in pipeline (raise row capacity)"); return FBE_E_CAPACITY; }
-    return FBE_OK;
+    if (p->feat_q_used[k]) FBE_CUDA(cudaEventSynchronize(p->ev_feat_q[k]));
+    return check_flags(p->h_flags + kFlagInts * k, p->row_cap);
 }
 
 // live per-stage device timing of the FRONT and BIRD extractors (CUDA events on their launching streams).

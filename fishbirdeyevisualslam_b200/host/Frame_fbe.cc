@@ -14,6 +14,7 @@
 
 #include "Frame.h"
 #include "fbe_cabi.h"
+#include "fbe_host.h"
 
 namespace ORB_SLAM2 {
 
@@ -53,7 +54,7 @@ void Frame::UndistortKeyPoints() {
     const float K[4] = {mK.at<float>(0, 0), mK.at<float>(1, 1), mK.at<float>(0, 2), mK.at<float>(1, 2)};
     const float D[4] = {mDistCoef.at<float>(0), mDistCoef.at<float>(1), mDistCoef.at<float>(2), mDistCoef.at<float>(3)};
     mvKeysUn.resize(N);
-    if (N > 0 && fbe_undistort_keypoints(reinterpret_cast<const fbe_keypoint*>(mvKeys.data()), N, K, D, 0,
+    if (N > 0 && fbe_undistort_keypoints(reinterpret_cast<const fbe_keypoint*>(mvKeys.data()), N, K, D, fbe_host_device(),
                                          reinterpret_cast<fbe_keypoint*>(mvKeysUn.data())) != FBE_OK) {
         fprintf(stderr, "Frame::UndistortKeyPoints (fbe-b200): %s\n", fbe_last_error());
         abort();
@@ -73,7 +74,7 @@ void Frame::GuidenceKeyBirdPts(std::vector<cv::KeyPoint>& preKeysBird) {
     std::vector<cv::KeyPoint> kept(n);
     int32_t nkept = 0;
     if (fbe_bird_refine(c.ptr(0), step, NULL, 0, c.rows, c.cols, reinterpret_cast<const fbe_keypoint*>(preKeysBird.data()), n, 5, 5, 40,
-                        0.001, 0, NULL, reinterpret_cast<fbe_keypoint*>(kept.data()), &nkept, NULL) != FBE_OK) {
+                        0.001, fbe_host_device(), NULL, reinterpret_cast<fbe_keypoint*>(kept.data()), &nkept, NULL) != FBE_OK) {
         fprintf(stderr, "Frame::GuidenceKeyBirdPts (fbe-b200): %s\n", fbe_last_error());
         abort();
     }

@@ -24,6 +24,7 @@
 #include "MapPointBird.h"
 #include "ORBmatcher.h"
 #include "fbe_cabi.h"
+#include "fbe_host.h"
 
 namespace ORB_SLAM2 {
 
@@ -37,16 +38,26 @@ struct Matcher {          // one device matcher per calling thread and per (rati
     bool ori;
 };
 
+// A C-ABI failure (no GPU, CUDA error, capacity, invalid arguments) is fatal, exactly as in the extractor and Frame shims:
+// returning "0 matches" would read as "tracking lost" instead of a fault.  There is deliberately no CPU fallback.
+void die(const char* what, int rc) {
+    fprintf(stderr, "ORBmatcher (fbe-b200): %s failed: %d (%s)\n", what, rc, fbe_last_error());
+    abort();
+}
+#define FBE_CK(call) do { const int _rc = (call); if (_rc != FBE_OK) die(#call, _rc); } while (0)
+
+struct MatcherCache {     // the handles of a thread are destroyed when the thread exits
+    std::vector<Matcher> v;
+    ~MatcherCache() { for (size_t i = 0; i < v.size(); ++i) fbe_matcher_destroy(v[i].h); }
+};
+
 fbe_matcher* matcher_for(float ratio, bool ori) {
-    static thread_local std::vector<Matcher> cache;
-    for (size_t i = 0; i < cache.size(); ++i)
-        if (cache[i].ratio == ratio && cache[i].ori == ori) return cache[i].h;
+    static thread_local MatcherCache cache;
+    for (size_t i = 0; i < cache.v.size(); ++i)
+        if (cache.v[i].ratio == ratio && cache.v[i].ori == ori) return cache.v[i].h;
     Matcher m = {NULL, ratio, ori};
-    if (fbe_matcher_create(ratio, ori ? 1 : 0, 0, &m.h) != FBE_OK) {
-        fprintf(stderr, "ORBmatcher (fbe-b200): %s\n", fbe_last_error());
-        abort();      // no CPU fallback
-    }
-    cache.push_back(m);
+    FBE_CK(fbe_matcher_create(ratio, ori ? 1 : 0, fbe_host_device(), &m.h));     // same GPU as the extractor (FBE_DEVICE)
+    cache.v.push_back(m);
     return m.h;
 }
 
@@ -85,8 +96,8 @@ int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Po
     fbe_frame_view v1 = front_view(F1), v2 = front_view(F2);
     int nmatches = 0;
     static_assert(sizeof(cv::Point2f) == 8, "Point2f layout");
-    fbe_search_for_initialization(matcher_for(mfNNratio, mbCheckOrientation), &v1, &v2,
-                                  reinterpret_cast<float*>(vbPrevMatched.data()), vnMatches12.data(), windowSize, &nmatches);
+    FBE_CK(fbe_search_for_initialization(matcher_for(mfNNratio, mbCheckOrientation), &v1, &v2,
+                                  reinterpret_cast<float*>(vbPrevMatched.data()), vnMatches12.data(), windowSize, &nmatches));
     return nmatches;
 }
 
@@ -119,11 +130,15 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, 
     std::vector<int> cur_mp(CurrentFrame.N, -1);
     fbe_frame_view cv_ = front_view(CurrentFrame);
     int nmatches = 0;
-    (void)bMono;   // stereo windows (mvuRight) are not part of the hot path of this fork (monocular + bird)
-    fbe_search_by_projection_last(matcher_for(mfNNratio, mbCheckOrientation), &cv_,
+    if (!bMono) {   // the stereo branches (bForward / bBackward level windows :1349-1350,1386-1390, mvuRight check :1417-1424) are not
+                    // built: this fork tracks monocular + bird view, and silently running the mono search would change results
+        fprintf(stderr, "ORBmatcher::SearchByProjection (fbe-b200): bMono == false (stereo / RGB-D) is not supported by the drop-in\n");
+        abort();
+    }
+    FBE_CK(fbe_search_by_projection_last(matcher_for(mfNNratio, mbCheckOrientation), &cv_,
                                   reinterpret_cast<const fbe_keypoint*>(LastFrame.mvKeysUn.data()), proj.data(), mpdesc.data(), n,
                                   CurrentFrame.mvScaleFactors.data(), (int)CurrentFrame.mvScaleFactors.size(), taken.data(),
-                                  has_obs.data(), th, cur_mp.data(), &nmatches);
+                                  has_obs.data(), th, cur_mp.data(), &nmatches));
     // pointer writes of :1431 and :1461: -2 marks keypoints assigned by this call and then removed by the orientation
     // histogram, where the reference writes NULL whatever the keypoint held before
     for (int k = 0; k < CurrentFrame.N; k++) {
@@ -168,10 +183,10 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std
     std::vector<int> cur_mp(CurrentFrame.N, -1);
     fbe_frame_view cv_ = front_view(CurrentFrame);
     int nmatches = 0;
-    fbe_search_by_projection_reloc(matcher_for(mfNNratio, mbCheckOrientation), &cv_,
+    FBE_CK(fbe_search_by_projection_reloc(matcher_for(mfNNratio, mbCheckOrientation), &cv_,
                                    reinterpret_cast<const fbe_keypoint*>(pKF->mvKeysUn.data()), proj.data(), level.data(),
                                    mpdesc.data(), n, CurrentFrame.mvScaleFactors.data(), (int)CurrentFrame.mvScaleFactors.size(),
-                                   taken.data(), th, ORBdist, cur_mp.data(), &nmatches);
+                                   taken.data(), th, ORBdist, cur_mp.data(), &nmatches));
     for (int k = 0; k < CurrentFrame.N; k++) {
         if (cur_mp[k] >= 0) CurrentFrame.mvpMapPoints[k] = vpMPs[cur_mp[k]];
         else if (cur_mp[k] == -2) CurrentFrame.mvpMapPoints[k] = static_cast<MapPoint*>(NULL);
@@ -226,9 +241,9 @@ int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector
     kv.inv_w = pKF->mfGridElementWidthInv; kv.inv_h = pKF->mfGridElementHeightInv;
     kv.gcols = pKF->mnGridCols; kv.grows = pKF->mnGridRows;
     int nmatches = 0;
-    fbe_search_by_projection_loop(matcher_for(mfNNratio, mbCheckOrientation), &kv, proj.data(), level.data(), mpdesc.data(), n,
+    FBE_CK(fbe_search_by_projection_loop(matcher_for(mfNNratio, mbCheckOrientation), &kv, proj.data(), level.data(), mpdesc.data(), n,
                                   pKF->mvScaleFactors.data(), (int)pKF->mvScaleFactors.size(), matched.data(), th, kf_mp.data(),
-                                  &nmatches);
+                                  &nmatches));
     for (int k = 0; k < N; k++)
         if (kf_mp[k] >= 0) vpMatched[k] = vpPoints[kf_mp[k]];
     return nmatches;
@@ -257,9 +272,9 @@ int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMap
     std::vector<int> cur_mp(F.N, -1);
     fbe_frame_view v = front_view(F);
     int nmatches = 0;
-    fbe_search_by_projection_map(matcher_for(mfNNratio, mbCheckOrientation), &v, F.mvScaleFactors.data(), (int)F.mvScaleFactors.size(),
+    FBE_CK(fbe_search_by_projection_map(matcher_for(mfNNratio, mbCheckOrientation), &v, F.mvScaleFactors.data(), (int)F.mvScaleFactors.size(),
                                  proj.data(), level.data(), viewcos.data(), desc.data(), (int)src.size(), taken.data(),
-                                 has_obs.data(), th, cur_mp.data(), &nmatches);
+                                 has_obs.data(), th, cur_mp.data(), &nmatches));
     for (int k = 0; k < F.N; k++)
         if (cur_mp[k] >= 0) F.mvpMapPoints[k] = vpMapPoints[src[cur_mp[k]]];
     return nmatches;
@@ -293,10 +308,10 @@ int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpM
     Csr a = flatten(pKF->mFeatVec), b = flatten(F.mFeatVec);
     std::vector<int> f_mp(F.N, -1);
     int nmatches = 0;
-    fbe_search_by_bow(matcher_for(mfNNratio, mbCheckOrientation), reinterpret_cast<const fbe_keypoint*>(pKF->mvKeysUn.data()),
+    FBE_CK(fbe_search_by_bow(matcher_for(mfNNratio, mbCheckOrientation), reinterpret_cast<const fbe_keypoint*>(pKF->mvKeysUn.data()),
                       desc_ptr(pKF->mDescriptors), (int)pKF->mvKeysUn.size(), has_mp.data(), a.ids.data(), a.start.data(),
                       a.items.data(), (int)a.ids.size(), reinterpret_cast<const fbe_keypoint*>(F.mvKeys.data()), desc_ptr(F.mDescriptors),
-                      F.N, b.ids.data(), b.start.data(), b.items.data(), (int)b.ids.size(), f_mp.data(), &nmatches);
+                      F.N, b.ids.data(), b.start.data(), b.items.data(), (int)b.ids.size(), f_mp.data(), &nmatches));
     for (int k = 0; k < F.N; k++)
         if (f_mp[k] >= 0) vpMapPointMatches[k] = vpMapPointsKF[f_mp[k]];
     return nmatches;
@@ -310,11 +325,11 @@ int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint
     Csr a = flatten(pKF1->mFeatVec), b = flatten(pKF2->mFeatVec);
     std::vector<int> m12(std::max<size_t>(vpMapPoints1.size(), 1), -1);
     int nmatches = 0;
-    fbe_search_by_bow_kf(matcher_for(mfNNratio, mbCheckOrientation), reinterpret_cast<const fbe_keypoint*>(pKF1->mvKeysUn.data()),
+    FBE_CK(fbe_search_by_bow_kf(matcher_for(mfNNratio, mbCheckOrientation), reinterpret_cast<const fbe_keypoint*>(pKF1->mvKeysUn.data()),
                          desc_ptr(pKF1->mDescriptors), (int)vpMapPoints1.size(), has1.data(), a.ids.data(), a.start.data(), a.items.data(),
                          (int)a.ids.size(), reinterpret_cast<const fbe_keypoint*>(pKF2->mvKeysUn.data()), desc_ptr(pKF2->mDescriptors),
                          (int)vpMapPoints2.size(), has2.data(), b.ids.data(), b.start.data(), b.items.data(), (int)b.ids.size(),
-                         m12.data(), &nmatches);
+                         m12.data(), &nmatches));
     for (size_t i = 0; i < vpMapPoints1.size(); i++)
         if (m12[i] >= 0) vpMatches12[i] = vpMapPoints2[m12[i]];
     return nmatches;
@@ -348,12 +363,12 @@ int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F
         for (int c = 0; c < 3; c++) F[3 * r + c] = F12.at<float>(r, c);
     std::vector<int> m12(std::max(n1, 1), -1);
     int nmatches = 0;
-    fbe_search_for_triangulation(matcher_for(mfNNratio, mbCheckOrientation), reinterpret_cast<const fbe_keypoint*>(pKF1->mvKeysUn.data()),
+    FBE_CK(fbe_search_for_triangulation(matcher_for(mfNNratio, mbCheckOrientation), reinterpret_cast<const fbe_keypoint*>(pKF1->mvKeysUn.data()),
                                  desc_ptr(pKF1->mDescriptors), n1, skip1.data(), st1.data(), a.ids.data(), a.start.data(), a.items.data(),
                                  (int)a.ids.size(), reinterpret_cast<const fbe_keypoint*>(pKF2->mvKeysUn.data()),
                                  desc_ptr(pKF2->mDescriptors), n2, skip2.data(), st2.data(), b.ids.data(), b.start.data(), b.items.data(),
                                  (int)b.ids.size(), F, ex, ey, pKF2->mvScaleFactors.data(), pKF2->mvLevelSigma2.data(),
-                                 (int)pKF2->mvScaleFactors.size(), m12.data(), &nmatches);
+                                 (int)pKF2->mvScaleFactors.size(), m12.data(), &nmatches));
     vMatchedPairs.clear();
     vMatchedPairs.reserve(nmatches);
     for (int i = 0; i < n1; i++)
@@ -412,9 +427,9 @@ int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, c
     }
     std::vector<int> best_idx(std::max(nMPs, 1), -1), best_dist(std::max(nMPs, 1), INT_MAX);
     fbe_frame_view kv = keyframe_view(pKF);
-    fbe_fuse_search(matcher_for(mfNNratio, mbCheckOrientation), &kv, pKF->mvuRight.data(), pKF->mvInvLevelSigma2.data(),
+    FBE_CK(fbe_fuse_search(matcher_for(mfNNratio, mbCheckOrientation), &kv, pKF->mvuRight.data(), pKF->mvInvLevelSigma2.data(),
                     (int)pKF->mvInvLevelSigma2.size(), proj.data(), pur.data(), level.data(), radius.data(), mpdesc.data(), nMPs, 1,
-                    best_idx.data(), best_dist.data());
+                    best_idx.data(), best_dist.data()));
     int nFused = 0;
     for (int i = 0; i < nMPs; i++) {
         MapPoint* pMP = vpMapPoints[i];
@@ -475,8 +490,8 @@ int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& v
     }
     std::vector<int> best_idx(std::max(nPoints, 1), -1), best_dist(std::max(nPoints, 1), INT_MAX);
     fbe_frame_view kv = keyframe_view(pKF);
-    fbe_fuse_search(matcher_for(mfNNratio, mbCheckOrientation), &kv, NULL, NULL, 0, proj.data(), NULL, level.data(), radius.data(),
-                    mpdesc.data(), nPoints, 0, best_idx.data(), best_dist.data());
+    FBE_CK(fbe_fuse_search(matcher_for(mfNNratio, mbCheckOrientation), &kv, NULL, NULL, 0, proj.data(), NULL, level.data(), radius.data(),
+                    mpdesc.data(), nPoints, 0, best_idx.data(), best_dist.data()));
     int nFused = 0;
     for (int iMP = 0; iMP < nPoints; iMP++) {
         MapPoint* pMP = vpPoints[iMP];
@@ -531,8 +546,8 @@ void sim3_direction(ORBmatcher* self, fbe_matcher* m, KeyFrame* src, KeyFrame* d
     }
     std::vector<int> best_idx(std::max(N, 1), -1), best_dist(std::max(N, 1), INT_MAX);
     fbe_frame_view kv = keyframe_view(dst);
-    fbe_fuse_search(m, &kv, NULL, NULL, 0, proj.data(), NULL, level.data(), radius.data(), mpdesc.data(), N, 0, best_idx.data(),
-                    best_dist.data());
+    FBE_CK(fbe_fuse_search(m, &kv, NULL, NULL, 0, proj.data(), NULL, level.data(), radius.data(), mpdesc.data(), N, 0, best_idx.data(),
+                    best_dist.data()));
     match.assign(N, -1);
     for (int i = 0; i < N; i++)
         if (best_dist[i] <= ORBmatcher::TH_HIGH) match[i] = best_idx[i];
@@ -581,8 +596,8 @@ int ORBmatcher::BirdviewMatch(Frame& CurF, const std::vector<cv::KeyPoint>& vRef
     std::vector<int> dm(3 * (size_t)std::max(n, 1));
     int nd = 0, nmatches = 0;
     fbe_frame_view v = bird_view(CurF);
-    fbe_birdview_match(matcher_for(mfNNratio, mbCheckOrientation), reinterpret_cast<const fbe_keypoint*>(vRefKeysBird.data()),
-                       desc_ptr(DescriptorsBird), n, &v, windowSize, dm.data(), &nd, &nmatches);
+    FBE_CK(fbe_birdview_match(matcher_for(mfNNratio, mbCheckOrientation), reinterpret_cast<const fbe_keypoint*>(vRefKeysBird.data()),
+                       desc_ptr(DescriptorsBird), n, &v, windowSize, dm.data(), &nd, &nmatches));
     for (int i = 0; i < nd; i++) vDMatches12.push_back(cv::DMatch(dm[3 * i], dm[3 * i + 1], (float)dm[3 * i + 2]));
     return nmatches;
 }
@@ -607,8 +622,8 @@ int ORBmatcher::BirdMapPointMatch(Frame& CurF, const std::vector<MapPointBird*>&
     std::vector<int> vnMatches12(n, -1);
     int nmatches = 0;
     fbe_frame_view v = bird_view(CurF);
-    fbe_bird_map_point_match(matcher_for(mfNNratio, mbCheckOrientation), pix.data(), desc.data(), n, &v, windowSize,
-                             vnMatches12.data(), &nmatches);
+    FBE_CK(fbe_bird_map_point_match(matcher_for(mfNNratio, mbCheckOrientation), pix.data(), desc.data(), n, &v, windowSize,
+                             vnMatches12.data(), &nmatches));
     // second pass, :1865-1895, verbatim semantics (host arithmetic, `> 0` quirk, last writer wins)
     int InlierMatches = 0;
     cv::Mat Tcw2 = CurF.mTcw;

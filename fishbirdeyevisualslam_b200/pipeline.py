@@ -7,13 +7,13 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import KP_DTYPE, PAIR_RESULT_DTYPE, ExtractorCfg, PipelineCfg, check, ptr
+from ._lib import KP_DTYPE, PAIR_RESULT_DTYPE, ExtractorCfg, PipelineCfg, PipelineFeatures, check, ptr
 
 
 class FrontBirdPipeline:
     def __init__(self, batch: int, front_shape=(720, 1280), bird_shape=(384, 384), front_features=2000, bird_features=1000,
                  scale=1.2, nlevels=8, ini_th=15, min_th=5, nn_ratio=0.9, check_orientation=True, front_window=100,
-                 bird_window=10, device=0, front_fisheye=None):
+                 bird_window=10, device=0, front_fisheye=None, front_row_cap=0):
         """front_fisheye = (K, D) with K = (fx, fy, cx, cy), D = (k1, k2, p1, p2): undistort the front keypoints on the device
         before the grid (Frame::UndistortKeyPoints), as the reference's Frame constructor does for its fisheye camera."""
         self._L = _lib.load()
@@ -23,6 +23,7 @@ class FrontBirdPipeline:
                           ExtractorCfg(bird_features, scale, nlevels, ini_th, min_th, batch + 1, device),
                           front_shape[0], front_shape[1], bird_shape[0], bird_shape[1], batch, nn_ratio,
                           int(check_orientation), front_window, bird_window, device)
+        cfg.front_row_cap = int(front_row_cap)       # 0 = 256 candidates per front search window
         if front_fisheye is not None:
             cfg.front_fisheye = 1
             cfg.front_K[:] = [float(x) for x in front_fisheye[0]]
@@ -58,12 +59,28 @@ class FrontBirdPipeline:
         check(self._L.fbe_pipeline_step_host(self._h, C.c_void_p(h_front_ptr), C.c_void_p(h_bird_ptr), ptr(res),
                                              None if fm is None else ptr(fm), None if bm is None else ptr(bm)))
 
-    def submit_host(self, h_front_ptr: int, h_bird_ptr: int, res: np.ndarray, fm: np.ndarray | None = None, bm: np.ndarray | None = None) -> int:
-        """Asynchronous step through host (pinned) buffers; returns a ticket for wait().  Up to three steps may be in flight."""
+    def submit_host(self, h_front_ptr: int, h_bird_ptr: int, res: np.ndarray, fm: np.ndarray | None = None, bm: np.ndarray | None = None,
+                    features=None) -> int:
+        """Asynchronous step through host (pinned) buffers; returns a ticket for wait().  Up to three steps may be in flight.
+        features = (front_kps [B, front_cap] KP_DTYPE, front_desc [B, front_cap, 32] u8, bird_kps, bird_desc) host arrays that
+        receive what ORBextractor::operator() returns for every frame of the batch (any entry may be None)."""
         t = C.c_int32()
-        check(self._L.fbe_pipeline_submit_host(self._h, C.c_void_p(h_front_ptr), C.c_void_p(h_bird_ptr), ptr(res),
-                                               None if fm is None else ptr(fm), None if bm is None else ptr(bm), C.byref(t)))
+        if features is None:
+            check(self._L.fbe_pipeline_submit_host(self._h, C.c_void_p(h_front_ptr), C.c_void_p(h_bird_ptr), ptr(res),
+                                                   None if fm is None else ptr(fm), None if bm is None else ptr(bm), C.byref(t)))
+        else:
+            f = PipelineFeatures(*[None if a is None else a.ctypes.data for a in features])
+            check(self._L.fbe_pipeline_submit_host_features(self._h, C.c_void_p(h_front_ptr), C.c_void_p(h_bird_ptr), ptr(res),
+                                                            None if fm is None else ptr(fm), None if bm is None else ptr(bm),
+                                                            C.byref(f), C.byref(t)))
         return t.value
+
+    def device_results(self):
+        """Device addresses (ints) of the last step's fbe_pair_result[B], front matches12 [B, front_cap] i32 and bird matches12
+        [B, bird_cap] i32 -- for a caller that moves them between GPUs itself (shard.gather_matches)."""
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(self._L.fbe_pipeline_device_results(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def wait(self, ticket: int):
         check(self._L.fbe_pipeline_wait(self._h, C.c_int32(ticket)))

@@ -64,6 +64,63 @@ def run_offline_batch(front: np.ndarray, bird: np.ndarray, rank: int, world: int
             if g >= start:
                 rec[g - start] = [res["n_front"][p], res["n_bird"][p], res["front_matches"][p], res["bird_matches"][p]]
     pipe.close()
-    if start > 0 and halo_index(start) is not None and len(rec):
-        pass   # the halo pair's own record belongs to the previous block; its match result is discarded here
-    return rec
+    return rec           # the halo pair's own record belongs to the previous block: its result was skipped above (g < start)
+
+
+class _DeviceView:
+    """A raw device allocation of the library seen through __cuda_array_interface__, so that torch can alias it (zero copy)."""
+
+    def __init__(self, ptr: int, shape, typestr: str = "<i4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def match_record_bytes(front_cap: int, bird_cap: int) -> int:
+    """Bytes of one pair's fixed-stride match record: {n_front, n_bird, front_matches, bird_matches} + front idx[] + bird idx[]."""
+    return 16 + 4 * front_cap + 4 * bird_cap
+
+
+def gather_matches(pipe, world: int, group=None):
+    """north_star's one collective: all-gather of the last step's match results of every shard, DEVICE-RESIDENT.
+
+    The three record arrays of the pipeline (fbe_pair_result[B], front matches12 [B, front_cap], bird matches12
+    [B, bird_cap]; fixed stride, -1 = unmatched) are aliased as CUDA tensors -- no host staging, no copy on the
+    send side -- and gathered with NCCL (`all_gather_into_tensor`) on torch's current stream, ordered after the pipeline's
+    streams; the pipeline's next step is ordered after the gather.  Returns (res [world, B, 4], front [world, B, front_cap],
+    bird [world, B, bird_cap]) int32 CUDA tensors, identical on every rank."""
+    import torch
+    import torch.distributed as dist
+    B = pipe.batch
+    d_res, d_fm, d_bm = pipe.device_results()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    res = torch.as_tensor(_DeviceView(d_res, (B, 4)), device=dev)
+    fm = torch.as_tensor(_DeviceView(d_fm, (B, pipe.front_cap)), device=dev)
+    bm = torch.as_tensor(_DeviceView(d_bm, (B, pipe.bird_cap)), device=dev)
+    pipe.join()                                                  # the public stream now follows the step's last kernel
+    ps = torch.cuda.ExternalStream(pipe.stream_ptr, device=dev)
+    cur = torch.cuda.current_stream(dev)
+    cur.wait_stream(ps)
+    outs = []
+    for t in (res, fm, bm):
+        o = torch.empty((world,) + tuple(t.shape), dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_gather_into_tensor(o, t, group=group)
+        else:
+            o[0].copy_(t)
+        outs.append(o)
+    ps.wait_stream(cur)                                          # the next step overwrites the records only after they were read
+    return tuple(outs)
+
+
+def gather_fixed_records(parts, world: int, group=None):
+    """The same gather for tensors on any device (gloo on CPU in the tests): [B, k] -> [world, B, k] for every tensor."""
+    import torch
+    import torch.distributed as dist
+    outs = []
+    for t in parts:
+        if world > 1:
+            lst = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(lst, t.contiguous(), group=group)
+            outs.append(torch.stack(lst))
+        else:
+            outs.append(t.unsqueeze(0).clone())
+    return tuple(outs)

@@ -243,3 +243,66 @@ def test_soak_repeated_steps_reproduce(mode):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "mismatches: 0" in r.stdout
 
+
+
+def test_submit_host_returns_features():
+    """The host-buffer step that also returns what ORBextractor::operator() returns (keypoints + descriptors of every frame):
+    equal to the per-pair fetch of the same step, for three steps in flight."""
+    from fishbirdeyevisualslam_b200 import _lib
+    from fishbirdeyevisualslam_b200.pipeline import FrontBirdPipeline, PinnedBuffer
+    B, S = 3, 4
+    fr, bi = sequence(B * S, 900)
+    ref = run_pipeline(fr, bi, B)
+    pipe = FrontBirdPipeline(B)
+    hF, hB = [PinnedBuffer((B,) + fr.shape[1:]) for _ in range(S)], [PinnedBuffer((B,) + bi.shape[1:]) for _ in range(S)]
+    for s in range(S):
+        hF[s].array[...] = fr[s * B:(s + 1) * B]
+        hB[s].array[...] = bi[s * B:(s + 1) * B]
+    res = [PinnedBuffer((B,), _lib.PAIR_RESULT_DTYPE) for _ in range(S)]
+    fm = [PinnedBuffer((B, pipe.front_cap), np.int32) for _ in range(S)]
+    bm = [PinnedBuffer((B, pipe.bird_cap), np.int32) for _ in range(S)]
+    feat = [(PinnedBuffer((B, pipe.front_cap), _lib.KP_DTYPE), PinnedBuffer((B, pipe.front_cap, 32), np.uint8),
+             PinnedBuffer((B, pipe.bird_cap), _lib.KP_DTYPE), PinnedBuffer((B, pipe.bird_cap, 32), np.uint8)) for _ in range(S)]
+    q = []
+    for s in range(S):
+        q.append(pipe.submit_host(hF[s].ptr, hB[s].ptr, res[s].array, fm[s].array, bm[s].array, features=tuple(b.array for b in feat[s])))
+        if len(q) >= 3:
+            pipe.wait(q.pop(0))
+    for t in q:
+        pipe.wait(t)
+    for s in range(S):
+        for p in range(B):
+            r = ref[s * B + p]
+            nf, nb = int(res[s].array["n_front"][p]), int(res[s].array["n_bird"][p])
+            assert res[s].array[p].tobytes() == r["res"].tobytes()
+            assert feat[s][0].array[p][:nf].tobytes() == r["fk"].tobytes() and np.array_equal(feat[s][1].array[p][:nf], r["fd"])
+            assert feat[s][2].array[p][:nb].tobytes() == r["bk"].tobytes() and np.array_equal(feat[s][3].array[p][:nb], r["bd"])
+    pipe.close()
+
+
+def test_row_capacity_overflow_is_reported_per_step():
+    """A search window with more candidates than front_row_cap fails THAT step with FBE_E_CAPACITY (naming the pair); the
+    handle stays usable: a later step without such a window succeeds."""
+    import torch
+    from fishbirdeyevisualslam_b200 import _lib
+    from fishbirdeyevisualslam_b200.pipeline import FrontBirdPipeline
+    B = 2
+    fr, bi = sequence(2 * B, 1100)
+    pipe = FrontBirdPipeline(B, front_row_cap=4)
+    dF, dB = torch.from_numpy(fr).cuda(), torch.from_numpy(bi).cuda()
+    pipe.step_dev(dF.data_ptr(), dB.data_ptr())
+    with pytest.raises(_lib.FbeError) as ei:
+        pipe.fetch()
+    assert ei.value.code == _lib.FBE_E_CAPACITY and "pair" in str(ei.value) and "front_row_cap" in str(ei.value)
+    flatF, flatB = torch.full_like(dF[:B], 90), torch.full_like(dB[:B], 90)        # no corners -> no candidates -> no overflow
+    pipe.step_dev(flatF.data_ptr(), flatB.data_ptr())
+    pipe.step_dev(flatF.data_ptr(), flatB.data_ptr())
+    res, _, _ = pipe.fetch()
+    assert (res["n_front"] == 0).all() and (res["front_matches"] == 0).all()
+    pipe.close()
+    ok = FrontBirdPipeline(B, front_row_cap=1024)
+    ok.step_dev(dF.data_ptr(), dB.data_ptr())
+    ok.step_dev(dF[B:].data_ptr(), dB[B:].data_ptr())
+    res, _, _ = ok.fetch()
+    assert (res["front_matches"] > 100).all()
+    ok.close()
