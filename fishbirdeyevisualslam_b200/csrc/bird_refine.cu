@@ -191,29 +191,6 @@ static void subpix_mask(int hw, int hh, std::vector<float>& mask) {
     }
 }
 
-// Per-thread device arena that only grows: a call carves its buffers out of one allocation, so the steady state issues no
-// cudaMalloc / cudaFree (the entry point is re-entrant across threads like the other stateless calls of the C-ABI).
-struct Arena {
-    char* base = nullptr;
-    size_t cap = 0, used = 0;
-    int dev = -1;
-    ~Arena() { if (base) cudaFree(base); }
-    cudaError_t reserve(size_t bytes, int device) {
-        used = 0;
-        if (dev == device && cap >= bytes) return cudaSuccess;
-        if (base) { cudaFree(base); base = nullptr; cap = 0; }
-        dev = device;
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&base), bytes);
-        if (e == cudaSuccess) cap = bytes;
-        return e;
-    }
-    template <class T> T* take(size_t count) {
-        T* r = reinterpret_cast<T*>(base + used);
-        used += (count * sizeof(T) + 255) & ~(size_t)255;
-        return r;
-    }
-};
-inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 }  // namespace fbe
 

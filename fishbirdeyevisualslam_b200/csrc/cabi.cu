@@ -6,6 +6,8 @@
 
 using namespace fbe;
 
+#define FBE_TRY(expr) do { int _rc = (expr); if (_rc != FBE_OK) return _rc; } while (0)
+
 struct fbe_extractor {
     ExtractorCore core;
 };
@@ -160,6 +162,20 @@ int fbe_pyramid_level(fbe_extractor* e, int32_t slot, int32_t level, uint8_t* ds
     return FBE_OK;
 }
 
+int fbe_pyramid_fetch(fbe_extractor* e, int32_t slot, uint8_t* const* dst, const size_t* dst_step) {
+    if (!e || !dst || !dst_step || !e->core.have_ws || slot < 0 || slot >= e->core.cfg.max_batch) return FBE_E_INVALID;
+    ExtractorCore& c = e->core;
+    FBE_CUDA(cudaSetDevice(c.cfg.device));
+    for (int l = 0; l < c.cfg.nlevels; ++l) {
+        const LevelGeom& g = c.hplan.lv[l];
+        if (!dst[l] || dst_step[l] < (size_t)(g.w + 2 * kEdge)) return FBE_E_INVALID;
+        FBE_CUDA(cudaMemcpy2DAsync(dst[l], dst_step[l], c.ws.pyr + (size_t)slot * c.hplan.pyr_bytes + g.img_off, g.pitch, g.w + 2 * kEdge, g.ph,
+                                   cudaMemcpyDeviceToHost, c.stream));
+    }
+    FBE_CUDA(cudaStreamSynchronize(c.stream));
+    return FBE_OK;
+}
+
 int fbe_debug_blurred(fbe_extractor* e, int32_t slot, int32_t level, uint8_t* dst, int32_t* rows, int32_t* cols) {
     if (!e || !e->core.have_ws || level < 0 || level >= e->core.cfg.nlevels || slot < 0 || slot >= e->core.cfg.max_batch) return FBE_E_INVALID;
     ExtractorCore& c = e->core;
@@ -238,30 +254,37 @@ int fbe_debug_octree(const int32_t* xys, int32_t n, int32_t min_x, int32_t max_x
     return FBE_OK;
 }
 
+int fbe_set_device(int32_t device) {
+    FBE_CUDA(cudaSetDevice(device));
+    return FBE_OK;
+}
+
 int fbe_grid_assign(const fbe_keypoint* kps, int32_t n, float min_x, float min_y, float inv_w, float inv_h, int32_t gcols,
                     int32_t grows, int32_t* cell_start, int32_t* cell_items, int32_t* n_assigned) {
     if (n < 0 || gcols <= 0 || grows <= 0 || !cell_start || (n > 0 && (!kps || !cell_items))) return FBE_E_INVALID;
     const int gcells = gcols * grows;
-    fbe_keypoint* d_kps = nullptr;
-    int *d_n = nullptr, *d_cell = nullptr, *d_start = nullptr, *d_items = nullptr;
     const size_t nn = (size_t)std::max(n, 1);
-    FBE_CUDA(cudaMalloc(&d_kps, nn * sizeof(fbe_keypoint)));
-    FBE_CUDA(cudaMalloc(&d_n, 4));
-    FBE_CUDA(cudaMalloc(&d_cell, nn * 4));
-    FBE_CUDA(cudaMalloc(&d_start, (size_t)(gcells + 1) * 4));
-    FBE_CUDA(cudaMalloc(&d_items, nn * 4));
-    if (n > 0) FBE_CUDA(cudaMemcpy(d_kps, kps, (size_t)n * sizeof(fbe_keypoint), cudaMemcpyHostToDevice));
-    FBE_CUDA(cudaMemcpy(d_n, &n, 4, cudaMemcpyHostToDevice));
-    int rc = launch_grid_build(d_kps, d_n, (int)nn, 1, min_x, min_y, inv_w, inv_h, gcols, grows, d_cell, d_start, d_items, 0);
-    if (rc == FBE_OK) {
-        cudaError_t ce = cudaMemcpy(cell_start, d_start, (size_t)(gcells + 1) * 4, cudaMemcpyDeviceToHost);
-        if (ce == cudaSuccess && n > 0 && cell_start[gcells] > 0)
-            ce = cudaMemcpy(cell_items, d_items, (size_t)cell_start[gcells] * 4, cudaMemcpyDeviceToHost);
-        if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); rc = FBE_E_CUDA; }
-        if (n_assigned) *n_assigned = cell_start[gcells];
-    }
-    cudaFree(d_kps); cudaFree(d_n); cudaFree(d_cell); cudaFree(d_start); cudaFree(d_items);
-    return rc;
+    // per-thread arena on the thread's current device (fbe_set_device): no cudaMalloc / cudaFree in the steady state, nothing
+    // to leak on an error return
+    static thread_local Arena arena;
+    int dev = 0;
+    FBE_CUDA(cudaGetDevice(&dev));
+    FBE_CUDA(arena.reserve(pad256(nn * sizeof(fbe_keypoint)) + pad256(4) + 2 * pad256(nn * 4) + pad256((size_t)(gcells + 1) * 4), dev));
+    fbe_keypoint* d_kps = arena.take<fbe_keypoint>(nn);
+    int* d_n = arena.take<int>(1);
+    int* d_cell = arena.take<int>(nn);
+    int* d_start = arena.take<int>((size_t)gcells + 1);
+    int* d_items = arena.take<int>(nn);
+    cudaStream_t st = cudaStreamPerThread;
+    if (n > 0) FBE_CUDA(cudaMemcpyAsync(d_kps, kps, (size_t)n * sizeof(fbe_keypoint), cudaMemcpyHostToDevice, st));
+    FBE_CUDA(cudaMemcpyAsync(d_n, &n, 4, cudaMemcpyHostToDevice, st));
+    FBE_TRY(launch_grid_build(d_kps, d_n, (int)nn, 1, min_x, min_y, inv_w, inv_h, gcols, grows, d_cell, d_start, d_items, st));
+    FBE_CUDA(cudaMemcpyAsync(cell_start, d_start, (size_t)(gcells + 1) * 4, cudaMemcpyDeviceToHost, st));
+    // every keypoint lands in at most one cell: the whole item array is at most n entries (one copy, one synchronisation)
+    if (n > 0) FBE_CUDA(cudaMemcpyAsync(cell_items, d_items, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    FBE_CUDA(cudaStreamSynchronize(st));
+    if (n_assigned) *n_assigned = cell_start[gcells];
+    return FBE_OK;
 }
 
 int fbe_hamming256(const uint8_t a[32], const uint8_t b[32]) {

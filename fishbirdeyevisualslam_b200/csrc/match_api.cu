@@ -29,7 +29,25 @@ struct DevBuf {
 
 struct FrameBufs {
     DevBuf kps, desc, n, cell, start, items;
+    void release() { kps.release(); desc.release(); n.release(); cell.release(); start.release(); items.release(); }
 };
+
+// Device-resident frames of the matcher (SURVEY §8b `*_dev` intent for the per-frame drop-in chain): Tracking searches the
+// same frame several times in a row (SearchForInitialization retries, SearchByProjection with two radii, local-map search
+// after the last-frame search, bird + front on the same Frame ...).  The last few frames handed in through fbe_frame_view stay
+// on the device together with their CSR grid; a view is recognised by CONTENT (a host shadow copy is compared byte for byte:
+// ~5 us for 2000 keypoints, cheaper than three pageable uploads + the grid build), never by pointer, so a recycled
+// std::vector address can not alias a stale entry.
+struct CachedFrame {
+    FrameBufs b;
+    std::vector<uint8_t> shadow_kps, shadow_desc;
+    int n = -1;
+    bool has_grid = false;
+    float min_x = 0, min_y = 0, inv_w = 0, inv_h = 0;
+    int gcols = 0, grows = 0;
+    unsigned long long used = 0;
+};
+constexpr int kFrameCache = 4;
 
 }  // namespace
 
@@ -39,7 +57,9 @@ struct fbe_matcher {
     int device;
     cudaStream_t stream = nullptr;
     int row_cap = 128;
-    FrameBufs fa, fb;                          // target frame / auxiliary source frame
+    FrameBufs fa, fb;                          // target frame / auxiliary source frame (array-based entry points)
+    CachedFrame cache[kFrameCache];            // frames given as fbe_frame_view
+    unsigned long long tick = 0, cache_hits = 0, cache_misses = 0;
     DevBuf q, lv, qdesc, nq, rows, cnt, misc, i0, i1, i2, i3, i4, u0, u1, f0, partial;
 };
 
@@ -53,26 +73,52 @@ int upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t st) {
     return FBE_OK;
 }
 
-// uploads keypoints + descriptors of a frame and builds its CSR grid on the device
-int upload_frame(fbe_matcher* m, FrameBufs& fb, const fbe_frame_view* v, bool with_grid, FrameDev& out) {
+// keypoints + descriptors of a frame on the device, with its CSR grid when asked for: served from the matcher's frame cache
+// when the same content was seen recently, uploaded (and grid-built) otherwise
+int upload_frame(fbe_matcher* m, FrameBufs& /*unused: cached frames own their buffers*/, const fbe_frame_view* v, bool with_grid, FrameDev& out) {
     if (!v || v->n < 0 || (v->n > 0 && (!v->kps || !v->desc))) return FBE_E_INVALID;
+    if (with_grid && (v->gcols <= 0 || v->grows <= 0)) return FBE_E_INVALID;
     const int n = v->n, stride = std::max(n, 1);
-    FBE_TRY(upload(fb.kps, v->kps, (size_t)n * sizeof(fbe_keypoint), m->stream));
-    FBE_TRY(upload(fb.desc, v->desc, (size_t)n * 32, m->stream));
-    FBE_TRY(upload(fb.n, &v->n, sizeof(int), m->stream));
+    const size_t kb = (size_t)n * sizeof(fbe_keypoint), db = (size_t)n * 32;
+    const unsigned long long tick = ++m->tick;
+    CachedFrame* e = nullptr;
+    for (CachedFrame& c : m->cache)
+        if (c.n == n && (n == 0 || (std::memcmp(c.shadow_kps.data(), v->kps, kb) == 0 && std::memcmp(c.shadow_desc.data(), v->desc, db) == 0))) { e = &c; break; }
+    if (e) {
+        ++m->cache_hits;
+    } else {
+        ++m->cache_misses;
+        e = &m->cache[0];
+        for (CachedFrame& c : m->cache) if (c.used < e->used) e = &c;       // least recently used (the other frame of this call is the newest)
+        e->n = -1; e->has_grid = false;
+        FBE_TRY(upload(e->b.kps, v->kps, kb, m->stream));
+        FBE_TRY(upload(e->b.desc, v->desc, db, m->stream));
+        FBE_TRY(upload(e->b.n, &v->n, sizeof(int), m->stream));
+        // the caller's arrays cannot change before this (synchronous) entry point returns: the shadow equals what was uploaded
+        e->shadow_kps.assign(reinterpret_cast<const uint8_t*>(v->kps), reinterpret_cast<const uint8_t*>(v->kps) + kb);
+        e->shadow_desc.assign(v->desc, v->desc + db);
+        e->n = n;
+    }
+    e->used = tick;
     out = FrameDev();
-    out.kps = fb.kps.as<fbe_keypoint>(); out.desc = fb.desc.as<uint8_t>(); out.n = fb.n.as<int>();
+    out.kps = e->b.kps.as<fbe_keypoint>(); out.desc = e->b.desc.as<uint8_t>(); out.n = e->b.n.as<int>();
     out.kp_stride = stride;
     out.min_x = v->min_x; out.min_y = v->min_y; out.inv_w = v->inv_w; out.inv_h = v->inv_h;
     out.gcols = v->gcols; out.grows = v->grows;
     if (with_grid) {
-        if (v->gcols <= 0 || v->grows <= 0) return FBE_E_INVALID;
-        FBE_TRY(fb.cell.ensure((size_t)stride * 4));
-        FBE_TRY(fb.start.ensure((size_t)(v->gcols * v->grows + 1) * 4));
-        FBE_TRY(fb.items.ensure((size_t)stride * 4));
-        FBE_TRY(launch_grid_build(out.kps, out.n, stride, 1, v->min_x, v->min_y, v->inv_w, v->inv_h, v->gcols, v->grows,
-                                  fb.cell.as<int>(), fb.start.as<int>(), fb.items.as<int>(), m->stream));
-        out.start = fb.start.as<int>(); out.items = fb.items.as<int>();
+        const bool same = e->has_grid && e->min_x == v->min_x && e->min_y == v->min_y && e->inv_w == v->inv_w && e->inv_h == v->inv_h &&
+                          e->gcols == v->gcols && e->grows == v->grows;
+        if (!same) {
+            e->has_grid = false;
+            FBE_TRY(e->b.cell.ensure((size_t)stride * 4));
+            FBE_TRY(e->b.start.ensure((size_t)(v->gcols * v->grows + 1) * 4));
+            FBE_TRY(e->b.items.ensure((size_t)stride * 4));
+            FBE_TRY(launch_grid_build(out.kps, out.n, stride, 1, v->min_x, v->min_y, v->inv_w, v->inv_h, v->gcols, v->grows,
+                                      e->b.cell.as<int>(), e->b.start.as<int>(), e->b.items.as<int>(), m->stream));
+            e->min_x = v->min_x; e->min_y = v->min_y; e->inv_w = v->inv_w; e->inv_h = v->inv_h; e->gcols = v->gcols; e->grows = v->grows;
+            e->has_grid = true;
+        }
+        out.start = e->b.start.as<int>(); out.items = e->b.items.as<int>();
     }
     return FBE_OK;
 }
@@ -137,10 +183,18 @@ int fbe_matcher_destroy(fbe_matcher* m) {
     if (!m) return FBE_E_INVALID;
     cudaSetDevice(m->device);
     cudaStreamSynchronize(m->stream);
-    for (FrameBufs* f : {&m->fa, &m->fb}) { f->kps.release(); f->desc.release(); f->n.release(); f->cell.release(); f->start.release(); f->items.release(); }
+    m->fa.release(); m->fb.release();
+    for (CachedFrame& c : m->cache) c.b.release();
     for (DevBuf* b : {&m->q, &m->lv, &m->qdesc, &m->nq, &m->rows, &m->cnt, &m->misc, &m->i0, &m->i1, &m->i2, &m->i3, &m->i4, &m->u0, &m->u1, &m->f0, &m->partial}) b->release();
     cudaStreamDestroy(m->stream);
     delete m;
+    return FBE_OK;
+}
+
+int fbe_matcher_cache_stats(const fbe_matcher* m, uint64_t* hits, uint64_t* misses) {
+    if (!m) return FBE_E_INVALID;
+    if (hits) *hits = m->cache_hits;
+    if (misses) *misses = m->cache_misses;
     return FBE_OK;
 }
 

@@ -26,6 +26,8 @@ void fill_grid(const std::vector<cv::KeyPoint>& keys, int n, float min_x, float 
                std::vector<std::size_t> (&grid)[COLS][ROWS]) {
     std::vector<int> start(COLS * ROWS + 1, 0), items(n > 0 ? n : 1, 0);
     int assigned = 0;
+    static thread_local const int dev_rc = fbe_set_device(fbe_host_device());     // same GPU as the extractor and the matchers
+    (void)dev_rc;
     if (n > 0 && fbe_grid_assign(reinterpret_cast<const fbe_keypoint*>(keys.data()), n, min_x, min_y, inv_w, inv_h, COLS, ROWS,
                                  start.data(), items.data(), &assigned) != FBE_OK) {
         fprintf(stderr, "Frame::AssignFeaturesToGrid (fbe-b200): %s\n", fbe_last_error());

@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "fbe_cabi.h"
+#include "fbe_host.h"
 
 namespace ORB_SLAM2 {
 
@@ -20,11 +21,11 @@ static void die(const char* what, int rc) {
 
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
-      handle_(NULL) {
+      handle_(NULL), fill_pyramid_(true), pyr_host_(NULL), pyr_host_bytes_(0), pyr_rows_(0), pyr_cols_(0) {
     fbe_extractor_cfg cfg;
     cfg.nfeatures = _nfeatures; cfg.scale_factor = _scaleFactor; cfg.nlevels = _nlevels;
-    cfg.ini_th_fast = _iniThFAST; cfg.min_th_fast = _minThFAST; cfg.max_batch = 1; cfg.device = 0;
-    if (const char* d = std::getenv("FBE_DEVICE")) cfg.device = std::atoi(d);
+    cfg.ini_th_fast = _iniThFAST; cfg.min_th_fast = _minThFAST; cfg.max_batch = 1; cfg.device = fbe_host_device();
+    if (const char* p = std::getenv("FBE_IMAGE_PYRAMID")) fill_pyramid_ = std::atoi(p) != 0;
     int rc = fbe_extractor_create(&cfg, &handle_);
     if (rc != FBE_OK) die("fbe_extractor_create", rc);
     int32_t n = 0;
@@ -41,6 +42,8 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
 }
 
 ORBextractor::~ORBextractor() {
+    mvImagePyramid.clear();
+    if (pyr_host_) fbe_host_free(pyr_host_);
     if (handle_) fbe_extractor_destroy(handle_);
 }
 
@@ -71,15 +74,43 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, st
     }
     kps.resize(n);
     _keypoints.swap(kps);
+    if (fill_pyramid_) FillImagePyramid(image.rows, image.cols);
 }
 
-void ORBextractor::SyncImagePyramid() {
+// mvImagePyramid of the image just processed (src/ORBextractor.cc:1107-1132 leaves it behind as a side effect of operator()).
+void ORBextractor::FillImagePyramid(int rows, int cols) {
+    std::vector<unsigned char*> dst(nlevels);
+    std::vector<size_t> steps(nlevels);
+    std::vector<int32_t> lr(nlevels), lc(nlevels);
+    size_t total = 0;
     for (int l = 0; l < nlevels; ++l) {
-        int32_t r = 0, c = 0;
-        if (fbe_pyramid_level(handle_, 0, l, NULL, 0, &r, &c) != FBE_OK) return;
-        cv::Mat padded(r + 38, c + 38, CV_8UC1);
-        fbe_pyramid_level(handle_, 0, l, padded.ptr(0), (size_t)padded.step, &r, &c);
-        mvImagePyramid[l] = padded(cv::Rect(19, 19, c, r));      // ROI view with the 19-px frame around it, like the reference
+        int rc = fbe_pyramid_level(handle_, 0, l, NULL, 0, &lr[l], &lc[l]);
+        if (rc != FBE_OK) die("fbe_pyramid_level", rc);
+        steps[l] = ((size_t)lc[l] + 38 + 63) & ~(size_t)63;
+        total += steps[l] * (size_t)(lr[l] + 38);
+    }
+    if (total > pyr_host_bytes_ || rows != pyr_rows_ || cols != pyr_cols_) {
+        for (int l = 0; l < nlevels; ++l) mvImagePyramid[l] = cv::Mat();
+        if (total > pyr_host_bytes_) {
+            if (pyr_host_) fbe_host_free(pyr_host_);
+            void* p = NULL;
+            int rc = fbe_host_alloc(&p, total);
+            if (rc != FBE_OK) die("fbe_host_alloc", rc);
+            pyr_host_ = static_cast<unsigned char*>(p);
+            pyr_host_bytes_ = total;
+        }
+        pyr_rows_ = rows; pyr_cols_ = cols;
+    }
+    size_t off = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        dst[l] = pyr_host_ + off;
+        off += steps[l] * (size_t)(lr[l] + 38);
+    }
+    int rc = fbe_pyramid_fetch(handle_, 0, dst.data(), steps.data());
+    if (rc != FBE_OK) die("fbe_pyramid_fetch", rc);
+    for (int l = 0; l < nlevels; ++l) {
+        cv::Mat padded(lr[l] + 38, lc[l] + 38, CV_8UC1, dst[l], steps[l]);
+        mvImagePyramid[l] = padded(cv::Rect(19, 19, lc[l], lr[l]));      // ROI view with the 19-px frame around it, like the reference
     }
 }
 

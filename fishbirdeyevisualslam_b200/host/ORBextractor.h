@@ -30,10 +30,12 @@ public:
     std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
     std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 
-    // Filled lazily: the pyramid lives on the device; call SyncImagePyramid() before reading it on the host
-    // (only Frame::ComputeStereoMatches does, src/Frame.cc:804,894,911 -- the stereo path).
+    // Filled by every operator() call like the reference's ComputePyramid (include/ORBextractor.h:85; read by
+    // Frame::ComputeStereoMatches, src/Frame.cc:804,894,911): ROI views (19-px frame around them) over ONE pinned host buffer
+    // owned by this extractor, refreshed by a DMA copy of the device pyramid.  A Mat taken from here is valid until the next
+    // operator() call of the same extractor (clone() it to keep it).  FBE_IMAGE_PYRAMID=0 in the environment skips the copy
+    // for callers that never read the pyramid (this fork's monocular + bird-view tracking) and leaves the Mats empty.
     std::vector<cv::Mat> mvImagePyramid;
-    void SyncImagePyramid();
 
 protected:
     int nfeatures;
@@ -51,6 +53,11 @@ private:
     ORBextractor(const ORBextractor&);
     ORBextractor& operator=(const ORBextractor&);
     fbe_extractor* handle_;
+    bool fill_pyramid_;
+    unsigned char* pyr_host_;         // pinned (fbe_host_alloc)
+    size_t pyr_host_bytes_;
+    int pyr_rows_, pyr_cols_;         // image size the views were laid out for
+    void FillImagePyramid(int rows, int cols);
 };
 
 }  // namespace ORB_SLAM2

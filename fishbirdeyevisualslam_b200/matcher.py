@@ -203,6 +203,12 @@ class ORBmatcher:
 
     __del__ = close
 
+    def cache_stats(self):
+        """(hits, misses) of the matcher's device-resident frame cache (frames are recognised by content)."""
+        h, m = C.c_uint64(), C.c_uint64()
+        check(self._L.fbe_matcher_cache_stats(self._h, C.byref(h), C.byref(m)))
+        return h.value, m.value
+
     @staticmethod
     def DescriptorDistance(a: np.ndarray, b: np.ndarray) -> int:
         """ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1951-1967): host inline, never a device round trip."""

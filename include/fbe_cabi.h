@@ -101,6 +101,10 @@ FBE_API int fbe_extract_batch(fbe_extractor* e, const uint8_t* const* imgs, int3
  * with its 19-px REFLECT_101 frame ((rows+38) x (cols+38) written to dst). dst may be NULL to query the size. */
 FBE_API int fbe_pyramid_level(fbe_extractor* e, int32_t slot, int32_t level, uint8_t* dst_padded, size_t dst_step,
                       int32_t* rows, int32_t* cols);
+/* All levels of one slot in one call (the drop-in ORBextractor::operator() fills mvImagePyramid with it): dst_padded[l] receives
+ * the padded (rows+38) x (cols+38) level l with row stride dst_step[l]; the copies are enqueued together and waited for once.
+ * Pinned destinations (fbe_host_alloc) make them true DMA transfers. */
+FBE_API int fbe_pyramid_fetch(fbe_extractor* e, int32_t slot, uint8_t* const* dst_padded, const size_t* dst_step);
 
 /* Stage taps for the parity tests (slot of the LAST call). Not part of the reference interface. */
 /* vToDistributeKeys of one level in reference order: (x, y, score) triples in level coordinates */
@@ -211,6 +215,10 @@ FBE_API int fbe_bird_refine_batch(const uint8_t* contours, size_t contour_step, 
                                   int32_t max_iter, double eps, int32_t device, uint8_t* keep, fbe_keypoint* out_kps,
                                   int32_t* n_out, int32_t* iters);
 
+/* Selects the CUDA device of the CALLING THREAD for the entry points that take no handle and no device argument
+ * (fbe_grid_assign).  The host shims call it once per thread with FBE_DEVICE. */
+FBE_API int fbe_set_device(int32_t device);
+
 /* ---- Frame grid -------------------------------------------------------------------------------- */
 /* Frame::AssignFeaturesToGrid / PosInGrid / PosInGridBirdview, src/Frame.cc:381-411,548-570.
  * cell = (round((x-min_x)*inv_w), round((y-min_y)*inv_h)), dropped when outside gcols x grows.
@@ -236,6 +244,10 @@ typedef struct fbe_matcher fbe_matcher;
 /* ORBmatcher::ORBmatcher(nnratio, checkOri), src/ORBmatcher.cc:42 */
 FBE_API int fbe_matcher_create(float nn_ratio, int32_t check_orientation, int32_t device, fbe_matcher** out);
 FBE_API int fbe_matcher_destroy(fbe_matcher* m);
+/* Frames handed in as fbe_frame_view stay on the device (keypoints, descriptors, CSR grid) in a small per-matcher cache and
+ * are recognised by content, so the searches Tracking runs back to back on one Frame upload and bucket it once.
+ * Diagnostic counters of that cache (either pointer may be NULL). */
+FBE_API int fbe_matcher_cache_stats(const fbe_matcher* m, uint64_t* hits, uint64_t* misses);
 
 /* ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:406-521.
  * prev_matched: n1 (x,y) pairs, in/out (vbPrevMatched). matches12: n1 ints out (-1 = none). */

@@ -79,6 +79,7 @@ public:
     Mat();
     Mat(Size sz, int type);
     Mat(int rows, int cols, int type);
+    Mat(int rows, int cols, int type, void* data, size_t step);   // header over external memory (not owned)
     Mat(const Mat& m);
     Mat(const MatZeros& z);
     ~Mat();

@@ -19,6 +19,7 @@ namespace cv {
 Mat::Mat() : rows(0), cols(0), step(0), data(nullptr) {}
 Mat::Mat(Size sz, int type) : rows(0), cols(0), step(0), data(nullptr) { create(sz.height, sz.width, type); }
 Mat::Mat(int r, int c, int type) : rows(0), cols(0), step(0), data(nullptr) { create(r, c, type); }
+Mat::Mat(int r, int c, int, void* d, size_t st) : rows(r), cols(c), step(st), data(static_cast<uchar*>(d)) {}
 Mat::Mat(const Mat& m) : rows(m.rows), cols(m.cols), step(m.step), data(m.data), buf_(m.buf_) {}
 Mat::Mat(const MatZeros& z) : rows(0), cols(0), step(0), data(nullptr) { *this = z; }
 Mat::~Mat() {}

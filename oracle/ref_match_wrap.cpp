@@ -19,6 +19,7 @@
 #include <mutex>
 #include <set>
 #include <string>
+#include <chrono>
 #include <vector>
 #include "ORBVocabulary.h"
 #include "opencv2/core/core.hpp"
@@ -172,6 +173,8 @@ bool check_grid(const FrameView& f, int cols, int rows) { return f.gcols == cols
 
 }  // namespace
 
+static double g_last_method_us = 0.0;
+
 extern "C" {
 
 // Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:381-411, 548-558) as CSR [ix*rows+iy]
@@ -223,10 +226,16 @@ int refm_search_for_initialization(const FrameView* f1, const FrameView* f2, flo
     for (int i = 0; i < f1->n; ++i) prev[i] = cv::Point2f(prev_matched[2 * i], prev_matched[2 * i + 1]);
     std::vector<int> m12;
     ORBmatcher m(nn_ratio, check_ori != 0);
+    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     const int n = m.SearchForInitialization(F1, F2, prev, m12, window);
+    g_last_method_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
     for (int i = 0; i < f1->n; ++i) { matches12[i] = m12[i]; prev_matched[2 * i] = prev[i].x; prev_matched[2 * i + 1] = prev[i].y; }
     return n;
 }
+
+// wall time of the ORBmatcher METHOD CALL inside the last refm_search_for_initialization (the harness's Frame construction
+// from POD arrays is outside it): used to time config C1 through the C++ class (tools/c1_cpp.py)
+double refm_last_method_us() { return g_last_method_us; }
 
 // ORBmatcher::BirdviewMatch, isProject == 0 (src/ORBmatcher.cc:1602-1760)
 int refm_birdview_match(const Kp* ref_kps, const uint8_t* ref_desc, int n_ref, const FrameView* cur, int window, float nn_ratio,

@@ -18,7 +18,6 @@ int main(int argc, char** argv) {
     cv::Mat desc;
     (*ex)(im, cv::Mat(), keys, desc);
     (*ex)(im, cv::Mat(), keys, desc);            // second call reuses the workspace
-    ex->SyncImagePyramid();
     int n = (int)keys.size();
     f = std::fopen(argv[6], "wb");
     std::fwrite(&n, 4, 1, f);

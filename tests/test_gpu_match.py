@@ -404,3 +404,55 @@ def test_widened_entry_points_edge_cases(oracle):
                                  Fm.ctypes.data_as(C.c_void_p), 1, C.c_float(1.0), 0, sc.ctypes.data_as(C.c_void_p), None)
     assert rc != 0
 
+
+
+def test_frame_cache_is_content_addressed(oracle):
+    """Frames handed to the matcher stay on the device between calls and are recognised by CONTENT: repeated searches on the
+    same frames hit the cache and give identical results; changing one keypoint in place (same buffer address) is a miss and
+    gives the result of the changed frame."""
+    import numpy as np
+    from fishbirdeyevisualslam_b200 import synth
+    from fishbirdeyevisualslam_b200.extractor import ORBextractor
+    from fishbirdeyevisualslam_b200.matcher import Frame, ORBmatcher
+    h, w = 240, 320
+    a, b = synth.frame_pair_in_time(h, w, 21)
+    ex = ORBextractor(500, 1.2, 6, 15, 5)
+    ka, da = ex(a)
+    kb, db = ex(b)
+    F1, F2 = Frame.front(ka, da, w, h), Frame.front(kb, db, w, h)
+    m = ORBmatcher(0.9, True)
+
+    def run():
+        pm = np.ascontiguousarray(np.stack([F1.kps["x"], F1.kps["y"]], 1), np.float32)
+        n, m12 = m.SearchForInitialization(F1, F2, pm, 100)
+        pmo = np.ascontiguousarray(np.stack([F1.kps["x"], F1.kps["y"]], 1), np.float32)
+        no, m12o = oracle.search_for_initialization(F1, F2, pmo, 100, 0.9, True)
+        assert n == no and np.array_equal(m12, m12o) and np.array_equal(pm, pmo)
+        return n
+
+    n0 = run()
+    assert m.cache_stats() == (0, 2)
+    assert run() == n0 and run() == n0
+    assert m.cache_stats() == (4, 2)
+    # SearchByProjection-style reuse with another window radius: still the same two frames
+    pm = np.ascontiguousarray(np.stack([F1.kps["x"], F1.kps["y"]], 1), np.float32)
+    m.SearchForInitialization(F1, F2, pm, 50)
+    assert m.cache_stats() == (6, 2)
+    # in-place change of the target frame (same address, different content) must not be served from the cache
+    F2.kps["x"][5] += 40.0
+    F2.kps["y"][5] += 25.0
+    run()
+    assert m.cache_stats() == (7, 3)
+    # six different frames cycle through the four entries without confusing contents
+    frames = []
+    for s in range(6):
+        k, d = ex(synth.frame(h, w, 40 + s))
+        frames.append(Frame.front(k, d, w, h))
+    for rep in range(2):
+        for f in frames:
+            pm = np.ascontiguousarray(np.stack([F1.kps["x"], F1.kps["y"]], 1), np.float32)
+            pmo = pm.copy()
+            n, m12 = m.SearchForInitialization(F1, f, pm, 100)
+            no, m12o = oracle.search_for_initialization(F1, f, pmo, 100, 0.9, True)
+            assert n == no and np.array_equal(m12, m12o)
+    m.close()

@@ -111,8 +111,8 @@ def test_gather_matches_single_gpu_aliases_device_records():
     from fishbirdeyevisualslam_b200.shard import gather_matches
     B = 4
     pipe = FrontBirdPipeline(B, (240, 320), (256, 256), 500, 300)
-    fr = synth.cheap_batch(2 * B, 240, 320, 5)
-    bi = synth.cheap_batch(2 * B, 256, 256, 6)
+    fr = np.stack([synth.frame(240, 320, 5, (i - 4, i // 2 - 2), noise_seed=i) for i in range(2 * B)])       # one scene, drifting window
+    bi = np.stack([synth.frame(256, 256, 6, (i - 4, i // 2 - 2), noise_seed=40 + i) for i in range(2 * B)])
     for k in range(2):
         dF, dB = torch.from_numpy(fr[k * B:(k + 1) * B]).cuda(), torch.from_numpy(bi[k * B:(k + 1) * B]).cuda()
         pipe.step_dev(dF.data_ptr(), dB.data_ptr())
