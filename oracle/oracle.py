@@ -536,6 +536,50 @@ def corner_subpix(img, xy, half_win=(5, 5), max_iter=40, eps=0.001):
     return out, it
 
 
+def resize_linear_exact(img, dw, dh):
+    """cv::resize(img u8, (dw, dh), INTER_LINEAR_EXACT) restated (the resize of cv::ORB's image / mask pyramid)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros((dh, dw), np.uint8)
+    lib().orc_resize_linear_exact_u8(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), dw, dh, dw)
+    return out
+
+
+def cvorb_blur(img):
+    """The GaussianBlur cv::ORB applies to a pyramid level (float sepFilter2D path with FMA, see oracle/cvorb_oracle.cpp)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros_like(img)
+    lib().orc_cvorb_blur(_p(img), img.shape[0], img.shape[1], img.strides[0], _p(out))
+    return out
+
+
+def cvorb_detect(img, mask=None, nfeatures=2000):
+    """cv::ORB::create(nfeatures)->detect(img, keypoints, mask) restated -> keypoints (KP_DTYPE) in cv::ORB's output order."""
+    img = np.asarray(img)
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    if mask is not None:
+        mask = np.asarray(mask)
+        assert mask.dtype == np.uint8 and mask.shape == img.shape and mask.strides[1] == 1
+    cap = 4 * nfeatures + 4096
+    while True:
+        out = np.zeros(cap, KP_DTYPE)
+        n = lib().orc_cvorb_detect(_p(img), img.shape[0], img.shape[1], img.strides[0], None if mask is None else _p(mask),
+                                   0 if mask is None else mask.strides[0], int(nfeatures), _p(out), cap, None)
+        if n <= cap:
+            return out[:n].copy()
+        cap = n
+
+
+def cvorb_compute(img, kps):
+    """cv::ORB::create(...)->compute(img, keypoints, descriptors) restated -> (surviving keypoints, descriptors [n, 32])."""
+    img = np.asarray(img)
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    k = np.array(kps, KP_DTYPE, order="C")
+    d = np.zeros((max(len(k), 1), 32), np.uint8)
+    n = lib().orc_cvorb_compute(_p(img), img.shape[0], img.shape[1], img.strides[0], _p(k), len(k), _p(d))
+    assert n >= 0
+    return k[:n].copy(), d[:n].copy()
+
+
 def rect_subpix(img, cx, cy, ww, wh):
     """cv::getRectSubPix(img u8, (ww, wh), (cx, cy), patchType=CV_32F) restated."""
     img = np.asarray(img); out = np.zeros((wh, ww), np.float32)

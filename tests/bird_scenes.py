@@ -59,3 +59,17 @@ def as_kps(xy: np.ndarray) -> np.ndarray:
     k["size"], k["angle"], k["octave"], k["class_id"] = 31, -1, 0, -1
     k["response"] = np.arange(len(xy), dtype=np.float32)          # a tag: the compaction must keep records whole and in order
     return k
+
+
+def bird_mask(seed: int, rows: int = 384, cols: int = 384):
+    """mBirdviewMask stand-ins: seed 0 -> no mask, 1 -> a vehicle-shaped hole (0) in 255 with a few non-binary values, 2 -> left half."""
+    if seed % 3 == 0:
+        return None
+    m = np.full((rows, cols), 255, np.uint8)
+    if seed % 3 == 1:
+        m[rows // 2 - 70:rows // 2 + 70, cols // 2 - 35:cols // 2 + 35] = 0
+        m[:40, :] = 7                       # non-zero, non-255: cv2 4.13 keeps these on every level
+        m[rows - 30:, cols - 120:] = 0
+    else:
+        m[:, cols // 2 + 8:] = 0
+    return m
