@@ -178,6 +178,8 @@ k_corner_subpix(const uint8_t* __restrict__ img, int rows, int cols, size_t step
     }
 }
 
+static inline bool img_too_large(int hw, int hh) { return hw < 1 || hh < 1 || hw > 10 || hh > 10; }
+
 static void subpix_mask(int hw, int hh, std::vector<float>& mask) {
     const int ww = 2 * hw + 1, wh = 2 * hh + 1;
     mask.resize((size_t)ww * wh);
@@ -191,6 +193,47 @@ static void subpix_mask(int hw, int hh, std::vector<float>& mask) {
     }
 }
 
+// Device-resident form for the bird feature block (bird_orb.cu chains detect -> this -> compute without a host round trip):
+// contour / img are [B][rows][cols] tightly packed device images (either may be NULL), d_in [B][cap] keypoints with counts
+// d_nin[B].  With a contour the kept keypoints go to d_out / d_nkept (ordered); cornerSubPix then refines that list in place.
+// *d_result / *d_result_n name the arrays that hold the final list.  d_mask: 441 floats of scratch.
+int launch_bird_refine_dev(const uint8_t* d_contour, const uint8_t* d_img, int rows, int cols, int B, fbe_keypoint* d_in, const int* d_nin,
+                           int cap, int half_w, int half_h, int max_iter, double eps, uint8_t* d_keep, fbe_keypoint* d_out, int* d_nkept,
+                           int* d_iters, float* d_mask, fbe_keypoint** d_result, const int** d_result_n, cudaStream_t st) {
+    if (img_too_large(half_w, half_h)) return FBE_E_INVALID;
+    const size_t total = (size_t)B * cap, img_bytes = (size_t)rows * cols;
+    const dim3 grid((cap + kWarpsPerCta - 1) / kWarpsPerCta, B);
+    fbe_keypoint* d_cur = d_in;
+    const int* d_count = d_nin;
+    if (d_contour) {
+        FBE_CUDA(cudaMemsetAsync(d_keep, 0, total, st));
+        k_near_edges<<<grid, kWarpsPerCta * 32, 0, st>>>(d_contour, rows, cols, (size_t)cols, img_bytes, d_cur, d_nin, cap, d_keep);
+        k_compact_kept<<<dim3(1, B), 1024, 0, st>>>(d_cur, d_keep, d_nin, cap, d_out, d_nkept);
+        count_launch(2);
+        d_cur = d_out;
+        d_count = d_nkept;
+    }
+    if (d_img) {
+        std::vector<float> mask;
+        subpix_mask(half_w, half_h, mask);
+        FBE_CUDA(cudaMemcpyAsync(d_mask, mask.data(), mask.size() * sizeof(float), cudaMemcpyHostToDevice, st));   // pageable: staged before return
+        FBE_CUDA(cudaMemsetAsync(d_iters, 0, total * sizeof(int), st));
+        if (max_iter < 1) max_iter = 1;
+        if (max_iter > 100) max_iter = 100;
+        double e2 = eps > 0 ? eps : 0;
+        e2 *= e2;
+        const int nq = (2 * half_w + 1) * (2 * half_h + 1), np = (2 * half_w + 3) * (2 * half_h + 3);
+        const size_t smem = (size_t)kWarpsPerCta * (5 * nq + (np + 1) / 2) * sizeof(double);
+        FBE_CUDA(cudaFuncSetAttribute(k_corner_subpix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_corner_subpix<<<grid, kWarpsPerCta * 32, smem, st>>>(d_img, rows, cols, (size_t)cols, img_bytes, d_cur, d_count, cap, half_w, half_h,
+                                                               max_iter, e2, d_mask, d_iters);
+        count_launch();
+    }
+    FBE_CUDA(cudaGetLastError());
+    *d_result = d_cur;
+    *d_result_n = d_count;
+    return FBE_OK;
+}
 
 }  // namespace fbe
 

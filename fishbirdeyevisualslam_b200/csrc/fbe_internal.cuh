@@ -165,6 +165,11 @@ int launch_grid_build(const fbe_keypoint* d_kps, const int* d_n, int n_stride, i
                       float inv_w, float inv_h, int gcols, int grows, int* d_cell_of, int* d_start, int* d_items,
                       cudaStream_t st);
 
+// bird-view guidance + cornerSubPix on device-resident arrays (bird_refine.cu), chained by the bird feature block (bird_orb.cu)
+int launch_bird_refine_dev(const uint8_t* d_contour, const uint8_t* d_img, int rows, int cols, int B, fbe_keypoint* d_in, const int* d_nin,
+                           int cap, int half_w, int half_h, int max_iter, double eps, uint8_t* d_keep, fbe_keypoint* d_out, int* d_nkept,
+                           int* d_iters, float* d_mask, fbe_keypoint** d_result, const int** d_result_n, cudaStream_t st);
+
 // ---- extractor core: plan + workspace + run ------------------------------------------------------
 struct ExtractorCore {
     fbe_extractor_cfg cfg;

@@ -215,6 +215,39 @@ FBE_API int fbe_bird_refine_batch(const uint8_t* contours, size_t contour_step, 
                                   int32_t max_iter, double eps, int32_t device, uint8_t* keep, fbe_keypoint* out_kps,
                                   int32_t* n_out, int32_t* iters);
 
+/* ---- The bird-view feature path the reference ships (row f-3): cv::ORB::create(2000) detect + compute ------------------ */
+/* src/Frame.cc:336-338  cv::Ptr<cv::ORB> extractorBird = cv::ORB::create(2000); extractorBird->detect(mBirdviewImg, preKeysBird, mBirdviewMask);
+ * src/Frame.cc:355      extractorBird->compute(mBirdviewImg, mvKeysBird, mDescriptorsBird);
+ * cv::ORB with its default parameters (scale 1.2, 8 levels, edge 31, Harris score, patch 31, FAST threshold 20), in the
+ * arithmetic of OpenCV 4.13 (pinned by the oracle against cv2 4.13.0): same keypoints in the same ORDER, same float
+ * responses / angles, same descriptors.  One handle = one image size and up to max_batch frames per call. */
+typedef struct fbe_bird_orb fbe_bird_orb;
+FBE_API int fbe_bird_orb_create(int32_t nfeatures, int32_t rows, int32_t cols, int32_t max_batch, int32_t device, fbe_bird_orb** out);
+FBE_API int fbe_bird_orb_destroy(fbe_bird_orb* h);
+/* capacity (records per frame) of the keypoint / descriptor arrays of the calls below */
+FBE_API int fbe_bird_orb_max_keypoints(const fbe_bird_orb* h, int32_t* cap);
+/* detect(): imgs / masks = nframes 8-bit images `stride` bytes apart with rows of `step` bytes (masks may be NULL; any non-zero
+ * mask value keeps a keypoint, on every level, as in OpenCV 4.13).  kps [nframes][cap], n [nframes].
+ * FBE_E_CAPACITY when response ties make a frame exceed cap; FBE_E_UNSUPPORTED when std::nth_element's heap-select fallback
+ * would be needed (never observed; reported instead of guessed). */
+/* parity-test tap: KeyPointsFilter::retainBest (std::nth_element + std::partition, larger response first) replayed on the device
+ * for an arbitrary response array -> order[n] = the permutation the algorithms leave behind (indices into `response`), of
+ * which the first *n_kept survive (-1: the heap-select fallback would have been needed). */
+FBE_API int fbe_debug_retain_best(const float* response, int32_t n, int32_t n_points, int32_t device, int32_t* order, int32_t* n_kept);
+FBE_API int fbe_bird_orb_detect(fbe_bird_orb* h, const uint8_t* imgs, size_t step, size_t stride, const uint8_t* masks, size_t mask_step,
+                                size_t mask_stride, int32_t nframes, fbe_keypoint* kps, int32_t* n);
+/* compute(): kps [nframes][cap] / n [nframes] in and out (keypoints within 31 px of the image border are removed, an unsorted
+ * list is regrouped by octave, as cv::ORB does), desc [nframes][cap][32]. */
+FBE_API int fbe_bird_orb_compute(fbe_bird_orb* h, const uint8_t* imgs, size_t step, size_t stride, int32_t nframes, fbe_keypoint* kps,
+                                 int32_t* n, uint8_t* desc);
+/* The reference's whole bird block, src/Frame.cc:336-355, device-resident: detect -> GuidenceKeyBirdPts (contours != NULL:
+ * Frame::nearEdges filter on mBirdviewContourICP, kept in order) -> cv::cornerSubPix(img, pts, Size(5,5), Size(-1,-1),
+ * {EPS+MAX_ITER, 40, 0.001}) -> compute.  Out: mvKeysBird [nframes][cap], their number, mDescriptorsBird [nframes][cap][32];
+ * n_detected (may be NULL) = |preKeysBird| per frame. */
+FBE_API int fbe_bird_features(fbe_bird_orb* h, const uint8_t* imgs, size_t step, size_t stride, const uint8_t* masks, size_t mask_step,
+                              size_t mask_stride, const uint8_t* contours, size_t contour_step, size_t contour_stride, int32_t nframes,
+                              fbe_keypoint* kps, int32_t* n, uint8_t* desc, int32_t* n_detected);
+
 /* Selects the CUDA device of the CALLING THREAD for the entry points that take no handle and no device argument
  * (fbe_grid_assign).  The host shims call it once per thread with FBE_DEVICE. */
 FBE_API int fbe_set_device(int32_t device);

@@ -266,6 +266,24 @@ void orc_resize_linear_exact_u8(const uint8_t* src, int sw, int sh, int sstep, u
     resize_linear_exact_u8(src, sw, sh, (size_t)sstep, dst, dw, dh, (size_t)dstep);
 }
 
+// KeyPointsFilter::retainBest on a bare response array: order[n] = the permutation std::nth_element + std::partition leave behind,
+// returns the number kept
+int orc_retain_best(const float* response, int n, int n_points, int32_t* order) {
+    std::vector<Kp> k(n);
+    for (int i = 0; i < n; ++i) { k[i] = Kp{0, 0, 0, 0, response[i], 0, i}; }
+    const size_t before = k.size();
+    std::vector<Kp> all = k;
+    if (n_points >= 0 && k.size() > (size_t)n_points && n_points > 0) {
+        std::nth_element(all.begin(), all.begin() + n_points - 1, all.end(), ResponseGreater());
+        const float ambiguous = all[n_points - 1].response;
+        std::vector<Kp>::iterator new_end = std::partition(all.begin() + n_points, all.end(), [ambiguous](const Kp& p) { return p.response >= ambiguous; });
+        for (size_t i = 0; i < before; ++i) order[i] = all[i].class_id;
+        return (int)(new_end - all.begin());
+    }
+    for (size_t i = 0; i < before; ++i) order[i] = (int)i;
+    return n_points == 0 ? 0 : n;
+}
+
 // the blur of one pyramid level as cv::ORB computes it (see gauss7_float_u8), on a stand-alone image with REFLECT_101 borders
 void orc_cvorb_blur(const uint8_t* img, int rows, int cols, int step, uint8_t* dst) {
     Level v;

@@ -544,6 +544,14 @@ def resize_linear_exact(img, dw, dh):
     return out
 
 
+def retain_best(response, n_points):
+    """KeyPointsFilter::retainBest on a response array -> (order [n] after std::nth_element + std::partition, number kept)."""
+    r = np.ascontiguousarray(response, np.float32)
+    order = np.zeros(max(len(r), 1), np.int32)
+    kept = lib().orc_retain_best(_p(r), len(r), int(n_points), _p(order))
+    return order[:len(r)], kept
+
+
 def cvorb_blur(img):
     """The GaussianBlur cv::ORB applies to a pyramid level (float sepFilter2D path with FMA, see oracle/cvorb_oracle.cpp)."""
     img = np.ascontiguousarray(img, np.uint8)
