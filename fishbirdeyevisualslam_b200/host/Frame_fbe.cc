@@ -10,6 +10,7 @@
 // fbe_undistort_keypoints (same K, same mDistCoef, P = K); the k1 == 0 copy stays.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "Frame.h"
@@ -81,6 +82,52 @@ void Frame::GuidenceKeyBirdPts(std::vector<cv::KeyPoint>& preKeysBird) {
         abort();
     }
     mvKeysBird.insert(mvKeysBird.end(), kept.begin(), kept.begin() + nkept);
+}
+
+// The reference's bird feature block of the Frame constructor (src/Frame.cc:336-355) -- cv::ORB::create(2000)->detect with
+// mBirdviewMask, GuidenceKeyBirdPts' nearEdges filter, cv::cornerSubPix(5x5, 40 iterations, 0.001), ->compute -- as ONE
+// device-resident call.  INTEGRATION.md shows the constructor patch: `genEdgesPC();` (it feeds the ICP and used to run inside
+// GuidenceKeyBirdPts) followed by this call.  Keypoints, their order, and descriptors are those of OpenCV 4.13's cv::ORB.
+void FbeBirdFeatures(const cv::Mat& birdGray, const cv::Mat& birdMask, const cv::Mat& contourICP, std::vector<cv::KeyPoint>& keysBird,
+                     cv::Mat& descriptorsBird) {
+    struct Handle {
+        fbe_bird_orb* h;
+        int rows, cols;
+        Handle() : h(NULL), rows(0), cols(0) {}
+        ~Handle() { if (h) fbe_bird_orb_destroy(h); }
+    };
+    static thread_local Handle H;
+    keysBird.clear();
+    descriptorsBird.release();
+    if (birdGray.empty()) return;
+    if (!H.h || H.rows != birdGray.rows || H.cols != birdGray.cols) {
+        if (H.h) fbe_bird_orb_destroy(H.h);
+        H.h = NULL;
+        if (fbe_bird_orb_create(2000, birdGray.rows, birdGray.cols, 1, fbe_host_device(), &H.h) != FBE_OK) {
+            fprintf(stderr, "FbeBirdFeatures (fbe-b200): %s\n", fbe_last_error());
+            abort();      // no CPU fallback
+        }
+        H.rows = birdGray.rows; H.cols = birdGray.cols;
+    }
+    int32_t cap = 0, n = 0;
+    fbe_bird_orb_max_keypoints(H.h, &cap);
+    std::vector<cv::KeyPoint> kps(cap);
+    std::vector<unsigned char> desc((size_t)cap * 32);
+    const size_t istep = birdGray.rows > 1 ? (size_t)(birdGray.ptr(1) - birdGray.ptr(0)) : (size_t)birdGray.cols;
+    const size_t mstep = birdMask.rows > 1 ? (size_t)(birdMask.ptr(1) - birdMask.ptr(0)) : (size_t)birdMask.cols;
+    const size_t cstep = contourICP.rows > 1 ? (size_t)(contourICP.ptr(1) - contourICP.ptr(0)) : (size_t)contourICP.cols;
+    if (fbe_bird_features(H.h, birdGray.ptr(0), istep, 0, birdMask.empty() ? NULL : birdMask.ptr(0), mstep, 0,
+                          contourICP.empty() ? NULL : contourICP.ptr(0), cstep, 0, 1, reinterpret_cast<fbe_keypoint*>(kps.data()), &n,
+                          desc.data(), NULL) != FBE_OK) {
+        fprintf(stderr, "FbeBirdFeatures (fbe-b200): %s\n", fbe_last_error());
+        abort();
+    }
+    kps.resize(n);
+    keysBird.swap(kps);
+    if (n > 0) {
+        descriptorsBird.create(n, 32, CV_8U);
+        for (int i = 0; i < n; ++i) std::memcpy(descriptorsBird.ptr(i), &desc[(size_t)i * 32], 32);
+    }
 }
 
 }  // namespace ORB_SLAM2

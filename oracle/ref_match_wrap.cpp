@@ -175,6 +175,13 @@ bool check_grid(const FrameView& f, int cols, int rows) { return f.gcols == cols
 
 static double g_last_method_us = 0.0;
 
+#ifdef FBE_DROPIN
+namespace ORB_SLAM2 {
+void FbeBirdFeatures(const cv::Mat& birdGray, const cv::Mat& birdMask, const cv::Mat& contourICP, std::vector<cv::KeyPoint>& keysBird,
+                     cv::Mat& descriptorsBird);
+}
+#endif
+
 extern "C" {
 
 // Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:381-411, 548-558) as CSR [ix*rows+iy]
@@ -662,6 +669,21 @@ void refm_undistort_keypoints(const Kp* kps, int n, const float* K, const float*
     for (int i = 0; i < 4; ++i) F.mDistCoef.at<float>(i) = D[i];
     F.UndistortKeyPoints();
     if (n) std::memcpy(out, F.mvKeysUn.data(), (size_t)n * sizeof(Kp));
+}
+
+// The bird feature block of the Frame constructor (src/Frame.cc:336-355) through the drop-in helper of host/Frame_fbe.cc, on
+// cv::Mat inputs like the constructor's members.  Returns the number of bird keypoints (at most cap are written).
+int refm_bird_features(const uint8_t* img, const uint8_t* mask, const uint8_t* contour, int rows, int cols, Kp* out, uint8_t* desc, int cap) {
+    cv::Mat I(rows, cols, CV_8U), M, Cn;
+    for (int y = 0; y < rows; ++y) std::memcpy(I.ptr(y), img + (size_t)y * cols, (size_t)cols);
+    if (mask) { M = cv::Mat(rows, cols, CV_8U); for (int y = 0; y < rows; ++y) std::memcpy(M.ptr(y), mask + (size_t)y * cols, (size_t)cols); }
+    if (contour) { Cn = cv::Mat(rows, cols, CV_8U); for (int y = 0; y < rows; ++y) std::memcpy(Cn.ptr(y), contour + (size_t)y * cols, (size_t)cols); }
+    std::vector<cv::KeyPoint> keys;
+    cv::Mat D;
+    FbeBirdFeatures(I, M, Cn, keys, D);
+    const int n = (int)keys.size();
+    for (int i = 0; i < n && i < cap; ++i) { std::memcpy(out + i, &keys[i], sizeof(Kp)); std::memcpy(desc + (size_t)i * 32, D.ptr(i), 32); }
+    return n;
 }
 #endif
 

@@ -70,3 +70,29 @@ def test_dropin_frame_undistort_keypoints(oracle, dropin):
         for f in ("size", "angle", "response", "octave", "class_id"):
             assert np.array_equal(out[f], kps[f])
 
+
+
+def test_dropin_frame_bird_feature_block(oracle, dropin):
+    """The bird feature block of the Frame constructor (src/Frame.cc:336-355) through host/Frame_fbe.cc's FbeBirdFeatures on
+    cv::Mat inputs: mvKeysBird (order included) and mDescriptorsBird equal the oracle chain cv::ORB detect -> nearEdges ->
+    cornerSubPix -> cv::ORB compute, which is pinned to cv2 4.13."""
+    import ctypes as C
+    import bird_scenes as S
+    from fishbirdeyevisualslam_b200._lib import KP_DTYPE
+    for i, with_mask, with_contour in ((0, False, True), (1, True, True), (2, True, False)):
+        img = S.bird_image(i)
+        mask = S.bird_mask(i) if with_mask else None
+        contour = S.contour_image(i) if with_contour else None
+        det = oracle.cvorb_detect(img, mask)
+        kept = det[oracle.bird_near_edges(contour, np.stack([det["x"], det["y"]], 1)).astype(bool)] if with_contour else det
+        xy, _ = oracle.corner_subpix(img, np.stack([kept["x"], kept["y"]], 1))
+        moved = kept.copy()
+        moved["x"], moved["y"] = xy[:, 0], xy[:, 1]
+        rk, rd = oracle.cvorb_compute(img, moved)
+        cap = 8192
+        out = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        p = lambda a: None if a is None else np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
+        n = dropin.L.refm_bird_features(p(img), p(mask), p(contour), 384, 384, p(out), p(desc), cap)
+        assert n == len(rk) > 100
+        assert out[:n].tobytes() == rk.tobytes() and np.array_equal(desc[:n], rd), i
