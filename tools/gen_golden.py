@@ -62,7 +62,8 @@ for i, (h, w, nf, nl, seed) in enumerate(small):
     e[f"small{i}_img_crc"] = np.array(synth.crc(img), np.uint32)
     e[f"small{i}_kps"] = k.view(np.uint8).reshape(-1, 28)
     e[f"small{i}_desc"] = dsc
-big = [(480, 640, 1000, 8, 1), (720, 1280, 2000, 8, 2), (384, 384, 1000, 8, 3), (400, 950, 2000, 8, 4)]
+big = [(480, 640, 1000, 8, 1), (720, 1280, 2000, 8, 2), (384, 384, 1000, 8, 3), (400, 950, 2000, 8, 4),
+       (2160, 3840, 8000, 12, 5)]          # BASELINE config C5 (stress): verbatim-reference fixture
 rows = []
 for (h, w, nf, nl, seed) in big:
     img = synth.frame(h, w, seed)
