@@ -229,14 +229,17 @@ int fbe_debug_octree(const int32_t* xys, int32_t n, int32_t min_x, int32_t max_x
         if (xys[3 * i] < 0 || xys[3 * i] + 16 > kMaxDim || xys[3 * i + 1] < 0 || xys[3 * i + 1] + 16 > kMaxDim) return FBE_E_INVALID;
         keys[i] = pack_key(xys[3 * i] + 16, xys[3 * i + 1] + 16, xys[3 * i + 2]);
     }
-    uint32_t *d_keys = nullptr, *d_knode = nullptr, *d_sel = nullptr;
-    uint8_t* d_scr = nullptr;
-    int* d_n = nullptr;
-    FBE_CUDA(cudaMalloc(&d_keys, keys.size() * 4));
-    FBE_CUDA(cudaMalloc(&d_knode, keys.size() * 4));
-    FBE_CUDA(cudaMalloc(&d_sel, (size_t)ncap * 4));
-    FBE_CUDA(cudaMalloc(&d_scr, octree_debug_scratch_bytes(ncap, nini, nfeat)));
-    FBE_CUDA(cudaMalloc(&d_n, 4));
+    // per-thread arena (nothing to leak on an error return, no cudaMalloc / cudaFree in the steady state)
+    static thread_local Arena arena;
+    int dev = 0;
+    FBE_CUDA(cudaGetDevice(&dev));
+    const size_t scr = octree_debug_scratch_bytes(ncap, nini, nfeat);
+    FBE_CUDA(arena.reserve(2 * pad256(keys.size() * 4) + pad256((size_t)ncap * 4) + pad256(scr) + pad256(4), dev));
+    uint32_t* d_keys = arena.take<uint32_t>(keys.size());
+    uint32_t* d_knode = arena.take<uint32_t>(keys.size());
+    uint32_t* d_sel = arena.take<uint32_t>((size_t)ncap);
+    uint8_t* d_scr = arena.take<uint8_t>(scr);
+    int* d_n = arena.take<int>(1);
     FBE_CUDA(cudaMemcpy(d_keys, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice));
     int rc = launch_octree_debug(d_keys, d_knode, n, nini, hx, H, nfeat, ncap, d_scr, d_sel, d_n, 0);
     int hn = 0;
@@ -246,7 +249,6 @@ int fbe_debug_octree(const int32_t* xys, int32_t n, int32_t min_x, int32_t max_x
         if (ce == cudaSuccess && hn > 0) ce = cudaMemcpy(hsel.data(), d_sel, (size_t)hn * 4, cudaMemcpyDeviceToHost);
         if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); rc = FBE_E_CUDA; }
     }
-    cudaFree(d_keys); cudaFree(d_knode); cudaFree(d_sel); cudaFree(d_scr); cudaFree(d_n);
     if (rc != FBE_OK) return rc;
     if (hn < 0) { set_error("octree workspace overflow"); return FBE_E_CAPACITY; }
     *n_sel = hn;

@@ -80,7 +80,8 @@ int ExtractorCore::set_fisheye(const float K[4], const float D[4]) {
 }
 
 int ExtractorCore::set_grid(float min_x, float min_y, float inv_w, float inv_h, int gcols, int grows) {
-    if (gcols * grows > kMaxGridCells * 4) { set_error("grid too large"); return FBE_E_UNSUPPORTED; }
+    // the same limit as the grid kernel's shared-memory histogram (launch_grid_build): a grid accepted here always runs
+    if (gcols < 0 || grows < 0 || (size_t)(gcols * grows + 1) * sizeof(int) > 48 * 1024) { set_error("grid too large"); return FBE_E_UNSUPPORTED; }
     const bool realloc_grid = have_ws && gcols * grows != g_cols * g_rows;
     g_min_x = min_x; g_min_y = min_y; g_inv_w = inv_w; g_inv_h = inv_h; g_cols = gcols; g_rows = grows;
     if (have_ws) {
@@ -89,8 +90,10 @@ int ExtractorCore::set_grid(float min_x, float min_y, float inv_w, float inv_h, 
         FBE_CUDA(cudaMemcpyAsync(dplan, &hplan, sizeof(Plan), cudaMemcpyHostToDevice, stream));
         FBE_CUDA(cudaStreamSynchronize(stream));
         if (realloc_grid) {
+            FBE_CUDA(cudaDeviceSynchronize());            // every stream that may still read the old CSR (matching, copy-out) has drained
             cudaFree(ws.grid_start);
-            FBE_CUDA(cudaMalloc(&ws.grid_start, (size_t)cfg.max_batch * out_sets * (gcols * grows + 1) * sizeof(int)));
+            ws.grid_start = nullptr;                      // never left dangling if the allocation below fails
+            FBE_CUDA(cudaMalloc(&ws.grid_start, (size_t)cfg.max_batch * out_sets * (std::max(gcols * grows, kMaxGridCells) + 1) * sizeof(int)));
         }
     }
     return FBE_OK;
@@ -98,6 +101,12 @@ int ExtractorCore::set_grid(float min_x, float min_y, float inv_w, float inv_h, 
 
 int ExtractorCore::ensure_plan(int rows, int cols) {
     if (have_ws && rows == plan_rows && cols == plan_cols) return FBE_OK;
+    const int rc = build_workspace(rows, cols);
+    if (rc != FBE_OK) free_ws();                          // a failed allocation leaves nothing behind (free_ws accepts null members)
+    return rc;
+}
+
+int ExtractorCore::build_workspace(int rows, int cols) {
     FBE_CUDA(cudaSetDevice(cfg.device));
     if (have_ws) { FBE_CUDA(cudaStreamSynchronize(stream)); FBE_CUDA(cudaStreamSynchronize(stream2)); free_ws(); }
     std::vector<ResizeTab> tabs;

@@ -213,6 +213,7 @@ struct ExtractorCore {
     int init(const fbe_extractor_cfg& c);
     void destroy();
     int ensure_plan(int rows, int cols);
+    int build_workspace(int rows, int cols);   // the allocating part of ensure_plan
     int set_grid(float min_x, float min_y, float inv_w, float inv_h, int gcols, int grows);
     // images already on the device: [nimg][rows][pitch]; results go to workspace slots slot0 .. slot0+nimg-1
     // `out_set` selects one of `out_sets` copies of the OUTPUT arrays (keypoints, descriptors, counts, grid): the batch
