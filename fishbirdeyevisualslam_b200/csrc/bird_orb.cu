@@ -58,6 +58,7 @@ struct BorbLevel {
     int band_cap;               // survivors per band
     int cand_cap, cand_off;     // candidates of the level
     int tabx_off, taby_off;     // resize taps (levels >= 1)
+    int blur_tiles;             // 64 x 32 tiles of the blur kernel
 };
 
 struct BorbPlan {
@@ -86,30 +87,34 @@ __global__ void k_borb_level0(const BorbPlan* __restrict__ plan, const uint8_t* 
             masks[(size_t)b * mstride + (size_t)(py - kBorbBorder) * mstep + (px - kBorbBorder)] ? 255 : 0;
 }
 
-// level l (padded, frame = reflection of the level itself) from the ROI of level l-1; MASK: unpadded, thresholded (> 254 kept)
-template <bool MASK>
-__global__ void k_borb_resize(const BorbPlan* __restrict__ plan, const BorbTab* __restrict__ tabs, int l, uint8_t* __restrict__ slab) {
-    const BorbLevel& g = plan->lv[l];
-    const BorbLevel& s = plan->lv[l - 1];
-    const int b = blockIdx.z, px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
-    const int pw = MASK ? g.w : g.w + 2 * kBorbBorder;
-    if (px >= pw) return;
-    const int x = MASK ? px : borb_reflect101(px - kBorbBorder, g.w), y = MASK ? py : borb_reflect101(py - kBorbBorder, g.h);
-    const BorbTab tx = tabs[g.tabx_off + x], ty = tabs[g.taby_off + y];
-    const uint8_t* S;
-    int sp;
-    if (MASK) { S = slab + (size_t)b * plan->mask_bytes + s.mask_off; sp = s.w; }
-    else { S = slab + (size_t)b * plan->pyr_bytes + s.img_off + (size_t)kBorbBorder * s.pitch + kBorbBorder; sp = s.pitch; }
+// level l from the ROI of level l-1: the image padded (frame = reflection of the level itself) and, when there is a mask, the mask
+// level unpadded and re-thresholded (> 254 kept), in the same launch (blockIdx.y < ph: image rows, above: mask rows)
+__device__ __forceinline__ unsigned borb_exact_tap(const uint8_t* S, int sp, const BorbTab tx, const BorbTab ty) {
     const uint8_t* r0 = S + (size_t)ty.o0 * sp;
     const uint8_t* r1 = S + (size_t)ty.o1 * sp;
     const unsigned h0 = (unsigned)tx.c0 * r0[tx.o0] + (unsigned)tx.c1 * r0[tx.o1];
     const unsigned h1 = (unsigned)tx.c0 * r1[tx.o0] + (unsigned)tx.c1 * r1[tx.o1];
-    unsigned v = ((unsigned)ty.c0 * h0 + (unsigned)ty.c1 * h1 + 32768u) >> 16;
-    if (MASK) {
-        if (v <= 254u) v = 0;
-        slab[(size_t)b * plan->mask_bytes + g.mask_off + (size_t)py * g.w + px] = (uint8_t)v;
+    return ((unsigned)ty.c0 * h0 + (unsigned)ty.c1 * h1 + 32768u) >> 16;
+}
+
+__global__ void k_borb_resize(const BorbPlan* __restrict__ plan, const BorbTab* __restrict__ tabs, int l, uint8_t* __restrict__ pyr,
+                              uint8_t* __restrict__ mpyr) {
+    const BorbLevel& g = plan->lv[l];
+    const BorbLevel& s = plan->lv[l - 1];
+    const int b = blockIdx.z, px = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int)blockIdx.y < g.ph) {
+        const int py = blockIdx.y;
+        if (px >= g.w + 2 * kBorbBorder) return;
+        const int x = borb_reflect101(px - kBorbBorder, g.w), y = borb_reflect101(py - kBorbBorder, g.h);
+        const uint8_t* S = pyr + (size_t)b * plan->pyr_bytes + s.img_off + (size_t)kBorbBorder * s.pitch + kBorbBorder;
+        pyr[(size_t)b * plan->pyr_bytes + g.img_off + (size_t)py * g.pitch + px] =
+            (uint8_t)borb_exact_tap(S, s.pitch, tabs[g.tabx_off + x], tabs[g.taby_off + y]);
     } else {
-        slab[(size_t)b * plan->pyr_bytes + g.img_off + (size_t)py * g.pitch + px] = (uint8_t)v;
+        const int py = blockIdx.y - g.ph;
+        if (px >= g.w) return;
+        const uint8_t* S = mpyr + (size_t)b * plan->mask_bytes + s.mask_off;
+        const unsigned v = borb_exact_tap(S, s.w, tabs[g.tabx_off + px], tabs[g.taby_off + py]);
+        mpyr[(size_t)b * plan->mask_bytes + g.mask_off + (size_t)py * g.w + px] = (uint8_t)(v > 254u ? v : 0u);
     }
 }
 
@@ -222,10 +227,17 @@ __global__ void __launch_bounds__(kBorbThreads) k_borb_gather(const BorbPlan* __
     const BorbLevel& g = plan->lv[l];
     __shared__ int off[512];
     const int* bc = band_count + (size_t)b * plan->bands_total + g.band_off;
-    if (tid == 0) {
-        int o = 0;
-        for (int i = 0; i < g.nbands; ++i) { off[i] = o; o += bc[i]; }
-        cand_n[b * kBorbLevels + l] = o;
+    if (tid < 32) {                                              // exclusive prefix of the band counts, 32 bands per step
+        int carry = 0;
+        for (int c0 = 0; c0 < g.nbands; c0 += 32) {
+            const int v = c0 + tid < g.nbands ? bc[c0 + tid] : 0;
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
+            if (c0 + tid < g.nbands) off[c0 + tid] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (tid == 0) cand_n[b * kBorbLevels + l] = carry;
     }
     __syncthreads();
     for (int i = 0; i < g.nbands; ++i) {
@@ -413,15 +425,17 @@ __global__ void k_borb_harris(const BorbPlan* __restrict__ plan, const uint8_t* 
     resp2[base + i] = r;
 }
 
-// second retainBest result -> ICAngles -> the keypoint records of detect(), levels concatenated
-__global__ void k_borb_finish(const BorbPlan* __restrict__ plan, const uint8_t* __restrict__ pyr, const uint32_t* __restrict__ cand_xy,
-                              const int* __restrict__ idx1, const int* __restrict__ idx2, const float* __restrict__ resp2,
-                              const int* __restrict__ n2, int cap, fbe_keypoint* __restrict__ out, int* __restrict__ out_n, int* __restrict__ err) {
-    const int l = blockIdx.y, b = blockIdx.z, j = blockIdx.x * blockDim.x + threadIdx.x;
+// second retainBest result -> ICAngles -> the keypoint records of detect(), levels concatenated.  One warp per keypoint: lane = row
+// v = lane - 15 of the radius-15 disc (integer sums, so the order of addition is free).
+__global__ void __launch_bounds__(128) k_borb_finish(const BorbPlan* __restrict__ plan, const uint8_t* __restrict__ pyr, const uint32_t* __restrict__ cand_xy,
+                                                     const int* __restrict__ idx1, const int* __restrict__ idx2, const float* __restrict__ resp2,
+                                                     const int* __restrict__ n2, int cap, fbe_keypoint* __restrict__ out, int* __restrict__ out_n,
+                                                     int* __restrict__ err) {
+    const int l = blockIdx.y, b = blockIdx.z, j = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int* cnt = n2 + b * kBorbLevels;
     int off = 0, total = 0;
     for (int i = 0; i < kBorbLevels; ++i) { if (i < l) off += cnt[i]; total += cnt[i]; }
-    if (l == 0 && j == 0) { out_n[b] = min(total, cap); if (total > cap) atomicExch(err, 2); }
+    if (l == 0 && blockIdx.x == 0 && threadIdx.x == 0) { out_n[b] = min(total, cap); if (total > cap) atomicExch(err, 2); }
     if (j >= cnt[l] || off + j >= cap) return;
     const BorbLevel& g = plan->lv[l];
     const size_t base = (size_t)b * plan->cand_total + g.cand_off;
@@ -430,24 +444,24 @@ __global__ void k_borb_finish(const BorbPlan* __restrict__ plan, const uint8_t* 
     const int x0 = (int)(xy & 0xFFFFu), y0 = (int)(xy >> 16), step = g.pitch;
     const uint8_t* c = pyr + (size_t)b * plan->pyr_bytes + g.img_off + (size_t)(y0 + kBorbBorder) * step + (x0 + kBorbBorder);
     int m01 = 0, m10 = 0;
-    for (int u = -15; u <= 15; ++u) m10 += u * c[u];
-    for (int v = 1; v <= 15; ++v) {
-        int vs = 0;
-        const int d = c_borb_umax[v];
-        for (int u = -d; u <= d; ++u) {
-            const int vp = c[u + v * step], vm = c[u - v * step];
-            vs += vp - vm;
-            m10 += u * (vp + vm);
-        }
-        m01 += v * vs;
+    if (lane < 31) {
+        const int v = lane - 15, d = c_borb_umax[v < 0 ? -v : v];
+        const uint8_t* row = c + v * step;
+        int rs = 0;
+        for (int u = -d; u <= d; ++u) { const int q = row[u]; rs += q; m10 += u * q; }
+        m01 = v * rs;
     }
-    fbe_keypoint k;
-    k.x = __fmul_rn((float)x0, g.scale); k.y = __fmul_rn((float)y0, g.scale);
-    k.size = __fmul_rn(31.f, g.scale);
-    k.angle = fast_atan2_deg((float)m01, (float)m10);
-    k.response = resp2[base + i1];
-    k.octave = l; k.class_id = -1;
-    out[(size_t)b * cap + off + j] = k;
+    m01 = __reduce_add_sync(0xffffffffu, m01);
+    m10 = __reduce_add_sync(0xffffffffu, m10);
+    if (lane == 0) {
+        fbe_keypoint k;
+        k.x = __fmul_rn((float)x0, g.scale); k.y = __fmul_rn((float)y0, g.scale);
+        k.size = __fmul_rn(31.f, g.scale);
+        k.angle = fast_atan2_deg((float)m01, (float)m10);
+        k.response = resp2[base + i1];
+        k.octave = l; k.class_id = -1;
+        out[(size_t)b * cap + off + j] = k;
+    }
 }
 
 // ---- compute() -------------------------------------------------------------------------------------------------------------------
@@ -496,11 +510,14 @@ __global__ void __launch_bounds__(1024) k_borb_prefilter(const BorbPlan* __restr
 }
 
 // float sepFilter2D Gaussian of a level ROI (see file header): tile 64 x 32, taps as float32 bit patterns of getGaussianKernel(7, 2, CV_32F)
-__global__ void __launch_bounds__(256) k_borb_blur(const BorbPlan* __restrict__ plan, int l, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
+__global__ void __launch_bounds__(256) k_borb_blur(const BorbPlan* __restrict__ plan, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
     constexpr int TW = 64, TH = 32;
     __shared__ float hs[(TH + 6) * TW];
+    int l = 0, t = blockIdx.x;                                   // tile index over all levels -> (level, tile)
+    while (l < kBorbLevels - 1 && t >= plan->lv[l].blur_tiles) { t -= plan->lv[l].blur_tiles; ++l; }
     const BorbLevel& g = plan->lv[l];
-    const int b = blockIdx.z, x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, tid = threadIdx.x;
+    const int ntx = (g.w + TW - 1) / TW;
+    const int b = blockIdx.y, x0 = (t % ntx) * TW, y0 = (t / ntx) * TH, tid = threadIdx.x;
     const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu), k2 = __uint_as_float(0x3e434a39u), k3 = __uint_as_float(0x3e5d4ae0u);
     const uint8_t* img = pyr + (size_t)b * plan->pyr_bytes + g.img_off + (size_t)kBorbBorder * g.pitch + kBorbBorder;
     for (int i = tid; i < (TH + 6) * TW; i += 256) {
@@ -644,6 +661,7 @@ int build_borb_plan(int nfeatures, int rows, int cols, BorbPlan& p, std::vector<
         g.cand_cap = g.nbands ? ((g.kw + 1) / 2) * ((g.kh + 1) / 2) + 8 : 8;  // ... nor vertical ones
         g.cand_off = cand_off; cand_off += g.cand_cap;
         for (int i = 0; i < g.nbands; ++i) band_level.push_back((short)l);
+        g.blur_tiles = ((g.w + 63) / 64) * ((g.h + 31) / 32);
         if (l > 0) {
             g.tabx_off = (int)tabs.size(); exact_tab(p.lv[l - 1].w, g.w, tabs);
             g.taby_off = (int)tabs.size(); exact_tab(p.lv[l - 1].h, g.h, tabs);
@@ -683,12 +701,8 @@ int run_pyramid(fbe_bird_orb* h, int B, bool has_mask) {
     }
     for (int l = 1; l < kBorbLevels; ++l) {
         const BorbLevel& g = p.lv[l];
-        k_borb_resize<false><<<dim3((g.w + 2 * kBorbBorder + 127) / 128, g.ph, B), 128, 0, st>>>(h->dplan, h->d_tabs, l, h->pyr);
+        k_borb_resize<<<dim3((g.w + 2 * kBorbBorder + 127) / 128, g.ph + (has_mask ? g.h : 0), B), 128, 0, st>>>(h->dplan, h->d_tabs, l, h->pyr, h->mpyr);
         count_launch();
-        if (has_mask) {
-            k_borb_resize<true><<<dim3((g.w + 127) / 128, g.h, B), 128, 0, st>>>(h->dplan, h->d_tabs, l, h->mpyr);
-            count_launch();
-        }
     }
     FBE_CUDA(cudaGetLastError());
     return FBE_OK;
@@ -704,9 +718,10 @@ int run_detect(fbe_bird_orb* h, int B, bool has_mask) {
     k_borb_retain<<<dim3(kBorbLevels, B), kBorbThreads, 0, st>>>(h->dplan, 0, h->cand_resp, h->cand_n, h->key, h->idx1, h->lpos, h->rpos, h->n1, h->err);
     int max_cap = 0;
     for (int l = 0; l < kBorbLevels; ++l) max_cap = std::max(max_cap, p.lv[l].cand_cap);
+    const int max_kp = std::min(max_cap, h->kp_cap);                  // a level can not contribute more than the output holds
     k_borb_harris<<<dim3((max_cap + 127) / 128, kBorbLevels, B), 128, 0, st>>>(h->dplan, h->pyr, h->cand_xy, h->idx1, h->n1, h->resp2);
     k_borb_retain<<<dim3(kBorbLevels, B), kBorbThreads, 0, st>>>(h->dplan, 1, h->resp2, h->n1, h->key, h->idx2, h->lpos, h->rpos, h->n2, h->err);
-    k_borb_finish<<<dim3((max_cap + 127) / 128, kBorbLevels, B), 128, 0, st>>>(h->dplan, h->pyr, h->cand_xy, h->idx1, h->idx2, h->resp2, h->n2, h->kp_cap,
+    k_borb_finish<<<dim3((max_kp + 3) / 4, kBorbLevels, B), 128, 0, st>>>(h->dplan, h->pyr, h->cand_xy, h->idx1, h->idx2, h->resp2, h->n2, h->kp_cap,
                                                                             h->kps_a, h->n_a, h->err);
     count_launch(6);
     FBE_CUDA(cudaGetLastError());
@@ -719,11 +734,10 @@ int run_compute(fbe_bird_orb* h, int B, const fbe_keypoint* d_in, const int* d_n
     cudaStream_t st = h->stream;
     k_borb_prefilter<<<B, 1024, 0, st>>>(h->dplan, d_in, d_nin, h->kp_cap, h->kps_b, h->n_b, h->err);
     count_launch();
-    for (int l = 0; l < kBorbLevels; ++l) {
-        const BorbLevel& g = p.lv[l];
-        k_borb_blur<<<dim3((g.w + 63) / 64, (g.h + 31) / 32, B), 256, 0, st>>>(h->dplan, l, h->pyr, h->blur);
-        count_launch();
-    }
+    int tiles = 0;
+    for (int l = 0; l < kBorbLevels; ++l) tiles += p.lv[l].blur_tiles;
+    k_borb_blur<<<dim3(tiles, B), 256, 0, st>>>(h->dplan, h->pyr, h->blur);
+    count_launch();
     k_borb_describe<<<dim3((h->kp_cap + 3) / 4, B), 128, 0, st>>>(h->dplan, h->pyr, h->blur, h->kps_b, h->n_b, h->kp_cap, h->desc);
     count_launch();
     FBE_CUDA(cudaGetLastError());
@@ -738,6 +752,21 @@ int check_err(fbe_bird_orb* h) {
     if (e == 1) { set_error("retainBest: introselect reached its depth limit (heap-select fallback of std::nth_element is not replayed)"); return FBE_E_UNSUPPORTED; }
     if (e == 2) { set_error("more keypoints than the output capacity (ties of the n-th best response are all kept)"); return FBE_E_CAPACITY; }
     if (e == 3) { set_error("keypoint octave outside 0 .. 7"); return FBE_E_INVALID; }
+    return FBE_OK;
+}
+
+// results to the host: the counts (and the error word) first, then only the used front of every fixed-stride list
+int download(fbe_bird_orb* h, int B, const int* d_n, const fbe_keypoint* d_kps, const uint8_t* d_desc, int32_t* n, fbe_keypoint* kps, uint8_t* desc) {
+    FBE_CUDA(cudaMemcpyAsync(n, d_n, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    FBE_TRY(check_err(h));                                       // synchronises the stream
+    int nmax = 0;
+    for (int b = 0; b < B; ++b) nmax = std::max(nmax, (int)n[b]);
+    if (nmax == 0) return FBE_OK;
+    const size_t cap = (size_t)h->kp_cap;
+    FBE_CUDA(cudaMemcpy2DAsync(kps, cap * sizeof(fbe_keypoint), d_kps, cap * sizeof(fbe_keypoint), (size_t)nmax * sizeof(fbe_keypoint), (size_t)B,
+                               cudaMemcpyDeviceToHost, h->stream));
+    if (desc) FBE_CUDA(cudaMemcpy2DAsync(desc, cap * 32, d_desc, cap * 32, (size_t)nmax * 32, (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+    FBE_CUDA(cudaStreamSynchronize(h->stream));
     return FBE_OK;
 }
 
@@ -841,9 +870,7 @@ int fbe_bird_orb_detect(fbe_bird_orb* h, const uint8_t* imgs, size_t step, size_
     if (masks) FBE_TRY(upload_images(h, h->d_mask, masks, mask_step, mask_stride, nframes));
     FBE_TRY(run_pyramid(h, nframes, masks != nullptr));
     FBE_TRY(run_detect(h, nframes, masks != nullptr));
-    FBE_CUDA(cudaMemcpyAsync(n, h->n_a, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    FBE_CUDA(cudaMemcpyAsync(kps, h->kps_a, (size_t)nframes * h->kp_cap * sizeof(fbe_keypoint), cudaMemcpyDeviceToHost, h->stream));
-    return check_err(h);
+    return download(h, nframes, h->n_a, h->kps_a, nullptr, n, kps, nullptr);
 }
 
 int fbe_bird_orb_compute(fbe_bird_orb* h, const uint8_t* imgs, size_t step, size_t stride, int32_t nframes, fbe_keypoint* kps, int32_t* n,
@@ -856,10 +883,7 @@ int fbe_bird_orb_compute(fbe_bird_orb* h, const uint8_t* imgs, size_t step, size
     FBE_CUDA(cudaMemcpyAsync(h->kps_a, kps, (size_t)nframes * h->kp_cap * sizeof(fbe_keypoint), cudaMemcpyHostToDevice, h->stream));
     FBE_CUDA(cudaMemcpyAsync(h->n_a, n, (size_t)nframes * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     FBE_TRY(run_compute(h, nframes, h->kps_a, h->n_a));
-    FBE_CUDA(cudaMemcpyAsync(n, h->n_b, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    FBE_CUDA(cudaMemcpyAsync(kps, h->kps_b, (size_t)nframes * h->kp_cap * sizeof(fbe_keypoint), cudaMemcpyDeviceToHost, h->stream));
-    FBE_CUDA(cudaMemcpyAsync(desc, h->desc, (size_t)nframes * h->kp_cap * 32, cudaMemcpyDeviceToHost, h->stream));
-    return check_err(h);
+    return download(h, nframes, h->n_b, h->kps_b, h->desc, n, kps, desc);
 }
 
 int fbe_bird_features(fbe_bird_orb* h, const uint8_t* imgs, size_t step, size_t stride, const uint8_t* masks, size_t mask_step, size_t mask_stride,
@@ -884,10 +908,7 @@ int fbe_bird_features(fbe_bird_orb* h, const uint8_t* imgs, size_t step, size_t 
         d_res = h->kps_a;
     }
     FBE_TRY(run_compute(h, nframes, d_res, d_res_n));                     // extractorBird->compute(mBirdviewImg, mvKeysBird, mDescriptorsBird)
-    FBE_CUDA(cudaMemcpyAsync(n, h->n_b, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    FBE_CUDA(cudaMemcpyAsync(kps, h->kps_b, (size_t)nframes * h->kp_cap * sizeof(fbe_keypoint), cudaMemcpyDeviceToHost, h->stream));
-    FBE_CUDA(cudaMemcpyAsync(desc, h->desc, (size_t)nframes * h->kp_cap * 32, cudaMemcpyDeviceToHost, h->stream));
-    return check_err(h);
+    return download(h, nframes, h->n_b, h->kps_b, h->desc, n, kps, desc);
 }
 
 }  // extern "C"

@@ -21,6 +21,7 @@ __constant__ int8_t c_pattern[256 * 4] = {
 };
 
 constexpr int kDescWarps = 8, kDescPerWarp = 4, kDescPerCta = kDescWarps * kDescPerWarp;
+constexpr int kCoefRows = 37;         // 11 passes x 3 rows + the 5 idle lanes' reach, rows >= 31 hold zeros
 constexpr int kPatchR = 18, kPatchRows = 2 * kPatchR + 1, kPatchWords = 11;      // 37 rows x 44 bytes
 
 __global__ void __launch_bounds__(kDescWarps * 32, 8) k_describe(const Plan* __restrict__ plan, Workspace ws) {
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(kDescWarps * 32, 8) k_describe(const Plan* __r
     __shared__ uint32_t s_key[kDescPerCta];
     __shared__ int s_lvl[kDescPerCta];
     __shared__ float s_angle[kDescPerCta], s_cos[kDescPerCta], s_sin[kDescPerCta];
+    __shared__ unsigned s_coef[2 * kCoefRows * 9];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int b = blockIdx.y;
@@ -45,6 +47,28 @@ __global__ void __launch_bounds__(kDescWarps * 32, 8) k_describe(const Plan* __r
     }
 
     // ---- A: IC_Angle on the unblurred level ---------------------------------------------------------------------
+    // A disc row is 31 bytes = 9 aligned words; lanes 0..26 hold (row group 0..2, word 0..8), so one coalesced load fetches three
+    // rows and 11 passes cover the 31 rows.  Neighbouring lanes exchange words (SHFL) to realign them to the window u = -15 .. 16
+    // (funnel shift), and the row sums are integer dot products (IDP.4A) with coefficient words from shared memory: sum(I) with
+    // the disc mask, sum((u + 15) * I) with the masked weights; m10 = sum((u + 15) I) - 15 sum(I), m01 = sum(v * rowsum) -- exact ints.
+    {
+        // s_coef[r * 9 + i]: mask word i of row r; s_coef[kCoefRows * 9 + r * 9 + i]: weight word (rows >= 31 and word 8 are zero)
+        for (int k = tid; k < 2 * kCoefRows * 9; k += kDescWarps * 32) {
+            const int kk = k % (kCoefRows * 9), r = kk / 9, i = kk - 9 * r, av = r < 15 ? 15 - r : r - 15;
+            unsigned wv = 0;
+            if (r < 31 && i < 8) {
+                const int d = kUmaxDev(av);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int u = -15 + 4 * i + j;
+                    if (u >= -d && u <= d) wv |= (k < kCoefRows * 9 ? 1u : (unsigned)(u + 15)) << (8 * j);
+                }
+            }
+            s_coef[k] = wv;
+        }
+    }
+    __syncthreads();
+    const int grp = lane / 9, wi = lane - 9 * grp;
 #pragma unroll 1
     for (int k = 0; k < kDescPerWarp; ++k) {
         const int slot = wid * kDescPerWarp + k, gidx = g0 + slot;
@@ -53,27 +77,24 @@ __global__ void __launch_bounds__(kDescWarps * 32, 8) k_describe(const Plan* __r
         while (gidx >= off + level_n[l]) { off += level_n[l]; ++l; }
         const LevelGeom& g = plan->lv[l];
         const uint32_t key = ws.sel[(size_t)b * plan->kp_cap_total + g.kp_base + (gidx - off)];
-        const int kx = key_x(key), ky = key_y(key), pitch = g.pitch;
-        const uint8_t* c = ws.pyr + (size_t)b * plan->pyr_bytes + g.img_off + (size_t)(ky + kEdge) * pitch + (kx + kEdge);
-        const int u = lane - 15, au = u < 0 ? -u : u;
-        int m10 = 0, m01 = 0;
-        if (lane < 31) {
-            int colsum = 0;
-            const uint8_t* p = c + u - 15 * pitch;                 // walks down the column; one 64-bit add per row
-#define FBE_ROW(V)                                   \
-    if (au <= UmaxOf<V>::value) {                    \
-        const int q = *p;                            \
-        colsum += q;                                 \
-        m01 += (V) * q;                              \
-    }                                                \
-    p += pitch;
-            FBE_ROW(-15) FBE_ROW(-14) FBE_ROW(-13) FBE_ROW(-12) FBE_ROW(-11) FBE_ROW(-10) FBE_ROW(-9) FBE_ROW(-8)
-            FBE_ROW(-7) FBE_ROW(-6) FBE_ROW(-5) FBE_ROW(-4) FBE_ROW(-3) FBE_ROW(-2) FBE_ROW(-1) FBE_ROW(0)
-            FBE_ROW(1) FBE_ROW(2) FBE_ROW(3) FBE_ROW(4) FBE_ROW(5) FBE_ROW(6) FBE_ROW(7) FBE_ROW(8)
-            FBE_ROW(9) FBE_ROW(10) FBE_ROW(11) FBE_ROW(12) FBE_ROW(13) FBE_ROW(14) FBE_ROW(15)
-#undef FBE_ROW
-            m10 = u * colsum;
+        const int kx = key_x(key), ky = key_y(key), pw = g.pitch >> 2;              // pitch is a multiple of 16: every row shares the alignment
+        const size_t byte0 = (size_t)b * plan->pyr_bytes + g.img_off + (size_t)(ky + kEdge - 15) * g.pitch + (kx + kEdge - 15);     // (u, v) = (-15, -15)
+        const int sh = (int)(byte0 & 3) * 8;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(ws.pyr + (byte0 & ~(size_t)3)) + wi + grp * pw;
+        unsigned RS = 0, US = 0;
+        int T = 0;
+#pragma unroll
+        for (int p = 0; p < 11; ++p) {
+            const int r = 3 * p + grp;
+            const uint32_t x = (lane < 27 && r < 31) ? __ldg(w + 3 * p * pw) : 0u;
+            const uint32_t xn = __shfl_down_sync(0xffffffffu, x, 1);
+            const unsigned q = __funnelshift_r(x, xn, sh);
+            const unsigned a = __dp4a(q, s_coef[27 * p + lane], 0u);             // lanes >= 27 read zero rows of the table
+            RS += a;
+            T += (r - 15) * (int)a;
+            US = __dp4a(q, s_coef[kCoefRows * 9 + 27 * p + lane], US);
         }
+        int m10 = (int)US - 15 * (int)RS, m01 = T;
         m10 = __reduce_add_sync(0xffffffffu, m10);
         m01 = __reduce_add_sync(0xffffffffu, m01);
         if (lane == 0) {
@@ -131,10 +152,12 @@ __global__ void __launch_bounds__(kDescWarps * 32, 8) k_describe(const Plan* __r
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float4 p = s_pat[j * 32 + lane];
-            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(p.x, bb), __fmul_rn(p.y, a)));
-            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(p.x, a), __fmul_rn(p.y, bb)));
-            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(p.z, bb), __fmul_rn(p.w, a)));
-            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(p.z, a), __fmul_rn(p.w, bb)));
+            // cvRound of a value below 2^22 in magnitude: adding 1.5 * 2^23 rounds to the nearest integer, ties to even, exactly
+            // like cvtss2si / F2I.RN, and leaves the integer in the low mantissa bits (FADD + IADD instead of the quarter-rate F2I)
+            const int r0 = cv_round_small(__fadd_rn(__fmul_rn(p.x, bb), __fmul_rn(p.y, a)));
+            const int c0 = cv_round_small(__fsub_rn(__fmul_rn(p.x, a), __fmul_rn(p.y, bb)));
+            const int r1 = cv_round_small(__fadd_rn(__fmul_rn(p.z, bb), __fmul_rn(p.w, a)));
+            const int c1 = cv_round_small(__fsub_rn(__fmul_rn(p.z, a), __fmul_rn(p.w, bb)));
             const int t0 = pc[r0 * (kPatchWords * 4) + c0], t1 = pc[r1 * (kPatchWords * 4) + c1];
             val |= (unsigned)(t0 < t1) << j;
         }

@@ -26,8 +26,15 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
+// cvRound(x) for |x| < 2^22 without the conversion pipe: (x + 1.5 * 2^23) has the rounded integer in its low mantissa bits
+__device__ __forceinline__ int cv_round_small(float x) { return __float_as_int(__fadd_rn(x, 12582912.f)) - 0x4B400000; }
+
 // row half-widths of the radius-15 disc (umax, src/ORBextractor.cc:452-469; HALF_PATCH_SIZE is a compile-time constant)
 constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+// the same table for a run-time row index (a switch the compiler turns into a select chain / constant lookup)
+__device__ __forceinline__ int kUmaxDev(int av) {
+    return (int)((0x3689ABCDDEEEFFFFull >> (4 * av)) & 15ull);      // kUmax packed 4 bits per row, low nibble = row 0
+}
 template <int V> struct UmaxOf { static constexpr int value = kUmax[V < 0 ? -V : V]; };
 
 }  // namespace fbe

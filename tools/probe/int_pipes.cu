@@ -3,6 +3,7 @@
 // whether a pair of instructions shares a pipe (mix rate == single rate) or not (mix rate ~ 2x).
 // Prints results per clock per SM (clock taken from the device's current SM clock).
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <cstdio>
 
 template <int OP>
@@ -26,6 +27,12 @@ __global__ void k(unsigned* out, int iters, unsigned seed) {
             if (OP == 9) { if (j & 1) s[j] = __dp4a(a[j], c, s[j]); else s[j] = s[j] * c + a[j]; }         // IDP4A + IMAD
             if (OP == 10) s[j] = __vimax3_s16x2(s[j], a[j], c);                     // VIMNMX3.S16x2
             if (OP == 11) s[j] = __funnelshift_r(s[j], a[j], 8);                    // SHF
+            if (OP == 12) { __half2 x = *reinterpret_cast<__half2*>(&s[j]), y = *reinterpret_cast<__half2*>(&a[j]); x = __hmax2(x, y); s[j] = *reinterpret_cast<unsigned*>(&x) + 1u; }   // HMNMX2 (+1 keeps the chain live)
+            if (OP == 13) s[j] = __umulhi(s[j], c) + a[j];                           // IMAD.HI
+            if (OP == 14) s[j] = __float_as_uint(fmaxf(__uint_as_float(s[j]), __uint_as_float(a[j]))) ^ c;   // FMNMX
+            if (OP == 15) s[j] = __vmaxs2(s[j], a[j]) + c;                      // VIMNMX.S16x2 (2-input)
+            if (OP == 16) { if (j & 1) { __half2 x = *reinterpret_cast<__half2*>(&s[j]), y = *reinterpret_cast<__half2*>(&a[j]); x = __hmax2(x, y); s[j] = *reinterpret_cast<unsigned*>(&x); } else s[j] = __vimin3_u16x2(s[j], a[j], c); }   // HMNMX2 + VIMNMX3 mix
+            if (OP == 17) s[j] = __popc(s[j] ^ a[j]) + c;                            // POPC
         }
     }
     unsigned t = 0;
@@ -57,6 +64,7 @@ int main() {
     printf("SM clock (max) %.3f GHz\n", ghz);
     run<0>("IMAD", d, ghz); run<1>("IADD3", d, ghz); run<2>("LOP3", d, ghz); run<3>("PRMT", d, ghz); run<11>("SHF", d, ghz);
     run<4>("VIMNMX3.U16x2", d, ghz); run<10>("VIMNMX3.S16x2", d, ghz); run<5>("IDP4A", d, ghz); run<6>("IDP2A", d, ghz);
+    run<12>("HMNMX2(+IADD)", d, ghz); run<13>("IMAD.HI", d, ghz); run<14>("FMNMX(+LOP)", d, ghz); run<15>("VIMNMX.S16x2(+IADD)", d, ghz); run<16>("HMNMX2+VIMNMX3 mix", d, ghz); run<17>("POPC(+LOP+IADD)", d, ghz);
     run<7>("IMAD+VIMNMX3 mix", d, ghz); run<8>("IDP4A+VIMNMX3 mix", d, ghz); run<9>("IDP4A+IMAD mix", d, ghz);
     return 0;
 }
