@@ -116,7 +116,7 @@ int fbe_extract_batch(fbe_extractor* e, const uint8_t* const* imgs, int32_t nimg
         for (int i = 0; i < nb; ++i)
             FBE_CUDA(cudaMemcpy2DAsync(c.d_in + (size_t)i * img_bytes, cols, imgs[base + i], step, cols, rows,
                                        cudaMemcpyHostToDevice, c.stream));
-        rc = c.run_dev(c.d_in, cols, (int)img_bytes, nb, rows, cols);
+        rc = c.run_dev_graph(c.d_in, cols, (int)img_bytes, nb, rows, cols);
         if (rc != FBE_OK) return rc;
         uint8_t* hp = c.h_pin;
         fbe_keypoint* h_kps = reinterpret_cast<fbe_keypoint*>(hp);

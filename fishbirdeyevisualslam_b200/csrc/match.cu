@@ -216,20 +216,43 @@ __device__ inline void three_maxima(const int* histo, int& ind1, int& ind2, int&
 }
 
 // ---- sequential stage: one CTA per problem replays the reference's loop over the stored rows ----------------------
-// The replay itself is inherently serial (each accepted match changes what later queries may take), so its speed is
-// set by the latency of every dependent access.  All 256 threads first STAGE the problem in shared memory -- the
-// candidate rows compacted back to back (block scan of the row lengths), and for SearchForInitialization the per-target
-// state vMatchedDistance / vnMatches21 -- then warp 0 alone walks the queries with ~30-cycle shared-memory accesses
-// instead of ~600-cycle dependent global loads.  Problems whose rows exceed the shared-memory budget fall back to
-// reading the rows from global memory.
-constexpr int kResolveThreads = 256;
+// The reference's loop is serial: each accepted match changes which candidates later queries may take (vMatchedDistance
+// for SearchForInitialization, the taken flags elsewhere).  But an accept touches ONE target, and it changes the outcome
+// of a later query only when that target is the later query's best or second-best candidate -- rare.  So the replay runs
+// in waves of kResolveWave queries: every warp evaluates one query of the wave against the state left by the previous
+// wave (top-2 over its row), then warp 0 takes one lane per query, decides accept / reject for all of them at once, and
+// finds the first query whose best or second-best target was accepted by an EARLIER query of the same wave (one
+// MATCH.ANY over the 2 x 16 target indices).  Everything before that query commits in parallel -- their targets are
+// pairwise distinct by construction -- and the next wave starts at the conflicting query, which is then evaluated
+// against the updated state.  The result is the reference's, query by query; a wave always commits at least its first.
+// All threads first STAGE the problem in shared memory -- the candidate rows compacted back to back (block scan of the
+// row lengths), the list of queries that have candidates, and for SearchForInitialization the per-target state
+// vMatchedDistance / vnMatches21.  Problems whose rows exceed the shared-memory budget read the rows from global memory.
+constexpr int kResolveWave = 16;
+constexpr int kResolveThreads = 32 * kResolveWave;
+
+// top-2 of one query's row under the current skip state; whole warp, result warp-uniform
+__device__ __forceinline__ void resolve_row_top2(const unsigned* row, int c, int lane, bool init, const int* md, const uint8_t* taken,
+                                                 unsigned& k1, unsigned& k2) {
+    k1 = kNoKey; k2 = kNoKey;
+    for (int j = lane; j < c; j += 32) {
+        const unsigned e = row[j];
+        const int idx = (int)(e >> kRowDistBits), dist = (int)(e & ((1u << kRowDistBits) - 1u));
+        bool skip;
+        if (init) skip = md[idx] <= dist;                              // :445-446
+        else skip = taken[idx] != 0 || dist >= 256;                    // :88-90, :1404-1406, :210-211
+        if (!skip) top2_push(k1, k2, ((unsigned)dist << 20) | (unsigned)j);
+    }
+    top2_warp_merge(k1, k2);
+}
 
 __global__ void __launch_bounds__(kResolveThreads) k_resolve(ResolveArgs a, int row_budget, int state_in_smem) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
     __shared__ int s_hist[FBE_HISTO_LENGTH];
     __shared__ int s_ind[3];
     __shared__ int s_warp[kResolveThreads / 32];
-    __shared__ int s_carry;
+    __shared__ int s_carry, s_nlist, s_base;
+    __shared__ int s_bd[kResolveWave], s_bd2[kResolveWave], s_bi[kResolveWave], s_si[kResolveWave], s_l1[kResolveWave], s_l2[kResolveWave];
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nq = a.nq[b], nt = a.nt[b];
@@ -237,11 +260,13 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(ResolveArgs a, int 
     const bool init = a.mode == kResolveInit;
 
     int* s_off = reinterpret_cast<int*>(rs_smem);                       // [q_stride + 1] row starts in s_rows
-    int* s_md = s_off + a.q_stride + 1;                                 // [t_stride] (INIT, state_in_smem)
+    int* s_ql = s_off + a.q_stride + 1;                                 // [q_stride] queries that have candidates, in order
+    int* s_md = s_ql + a.q_stride;                                      // [t_stride] (INIT, state_in_smem)
     int* s_m21 = s_md + (state_in_smem ? a.t_stride : 0);
     unsigned* s_rows = reinterpret_cast<unsigned*>(s_m21 + (state_in_smem ? a.t_stride : 0));
     int* md = state_in_smem ? s_md : a.matched_dist + tb;
     int* m21 = state_in_smem ? s_m21 : a.match21 + tb;
+    const uint8_t* taken = init ? nullptr : a.taken + tb;
 
     // ---- stage: row offsets (exclusive block scan of cnt), rows, state -----------------------------------------------
     if (tid == 0) s_carry = 0;
@@ -270,9 +295,20 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(ResolveArgs a, int 
     if (tid == 0) s_off[nq] = total_rows;
     const bool staged = total_rows <= row_budget;
     __syncthreads();                           // s_off[nq] visible
-    if (staged) {
+    if (wid == kResolveWave - 1) {
+        // the last warp lists the queries that have candidates (most keypoints are not octave-0 queries) while the others copy rows
+        int n = 0;
+        for (int qbase = 0; qbase < nq; qbase += 32) {
+            const int q = qbase + lane;
+            const bool has = q < nq && s_off[q + 1] > s_off[q];
+            const unsigned bal = __ballot_sync(0xffffffffu, has);
+            if (has) s_ql[n + __popc(bal & ((1u << lane) - 1u))] = q;
+            n += __popc(bal);
+        }
+        if (lane == 0) { s_nlist = n; s_base = 0; }
+    } else if (staged) {
         // row lengths come from shared memory, so the global row loads of successive queries are independent
-        for (int q = wid; q < nq; q += kResolveThreads / 32) {
+        for (int q = wid; q < nq; q += kResolveWave - 1) {
             const int o = s_off[q], c = s_off[q + 1] - o;
             if (c == 0) continue;
             const unsigned* row = a.rows + (qb + q) * a.C;
@@ -288,67 +324,82 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(ResolveArgs a, int 
     for (int i = tid; i < nq; i += kResolveThreads) a.q_hit[qb + i] = -1;
     if (tid < FBE_HISTO_LENGTH) s_hist[tid] = 0;
     __syncthreads();
-    if (wid != 0) return;                      // the replay is one warp; no block barrier below this line
 
-    int nm = 0;
+    int nm = 0;                                // warp 0: per-lane count of accepts minus steals, summed at the end
     const int sentinel = init ? INT_MAX : 256;
-    // queries without candidates are skipped 32 at a time (most keypoints are not octave-0 queries)
-    for (int qbase = 0; qbase < nq; qbase += 32) {
-      const int c_lane = (qbase + lane < nq) ? s_off[qbase + lane + 1] - s_off[qbase + lane] : 0;
-      unsigned todo = __ballot_sync(0xffffffffu, c_lane > 0);
-      while (todo) {
-        const int jq = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int qi = qbase + jq;
-        const int c = __shfl_sync(0xffffffffu, c_lane, jq);
-        const unsigned* row = staged ? (s_rows + s_off[qi]) : (a.rows + (qb + qi) * a.C);
-        unsigned k1 = kNoKey, k2 = kNoKey;
-        for (int j = lane; j < c; j += 32) {
-            const unsigned e = row[j];
-            const int idx = (int)(e >> kRowDistBits), dist = (int)(e & ((1u << kRowDistBits) - 1u));
-            bool skip;
-            if (init) skip = md[idx] <= dist;                              // :445-446
-            else skip = a.taken[tb + idx] != 0 || dist >= 256;            // :88-90, :1404-1406, :210-211
-            if (!skip) top2_push(k1, k2, ((unsigned)dist << 20) | (unsigned)j);
-        }
-        top2_warp_merge(k1, k2);
-        if (k1 == kNoKey) continue;
-        const int bestDist = (int)(k1 >> 20);
-        const int bestDist2 = k2 == kNoKey ? sentinel : (int)(k2 >> 20);
-        const int bestIdx = (int)(row[k1 & 0xFFFFFu] >> kRowDistBits);
-        bool accept = false;
-        switch (a.mode) {
-            case kResolveInit: accept = bestDist <= FBE_TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, a.nn_ratio); break;
-            case kResolveLast: accept = bestDist <= (a.th_dist > 0 ? a.th_dist : FBE_TH_HIGH); break;
-            case kResolveMap: {
-                accept = bestDist <= FBE_TH_HIGH;
-                if (accept) {
-                    const int lvl1 = a.t_kps[tb + bestIdx].octave;
-                    const int lvl2 = k2 == kNoKey ? -1 : a.t_kps[tb + (int)(row[k2 & 0xFFFFFu] >> kRowDistBits)].octave;
-                    if (lvl1 == lvl2 && (float)bestDist > __fmul_rn(a.nn_ratio, (float)bestDist2)) accept = false;
+    const int nlist = s_nlist;
+    for (int base = 0; base < nlist;) {
+        // ---- evaluate: warp w takes query base + w of the list against the current state ------------------------------
+        const int li = base + wid;
+        if (li < nlist) {
+            const int qi = s_ql[li];
+            const int o = s_off[qi], c = s_off[qi + 1] - o;
+            const unsigned* row = staged ? (s_rows + o) : (a.rows + (qb + qi) * a.C);
+            unsigned k1, k2;
+            resolve_row_top2(row, c, lane, init, md, taken, k1, k2);
+            if (lane == 0) {
+                const int bi = k1 == kNoKey ? -1 : (int)(row[k1 & 0xFFFFFu] >> kRowDistBits);
+                const int si = k2 == kNoKey ? -1 : (int)(row[k2 & 0xFFFFFu] >> kRowDistBits);
+                s_bd[wid] = (int)(k1 >> 20);
+                s_bd2[wid] = k2 == kNoKey ? sentinel : (int)(k2 >> 20);
+                s_bi[wid] = bi; s_si[wid] = si;
+                if (a.mode == kResolveMap) {
+                    s_l1[wid] = bi < 0 ? -1 : a.t_kps[tb + bi].octave;
+                    s_l2[wid] = si < 0 ? -1 : a.t_kps[tb + si].octave;
                 }
-            } break;
-            default: accept = bestDist <= (a.th_dist > 0 ? a.th_dist : FBE_TH_LOW) && (float)bestDist < __fmul_rn(a.nn_ratio, (float)bestDist2); break;
-        }
-        if (!accept) continue;
-        if (lane == 0) {
-            const int src = a.q_src ? a.q_src[qb + qi] : qi;
-            if (init) {
-                const int old = m21[bestIdx];
-                if (old >= 0) { a.matches12[qb + old] = -1; --nm; }          // steal (:464-468)
-                a.matches12[qb + qi] = bestIdx;
-                m21[bestIdx] = qi;
-                md[bestIdx] = bestDist;
-            } else {
-                a.cur_mp[tb + bestIdx] = src;
-                if (!a.q_has_obs || a.q_has_obs[qb + qi]) a.taken[tb + bestIdx] = 1;
             }
-            ++nm;
-            a.q_hit[qb + qi] = bestIdx;        // every accept is one rotHist push (:474-484), stolen or not
         }
-        __syncwarp();
-      }
+        __syncthreads();
+        // ---- commit: warp 0, lane t = query base + t; lanes 16..31 carry the second-best targets for the conflict match --
+        if (wid == 0) {
+            const int t = lane & (kResolveWave - 1);
+            const int cnt = min(kResolveWave, nlist - base);
+            const bool live = t < cnt;
+            const int bi = live ? s_bi[t] : -1, si = live ? s_si[t] : -1;
+            bool accept = false;
+            int bestDist = 0;
+            if (live && bi >= 0) {
+                bestDist = s_bd[t];
+                const int bestDist2 = s_bd2[t];
+                switch (a.mode) {
+                    case kResolveInit: accept = bestDist <= FBE_TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, a.nn_ratio); break;
+                    case kResolveLast: accept = bestDist <= (a.th_dist > 0 ? a.th_dist : FBE_TH_HIGH); break;
+                    case kResolveMap:
+                        accept = bestDist <= FBE_TH_HIGH;
+                        if (accept && s_l1[t] == s_l2[t] && (float)bestDist > __fmul_rn(a.nn_ratio, (float)bestDist2)) accept = false;
+                        break;
+                    default: accept = bestDist <= (a.th_dist > 0 ? a.th_dist : FBE_TH_LOW) && (float)bestDist < __fmul_rn(a.nn_ratio, (float)bestDist2); break;
+                }
+            }
+            const int mine = lane < kResolveWave ? bi : si;
+            const unsigned same = __match_any_sync(0xffffffffu, mine >= 0 ? mine : -1 - lane);     // absent targets match nobody
+            const unsigned same2 = __shfl_down_sync(0xffffffffu, same, kResolveWave);              // ... of this query's second best
+            const unsigned acc = __ballot_sync(0xffffffffu, lane < kResolveWave && accept);
+            const bool conflict = lane < kResolveWave && live && (((same | same2) & acc & ((1u << lane) - 1u)) != 0u);
+            const unsigned cf = __ballot_sync(0xffffffffu, conflict);
+            const int ncommit = cf ? __ffs(cf) - 1 : cnt;            // >= 1: lane 0 has nobody before it
+            if (lane < ncommit && accept) {
+                const int qi = s_ql[base + lane];
+                if (init) {
+                    const int old = m21[bi];
+                    if (old >= 0) { a.matches12[qb + old] = -1; --nm; }          // steal (:464-468); `old` is from an earlier wave
+                    a.matches12[qb + qi] = bi;
+                    m21[bi] = qi;
+                    md[bi] = bestDist;
+                } else {
+                    a.cur_mp[tb + bi] = a.q_src ? a.q_src[qb + qi] : qi;
+                    if (!a.q_has_obs || a.q_has_obs[qb + qi]) a.taken[tb + bi] = 1;
+                }
+                ++nm;
+                a.q_hit[qb + qi] = bi;         // every accept is one rotHist push (:474-484), stolen or not
+            }
+            if (lane == 0) s_base = base + ncommit;
+        }
+        __syncthreads();
+        base = s_base;
     }
+    if (wid != 0) return;                      // the epilogue is one warp; no block barrier below this line
+    nm = __reduce_add_sync(0xffffffffu, nm);
     __syncwarp();
     if (a.check_ori && a.mode != kResolveMap) {
         // rotation histogram of all pushes, off the serial path: bins computed by the whole warp
@@ -574,9 +625,9 @@ int launch_window_top2_reproj(const FrameDev& f, const QueryDev& qs, int max_nq,
 }
 
 int launch_resolve(const ResolveArgs& a, int nb, cudaStream_t st) {
-    // shared memory: row offsets + (INIT) per-target state + as many staged row entries as fit in the rest
+    // shared memory: row offsets + query list + (INIT) per-target state + as many staged row entries as fit in the rest
     const size_t kMax = 200 * 1024;
-    size_t fixed = (size_t)(a.q_stride + 1) * 4;
+    size_t fixed = (size_t)(2 * a.q_stride + 1) * 4;
     int state_in_smem = 0;
     if (a.mode == kResolveInit && fixed + (size_t)a.t_stride * 8 <= kMax / 2) { state_in_smem = 1; fixed += (size_t)a.t_stride * 8; }
     if (fixed > kMax) { set_error("resolve: too many queries for the shared-memory offsets"); return FBE_E_UNSUPPORTED; }
