@@ -295,8 +295,8 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(ResolveArgs a, int 
     if (tid == 0) s_off[nq] = total_rows;
     const bool staged = total_rows <= row_budget;
     __syncthreads();                           // s_off[nq] visible
-    if (wid == kResolveWave - 1) {
-        // the last warp lists the queries that have candidates (most keypoints are not octave-0 queries) while the others copy rows
+    if (wid == 0) {
+        // list the queries that have candidates (most keypoints are not octave-0 queries)
         int n = 0;
         for (int qbase = 0; qbase < nq; qbase += 32) {
             const int q = qbase + lane;
@@ -306,13 +306,34 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(ResolveArgs a, int 
             n += __popc(bal);
         }
         if (lane == 0) { s_nlist = n; s_base = 0; }
-    } else if (staged) {
-        // row lengths come from shared memory, so the global row loads of successive queries are independent
-        for (int q = wid; q < nq; q += kResolveWave - 1) {
-            const int o = s_off[q], c = s_off[q + 1] - o;
-            if (c == 0) continue;
-            const unsigned* row = a.rows + (qb + q) * a.C;
-            for (int j = lane; j < c; j += 32) s_rows[o + j] = row[j];
+    }
+    __syncthreads();
+    const int nlist = s_nlist;
+    if (staged) {
+        // copy the rows: 4 list entries per warp per pass, their first 64 entries loaded before anything is stored, so the
+        // global loads of one pass are in flight together (row lengths and offsets come from shared memory)
+        for (int e0 = wid * 4; e0 < nlist; e0 += kResolveWave * 4) {
+            int o[4], c[4];
+            unsigned v0[4], v1[4];
+            const unsigned* row[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int q = e0 + u < nlist ? s_ql[e0 + u] : -1;
+                o[u] = q >= 0 ? s_off[q] : 0;
+                c[u] = q >= 0 ? s_off[q + 1] - o[u] : 0;
+                row[u] = a.rows + (qb + max(q, 0)) * a.C;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v0[u] = lane < c[u] ? row[u][lane] : 0u;
+                v1[u] = lane + 32 < c[u] ? row[u][lane + 32] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (lane < c[u]) s_rows[o[u] + lane] = v0[u];
+                if (lane + 32 < c[u]) s_rows[o[u] + lane + 32] = v1[u];
+                for (int j = lane + 64; j < c[u]; j += 32) s_rows[o[u] + j] = row[u][j];
+            }
         }
     }
     if (init) {
@@ -327,7 +348,6 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(ResolveArgs a, int 
 
     int nm = 0;                                // warp 0: per-lane count of accepts minus steals, summed at the end
     const int sentinel = init ? INT_MAX : 256;
-    const int nlist = s_nlist;
     for (int base = 0; base < nlist;) {
         // ---- evaluate: warp w takes query base + w of the list against the current state ------------------------------
         const int li = base + wid;
@@ -371,11 +391,19 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(ResolveArgs a, int 
                     default: accept = bestDist <= (a.th_dist > 0 ? a.th_dist : FBE_TH_LOW) && (float)bestDist < __fmul_rn(a.nn_ratio, (float)bestDist2); break;
                 }
             }
+            // An earlier accept of this query's BEST target always matters.  An earlier accept of its SECOND best only makes
+            // bestDist2 larger (or changes the second's level): that can flip a ratio-test reject into an accept, never the
+            // reverse, and in the map search it can flip the same-level ratio gate either way.
+            bool sens = false;
+            if (live && bi >= 0) {
+                if (a.mode == kResolveMap) sens = bestDist <= FBE_TH_HIGH;
+                else if (a.mode != kResolveLast) sens = !accept && bestDist <= (init ? FBE_TH_LOW : (a.th_dist > 0 ? a.th_dist : FBE_TH_LOW));
+            }
             const int mine = lane < kResolveWave ? bi : si;
             const unsigned same = __match_any_sync(0xffffffffu, mine >= 0 ? mine : -1 - lane);     // absent targets match nobody
             const unsigned same2 = __shfl_down_sync(0xffffffffu, same, kResolveWave);              // ... of this query's second best
             const unsigned acc = __ballot_sync(0xffffffffu, lane < kResolveWave && accept);
-            const bool conflict = lane < kResolveWave && live && (((same | same2) & acc & ((1u << lane) - 1u)) != 0u);
+            const bool conflict = lane < kResolveWave && live && (((same | (sens ? same2 : 0u)) & acc & ((1u << lane) - 1u)) != 0u);
             const unsigned cf = __ballot_sync(0xffffffffu, conflict);
             const int ncommit = cf ? __ffs(cf) - 1 : cnt;            // >= 1: lane 0 has nobody before it
             if (lane < ncommit && accept) {
@@ -398,12 +426,15 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(ResolveArgs a, int 
         __syncthreads();
         base = s_base;
     }
-    if (wid != 0) return;                      // the epilogue is one warp; no block barrier below this line
-    nm = __reduce_add_sync(0xffffffffu, nm);
-    __syncwarp();
+    // ---- epilogue on the whole CTA: rotation histogram of all pushes, the three maxima, removals, vnMatches12 -> prev_matched --
+    __shared__ int s_nm;
+    if (wid == 0) {
+        nm = __reduce_add_sync(0xffffffffu, nm);
+        if (lane == 0) s_nm = nm;
+    }
+    __syncthreads();
     if (a.check_ori && a.mode != kResolveMap) {
-        // rotation histogram of all pushes, off the serial path: bins computed by the whole warp
-        for (int qi = lane; qi < nq; qi += 32) {
+        for (int qi = tid; qi < nq; qi += kResolveThreads) {
             const int hit = a.q_hit[qb + qi];
             int bin = -1;
             if (hit >= 0) {
@@ -413,12 +444,12 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(ResolveArgs a, int 
             }
             a.q_bin[qb + qi] = bin;
         }
-        __syncwarp();
-        if (lane == 0) { int i1, i2, i3; three_maxima(s_hist, i1, i2, i3); s_ind[0] = i1; s_ind[1] = i2; s_ind[2] = i3; }
-        __syncwarp();
+        __syncthreads();
+        if (tid == 0) { int i1, i2, i3; three_maxima(s_hist, i1, i2, i3); s_ind[0] = i1; s_ind[1] = i2; s_ind[2] = i3; }
+        __syncthreads();
         const int i1 = s_ind[0], i2 = s_ind[1], i3 = s_ind[2];
         int dec = 0;
-        for (int qi = lane; qi < nq; qi += 32) {
+        for (int qi = tid; qi < nq; qi += kResolveThreads) {       // same thread -> same qi as above: it reads its own q_bin
             const int bin = a.q_bin[qb + qi];
             if (bin < 0 || bin == i1 || bin == i2 || bin == i3) continue;
             if (init) {
@@ -429,16 +460,16 @@ __global__ void __launch_bounds__(kResolveThreads) k_resolve(ResolveArgs a, int 
             }
         }
         dec = __reduce_add_sync(0xffffffffu, dec);
-        nm -= dec;     // only lane 0's nm is meaningful; dec is warp-uniform
+        if (lane == 0 && dec) atomicSub(&s_nm, dec);
+        __syncthreads();
     }
-    __syncwarp();
     if (init && a.prev_matched) {
-        for (int qi = lane; qi < nq; qi += 32) {
+        for (int qi = tid; qi < nq; qi += kResolveThreads) {
             const int m = a.matches12[qb + qi];
             if (m >= 0) a.prev_matched[qb + qi] = make_float2(a.t_kps[tb + m].x, a.t_kps[tb + m].y);
         }
     }
-    if (lane == 0) a.nmatches[b] = nm;
+    if (tid == 0) a.nmatches[b] = s_nm;
 }
 
 // ---- BirdviewMatch epilogue (src/ORBmatcher.cc:1700-1759): ratio test, orientation histogram, DMatch list -----------
