@@ -20,11 +20,13 @@ __constant__ int8_t c_pattern[256 * 4] = {
 #include "orb_pattern.inc"
 };
 
-constexpr int kDescWarps = 8, kDescPerWarp = 4, kDescPerCta = kDescWarps * kDescPerWarp;
+constexpr int kDescWarps = 8;        // keypoints per warp (kDescPerWarp) is a template parameter: 4 for batches, 1 when a call is latency-bound
 constexpr int kCoefRows = 37;         // 11 passes x 3 rows + the 5 idle lanes' reach, rows >= 31 hold zeros
 constexpr int kPatchR = 18, kPatchRows = 2 * kPatchR + 1, kPatchWords = 11;      // 37 rows x 44 bytes
 
+template <int kDescPerWarp>
 __global__ void __launch_bounds__(kDescWarps * 32, 8) k_describe(const Plan* __restrict__ plan, Workspace ws) {
+    constexpr int kDescPerCta = kDescWarps * kDescPerWarp;
     __shared__ float4 s_pat[256];                                       // [j][lane]: pair lane*8 + j as (x0, y0, x1, y1)
     __shared__ uint32_t s_patch[kDescWarps][kPatchRows * kPatchWords];
     __shared__ uint32_t s_key[kDescPerCta];
@@ -32,6 +34,8 @@ __global__ void __launch_bounds__(kDescWarps * 32, 8) k_describe(const Plan* __r
     __shared__ float s_angle[kDescPerCta], s_cos[kDescPerCta], s_sin[kDescPerCta];
     __shared__ unsigned s_coef[2 * kCoefRows * 9];
 
+    pdl_launch_dependents();
+    pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int b = blockIdx.y;
     const int* level_n = ws.level_n + (size_t)b * FBE_MAX_LEVELS;
@@ -176,8 +180,14 @@ __global__ void __launch_bounds__(kDescWarps * 32, 8) k_describe(const Plan* __r
 }
 
 int launch_describe(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg, cudaStream_t st) {
-    dim3 grid((hp.kp_cap_total + kDescPerCta - 1) / kDescPerCta, nimg);
-    k_describe<<<grid, kDescWarps * 32, 0, st>>>(dp, ws);
+    // a few frames cannot fill the GPU with 32 keypoints per CTA: one keypoint per warp shortens the call's critical path
+    if ((size_t)nimg * hp.kp_cap_total <= (size_t)4 * 148 * kDescWarps) {
+        dim3 grid((hp.kp_cap_total + kDescWarps - 1) / kDescWarps, nimg);
+        FBE_CUDA(launch_dep(k_describe<1>, grid, dim3(kDescWarps * 32), 0, st, dp, ws));
+    } else {
+        dim3 grid((hp.kp_cap_total + 4 * kDescWarps - 1) / (4 * kDescWarps), nimg);
+        FBE_CUDA(launch_dep(k_describe<4>, grid, dim3(kDescWarps * 32), 0, st, dp, ws));
+    }
     count_launch();
     FBE_CUDA(cudaGetLastError());
     return FBE_OK;

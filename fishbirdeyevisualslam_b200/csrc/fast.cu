@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast_cells(const Plan* __re
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
 
+    pdl_launch_dependents();
+    pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int b = blockIdx.y;
     const uint32_t te = __ldg(ws.fast_tab + blockIdx.x);
@@ -308,7 +310,7 @@ int launch_fast_cells(const Plan& hp, const Plan* dp, const Workspace& ws, const
     if (smem > 200 * 1024) { set_error("FAST strip too large for shared memory"); return FBE_E_UNSUPPORTED; }
     if (smem > 48 * 1024) FBE_CUDA(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(hp.ngroups_total, nimg);
-    k_fast_cells<<<grid, kFastThreads, smem, st>>>(dp, ws, maps);
+    FBE_CUDA(launch_dep(k_fast_cells, grid, dim3(kFastThreads), smem, st, dp, ws, maps));
     count_launch();
     FBE_CUDA(cudaGetLastError());
     return FBE_OK;

@@ -109,6 +109,25 @@ struct ResizeTab { int ofs; short a0, a1; };   // 8 bytes per padded coordinate
 void set_error(const std::string& s);
 const char* last_error();
 extern std::atomic<unsigned long long> g_launches;
+// Programmatic dependent launch: the extractor is a chain of short kernels, each consuming its predecessor's output.  A kernel
+// launched with launch_dep() may start while its predecessor on the stream is still draining: CTAs are scheduled and run
+// whatever precedes pdl_wait() (index arithmetic, barrier set-up, constant tables); pdl_wait() returns once the predecessor
+// has completed and its writes are visible.  Launched without the attribute both calls are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... P, typename... A>
+inline cudaError_t launch_dep(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    cudaLaunchConfig_t c = {};
+    c.gridDim = grid; c.blockDim = block; c.dynamicSmemBytes = smem; c.stream = st;
+    cudaLaunchAttribute at = {};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    c.attrs = &at; c.numAttrs = 1;
+    return cudaLaunchKernelEx(&c, kern, P(std::forward<A>(args))...);
+}
+#endif
+
 inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 #define FBE_CUDA(expr)                                                                                   \

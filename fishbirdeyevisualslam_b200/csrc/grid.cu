@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(kGridThreads) k_grid_build(const fbe_keypoint*
     extern __shared__ int s_cnt[];          // gcells + 1
     __shared__ int s_warp[kGridThreads / 32];
     __shared__ int s_carry;
+    pdl_launch_dependents();
+    pdl_wait();
     const int f = blockIdx.x;
     const int n = n_arr[f];
     const int gcells = gcols * grows;
@@ -87,8 +89,8 @@ int launch_grid_build(const fbe_keypoint* d_kps, const int* d_n, int n_stride, i
                       cudaStream_t st) {
     const size_t smem = (size_t)(gcols * grows + 1) * sizeof(int);
     if (smem > 48 * 1024) { set_error("grid too large"); return FBE_E_UNSUPPORTED; }
-    k_grid_build<<<nframes, kGridThreads, smem, st>>>(d_kps, d_n, n_stride, min_x, min_y, inv_w, inv_h, gcols, grows,
-                                                      d_cell_of, d_start, d_items);
+    FBE_CUDA(launch_dep(k_grid_build, dim3(nframes), dim3(kGridThreads), smem, st, d_kps, d_n, n_stride, min_x, min_y, inv_w, inv_h, gcols, grows,
+                        d_cell_of, d_start, d_items));
     count_launch();
     FBE_CUDA(cudaGetLastError());
     return FBE_OK;

@@ -428,6 +428,8 @@ __global__ void __launch_bounds__(kOctThreads, 3) k_octree(const Plan* __restric
     extern __shared__ __align__(16) uint8_t dyn[];
     __shared__ int s_warp[kOctThreads / 32 + 1];
     __shared__ int s_ctl[4];
+    pdl_launch_dependents();
+    pdl_wait();
     const int tid = threadIdx.x;
     const int l = blockIdx.x, b = blockIdx.y;
     const LevelGeom g = plan->lv[l];
@@ -562,7 +564,7 @@ int launch_octree(const Plan& hp, const Plan* dp, const Workspace& ws, int nimg,
     size_t smem = use_smem ? need : 0;
     if (smem > 48 * 1024) FBE_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(hp.nlevels, nimg);
-    k_octree<<<grid, kOctThreads, smem, st>>>(dp, ws, use_smem, (int)need);
+    FBE_CUDA(launch_dep(k_octree, grid, dim3(kOctThreads), smem, st, dp, ws, use_smem, (int)need));
     count_launch();
     FBE_CUDA(cudaGetLastError());
     return FBE_OK;

@@ -22,6 +22,8 @@ __device__ __forceinline__ int reflect101_once(int p, int len) {
 }
 
 __global__ void __launch_bounds__(256) k_level0(const Plan* __restrict__ plan, Workspace ws, int first_chunk, int nchunks) {
+    pdl_launch_dependents();
+    pdl_wait();
     const LevelGeom& g = plan->lv[0];
     const int ci = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
@@ -40,6 +42,8 @@ __global__ void __launch_bounds__(256) k_level0(const Plan* __restrict__ plan, W
 
 // border chunks: chunk index = bc < nlead ? bc : first_tail + (bc - nlead)
 __global__ void __launch_bounds__(256) k_level0_border(const Plan* __restrict__ plan, Workspace ws, int nlead, int first_tail, int nborder) {
+    pdl_launch_dependents();
+    pdl_wait();
     const LevelGeom& g = plan->lv[0];
     const int t = blockIdx.x * 256 + threadIdx.x;
     const int b = blockIdx.z;
@@ -69,6 +73,8 @@ constexpr int kRsRowsPerWarp = 8, kRsWarps = 8;
 
 __global__ void __launch_bounds__(256) k_resize(const Plan* __restrict__ plan, Workspace ws,
                                                 const ResizeTab* __restrict__ tab, int level) {
+    pdl_launch_dependents();
+    pdl_wait();
     const LevelGeom& g = plan->lv[level];
     const LevelGeom& s = plan->lv[level - 1];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -132,9 +138,11 @@ __global__ void __launch_bounds__(256) k_resize_tma(const Plan* __restrict__ pla
     const int b = blockIdx.z;
     const int bw = g.rs_bw, bh = g.rs_bh;
     const int x0s = plan->rs_x0[level][blockIdx.x], y0s = plan->rs_y0[level][blockIdx.y];
+    pdl_launch_dependents();
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
+        pdl_wait();              // the source level: everything the CTA reads of it arrives through this TMA load; all threads wait on its barrier
         mbar_expect_tx(&bar, (uint32_t)(bw * bh));
         tma_load_3d(rs_tile, &map, &bar, x0s, y0s, ws.slot0 + b);
     }
@@ -194,21 +202,21 @@ int launch_pyramid(const Plan& hp, const Plan* dp, const Workspace& ws, const Re
             const int nint = (aligned16 && last >= first) ? last - first + 1 : 0;
             if (nint > 0) {
                 dim3 grid((nint + 31) / 32, (g.ph + 7) / 8, nimg);
-                k_level0<<<grid, dim3(32, 8), 0, st>>>(dp, ws, first, nint);
+                FBE_CUDA(launch_dep(k_level0, grid, dim3(32, 8), 0, st, dp, ws, first, nint));
                 count_launch();
             }
             const int nlead = nint > 0 ? first : nchunk, first_tail = last + 1;
             const int nborder = nint > 0 ? nlead + (nchunk - first_tail) : nchunk;
             dim3 bgrid((g.ph * nborder + 255) / 256, 1, nimg);
-            k_level0_border<<<bgrid, 256, 0, st>>>(dp, ws, nlead, first_tail, nborder);
+            FBE_CUDA(launch_dep(k_level0_border, bgrid, dim3(256), 0, st, dp, ws, nlead, first_tail, nborder));
         } else {
             dim3 rgrid((g.pitch + kRsTW - 1) / kRsTW, (g.ph + kRsTH - 1) / kRsTH, nimg);
             if (g.rs_bw > 0) {
                 const size_t smem = (size_t)g.rs_bw * g.rs_bh;
                 if (smem > 48 * 1024) FBE_CUDA(cudaFuncSetAttribute(k_resize_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-                k_resize_tma<<<rgrid, 256, smem, st>>>(dp, ws, d_tab, l, rs_maps.m[l]);
+                FBE_CUDA(launch_dep(k_resize_tma, rgrid, dim3(256), smem, st, dp, ws, d_tab, l, rs_maps.m[l]));
             } else {
-                k_resize<<<rgrid, 256, 0, st>>>(dp, ws, d_tab, l);
+                FBE_CUDA(launch_dep(k_resize, rgrid, dim3(256), 0, st, dp, ws, d_tab, l));
             }
         }
         count_launch();

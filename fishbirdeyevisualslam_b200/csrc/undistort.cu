@@ -57,6 +57,8 @@ __global__ void k_undistort(const fbe_keypoint* __restrict__ in, int n, float fx
 // the same per-point arithmetic over the device-resident keypoints of a batch (n_arr[b] valid entries per image)
 __global__ void k_undistort_batch(const fbe_keypoint* __restrict__ in, const int* __restrict__ n_arr, int stride, float fx, float fy,
                                   float cx, float cy, float k0, float k1, float k2, float k3, fbe_keypoint* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_arr[b]) return;
     fbe_keypoint kp = in[(size_t)b * stride + i];
@@ -70,7 +72,7 @@ __global__ void k_undistort_batch(const fbe_keypoint* __restrict__ in, const int
 int launch_undistort_batch(const fbe_keypoint* in, const int* n_arr, int stride, int nimg, const float K[4], const float D[4],
                            fbe_keypoint* out, cudaStream_t st) {
     dim3 grid((stride + 127) / 128, nimg);
-    k_undistort_batch<<<grid, 128, 0, st>>>(in, n_arr, stride, K[0], K[1], K[2], K[3], D[0], D[1], D[2], D[3], out);
+    FBE_CUDA(launch_dep(k_undistort_batch, grid, dim3(128), 0, st, in, n_arr, stride, K[0], K[1], K[2], K[3], D[0], D[1], D[2], D[3], out));
     count_launch();
     FBE_CUDA(cudaGetLastError());
     return FBE_OK;
