@@ -86,8 +86,11 @@ int fbe_plan_query(const fbe_extractor_cfg* cfg, int32_t rows, int32_t cols, int
     return FBE_OK;
 }
 
-int fbe_extract_batch(fbe_extractor* e, const uint8_t* const* imgs, int32_t nimg, int32_t rows, int32_t cols, size_t step,
-                      fbe_keypoint* kps, uint8_t* desc, int32_t capacity, int32_t* n_out) {
+// pyr_dst / pyr_step (optional, one image only): the padded pyramid levels are copied out on the side stream as soon as the pyramid
+// kernels have finished, i.e. behind FAST / octree / describe instead of after them.
+static int extract_batch_impl(fbe_extractor* e, const uint8_t* const* imgs, int32_t nimg, int32_t rows, int32_t cols, size_t step,
+                              fbe_keypoint* kps, uint8_t* desc, int32_t capacity, int32_t* n_out, uint8_t* const* pyr_dst,
+                              const size_t* pyr_step) {
     if (!e || !n_out) return FBE_E_INVALID;
     for (int i = 0; i < nimg; ++i) n_out[i] = 0;
     if (!imgs || nimg <= 0 || rows <= 0 || cols <= 0) return FBE_OK;   // reference: empty image -> silent return (:1046-1047)
@@ -116,8 +119,15 @@ int fbe_extract_batch(fbe_extractor* e, const uint8_t* const* imgs, int32_t nimg
         for (int i = 0; i < nb; ++i)
             FBE_CUDA(cudaMemcpy2DAsync(c.d_in + (size_t)i * img_bytes, cols, imgs[base + i], step, cols, rows,
                                        cudaMemcpyHostToDevice, c.stream));
-        rc = c.run_dev_graph(c.d_in, cols, (int)img_bytes, nb, rows, cols);
+        rc = c.run_dev(c.d_in, cols, (int)img_bytes, nb, rows, cols);
         if (rc != FBE_OK) return rc;
+        if (pyr_dst) {                 // stream2 has run the blur behind the pyramid event; the level copies queue up after it
+            for (int l = 0; l < c.cfg.nlevels; ++l) {
+                const LevelGeom& g = c.hplan.lv[l];
+                FBE_CUDA(cudaMemcpy2DAsync(pyr_dst[l], pyr_step[l], c.ws.pyr + g.img_off, g.pitch, g.w + 2 * kEdge, g.ph,
+                                           cudaMemcpyDeviceToHost, c.stream2));
+            }
+        }
         uint8_t* hp = c.h_pin;
         fbe_keypoint* h_kps = reinterpret_cast<fbe_keypoint*>(hp);
         uint8_t* h_desc = hp + (size_t)c.cfg.max_batch * cap_total * sizeof(fbe_keypoint);
@@ -128,6 +138,7 @@ int fbe_extract_batch(fbe_extractor* e, const uint8_t* const* imgs, int32_t nimg
         FBE_CUDA(cudaMemcpyAsync(h_kps, c.ws.out_kps, (size_t)nb * cap_total * sizeof(fbe_keypoint), cudaMemcpyDeviceToHost, c.stream));
         FBE_CUDA(cudaMemcpyAsync(h_desc, c.ws.out_desc, (size_t)nb * cap_total * 32, cudaMemcpyDeviceToHost, c.stream));
         FBE_CUDA(cudaStreamSynchronize(c.stream));
+        if (pyr_dst) FBE_CUDA(cudaStreamSynchronize(c.stream2));
         for (int i = 0; i < nb; ++i) {
             if (h_status[i]) { set_error("octree workspace overflow"); return FBE_E_CAPACITY; }
             const int n = h_n[i];
@@ -140,6 +151,24 @@ int fbe_extract_batch(fbe_extractor* e, const uint8_t* const* imgs, int32_t nimg
         }
     }
     return FBE_OK;
+}
+
+int fbe_extract_batch(fbe_extractor* e, const uint8_t* const* imgs, int32_t nimg, int32_t rows, int32_t cols, size_t step,
+                      fbe_keypoint* kps, uint8_t* desc, int32_t capacity, int32_t* n_out) {
+    return extract_batch_impl(e, imgs, nimg, rows, cols, step, kps, desc, capacity, n_out, nullptr, nullptr);
+}
+
+int fbe_extract_pyramid(fbe_extractor* e, const uint8_t* img, int32_t rows, int32_t cols, size_t step, fbe_keypoint* kps, uint8_t* desc,
+                        int32_t capacity, int32_t* n_out, uint8_t* const* pyr_dst, const size_t* pyr_step) {
+    if (!e || !pyr_dst || !pyr_step) return FBE_E_INVALID;
+    if (!img || rows <= 0 || cols <= 0) { if (n_out) *n_out = 0; return n_out ? FBE_OK : FBE_E_INVALID; }
+    FBE_CUDA(cudaSetDevice(e->core.cfg.device));
+    int rc = e->core.ensure_plan(rows, cols);          // the level sizes the destinations are checked against
+    if (rc != FBE_OK) return rc;
+    for (int l = 0; l < e->core.cfg.nlevels; ++l)
+        if (!pyr_dst[l] || pyr_step[l] < (size_t)(e->core.hplan.lv[l].w + 2 * kEdge)) return FBE_E_INVALID;
+    const uint8_t* one[1] = {img};
+    return extract_batch_impl(e, one, 1, rows, cols, step, kps, desc, capacity, n_out, pyr_dst, pyr_step);
 }
 
 int fbe_extract(fbe_extractor* e, const uint8_t* img, int32_t rows, int32_t cols, size_t step, fbe_keypoint* kps,
@@ -159,6 +188,15 @@ int fbe_pyramid_level(fbe_extractor* e, int32_t slot, int32_t level, uint8_t* ds
     FBE_CUDA(cudaMemcpy2DAsync(dst, dst_step, c.ws.pyr + (size_t)slot * c.hplan.pyr_bytes + g.img_off, g.pitch, g.w + 2 * kEdge, g.ph,
                                cudaMemcpyDeviceToHost, c.stream));
     FBE_CUDA(cudaStreamSynchronize(c.stream));
+    return FBE_OK;
+}
+
+int fbe_pyramid_geometry(fbe_extractor* e, int32_t rows, int32_t cols, int32_t* level_rows, int32_t* level_cols) {
+    if (!e || !level_rows || !level_cols || rows <= 0 || cols <= 0) return FBE_E_INVALID;
+    FBE_CUDA(cudaSetDevice(e->core.cfg.device));
+    const int rc = e->core.ensure_plan(rows, cols);
+    if (rc != FBE_OK) return rc;
+    for (int l = 0; l < e->core.cfg.nlevels; ++l) { level_rows[l] = e->core.hplan.lv[l].h; level_cols[l] = e->core.hplan.lv[l].w; }
     return FBE_OK;
 }
 

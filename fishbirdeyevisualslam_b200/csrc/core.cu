@@ -39,7 +39,6 @@ int ExtractorCore::init(const fbe_extractor_cfg& c) {
 }
 
 int ExtractorCore::free_ws() {
-    if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }      // the graph holds pointers into the workspace
     cudaFree(ws.pyr); cudaFree(ws.blur); cudaFree(ws.cell_count); cudaFree(ws.slots); cudaFree(ws.keys);
     cudaFree(ws.key_node); cudaFree(ws.oct_scratch); cudaFree(ws.sel); cudaFree(ws.level_n); if (ws.out_kps_un != ws.out_kps) cudaFree(ws.out_kps_un);
     cudaFree(ws.out_kps);
@@ -257,43 +256,6 @@ int ExtractorCore::run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, in
 #undef FBE_STAGE
 #undef FBE_MARK
     last_nimg = nimg;
-    return FBE_OK;
-}
-
-int ExtractorCore::run_dev_graph(const uint8_t* d_imgs, int pitch, int slot_stride, int nimg, int rows, int cols, int slot0, int out_set) {
-    static const bool use_graph = []() { const char* e = std::getenv("FBE_GRAPH"); return !(e && e[0] == '0'); }();
-    static const bool sync_debug = std::getenv("FBE_SYNC_DEBUG") != nullptr;
-    if (!use_graph || timing || sync_debug) return run_dev(d_imgs, pitch, slot_stride, nimg, rows, cols, slot0, out_set);
-    FBE_CUDA(cudaSetDevice(cfg.device));
-    int rc = ensure_plan(rows, cols);                    // allocations happen outside the capture
-    if (rc != FBE_OK) return rc;
-    const GraphKey key = {d_imgs, pitch, slot_stride, nimg, rows, cols, slot0, out_set};
-    if (gexec && std::memcmp(&key, &gkey, sizeof(key)) == 0) {
-        FBE_CUDA(cudaGraphLaunch(gexec, stream));
-        count_launch(glaunches);
-        last_nimg = nimg;
-        return FBE_OK;
-    }
-    if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
-    const unsigned long long l0 = g_launches.load(std::memory_order_relaxed);
-    FBE_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-    rc = run_dev(d_imgs, pitch, slot_stride, nimg, rows, cols, slot0, out_set);      // enqueues on `stream` and (forked / joined by events) `stream2`
-    cudaGraph_t graph = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
-    const int captured = (int)(g_launches.load(std::memory_order_relaxed) - l0);
-    g_launches.fetch_sub((unsigned long long)captured, std::memory_order_relaxed);     // captured, not executed
-    if (rc != FBE_OK || ce != cudaSuccess || !graph) {
-        if (graph) cudaGraphDestroy(graph);
-        if (rc == FBE_OK) { set_error(std::string("graph capture of the extractor failed: ") + cudaGetErrorString(ce)); rc = FBE_E_CUDA; }
-        return rc;
-    }
-    const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ie != cudaSuccess) { gexec = nullptr; set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); return FBE_E_CUDA; }
-    gkey = key;
-    glaunches = captured;
-    FBE_CUDA(cudaGraphLaunch(gexec, stream));
-    count_launch(glaunches);
     return FBE_OK;
 }
 

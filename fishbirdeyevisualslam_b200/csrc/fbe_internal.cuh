@@ -238,13 +238,6 @@ struct ExtractorCore {
     // `out_set` selects one of `out_sets` copies of the OUTPUT arrays (keypoints, descriptors, counts, grid): the batch
     // pipeline alternates between two so that matching of step N can run beside the extraction of step N+1.
     int run_dev(const uint8_t* d_imgs, int pitch, int slot_stride, int nimg, int rows, int cols, int slot0 = 0, int out_set = 0);
-    // The same sequence replayed from a CUDA graph (captured on first use, re-captured when an argument changes): the
-    // single-frame drop-in path is launch-bound -- ~14 kernels of ~5 us on two streams -- so one cudaGraphLaunch replaces the
-    // launch calls and the cross-stream event traffic.  FBE_GRAPH=0 disables; per-stage timing and FBE_SYNC_DEBUG use run_dev.
-    int run_dev_graph(const uint8_t* d_imgs, int pitch, int slot_stride, int nimg, int rows, int cols, int slot0 = 0, int out_set = 0);
-    cudaGraphExec_t gexec = nullptr;
-    struct GraphKey { const uint8_t* d_imgs; int pitch, slot_stride, nimg, rows, cols, slot0, out_set; } gkey = {};
-    int glaunches = 0;
     Workspace slot_view(int slot0, int out_set = 0) const;
     int out_sets = 1;      // set before the first ensure_plan()
     int free_ws();

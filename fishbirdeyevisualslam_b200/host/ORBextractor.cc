@@ -61,9 +61,20 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, st
     std::vector<cv::KeyPoint> kps(cap);
     std::vector<unsigned char> desc((size_t)cap * 32);
     int32_t n = 0;
-    rc = fbe_extract(handle_, image.ptr(0), image.rows, image.cols, (size_t)image.step, reinterpret_cast<fbe_keypoint*>(kps.data()),
-                     desc.data(), cap, &n);
-    if (rc != FBE_OK) die("fbe_extract", rc);
+    if (fill_pyramid_) {
+        // mvImagePyramid is a side effect of operator() in the reference (ComputePyramid, src/ORBextractor.cc:1052): the level
+        // copies ride behind detection and description inside the same call
+        std::vector<unsigned char*> dst(nlevels);
+        std::vector<size_t> steps(nlevels);
+        LayoutImagePyramid(image.rows, image.cols, dst, steps);
+        rc = fbe_extract_pyramid(handle_, image.ptr(0), image.rows, image.cols, (size_t)image.step, reinterpret_cast<fbe_keypoint*>(kps.data()),
+                                 desc.data(), cap, &n, dst.data(), steps.data());
+        if (rc != FBE_OK) die("fbe_extract_pyramid", rc);
+    } else {
+        rc = fbe_extract(handle_, image.ptr(0), image.rows, image.cols, (size_t)image.step, reinterpret_cast<fbe_keypoint*>(kps.data()),
+                         desc.data(), cap, &n);
+        if (rc != FBE_OK) die("fbe_extract", rc);
+    }
 
     if (n == 0) {
         _descriptors.release();
@@ -74,27 +85,26 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, st
     }
     kps.resize(n);
     _keypoints.swap(kps);
-    if (fill_pyramid_) FillImagePyramid(image.rows, image.cols);
 }
 
-// mvImagePyramid of the image just processed (src/ORBextractor.cc:1107-1132 leaves it behind as a side effect of operator()).
-void ORBextractor::FillImagePyramid(int rows, int cols) {
-    std::vector<unsigned char*> dst(nlevels);
-    std::vector<size_t> steps(nlevels);
+// Pinned host storage for mvImagePyramid of a rows x cols image: every level with its 19-px frame, rows padded to 64 bytes;
+// mvImagePyramid[l] is the ROI view inside the frame, like the reference's (src/ORBextractor.cc:1107-1132).  Laid out once per image size.
+void ORBextractor::LayoutImagePyramid(int rows, int cols, std::vector<unsigned char*>& dst, std::vector<size_t>& steps) {
     std::vector<int32_t> lr(nlevels), lc(nlevels);
+    int rc = fbe_pyramid_geometry(handle_, rows, cols, lr.data(), lc.data());
+    if (rc != FBE_OK) die("fbe_pyramid_geometry", rc);
     size_t total = 0;
     for (int l = 0; l < nlevels; ++l) {
-        int rc = fbe_pyramid_level(handle_, 0, l, NULL, 0, &lr[l], &lc[l]);
-        if (rc != FBE_OK) die("fbe_pyramid_level", rc);
         steps[l] = ((size_t)lc[l] + 38 + 63) & ~(size_t)63;
         total += steps[l] * (size_t)(lr[l] + 38);
     }
-    if (total > pyr_host_bytes_ || rows != pyr_rows_ || cols != pyr_cols_) {
+    const bool relayout = total > pyr_host_bytes_ || rows != pyr_rows_ || cols != pyr_cols_;
+    if (relayout) {
         for (int l = 0; l < nlevels; ++l) mvImagePyramid[l] = cv::Mat();
         if (total > pyr_host_bytes_) {
             if (pyr_host_) fbe_host_free(pyr_host_);
             void* p = NULL;
-            int rc = fbe_host_alloc(&p, total);
+            rc = fbe_host_alloc(&p, total);
             if (rc != FBE_OK) die("fbe_host_alloc", rc);
             pyr_host_ = static_cast<unsigned char*>(p);
             pyr_host_bytes_ = total;
@@ -105,12 +115,10 @@ void ORBextractor::FillImagePyramid(int rows, int cols) {
     for (int l = 0; l < nlevels; ++l) {
         dst[l] = pyr_host_ + off;
         off += steps[l] * (size_t)(lr[l] + 38);
-    }
-    int rc = fbe_pyramid_fetch(handle_, 0, dst.data(), steps.data());
-    if (rc != FBE_OK) die("fbe_pyramid_fetch", rc);
-    for (int l = 0; l < nlevels; ++l) {
-        cv::Mat padded(lr[l] + 38, lc[l] + 38, CV_8UC1, dst[l], steps[l]);
-        mvImagePyramid[l] = padded(cv::Rect(19, 19, lc[l], lr[l]));      // ROI view with the 19-px frame around it, like the reference
+        if (relayout) {
+            cv::Mat padded(lr[l] + 38, lc[l] + 38, CV_8UC1, dst[l], steps[l]);
+            mvImagePyramid[l] = padded(cv::Rect(19, 19, lc[l], lr[l]));      // ROI view with the 19-px frame around it, like the reference
+        }
     }
 }
 

@@ -57,7 +57,7 @@ private:
     unsigned char* pyr_host_;         // pinned (fbe_host_alloc)
     size_t pyr_host_bytes_;
     int pyr_rows_, pyr_cols_;         // image size the views were laid out for
-    void FillImagePyramid(int rows, int cols);
+    void LayoutImagePyramid(int rows, int cols, std::vector<unsigned char*>& dst, std::vector<size_t>& steps);
 };
 
 }  // namespace ORB_SLAM2

@@ -105,6 +105,14 @@ FBE_API int fbe_pyramid_level(fbe_extractor* e, int32_t slot, int32_t level, uin
  * the padded (rows+38) x (cols+38) level l with row stride dst_step[l]; the copies are enqueued together and waited for once.
  * Pinned destinations (fbe_host_alloc) make them true DMA transfers. */
 FBE_API int fbe_pyramid_fetch(fbe_extractor* e, int32_t slot, uint8_t* const* dst_padded, const size_t* dst_step);
+/* fbe_extract + fbe_pyramid_fetch of the same image in one call -- what ORBextractor::operator() does in the reference
+ * (src/ORBextractor.cc:1052 ComputePyramid fills mvImagePyramid, then keypoints and descriptors follow): the level copies leave on a
+ * side stream as soon as the pyramid is built, behind detection and description instead of after them.  dst_padded / dst_step as
+ * in fbe_pyramid_fetch (sizes from fbe_pyramid_geometry). */
+FBE_API int fbe_extract_pyramid(fbe_extractor* e, const uint8_t* img, int32_t rows, int32_t cols, size_t step, fbe_keypoint* kps,
+                        uint8_t* desc, int32_t capacity, int32_t* n_out, uint8_t* const* dst_padded, const size_t* dst_step);
+/* Level sizes (without the frame) an image of rows x cols gets; usable before the first extraction of that size. */
+FBE_API int fbe_pyramid_geometry(fbe_extractor* e, int32_t rows, int32_t cols, int32_t* level_rows, int32_t* level_cols);
 
 /* Stage taps for the parity tests (slot of the LAST call). Not part of the reference interface. */
 /* vToDistributeKeys of one level in reference order: (x, y, score) triples in level coordinates */

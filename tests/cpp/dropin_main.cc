@@ -28,11 +28,14 @@ int main(int argc, char** argv) {
     std::vector<float> sf = ex->GetScaleFactors(), isig = ex->GetInverseScaleSigmaSquares();
     std::fwrite(sf.data(), 4, lv, f);
     std::fwrite(isig.data(), 4, lv, f);
-    const cv::Mat& top = ex->mvImagePyramid[lv - 1];
-    int tr = top.rows, tc = top.cols;
-    std::fwrite(&tr, 4, 1, f);
-    std::fwrite(&tc, 4, 1, f);
-    for (int y = 0; y < tr; ++y) std::fwrite(top.ptr(y), 1, tc, f);
+    // every level of mvImagePyramid WITH the 19-px frame around the view (the reference's views sit inside padded storage too)
+    for (int l = 0; l < lv; ++l) {
+        const cv::Mat& L = ex->mvImagePyramid[l];
+        int tr = L.rows, tc = L.cols;
+        std::fwrite(&tr, 4, 1, f);
+        std::fwrite(&tc, 4, 1, f);
+        for (int y = -19; y < tr + 19; ++y) std::fwrite(L.ptr(0) + (long)y * (long)L.step - 19, 1, tc + 38, f);
+    }
     std::fclose(f);
     delete ex;
     return 0;

@@ -49,9 +49,12 @@ def test_dropin_matches_oracle(oracle, tmp_path):
     sf = np.frombuffer(b, np.float32, lv, off + 4)
     assert np.array_equal(sf, o.tables()["scale"])
     off += 4 + 8 * lv
-    tr, tc = struct.unpack_from("<ii", b, off)
-    top = np.frombuffer(b, np.uint8, tr * tc, off + 8).reshape(tr, tc)
-    assert np.array_equal(top, o.level_padded(nl - 1)[19:-19, 19:-19])
+    for l in range(nl):                 # every mvImagePyramid level, frame included (filled inside the second operator() call)
+        tr, tc = struct.unpack_from("<ii", b, off)
+        lvl = np.frombuffer(b, np.uint8, (tr + 38) * (tc + 38), off + 8).reshape(tr + 38, tc + 38)
+        assert np.array_equal(lvl, o.level_padded(l)), f"mvImagePyramid[{l}]"
+        off += 8 + (tr + 38) * (tc + 38)
+    assert off == len(b)
 
 
 def test_dropin_matcher_library_links(fbe):
