@@ -27,6 +27,23 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// pinned host staging for results: a device->host copy into the caller's pageable arrays is staged by the driver and costs a
+// round trip each; results land here with ONE synchronise per search and are copied out by the host
+struct HostPin {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return FBE_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        FBE_CUDA(cudaMallocHost(&p, want));
+        cap = want;
+        return FBE_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct FrameBufs {
     DevBuf kps, desc, n, cell, start, items;
     void release() { kps.release(); desc.release(); n.release(); cell.release(); start.release(); items.release(); }
@@ -61,6 +78,7 @@ struct fbe_matcher {
     CachedFrame cache[kFrameCache];            // frames given as fbe_frame_view
     unsigned long long tick = 0, cache_hits = 0, cache_misses = 0;
     DevBuf q, lv, qdesc, nq, rows, cnt, misc, i0, i1, i2, i3, i4, u0, u1, f0, partial;
+    HostPin hres;                              // [0, 64): flags + counts, [64, ...): the search's result arrays
 };
 
 namespace {
@@ -135,9 +153,13 @@ int upload_queries(fbe_matcher* m, const std::vector<float4>& q, const std::vect
     return FBE_OK;
 }
 
-// rows + sequential resolve with automatic growth of the per-query row capacity
-template <class Setup>
-int rows_and_resolve(fbe_matcher* m, const FrameDev& tf, const QueryDev& qs, int nq, int nt, bool incl, ResolveArgs a, Setup&& before_resolve) {
+// rows + sequential resolve with automatic growth of the per-query row capacity.  before_resolve(attempt) restores the state the
+// resolve kernel modifies (a retry must start from the caller's data again); enqueue_results() queues the device->host copies of
+// the search's outputs into m->hres behind the resolve kernel, so that one synchronise serves flags, counts and results.
+template <class Setup, class Results>
+int rows_and_resolve(fbe_matcher* m, const FrameDev& tf, const QueryDev& qs, int nq, bool incl, ResolveArgs a, Setup&& before_resolve,
+                     Results&& enqueue_results) {
+    FBE_TRY(m->hres.ensure(64));
     for (int attempt = 0; attempt < 8; ++attempt) {
         const int C = m->row_cap;
         FBE_TRY(m->rows.ensure((size_t)std::max(nq, 1) * C * 4));
@@ -145,15 +167,15 @@ int rows_and_resolve(fbe_matcher* m, const FrameDev& tf, const QueryDev& qs, int
         FBE_TRY(m->misc.ensure(64));
         FBE_CUDA(cudaMemsetAsync(m->misc.p, 0, 64, m->stream));
         FBE_TRY(launch_window_rows(tf, qs, 1, nq, incl, C, m->rows.as<unsigned>(), m->cnt.as<int>(), m->misc.as<int>(), m->stream));
-        FBE_TRY(before_resolve());
+        FBE_TRY(before_resolve(attempt));
         a.C = C; a.rows = m->rows.as<unsigned>(); a.cnt = m->cnt.as<int>();
         a.nq = qs.nq; a.q_stride = qs.stride; a.t_stride = tf.kp_stride; a.nt = tf.n; a.t_kps = tf.kps;
         a.nmatches = m->misc.as<int>() + 1;
-        (void)nt;
         FBE_TRY(launch_resolve(a, 1, m->stream));
-        int h[2] = {0, 0};
-        FBE_CUDA(cudaMemcpyAsync(h, m->misc.p, 8, cudaMemcpyDeviceToHost, m->stream));
+        FBE_TRY(enqueue_results());
+        FBE_CUDA(cudaMemcpyAsync(m->hres.p, m->misc.p, 8, cudaMemcpyDeviceToHost, m->stream));
         FBE_CUDA(cudaStreamSynchronize(m->stream));
+        const int* h = reinterpret_cast<const int*>(m->hres.p);
         if (!h[0]) return h[1];           // >= 0 : nmatches
         m->row_cap *= 2;                  // a window held more candidates than the row capacity: redo, larger
     }
@@ -185,6 +207,7 @@ int fbe_matcher_destroy(fbe_matcher* m) {
     cudaStreamSynchronize(m->stream);
     m->fa.release(); m->fb.release();
     for (CachedFrame& c : m->cache) c.b.release();
+    m->hres.release();
     for (DevBuf* b : {&m->q, &m->lv, &m->qdesc, &m->nq, &m->rows, &m->cnt, &m->misc, &m->i0, &m->i1, &m->i2, &m->i3, &m->i4, &m->u0, &m->u1, &m->f0, &m->partial}) b->release();
     cudaStreamDestroy(m->stream);
     delete m;
@@ -210,6 +233,7 @@ int fbe_search_for_initialization(fbe_matcher* m, const fbe_frame_view* f1, cons
     FBE_TRY(upload_frame(m, m->fb, f1, false, F1));
     FBE_TRY(upload_frame(m, m->fa, f2, true, F2));
     FBE_TRY(upload(m->f0, prev_matched, (size_t)n1 * 8, m->stream));
+    FBE_TRY(m->hres.ensure(64 + (size_t)n1 * 12));
     FBE_TRY(m->q.ensure((size_t)n1 * sizeof(float4)));
     FBE_TRY(m->lv.ensure((size_t)n1 * sizeof(int2)));
     FBE_TRY(launch_queries_from_kps(F1.kps, m->f0.as<float2>(), nullptr, F1.n, n1, 1, (float)window_size, m->q.as<float4>(),
@@ -222,15 +246,18 @@ int fbe_search_for_initialization(fbe_matcher* m, const fbe_frame_view* f1, cons
     a.nn_ratio = m->nn_ratio; a.check_ori = m->check_ori;
     a.matched_dist = m->i0.as<int>(); a.match21 = m->i1.as<int>(); a.matches12 = m->i2.as<int>();
     a.prev_matched = m->f0.as<float2>(); a.q_bin = m->i3.as<int>(); a.q_hit = m->i4.as<int>();
-    // a retry after a row overflow must start from the caller's vbPrevMatched again
-    int rc = rows_and_resolve(m, F2, qs, n1, n2, true, a, [&]() {
-        return upload(m->f0, prev_matched, (size_t)n1 * 8, m->stream);
-    });
+    // a retry after a row overflow must start from the caller's vbPrevMatched again (the first attempt still has the upload above)
+    int rc = rows_and_resolve(m, F2, qs, n1, true, a,
+        [&](int attempt) { return attempt ? upload(m->f0, prev_matched, (size_t)n1 * 8, m->stream) : FBE_OK; },
+        [&]() {
+            FBE_CUDA(cudaMemcpyAsync(m->hres.p + 64, m->i2.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, m->stream));
+            FBE_CUDA(cudaMemcpyAsync(m->hres.p + 64 + (size_t)n1 * 4, m->f0.p, (size_t)n1 * 8, cudaMemcpyDeviceToHost, m->stream));
+            return FBE_OK;
+        });
     if (rc < 0) return rc;
     *nmatches = rc;
-    FBE_CUDA(cudaMemcpyAsync(matches12, m->i2.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, m->stream));
-    FBE_CUDA(cudaMemcpyAsync(prev_matched, m->f0.p, (size_t)n1 * 8, cudaMemcpyDeviceToHost, m->stream));
-    FBE_CUDA(cudaStreamSynchronize(m->stream));
+    std::memcpy(matches12, m->hres.p + 64, (size_t)n1 * 4);
+    std::memcpy(prev_matched, m->hres.p + 64 + (size_t)n1 * 4, (size_t)n1 * 8);
     return FBE_OK;
 }
 
@@ -320,12 +347,16 @@ static int projection_search(fbe_matcher* m, int mode, const fbe_frame_view* cur
     a.cur_mp = m->i0.as<int>(); a.q_bin = m->i3.as<int>(); a.q_hit = m->i4.as<int>();
     FBE_TRY(m->u0.ensure((size_t)nt));
     a.taken = m->u0.as<uint8_t>();
-    int rc = rows_and_resolve(m, Cf, qs, nq, nt, true, a, [&]() {
-        return upload(m->u0, taken.data(), (size_t)nt, m->stream);      // fresh `taken` state on every attempt
-    });
+    FBE_TRY(m->hres.ensure(64 + (size_t)nt * 4));
+    int rc = rows_and_resolve(m, Cf, qs, nq, true, a,
+        [&](int) { return upload(m->u0, taken.data(), (size_t)nt, m->stream); },      // fresh `taken` state on every attempt
+        [&]() {
+            FBE_CUDA(cudaMemcpyAsync(m->hres.p + 64, m->i0.p, (size_t)nt * 4, cudaMemcpyDeviceToHost, m->stream));
+            return FBE_OK;
+        });
     if (rc < 0) return rc;
     *nmatches = rc;
-    FBE_CUDA(cudaMemcpy(cur_mp, m->i0.p, (size_t)nt * 4, cudaMemcpyDeviceToHost));
+    std::memcpy(cur_mp, m->hres.p + 64, (size_t)nt * 4);
     return FBE_OK;
 }
 
