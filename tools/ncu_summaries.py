@@ -63,6 +63,6 @@ def stage(path):
 
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
-        launches(sys.argv[2], int(sys.argv[3]))
+        launches(sys.argv[2], float(sys.argv[3]))
     else:
         stage(sys.argv[2])
