@@ -453,10 +453,30 @@ __global__ void __launch_bounds__(kOctThreads, 3) k_octree(const Plan* __restric
         nk += tot;
     }
     __syncthreads();
-    for (int c = tid >> 5; c < ncells; c += kOctThreads / 32) {
-        const int cnt = ccount[c], off = (int)knode[c];
-        const uint32_t* src = slots + (size_t)c * g.cell_cap;
-        for (int i = tid & 31; i < cnt; i += 32) keys[off + i] = src[i];
+    {
+        // four cells per warp per pass; count, offset and the first 32 slots of each are loaded before any of them is used (a slot
+        // beyond the count holds stale keys, never out-of-bounds memory), so a pass costs one global-memory latency, not two per cell
+        const int lane = tid & 31, wid = tid >> 5;
+        const bool lane_in_cap = lane < g.cell_cap;
+        for (int c0 = wid * 4; c0 < ncells; c0 += (kOctThreads / 32) * 4) {
+            int cnt[4], off[4];
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = min(c0 + u, ncells - 1);
+                cnt[u] = c0 + u < ncells ? ccount[c] : 0;
+                off[u] = (int)knode[c];
+                v[u] = lane_in_cap ? slots[(size_t)c * g.cell_cap + lane] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (lane < cnt[u]) keys[off[u] + lane] = v[u];
+                if (cnt[u] > 32) {
+                    const uint32_t* src = slots + (size_t)(c0 + u) * g.cell_cap;
+                    for (int i = lane + 32; i < cnt[u]; i += 32) keys[off[u] + i] = src[i];
+                }
+            }
+        }
     }
     __syncthreads();
 
