@@ -8,7 +8,7 @@
 
 namespace fbe {
 
-constexpr int kGridThreads = 256;
+constexpr int kGridThreads = 1024;
 
 __global__ void __launch_bounds__(kGridThreads) k_grid_build(const fbe_keypoint* __restrict__ kps, const int* __restrict__ n_arr,
                                                              int stride, float min_x, float min_y, float inv_w, float inv_h,
