@@ -95,11 +95,14 @@ class BirdORB:
         return self.features_batch(img, mask, contour)[0]
 
 
-def retain_best(response: np.ndarray, n_points: int, device: int = 0):
-    """Parity-test tap: KeyPointsFilter::retainBest replayed on the device -> (order [n], number kept)."""
+def retain_best(response: np.ndarray, n_points: int, device: int = 0, with_flag: bool = False):
+    """Parity-test tap: KeyPointsFilter::retainBest replayed on the device -> (order [n], number kept[, heap select used])."""
     L = _lib.load()
     r = np.ascontiguousarray(response, np.float32)
     order = np.zeros(max(len(r), 1), np.int32)
     kept = C.c_int32()
-    check(L.fbe_debug_retain_best(ptr(r), len(r), int(n_points), int(device), ptr(order), C.byref(kept)))
+    heap = C.c_int32()
+    check(L.fbe_debug_retain_best(ptr(r), len(r), int(n_points), int(device), ptr(order), C.byref(kept), C.byref(heap)))
+    if with_flag:
+        return order[:len(r)], kept.value, bool(heap.value)
     return order[:len(r)], kept.value

@@ -18,7 +18,9 @@
 //                                   (and so every downstream index of the reference) inherits.  A Hoare partition pass is
 //                                   order-equivalent to: swap the k-th element from the left that stops the left scan with the
 //                                   k-th from the right that stops the right scan, for all k while left < right -- two scans
-//                                   and one scatter per pass instead of a pointer chase.
+//                                   and one scatter per pass instead of a pointer chase.  When introselect runs out of its depth
+//                                   budget (adversarial inputs only) libstdc++ finishes with __heap_select + iter_swap; that exit
+//                                   is replayed as well, serially (tests/test_gpu_bird_orb.py drives it with McIlroy's adversary).
 //   k_borb_harris                   HarrisResponses (7x7 block of Sobel-like sums, fp32 formula without contraction).
 //   k_borb_finish                   second retainBest result -> ICAngles (integer moments, fastAtan2) -> keypoint records.
 //   k_borb_prefilter                compute(): runByImageBorder on the rounded positions + regrouping by octave when unsorted.
@@ -316,15 +318,72 @@ __device__ int swap_pairs(float* key, int* idx, int* lpos, int* rpos, int lo, in
     return K;
 }
 
-// retainBest(keys, n_points) on key[0..n) (comparison: larger response first) with payload idx; returns the number kept, -1 when
-// introselect's depth limit was reached (libstdc++ then switches to heap select, which is not replayed: reported, never guessed)
-__device__ int retain_best_cta(float* key, int* idx, int* lpos, int* rpos, int n, int n_points, int* s) {
+// libstdc++'s heap algorithms on (key, idx) pairs with comp(a, b) = a.key > b.key, as one thread (bits/stl_heap.h: __adjust_heap with
+// its trailing __push_heap, __make_heap, __pop_heap, __heap_select).  Only reached when introselect runs out of its depth budget,
+// which takes an adversarial input; the replay is serial like the original.
+__device__ void adjust_heap_serial(float* key, int* idx, int hole, int len, float vk, int vi) {
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (key[child] > key[child - 1]) --child;
+        key[hole] = key[child]; idx[hole] = idx[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        key[hole] = key[child - 1]; idx[hole] = idx[child - 1];
+        hole = child - 1;
+    }
+    int parent = (hole - 1) / 2;
+    while (hole > top && key[parent] > vk) {
+        key[hole] = key[parent]; idx[hole] = idx[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    key[hole] = vk; idx[hole] = vi;
+}
+
+// std::__heap_select(first, middle, last, greater) followed by std::iter_swap(first, nth) -- the depth-limit exit of std::__introselect
+__device__ void heap_select_serial(float* key, int* idx, int first, int middle, int last, int nth) {
+    float* k = key + first;
+    int* x = idx + first;
+    const int len = middle - first;
+    if (len >= 2) {
+        for (int parent = (len - 2) / 2;; --parent) {
+            adjust_heap_serial(k, x, parent, len, k[parent], x[parent]);
+            if (parent == 0) break;
+        }
+    }
+    for (int i = middle; i < last; ++i) {
+        if (key[i] > k[0]) {
+            const float vk = key[i];
+            const int vi = idx[i];
+            key[i] = k[0]; idx[i] = x[0];
+            adjust_heap_serial(k, x, 0, len, vk, vi);
+        }
+    }
+    const float tk = key[first]; key[first] = key[nth]; key[nth] = tk;
+    const int ti = idx[first]; idx[first] = idx[nth]; idx[nth] = ti;
+}
+
+// retainBest(keys, n_points) on key[0..n) (comparison: larger response first) with payload idx; returns the number kept.
+// *heap_used (optional) is set when introselect's depth limit was reached and libstdc++'s heap select had to be replayed.
+__device__ int retain_best_cta(float* key, int* idx, int* lpos, int* rpos, int n, int n_points, int* s, int* heap_used = nullptr) {
     if (n_points < 0 || n <= n_points) return n;
     if (n_points == 0) return 0;
     const int tid = threadIdx.x, nth = n_points - 1;
     int first = 0, last = n, depth = 2 * (31 - __clz(n));
+    bool sorted_tail = true;
     while (last - first > 3) {
-        if (depth == 0) return -1;
+        if (depth == 0) {
+            if (tid == 0) {
+                heap_select_serial(key, idx, first, nth + 1, last, nth);
+                if (heap_used) *heap_used = 1;
+            }
+            sorted_tail = false;                                 // std::__introselect returns here, without the insertion sort
+            break;
+        }
         --depth;
         if (tid == 0) {                                          // std::__move_median_to_first(first, first + 1, mid, last - 1), comp = greater
             const int a = first + 1, b = first + (last - first) / 2, c = last - 1;
@@ -347,7 +406,7 @@ __device__ int retain_best_cta(float* key, int* idx, int* lpos, int* rpos, int n
         if (cut <= nth) first = cut; else last = cut;
         __syncthreads();
     }
-    if (tid == 0) {                                              // std::__insertion_sort(first, last), at most 3 elements
+    if (tid == 0 && sorted_tail) {                               // std::__insertion_sort(first, last), at most 3 elements
         for (int i = first + 1; i < last; ++i) {
             const float v = key[i];
             const int vi = idx[i];
@@ -384,7 +443,7 @@ __global__ void __launch_bounds__(kBorbThreads) k_borb_retain(const BorbPlan* __
     const int kept = retain_best_cta(key + base, idx + base, lpos + base, rpos + base, n, stage == 0 ? 2 * g.nfeat : g.nfeat, s);
     if (tid == 0) {
         n_out[b * kBorbLevels + l] = kept < 0 ? 0 : kept;
-        if (kept < 0) atomicExch(err, 1);
+        if (kept < 0) atomicExch(err, 1);                        // partition found no cut: cannot happen, reported rather than trusted
     }
 }
 
@@ -392,9 +451,10 @@ __global__ void __launch_bounds__(kBorbThreads) k_borb_retain(const BorbPlan* __
 __global__ void __launch_bounds__(kBorbThreads) k_borb_retain_debug(float* key, int* idx, int* lpos, int* rpos, int n, int n_points, int* n_out) {
     __shared__ int s[kBorbThreads / 32];
     for (int i = threadIdx.x; i < n; i += kBorbThreads) idx[i] = i;
+    if (threadIdx.x == 0) n_out[1] = 0;
     __syncthreads();
-    const int kept = retain_best_cta(key, idx, lpos, rpos, n, n_points, s);
-    if (threadIdx.x == 0) *n_out = kept;
+    const int kept = retain_best_cta(key, idx, lpos, rpos, n, n_points, s, n_out + 1);
+    if (threadIdx.x == 0) n_out[0] = kept;
 }
 
 // HarrisResponses of the keypoints kept by the first retainBest, in their kept order
@@ -749,7 +809,7 @@ int check_err(fbe_bird_orb* h) {
     FBE_CUDA(cudaMemcpyAsync(&e, h->err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     FBE_CUDA(cudaStreamSynchronize(h->stream));
     if (e) FBE_CUDA(cudaMemsetAsync(h->err, 0, sizeof(int), h->stream));
-    if (e == 1) { set_error("retainBest: introselect reached its depth limit (heap-select fallback of std::nth_element is not replayed)"); return FBE_E_UNSUPPORTED; }
+    if (e == 1) { set_error("retainBest: a partition pass of the introselect replay found no cut (internal error)"); return FBE_E_UNSUPPORTED; }
     if (e == 2) { set_error("more keypoints than the output capacity (ties of the n-th best response are all kept)"); return FBE_E_CAPACITY; }
     if (e == 3) { set_error("keypoint octave outside 0 .. 7"); return FBE_E_INVALID; }
     return FBE_OK;
@@ -843,19 +903,23 @@ int fbe_bird_orb_max_keypoints(const fbe_bird_orb* h, int32_t* cap) {
     return FBE_OK;
 }
 
-int fbe_debug_retain_best(const float* response, int32_t n, int32_t n_points, int32_t device, int32_t* order, int32_t* n_kept) {
+int fbe_debug_retain_best(const float* response, int32_t n, int32_t n_points, int32_t device, int32_t* order, int32_t* n_kept,
+                          int32_t* heap_select_used) {
     if (!response || !order || !n_kept || n < 0) return FBE_E_INVALID;
     FBE_CUDA(cudaSetDevice(device));
     float* key = nullptr; int *idx = nullptr, *lp = nullptr, *rp = nullptr, *no = nullptr;
     const size_t nn = (size_t)std::max(n, 1);
     int rc = FBE_OK;
     if (cudaMalloc(&key, nn * 4) != cudaSuccess || cudaMalloc(&idx, nn * 4) != cudaSuccess || cudaMalloc(&lp, nn * 4) != cudaSuccess ||
-        cudaMalloc(&rp, nn * 4) != cudaSuccess || cudaMalloc(&no, 4) != cudaSuccess) { set_error("allocation failed"); rc = FBE_E_CUDA; }
+        cudaMalloc(&rp, nn * 4) != cudaSuccess || cudaMalloc(&no, 8) != cudaSuccess) { set_error("allocation failed"); rc = FBE_E_CUDA; }
     if (rc == FBE_OK) {
         cudaMemcpy(key, response, (size_t)n * 4, cudaMemcpyHostToDevice);
         k_borb_retain_debug<<<1, kBorbThreads>>>(key, idx, lp, rp, n, n_points, no);
         count_launch();
-        cudaMemcpy(n_kept, no, 4, cudaMemcpyDeviceToHost);
+        int h_no[2] = {0, 0};
+        cudaMemcpy(h_no, no, 8, cudaMemcpyDeviceToHost);
+        *n_kept = h_no[0];
+        if (heap_select_used) *heap_select_used = h_no[1];
         if (cudaMemcpy(order, idx, (size_t)n * 4, cudaMemcpyDeviceToHost) != cudaSuccess || cudaGetLastError() != cudaSuccess) { set_error("retain_best debug run failed"); rc = FBE_E_CUDA; }
     }
     cudaFree(key); cudaFree(idx); cudaFree(lp); cudaFree(rp); cudaFree(no);

@@ -236,12 +236,14 @@ FBE_API int fbe_bird_orb_destroy(fbe_bird_orb* h);
 FBE_API int fbe_bird_orb_max_keypoints(const fbe_bird_orb* h, int32_t* cap);
 /* detect(): imgs / masks = nframes 8-bit images `stride` bytes apart with rows of `step` bytes (masks may be NULL; any non-zero
  * mask value keeps a keypoint, on every level, as in OpenCV 4.13).  kps [nframes][cap], n [nframes].
- * FBE_E_CAPACITY when response ties make a frame exceed cap; FBE_E_UNSUPPORTED when std::nth_element's heap-select fallback
- * would be needed (never observed; reported instead of guessed). */
+ * FBE_E_CAPACITY when response ties make a frame exceed cap.  std::nth_element's heap-select fallback (introselect out of its
+ * depth budget: adversarial inputs only) is replayed too, serially. */
 /* parity-test tap: KeyPointsFilter::retainBest (std::nth_element + std::partition, larger response first) replayed on the device
  * for an arbitrary response array -> order[n] = the permutation the algorithms leave behind (indices into `response`), of
- * which the first *n_kept survive (-1: the heap-select fallback would have been needed). */
-FBE_API int fbe_debug_retain_best(const float* response, int32_t n, int32_t n_points, int32_t device, int32_t* order, int32_t* n_kept);
+ * which the first *n_kept survive; *heap_select_used (may be NULL) = 1 when introselect hit its depth limit and libstdc++'s
+ * heap select was replayed. */
+FBE_API int fbe_debug_retain_best(const float* response, int32_t n, int32_t n_points, int32_t device, int32_t* order, int32_t* n_kept,
+                          int32_t* heap_select_used);
 FBE_API int fbe_bird_orb_detect(fbe_bird_orb* h, const uint8_t* imgs, size_t step, size_t stride, const uint8_t* masks, size_t mask_step,
                                 size_t mask_stride, int32_t nframes, fbe_keypoint* kps, int32_t* n);
 /* compute(): kps [nframes][cap] / n [nframes] in and out (keypoints within 31 px of the image border are removed, an unsorted

@@ -266,6 +266,29 @@ void orc_resize_linear_exact_u8(const uint8_t* src, int sw, int sh, int sstep, u
     resize_linear_exact_u8(src, sw, sh, (size_t)sstep, dst, dw, dh, (size_t)dstep);
 }
 
+// An input on which std::nth_element(first, first + nth, last, ResponseGreater) of THIS libstdc++ runs out of its introselect depth
+// budget and falls back to heap select: McIlroy's adversary ("A Killer Adversary for Quicksort", 1999) answers the comparisons
+// of a real std::nth_element run so that every pivot is extreme, fixing the values as late as possible; the responses it leaves
+// are distinct and consistent with every answer given, so a replay on them makes the same comparisons.  Returns the number of
+// comparisons of the adversarial run (diagnostic).
+int orc_antiselect(int n, int nth, float* response) {
+    std::vector<int> val(n, n);                 // n = "gas": not fixed yet, compares after every fixed value
+    int nsolid = 0, candidate = 0;
+    long ncmp = 0;
+    std::vector<int> p(n);
+    for (int i = 0; i < n; ++i) p[i] = i;
+    auto precedes = [&](int x, int y) {         // plays the role of ResponseGreater: true <=> x has the larger response
+        ++ncmp;
+        if (val[x] == n && val[y] == n) { if (x == candidate) val[x] = nsolid++; else val[y] = nsolid++; }
+        if (val[x] == n) candidate = x; else if (val[y] == n) candidate = y;
+        return val[x] < val[y];
+    };
+    if (n > 0) std::nth_element(p.begin(), p.begin() + std::min(std::max(nth, 0), n - 1), p.end(), precedes);
+    for (int i = 0; i < n; ++i) if (val[i] == n) val[i] = nsolid++;
+    for (int i = 0; i < n; ++i) response[i] = (float)(n - val[i]);       // earlier in the order = larger response; exact below 2^24
+    return (int)std::min<long>(ncmp, 0x7fffffff);
+}
+
 // KeyPointsFilter::retainBest on a bare response array: order[n] = the permutation std::nth_element + std::partition leave behind,
 // returns the number kept
 int orc_retain_best(const float* response, int n, int n_points, int32_t* order) {

@@ -552,6 +552,14 @@ def retain_best(response, n_points):
     return order[:len(r)], kept
 
 
+def antiselect(n, nth):
+    """Responses on which this libstdc++'s std::nth_element(.., nth, .., greater) exhausts introselect's depth budget and falls back
+    to heap select (McIlroy's adversary run against the real algorithm, oracle/cvorb_oracle.cpp)."""
+    out = np.zeros(max(n, 1), np.float32)
+    lib().orc_antiselect(int(n), int(nth), _p(out))
+    return out[:n]
+
+
 def cvorb_blur(img):
     """The GaussianBlur cv::ORB applies to a pyramid level (float sepFilter2D path with FMA, see oracle/cvorb_oracle.cpp)."""
     img = np.ascontiguousarray(img, np.uint8)

@@ -38,6 +38,26 @@ def test_retain_best_replay_equals_std_algorithms(oracle):
             assert np.array_equal(go[:gk], oo[:ok]), (n, k)
 
 
+def test_retain_best_heap_select_fallback(oracle):
+    """Adversarial responses (McIlroy's adversary played against the oracle side's real std::nth_element) drive introselect past
+    its depth budget: libstdc++ then finishes with __heap_select + iter_swap, and so does the device replay -- same permutation."""
+    from fishbirdeyevisualslam_b200.bird_orb import retain_best
+    hit = 0
+    for n in (200, 1000, 5000, 20000):
+        for k in (n // 2, n // 3, (2 * n) // 3):
+            r = oracle.antiselect(n, k - 1)
+            assert len(np.unique(r)) == n
+            oo, ok = oracle.retain_best(r, k)
+            go, gk, heap = retain_best(r, k, with_flag=True)
+            hit += heap
+            assert gk == ok == k, (n, k)
+            assert np.array_equal(go[:gk], oo[:ok]), (n, k)
+            assert np.array_equal(go, oo), (n, k)               # the discarded tail is the same permutation as well
+    assert hit >= 8                                            # the inputs do reach the fallback
+    r = np.random.default_rng(1).random(5000).astype(np.float32)
+    assert retain_best(r, 2500, with_flag=True)[2] is False    # ordinary inputs never do
+
+
 @pytest.mark.parametrize("i", range(6))
 def test_detect_equals_oracle(oracle, i):
     from fishbirdeyevisualslam_b200.bird_orb import BirdORB
