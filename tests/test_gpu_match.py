@@ -311,6 +311,58 @@ def test_random_scenes_all_matchers(oracle, seed):
     assert n_g == n_o and np.array_equal(d_g, d_o)
 
 
+@pytest.mark.parametrize("kind", ["ties", "steals"])
+@pytest.mark.parametrize("seed", range(4))
+def test_resolve_under_contention(oracle, seed, kind):
+    """The sequential accept / steal chain is replayed in speculative waves of 16 queries (csrc/match.cu: k_resolve); this is the
+    input that makes the speculation fail as often as possible: many octave-0 queries packed into one window, few targets,
+    descriptors drawn from a handful of prototypes a few bits apart ("ties": queries of one wave keep choosing the same best / second
+    best target and distances tie) or every target its own prototype with ~17 noisy copies among the queries ("steals": nearly every
+    query is accepted, targets are stolen again and again, and a wave of 16 queries over 40-115 targets collides all the time).
+    Every search mode that goes through k_resolve."""
+    from fishbirdeyevisualslam_b200.matcher import Frame, ORBmatcher
+    rng = np.random.default_rng(500 + seed)
+    nproto, n1, n2 = 6, 700, 40 + 25 * seed
+    if kind == "ties":
+        proto = rng.integers(0, 256, (nproto, 32), dtype=np.uint8)
+        d1 = flip_bits(rng, proto[rng.integers(0, nproto, n1)], 3)
+        d2 = flip_bits(rng, proto[rng.integers(0, nproto, n2)], 2)
+    else:
+        d2 = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+        src = d2[rng.integers(0, n2, n1)]
+        d1 = np.concatenate([flip_bits(rng, src[:200], 20), flip_bits(rng, src[200:450], 8), flip_bits(rng, src[450:], 2)])
+        d1 = d1[rng.permutation(n1)]
+    x1 = rng.uniform(300, 340, n1).astype(np.float32); y1 = rng.uniform(220, 260, n1).astype(np.float32)
+    x2 = rng.uniform(300, 340, n2).astype(np.float32); y2 = rng.uniform(220, 260, n2).astype(np.float32)
+    sf = (1.2 ** np.arange(8)).astype(np.float32)
+    a1 = rng.choice([10.0, 40.0, 200.0], n1).astype(np.float32); a2 = rng.choice([10.0, 40.0, 200.0], n2).astype(np.float32)
+    F1 = Frame.front(make_kps(x1, y1, np.zeros(n1, np.int32), a1), d1, 640, 480, sf)
+    F2 = Frame.front(make_kps(x2, y2, np.zeros(n2, np.int32), a2), d2, 640, 480, sf)
+    for ratio, ori in [(0.9, True), (0.9, False), (1.0, False), (0.6, True)]:
+        pm_g = np.ascontiguousarray(np.stack([x1, y1], 1), np.float32)
+        pm_o = pm_g.copy()
+        n_g, m_g = ORBmatcher(ratio, ori).SearchForInitialization(F1, F2, pm_g, 100)
+        n_o, m_o = oracle.search_for_initialization(F1, F2, pm_o, 100, ratio, ori)
+        assert n_g == n_o and np.array_equal(m_g, m_o) and np.array_equal(pm_g, pm_o), (ratio, ori)
+    assert n_o > (0 if kind == "ties" else n2 // 2)
+    # last-frame projection search: `taken` grows with every accept (has_obs) or never (no obs: later queries overwrite earlier ones)
+    proj = np.stack([x1, y1], 1).astype(np.float32)
+    obs = (rng.random(n1) < 0.5).astype(np.uint8)
+    for th, ori, ho in [(30, True, None), (30, False, obs), (30, True, np.zeros(n1, np.uint8))]:
+        n_g, c_g = ORBmatcher(0.9, ori).SearchByProjectionLast(F2, F1.kps, proj, d1, th, last_has_obs=ho)
+        n_o, c_o = oracle.search_by_projection_last(F2, F1.kps, proj, d1, sf, th, ori, last_has_obs=ho)
+        assert n_g == n_o and np.array_equal(c_g, c_o), (th, ori)
+    # map-point projection search: the second-best candidate's LEVEL enters the ratio gate
+    lv2 = rng.integers(0, 3, n2).astype(np.int32)
+    F2l = Frame.front(make_kps(x2, y2, lv2, a2), d2, 640, 480, sf)
+    mlevel = rng.integers(0, 3, n1).astype(np.int32)
+    mcos = rng.uniform(0.99, 1.0, n1).astype(np.float32)
+    for th, ratio in [(5.0, 0.8), (5.0, 0.95), (3.0, 0.6)]:
+        n_g, c_g = ORBmatcher(ratio, True).SearchByProjectionMap(F2l, proj, mlevel, mcos, d1, th)
+        n_o, c_o = oracle.search_by_projection_map(F2l, sf, proj, mlevel, mcos, d1, th, ratio)
+        assert n_g == n_o and np.array_equal(c_g, c_o), (th, ratio)
+
+
 def test_quirk_cases_on_device(oracle):
     from fishbirdeyevisualslam_b200.matcher import Frame, ORBmatcher
     rng = np.random.default_rng(0)
