@@ -124,3 +124,20 @@ def test_live_cv2_primitives(oracle):
     img = synth.frame(384, 384, 9)
     kern = cv2.getGaussianKernel(7, 2, cv2.CV_32F)
     assert np.array_equal(oracle.cvorb_blur(img), cv2.sepFilter2D(img, cv2.CV_8U, kern, kern, borderType=cv2.BORDER_REFLECT_101))
+
+
+def test_retain_best_and_its_adversary(oracle):
+    """oracle.retain_best (the real std::nth_element + std::partition) keeps exactly the k largest responses plus the ties of the
+    k-th, on ordinary inputs and on the adversarial ones of oracle.antiselect (which exist to drive the GPU replay into introselect's
+    heap-select exit: tests/test_gpu_bird_orb.py); the adversary's output is a permutation-valued response array."""
+    rng = np.random.default_rng(3)
+    for n in (50, 1000, 5000):
+        for r in (rng.random(n).astype(np.float32), rng.integers(0, 8, n).astype(np.float32), oracle.antiselect(n, n // 2 - 1)):
+            k = n // 2
+            order, kept = oracle.retain_best(r, k)
+            assert sorted(order.tolist()) == list(range(n))
+            kth = np.sort(r)[::-1][k - 1]
+            assert kept == int((r >= kth).sum())
+            assert set(order[:kept].tolist()) == set(np.nonzero(r >= kth)[0].tolist())
+    a = oracle.antiselect(2000, 999)
+    assert sorted(a.tolist()) == [float(v) for v in range(1, 2001)]
