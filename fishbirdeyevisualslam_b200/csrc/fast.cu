@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast_cells(const Plan* __re
         uint4* z = reinterpret_cast<uint4*>(sc);
         for (int i = tid; i < (L.sc_bytes >> 4); i += kFastThreads) z[i] = make_uint4(0, 0, 0, 0);
         for (int i = tid; i < L.mask_words; i += kFastThreads) mask[i] = 0u;
+        const unsigned wrecip = (unsigned)g.wcell_recip;
         for (int x = tid; x < gw; x += kFastThreads) {
-            xinfo[x] = (uint8_t)(x / wcell);                       // cell index of the strip column
+            xinfo[x] = (uint8_t)(((unsigned)x * wrecip) >> 16);    // cell index of the strip column = x / wcell (exact: x < 256, wcell >= 30)
         }
     }
     mbar_wait(&bar, 0);
@@ -181,11 +182,9 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast_cells(const Plan* __re
                                                  __byte_perm(rt1, 0, 0x4342), __byte_perm(lf1, 0, 0x4342), k2);
                 q = (p0 >> 15) | (p1 >> 13) | (p2 >> 11) | (p3 >> 9);
                 if (xs < 0 || xs + 7 >= gw) {                    // first / last octet: drop the pixels outside the strip
-                    unsigned keep = 0;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if ((unsigned)(xs + k) < (unsigned)gw) keep |= 1u << ((k & 1) * 16 + (k >> 1) * 2);
-                    q &= keep;
+                    // pixels k in [max(0, -xs), min(8, gw - xs)) stay; their pass bits sit at k (even k) and 15 + k (odd k)
+                    const unsigned m8 = (0xFFu >> (8 - min(8, gw - xs))) & (0xFFu << max(0, -xs));
+                    q &= (m8 & 0x55u) | ((m8 & 0xAAu) << 15);
                 }
             }
             // append the passing pixels of all lanes: one popcount per lane, warp scan by shuffles, predicated stores

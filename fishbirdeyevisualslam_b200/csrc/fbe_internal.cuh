@@ -33,6 +33,7 @@ struct LevelGeom {
     int img_off;         // byte offset of the padded level inside the per-slot pyramid slab (256-aligned)
     int ncols, nrows;    // FAST cell grid (src/ORBextractor.cc:781-787)
     int wcell, hcell;
+    int wcell_recip;     // 65536 / wcell + 1: x / wcell == (x * wcell_recip) >> 16 for x < 256 (wcell in 30 .. 64)
     int cell_base;       // first cell of this level in the per-slot cell arrays
     int cell_cap;        // candidate slots per cell = ceil(wcell/2)*ceil(hcell/2) (NMS survivors are never adjacent)
     int gcells;          // FAST kernel: cells per CTA group (consecutive cells of one cell row, group width <= 256 px)

@@ -111,6 +111,7 @@ int build_plan(const fbe_extractor_cfg& cfg, const std::vector<float>& scale, co
         g.ncols = ncols; g.nrows = nrows;
         g.wcell = (int)ceilf(width / ncols);
         g.hcell = (int)ceilf(height / nrows);
+        g.wcell_recip = 65536 / g.wcell + 1;
         g.cell_base = cell_base;
         g.cell_cap = ((g.wcell + 1) / 2) * ((g.hcell + 1) / 2);
         g.slot_base = slot_base;
