@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast_cells(const Plan* __re
     {
         uint4* z = reinterpret_cast<uint4*>(sc);
         for (int i = tid; i < (L.sc_bytes >> 4); i += kFastThreads) z[i] = make_uint4(0, 0, 0, 0);
-        for (int i = tid; i < L.mask_words; i += kFastThreads) mask[i] = 0u;
+        uint4* zm = reinterpret_cast<uint4*>(mask);             // mask_words is a multiple of 4 and the array is 16-byte aligned
+        for (int i = tid; i < (L.mask_words >> 2); i += kFastThreads) zm[i] = make_uint4(0, 0, 0, 0);
         const unsigned wrecip = (unsigned)g.wcell_recip;
         for (int x = tid; x < gw; x += kFastThreads) {
             xinfo[x] = (uint8_t)(((unsigned)x * wrecip) >> 16);    // cell index of the strip column = x / wcell (exact: x < 256, wcell >= 30)
@@ -279,8 +280,9 @@ __global__ void __launch_bounds__(kFastThreads, 4) k_fast_cells(const Plan* __re
         if (r1 < ch) { a1 = ml[r1 * 2] | ((unsigned long long)ml[r1 * 2 + 1] << 32); b1 = mi[r1 * 2] | ((unsigned long long)mi[r1 * 2 + 1] << 32); }
         if (__any_sync(0xffffffffu, (b0 | b1) != 0ull)) { a0 = b0; a1 = b1; }
         const int c0 = __popcll(a0), c1 = __popcll(a1);
-        const int s0 = warp_incl_scan(c0, lane), s1 = warp_incl_scan(c1, lane);
-        const int tot0 = __shfl_sync(0xffffffffu, s0, 31), tot1 = __shfl_sync(0xffffffffu, s1, 31);
+        const int s01 = warp_incl_scan(c0 | (c1 << 16), lane);          // both row halves in one scan (a cell holds < 2^16 survivors)
+        const int t01 = __shfl_sync(0xffffffffu, s01, 31);
+        const int s0 = s01 & 0xFFFF, s1 = s01 >> 16, tot0 = t01 & 0xFFFF, tot1 = t01 >> 16;
         int o0 = s0 - c0, o1 = tot0 + s1 - c1;
         uint32_t* slots = ws.slots + (size_t)b * plan->slots_total + g.slot_base + (size_t)(ci * ncols + cj0 + cj) * g.cell_cap;
         const int cx = cj * wcell;
