@@ -77,6 +77,9 @@ def load() -> C.CDLL:
         lib.fbe_extract_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_size_t, C.c_void_p,
                                           C.c_void_p, C.c_int32, C.c_void_p]
         lib.fbe_pyramid_level.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        lib.fbe_pyramid_geometry.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        lib.fbe_extract_pyramid.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_size_t, C.c_void_p, C.c_void_p,
+                                            C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.fbe_grid_assign.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.fbe_matcher_create.argtypes = [C.c_float, C.c_int32, C.c_int32, C.c_void_p]

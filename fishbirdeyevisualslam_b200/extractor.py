@@ -84,6 +84,26 @@ class ORBextractor:
         check(self._L.fbe_extract(self._h, ptr(image), rows, cols, image.strides[0], ptr(kps), ptr(desc), cap, C.byref(n)))
         return kps[:n.value].copy(), desc[:n.value].copy()
 
+    def extract_with_pyramid(self, image: np.ndarray):
+        """operator() as the reference runs it: keypoints, descriptors AND mvImagePyramid of the same image in one call
+        (fbe_extract_pyramid: the level copies ride behind detection).  Returns (keypoints, descriptors, [padded level images])."""
+        assert image.dtype == np.uint8 and image.ndim == 2
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        rows, cols = image.shape
+        cap = self.max_keypoints(rows, cols)
+        nl = self.GetLevels()
+        lr, lc = (C.c_int32 * nl)(), (C.c_int32 * nl)()
+        check(self._L.fbe_pyramid_geometry(self._h, rows, cols, lr, lc))
+        levels = [np.zeros((lr[l] + 38, lc[l] + 38), np.uint8) for l in range(nl)]
+        dst = (C.c_void_p * nl)(*[a.ctypes.data for a in levels])
+        steps = (C.c_size_t * nl)(*[a.strides[0] for a in levels])
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int32()
+        check(self._L.fbe_extract_pyramid(self._h, ptr(image), rows, cols, image.strides[0], ptr(kps), ptr(desc), cap, C.byref(n), dst, steps))
+        return kps[:n.value].copy(), desc[:n.value].copy(), levels
+
     def extract_batch(self, images):
         """List/array of equally sized u8 images -> list of (keypoints, descriptors)."""
         imgs = [np.ascontiguousarray(im, np.uint8) for im in images]

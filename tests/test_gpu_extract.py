@@ -57,6 +57,25 @@ def test_full_operator_and_stages(oracle, cfg):
     assert g.GetLevels() == nl
 
 
+def test_extract_with_pyramid_one_call(oracle):
+    """fbe_extract_pyramid (what the drop-in operator() calls): the same keypoints / descriptors as fbe_extract plus every
+    padded mvImagePyramid level, first on a fresh handle (the plan is built inside the call), then again with a new image
+    and a new image size on the same handle."""
+    from fishbirdeyevisualslam_b200.extractor import ORBextractor
+    g = ORBextractor(800, 1.2, 6, 15, 5)
+    for h, w, seed in ((240, 320, 5), (240, 320, 6), (300, 400, 7)):
+        img = synth.frame(h, w, seed)
+        o = oracle.OracleExtractor(800, 1.2, 6, 15, 5)
+        ko, do = o(img)
+        kg, dg, levels = g.extract_with_pyramid(img)
+        compare(kg, dg, ko, do, o.boundary)
+        assert len(levels) == 6
+        for l in range(6):
+            assert np.array_equal(levels[l], o.level_padded(l)), f"level {l}"
+        k2, d2 = g(img)
+        assert k2.tobytes() == kg.tobytes() and np.array_equal(d2, dg)
+
+
 def test_golden_reference_outputs(extract_golden):
     """CUDA path against outputs of the reference's own ORBextractor.cc (verbatim build), committed as fixtures."""
     from fishbirdeyevisualslam_b200.extractor import ORBextractor
