@@ -63,14 +63,40 @@ __device__ __forceinline__ int window_walk(const fbe_keypoint* __restrict__ kps,
     const int xe = incl ? cx1 + 1 : cx1, ye = incl ? cy1 + 1 : cy1;     // exclusive ends (bird: quirk Q2)
     int rank = 0;
     if (ye <= cy0) return 0;
-    for (int ix = cx0; ix < xe; ++ix) {
-        const int beg = start[ix * grows + cy0], end = start[ix * grows + ye];
-        for (int base = beg; base < end; base += 32) {
-            const int p = base + lane;
+    // The window's columns are FLATTENED into one candidate sequence: lane j fetches the item range of column cx0 + j (one
+    // load latency for all columns instead of one per column), a warp scan turns the range lengths into offsets, and the
+    // candidates are then taken 32 at a time across column boundaries -- traversal order (ix outer, iy inner, in-cell order)
+    // is the flattened order, and no lane idles because one column happens to hold five keypoints.
+    for (int cbase = cx0; cbase < xe; cbase += 32) {                 // 32 columns per pass (a window is rarely wider)
+        const int ix = cbase + lane;
+        int beg = 0, cnt = 0;
+        if (ix < xe) {
+            beg = start[ix * grows + cy0];
+            cnt = start[ix * grows + ye] - beg;
+        }
+        int inc = cnt;                                              // inclusive prefix of the range lengths
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        const int exc = inc - cnt;
+        for (int pbase = 0; pbase < total; pbase += 32) {
+            const int p = pbase + lane;
+            // column of candidate p = number of columns whose inclusive prefix is <= p (upper bound by bisection over the lanes)
+            int col = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, inc, col + step - 1);
+                if (v <= p) col += step;
+            }
+            col = min(col, 31);
+            const int cbeg = __shfl_sync(0xffffffffu, beg, col), cexc = __shfl_sync(0xffffffffu, exc, col);
             int idx = -1;
             bool pass = false;
-            if (p < end) {
-                idx = items[p];
+            if (p < total) {
+                idx = items[cbeg + (p - cexc)];
                 const fbe_keypoint* kp = kps + idx;
                 const int oct = kp->octave;
                 bool ok = true;
