@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kBorbThreads) k_borb_gather(const BorbPlan* __
                                                               float* __restrict__ cand_resp, int* __restrict__ cand_n) {
     const int l = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const BorbLevel& g = plan->lv[l];
-    __shared__ int off[512];
+    __shared__ int off[512], cnt[512];
     const int* bc = band_count + (size_t)b * plan->bands_total + g.band_off;
     if (tid < 32) {                                              // exclusive prefix of the band counts, 32 bands per step
         int carry = 0;
@@ -236,19 +236,22 @@ __global__ void __launch_bounds__(kBorbThreads) k_borb_gather(const BorbPlan* __
             int inc = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
-            if (c0 + tid < g.nbands) off[c0 + tid] = carry + inc - v;
+            if (c0 + tid < g.nbands) { off[c0 + tid] = carry + inc - v; cnt[c0 + tid] = v; }
             carry += __shfl_sync(0xffffffffu, inc, 31);
         }
         if (tid == 0) cand_n[b * kBorbLevels + l] = carry;
     }
     __syncthreads();
-    for (int i = 0; i < g.nbands; ++i) {
+    // one warp per band (counts and offsets come from shared memory, so the bands' loads are independent of each other)
+    uint32_t* oxy = cand_xy + (size_t)b * plan->cand_total + g.cand_off;
+    float* oresp = cand_resp + (size_t)b * plan->cand_total + g.cand_off;
+    for (int i = tid >> 5; i < g.nbands; i += kBorbThreads / 32) {
         const uint2* src = band_slots + (size_t)b * plan->band_slots_total + (size_t)(g.band_off + i) * plan->lv[0].band_cap;
-        const int n = bc[i];
-        for (int k = tid; k < n; k += kBorbThreads) {
+        const int n = cnt[i], o = off[i];
+        for (int k = tid & 31; k < n; k += 32) {
             const uint2 v = src[k];
-            cand_xy[(size_t)b * plan->cand_total + g.cand_off + off[i] + k] = v.x;
-            cand_resp[(size_t)b * plan->cand_total + g.cand_off + off[i] + k] = (float)v.y;
+            oxy[o + k] = v.x;
+            oresp[o + k] = (float)v.y;
         }
     }
 }
