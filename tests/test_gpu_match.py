@@ -311,6 +311,25 @@ def test_random_scenes_all_matchers(oracle, seed):
     assert n_g == n_o and np.array_equal(d_g, d_o)
 
 
+def test_window_wider_than_32_grid_columns(oracle):
+    """The window walk flattens the grid columns of a window 32 at a time (csrc/match.cu: window_walk); windows of 41-64 columns
+    need a second pass whose ranks continue the first pass's -- front (64 columns of 10 px) and bird (48 columns of 8 px) grids."""
+    from fishbirdeyevisualslam_b200.matcher import ORBmatcher
+    rng = np.random.default_rng(77)
+    F1, F2 = frame_pair(rng, 500)
+    for win in (200, 330, 700):
+        pm_g = np.ascontiguousarray(np.stack([F1.kps["x"], F1.kps["y"]], 1), np.float32)
+        pm_o = pm_g.copy()
+        n_g, m_g = ORBmatcher(0.9, True).SearchForInitialization(F1, F2, pm_g, win)
+        n_o, m_o = oracle.search_for_initialization(F1, F2, pm_o, win, 0.9, True)
+        assert n_g == n_o and np.array_equal(m_g, m_o) and np.array_equal(pm_g, pm_o), win
+    B1, B2 = frame_pair(rng, 500, 384, 384, bird=True)
+    for win in (150, 400):
+        n_g, d_g = ORBmatcher(0.9, True).BirdviewMatch(B2, B1.kps, B1.desc, win)
+        n_o, d_o = oracle.birdview_match(B1.kps, B1.desc, B2, win, 0.9, True)
+        assert n_g == n_o and np.array_equal(d_g, d_o), win
+
+
 @pytest.mark.parametrize("kind", ["ties", "steals"])
 @pytest.mark.parametrize("seed", range(4))
 def test_resolve_under_contention(oracle, seed, kind):
