@@ -22,7 +22,8 @@ __constant__ int8_t c_pattern[256 * 4] = {
 
 constexpr int kDescWarps = 8;        // keypoints per warp (kDescPerWarp) is a template parameter: 4 for batches, 1 when a call is latency-bound
 constexpr int kCoefRows = 37;         // 11 passes x 3 rows + the 5 idle lanes' reach, rows >= 31 hold zeros
-constexpr int kPatchR = 18, kPatchRows = 2 * kPatchR + 1, kPatchWords = 11;      // 37 rows x 44 bytes
+constexpr int kPatchR = 18, kPatchRows = 2 * kPatchR + 1, kPatchWords = 12;      // 37 rows x 44 bytes, stored with a pitch of 12 words:
+                                                                                 // the staging stores of 8 rows x 4 words then hit 32 distinct banks (pitch 11: 2-3 way conflicts)
 
 template <int kDescPerWarp>
 __global__ void __launch_bounds__(kDescWarps * 32, 8) k_describe(const Plan* __restrict__ plan, Workspace ws) {
