@@ -181,7 +181,18 @@ int build_plan(const fbe_extractor_cfg& cfg, const std::vector<float>& scale, co
                 bh = std::max(bh, hi + 2 - lo);
             }
             bw = (bw + 15) & ~15;
-            if (bw <= 256 && bh <= 256 && (size_t)bw * bh <= 64 * 1024) { g.rs_bw = bw; g.rs_bh = bh; }
+            // the TMA kernel reads the sources of four adjacent columns out of one realigned 8-byte span (pyramid.cu)
+            bool narrow = true;
+            for (int x4 = 0; x4 + 3 < (int)(((size_t)g.pitch + 3) & ~(size_t)3) && narrow; x4 += 4) {
+                int lo = 1 << 30, hi = -1;
+                for (int i = 0; i < 4; ++i) {
+                    const size_t e = (size_t)g.tabx_off + x4 + i;
+                    if (e >= tabs.size()) break;
+                    lo = std::min(lo, tabs[e].ofs); hi = std::max(hi, tabs[e].ofs);
+                }
+                if (hi - lo > 6) narrow = false;
+            }
+            if (narrow && bw <= 256 && bh <= 256 && (size_t)bw * bh <= 64 * 1024) { g.rs_bw = bw; g.rs_bh = bh; }
             else g.rs_bw = g.rs_bh = 0;       // scale factor too large for one TMA box: direct-global kernel
         } else {
             g.tabx_off = g.taby_off = 0;

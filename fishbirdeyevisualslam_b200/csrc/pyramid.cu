@@ -149,13 +149,27 @@ __global__ void __launch_bounds__(256) k_resize_tma(const Plan* __restrict__ pla
     const int x4 = (blockIdx.x * 32 + lane) * 4;
     const int pitch = g.pitch, ph = g.ph;
     const bool active = x4 < pitch;
-    int col[4] = {0, 0, 0, 0}, a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+    // The four columns of a thread read source bytes within a span of <= 8 (scale factors up to 1.8, reflected frame columns
+    // included): three aligned words of the staged row cover it.  base4 / sh locate the span, sel[i] picks the byte pair
+    // (S[col], S[col + 1]) of column i out of the realigned 8 bytes, w01[i] holds its two 11-bit weights as u16x2 for IDP.2A.
+    // (build_plan sends a level to the direct-global kernel when a group of four columns spans more than that.)
+    int base4 = 0, sh = 0;
+    unsigned sel[4] = {0, 0, 0, 0}, w01[4] = {0, 0, 0, 0};
     if (active) {
+        int col[4], a0[4], a1[4];
         const uint4* tx4 = reinterpret_cast<const uint4*>(tab + g.tabx_off + x4);      // 4 column entries = 32 bytes
         const uint4 ta = __ldg(tx4), tb = __ldg(tx4 + 1);
         col[0] = (int)ta.x - x0s; col[1] = (int)ta.z - x0s; col[2] = (int)tb.x - x0s; col[3] = (int)tb.z - x0s;
         a0[0] = (int)(short)(ta.y & 0xFFFFu); a0[1] = (int)(short)(ta.w & 0xFFFFu); a0[2] = (int)(short)(tb.y & 0xFFFFu); a0[3] = (int)(short)(tb.w & 0xFFFFu);
         a1[0] = (int)ta.y >> 16; a1[1] = (int)ta.w >> 16; a1[2] = (int)tb.y >> 16; a1[3] = (int)tb.w >> 16;
+        const int cmin = min(min(col[0], col[1]), min(col[2], col[3]));
+        base4 = cmin & ~3; sh = (cmin & 3) * 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int d = col[i] - cmin;
+            sel[i] = (unsigned)d | ((unsigned)(d + 1) << 4);
+            w01[i] = (unsigned)a0[i] | ((unsigned)a1[i] << 16);               // weights are in [0, 2048]
+        }
     }
     mbar_wait(&bar, 0);
     if (!active) return;
@@ -166,9 +180,12 @@ __global__ void __launch_bounds__(256) k_resize_tma(const Plan* __restrict__ pla
     int cur = -4;                 // source row (tile coordinates) whose interpolation sits in r_lo (r_hi holds cur + 1)
     unsigned r_lo[4], r_hi[4];
     auto hrow = [&](int sy, unsigned (&r)[4]) {
-        const uint8_t* S = rs_tile + sy * bw;
+        // 3 LDS.32 + 2 SHF realign the span; per column one PRMT (byte pair) + one IDP.2A (a0 * S0 + a1 * S1) + the >> 4
+        const uint32_t* W = reinterpret_cast<const uint32_t*>(rs_tile + sy * bw + base4);
+        const uint32_t w0 = W[0], w1 = W[1], w2 = W[2];
+        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) r[i] = (unsigned)((int)S[col[i]] * a0[i] + (int)S[col[i] + 1] * a1[i]) >> 4;
+        for (int i = 0; i < 4; ++i) r[i] = __dp2a_lo(w01[i], __byte_perm(lo, hi, sel[i]), 0u) >> 4;
     };
     for (; y < yend; ++y) {
         const ResizeTab t = ty[y];
@@ -212,7 +229,7 @@ int launch_pyramid(const Plan& hp, const Plan* dp, const Workspace& ws, const Re
         } else {
             dim3 rgrid((g.pitch + kRsTW - 1) / kRsTW, (g.ph + kRsTH - 1) / kRsTH, nimg);
             if (g.rs_bw > 0) {
-                const size_t smem = (size_t)g.rs_bw * g.rs_bh;
+                const size_t smem = (size_t)g.rs_bw * g.rs_bh + 16;     // + 16: the word loads of the last row's last span may run past the box
                 if (smem > 48 * 1024) FBE_CUDA(cudaFuncSetAttribute(k_resize_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
                 FBE_CUDA(launch_dep(k_resize_tma, rgrid, dim3(256), smem, st, dp, ws, d_tab, l, rs_maps.m[l]));
             } else {
