@@ -11,6 +11,7 @@
 //   C. descriptor: the warp stages the 37x37 patch of the BLURRED level into shared memory with aligned 32-bit loads
 //      (pattern radius 13 -> rotated reach <= 18), then lane = output byte, 16 rotated samples each, read from shared memory;
 //      cvRound(x*b + y*a), cvRound(x*a - y*b) as __float2int_rn of un-contracted fp32 products.
+#include <cuda_fp16.h>
 #include "fbe_internal.cuh"
 #include "orb_device.cuh"
 
@@ -28,7 +29,8 @@ constexpr int kPatchR = 18, kPatchRows = 2 * kPatchR + 1, kPatchWords = 12;     
 template <int kDescPerWarp>
 __global__ void __launch_bounds__(kDescWarps * 32, 8) k_describe(const Plan* __restrict__ plan, Workspace ws) {
     constexpr int kDescPerCta = kDescWarps * kDescPerWarp;
-    __shared__ float4 s_pat[256];                                       // [j][lane]: pair lane*8 + j as (x0, y0, x1, y1)
+    __shared__ uint2 s_pat[256];                                        // [j][lane]: pair lane*8 + j as (x0, y0, x1, y1) in fp16 (|coordinate| <= 13: exact):
+                                                                        // 8 bytes per lane = 2 shared-memory wavefronts per load instead of 4
     __shared__ uint32_t s_patch[kDescWarps][kPatchRows * kPatchWords];
     __shared__ uint32_t s_key[kDescPerCta];
     __shared__ int s_lvl[kDescPerCta];
@@ -48,7 +50,9 @@ __global__ void __launch_bounds__(kDescWarps * 32, 8) k_describe(const Plan* __r
     if (g0 >= total) return;
     {
         const int p = (tid & 31) * 8 + (tid >> 5);                       // s_pat[tid] = pair p
-        s_pat[tid] = make_float4((float)c_pattern[4 * p], (float)c_pattern[4 * p + 1], (float)c_pattern[4 * p + 2], (float)c_pattern[4 * p + 3]);
+        const __half2 h01 = __floats2half2_rn((float)c_pattern[4 * p], (float)c_pattern[4 * p + 1]);
+        const __half2 h23 = __floats2half2_rn((float)c_pattern[4 * p + 2], (float)c_pattern[4 * p + 3]);
+        s_pat[tid] = make_uint2(*reinterpret_cast<const unsigned*>(&h01), *reinterpret_cast<const unsigned*>(&h23));
     }
 
     // ---- A: IC_Angle on the unblurred level ---------------------------------------------------------------------
@@ -156,7 +160,9 @@ __global__ void __launch_bounds__(kDescWarps * 32, 8) k_describe(const Plan* __r
         unsigned val = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float4 p = s_pat[j * 32 + lane];
+            const uint2 ph = s_pat[j * 32 + lane];
+            const float2 p01 = __half22float2(*reinterpret_cast<const __half2*>(&ph.x)), p23 = __half22float2(*reinterpret_cast<const __half2*>(&ph.y));
+            const float4 p = make_float4(p01.x, p01.y, p23.x, p23.y);
             // cvRound of a value below 2^22 in magnitude: adding 1.5 * 2^23 rounds to the nearest integer, ties to even, exactly
             // like cvtss2si / F2I.RN, and leaves the integer in the low mantissa bits (FADD + IADD instead of the quarter-rate F2I)
             const int r0 = cv_round_small(__fadd_rn(__fmul_rn(p.x, bb), __fmul_rn(p.y, a)));
