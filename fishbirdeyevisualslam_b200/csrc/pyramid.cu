@@ -230,7 +230,7 @@ int launch_pyramid(const Plan& hp, const Plan* dp, const Workspace& ws, const Re
             dim3 rgrid((g.pitch + kRsTW - 1) / kRsTW, (g.ph + kRsTH - 1) / kRsTH, nimg);
             if (g.rs_bw > 0) {
                 const size_t smem = (size_t)g.rs_bw * g.rs_bh + 16;     // + 16: the word loads of the last row's last span may run past the box
-                if (smem > 48 * 1024) FBE_CUDA(cudaFuncSetAttribute(k_resize_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                if (smem > 48 * 1024) FBE_CUDA(cudaFuncSetAttribute(k_resize_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024 + 16));   // box <= 64 KB (build_plan) + the slack
                 FBE_CUDA(launch_dep(k_resize_tma, rgrid, dim3(256), smem, st, dp, ws, d_tab, l, rs_maps.m[l]));
             } else {
                 FBE_CUDA(launch_dep(k_resize, rgrid, dim3(256), 0, st, dp, ws, d_tab, l));
