@@ -6,12 +6,23 @@
 #include <cuda_fp16.h>
 #include <cstdio>
 
+// nvcc fuses the two HMNMX2 of a nested __hmin2 into ONE 3-input VHMNMX on sm_100a
+__device__ __forceinline__ unsigned hmin3(unsigned a, unsigned b, unsigned c) {
+    const __half2 r = __hmin2(__hmin2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b)), *reinterpret_cast<const __half2*>(&c));
+    return *reinterpret_cast<const unsigned*>(&r);
+}
+
 template <int OP>
 __global__ void k(unsigned* out, int iters, unsigned seed) {
     unsigned a[8], s[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { a[j] = seed * (2 * j + 3) + threadIdx.x; s[j] = j; }
     const unsigned c = seed | 0x01020304u;
+    const unsigned ch = (seed & 0x03FF03FFu) | 0x64006400u;                         // two positive normal fp16 values
+    if (OP >= 18) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a[j] = (a[j] & 0x03FF03FFu) | 0x64006400u; s[j] = 0x65FF65FFu - j; }
+    }
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -33,6 +44,10 @@ __global__ void k(unsigned* out, int iters, unsigned seed) {
             if (OP == 15) s[j] = __vmaxs2(s[j], a[j]) + c;                      // VIMNMX.S16x2 (2-input)
             if (OP == 16) { if (j & 1) { __half2 x = *reinterpret_cast<__half2*>(&s[j]), y = *reinterpret_cast<__half2*>(&a[j]); x = __hmax2(x, y); s[j] = *reinterpret_cast<unsigned*>(&x); } else s[j] = __vimin3_u16x2(s[j], a[j], c); }   // HMNMX2 + VIMNMX3 mix
             if (OP == 17) s[j] = __popc(s[j] ^ a[j]) + c;                            // POPC
+            if (OP == 18) s[j] = hmin3(s[j], a[j], ch);                               // VHMNMX (3-input half2 min, sm_100)
+            if (OP == 19) { if (j & 1) s[j] = hmin3(s[j], a[j], ch); else s[j] = __vimin3_s16x2(s[j], a[j], ch); }   // VHMNMX + VIMNMX3
+            if (OP == 20) { if (j & 1) s[j] = hmin3(s[j], a[j], ch); else s[j] = s[j] * c + a[j]; }                  // VHMNMX + IMAD
+            if (OP == 21) { if (j % 3 == 0) s[j] = hmin3(s[j], a[j], ch); else s[j] = __vimin3_s16x2(s[j], a[j], ch); }   // 1 VHMNMX : 2 VIMNMX3
         }
     }
     unsigned t = 0;
@@ -65,6 +80,7 @@ int main() {
     run<0>("IMAD", d, ghz); run<1>("IADD3", d, ghz); run<2>("LOP3", d, ghz); run<3>("PRMT", d, ghz); run<11>("SHF", d, ghz);
     run<4>("VIMNMX3.U16x2", d, ghz); run<10>("VIMNMX3.S16x2", d, ghz); run<5>("IDP4A", d, ghz); run<6>("IDP2A", d, ghz);
     run<12>("HMNMX2(+IADD)", d, ghz); run<13>("IMAD.HI", d, ghz); run<14>("FMNMX(+LOP)", d, ghz); run<15>("VIMNMX.S16x2(+IADD)", d, ghz); run<16>("HMNMX2+VIMNMX3 mix", d, ghz); run<17>("POPC(+LOP+IADD)", d, ghz);
+    run<18>("VHMNMX", d, ghz); run<19>("VHMNMX+VIMNMX3 mix", d, ghz); run<20>("VHMNMX+IMAD mix", d, ghz); run<21>("VHMNMX+2 VIMNMX3 mix", d, ghz);
     run<7>("IMAD+VIMNMX3 mix", d, ghz); run<8>("IDP4A+VIMNMX3 mix", d, ghz); run<9>("IDP4A+IMAD mix", d, ghz);
     return 0;
 }
