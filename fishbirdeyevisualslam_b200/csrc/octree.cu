@@ -128,8 +128,7 @@ __device__ __forceinline__ int root_of(uint32_t key, float hx, int nini) {
 }
 
 // assigns every key to the live node it belongs to: table[off(depth) + path] = node index for live nodes, -1 elsewhere
-__device__ void materialise_knode(const uint32_t* __restrict__ keys, uint32_t* knode, int nk, const OctNode* cur, int n, int nini,
-                                  float hx, int H, int D, int* table, int table_n) {
+__device__ void materialise_knode(uint32_t* knode, int nk, const OctNode* cur, int n, int nini, int D, int* table, int table_n) {
     const int tid = threadIdx.x;
     for (int i = tid; i < table_n; i += kOctThreads) table[i] = -1;
     __syncthreads();
@@ -138,22 +137,35 @@ __device__ void materialise_knode(const uint32_t* __restrict__ keys, uint32_t* k
         table[hist_offset(nini, pd >> kPdShift) + (pd & ((1 << kPdShift) - 1))] = i;
     }
     __syncthreads();
+    // the histogram pass parked every key's depth-D path in knode[k]; its path at depth d is that value >> 2 (D - d)
+    // (path = 4 * path + quadrant per level), so the walk down the geometry is not repeated
     for (int k = tid; k < nk; k += kOctThreads) {
-        const uint32_t key = keys[k];
+        const int leaf = (int)knode[k];
         int node = 0;
-        descend(key_x(key) - 16, key_y(key) - 16, root_of(key, hx, nini), hx, H, D, [&](int d, int path) {
-            const int t = table[hist_offset(nini, d) + path];
-            if (t >= 0) { node = t; return true; }
-            return false;
-        });
+        for (int d = 0; d <= D; ++d) {
+            const int t = table[hist_offset(nini, d) + (leaf >> (2 * (D - d)))];
+            if (t >= 0) { node = t; break; }
+        }
         knode[k] = (uint32_t)node;
     }
     __syncthreads();
 }
 
+// One axis of descend(): the depth-D path digits contributed by coordinate v inside [lo, hi) (bit `bit` of every base-4 digit)
+__device__ __forceinline__ int descend_axis(int v, int lo, int hi, int D, int bit) {
+    int path = 0;
+    for (int d = 0; d < D; ++d) {
+        const int m = lo + ((hi - lo + 1) >> 1);
+        int q = 0;
+        if (v < m) hi = m; else { lo = m; q = bit; }
+        path = 4 * path + q;
+    }
+    return path;
+}
+
 // The replay proper.  keys/knode: nk entries.  Returns the number of live nodes; `cur` points at the final array.
 // All pointers may be shared or global memory.
-__device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode, int nk, int nini, float hx, int H,
+__device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode, int nk, int nini, float hx, int W, int H,
                              int N, int cap, OctNode* nodesA, OctNode* nodesB, int* cnt4, int* cnt4b, int* newidx, int* splitf,
                              int* order, unsigned long long* sortbuf, BlockScan& bs, int* s_ctl, OctNode** out_nodes, int* hist, int D) {
     const int tid = threadIdx.x;
@@ -167,10 +179,29 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
         for (int i = tid; i < hist_n; i += kOctThreads) hist[i] = 0;
         __syncthreads();
         int* hD = hist + hist_offset(nini, D);
+        // The x and y decisions of descend() are independent, so the depth-D path of (x, y) is xtab[x] + ytab[y]: root and x digits of
+        // every column, y digits of every row, tabulated once per CTA (W + H one-axis walks instead of one two-axis walk per key).
+        // The tables borrow cnt4b, which the replay does not touch before its first round; levels whose tables do not fit walk per key.
+        uint16_t* xtab = reinterpret_cast<uint16_t*>(cnt4b);
+        uint16_t* ytab = xtab + W;
+        const bool tabs = W > 0 && 2 * (W + H) <= 16 * cap && (nini << (2 * D)) <= 65536;
+        if (tabs) {
+            for (int i = tid; i < W + H; i += kOctThreads) {
+                if (i < W) {
+                    const int r = min(max((int)__fdiv_rn((float)i, hx), 0), nini - 1);            // root_of()
+                    xtab[i] = (uint16_t)((r << (2 * D)) + descend_axis(i, (int)__fmul_rn(hx, (float)r), (int)__fmul_rn(hx, (float)(r + 1)), D, 1));
+                } else {
+                    ytab[i - W] = (uint16_t)descend_axis(i - W, 0, H, D, 2);
+                }
+            }
+            __syncthreads();
+        }
         for (int k = tid; k < nk; k += kOctThreads) {
             const uint32_t key = keys[k];
             int leaf = 0;
-            descend(key_x(key) - 16, key_y(key) - 16, root_of(key, hx, nini), hx, H, D, [&](int d, int path) { leaf = path; return false; });
+            if (tabs) leaf = (int)xtab[key_x(key) - 16] + (int)ytab[key_y(key) - 16];
+            else descend(key_x(key) - 16, key_y(key) - 16, root_of(key, hx, nini), hx, H, D, [&](int d, int path) { leaf = path; return false; });
+            knode[k] = (uint32_t)leaf;             // parked for materialise_knode()
             agg_inc(hD, leaf);
         }
         __syncthreads();
@@ -242,7 +273,7 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
             __syncthreads();
             if (s_ctl[3]) {
                 hist_mode = false;               // leave histogram mode: keys get their nodes, then per-key counting
-                materialise_knode(keys, knode, nk, cur, n, nini, hx, H, D, hist, hist_n);
+                materialise_knode(knode, nk, cur, n, nini, D, hist, hist_n);
                 for (int i = tid; i < 4 * n; i += kOctThreads) cnt4[i] = 0;
                 __syncthreads();
                 for_keys(keys, knode, nk, [&](int, uint32_t key, uint32_t node) {
@@ -419,7 +450,7 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
         if (n >= N || n == prev) break;
         if (!refine && n + 3 * nexp > N) refine = true;
     }
-    if (hist_mode && n > 0) materialise_knode(keys, knode, nk, cur, n, nini, hx, H, D, hist, hist_n);
+    if (hist_mode && n > 0) materialise_knode(knode, nk, cur, n, nini, D, hist, hist_n);
     *out_nodes = cur;
     return n;
 }
@@ -498,9 +529,8 @@ __global__ void __launch_bounds__(kOctThreads, 4) k_octree(const Plan* __restric
     const int D = oct_hist_depth(g.nini, g.nfeat);
 
     const int W = g.w - 2 * kEdge + 6, H = g.h - 2 * kEdge + 6;   // maxBorder - minBorder
-    (void)W;
     OctNode* fin = nullptr;
-    int n = octree_replay(keys, knode, nk, g.nini, g.hx, H, g.nfeat, cap, nodesA, nodesB, cnt4, cnt4b, newidx, splitf, order,
+    int n = octree_replay(keys, knode, nk, g.nini, g.hx, W, H, g.nfeat, cap, nodesA, nodesB, cnt4, cnt4b, newidx, splitf, order,
                           sortbuf, bs, s_ctl, &fin, hist, D);
     int* level_n = ws.level_n + (size_t)b * FBE_MAX_LEVELS + l;
     if (n < 0) {
@@ -541,7 +571,7 @@ __global__ void __launch_bounds__(kOctThreads) k_octree_debug(const uint32_t* ke
     int* order = splitf + cap;
     int* hist = order + cap;
     OctNode* fin = nullptr;
-    int n = octree_replay(keys, knode, nk, nini, hx, H, N, cap, nodesA, nodesB, cnt4, cnt4b, newidx, splitf, order, sortbuf, bs, s_ctl, &fin,
+    int n = octree_replay(keys, knode, nk, nini, hx, /*W: unknown here, per-key walk*/ 0, H, N, cap, nodesA, nodesB, cnt4, cnt4b, newidx, splitf, order, sortbuf, bs, s_ctl, &fin,
                           hist, oct_hist_depth(nini, N));
     if (n < 0) { if (tid == 0) *n_out = -1; return; }
     unsigned* best = reinterpret_cast<unsigned*>(cnt4);
