@@ -76,6 +76,20 @@ __device__ __forceinline__ void for_keys(const uint32_t* __restrict__ keys, cons
     for (; k < nk; k += kOctThreads) f(k, keys[k], knode[k]);
 }
 
+// Walk of one array with the loads of 8 iterations in flight (same reason as for_keys)
+template <class F>
+__device__ __forceinline__ void for_each8(const uint32_t* arr, int nk, F&& f) {
+    int k = threadIdx.x;
+    for (; k + 7 * kOctThreads < nk; k += 8 * kOctThreads) {
+        uint32_t a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = arr[k + u * kOctThreads];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f(k + u * kOctThreads, a[u]);
+    }
+    for (; k < nk; k += kOctThreads) f(k, arr[k]);
+}
+
 // counter[idx] += 1 for every calling lane, with the lanes of a warp that hit the same counter folded into ONE shared-memory
 // atomic (MATCH.ANY): the first rounds have a handful of nodes, so 16k keys would otherwise serialise on <= 8 addresses.
 __device__ __forceinline__ void agg_inc(int* counter, int idx) {
@@ -139,15 +153,14 @@ __device__ void materialise_knode(uint32_t* knode, int nk, const OctNode* cur, i
     __syncthreads();
     // the histogram pass parked every key's depth-D path in knode[k]; its path at depth d is that value >> 2 (D - d)
     // (path = 4 * path + quadrant per level), so the walk down the geometry is not repeated
-    for (int k = tid; k < nk; k += kOctThreads) {
-        const int leaf = (int)knode[k];
+    for_each8(knode, nk, [&](int k, uint32_t leaf) {
         int node = 0;
         for (int d = 0; d <= D; ++d) {
-            const int t = table[hist_offset(nini, d) + (leaf >> (2 * (D - d)))];
+            const int t = table[hist_offset(nini, d) + ((int)leaf >> (2 * (D - d)))];
             if (t >= 0) { node = t; break; }
         }
         knode[k] = (uint32_t)node;
-    }
+    });
     __syncthreads();
 }
 
@@ -196,13 +209,20 @@ __device__ int octree_replay(const uint32_t* __restrict__ keys, uint32_t* knode,
             }
             __syncthreads();
         }
-        for (int k = tid; k < nk; k += kOctThreads) {
-            const uint32_t key = keys[k];
-            int leaf = 0;
-            if (tabs) leaf = (int)xtab[key_x(key) - 16] + (int)ytab[key_y(key) - 16];
-            else descend(key_x(key) - 16, key_y(key) - 16, root_of(key, hx, nini), hx, H, D, [&](int d, int path) { leaf = path; return false; });
-            knode[k] = (uint32_t)leaf;             // parked for materialise_knode()
-            agg_inc(hD, leaf);
+        if (tabs) {
+            for_each8(keys, nk, [&](int k, uint32_t key) {
+                const int leaf = (int)xtab[key_x(key) - 16] + (int)ytab[key_y(key) - 16];
+                knode[k] = (uint32_t)leaf;         // parked for materialise_knode()
+                agg_inc(hD, leaf);
+            });
+        } else {
+            for (int k = tid; k < nk; k += kOctThreads) {
+                const uint32_t key = keys[k];
+                int leaf = 0;
+                descend(key_x(key) - 16, key_y(key) - 16, root_of(key, hx, nini), hx, H, D, [&](int d, int path) { leaf = path; return false; });
+                knode[k] = (uint32_t)leaf;
+                agg_inc(hD, leaf);
+            }
         }
         __syncthreads();
         for (int d = D - 1; d >= 0; --d) {        // coarser depths = sums of their four children
