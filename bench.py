@@ -40,13 +40,13 @@ BYTES_PER_PAIR = 5_742_040
 # pixels of all pyramid levels (what the FAST kernel reads once): front 2 853 088, bird 456 460
 PYR_PIXELS_FRONT, PYR_PIXELS_BIRD = 2_853_088, 456_460
 # dram__bytes_read.sum + dram__bytes_write.sum of one front k_fast_cells launch over 128 images (ncu --set full,
-# the k_fast_cells (406, 128, 1) row of profiles/r2_24_stage_ncu.md): 384.71 MB + 35.57 MB
-FAST_DRAM_BYTES_PER_FRONT_IMAGE = int((384.706304e6 + 35.573760e6) / 128)
+# the k_fast_cells (406, 128, 1) row of profiles/r2_29_stage_ncu.md): 384.71 MB + 36.98 MB
+FAST_DRAM_BYTES_PER_FRONT_IMAGE = int((384.710400e6 + 36.979200e6) / 128)
 # warp-instructions executed by the same launch (smsp__inst_executed.sum of the same capture)
-FAST_WARP_INST_PER_FRONT_IMAGE = 1_024_480_464 / 128
-FAST_PROFILE = "profiles/r2_24_stage_ncu.md (source-level detail: profiles/r2_01_fast_blur_ncu.md)"
-# warp-instructions of ALL kernels of one 128-pair step (sum of smsp__inst_executed.sum over profiles/r2_24_stage_ncu.md)
-STEP_WARP_INST_PER_PAIR = 2_343.6e6 / 128
+FAST_WARP_INST_PER_FRONT_IMAGE = 1_024_480_494 / 128
+FAST_PROFILE = "profiles/r2_29_stage_ncu.md (source-level detail: profiles/r2_01_fast_blur_ncu.md)"
+# warp-instructions of ALL kernels of one 128-pair step (sum of smsp__inst_executed.sum over profiles/r2_29_stage_ncu.md)
+STEP_WARP_INST_PER_PAIR = 2_250.3e6 / 128
 METRIC = "front+bird frame-pairs/sec ORB extract+match at 1/2/4/8 B200 vs host CPU ref"
 WORKLOAD = ("C4: offline job of 4096 synthetic front(1280x720 @2000)+bird(384x384 @1000) frame pairs per GPU, sharded by frame; "
             "extract + grid + frame-to-frame match (pair shape of C2)")
@@ -619,7 +619,7 @@ def run_ours(args):
                              "whole_step": {"bytes_per_pair": BYTES_PER_PAIR, "achieved_gbs": value / world * BYTES_PER_PAIR / 1e9,
                                             "frac": value / world * BYTES_PER_PAIR / 1e9 / peak,
                                             "issue_frac": value / world * STEP_WARP_INST_PER_PAIR / issue_peak,
-                                            "issue_note": "warp-instructions of every kernel of a step (profiles/r2_24_stage_ncu.md) x pairs/s over "
+                                            "issue_note": "warp-instructions of every kernel of a step (profiles/r2_29_stage_ncu.md) x pairs/s over "
                                                           "the warp-instruction issue peak: the step as a whole is instruction-bound"}},
                 "stage_ms": {"front_fast_cells": fast_ms,
                              "note": "CUDA events around the front FAST launch on its own (highest-priority) stream: agrees with the ncu launch "
