@@ -91,7 +91,9 @@ FBE_API int fbe_plan_query(const fbe_extractor_cfg* cfg, int32_t rows, int32_t c
 
 /* ORBextractor::operator()(image, mask, keypoints, descriptors), src/ORBextractor.cc:1043-1105.
  * Host buffers.  img: rows x cols 8-bit, `step` bytes per row.  kps/desc: `capacity` entries / x32 bytes.
- * Empty image (img NULL or rows/cols <= 0) -> *n_out = 0 and outputs untouched, like the reference's early return. */
+ * Empty image (img NULL or rows/cols <= 0) -> *n_out = 0 and outputs untouched, like the reference's early return.
+ * Limits (FBE_E_UNSUPPORTED, never a silent difference): rows, cols <= 4095 (candidate coordinates are packed in 12 bits each);
+ * every pyramid level must hold at least one 30-px FAST cell (the reference divides by zero there). */
 FBE_API int fbe_extract(fbe_extractor* e, const uint8_t* img, int32_t rows, int32_t cols, size_t step, fbe_keypoint* kps,
                 uint8_t* desc, int32_t capacity, int32_t* n_out);
 /* nimg images of one size; kps is [nimg][capacity], desc [nimg][capacity][32], n_out [nimg]. */
